@@ -1,0 +1,1181 @@
+"""CPU oracle for the LESGO per-timestep pseudo-spectral core.  TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED: the reference (lesgo-jhu/lesgo, Fortran + FFTW3 + MPI) cannot be
+built or run in this container (no Fortran compiler, no FFTW3, no MPI) and ships no
+golden vectors / known-answer tests for this path (its test strategy is a
+compile-and-run smoke matrix, `test-lesgo:72-73,125`).  This file is therefore a
+*restatement* of the reference algorithm, line-cited below, validated by the analytic
+known-answer tests in `tests/test_oracle_*.py` (single Fourier modes, discrete Poisson
+eigenfunctions, scipy banded solves, multi-slab == single-slab).  Third-party
+arithmetic on the path is FFTW3 (unvendored, unpinned: `CMakeLists.txt:63-66`,
+3.3.6-pl2 / 3.3.8 named at `:112-154`), whose published definition (unnormalised DFT,
+forward sign -1, r2c keeps kx = 0..nx/2 of the contiguous dimension, c2r ignores the
+imaginary parts of the kx=0 / kx=nx/2 columns after the y pass) is restated with
+`scipy.fft.rfft2 / irfft2(norm="forward")`.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl
+reference` leg may import this module.  The product path (`lesgo_b200/`) never does.
+
+Layout convention.  A Fortran array `f(ld, ny, lbz:nz)` with `lbz = 0` (the MPI build,
+`param.f90:68`) is held as a C-ordered numpy array `f[k, j, i]` of shape
+`(nz+1, ny, ld)` -- byte-identical memory.  Fortran's 1-based `(jx, jy, jz)` is
+`[jz, jy-1, jx-1]`.  Arrays the reference declares `1:nz` (`dpdx`, `S11`, ...) are also
+allocated `0:nz` here with plane 0 unused, so the z index is always the Fortran one.
+Complex numbers are interleaved along x: `(re, im) = f[k, j, 2*m : 2*m+2]`.
+
+Multi-rank runs: every routine takes a `comm` with MPI-like blocking `send/recv/
+sendrecv/allreduce`.  `LocalComm` (nproc = 1), `ThreadComm` (one Python thread per
+rank, in-process queues; used by the tests and the golden-vector generator) and
+`lesgo_b200.slab.TorchComm` (torch.distributed, gloo on CPU) all implement it.
+"""
+from __future__ import annotations
+
+import math
+import queue
+import threading
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+try:  # scipy's pocketfft has a `workers=` argument (multi-threaded batched FFTs)
+    import scipy.fft as _fft
+    _HAVE_SCIPY = True
+except Exception:  # pragma: no cover
+    import numpy.fft as _fft
+    _HAVE_SCIPY = False
+
+BOGUS = -1234567890.0  # param.f90:93
+FFT_WORKERS = 1        # bench.py raises this for the multi-threaded CPU baseline
+
+
+# ----------------------------------------------------------------------------------
+# Parameters (param.f90, input_util.f90:197-235)
+# ----------------------------------------------------------------------------------
+@dataclass
+class Params:
+    nx: int
+    ny: int
+    Nz: int                      # "Nz" of lesgo.conf, NOT the level count (Appendix A.1)
+    nproc: int = 1
+    coord: int = 0
+    L_x: float = 2.0 * math.pi
+    L_y: float = 2.0 * math.pi
+    L_z: float = 2.0
+    z_i: float = 1.0
+    lbc_mom: int = 1
+    ubc_mom: int = 1
+    sgs: bool = False
+    sgs_model: int = 1
+    molec: bool = True
+    nu_molec: float = 1e-3
+    u_star: float = 1.0
+    Co: float = 0.16
+    wall_damp_exp: float = 2.0
+    vonk: float = 0.4
+    zo: float = 1e-4
+    ifilter: int = 1
+    ubot: float = 0.0
+    utop: float = 0.0
+    dt: float = 2e-4
+    tadv1: float = 1.5           # input_util.f90:403-408 (fixed dt)
+    tadv2: float = -0.5
+    use_mean_p_force: bool = False
+    mean_p_force_x: float = 0.0
+    mean_p_force_y: float = 0.0
+    # derived
+    nz: int = field(init=False)
+    nz_tot: int = field(init=False)
+    lh: int = field(init=False)
+    ld: int = field(init=False)
+    nx2: int = field(init=False)
+    ny2: int = field(init=False)
+    lh_big: int = field(init=False)
+    ld_big: int = field(init=False)
+    dx: float = field(init=False)
+    dy: float = field(init=False)
+    dz: float = field(init=False)
+
+    def __post_init__(self):
+        # input_util.f90:197-235
+        self.nz = self.Nz // self.nproc + 1
+        self.nz_tot = (self.nz - 1) * self.nproc + 1
+        self.nx2 = 3 * self.nx // 2
+        self.ny2 = 3 * self.ny // 2
+        self.lh = self.nx // 2 + 1
+        self.ld = 2 * self.lh
+        self.lh_big = self.nx2 // 2 + 1
+        self.ld_big = 2 * self.lh_big
+        self.dx = self.L_x / self.nx
+        self.dy = self.L_y / self.ny
+        self.dz = self.L_z / (self.nz_tot - 1)
+
+    @property
+    def nu(self) -> float:       # sgs_param.f90:188-192
+        return self.nu_molec / (self.u_star * self.z_i) if self.molec else 0.0
+
+    @property
+    def delta(self) -> float:    # sgs_param.f90:187, filter_size = 1
+        return (self.dx * self.dy * self.dz) ** (1.0 / 3.0)
+
+    def for_rank(self, coord: int) -> "Params":
+        d = {k: getattr(self, k) for k in self.__dataclass_fields__
+             if self.__dataclass_fields__[k].init}
+        d["coord"] = coord
+        return Params(**d)
+
+
+# ----------------------------------------------------------------------------------
+# Communication (mpi_defs.f90:77-87: 1-D non-periodic chain, up/down = PROC_NULL at ends)
+# ----------------------------------------------------------------------------------
+class LocalComm:
+    """nproc = 1: every neighbour is MPI_PROC_NULL, so sends vanish and receives leave
+    the buffer untouched (MPI semantics the reference relies on, mpi_defs.f90:79-83)."""
+    nproc = 1
+    coord = 0
+
+    def send(self, buf, dest, tag):
+        pass
+
+    def recv(self, buf, src, tag):
+        pass
+
+    def sendrecv(self, sendbuf, dest, recvbuf, src, tag):
+        pass
+
+    def allreduce(self, value, op):
+        return value
+
+
+class ThreadComm:
+    """One instance per rank; ranks run in threads of one process (see `run_ranks`)."""
+
+    def __init__(self, coord, nproc, boxes):
+        self.coord, self.nproc, self._boxes = coord, nproc, boxes
+
+    def _q(self, src, dst, tag):
+        key = (src, dst, tag)
+        with self._boxes["lock"]:
+            if key not in self._boxes:
+                self._boxes[key] = queue.Queue()
+            return self._boxes[key]
+
+    def send(self, buf, dest, tag):
+        if 0 <= dest < self.nproc:
+            self._q(self.coord, dest, tag).put(np.array(buf, copy=True))
+
+    def recv(self, buf, src, tag):
+        if 0 <= src < self.nproc:
+            buf[...] = self._q(src, self.coord, tag).get(timeout=600)
+
+    def sendrecv(self, sendbuf, dest, recvbuf, src, tag):
+        self.send(sendbuf, dest, tag)
+        self.recv(recvbuf, src, tag)
+
+    def allreduce(self, value, op):
+        # gather to all through the mailboxes (tiny, scalar)
+        for r in range(self.nproc):
+            if r != self.coord:
+                self._q(self.coord, r, ("ar", op)).put(value)
+        vals = [value] + [self._q(r, self.coord, ("ar", op)).get(timeout=600)
+                          for r in range(self.nproc) if r != self.coord]
+        return {"min": min, "max": max, "sum": sum}[op](vals)
+
+
+def run_ranks(nproc, fn):
+    """Run `fn(coord, comm)` for every rank concurrently; returns the list of results."""
+    if nproc == 1:
+        return [fn(0, LocalComm())]
+    boxes = {"lock": threading.Lock()}
+    out, err = [None] * nproc, [None] * nproc
+
+    def work(c):
+        try:
+            out[c] = fn(c, ThreadComm(c, nproc, boxes))
+        except BaseException as e:  # noqa
+            err[c] = e
+
+    ts = [threading.Thread(target=work, args=(c,)) for c in range(nproc)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+def mpi_sync_real_array(var, p: Params, comm, down=True, up=True):
+    """mpi_defs.f90:167-264.  SYNC_DOWN: k=1 of coord+1 -> k=nz of coord (:245-252);
+    SYNC_UP: k=nz-1 of coord -> k=0 of coord+1 (:255-262)."""
+    nz = p.nz
+    if down:
+        comm.sendrecv(var[1], comm.coord - 1, var[nz], comm.coord + 1, 1)
+    if up:
+        comm.sendrecv(var[nz - 1], comm.coord + 1, var[0], comm.coord - 1, 2)
+
+
+# ----------------------------------------------------------------------------------
+# FFTW3 restatement + fft.f90
+# ----------------------------------------------------------------------------------
+def _kw():
+    return {"workers": FFT_WORKERS} if _HAVE_SCIPY else {}
+
+
+def r2c(a, n_fast):
+    """dfftw_execute_dft_r2c on `(…, n_slow, 2*(n_fast/2+1))` real planes; returns the
+    interleaved half spectrum in the same shape.  Unnormalised, forward sign -1."""
+    c = _fft.rfft2(a[..., :n_fast], axes=(-2, -1), **_kw())
+    out = np.empty(a.shape[:-1] + (n_fast // 2 + 1,), np.complex128)
+    out[...] = c
+    return out.view(np.float64)
+
+
+def c2r(a, n_fast):
+    """dfftw_execute_dft_c2r (unnormalised).  The two pad reals per row, which FFTW
+    leaves unspecified, are returned as 0."""
+    c = np.ascontiguousarray(a).view(np.complex128)
+    n_slow = a.shape[-2]
+    r = _fft.irfft2(c, s=(n_slow, n_fast), axes=(-2, -1), norm="forward", **_kw())
+    out = np.zeros(a.shape, np.float64)
+    out[..., :n_fast] = r
+    return out
+
+
+class Spectral:
+    """fft.f90: wavenumbers (init_wavenumber :130-160), padd (:43-71), unpadd (:74-99)."""
+
+    def __init__(self, p: Params):
+        self.p = p
+        nx, ny, lh = p.nx, p.ny, p.lh
+        kx = np.zeros((ny, lh))
+        ky = np.zeros((ny, lh))
+        kx[:, : lh - 1] = np.arange(lh - 1, dtype=np.float64)[None, :]
+        jy = np.arange(1, ny + 1)
+        ky[:, :] = (np.mod(jy - 1 + ny // 2, ny) - ny // 2).astype(np.float64)[:, None]
+        kx[:, lh - 1] = 0.0
+        ky[:, lh - 1] = 0.0
+        kx[ny // 2, :] = 0.0
+        ky[ny // 2, :] = 0.0
+        self.kx = 2.0 * math.pi / p.L_x * kx
+        self.ky = 2.0 * math.pi / p.L_y * ky
+        self.k2 = self.kx * self.kx + self.ky * self.ky
+
+    def forw(self, a):
+        return r2c(a, self.p.nx)
+
+    def back(self, a):
+        return c2r(a, self.p.nx)
+
+    def forw_big(self, a):
+        return r2c(a, self.p.nx2)
+
+    def back_big(self, a):
+        return c2r(a, self.p.nx2)
+
+    def zero_oddballs(self, a):
+        """`f(ld-1:ld,:) = 0; f(:,ny/2+1) = 0` (derivatives.f90:194-195)."""
+        a[..., self.p.ld - 2:] = 0.0
+        a[..., self.p.ny // 2, :] = 0.0
+        return a
+
+    def muli(self, a, k):
+        """emul_complex.f90:154-210: (re, im) * i*k = (-im*k, re*k)."""
+        out = np.empty_like(a)
+        out[..., 0::2] = -a[..., 1::2] * k
+        out[..., 1::2] = a[..., 0::2] * k
+        return out
+
+    def mulr(self, a, g):
+        """emul_complex.f90:213-262."""
+        out = np.empty_like(a)
+        out[..., 0::2] = a[..., 0::2] * g
+        out[..., 1::2] = a[..., 1::2] * g
+        return out
+
+    def padd(self, u):
+        p = self.p
+        nyh = p.ny // 2
+        big = np.zeros(u.shape[:-2] + (p.ny2, p.ld_big))
+        big[..., :nyh, : p.nx] = u[..., :nyh, : p.nx]
+        # j_s = ny/2+2 .. ny  ->  j_big_s = ny2-ny/2+2 .. ny2   (1-based)
+        big[..., p.ny2 - nyh + 1:, : p.nx] = u[..., nyh + 1:, : p.nx]
+        return big
+
+    def unpadd(self, cc_big):
+        p = self.p
+        nyh = p.ny // 2
+        cc = np.zeros(cc_big.shape[:-2] + (p.ny, p.ld))
+        cc[..., :nyh, : p.nx] = cc_big[..., :nyh, : p.nx]
+        cc[..., nyh + 1:, : p.nx] = cc_big[..., p.ny2 - nyh + 1:, : p.nx]
+        # oddballs cc(ld-1:ld,:) and cc(:,ny/2+1) stay 0 (fft.f90:91-92)
+        return cc
+
+
+# ----------------------------------------------------------------------------------
+# derivatives.f90
+# ----------------------------------------------------------------------------------
+def ddx(f, sp: Spectral):
+    """derivatives.f90:37-76, all planes lbz:nz."""
+    p = sp.p
+    h = sp.zero_oddballs(sp.forw((1.0 / (p.nx * p.ny)) * f))
+    return sp.back(sp.muli(h, sp.kx))
+
+
+def ddy(f, sp: Spectral):
+    """derivatives.f90:79-118."""
+    p = sp.p
+    h = sp.zero_oddballs(sp.forw((1.0 / (p.nx * p.ny)) * f))
+    return sp.back(sp.muli(h, sp.ky))
+
+
+def ddxy(f, sp: Spectral):
+    """derivatives.f90:121-163."""
+    p = sp.p
+    h = sp.zero_oddballs(sp.forw((1.0 / (p.nx * p.ny)) * f))
+    return sp.back(sp.muli(h, sp.kx)), sp.back(sp.muli(h, sp.ky))
+
+
+def filt_da(f, sp: Spectral):
+    """derivatives.f90:166-211.  Returns (f_filtered, dfdx, dfdy); the reference
+    overwrites f in place (intent(inout))."""
+    p = sp.p
+    h = sp.zero_oddballs(sp.forw((1.0 / (p.nx * p.ny)) * f))
+    return sp.back(h), sp.back(sp.muli(h, sp.kx)), sp.back(sp.muli(h, sp.ky))
+
+
+def ddz_uv(f, p: Params, dfdz=None):
+    """derivatives.f90:214-264: dfdz(k) = (f(k)-f(k-1))/dz, k = lbz+1..nz over 1:nx;
+    dfdz(0)=BOGUS; plane 1 on coord 0 and plane nz on the top rank BOGUS (SAFETYMODE)."""
+    if dfdz is None:
+        dfdz = np.zeros_like(f)
+    c = 1.0 / p.dz
+    dfdz[0] = BOGUS
+    dfdz[1:, :, : p.nx] = c * (f[1:, :, : p.nx] - f[:-1, :, : p.nx])
+    if p.coord == 0:
+        dfdz[1] = BOGUS
+    if p.coord == p.nproc - 1:
+        dfdz[p.nz] = BOGUS
+    return dfdz
+
+
+def ddz_w(f, p: Params, dfdz=None):
+    """derivatives.f90:267-311: dfdz(k) = (f(k+1)-f(k))/dz, k = lbz..nz-1."""
+    if dfdz is None:
+        dfdz = np.zeros_like(f)
+    c = 1.0 / p.dz
+    dfdz[:-1, :, : p.nx] = c * (f[1:, :, : p.nx] - f[:-1, :, : p.nx])
+    if p.coord == 0:
+        dfdz[0] = BOGUS
+    dfdz[p.nz] = BOGUS
+    return dfdz
+
+
+# ----------------------------------------------------------------------------------
+# convec.f90
+# ----------------------------------------------------------------------------------
+def convec(s, sp: Spectral):
+    """convec.f90:21-334.  `s` holds u,v,w,dudy,dudz,dvdx,dvdz,dwdx,dwdy (0:nz).
+    Returns RHSx, RHSy, RHSz (0:nz) with the reference's BOGUS planes."""
+    p = sp.p
+    nz, nproc, coord = p.nz, p.nproc, p.coord
+    jzLo = 2 if p.sgs else 1          # :47-53
+    jzHi = nz - 1
+    const = 1.0 / (p.nx * p.ny)
+
+    # :73-93  u,v,w -> 3/2 grid, planes lbz:nz
+    def to_big(a):
+        return sp.back_big(sp.padd(sp.forw(const * a)))
+
+    u_big, v_big, w_big = to_big(s.u), to_big(s.v), to_big(s.w)
+
+    # :97-168 vorticity, planes 1:nz
+    vx = np.zeros_like(s.u)
+    vy = np.zeros_like(s.u)
+    vz = np.zeros_like(s.u)
+    for jz in range(1, nz + 1):
+        special_bot = (coord == 0 and jz == 1)
+        special_top = (coord == nproc - 1 and jz == nz)
+        if special_bot:
+            if p.lbc_mom == 0:
+                vx[1] = 0.0
+                vy[1] = 0.0
+            else:
+                vx[1] = const * (0.5 * (s.dwdy[1] + s.dwdy[2]) - s.dvdz[1])
+                vy[1] = const * (s.dudz[1] - 0.5 * (s.dwdx[1] + s.dwdx[2]))
+        if special_top:
+            if p.ubc_mom == 0:
+                vx[nz] = 0.0
+                vy[nz] = 0.0
+            else:
+                vx[nz] = const * (0.5 * (s.dwdy[nz - 1] + s.dwdy[nz]) - s.dvdz[nz - 1])
+                vy[nz] = const * (s.dudz[nz - 1] - 0.5 * (s.dwdx[nz - 1] + s.dwdx[nz]))
+        # :145-151 the "very kludgy" overwrite
+        if not special_bot and not (p.ubc_mom > 0 and special_top):
+            vx[jz] = const * (s.dwdy[jz] - s.dvdz[jz])
+            vy[jz] = const * (s.dudz[jz] - s.dwdx[jz])
+        vz[jz] = const * (s.dvdx[jz] - s.dudy[jz])
+    vort1_big = np.zeros_like(u_big)
+    vort2_big = np.zeros_like(u_big)
+    vort3_big = np.zeros_like(u_big)
+    vort1_big[1:] = sp.back_big(sp.padd(sp.forw(vx[1:])))
+    vort2_big[1:] = sp.back_big(sp.padd(sp.forw(vy[1:])))
+    vort3_big[1:] = sp.back_big(sp.padd(sp.forw(vz[1:])))
+
+    const = 1.0 / (p.nx2 * p.ny2)     # :172
+    cc = np.zeros_like(u_big)
+
+    def to_small(cc_planes):
+        return sp.back(sp.unpadd(sp.forw_big(cc_planes)))
+
+    RHSx = np.full_like(s.u, BOGUS)
+    RHSy = np.full_like(s.u, BOGUS)
+    RHSz = np.full_like(s.u, BOGUS)
+
+    # ---- RHSx :174-213
+    if coord == 0:
+        cc[1] = const * (v_big[1] * (-vort3_big[1]) + 0.5 * w_big[2] * vort2_big[jzLo])
+        jz_min = 2
+    else:
+        jz_min = 1
+    if coord == nproc - 1:
+        cc[nz - 1] = const * (v_big[nz - 1] * (-vort3_big[nz - 1])
+                              + 0.5 * w_big[nz - 1] * vort2_big[jzHi])
+        jz_max = nz - 2
+    else:
+        jz_max = nz - 1
+    for jz in range(jz_min, jz_max + 1):
+        cc[jz] = const * (v_big[jz] * (-vort3_big[jz])
+                          + 0.5 * (w_big[jz + 1] * vort2_big[jz + 1]
+                                   + w_big[jz] * vort2_big[jz]))
+    RHSx[1:nz] = to_small(cc[1:nz])
+
+    # ---- RHSy :215-256
+    if coord == 0:
+        cc[1] = const * (u_big[1] * vort3_big[1] + 0.5 * w_big[2] * (-vort1_big[jzLo]))
+        jz_min = 2
+    else:
+        jz_min = 1
+    if coord == nproc - 1:
+        cc[nz - 1] = const * (u_big[nz - 1] * vort3_big[nz - 1]
+                              + 0.5 * w_big[nz - 1] * (-vort1_big[jzHi]))
+        jz_max = nz - 2
+    else:
+        jz_max = nz - 1
+    for jz in range(jz_min, jz_max + 1):
+        cc[jz] = const * (u_big[jz] * vort3_big[jz]
+                          + 0.5 * (w_big[jz + 1] * (-vort1_big[jz + 1])
+                                   + w_big[jz] * (-vort1_big[jz])))
+    RHSy[1:nz] = to_small(cc[1:nz])
+
+    # ---- RHSz :258-317
+    if coord == 0:
+        cc[1] = 0.0
+        jz_min = 2
+    else:
+        jz_min = 1
+    if coord == nproc - 1:
+        cc[nz] = 0.0
+    jz_max = nz - 1
+    for jz in range(jz_min, jz_max + 1):
+        cc[jz] = const * 0.5 * ((u_big[jz] + u_big[jz - 1]) * (-vort2_big[jz])
+                                + (v_big[jz] + v_big[jz - 1]) * vort1_big[jz])
+    RHSz[1:nz + 1] = to_small(cc[1:nz + 1])
+
+    # :319-332
+    RHSx[0] = BOGUS
+    RHSy[0] = BOGUS
+    RHSz[0] = BOGUS
+    RHSx[nz] = BOGUS
+    RHSy[nz] = BOGUS
+    if coord < nproc - 1:
+        RHSz[nz] = BOGUS
+    return RHSx, RHSy, RHSz
+
+
+# ----------------------------------------------------------------------------------
+# tridag_array.f90 (MPI version :22-162; with nproc = 1 it equals the serial :166-246)
+# ----------------------------------------------------------------------------------
+def tridag_array(a, b, c, r, u, p: Params, comm):
+    """a,b,c: (nz+2, ny, lh) with Fortran row j at index j (index 0 unused);
+    r,u: (nz+2, ny, ld) likewise.  `u` is modified in place (rows 1..n).  Same
+    elimination order and same skipped modes as the reference; the per-jy chunking of
+    the pipeline (:47, nchunks = ny) does not change any arithmetic so the whole plane
+    is handed over at once."""
+    nz, ny, lh = p.nz, p.ny, p.lh
+    coord, nproc = p.coord, p.nproc
+    n = nz + 1
+    m = lh - 1                                   # jx = 1..lh-1
+    # solved modes: jy /= ny/2+1, jx <= lh-1, (jx,jy) /= (1,1)   (:93-97)
+    M = np.zeros((ny, lh), bool)
+    M[:, :m] = True
+    M[ny // 2, :] = False
+    M[0, 0] = False
+    bet = np.zeros((ny, lh))
+    gam = np.zeros((n + 2, ny, lh))
+    c = c.copy()                                 # the pipeline overwrites c(:,:,1)
+
+    uc = u.view(np.complex128)                   # (n+1, ny, lh)
+    rc = np.ascontiguousarray(r).view(np.complex128)
+
+    if coord == 0:
+        # :53-66 first row solved for ALL jy, jx <= lh-1
+        uc[1, :, :m] = rc[1, :, :m] / b[1, :, :m]
+        bet[:, :] = b[1]
+        j_min = 1
+    else:
+        j_min = 2
+    j_max = n if coord == nproc - 1 else n - 1
+
+    if coord != 0:
+        comm.recv(c[1], coord - 1, 101)
+        comm.recv(bet, coord - 1, 102)
+        comm.recv(u[1], coord - 1, 103)
+
+    for j in range(2, j_max + 1):
+        g = c[j - 1][M] / bet[M]
+        gam[j][M] = g
+        bt = b[j][M] - a[j][M] * g
+        if np.any(bt == 0.0):
+            raise ZeroDivisionError("tridag_array failed (zero pivot), j=%d" % j)
+        bet[M] = bt
+        uc[j][M] = (rc[j][M] - a[j][M] * uc[j - 1][M]) / bt
+
+    if coord != nproc - 1:
+        comm.send(c[n - 1], coord + 1, 101)
+        comm.send(bet, coord + 1, 102)
+        comm.send(u[n - 1], coord + 1, 103)
+
+    if coord != nproc - 1:
+        comm.recv(u[n], coord + 1, 104)
+        comm.recv(gam[n], coord + 1, 105)
+    for j in range(n - 1, j_min - 1, -1):
+        uc[j][M] = uc[j][M] - gam[j + 1][M] * uc[j + 1][M]
+    comm.send(u[2], coord - 1, 104)
+    comm.send(gam[2], coord - 1, 105)
+    return u
+
+
+# ----------------------------------------------------------------------------------
+# press_stag_array.f90
+# ----------------------------------------------------------------------------------
+def press_stag_array(s, sp: Spectral, comm):
+    """press_stag_array.f90:21-290.  Reads s.u,v,w, s.divtz; returns p (0:nz), dpdx,
+    dpdy, dpdz (1:nz, plane 0 unused)."""
+    P = sp.p
+    nx, ny, nz, ld, lh = P.nx, P.ny, P.nz, P.ld, P.lh
+    coord, nproc, dz = P.coord, P.nproc, P.dz
+    const = 1.0 / (nx * ny)
+    const2 = const / P.tadv1 / P.dt
+    const3 = 1.0 / dz ** 2
+    const4 = 1.0 / dz
+
+    rH_x = np.full((nz + 1, ny, ld), BOGUS)
+    rH_y = np.full((nz + 1, ny, ld), BOGUS)
+    rH_z = np.full((nz + 1, ny, ld), BOGUS)
+    rH_x[1:nz] = sp.forw(const2 * s.u[1:nz])        # :77-85
+    rH_y[1:nz] = sp.forw(const2 * s.v[1:nz])
+    rH_z[1:nz] = sp.forw(const2 * s.w[1:nz])
+    if coord == nproc - 1:                           # :100-103
+        rH_z[nz] = sp.forw(const2 * s.w[nz])
+    rbottomw = np.zeros((ny, ld))
+    rtopw = np.zeros((ny, ld))
+    if coord == 0:                                   # :114-117
+        rbottomw = sp.forw(const * s.divtz[1])
+    if coord == nproc - 1:                           # :119-126
+        rtopw = sp.forw(const * s.divtz[nz])
+    # :129-146 oddballs
+    sp.zero_oddballs(rH_x[1:nz]); sp.zero_oddballs(rH_y[1:nz]); sp.zero_oddballs(rH_z[1:nz])
+    if coord == nproc - 1:
+        sp.zero_oddballs(rH_z[nz])
+    sp.zero_oddballs(rtopw); sp.zero_oddballs(rbottomw)
+
+    # system rows 1..nz+1 at index j (index 0 unused)
+    a = np.full((nz + 2, ny, lh), BOGUS)
+    b = np.full((nz + 2, ny, lh), BOGUS)
+    c = np.full((nz + 2, ny, lh), BOGUS)
+    RHS_col = np.zeros((nz + 2, ny, ld))
+    if coord == 0:                                   # :149-162
+        b[1] = -1.0
+        c[1] = 1.0
+        RHS_col[1] = -dz * rbottomw
+        jz_min = 2
+    else:
+        jz_min = 1
+    if coord == nproc - 1:                           # :164-175
+        a[nz + 1] = -1.0
+        b[nz + 1] = 1.0
+        RHS_col[nz + 1] = -dz * rtopw
+
+    # :177-186 halos
+    comm.sendrecv(rH_x[nz - 1], coord + 1, rH_x[0], coord - 1, 11)
+    comm.sendrecv(rH_y[nz - 1], coord + 1, rH_y[0], coord - 1, 12)
+    comm.sendrecv(rH_z[nz - 1], coord + 1, rH_z[0], coord - 1, 13)
+    comm.sendrecv(rH_z[1], coord - 1, rH_z[nz], coord + 1, 16)
+
+    # :188-215
+    kx, ky = sp.kx, sp.ky
+    for jz in range(jz_min, nz + 1):
+        a[jz] = const3
+        b[jz] = -(kx ** 2 + ky ** 2 + 2.0 * const3)
+        c[jz] = const3
+        hx = rH_x[jz - 1].view(np.complex128)
+        hy = rH_y[jz - 1].view(np.complex128)
+        rc = RHS_col[jz].view(np.complex128)
+        aHx_re = -hx.imag * kx
+        aHx_im = hx.real * kx
+        aHy_re = -hy.imag * ky
+        aHy_im = hy.real * ky
+        dzr = (rH_z[jz] - rH_z[jz - 1]) * const4
+        rc.real[...] = aHx_re + aHy_re + dzr[:, 0::2]
+        rc.imag[...] = aHx_im + aHy_im + dzr[:, 1::2]
+
+    # p(ld, ny, 0:nz): system row j <-> p(:,:,j-1)
+    p_sys = np.zeros((nz + 2, ny, ld))      # row j at index j
+    if coord != 0:
+        p_sys[1] = BOGUS                     # :66-71 p(:,:,0) = BOGUS
+    tridag_array(a, b, c, RHS_col, p_sys, P, comm)   # :218
+    p = np.ascontiguousarray(p_sys[1:])      # p[k] = row k+1, k = 0..nz
+
+    # :220-239 zero-wavenumber chain
+    buf = np.zeros(2)
+    if coord != 0:
+        comm.recv(buf, coord - 1, 8)
+        p[1, 0, 0:2] = buf
+    if coord == 0:
+        p[0, 0, 0:2] = 0.0
+        p[1, 0, 0:2] = p[0, 0, 0:2] - dz * rbottomw[0, 0:2]
+    for jz in range(2, nz + 1):
+        p[jz, 0, 0:2] = p[jz - 1, 0, 0:2] + rH_z[jz, 0, 0:2] * dz
+    comm.send(p[nz, 0, 0:2], coord + 1, 8)
+
+    # :241-246
+    comm.sendrecv(p[nz - 1], coord + 1, p[0], coord - 1, 2)
+
+    # :248-250
+    sp.zero_oddballs(p)
+
+    dpdx = np.full((nz + 1, ny, ld), BOGUS)
+    dpdy = np.full((nz + 1, ny, ld), BOGUS)
+    dpdz = np.full((nz + 1, ny, ld), BOGUS)
+    # :252-273
+    dpdx[1:nz] = sp.back(sp.muli(p[1:nz], kx))
+    dpdy[1:nz] = sp.back(sp.muli(p[1:nz], ky))
+    p[0:nz] = sp.back(p[0:nz])
+    if coord == nproc - 1:
+        p[nz] = sp.back(p[nz])
+    else:
+        p[nz] = BOGUS
+    # :282-288
+    dpdz[1:nz, :, :nx] = (p[1:nz, :, :nx] - p[0:nz - 1, :, :nx]) / dz
+    if coord == nproc - 1:
+        dpdz[nz, :, :nx] = (p[nz, :, :nx] - p[nz - 1, :, :nx]) / dz
+    return p, dpdx, dpdy, dpdz
+
+
+# ----------------------------------------------------------------------------------
+# test_filtermodule.f90
+# ----------------------------------------------------------------------------------
+def test_filter_kernel(sp: Spectral, alpha=2.0):
+    """test_filter_init (test_filtermodule.f90:38-123) for the first test filter."""
+    p = sp.p
+    G = np.full((p.ny, p.lh), 1.0 / (p.nx * p.ny))
+    delta_t = alpha * math.sqrt(p.dx * p.dy)
+    if p.ifilter == 1:
+        kc2 = (math.pi / delta_t) ** 2
+        G[sp.k2 >= kc2] = 0.0
+    elif p.ifilter == 2:
+        G = np.exp(-(delta_t ** 2) * sp.k2 / (4.0 * 6.0)) * G
+    elif p.ifilter == 3:
+        G = ((np.sin(sp.kx * delta_t / 2.0) * np.sin(sp.ky * delta_t / 2.0) + 1e-8)
+             / (sp.kx * delta_t / 2.0 * sp.ky * delta_t / 2.0 + 1e-8)) * G
+    G[:, p.lh - 1] = 0.0
+    G[p.ny // 2, :] = 0.0
+    return G
+
+
+def test_filter(f, sp: Spectral, G):
+    """test_filtermodule.f90:126-146."""
+    return sp.back(sp.mulr(sp.forw(f), G))
+
+
+# ----------------------------------------------------------------------------------
+# wallstress.f90
+# ----------------------------------------------------------------------------------
+def wallstress(s, sp: Spectral, G_test=None):
+    """wallstress.f90:47-255 (lbc/ubc = 0 stress free, 1 DNS wall, 2 equilibrium)."""
+    p = sp.p
+    nx, nz, dz = p.nx, p.nz, p.dz
+    nu = p.nu_molec / (p.z_i * p.u_star)
+    if p.coord == 0:
+        if p.lbc_mom == 0:
+            s.txz[1] = 0.0; s.tyz[1] = 0.0; s.dudz[1] = 0.0; s.dvdz[1] = 0.0
+        elif p.lbc_mom == 1:
+            s.dudz[1, :, :nx] = (s.u[1, :, :nx] - p.ubot) / (0.5 * dz)
+            s.dvdz[1, :, :nx] = s.v[1, :, :nx] / (0.5 * dz)
+            s.txz[1, :, :nx] = -nu * s.dudz[1, :, :nx]
+            s.tyz[1, :, :nx] = -nu * s.dvdz[1, :, :nx]
+        elif p.lbc_mom == 2:
+            u1 = test_filter(s.u[1], sp, G_test)
+            v1 = test_filter(s.v[1], sp, G_test)
+            denom = math.log(0.5 * dz / p.zo)
+            u_avg = np.sqrt(u1[:, :nx] ** 2 + v1[:, :nx] ** 2)
+            ustar = u_avg * p.vonk / denom
+            const = -(ustar ** 2) / u_avg
+            s.txz[1, :, :nx] = const * u1[:, :nx]
+            s.tyz[1, :, :nx] = const * v1[:, :nx]
+            du = ustar / (0.5 * dz * p.vonk) * s.u[1, :, :nx] / u_avg
+            dv = ustar / (0.5 * dz * p.vonk) * s.v[1, :, :nx] / u_avg
+            s.dudz[1, :, :nx] = np.where(s.u[1, :, :nx] == 0.0, 0.0, du)
+            s.dvdz[1, :, :nx] = np.where(s.v[1, :, :nx] == 0.0, 0.0, dv)
+        else:
+            raise ValueError("invalid lbc_mom")
+    if p.coord == p.nproc - 1:
+        if p.ubc_mom == 0:
+            s.txz[nz] = 0.0; s.tyz[nz] = 0.0; s.dudz[nz] = 0.0; s.dvdz[nz] = 0.0
+        elif p.ubc_mom == 1:
+            s.dudz[nz, :, :nx] = (p.utop - s.u[nz - 1, :, :nx]) / (0.5 * dz)
+            s.dvdz[nz, :, :nx] = -s.v[nz - 1, :, :nx] / (0.5 * dz)
+            s.txz[nz, :, :nx] = -nu * s.dudz[nz, :, :nx]
+            s.tyz[nz, :, :nx] = -nu * s.dvdz[nz, :, :nx]
+        elif p.ubc_mom == 2:
+            u1 = test_filter(s.u[nz - 1], sp, G_test)
+            v1 = test_filter(s.v[nz - 1], sp, G_test)
+            denom = math.log(0.5 * dz / p.zo)
+            u_avg = np.sqrt(u1[:, :nx] ** 2 + v1[:, :nx] ** 2)
+            ustar = u_avg * p.vonk / denom
+            const = (ustar ** 2) / u_avg
+            s.txz[nz, :, :nx] = const * u1[:, :nx]
+            s.tyz[nz, :, :nx] = const * v1[:, :nx]
+            du = -ustar / (0.5 * dz * p.vonk) * s.u[nz - 1, :, :nx] / u_avg
+            dv = -ustar / (0.5 * dz * p.vonk) * s.v[nz - 1, :, :nx] / u_avg
+            s.dudz[nz, :, :nx] = np.where(s.u[nz - 1, :, :nx] == 0.0, 0.0, du)
+            s.dvdz[nz, :, :nx] = np.where(s.v[nz - 1, :, :nx] == 0.0, 0.0, dv)
+        else:
+            raise ValueError("invalid ubc_mom")
+
+
+# ----------------------------------------------------------------------------------
+# sgs_stag_util.f90: calc_Sij (:467-634), sgs_stag (:43-465), constant-coefficient paths
+# ----------------------------------------------------------------------------------
+def calc_Sij(s, p: Params, comm):
+    nx, nz = p.nx, p.nz
+    X = slice(0, nx)
+    S = {k: np.zeros_like(s.u) for k in ("S11", "S12", "S13", "S22", "S23", "S33")}
+    if p.coord == 0:
+        if p.lbc_mom == 0:
+            S["S11"][1, :, X] = s.dudx[1, :, X]
+            S["S12"][1, :, X] = 0.5 * (s.dudy[1, :, X] + s.dvdx[1, :, X])
+            S["S13"][1, :, X] = 0.5 * (s.dudz[1, :, X] + s.dwdx[1, :, X])
+            S["S22"][1, :, X] = s.dvdy[1, :, X]
+            S["S23"][1, :, X] = 0.5 * (s.dvdz[1, :, X] + s.dwdy[1, :, X])
+            S["S33"][1, :, X] = 0.5 * (s.dwdz[1, :, X] + 0.0)
+        else:
+            S["S11"][1, :, X] = s.dudx[1, :, X]
+            S["S12"][1, :, X] = 0.5 * (s.dudy[1, :, X] + s.dvdx[1, :, X])
+            wx = 0.5 * (s.dwdx[1, :, X] + s.dwdx[2, :, X])
+            S["S13"][1, :, X] = 0.5 * (s.dudz[1, :, X] + wx)
+            S["S22"][1, :, X] = s.dvdy[1, :, X]
+            wy = 0.5 * (s.dwdy[1, :, X] + s.dwdy[2, :, X])
+            S["S23"][1, :, X] = 0.5 * (s.dvdz[1, :, X] + wy)
+            S["S33"][1, :, X] = s.dwdz[1, :, X]
+        jz_min = 2
+    else:
+        jz_min = 1
+    if p.coord == p.nproc - 1:
+        if p.ubc_mom == 0:
+            S["S11"][nz, :, X] = s.dudx[nz - 1, :, X]
+            S["S12"][nz, :, X] = 0.5 * (s.dudy[nz - 1, :, X] + s.dvdx[nz - 1, :, X])
+            S["S13"][nz, :, X] = 0.5 * (s.dudz[nz, :, X] + s.dwdx[nz, :, X])
+            S["S22"][nz, :, X] = s.dvdy[nz - 1, :, X]
+            S["S23"][nz, :, X] = 0.5 * (s.dvdz[nz, :, X] + s.dwdy[nz, :, X])
+            S["S33"][nz, :, X] = 0.5 * (s.dwdz[nz - 1, :, X] + 0.0)
+        else:
+            S["S11"][nz, :, X] = s.dudx[nz - 1, :, X]
+            S["S12"][nz, :, X] = 0.5 * (s.dudy[nz - 1, :, X] + s.dvdx[nz - 1, :, X])
+            wx = 0.5 * (s.dwdx[nz - 1, :, X] + s.dwdx[nz, :, X])
+            S["S13"][nz, :, X] = 0.5 * (s.dudz[nz, :, X] + wx)
+            S["S22"][nz, :, X] = s.dvdy[nz - 1, :, X]
+            wy = 0.5 * (s.dwdy[nz - 1, :, X] + s.dwdy[nz, :, X])
+            S["S23"][nz, :, X] = 0.5 * (s.dvdz[nz, :, X] + wy)
+            S["S33"][nz, :, X] = s.dwdz[nz - 1, :, X]
+        jz_max = nz - 1
+    else:
+        jz_max = nz
+    # :611-614 dwdz plane 1 of coord+1 -> plane nz of coord
+    comm.sendrecv(s.dwdz[1], comm.coord - 1, s.dwdz[nz], comm.coord + 1, 1)
+    K = slice(jz_min, jz_max + 1)
+    Km = slice(jz_min - 1, jz_max)
+    S["S11"][K, :, X] = 0.5 * (s.dudx[K, :, X] + s.dudx[Km, :, X])
+    uy = s.dudy[K, :, X] + s.dudy[Km, :, X]
+    vx = s.dvdx[K, :, X] + s.dvdx[Km, :, X]
+    S["S12"][K, :, X] = 0.25 * (uy + vx)
+    S["S13"][K, :, X] = 0.5 * (s.dudz[K, :, X] + s.dwdx[K, :, X])
+    S["S22"][K, :, X] = 0.5 * (s.dvdy[K, :, X] + s.dvdy[Km, :, X])
+    S["S23"][K, :, X] = 0.5 * (s.dvdz[K, :, X] + s.dwdy[K, :, X])
+    S["S33"][K, :, X] = 0.5 * (s.dwdz[K, :, X] + s.dwdz[Km, :, X])
+    return S
+
+
+def _smag_length(p: Params):
+    """sgs_stag_util.f90:87-179: Mason wall-damped length l(1:nz) for sgs_model 1."""
+    nz, dz, Co, n, vonk, delta = p.nz, p.dz, p.Co, p.wall_damp_exp, p.vonk, p.delta
+    l = np.full(nz + 1, delta)
+
+    def damp(zz):
+        return (Co ** n * (vonk * zz) ** (-n) + delta ** (-n)) ** (-1.0 / n)
+
+    lb, ub = p.lbc_mom, p.ubc_mom
+    if lb == 0 and ub == 0:
+        return l
+    jz_min, jz_max = 1, nz
+    if lb > 0 and p.coord == 0:
+        l[1] = damp(0.5 * dz)
+        jz_min = 2
+    if ub > 0 and p.coord == p.nproc - 1:
+        l[nz] = damp(0.5 * dz)
+        jz_max = nz - 1
+    for jz in range(jz_min, jz_max + 1):
+        if lb > 0 and ub == 0:
+            zz = ((jz - 1) + p.coord * (nz - 1)) * dz
+        elif lb > 0 and ub > 0:
+            zz = ((jz - 1) + p.coord * (nz - 1)) * dz
+            zz = min(zz, (nz - 1) * p.nproc * dz - zz)
+        else:
+            zz = ((p.nproc - p.coord) * (nz - 1) - (jz - 1)) * dz
+        l[jz] = damp(zz)
+    return l
+
+
+def sgs_stag(s, p: Params, comm, Cs_opt2_const: Optional[float] = None):
+    """sgs_stag_util.f90:43-465 for: sgs = .false. (molecular stress only), sgs_model 1
+    (Smagorinsky, Cs_opt2 = Co**2, Mason damping), and the pre-DYN_init phase of the
+    dynamic models (Cs_opt2 = 0.03, l = delta, :187-189).  Writes txx..tzz into s."""
+    nx, nz = p.nx, p.nz
+    X = slice(0, nx)
+    nu = p.nu
+    S = calc_Sij(s, p, comm)
+    s.S = S
+    if p.sgs:
+        if p.sgs_model == 1:
+            l = _smag_length(p)
+            Cs = p.Co ** 2
+        else:
+            l = np.full(nz + 1, p.delta)
+            Cs = 0.03 if Cs_opt2_const is None else Cs_opt2_const
+        Smag = np.sqrt(2.0 * (S["S11"] ** 2 + S["S22"] ** 2 + S["S33"] ** 2
+                              + 2.0 * (S["S12"] ** 2 + S["S13"] ** 2 + S["S23"] ** 2)))
+        Nu_t = Smag * Cs * (l ** 2)[:, None, None]
+    else:
+        Nu_t = np.zeros_like(s.u)
+    s.Nu_t = Nu_t
+    t = {k: getattr(s, k) for k in ("txx", "txy", "tyy", "tzz", "txz", "tyz")}
+    pairs = (("txx", "S11"), ("txy", "S12"), ("tyy", "S22"), ("tzz", "S33"))
+    if p.coord == 0:
+        if p.lbc_mom == 0:
+            cst = (0.5 * (Nu_t[1, :, X] + Nu_t[2, :, X]) + nu) if p.sgs else nu
+            for tn, sn in pairs:
+                t[tn][1, :, X] = -cst * (S[sn][1, :, X] + S[sn][2, :, X])
+        else:
+            cst = -2.0 * (Nu_t[1, :, X] + nu) if p.sgs else -2.0 * nu
+            for tn, sn in pairs:
+                t[tn][1, :, X] = cst * S[sn][1, :, X]
+        jz_min = 2
+    else:
+        jz_min = 1
+    if p.coord == p.nproc - 1:
+        if p.ubc_mom == 0:
+            cst = (0.5 * (Nu_t[nz - 1, :, X] + Nu_t[nz, :, X]) + nu) if p.sgs else nu
+            cst2 = 2.0 * (Nu_t[nz - 1, :, X] + nu) if p.sgs else 2.0 * nu
+            for tn, sn in pairs:
+                t[tn][nz - 1, :, X] = -cst * (S[sn][nz - 1, :, X] + S[sn][nz, :, X])
+            t["txz"][nz - 1, :, X] = -cst2 * S["S13"][nz - 1, :, X]
+            t["tyz"][nz - 1, :, X] = -cst2 * S["S23"][nz - 1, :, X]
+        else:
+            if p.sgs:
+                cst = -2.0 * (Nu_t[nz, :, X] + nu)
+                cst2 = -2.0 * (Nu_t[nz - 1, :, X] + nu)
+                for tn, sn in pairs:
+                    t[tn][nz - 1, :, X] = cst * S[sn][nz, :, X]
+            else:
+                # NB the reference's DNS branch uses Sij(nz-1) here (:353-356)
+                cst2 = -2.0 * nu
+                for tn, sn in pairs:
+                    t[tn][nz - 1, :, X] = -2.0 * nu * S[sn][nz - 1, :, X]
+            t["txz"][nz - 1, :, X] = cst2 * S["S13"][nz - 1, :, X]
+            t["tyz"][nz - 1, :, X] = cst2 * S["S23"][nz - 1, :, X]
+        jz_max = nz - 2
+    else:
+        jz_max = nz - 1
+    K = slice(jz_min, jz_max + 1)
+    Kp = slice(jz_min + 1, jz_max + 2)
+    if p.sgs:
+        const3 = -2.0 * nu * 0.5
+        const4 = -2.0 * nu
+        cst = -0.5 * (Nu_t[K, :, X] + Nu_t[Kp, :, X])
+        cst2 = -2.0 * Nu_t[K, :, X]
+        for tn, sn in pairs:
+            t[tn][K, :, X] = (cst + const3) * (S[sn][K, :, X] + S[sn][Kp, :, X])
+        t["txz"][K, :, X] = (cst2 + const4) * S["S13"][K, :, X]
+        t["tyz"][K, :, X] = (cst2 + const4) * S["S23"][K, :, X]
+    else:
+        for tn, sn in pairs:
+            t[tn][K, :, X] = -nu * (S[sn][K, :, X] + S[sn][Kp, :, X])
+        t["txz"][K, :, X] = -2.0 * nu * S["S13"][K, :, X]
+        t["tyz"][K, :, X] = -2.0 * nu * S["S23"][K, :, X]
+    # :437-465
+    mpi_sync_real_array(s.txz, p, comm, down=True, up=False)
+    mpi_sync_real_array(s.tyz, p, comm, down=True, up=False)
+    for tn in ("txx", "txy", "txz", "tyy", "tyz", "tzz"):
+        t[tn][0] = BOGUS
+    for tn in ("txx", "txy", "tyy", "tzz"):
+        t[tn][nz] = BOGUS
+
+
+# ----------------------------------------------------------------------------------
+# divstress_uv.f90 / divstress_w.f90
+# ----------------------------------------------------------------------------------
+def divstress_uv(s, sp: Spectral):
+    """divstress_uv.f90:21-86."""
+    p = sp.p
+    nz, ld = p.nz, p.ld
+    dtxdx = ddx(s.txx, sp)
+    dtzdz = ddz_w(s.txz, p)
+    dtydy2 = ddy(s.tyy, sp)
+    dtzdz2 = ddz_w(s.tyz, p)
+    dtxdx2, dtydy = ddxy(s.txy, sp)
+    divtx = np.full_like(s.u, BOGUS)
+    divty = np.full_like(s.u, BOGUS)
+    divtx[1:nz] = dtxdx[1:nz] + dtydy[1:nz] + dtzdz[1:nz]
+    divtx[1:nz, :, ld - 2:] = 0.0
+    divty[1:nz] = dtxdx2[1:nz] + dtydy2[1:nz] + dtzdz2[1:nz]
+    divty[1:nz, :, ld - 2:] = 0.0
+    return divtx, divty
+
+
+def divstress_w(s, sp: Spectral):
+    """divstress_w.f90:21-116 (tx=txz, ty=tyz, tz=tzz)."""
+    p = sp.p
+    nx, nz, ld = p.nx, p.nz, p.ld
+    X = slice(0, nx)
+    dtxdx = ddx(s.txz, sp)
+    dtydy = ddy(s.tyz, sp)
+    dtzdz = ddz_uv(s.tzz, p)
+    divt = np.full_like(s.u, BOGUS)
+    if p.coord == 0:
+        divt[1, :, X] = dtxdx[1, :, X] + dtydy[1, :, X]
+    else:
+        divt[1, :, X] = dtxdx[1, :, X] + dtydy[1, :, X] + dtzdz[1, :, X]
+    if p.coord == p.nproc - 1:
+        divt[nz, :, X] = dtxdx[nz, :, X] + dtydy[nz, :, X]
+    else:
+        divt[nz, :, X] = dtxdx[nz, :, X] + dtydy[nz, :, X] + dtzdz[nz, :, X]
+    divt[2:nz, :, X] = dtxdx[2:nz, :, X] + dtydy[2:nz, :, X] + dtzdz[2:nz, :, X]
+    divt[1:nz, :, ld - 2:] = 0.0
+    return divt
+
+
+# ----------------------------------------------------------------------------------
+# forcing.f90: project; cfl_util.f90; rmsdiv.f90
+# ----------------------------------------------------------------------------------
+def project(s, p: Params, comm):
+    """forcing.f90:149-244 (no level set, no inflow)."""
+    nx, nz = p.nx, p.nz
+    X = slice(0, nx)
+    dt, tadv1 = p.dt, p.tadv1
+    s.u[1:nz, :, X] = s.u[1:nz, :, X] + dt * (-tadv1 * s.dpdx[1:nz, :, X])
+    s.v[1:nz, :, X] = s.v[1:nz, :, X] + dt * (-tadv1 * s.dpdy[1:nz, :, X])
+    jz_min = 2 if p.coord == 0 else 1
+    s.w[jz_min:nz, :, X] = s.w[jz_min:nz, :, X] + dt * (-tadv1 * s.dpdz[jz_min:nz, :, X])
+    for f in (s.u, s.v, s.w):
+        mpi_sync_real_array(f, p, comm, down=True, up=True)
+    if p.coord == p.nproc - 1:
+        if p.ubc_mom == 0:
+            s.u[nz] = s.u[nz - 1]
+            s.v[nz] = s.v[nz - 1]
+        s.w[nz] = 0.0
+    if p.coord == 0:
+        s.w[1] = 0.0
+
+
+def get_max_cfl(s, p: Params, comm):
+    """cfl_util.f90:35-69."""
+    nx, nz = p.nx, p.nz
+    cu = np.abs(s.u[1:nz, :, :nx]).max() / p.dx
+    cv = np.abs(s.v[1:nz, :, :nx]).max() / p.dy
+    cw = np.abs(s.w[1:nz, :, :nx]).max() / p.dz
+    return comm.allreduce(p.dt * max(cu, cv, cw), "max")
+
+
+def get_cfl_dt(s, p: Params, comm, cfl):
+    """cfl_util.f90:72-111."""
+    nx, nz = p.nx, p.nz
+    cu = np.abs(s.u[1:nz, :, :nx]).max() / p.dx
+    cv = np.abs(s.v[1:nz, :, :nx]).max() / p.dy
+    cw = np.abs(s.w[1:nz, :, :nx]).max() / p.dz
+    return comm.allreduce(cfl / max(cu, cv, cw), "min")
+
+
+def rmsdiv(s, p: Params, comm):
+    """rmsdiv.f90:21-59: L1 norm of the divergence over 1:nz-1, averaged over ranks."""
+    nx, ny, nz = p.nx, p.ny, p.nz
+    r = np.abs(s.dudx[1:nz, :, :nx] + s.dvdy[1:nz, :, :nx] + s.dwdz[1:nz, :, :nx]).sum()
+    r = r / (nx * ny * (nz - 1))
+    return comm.allreduce(r, "sum") / p.nproc
+
+
+# ----------------------------------------------------------------------------------
+# State + one timestep (main.f90:130-344)
+# ----------------------------------------------------------------------------------
+FIELDS = ("u", "v", "w", "dudx", "dudy", "dudz", "dvdx", "dvdy", "dvdz", "dwdx", "dwdy",
+          "dwdz", "RHSx", "RHSy", "RHSz", "RHSx_f", "RHSy_f", "RHSz_f", "dpdx", "dpdy",
+          "dpdz", "p", "txx", "txy", "txz", "tyy", "tyz", "tzz", "divtx", "divty", "divtz")
+
+
+class State:
+    """sim_param.f90:31-82 (the subset of the 33 module arrays this path touches)."""
+
+    def __init__(self, p: Params):
+        self.p = p
+        shape = (p.nz + 1, p.ny, p.ld)
+        for n in FIELDS:
+            setattr(self, n, np.zeros(shape))
+
+    def copy(self):
+        o = State(self.p)
+        for n in FIELDS:
+            getattr(o, n)[...] = getattr(self, n)
+        return o
+
+
+def step(s: State, sp: Spectral, comm, mode="full", first_step=False, G_test=None):
+    """One timestep, main.f90:130-344.
+
+    mode = "core": the scope-table (a)-(e) path only -- derivatives, convec, AB2,
+        pressure, projection; the stress divergence divt* is taken as zero (i.e. sgs
+        rows (f)-1 skipped), wallstress still supplies dudz/dvdz at the walls because
+        convec's wall planes read them (convec.f90:108-112,133-138).
+    mode = "full": adds wallstress + sgs_stag + divstress (rows (f)-1), which is the
+        reference's complete step for a DNS / constant-coefficient LES configuration.
+    """
+    p = sp.p
+    nz, nproc, coord = p.nz, p.nproc, p.coord
+    # :155-157
+    s.RHSx_f[...] = s.RHSx; s.RHSy_f[...] = s.RHSy; s.RHSz_f[...] = s.RHSz
+    # :161-163
+    s.u, s.dudx, s.dudy = filt_da(s.u, sp)
+    s.v, s.dvdx, s.dvdy = filt_da(s.v, sp)
+    s.w, s.dwdx, s.dwdy = filt_da(s.w, sp)
+    # :167-172
+    ddz_uv(s.u, p, s.dudz); ddz_uv(s.v, p, s.dvdz); ddz_w(s.w, p, s.dwdz)
+    # :182-184
+    if coord == 0 or coord == nproc - 1:
+        wallstress(s, sp, G_test)
+    if mode == "full":
+        sgs_stag(s, p, comm)                                         # :189
+        comm.sendrecv(s.tzz[nz - 1], coord + 1, s.tzz[0], coord - 1, 6)   # :194
+        s.divtx, s.divty = divstress_uv(s, sp)                       # :202
+        s.divtz = divstress_w(s, sp)                                 # :203
+    else:
+        s.divtx[...] = 0.0; s.divty[...] = 0.0; s.divtz[...] = 0.0
+    s.RHSx, s.RHSy, s.RHSz = convec(s, sp)                           # :207
+    # :211-214
+    s.RHSx[1:nz] = -s.RHSx[1:nz] - s.divtx[1:nz]
+    s.RHSy[1:nz] = -s.RHSy[1:nz] - s.divty[1:nz]
+    s.RHSz[1:nz] = -s.RHSz[1:nz] - s.divtz[1:nz]
+    if coord == nproc - 1:
+        s.RHSz[nz] = -s.RHSz[nz] - s.divtz[nz]
+    # :229-232
+    if p.use_mean_p_force:
+        s.RHSx[1:nz] = s.RHSx[1:nz] + p.mean_p_force_x
+        s.RHSy[1:nz] = s.RHSy[1:nz] + p.mean_p_force_y
+    # :273-280
+    if first_step:
+        s.RHSx_f[...] = s.RHSx; s.RHSy_f[...] = s.RHSy; s.RHSz_f[...] = s.RHSz
+    # :287-296
+    dt, t1, t2 = p.dt, p.tadv1, p.tadv2
+    s.u[1:nz] = s.u[1:nz] + dt * (t1 * s.RHSx[1:nz] + t2 * s.RHSx_f[1:nz])
+    s.v[1:nz] = s.v[1:nz] + dt * (t1 * s.RHSy[1:nz] + t2 * s.RHSy_f[1:nz])
+    s.w[1:nz] = s.w[1:nz] + dt * (t1 * s.RHSz[1:nz] + t2 * s.RHSz_f[1:nz])
+    if coord == nproc - 1:
+        s.w[nz] = s.w[nz] + dt * (t1 * s.RHSz[nz] + t2 * s.RHSz_f[nz])
+    # :299-308
+    s.u[0] = BOGUS; s.v[0] = BOGUS; s.w[0] = BOGUS
+    s.u[nz] = BOGUS; s.v[nz] = BOGUS
+    if coord < nproc - 1:
+        s.w[nz] = BOGUS
+    # :317
+    s.p, s.dpdx, s.dpdy, s.dpdz = press_stag_array(s, sp, comm)
+    # :321-326
+    s.RHSx[1:nz] = s.RHSx[1:nz] - s.dpdx[1:nz]
+    s.RHSy[1:nz] = s.RHSy[1:nz] - s.dpdy[1:nz]
+    s.RHSz[1:nz] = s.RHSz[1:nz] - s.dpdz[1:nz]
+    if coord == nproc - 1:
+        s.RHSz[nz] = s.RHSz[nz] - s.dpdz[nz]
+    # :344
+    project(s, p, comm)
+
+
+# ----------------------------------------------------------------------------------
+# Synthetic channel fields; global -> per-rank slabs with ghost planes
+# ----------------------------------------------------------------------------------
+def synthetic_global(nx, ny, Nz, nproc=1, seed=20240607, amp=0.5, L_x=2 * math.pi,
+                     L_y=2 * math.pi, L_z=2.0, mean="parabolic"):
+    """Global u,v,w on levels 1..nz_tot (index 0 unused) in the (k, j, i) layout with the
+    ld pad, band-limited by one filt_da, w = 0 on both walls."""
+    pg = Params(nx=nx, ny=ny, Nz=Nz, nproc=1, L_x=L_x, L_y=L_y, L_z=L_z)
+    pr = Params(nx=nx, ny=ny, Nz=Nz, nproc=nproc, L_x=L_x, L_y=L_y, L_z=L_z)
+    nzt = pr.nz_tot
+    rng = np.random.default_rng(seed)
+    ld = pg.ld
+    sp = Spectral(pg)
+    out = []
+    z_uv = (np.arange(nzt + 1) - 0.5) * pr.dz
+    z_w = (np.arange(nzt + 1) - 1.0) * pr.dz
+    for comp in range(3):
+        f = np.zeros((nzt + 1, ny, ld))
+        noise = rng.random((nzt, ny, nx)) - 0.5
+        f[1:, :, :nx] = amp * noise
+        if comp == 0:
+            if mean == "parabolic":
+                prof = 1.5 * (1.0 - (z_uv / (0.5 * L_z) - 1.0) ** 2)
+            else:
+                prof = np.zeros_like(z_uv)
+            f[:, :, :nx] += prof[:, None, None]
+        # taper the noise towards the walls so the field is channel-like
+        zz = z_w if comp == 2 else z_uv
+        taper = np.clip(np.sin(math.pi * np.clip(zz / L_z, 0.0, 1.0)), 0.0, 1.0) ** 0.5
+        if comp != 0:
+            f *= taper[:, None, None]
+        f, _, _ = filt_da(f, sp)
+        out.append(f)
+    u, v, w = out
+    w[1] = 0.0
+    w[nzt] = 0.0
+    return u, v, w
+
+
+def scatter_slab(g, p: Params):
+    """Global (nz_tot+1, ny, ld) array (levels 1..nz_tot) -> this rank's (nz+1, ny, ld)
+    with ghost planes: local k <-> global coord*(nz-1)+k (grid.f90:82, mpi_defs.f90:177).
+    Plane 0 on coord 0 is BOGUS (initial.f90:178-182)."""
+    nz = p.nz
+    loc = np.full((nz + 1,) + g.shape[1:], BOGUS)
+    base = p.coord * (nz - 1)
+    for k in range(0, nz + 1):
+        gk = base + k
+        if 1 <= gk <= p.nz_tot:
+            loc[k] = g[gk]
+    return loc
+
+
+def gather_slabs(locs, ps, kmin=1, top_extra=True):
+    """Inverse of scatter_slab over owned planes 1..nz-1 (+ nz on the top rank)."""
+    p0 = ps[0]
+    nzt = p0.nz_tot
+    g = np.full((nzt + 1,) + locs[0].shape[1:], np.nan)
+    for loc, p in zip(locs, ps):
+        base = p.coord * (p.nz - 1)
+        hi = p.nz if (p.coord == p.nproc - 1 and top_extra) else p.nz - 1
+        for k in range(kmin, hi + 1):
+            g[base + k] = loc[k]
+    return g

@@ -1,0 +1,135 @@
+/* lesgo_gpu.h -- C ABI of liblesgo_cuda.so: the B200 (sm_100a) implementation of
+ * LESGO's per-timestep pseudo-spectral core, callable from Fortran through
+ * ISO_C_BINDING (see fortran/ and INTEGRATION.md).
+ *
+ * Array layout everywhere: the Fortran layout of the reference, FP64, column major,
+ * f(ld, ny, 0:nz) with ld = nx + 2, i.e. element (jx, jy, jz) (1-based x, y; z from
+ * 0) at  f[(jz*ny + (jy-1))*ld + (jx-1)].  "nz" is the per-rank nz of param.f90 (each
+ * array has nz+1 planes; the library is built for the MPI layout lbz = 0 only,
+ * SURVEY Appendix A.2).  Arrays the reference declares 1:nz (dpdx, dpdy, dpdz) are
+ * passed as the address of their plane 1 MINUS one plane, or simply allocate them
+ * 0:nz -- every entry point documents which planes it reads and writes.
+ * Complex values are interleaved along x (re, im).
+ *
+ * Pointers may be host pointers (the Fortran module arrays) or CUDA device pointers;
+ * the library detects which (cudaPointerGetAttributes).  Host arrays are staged
+ * through device buffers inside the call; device arrays are used in place.
+ *
+ * All functions return 0 on success, non-zero on error (lesgo_gpu_last_error gives
+ * the text); the Fortran shim turns non-zero into `call error(...)`
+ * (messages.f90:228-240).  There is NO CPU fallback: lesgo_gpu_create fails when no
+ * CUDA device is usable.
+ */
+#ifndef LESGO_GPU_H
+#define LESGO_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lesgo_gpu_ctx lesgo_gpu_ctx;
+
+typedef struct lesgo_gpu_dims {
+    int nx, ny, nz;          /* param.f90:96-99; nz = per-rank nz (levels 0..nz)        */
+    int nz_tot;              /* (nz-1)*nproc + 1, input_util.f90:200                    */
+    int nproc, coord;        /* z-slab decomposition, mpi_defs.f90:77-87                */
+    double L_x, L_y, dz;     /* fft.f90:154-155 wavenumber scaling; input_util.f90:235  */
+    int lbc_mom, ubc_mom;    /* wall types: select convec.f90:101-151 special planes    */
+    int sgs;                 /* convec.f90:47-53: jzLo = 2 when LES, 1 when DNS         */
+    int device;              /* CUDA device ordinal, or -1 = current device             */
+} lesgo_gpu_dims;
+
+/* ---- lifetime (replaces init_fft, fft.f90:102-127) -------------------------------- */
+int lesgo_gpu_create(const lesgo_gpu_dims* dims, lesgo_gpu_ctx** ctx);
+int lesgo_gpu_destroy(lesgo_gpu_ctx* ctx);
+const char* lesgo_gpu_last_error(const lesgo_gpu_ctx* ctx);   /* ctx may be NULL */
+int lesgo_gpu_set_stream(lesgo_gpu_ctx* ctx, void* cuda_stream);
+int lesgo_gpu_synchronize(lesgo_gpu_ctx* ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+long lesgo_gpu_launch_count(const lesgo_gpu_ctx* ctx);
+/* per-launch CUDA-event timing for bench.py / profiling: enable = 1/0; when report != NULL
+ * it receives "label count total_ms" lines for the launches recorded so far (and clears them) */
+int lesgo_gpu_profile(lesgo_gpu_ctx* ctx, int enable, char* report, int report_len);
+
+/* ---- module fft (fft.f90) ------------------------------------------------------------ */
+/* kx, ky, k2 (lh, ny) as init_wavenumber builds them, fft.f90:130-160 (host arrays) */
+int lesgo_gpu_wavenumbers(lesgo_gpu_ctx* ctx, double* kx, double* ky, double* k2);
+/* padd(u_big, u), fft.f90:43-71: nplanes planes of (ld, ny) -> (ld_big, ny2) */
+int lesgo_gpu_padd(lesgo_gpu_ctx* ctx, double* u_big, const double* u, int nplanes);
+/* unpadd(cc, cc_big), fft.f90:74-99 */
+int lesgo_gpu_unpadd(lesgo_gpu_ctx* ctx, double* cc, const double* cc_big, int nplanes);
+/* dfftw_execute_dft_r2c / c2r with the plans forw, back (big = 0) or forw_big,
+ * back_big (big = 1), fft.f90:114-121; unnormalised, nplanes planes, out may equal in */
+int lesgo_gpu_fft_r2c(lesgo_gpu_ctx* ctx, const double* in, double* out, int nplanes, int big);
+int lesgo_gpu_fft_c2r(lesgo_gpu_ctx* ctx, const double* in, double* out, int nplanes, int big);
+
+/* ---- module derivatives (derivatives.f90); all arrays (ld, ny, 0:nz) ------------------- */
+int lesgo_gpu_ddx(lesgo_gpu_ctx* ctx, const double* f, double* dfdx);                   /* :37  */
+int lesgo_gpu_ddy(lesgo_gpu_ctx* ctx, const double* f, double* dfdy);                   /* :79  */
+int lesgo_gpu_ddxy(lesgo_gpu_ctx* ctx, const double* f, double* dfdx, double* dfdy);    /* :121 */
+int lesgo_gpu_filt_da(lesgo_gpu_ctx* ctx, double* f, double* dfdx, double* dfdy);       /* :166, f inout */
+int lesgo_gpu_ddz_uv(lesgo_gpu_ctx* ctx, const double* f, double* dfdz);                /* :214 */
+int lesgo_gpu_ddz_w(lesgo_gpu_ctx* ctx, const double* f, double* dfdz);                 /* :267 */
+/* test_filter(f) with a caller-supplied kernel G(lh, ny) (test_filtermodule.f90:126-146);
+ * nplanes planes of (ld, ny), in place */
+int lesgo_gpu_test_filter(lesgo_gpu_ctx* ctx, double* f, const double* G, int nplanes);
+
+/* ---- convec (convec.f90:21-334); module arrays passed explicitly ----------------------- */
+int lesgo_gpu_convec(lesgo_gpu_ctx* ctx, const double* u, const double* v, const double* w,
+                     const double* dudy, const double* dudz, const double* dvdx,
+                     const double* dvdz, const double* dwdx, const double* dwdy,
+                     double* RHSx, double* RHSy, double* RHSz);
+
+/* ---- press_stag_array (press_stag_array.f90:21-290) ------------------------------------
+ * reads u, v, w (1:nz-1, + w(nz) on the top rank), divtz(1) on coord 0, divtz(nz) on the
+ * top rank; writes p (0:nz), dpdx, dpdy, dpdz (all passed as (ld, ny, 0:nz) arrays; planes
+ * 1:nz-1 valid, + nz of p/dpdz on the top rank).  Includes tridag_array and, for
+ * nproc > 1, the halo / transpose communication (lesgo_gpu_comm_init first). */
+int lesgo_gpu_press_stag_array(lesgo_gpu_ctx* ctx, const double* u, const double* v,
+                               const double* w, const double* divtz, double dt, double tadv1,
+                               double* p, double* dpdx, double* dpdy, double* dpdz);
+
+/* ---- tridag_array (tridag_array.f90:166-246, serial form): general coefficients ---------
+ * a, b, c (lh, ny, n), r, u (ld, ny, n), n rows; solves every (jx <= lh-1, jy /= ny/2+1,
+ * (jx,jy) /= (1,1)) mode like the reference. */
+int lesgo_gpu_tridag_array(lesgo_gpu_ctx* ctx, const double* a, const double* b,
+                           const double* c, const double* r, double* u, int n);
+
+/* ---- device-resident state (sim_param.f90:31-82) and whole-step entry --------------------- */
+enum lesgo_gpu_field {
+    LG_U = 0, LG_V, LG_W, LG_DUDX, LG_DUDY, LG_DUDZ, LG_DVDX, LG_DVDY, LG_DVDZ,
+    LG_DWDX, LG_DWDY, LG_DWDZ, LG_RHSX, LG_RHSY, LG_RHSZ, LG_RHSX_F, LG_RHSY_F, LG_RHSZ_F,
+    LG_P, LG_DPDX, LG_DPDY, LG_DPDZ, LG_DIVTX, LG_DIVTY, LG_DIVTZ,
+    LG_TXX, LG_TXY, LG_TXZ, LG_TYY, LG_TYZ, LG_TZZ, LG_NFIELDS
+};
+/* device pointer of a resident field ((ld, ny, 0:nz) doubles); allocated on first use */
+double* lesgo_gpu_field_ptr(lesgo_gpu_ctx* ctx, int field);
+int lesgo_gpu_upload(lesgo_gpu_ctx* ctx, int field, const double* host);
+int lesgo_gpu_download(lesgo_gpu_ctx* ctx, int field, double* host);
+
+typedef struct lesgo_gpu_step_params {
+    double dt, tadv1, tadv2;            /* main.f90:135-144, input_util.f90:403-408 */
+    double mean_p_force_x, mean_p_force_y;   /* 0 when use_mean_p_force = .false.   */
+    double ubot, utop, nu_molec_nd;     /* wallstress.f90 DNS walls: nu_molec/(z_i u_star) */
+    int first_step;                     /* main.f90:273-280 Euler start                */
+    int mode;                           /* 0 = core (divt* taken from the resident fields
+                                           as given), 1 = + DNS wallstress/sgs/divstress */
+} lesgo_gpu_step_params;
+/* One timestep main.f90:155-344 on the resident fields, no host round trip. */
+int lesgo_gpu_step(lesgo_gpu_ctx* ctx, const lesgo_gpu_step_params* sp);
+/* cfl_util.f90:35-69 get_max_cfl (dx, dy from L/n) and rmsdiv.f90 on resident fields */
+int lesgo_gpu_max_cfl(lesgo_gpu_ctx* ctx, double dt, double* cfl);
+int lesgo_gpu_rmsdiv(lesgo_gpu_ctx* ctx, double* rms);
+
+/* ---- multi-GPU (mpi_defs.f90 -> NCCL) --------------------------------------------------------
+ * id: 128-byte ncclUniqueId made by lesgo_gpu_comm_unique_id on coord 0 and broadcast by
+ * the host (MPI_Bcast in the Fortran shim, torch.distributed in the Python host). */
+int lesgo_gpu_comm_unique_id(void* id128);
+int lesgo_gpu_comm_init(lesgo_gpu_ctx* ctx, const void* id128);
+/* mpi_sync_real_array(var, 0, isync), mpi_defs.f90:167-264: isync 1 = DOWN, 2 = UP, 3 = DOWNUP */
+int lesgo_gpu_sync_real_array(lesgo_gpu_ctx* ctx, double* var, int isync);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LESGO_GPU_H */

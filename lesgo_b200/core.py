@@ -1,0 +1,276 @@
+"""Host-side mirror of the reference interface for the hot path.
+
+`Core` owns one library context (= one MPI rank / one GPU of the reference's z-slab
+decomposition, mpi_defs.f90:77-87) and exposes the reference's subroutine names with
+the same argument meaning:
+
+    derivatives.f90 : ddx, ddy, ddxy, filt_da, ddz_uv, ddz_w
+    convec.f90      : convec
+    press_stag_array.f90 : press_stag_array          (tridag_array inside)
+    fft.f90         : padd, unpadd, wavenumbers, fft_r2c / fft_c2r (the FFTW plans)
+    main.f90 loop   : step  (device-resident fields), max_cfl, rmsdiv
+
+Arrays are the reference's `(ld, ny, 0:nz)` Fortran arrays held as C-ordered
+`[k, j, i]` arrays of shape `(nz+1, ny, ld)`: numpy arrays (host; staged through the
+device inside each call, like the Fortran shim does) or CUDA `torch.float64` tensors
+(used in place).  Errors raise `LibraryError` with the library's message, the analogue
+of the reference's `call error(...)` (messages.f90:228-240).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from .lib import DimsStruct, Library, LibraryError, StepParams, load_library
+
+FIELD_IDS = {n: i for i, n in enumerate(
+    ["u", "v", "w", "dudx", "dudy", "dudz", "dvdx", "dvdy", "dvdz", "dwdx", "dwdy", "dwdz",
+     "RHSx", "RHSy", "RHSz", "RHSx_f", "RHSy_f", "RHSz_f", "p", "dpdx", "dpdy", "dpdz",
+     "divtx", "divty", "divtz", "txx", "txy", "txz", "tyy", "tyz", "tzz"])}
+
+
+@dataclass
+class Dims:
+    """Grid / decomposition parameters, named as in param.f90 / lesgo.conf."""
+    nx: int
+    ny: int
+    Nz: int                      # lesgo.conf "Nz"; per-rank nz = Nz//nproc + 1 (input_util.f90:197)
+    nproc: int = 1
+    coord: int = 0
+    L_x: float = 2.0 * math.pi
+    L_y: float = 2.0 * math.pi
+    L_z: float = 2.0
+    lbc_mom: int = 1
+    ubc_mom: int = 1
+    sgs: bool = False
+    device: int = -1
+
+    @property
+    def nz(self):
+        return self.Nz // self.nproc + 1
+
+    @property
+    def nz_tot(self):
+        return (self.nz - 1) * self.nproc + 1
+
+    @property
+    def dz(self):
+        return self.L_z / (self.nz_tot - 1)
+
+    @property
+    def ld(self):
+        return 2 * (self.nx // 2 + 1)
+
+    @property
+    def lh(self):
+        return self.nx // 2 + 1
+
+    @property
+    def shape(self):
+        return (self.nz + 1, self.ny, self.ld)
+
+    @property
+    def shape_big(self):
+        return (self.nz + 1, 3 * self.ny // 2, 2 * (3 * self.nx // 4 + 1))
+
+
+def _addr(a, shape=None, writable=False):
+    """Address of a numpy array or torch tensor holding C-contiguous float64 data."""
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float64 or not a.flags.c_contiguous:
+            raise LibraryError("arrays must be C-contiguous float64")
+        if writable and not a.flags.writeable:
+            raise LibraryError("output array is read-only")
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise LibraryError(f"array shape {a.shape} != expected {tuple(shape)}")
+        return a.ctypes.data
+    # torch tensor (duck-typed so numpy-only callers never import torch)
+    if hasattr(a, "data_ptr"):
+        import torch
+        if a.dtype != torch.float64 or not a.is_contiguous():
+            raise LibraryError("tensors must be contiguous float64")
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise LibraryError(f"tensor shape {tuple(a.shape)} != expected {tuple(shape)}")
+        return a.data_ptr()
+    raise LibraryError(f"unsupported array type {type(a)}")
+
+
+class Core:
+    def __init__(self, dims: Dims, lib: Library | None = None):
+        self.lib = lib or load_library()
+        self.dims = dims
+        d = DimsStruct(dims.nx, dims.ny, dims.nz, dims.nz_tot, dims.nproc, dims.coord,
+                       dims.L_x, dims.L_y, dims.dz, dims.lbc_mom, dims.ubc_mom, int(dims.sgs), dims.device)
+        self._ctx = C.c_void_p()
+        if self.lib.create(C.byref(d), C.byref(self._ctx)):
+            raise LibraryError("lesgo_gpu_create: " + self.lib.error(None))
+
+    # -- plumbing ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc:
+            raise LibraryError(f"{what}: {self.lib.error(self._ctx)}")
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.lib.set_stream(self._ctx, C.c_void_p(cuda_stream)), "set_stream")
+
+    def synchronize(self):
+        self._ck(self.lib.synchronize(self._ctx), "synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.launch_count(self._ctx))
+
+    def profile(self, enable=True, report=False):
+        """Per-launch CUDA-event timing; returns {label: (count, total_ms)} when report=True."""
+        buf = C.create_string_buffer(8192) if report else None
+        self._ck(self.lib.profile(self._ctx, int(enable), buf, 8192 if report else 0), "profile")
+        out = {}
+        if report:
+            for line in buf.value.decode().splitlines():
+                lab, n, ms = line.split()
+                out[lab] = (int(n), float(ms))
+        return out
+
+    def empty(self, big=False):
+        return np.zeros(self.dims.shape_big if big else self.dims.shape)
+
+    # -- module fft ---------------------------------------------------------------------
+    def wavenumbers(self):
+        d = self.dims
+        kx, ky, k2 = (np.zeros((d.ny, d.lh)) for _ in range(3))
+        self._ck(self.lib.wavenumbers(self._ctx, kx.ctypes.data, ky.ctypes.data, k2.ctypes.data), "wavenumbers")
+        return kx, ky, k2
+
+    def fft_r2c(self, a, out=None, big=False):
+        out = a if out is None else out
+        self._ck(self.lib.fft_r2c(self._ctx, _addr(a), _addr(out, writable=True), a.shape[0], int(big)), "fft_r2c")
+        return out
+
+    def fft_c2r(self, a, out=None, big=False):
+        out = a if out is None else out
+        self._ck(self.lib.fft_c2r(self._ctx, _addr(a), _addr(out, writable=True), a.shape[0], int(big)), "fft_c2r")
+        return out
+
+    def padd(self, u_big, u):
+        self._ck(self.lib.padd(self._ctx, _addr(u_big, writable=True), _addr(u), u.shape[0]), "padd")
+        return u_big
+
+    def unpadd(self, cc, cc_big):
+        self._ck(self.lib.unpadd(self._ctx, _addr(cc, writable=True), _addr(cc_big), cc.shape[0]), "unpadd")
+        return cc
+
+    # -- module derivatives ---------------------------------------------------------------
+    def ddx(self, f, dfdx):
+        s = self.dims.shape
+        self._ck(self.lib.ddx(self._ctx, _addr(f, s), _addr(dfdx, s, True)), "ddx")
+        return dfdx
+
+    def ddy(self, f, dfdy):
+        s = self.dims.shape
+        self._ck(self.lib.ddy(self._ctx, _addr(f, s), _addr(dfdy, s, True)), "ddy")
+        return dfdy
+
+    def ddxy(self, f, dfdx, dfdy):
+        s = self.dims.shape
+        self._ck(self.lib.ddxy(self._ctx, _addr(f, s), _addr(dfdx, s, True), _addr(dfdy, s, True)), "ddxy")
+        return dfdx, dfdy
+
+    def filt_da(self, f, dfdx, dfdy):
+        """f is intent(inout): replaced by its Nyquist-filtered self (derivatives.f90:180)."""
+        s = self.dims.shape
+        self._ck(self.lib.filt_da(self._ctx, _addr(f, s, True), _addr(dfdx, s, True), _addr(dfdy, s, True)), "filt_da")
+        return f, dfdx, dfdy
+
+    def ddz_uv(self, f, dfdz):
+        s = self.dims.shape
+        self._ck(self.lib.ddz_uv(self._ctx, _addr(f, s), _addr(dfdz, s, True)), "ddz_uv")
+        return dfdz
+
+    def ddz_w(self, f, dfdz):
+        s = self.dims.shape
+        self._ck(self.lib.ddz_w(self._ctx, _addr(f, s), _addr(dfdz, s, True)), "ddz_w")
+        return dfdz
+
+    def test_filter(self, f, G):
+        self._ck(self.lib.test_filter(self._ctx, _addr(f, writable=True), _addr(G), f.shape[0]), "test_filter")
+        return f
+
+    # -- convec / pressure ------------------------------------------------------------------
+    def convec(self, u, v, w, dudy, dudz, dvdx, dvdz, dwdx, dwdy, RHSx, RHSy, RHSz):
+        s = self.dims.shape
+        ins = [_addr(a, s) for a in (u, v, w, dudy, dudz, dvdx, dvdz, dwdx, dwdy)]
+        outs = [_addr(a, s, True) for a in (RHSx, RHSy, RHSz)]
+        self._ck(self.lib.convec(self._ctx, *ins, *outs), "convec")
+        return RHSx, RHSy, RHSz
+
+    def press_stag_array(self, u, v, w, divtz, dt, tadv1, p, dpdx, dpdy, dpdz):
+        s = self.dims.shape
+        self._ck(self.lib.press_stag_array(self._ctx, _addr(u, s), _addr(v, s), _addr(w, s), _addr(divtz, s),
+                                           float(dt), float(tadv1), _addr(p, s, True), _addr(dpdx, s, True),
+                                           _addr(dpdy, s, True), _addr(dpdz, s, True)), "press_stag_array")
+        return p, dpdx, dpdy, dpdz
+
+    def tridag_array(self, a, b, c, r, u):
+        n = r.shape[0]
+        self._ck(self.lib.tridag_array(self._ctx, _addr(a), _addr(b), _addr(c), _addr(r), _addr(u, writable=True), n),
+                 "tridag_array")
+        return u
+
+    # -- device-resident state ------------------------------------------------------------------
+    def upload(self, name, host):
+        self._ck(self.lib.upload(self._ctx, FIELD_IDS[name], _addr(host, self.dims.shape)), "upload")
+
+    def download(self, name, out=None):
+        out = self.empty() if out is None else out
+        self._ck(self.lib.download(self._ctx, FIELD_IDS[name], _addr(out, self.dims.shape, True)), "download")
+        return out
+
+    def field_ptr(self, name) -> int:
+        p = self.lib.field_ptr(self._ctx, FIELD_IDS[name])
+        if not p:
+            raise LibraryError("field_ptr: " + self.lib.error(self._ctx))
+        return int(p)
+
+    def step(self, dt, tadv1=1.5, tadv2=-0.5, first_step=False, mode=0, mean_p_force_x=0.0,
+             mean_p_force_y=0.0, ubot=0.0, utop=0.0, nu=0.0):
+        sp = StepParams(dt, tadv1, tadv2, mean_p_force_x, mean_p_force_y, ubot, utop, nu, int(first_step), int(mode))
+        self._ck(self.lib.step(self._ctx, C.byref(sp)), "step")
+
+    def max_cfl(self, dt):
+        v = C.c_double()
+        self._ck(self.lib.max_cfl(self._ctx, float(dt), C.byref(v)), "max_cfl")
+        return v.value
+
+    def rmsdiv(self):
+        v = C.c_double()
+        self._ck(self.lib.rmsdiv(self._ctx, C.byref(v)), "rmsdiv")
+        return v.value
+
+    # -- multi-GPU ---------------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        if self.lib.comm_unique_id(buf):
+            raise LibraryError("comm_unique_id: " + self.lib.error(None))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.lib.comm_init(self._ctx, buf), "comm_init")
+
+    def sync_real_array(self, var, isync=3):
+        self._ck(self.lib.sync_real_array(self._ctx, _addr(var, self.dims.shape, True), int(isync)), "sync_real_array")
+        return var

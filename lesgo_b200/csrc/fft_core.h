@@ -1,0 +1,348 @@
+// fft_core.h -- FP64 radix-2/3/4/5/6/8/10/12/16 Stockham building blocks.
+//
+// Replaces the FFTW plans of the reference (fft.f90:114-121).  Everything here is
+// host/device so the same code runs on sm_100a and in the CPU kernel-logic emulator.
+//
+// A length-N complex FFT is a sequence of up to four Stockham autosort stages with
+// radices R1*R2*R3*R4 = N.  Stage s (radix R, Ns = product of earlier radices) has
+// N/R work items j:   v[r] = in[j + r*N/R] * W_N^{(j % Ns) * r * N/(Ns*R)}
+//                      v    = DFT_R(v)
+//                      out[(j/Ns)*Ns*R + (j%Ns) + r*Ns] = v[r]
+// so reads are always unit-stride in j (coalesced from global memory in the first
+// stage, conflict-free from shared memory later), the output of the last stage is in
+// natural order, and its writes are again unit-stride in j.  The inverse transform
+// uses the same code on (im, re)-swapped data, i.e. conjugated twiddles.
+#pragma once
+#include "portable.h"
+
+namespace lg {
+
+typedef double2 cplx;
+
+LG_HD cplx cmul(cplx a, cplx b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+LG_HD cplx cmulc(cplx a, cplx b) {   // a * conj(b)
+    return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
+}
+LG_HD cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+LG_HD cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+LG_HD cplx cswap(cplx a) { return make_double2(a.y, a.x); }
+LG_HD cplx cmul_mi(cplx a) { return make_double2(a.y, -a.x); }   // a * (-i)
+LG_HD cplx cmul_pi(cplx a) { return make_double2(-a.y, a.x); }   // a * (+i)
+LG_HD cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+
+// ---------------------------------------------------------------------------------
+// Forward (sign -1) small DFTs on registers.
+// ---------------------------------------------------------------------------------
+template <int R> struct Dft;
+
+template <> struct Dft<1> { static LG_HD void run(cplx*) {} };
+
+template <> struct Dft<2> {
+    static LG_HD void run(cplx* v) {
+        cplx a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <> struct Dft<3> {
+    static LG_HD void run(cplx* v) {
+        const double s = 0.86602540378443864676;   // sqrt(3)/2
+        cplx t1 = cadd(v[1], v[2]);
+        cplx t2 = make_double2(fma(-0.5, t1.x, v[0].x), fma(-0.5, t1.y, v[0].y));
+        cplx d = csub(v[1], v[2]);
+        cplx t3 = make_double2(s * d.y, -s * d.x);   // -i * s * d
+        v[0] = cadd(v[0], t1);
+        v[1] = cadd(t2, t3);
+        v[2] = csub(t2, t3);
+    }
+};
+
+template <> struct Dft<4> {
+    static LG_HD void run(cplx* v) {
+        cplx t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        cplx t2 = cadd(v[1], v[3]), t3 = cmul_mi(csub(v[1], v[3]));
+        v[0] = cadd(t0, t2);
+        v[1] = cadd(t1, t3);
+        v[2] = csub(t0, t2);
+        v[3] = csub(t1, t3);
+    }
+};
+
+template <> struct Dft<5> {
+    static LG_HD void run(cplx* v) {
+        const double c1 = 0.30901699437494742410;    // cos(2pi/5)
+        const double c2 = -0.80901699437494742410;   // cos(4pi/5)
+        const double s1 = 0.95105651629515357212;    // sin(2pi/5)
+        const double s2 = 0.58778525229247312917;    // sin(4pi/5)
+        cplx a14 = cadd(v[1], v[4]), d14 = csub(v[1], v[4]);
+        cplx a23 = cadd(v[2], v[3]), d23 = csub(v[2], v[3]);
+        cplx x0 = v[0];
+        cplx p1 = make_double2(fma(c1, a14.x, fma(c2, a23.x, x0.x)), fma(c1, a14.y, fma(c2, a23.y, x0.y)));
+        cplx p2 = make_double2(fma(c2, a14.x, fma(c1, a23.x, x0.x)), fma(c2, a14.y, fma(c1, a23.y, x0.y)));
+        // q = -i * (s1*d14 + s2*d23), r = -i * (s2*d14 - s1*d23)
+        cplx u1 = make_double2(fma(s1, d14.x, s2 * d23.x), fma(s1, d14.y, s2 * d23.y));
+        cplx u2 = make_double2(fma(s2, d14.x, -s1 * d23.x), fma(s2, d14.y, -s1 * d23.y));
+        cplx q1 = cmul_mi(u1), q2 = cmul_mi(u2);
+        v[0] = cadd(x0, cadd(a14, a23));
+        v[1] = cadd(p1, q1);
+        v[4] = csub(p1, q1);
+        v[2] = cadd(p2, q2);
+        v[3] = csub(p2, q2);
+    }
+};
+
+template <> struct Dft<8> {
+    static LG_HD void run(cplx* v) {
+        const double h = 0.70710678118654752440;
+        // even / odd 4-point DFTs (decimation in time)
+        cplx e[4] = {v[0], v[2], v[4], v[6]};
+        cplx o[4] = {v[1], v[3], v[5], v[7]};
+        Dft<4>::run(e);
+        Dft<4>::run(o);
+        // twiddles W8^k, k=0..3: 1, (1-i)h, -i, (-1-i)h
+        cplx o1 = make_double2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
+        cplx o2 = cmul_mi(o[2]);
+        cplx o3 = make_double2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+        v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+        v[1] = cadd(e[1], o1);   v[5] = csub(e[1], o1);
+        v[2] = cadd(e[2], o2);   v[6] = csub(e[2], o2);
+        v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
+    }
+};
+
+template <> struct Dft<16> {
+    static LG_HD void run(cplx* v) {
+        // 4 x 4 Cooley-Tukey: n = 4*n1 + n2, k = k1 + 4*k2
+        const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;   // cos,sin(pi/8)
+        const double h = 0.70710678118654752440;
+        cplx t[4][4];
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+            cplx u[4] = {v[n2], v[4 + n2], v[8 + n2], v[12 + n2]};
+            Dft<4>::run(u);
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1) t[n2][k1] = u[k1];
+        }
+        // twiddle W16^{n2*k1}
+        t[1][1] = cmul(t[1][1], make_double2(c1, -s1));
+        t[1][2] = cmul(t[1][2], make_double2(h, -h));
+        t[1][3] = cmul(t[1][3], make_double2(s1, -c1));
+        t[2][1] = cmul(t[2][1], make_double2(h, -h));
+        t[2][2] = cmul_mi(t[2][2]);
+        t[2][3] = cmul(t[2][3], make_double2(-h, -h));
+        t[3][1] = cmul(t[3][1], make_double2(s1, -c1));
+        t[3][2] = cmul(t[3][2], make_double2(-h, -h));
+        t[3][3] = cmul(t[3][3], make_double2(-c1, s1));
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            cplx u[4] = {t[0][k1], t[1][k1], t[2][k1], t[3][k1]};
+            Dft<4>::run(u);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = u[k2];
+        }
+    }
+};
+
+// Good-Thomas prime-factor composition for coprime N1, N2 (no twiddles):
+// input n = (N2*n1 + N1*n2) mod N, output k with k = k1 (mod N1), k = k2 (mod N2).
+template <int N1, int N2> struct DftPfa {
+    static constexpr int N = N1 * N2;
+    static LG_HD void run(cplx* v) {
+        cplx t[N2][N1];
+#pragma unroll
+        for (int n2 = 0; n2 < N2; ++n2) {
+            cplx u[N1];
+#pragma unroll
+            for (int n1 = 0; n1 < N1; ++n1) u[n1] = v[(N2 * n1 + N1 * n2) % N];
+            Dft<N1>::run(u);
+#pragma unroll
+            for (int k1 = 0; k1 < N1; ++k1) t[n2][k1] = u[k1];
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < N1; ++k1) {
+            cplx u[N2];
+#pragma unroll
+            for (int n2 = 0; n2 < N2; ++n2) u[n2] = t[n2][k1];
+            Dft<N2>::run(u);
+#pragma unroll
+            for (int k2 = 0; k2 < N2; ++k2) v[crt_table(k1, k2)] = u[k2];
+        }
+    }
+    static LG_HD int crt_table(int k1, int k2) {
+        // k = k1*a + k2*b mod N with a = N2*(N2^-1 mod N1), b = N1*(N1^-1 mod N2)
+        return (k1 * A + k2 * B) % N;
+    }
+    static constexpr int inv_mod(int a, int m) {
+        for (int x = 1; x < m; ++x)
+            if ((a * x) % m == 1) return x;
+        return 1;
+    }
+    static constexpr int A = N2 * inv_mod(N2 % N1, N1);
+    static constexpr int B = N1 * inv_mod(N1 % N2, N2);
+};
+template <> struct Dft<6> { static LG_HD void run(cplx* v) { DftPfa<2, 3>::run(v); } };
+template <> struct Dft<10> { static LG_HD void run(cplx* v) { DftPfa<2, 5>::run(v); } };
+template <> struct Dft<12> { static LG_HD void run(cplx* v) { DftPfa<4, 3>::run(v); } };
+
+// ---------------------------------------------------------------------------------
+// Plans.  LG_PLAN(N, R1, R2, R3, R4): radices multiply to N; unused stages are 1.
+// Radices are ordered so that the first and last stage (the ones touching global
+// memory or fused operators) are wide.
+// ---------------------------------------------------------------------------------
+template <int N> struct Plan;
+#define LG_PLAN(N_, A_, B_, C_, D_)                                                  \
+    template <> struct Plan<N_> {                                                    \
+        static constexpr int N = N_, R1 = A_, R2 = B_, R3 = C_, R4 = D_;             \
+        static_assert(A_ * B_ * C_ * D_ == N_, "radices must multiply to N");        \
+    };
+LG_PLAN(8, 8, 1, 1, 1)
+LG_PLAN(12, 12, 1, 1, 1)
+LG_PLAN(16, 4, 4, 1, 1)
+LG_PLAN(24, 6, 4, 1, 1)
+LG_PLAN(32, 8, 4, 1, 1)
+LG_PLAN(36, 6, 6, 1, 1)
+LG_PLAN(40, 10, 4, 1, 1)
+LG_PLAN(48, 8, 6, 1, 1)
+LG_PLAN(60, 10, 6, 1, 1)
+LG_PLAN(64, 8, 8, 1, 1)
+LG_PLAN(72, 12, 6, 1, 1)
+LG_PLAN(80, 10, 8, 1, 1)
+LG_PLAN(96, 12, 8, 1, 1)
+LG_PLAN(120, 12, 10, 1, 1)
+LG_PLAN(128, 8, 4, 4, 1)
+LG_PLAN(144, 12, 12, 1, 1)
+LG_PLAN(160, 10, 4, 4, 1)
+LG_PLAN(192, 8, 6, 4, 1)
+LG_PLAN(240, 10, 6, 4, 1)
+LG_PLAN(256, 8, 8, 4, 1)
+LG_PLAN(288, 8, 6, 6, 1)
+LG_PLAN(320, 8, 10, 4, 1)
+LG_PLAN(384, 8, 8, 6, 1)
+LG_PLAN(480, 10, 8, 6, 1)
+LG_PLAN(512, 8, 8, 8, 1)
+LG_PLAN(576, 8, 12, 6, 1)
+LG_PLAN(640, 8, 10, 8, 1)
+LG_PLAN(768, 8, 12, 8, 1)
+LG_PLAN(1024, 8, 4, 4, 8)
+LG_PLAN(1536, 8, 6, 4, 8)
+#undef LG_PLAN
+
+// max work items of any stage / min: threads per FFT are sized to the widest radix
+template <int N> struct PlanInfo {
+    typedef Plan<N> P;
+    static constexpr int rmax = (P::R1 > P::R2 ? P::R1 : P::R2) > (P::R3 > P::R4 ? P::R3 : P::R4)
+                                    ? (P::R1 > P::R2 ? P::R1 : P::R2)
+                                    : (P::R3 > P::R4 ? P::R3 : P::R4);
+    static constexpr int rmin_nz(int a, int b) { return b == 1 ? a : (a < b ? a : b); }
+    static constexpr int rmin = rmin_nz(rmin_nz(rmin_nz(P::R1, P::R2), P::R3), P::R4);
+    static constexpr int threads = N / rmax;       // threads cooperating on one FFT
+    static constexpr int nstages = 1 + (P::R2 > 1) + (P::R3 > 1) + (P::R4 > 1);
+};
+
+// ---------------------------------------------------------------------------------
+// One Stockham stage for work item j (0 <= j < N/R).
+//   INV = false: forward (sign -1); true: inverse (sign +1, unnormalised).
+//   ld(idx) -> cplx   : fetch logical element idx of the stage input
+//   st(idx, cplx)     : deliver logical element idx of the stage output
+//   W                 : table W_N[m] = exp(-2 pi i m / N), m = 0..N-1
+// ---------------------------------------------------------------------------------
+template <int N, int R, int Ns, bool INV, class Ld, class St>
+LG_HD void fft_stage(int j, const cplx* __restrict__ W, Ld ld, St st) {
+    constexpr int T = N / R;
+    cplx v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = ld(j + r * T);
+    const int k = (Ns == 1) ? 0 : (j % Ns);
+    if (Ns > 1) {
+        constexpr int step = N / (Ns * R);
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            cplx w = W[k * r * step];
+            v[r] = INV ? cmulc(v[r], w) : cmul(v[r], w);
+        }
+    }
+    if (INV) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = cswap(v[r]);
+    }
+    Dft<R>::run(v);
+    if (INV) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = cswap(v[r]);
+    }
+    const int j0 = (Ns == 1) ? j * R : ((j / Ns) * Ns * R + k);
+#pragma unroll
+    for (int r = 0; r < R; ++r) st(j0 + r * Ns, v[r]);
+}
+
+// Shared-memory index padding: one extra cplx every 8 (keeps the radix-strided
+// writes of the first stage conflict-free for 16-byte accesses).
+LG_HD int spad(int i) { return i + (i >> 3); }
+template <int N> struct SmemLen { static constexpr int value = N + (N >> 3) + 1; };
+
+}  // namespace lg
+
+namespace lg {
+// ---------------------------------------------------------------------------------
+// Block-cooperative FFT over a tile of NF independent length-N transforms.
+//   FFT_FASTEST = true : consecutive threads take consecutive transforms (column
+//                        tiles of the y pass: the transform index is the contiguous
+//                        global-memory direction);
+//               = false: consecutive threads take consecutive butterflies of one
+//                        transform (row tiles of the x pass).
+//   ld(f, i)      : element i of transform f for the first stage (global or registers)
+//   st(f, i, v)   : element i of the result (natural order) from the last stage
+//   sidx(f, i)    : shared-memory slot of element i of transform f
+// bufA/bufB are two shared buffers (ping-pong); every thread of the block must call
+// this function (it contains __syncthreads()).
+// ---------------------------------------------------------------------------------
+template <int N, int R, int Ns, bool INV, int NF, bool FFT_FASTEST, class Ld, class St>
+LG_D void tile_stage(const cplx* __restrict__ W, Ld ld, St st) {
+    constexpr int T = N / R;
+    const int nthr = blockDim.x;
+    for (int it = threadIdx.x; it < NF * T; it += nthr) {
+        int f, j;
+        if (FFT_FASTEST) { f = it % NF; j = it / NF; }
+        else             { j = it % T;  f = it / T; }
+        fft_stage<N, R, Ns, INV>(j, W,
+            [&](int i) { return ld(f, i); },
+            [&](int i, cplx v) { st(f, i, v); });
+    }
+}
+
+template <int N, bool INV, int NF, bool FFT_FASTEST, class SIdx, class Ld, class St>
+LG_D void fft_tile(cplx* bufA, cplx* bufB, const cplx* __restrict__ W, SIdx sidx, Ld ld, St st) {
+    typedef Plan<N> P;
+    constexpr int NST = PlanInfo<N>::nstages;
+    auto ldA = [&](int f, int i) { return bufA[sidx(f, i)]; };
+    auto ldB = [&](int f, int i) { return bufB[sidx(f, i)]; };
+    auto stA = [&](int f, int i, cplx v) { bufA[sidx(f, i)] = v; };
+    auto stB = [&](int f, int i, cplx v) { bufB[sidx(f, i)] = v; };
+    if constexpr (NST == 1) {
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST>(W, ld, st);
+    } else if constexpr (NST == 2) {
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST>(W, ld, stA);
+        __syncthreads();
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST>(W, ldA, st);
+    } else if constexpr (NST == 3) {
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST>(W, ld, stA);
+        __syncthreads();
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST>(W, ldA, stB);
+        __syncthreads();
+        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST>(W, ldB, st);
+    } else {
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST>(W, ld, stA);
+        __syncthreads();
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST>(W, ldA, stB);
+        __syncthreads();
+        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST>(W, ldB, stA);
+        __syncthreads();
+        tile_stage<N, P::R4, P::R1 * P::R2 * P::R3, INV, NF, FFT_FASTEST>(W, ldA, st);
+    }
+    __syncthreads();
+}
+
+}  // namespace lg

@@ -1,0 +1,974 @@
+// lesgo_gpu.cu -- context, host-side orchestration and the extern "C" entry points of
+// include/lesgo_gpu.h.  Mirrors, routine by routine, the reference's derivatives.f90,
+// convec.f90, press_stag_array.f90, tridag_array.f90, fft.f90 and the time-loop glue of
+// main.f90:155-344 / forcing.f90:149-244.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lesgo_gpu.h"
+#include "comm.h"
+#include "launch.h"
+
+using namespace lg;
+
+namespace {
+const double kBogus = -1234567890.0;   // param.f90:93
+thread_local std::string g_err;
+
+struct HostDevArg;
+}  // namespace
+
+struct lesgo_gpu_ctx {
+    lesgo_gpu_dims d;
+    int nx, ny, nz, lh, ld, nx2, ny2, lh_big, ld_big, nzt;
+    long plane, plane_big, plane_bi;   // ld*ny, ld_big*ny2, ld*ny2 (big-y intermediate)
+    bool bottom, top;
+    int jzLo;
+    double kxs, kys;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    long launches = 0;
+    // twiddles: W_n[m] = exp(-2 pi i m/n); Wh_n[m] = exp(-2 pi i m/(2n)) for the real<->complex step
+    cplx *Wx = nullptr, *Whx = nullptr, *Wxb = nullptr, *Whxb = nullptr, *Wy = nullptr, *Wyb = nullptr;
+    // scratch
+    double* sa[kMaxFields] = {nullptr};    // small spectra / intermediates, (ld, ny, 0:nz)
+    double* bb[kMaxFields] = {nullptr};    // big-y intermediates, (ld, ny2, 0:nz)
+    double* big[kMaxFields] = {nullptr};   // 3/2-grid physical fields, (ld_big, ny2, 0:nz)
+    double* gam = nullptr;                 // tridiagonal gam(j) table (lh, ny, 0:nzt+1)
+    double* fields[LG_NFIELDS] = {nullptr};
+    std::vector<double*> staging;          // device staging for host-pointer arguments
+    std::vector<size_t> staging_bytes;
+    double* red_dev = nullptr;             // reductions
+    double* red_host = nullptr;
+    lg::Comm* comm = nullptr;
+    std::vector<void*> allocs;
+    // optional per-launch timing (lesgo_gpu_profile): CUDA events around every launch
+    bool prof = false;
+    struct ProfRec { const char* label; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+
+    Lay lay() const { return Lay{plane, ld}; }
+    Lay lay_big() const { return Lay{plane_big, ld_big}; }
+    int fail(const std::string& m) { err = m; g_err = m; return 1; }
+};
+
+namespace {
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess)                                                        \
+            return c->fail(std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+#ifdef LESGO_EMUL
+struct ProfScope { ProfScope(lesgo_gpu_ctx*, const char*) {} };
+#else
+struct ProfScope {
+    lesgo_gpu_ctx* c;
+    size_t idx = 0;
+    bool on;
+    ProfScope(lesgo_gpu_ctx* c_, const char* label) : c(c_), on(c_->prof) {
+        if (!on) return;
+        lesgo_gpu_ctx::ProfRec r;
+        r.label = label;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, c->stream);
+        idx = c->prof_recs.size();
+        c->prof_recs.push_back(r);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(c->prof_recs[idx].b, c->stream); }
+};
+#endif
+
+int dev_alloc(lesgo_gpu_ctx* c, double** p, size_t ndoubles) {
+    if (*p) return 0;
+    void* q = nullptr;
+    CK(cudaMalloc(&q, ndoubles * sizeof(double)));
+    CK(cudaMemsetAsync(q, 0, ndoubles * sizeof(double), c->stream));
+    c->allocs.push_back(q);
+    *p = static_cast<double*>(q);
+    return 0;
+}
+
+int make_twiddle(lesgo_gpu_ctx* c, cplx** dst, int n, int count, int denom) {
+    std::vector<cplx> h(count);
+    for (int m = 0; m < count; ++m) {
+        long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)denom;
+        h[m] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+    (void)n;
+    void* q = nullptr;
+    CK(cudaMalloc(&q, sizeof(cplx) * count));
+    CK(cudaMemcpy(q, h.data(), sizeof(cplx) * count, cudaMemcpyHostToDevice));
+    c->allocs.push_back(q);
+    *dst = static_cast<cplx*>(q);
+    return 0;
+}
+
+int need_small(lesgo_gpu_ctx* c, int n) {
+    for (int i = 0; i < n; ++i)
+        if (dev_alloc(c, &c->sa[i], size_t(c->plane) * (c->nz + 1))) return 1;
+    return 0;
+}
+int need_big(lesgo_gpu_ctx* c, int n) {
+    for (int i = 0; i < n; ++i) {
+        if (dev_alloc(c, &c->bb[i], size_t(c->plane_bi) * (c->nz + 1))) return 1;
+        if (dev_alloc(c, &c->big[i], size_t(c->plane_big) * (c->nz + 1))) return 1;
+    }
+    return 0;
+}
+
+// ---- argument staging: host pointers are mirrored in device buffers --------------------
+bool is_device_ptr(const void* p) {
+#ifdef LESGO_EMUL
+    (void)p;
+    return true;
+#else
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+#endif
+}
+
+struct Staged {
+    lesgo_gpu_ctx* c;
+    struct Item { double* host; double* dev; size_t bytes; bool out; };
+    std::vector<Item> items;
+    size_t next_slot = 0;
+    explicit Staged(lesgo_gpu_ctx* c_) : c(c_) {}
+    // returns the device pointer to use for user pointer p holding `n` doubles
+    double* in(const double* p, size_t n, bool copy_in, bool copy_out) {
+        if (!p) return nullptr;
+        if (is_device_ptr(p)) return const_cast<double*>(p);
+        // same host array passed twice (in and out) shares one slot
+        for (auto& it : items)
+            if (it.host == p) { it.out = it.out || copy_out; return it.dev; }
+        size_t slot = next_slot++;
+        if (c->staging.size() <= slot) { c->staging.push_back(nullptr); c->staging_bytes.push_back(0); }
+        if (c->staging_bytes[slot] < n * sizeof(double)) {
+            if (c->staging[slot]) cudaFree(c->staging[slot]);
+            void* q = nullptr;
+            if (cudaMalloc(&q, n * sizeof(double)) != cudaSuccess) { c->fail("cudaMalloc staging"); return nullptr; }
+            c->staging[slot] = static_cast<double*>(q);
+            c->staging_bytes[slot] = n * sizeof(double);
+        }
+        double* d = c->staging[slot];
+        if (copy_in) cudaMemcpyAsync(d, p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        items.push_back(Item{const_cast<double*>(p), d, n * sizeof(double), copy_out});
+        return d;
+    }
+    int finish() {
+        bool any = false;
+        for (auto& it : items)
+            if (it.out) { cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, c->stream); any = true; }
+        if (any || !items.empty()) {
+            cudaError_t e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) return c->fail(std::string("stream sync: ") + cudaGetErrorString(e));
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return c->fail(std::string("kernel: ") + cudaGetErrorString(e));
+        return 0;
+    }
+};
+
+// ---- pass wrappers ------------------------------------------------------------------------
+int grid1d(long n) {
+    long b = (n + kBlock - 1) / kBlock;
+    long cap = 148L * 16;
+    return int(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <class Pro>
+int xfwd(lesgo_gpu_ctx* c, bool bigx, const Pro& pro, int nf, double* const* dst, long dplane, int drow,
+         int ncol, int nyrows, int k0, int k1, int write_nyq = 0) {
+    XfOut o;
+    for (int i = 0; i < nf; ++i) o.dst[i] = dst[i];
+    o.plane = dplane; o.row = drow; o.ncol = ncol; o.write_nyq = write_nyq;
+    if (k1 <= k0) return 0;
+    ProfScope ps_(c, bigx ? "xfwd_big" : "xfwd");
+    int rc = launch_xfwd<Pro>(bigx ? c->nx2 : c->nx, pro, nf, o, nyrows, k0, k1 - k0,
+                              bigx ? c->Wxb : c->Wx, bigx ? c->Whxb : c->Whx, c->stream);
+    if (rc) return c->fail("unsupported nx for x-forward pass");
+    c->launches++;
+    return 0;
+}
+
+int xinv(lesgo_gpu_ctx* c, bool bigx, const double* const* src, long splane, int srow, int ncol, int nf,
+         double* const* dst, const Lay& dl, int nyrows, int k0, int k1, int pad = 1) {
+    XiSrc in;
+    EpiStore epi;
+    for (int i = 0; i < nf; ++i) { in.src[i] = src[i]; epi.dst[i] = dst[i]; }
+    in.plane = splane; in.row = srow; in.ncol = ncol;
+    epi.lay = dl; epi.nx = bigx ? c->nx2 : c->nx; epi.pad = pad;
+    if (k1 <= k0) return 0;
+    ProfScope ps_(c, bigx ? "xinv_big" : "xinv");
+    int rc = launch_xinv(bigx ? c->nx2 : c->nx, in, epi, nf, nyrows, k0, k1 - k0,
+                         bigx ? c->Wxb : c->Wx, bigx ? c->Whxb : c->Whx, c->stream);
+    if (rc) return c->fail("unsupported nx for x-inverse pass");
+    c->launches++;
+    return 0;
+}
+
+YArgs yargs(lesgo_gpu_ctx* c, long splane, int srow, long dplane, int drow, int ncols, int k0) {
+    YArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.nout = 1;
+    a.src_plane = splane; a.src_row = srow; a.dst_plane = dplane; a.dst_row = drow;
+    a.ncols = ncols; a.k0 = k0;
+    a.kxs = c->kxs; a.kys = c->kys;
+    a.table = nullptr; a.table_row = 0;
+    a.zero_col = -1; a.keep_nyq_row = 0;
+    return a;
+}
+
+int ypass(lesgo_gpu_ctx* c, int nin, int nout, const YArgs& a, int nf, int k0, int k1) {
+    if (k1 <= k0) return 0;
+    ProfScope ps_(c, nin == nout ? "ypass_deriv" : (nout == 0 ? "ypass_fwd" : (nin == 0 ? "ypass_inv" : (nin < nout ? "ypass_pad" : "ypass_trunc"))));
+    auto W = [&](int n) -> const cplx* { return n == c->ny ? c->Wy : (n == c->ny2 ? c->Wyb : nullptr); };
+    int rc = launch_ypass(nin, nout, a, nf, k1 - k0, nin ? W(nin) : W(nout), nout ? W(nout) : W(nin), c->stream);
+    if (rc) return c->fail("unsupported ny for y pass");
+    c->launches++;
+    return 0;
+}
+
+int fill(lesgo_gpu_ctx* c, double* f, long plane, int k0, int k1, double v) {
+    if (k1 <= k0) return 0;
+    ProfScope ps_(c, "fill");
+    LG_LAUNCH(k_fill, dim3(grid1d(plane * (k1 - k0))), dim3(kBlock), 0, c->stream, f, plane, k0, k1, v);
+    c->launches++;
+    return 0;
+}
+
+int glue(lesgo_gpu_ctx* c, int mode, double* a, const double* b, const double* cc, int nxlim, int k0, int k1,
+         double c0, double c1, double c2) {
+    if (k1 <= k0) return 0;
+    ProfScope ps_(c, "glue");
+    LG_LAUNCH(k_glue, dim3(grid1d(long(c->lh) * c->ny * (k1 - k0))), dim3(kBlock), 0, c->stream, mode, a, b, cc,
+              c->lay(), nxlim, c->ny, k0, k1, c0, c1, c2);
+    c->launches++;
+    return 0;
+}
+
+// ---- derivatives.f90 --------------------------------------------------------------------------
+// which: bit 0 = f itself (filt_da), bit 1 = d/dx, bit 2 = d/dy
+int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx, double* dfdy) {
+    if (need_small(c, 4)) return 1;
+    const int nz = c->nz;
+    ProScale pro;
+    pro.src[0] = f; pro.lay = c->lay(); pro.scale = 1.0 / (double(c->nx) * double(c->ny));
+    double* d0[1] = {c->sa[0]};
+    if (xfwd(c, false, pro, 1, d0, c->plane, c->ld, c->nx / 2, c->ny, 0, nz + 1)) return 1;
+    YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, c->nx / 2, 0);
+    a.fld[0].src = c->sa[0];
+    const double* xs[3];
+    double* xd[3];
+    int n = 0;
+    if (fout) { a.fld[0].out[n] = YOutSpec{c->sa[1 + n], Y_COPY}; xs[n] = c->sa[1 + n]; xd[n] = fout; ++n; }
+    if (dfdx) { a.fld[0].out[n] = YOutSpec{c->sa[1 + n], Y_IKX}; xs[n] = c->sa[1 + n]; xd[n] = dfdx; ++n; }
+    if (dfdy) { a.fld[0].out[n] = YOutSpec{c->sa[1 + n], Y_IKY}; xs[n] = c->sa[1 + n]; xd[n] = dfdy; ++n; }
+    a.nout = n;
+    if (ypass(c, c->ny, c->ny, a, 1, 0, nz + 1)) return 1;
+    return xinv(c, false, xs, c->plane, c->ld, c->nx / 2, n, xd, c->lay(), c->ny, 0, nz + 1);
+}
+
+int ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
+    const int nz = c->nz;
+    {
+        ProfScope ps_(c, "ddz");
+        LG_LAUNCH(k_ddz, dim3(grid1d(long(c->nx / 2) * c->ny * nz)), dim3(kBlock), 0, c->stream, f, dfdz, c->lay(),
+                  c->nx, c->ny, 1, nz + 1, -1, 0, 1.0 / c->d.dz);
+        c->launches++;
+    }
+    fill(c, dfdz, c->plane, 0, 1, kBogus);                           // derivatives.f90:236-238
+    if (c->bottom) fill(c, dfdz, c->plane, 1, 2, kBogus);            // :255-257
+    if (c->top) fill(c, dfdz, c->plane, nz, nz + 1, kBogus);         // :258-260
+    return 0;
+}
+
+int ddz_w(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
+    const int nz = c->nz;
+    {
+        ProfScope ps_(c, "ddz");
+        LG_LAUNCH(k_ddz, dim3(grid1d(long(c->nx / 2) * c->ny * nz)), dim3(kBlock), 0, c->stream, f, dfdz, c->lay(),
+                  c->nx, c->ny, 0, nz, 0, 1, 1.0 / c->d.dz);
+        c->launches++;
+    }
+    if (c->bottom) fill(c, dfdz, c->plane, 0, 1, kBogus);            // :303-305
+    fill(c, dfdz, c->plane, nz, nz + 1, kBogus);                     // :308
+    return 0;
+}
+
+// ---- convec.f90 --------------------------------------------------------------------------------
+int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, const double* dudy,
+           const double* dudz, const double* dvdx, const double* dvdz, const double* dwdx,
+           const double* dwdy, double* RHSx, double* RHSy, double* RHSz) {
+    if (need_small(c, 6) || need_big(c, 6)) return 1;
+    const int nz = c->nz, nxh = c->nx / 2;
+    const double cs = 1.0 / (double(c->nx) * double(c->ny));
+    // (1) u, v, w (planes 0..nz) and the vorticity (1..nz) to half spectra   convec.f90:73-82, 97-158
+    ProScale ps;
+    ps.src[0] = u; ps.src[1] = v; ps.src[2] = w; ps.lay = c->lay(); ps.scale = cs;
+    if (xfwd(c, false, ps, 3, c->sa, c->plane, c->ld, nxh, c->ny, 0, nz + 1)) return 1;
+    ProVort pv;
+    pv.dudy = dudy; pv.dudz = dudz; pv.dvdx = dvdx; pv.dvdz = dvdz; pv.dwdx = dwdx; pv.dwdy = dwdy;
+    pv.lay = c->lay(); pv.scale = cs; pv.nz = nz; pv.bottom = c->bottom; pv.top = c->top;
+    pv.lbc_mom = c->d.lbc_mom; pv.ubc_mom = c->d.ubc_mom;
+    if (xfwd(c, false, pv, 3, c->sa + 3, c->plane, c->ld, nxh, c->ny, 1, nz + 1)) return 1;
+    // (2) y forward, padd (fft.f90:43-71), y inverse on the 3/2 grid
+    {
+        YArgs a = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, 0);
+        for (int i = 0; i < 3; ++i) { a.fld[i].src = c->sa[i]; a.fld[i].out[0] = YOutSpec{c->bb[i], Y_COPY}; }
+        if (ypass(c, c->ny, c->ny2, a, 3, 0, nz + 1)) return 1;
+        YArgs b = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, 1);
+        for (int i = 0; i < 3; ++i) { b.fld[i].src = c->sa[3 + i]; b.fld[i].out[0] = YOutSpec{c->bb[3 + i], Y_COPY}; }
+        if (ypass(c, c->ny, c->ny2, b, 3, 1, nz + 1)) return 1;
+    }
+    // (3) x inverse on the 3/2 grid: only kx < nx/2 carries data                 :90-92, 165-167
+    if (xinv(c, true, c->bb, c->plane_bi, c->ld, nxh, 3, c->big, c->lay_big(), c->ny2, 0, nz + 1)) return 1;
+    if (xinv(c, true, c->bb + 3, c->plane_bi, c->ld, nxh, 3, c->big + 3, c->lay_big(), c->ny2, 1, nz + 1)) return 1;
+    // (4) products fused into the x forward pass on the 3/2 grid                 :172-305
+    ProConvec pc;
+    pc.u = c->big[0]; pc.v = c->big[1]; pc.w = c->big[2]; pc.o1 = c->big[3]; pc.o2 = c->big[4]; pc.o3 = c->big[5];
+    pc.lay = c->lay_big(); pc.scale = 1.0 / (double(c->nx2) * double(c->ny2));
+    pc.nz = nz; pc.bottom = c->bottom; pc.top = c->top; pc.jzLo = c->jzLo;
+    if (xfwd(c, true, pc, 3, c->bb, c->plane_bi, c->ld, nxh, c->ny2, 1, nz + 1)) return 1;
+    // (5) y forward on the 3/2 grid, unpadd (fft.f90:74-99), y inverse            :206-213
+    {
+        YArgs a = yargs(c, c->plane_bi, c->ld, c->plane, c->ld, nxh, 1);
+        for (int i = 0; i < 3; ++i) { a.fld[i].src = c->bb[i]; a.fld[i].out[0] = YOutSpec{c->sa[i], Y_COPY}; }
+        if (ypass(c, c->ny2, c->ny, a, 3, 1, nz + 1)) return 1;
+    }
+    // (6) x inverse -> RHS
+    double* out[3] = {RHSx, RHSy, RHSz};
+    if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, 1, nz + 1)) return 1;
+    // :319-332
+    fill(c, RHSx, c->plane, 0, 1, kBogus); fill(c, RHSy, c->plane, 0, 1, kBogus); fill(c, RHSz, c->plane, 0, 1, kBogus);
+    fill(c, RHSx, c->plane, nz, nz + 1, kBogus); fill(c, RHSy, c->plane, nz, nz + 1, kBogus);
+    if (!c->top) fill(c, RHSz, c->plane, nz, nz + 1, kBogus);
+    return 0;
+}
+
+// ---- press_stag_array.f90 ------------------------------------------------------------------------
+int tridag_setup(lesgo_gpu_ctx* c, TriGeom& g) {
+    g.lh = c->lh; g.ny = c->ny; g.nzt = c->nzt; g.row = c->ld; g.plane = c->plane;
+    g.gplane = long(c->lh) * c->ny; g.kxs = c->kxs; g.kys = c->kys; g.dz = c->d.dz;
+    if (!c->gam) {
+        if (dev_alloc(c, &c->gam, size_t(g.gplane) * (c->nzt + 2))) return 1;
+        const int nm = (c->lh - 1) * c->ny;
+        LG_LAUNCH(k_tridag_setup, dim3((nm + 127) / 128), dim3(128), 0, c->stream, g, c->gam);
+        c->launches++;
+    }
+    return 0;
+}
+
+int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, const double* divtz, double dt,
+          double tadv1, double* p, double* dpdx, double* dpdy, double* dpdz) {
+    if (c->d.nproc > 1) return c->fail("press_stag_array: nproc > 1 needs lesgo_gpu_comm_init (multi-GPU path)");
+    if (need_small(c, 6)) return 1;
+    const int nz = c->nz, nxh = c->nx / 2;
+    const double cst = 1.0 / (double(c->nx) * double(c->ny));
+    const double cst2 = cst / tadv1 / dt;                          // press_stag_array.f90:51-52
+    // (1) x forward of u*/(tadv1 dt): planes 1..nz-1, + w(nz) on the top rank      :77-103
+    ProScale ps;
+    ps.src[0] = u; ps.src[1] = v; ps.src[2] = w; ps.lay = c->lay(); ps.scale = cst2;
+    if (xfwd(c, false, ps, 3, c->sa, c->plane, c->ld, nxh, c->ny, 1, nz)) return 1;
+    if (c->top) {
+        ProScale pw; pw.src[0] = w; pw.lay = c->lay(); pw.scale = cst2;
+        double* d[1] = {c->sa[2]};
+        if (xfwd(c, false, pw, 1, d, c->plane, c->ld, nxh, c->ny, nz, nz + 1)) return 1;
+    }
+    // boundary planes from divtz                                                   :114-126
+    ProScale pd; pd.src[0] = divtz; pd.lay = c->lay(); pd.scale = cst;
+    double* d3[1] = {c->sa[3]};
+    if (c->bottom && xfwd(c, false, pd, 1, d3, c->plane, c->ld, nxh, c->ny, 1, 2)) return 1;
+    if (c->top && xfwd(c, false, pd, 1, d3, c->plane, c->ld, nxh, c->ny, nz, nz + 1)) return 1;
+    // (2) y forward in place, Nyquist row zeroed                                   :129-146
+    {
+        YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, 1);
+        for (int i = 0; i < 3; ++i) { a.fld[i].src = c->sa[i]; a.fld[i].out[0] = YOutSpec{c->sa[i], Y_COPY}; }
+        if (ypass(c, c->ny, 0, a, 3, 1, nz)) return 1;
+        YArgs b = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, nz);
+        b.fld[0].src = c->sa[2]; b.fld[0].out[0] = YOutSpec{c->sa[2], Y_COPY};
+        b.fld[1].src = c->sa[3]; b.fld[1].out[0] = YOutSpec{c->sa[3], Y_COPY};
+        if (c->top && ypass(c, c->ny, 0, b, 2, nz, nz + 1)) return 1;
+        YArgs e = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, 1);
+        e.fld[0].src = c->sa[3]; e.fld[0].out[0] = YOutSpec{c->sa[3], Y_COPY};
+        if (c->bottom && ypass(c, c->ny, 0, e, 1, 1, 2)) return 1;
+    }
+    // (3) tridiagonal solve with fused right-hand side + k=0 chain                 :149-239
+    TriGeom g;
+    if (tridag_setup(c, g)) return 1;
+    {
+        const int nm = (c->lh - 1) * c->ny;
+        ProfScope ps_(c, "tridag");
+        LG_LAUNCH(k_tridag_fused, dim3((nm + 127) / 128), dim3(128), 0, c->stream, g, c->sa[0], c->sa[1],
+                  c->sa[2], c->sa[3] + c->plane, c->sa[3] + c->plane * nz, c->gam, c->sa[4]);
+        c->launches++;
+    }
+    // (4) y inverse of p, i kx p, i ky p (oddballs dropped), x inverse              :248-273
+    {
+        YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, 0);
+        a.fld[0].src = c->sa[4];
+        a.fld[0].out[0] = YOutSpec{c->sa[0], Y_COPY};
+        a.fld[0].out[1] = YOutSpec{c->sa[1], Y_IKX};
+        a.fld[0].out[2] = YOutSpec{c->sa[2], Y_IKY};
+        a.nout = 3;
+        if (ypass(c, 0, c->ny, a, 1, 0, nz + 1)) return 1;
+        const double* s0[1] = {c->sa[0]};
+        double* o0[1] = {p};
+        if (xinv(c, false, s0, c->plane, c->ld, nxh, 1, o0, c->lay(), c->ny, 0, c->top ? nz + 1 : nz)) return 1;
+        const double* s1[2] = {c->sa[1], c->sa[2]};
+        double* o1[2] = {dpdx, dpdy};
+        if (xinv(c, false, s1, c->plane, c->ld, nxh, 2, o1, c->lay(), c->ny, 1, nz)) return 1;
+    }
+    // (5) dpdz                                                                       :276-288
+    {
+        const int k1 = c->top ? nz + 1 : nz;
+        ProfScope ps_(c, "dpdz");
+        LG_LAUNCH(k_dpdz, dim3(grid1d(long(nxh) * c->ny * (k1 - 1))), dim3(kBlock), 0, c->stream, p, dpdz, c->lay(),
+                  c->nx, c->ny, 1, k1, c->d.dz);
+        c->launches++;
+    }
+    fill(c, dpdx, c->plane, nz, nz + 1, kBogus);
+    fill(c, dpdy, c->plane, nz, nz + 1, kBogus);
+    if (!c->top) { fill(c, p, c->plane, nz, nz + 1, kBogus); fill(c, dpdz, c->plane, nz, nz + 1, kBogus); }
+    return 0;
+}
+
+double* field(lesgo_gpu_ctx* c, int id) {
+    if (id < 0 || id >= LG_NFIELDS) return nullptr;
+    if (!c->fields[id]) dev_alloc(c, &c->fields[id], size_t(c->plane) * (c->nz + 1));
+    return c->fields[id];
+}
+
+// ---- one timestep on the resident fields: main.f90:155-344 ----------------------------------------
+int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
+    const int nz = c->nz;
+    double* F[LG_NFIELDS];
+    for (int i = 0; i < LG_NFIELDS; ++i) {
+        F[i] = field(c, i);
+        if (!F[i]) return 1;
+    }
+    if (sp->mode != 0) return c->fail("lesgo_gpu_step: mode 1 (wallstress/sgs/divstress on device) not built yet");
+    const size_t fb = size_t(c->plane) * (nz + 1) * sizeof(double);
+    // :155-157
+    CK(cudaMemcpyAsync(F[LG_RHSX_F], F[LG_RHSX], fb, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(F[LG_RHSY_F], F[LG_RHSY], fb, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(F[LG_RHSZ_F], F[LG_RHSZ], fb, cudaMemcpyDeviceToDevice, c->stream));
+    // :161-172
+    if (spectral_deriv(c, F[LG_U], F[LG_U], F[LG_DUDX], F[LG_DUDY])) return 1;
+    if (spectral_deriv(c, F[LG_V], F[LG_V], F[LG_DVDX], F[LG_DVDY])) return 1;
+    if (spectral_deriv(c, F[LG_W], F[LG_W], F[LG_DWDX], F[LG_DWDY])) return 1;
+    ddz_uv(c, F[LG_U], F[LG_DUDZ]);
+    ddz_uv(c, F[LG_V], F[LG_DVDZ]);
+    ddz_w(c, F[LG_W], F[LG_DWDZ]);
+    // wallstress (:182-184), DNS / stress-free walls: dudz, dvdz on the wall planes
+    {
+        const double h = 0.5 * c->d.dz;
+        if (c->bottom) {
+            if (c->d.lbc_mom == 0) { fill(c, F[LG_DUDZ], c->plane, 1, 2, 0.0); fill(c, F[LG_DVDZ], c->plane, 1, 2, 0.0); }
+            else if (c->d.lbc_mom == 1) {
+                LG_LAUNCH(k_wall_dns, dim3(grid1d(long(c->nx / 2) * c->ny)), dim3(kBlock), 0, c->stream, F[LG_U], F[LG_V],
+                          F[LG_DUDZ], F[LG_DVDZ], c->lay(), c->nx, c->ny, 1, 1, sp->ubot, 1.0, h);
+                c->launches++;
+            } else return c->fail("lesgo_gpu_step: lbc_mom > 1 (wall models) not on device yet");
+        }
+        if (c->top) {
+            if (c->d.ubc_mom == 0) { fill(c, F[LG_DUDZ], c->plane, nz, nz + 1, 0.0); fill(c, F[LG_DVDZ], c->plane, nz, nz + 1, 0.0); }
+            else if (c->d.ubc_mom == 1) {
+                LG_LAUNCH(k_wall_dns, dim3(grid1d(long(c->nx / 2) * c->ny)), dim3(kBlock), 0, c->stream, F[LG_U], F[LG_V],
+                          F[LG_DUDZ], F[LG_DVDZ], c->lay(), c->nx, c->ny, nz - 1, nz, sp->utop, -1.0, h);
+                c->launches++;
+            } else return c->fail("lesgo_gpu_step: ubc_mom > 1 (wall models) not on device yet");
+        }
+    }
+    // :207
+    if (convec(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DUDY], F[LG_DUDZ], F[LG_DVDX], F[LG_DVDZ], F[LG_DWDX],
+               F[LG_DWDY], F[LG_RHSX], F[LG_RHSY], F[LG_RHSZ])) return 1;
+    // :211-214, 229-232
+    glue(c, G_RHS_ASSEMBLE, F[LG_RHSX], F[LG_DIVTX], nullptr, c->ld, 1, nz, sp->mean_p_force_x, 0, 0);
+    glue(c, G_RHS_ASSEMBLE, F[LG_RHSY], F[LG_DIVTY], nullptr, c->ld, 1, nz, sp->mean_p_force_y, 0, 0);
+    glue(c, G_RHS_ASSEMBLE, F[LG_RHSZ], F[LG_DIVTZ], nullptr, c->ld, 1, c->top ? nz + 1 : nz, 0.0, 0, 0);
+    // :273-280
+    if (sp->first_step) {
+        CK(cudaMemcpyAsync(F[LG_RHSX_F], F[LG_RHSX], fb, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(F[LG_RHSY_F], F[LG_RHSY], fb, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(F[LG_RHSZ_F], F[LG_RHSZ], fb, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    // :287-296
+    glue(c, G_AB2, F[LG_U], F[LG_RHSX], F[LG_RHSX_F], c->ld, 1, nz, sp->dt, sp->tadv1, sp->tadv2);
+    glue(c, G_AB2, F[LG_V], F[LG_RHSY], F[LG_RHSY_F], c->ld, 1, nz, sp->dt, sp->tadv1, sp->tadv2);
+    glue(c, G_AB2, F[LG_W], F[LG_RHSZ], F[LG_RHSZ_F], c->ld, 1, c->top ? nz + 1 : nz, sp->dt, sp->tadv1, sp->tadv2);
+    // :299-308
+    fill(c, F[LG_U], c->plane, 0, 1, kBogus); fill(c, F[LG_V], c->plane, 0, 1, kBogus); fill(c, F[LG_W], c->plane, 0, 1, kBogus);
+    fill(c, F[LG_U], c->plane, nz, nz + 1, kBogus); fill(c, F[LG_V], c->plane, nz, nz + 1, kBogus);
+    if (!c->top) fill(c, F[LG_W], c->plane, nz, nz + 1, kBogus);
+    // :317
+    if (press(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DIVTZ], sp->dt, sp->tadv1, F[LG_P], F[LG_DPDX], F[LG_DPDY],
+              F[LG_DPDZ])) return 1;
+    // :321-326
+    glue(c, G_SUB, F[LG_RHSX], F[LG_DPDX], nullptr, c->ld, 1, nz, 0, 0, 0);
+    glue(c, G_SUB, F[LG_RHSY], F[LG_DPDY], nullptr, c->ld, 1, nz, 0, 0, 0);
+    glue(c, G_SUB, F[LG_RHSZ], F[LG_DPDZ], nullptr, c->ld, 1, c->top ? nz + 1 : nz, 0, 0, 0);
+    // project, forcing.f90:149-244
+    glue(c, G_PROJECT, F[LG_U], F[LG_DPDX], nullptr, c->nx, 1, nz, sp->dt, sp->tadv1, 0);
+    glue(c, G_PROJECT, F[LG_V], F[LG_DPDY], nullptr, c->nx, 1, nz, sp->dt, sp->tadv1, 0);
+    glue(c, G_PROJECT, F[LG_W], F[LG_DPDZ], nullptr, c->nx, c->bottom ? 2 : 1, nz, sp->dt, sp->tadv1, 0);
+    if (c->comm) {
+        if (c->comm->sync_planes(F[LG_U], c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
+        if (c->comm->sync_planes(F[LG_V], c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
+        if (c->comm->sync_planes(F[LG_W], c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
+    }
+    if (c->top) {
+        if (c->d.ubc_mom == 0) {
+            CK(cudaMemcpyAsync(F[LG_U] + c->plane * nz, F[LG_U] + c->plane * (nz - 1), c->plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            CK(cudaMemcpyAsync(F[LG_V] + c->plane * nz, F[LG_V] + c->plane * (nz - 1), c->plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        }
+        fill(c, F[LG_W], c->plane, nz, nz + 1, 0.0);
+    }
+    if (c->bottom) fill(c, F[LG_W], c->plane, 1, 2, 0.0);
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* lesgo_gpu_last_error(const lesgo_gpu_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
+
+int lesgo_gpu_create(const lesgo_gpu_dims* d, lesgo_gpu_ctx** out) {
+    if (!d || !out) { g_err = "null argument"; return 1; }
+    *out = nullptr;
+    lesgo_gpu_ctx* c = new lesgo_gpu_ctx;
+    c->d = *d;
+    auto bail = [&](const std::string& m) { g_err = m; delete c; return 1; };
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return bail("no CUDA device: liblesgo_cuda has no CPU fallback");
+    if (d->device >= 0) {
+        if (d->device >= ndev) return bail("device ordinal out of range");
+        if (cudaSetDevice(d->device) != cudaSuccess) return bail("cudaSetDevice failed");
+    }
+    if (d->nx < 16 || d->ny < 16 || d->nz < 2 || (d->nx % 4) || (d->ny % 4)) return bail("bad grid size");
+    if (!size_supported(d->nx) || !size_supported(d->ny)) return bail("nx/ny not in the supported FFT size list (sizes.h)");
+    if (d->nproc < 1 || d->coord < 0 || d->coord >= d->nproc) return bail("bad nproc/coord");
+    if (d->nz_tot != (d->nz - 1) * d->nproc + 1) return bail("nz_tot must equal (nz-1)*nproc+1 (input_util.f90:200)");
+    c->nx = d->nx; c->ny = d->ny; c->nz = d->nz; c->nzt = d->nz_tot;
+    c->lh = c->nx / 2 + 1; c->ld = 2 * c->lh;
+    c->nx2 = 3 * c->nx / 2; c->ny2 = 3 * c->ny / 2;
+    c->lh_big = c->nx2 / 2 + 1; c->ld_big = 2 * c->lh_big;
+    c->plane = long(c->ld) * c->ny; c->plane_big = long(c->ld_big) * c->ny2; c->plane_bi = long(c->ld) * c->ny2;
+    c->bottom = d->coord == 0; c->top = d->coord == d->nproc - 1;
+    c->jzLo = d->sgs ? 2 : 1;
+    const double pi = 3.14159265358979323846;   // param.f90 pi
+    c->kxs = 2.0 * pi / d->L_x; c->kys = 2.0 * pi / d->L_y;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream create failed");
+    c->own_stream = true;
+    int rc = 0;
+    rc |= make_twiddle(c, &c->Wx, c->nx / 2, c->nx / 2, c->nx / 2);
+    rc |= make_twiddle(c, &c->Whx, c->nx / 2, c->nx / 4 + 1, c->nx);
+    rc |= make_twiddle(c, &c->Wxb, c->nx2 / 2, c->nx2 / 2, c->nx2 / 2);
+    rc |= make_twiddle(c, &c->Whxb, c->nx2 / 2, c->nx2 / 4 + 1, c->nx2);
+    rc |= make_twiddle(c, &c->Wy, c->ny, c->ny, c->ny);
+    rc |= make_twiddle(c, &c->Wyb, c->ny2, c->ny2, c->ny2);
+    if (rc) { std::string m = c->err; return bail(m); }
+    *out = c;
+    return 0;
+}
+
+int lesgo_gpu_destroy(lesgo_gpu_ctx* c) {
+    if (!c) return 0;
+    cudaStreamSynchronize(c->stream);
+    if (c->comm) { delete c->comm; c->comm = nullptr; }
+    for (void* p : c->allocs) cudaFree(p);
+    for (double* p : c->staging) if (p) cudaFree(p);
+    if (c->red_host) cudaFreeHost(c->red_host);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int lesgo_gpu_set_stream(lesgo_gpu_ctx* c, void* s) {
+    if (!c) return 1;
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+    c->stream = static_cast<cudaStream_t>(s);
+    return 0;
+}
+
+int lesgo_gpu_synchronize(lesgo_gpu_ctx* c) {
+    if (!c) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+long lesgo_gpu_launch_count(const lesgo_gpu_ctx* c) { return c ? c->launches : 0; }
+
+int lesgo_gpu_profile(lesgo_gpu_ctx* c, int enable, char* report, int report_len) {
+    // enable = 1/0 switches per-launch event timing; a non-NULL report receives
+    // "label count total_ms\n" lines for everything recorded so far and clears the records.
+    if (!c) return 1;
+#ifndef LESGO_EMUL
+    if (report && report_len > 0) {
+        CK(cudaStreamSynchronize(c->stream));
+        struct Acc { const char* l; int n; double ms; };
+        std::vector<Acc> acc;
+        for (auto& r : c->prof_recs) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+            bool found = false;
+            for (auto& a : acc) if (std::strcmp(a.l, r.label) == 0) { a.n++; a.ms += ms; found = true; break; }
+            if (!found) acc.push_back(Acc{r.label, 1, double(ms)});
+        }
+        c->prof_recs.clear();
+        std::string out;
+        char line[160];
+        for (auto& a : acc) { std::snprintf(line, sizeof line, "%s %d %.6f\n", a.l, a.n, a.ms); out += line; }
+        std::snprintf(report, size_t(report_len), "%s", out.c_str());
+    }
+#else
+    if (report && report_len > 0) report[0] = 0;
+#endif
+    c->prof = enable != 0;
+    return 0;
+}
+
+int lesgo_gpu_wavenumbers(lesgo_gpu_ctx* c, double* kx, double* ky, double* k2) {
+    // fft.f90:130-160
+    if (!c) return 1;
+    for (int jy = 0; jy < c->ny; ++jy)
+        for (int jx = 0; jx < c->lh; ++jx) {
+            double x = double(jx), y = double(((jy + c->ny / 2) % c->ny) - c->ny / 2);
+            if (jx == c->lh - 1 || jy == c->ny / 2) { x = 0.0; y = 0.0; }
+            x = c->kxs * x; y = c->kys * y;
+            const long o = long(jy) * c->lh + jx;
+            if (kx) kx[o] = x;
+            if (ky) ky[o] = y;
+            if (k2) k2[o] = x * x + y * y;
+        }
+    return 0;
+}
+
+#define NFIELD (size_t(c->plane) * (c->nz + 1))
+
+int lesgo_gpu_filt_da(lesgo_gpu_ctx* c, double* f, double* dfdx, double* dfdy) {
+    if (!c || !f || !dfdx || !dfdy) return 1;
+    Staged st(c);
+    double* df = st.in(f, NFIELD, true, true);
+    double* dx = st.in(dfdx, NFIELD, false, true);
+    double* dy = st.in(dfdy, NFIELD, false, true);
+    if (!df || !dx || !dy) return 1;
+    if (spectral_deriv(c, df, df, dx, dy)) return 1;
+    return st.finish();
+}
+
+int lesgo_gpu_ddx(lesgo_gpu_ctx* c, const double* f, double* dfdx) {
+    if (!c || !f || !dfdx) return 1;
+    Staged st(c);
+    double* df = st.in(f, NFIELD, true, false);
+    double* dx = st.in(dfdx, NFIELD, false, true);
+    if (!df || !dx) return 1;
+    if (spectral_deriv(c, df, nullptr, dx, nullptr)) return 1;
+    return st.finish();
+}
+
+int lesgo_gpu_ddy(lesgo_gpu_ctx* c, const double* f, double* dfdy) {
+    if (!c || !f || !dfdy) return 1;
+    Staged st(c);
+    double* df = st.in(f, NFIELD, true, false);
+    double* dy = st.in(dfdy, NFIELD, false, true);
+    if (!df || !dy) return 1;
+    if (spectral_deriv(c, df, nullptr, nullptr, dy)) return 1;
+    return st.finish();
+}
+
+int lesgo_gpu_ddxy(lesgo_gpu_ctx* c, const double* f, double* dfdx, double* dfdy) {
+    if (!c || !f || !dfdx || !dfdy) return 1;
+    Staged st(c);
+    double* df = st.in(f, NFIELD, true, false);
+    double* dx = st.in(dfdx, NFIELD, false, true);
+    double* dy = st.in(dfdy, NFIELD, false, true);
+    if (!df || !dx || !dy) return 1;
+    if (spectral_deriv(c, df, nullptr, dx, dy)) return 1;
+    return st.finish();
+}
+
+int lesgo_gpu_ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
+    if (!c || !f || !dfdz) return 1;
+    Staged st(c);
+    double* df = st.in(f, NFIELD, true, false);
+    double* dz = st.in(dfdz, NFIELD, true, true);
+    if (!df || !dz) return 1;
+    if (ddz_uv(c, df, dz)) return 1;
+    return st.finish();
+}
+
+int lesgo_gpu_ddz_w(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
+    if (!c || !f || !dfdz) return 1;
+    Staged st(c);
+    double* df = st.in(f, NFIELD, true, false);
+    double* dz = st.in(dfdz, NFIELD, true, true);
+    if (!df || !dz) return 1;
+    if (ddz_w(c, df, dz)) return 1;
+    return st.finish();
+}
+
+int lesgo_gpu_convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, const double* dudy,
+                     const double* dudz, const double* dvdx, const double* dvdz, const double* dwdx,
+                     const double* dwdy, double* RHSx, double* RHSy, double* RHSz) {
+    if (!c) return 1;
+    Staged st(c);
+    const double* in[9] = {u, v, w, dudy, dudz, dvdx, dvdz, dwdx, dwdy};
+    double* din[9];
+    for (int i = 0; i < 9; ++i) {
+        if (!in[i]) return c->fail("convec: null input");
+        din[i] = st.in(in[i], NFIELD, true, false);
+        if (!din[i]) return 1;
+    }
+    double* ox = st.in(RHSx, NFIELD, false, true);
+    double* oy = st.in(RHSy, NFIELD, false, true);
+    double* oz = st.in(RHSz, NFIELD, false, true);
+    if (!ox || !oy || !oz) return c->fail("convec: null output");
+    if (convec(c, din[0], din[1], din[2], din[3], din[4], din[5], din[6], din[7], din[8], ox, oy, oz)) return 1;
+    return st.finish();
+}
+
+int lesgo_gpu_press_stag_array(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w,
+                               const double* divtz, double dt, double tadv1, double* p, double* dpdx,
+                               double* dpdy, double* dpdz) {
+    if (!c || !u || !v || !w || !divtz || !p || !dpdx || !dpdy || !dpdz) return 1;
+    Staged st(c);
+    double* du = st.in(u, NFIELD, true, false);
+    double* dv = st.in(v, NFIELD, true, false);
+    double* dw = st.in(w, NFIELD, true, false);
+    double* dd = st.in(divtz, NFIELD, true, false);
+    double* op = st.in(p, NFIELD, false, true);
+    double* ox = st.in(dpdx, NFIELD, true, true);
+    double* oy = st.in(dpdy, NFIELD, true, true);
+    double* oz = st.in(dpdz, NFIELD, true, true);
+    if (!du || !dv || !dw || !dd || !op || !ox || !oy || !oz) return 1;
+    if (press(c, du, dv, dw, dd, dt, tadv1, op, ox, oy, oz)) return 1;
+    return st.finish();
+}
+
+int lesgo_gpu_fft_r2c(lesgo_gpu_ctx* c, const double* in, double* out, int nplanes, int bigg) {
+    if (!c || !in || !out || nplanes < 1) return 1;
+    const bool b = bigg != 0;
+    const long pl = b ? c->plane_big : c->plane;
+    const int row = b ? c->ld_big : c->ld, nyr = b ? c->ny2 : c->ny, nxr = b ? c->nx2 : c->nx;
+    Staged st(c);
+    double* di = st.in(in, size_t(pl) * nplanes, true, false);
+    double* dout = st.in(out, size_t(pl) * nplanes, false, true);
+    if (!di || !dout) return 1;
+    ProScale ps; ps.src[0] = di; ps.lay = Lay{pl, row}; ps.scale = 1.0;
+    double* d[1] = {dout};
+    if (xfwd(c, b, ps, 1, d, pl, row, nxr / 2, nyr, 0, nplanes, 2)) return 1;
+    YArgs a = yargs(c, pl, row, pl, row, nxr / 2 + 1, 0);
+    a.keep_nyq_row = 1;
+    a.fld[0].src = dout; a.fld[0].out[0] = YOutSpec{dout, Y_COPY};
+    if (ypass(c, nyr, 0, a, 1, 0, nplanes)) return 1;
+    return st.finish();
+}
+
+int lesgo_gpu_fft_c2r(lesgo_gpu_ctx* c, const double* in, double* out, int nplanes, int bigg) {
+    if (!c || !in || !out || nplanes < 1) return 1;
+    const bool b = bigg != 0;
+    const long pl = b ? c->plane_big : c->plane;
+    const int row = b ? c->ld_big : c->ld, nyr = b ? c->ny2 : c->ny, nxr = b ? c->nx2 : c->nx;
+    Staged st(c);
+    double* di = st.in(in, size_t(pl) * nplanes, true, false);
+    double* dout = st.in(out, size_t(pl) * nplanes, false, true);
+    if (!di || !dout) return 1;
+    // y inverse into a scratch spectrum, then x inverse
+    double* tmp = nullptr;
+    if (b) { if (need_big(c, 1)) return 1; }
+    else if (need_small(c, 1)) return 1;
+    if (nplanes > c->nz + 1) return c->fail("fft_c2r: at most nz+1 planes per call");
+    tmp = b ? c->big[0] : c->sa[0];
+    YArgs a = yargs(c, pl, row, pl, row, nxr / 2 + 1, 0);
+    a.keep_nyq_row = 1;
+    a.fld[0].src = di; a.fld[0].out[0] = YOutSpec{tmp, Y_COPY};
+    if (ypass(c, 0, nyr, a, 1, 0, nplanes)) return 1;
+    const double* s0[1] = {tmp};
+    double* o0[1] = {dout};
+    if (xinv(c, b, s0, pl, row, nxr / 2 + 1, 1, o0, Lay{pl, row}, nyr, 0, nplanes, 0)) return 1;
+    return st.finish();
+}
+
+double* lesgo_gpu_field_ptr(lesgo_gpu_ctx* c, int id) { return c ? field(c, id) : nullptr; }
+
+int lesgo_gpu_upload(lesgo_gpu_ctx* c, int id, const double* host) {
+    if (!c || !host) return 1;
+    double* f = field(c, id);
+    if (!f) return c->fail("bad field id");
+    CK(cudaMemcpyAsync(f, host, NFIELD * sizeof(double), cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lesgo_gpu_download(lesgo_gpu_ctx* c, int id, double* host) {
+    if (!c || !host) return 1;
+    double* f = field(c, id);
+    if (!f) return c->fail("bad field id");
+    CK(cudaMemcpyAsync(host, f, NFIELD * sizeof(double), cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lesgo_gpu_step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
+    if (!c || !sp) return 1;
+    if (step(c, sp)) return 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int lesgo_gpu_max_cfl(lesgo_gpu_ctx* c, double dt, double* cfl) {
+    // cfl_util.f90:35-69 (local part; the caller max-reduces over ranks, or comm does)
+    if (!c || !cfl) return 1;
+    if (!c->red_dev) { if (dev_alloc(c, &c->red_dev, 8)) return 1; }
+    if (!c->red_host) CK(cudaMallocHost(reinterpret_cast<void**>(&c->red_host), 8 * sizeof(double)));
+    CK(cudaMemsetAsync(c->red_dev, 0, 8 * sizeof(double), c->stream));
+    const int ids[3] = {LG_U, LG_V, LG_W};
+    for (int i = 0; i < 3; ++i) {
+        LG_LAUNCH(k_absmax, dim3(grid1d(long(c->nx / 2) * c->ny * (c->nz - 1))), dim3(kBlock), 0, c->stream,
+                  field(c, ids[i]), c->lay(), c->nx, c->ny, 1, c->nz,
+                  reinterpret_cast<unsigned long long*>(c->red_dev + i));
+        c->launches++;
+    }
+    CK(cudaMemcpyAsync(c->red_host, c->red_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const double dx = c->d.L_x / c->nx, dy = c->d.L_y / c->ny;
+    double m = std::fmax(c->red_host[0] / dx, std::fmax(c->red_host[1] / dy, c->red_host[2] / c->d.dz));
+    double r = dt * m;
+    if (c->comm && c->comm->allreduce_max(&r, c->stream)) return c->fail(c->comm->error());
+    *cfl = r;
+    return 0;
+}
+
+int lesgo_gpu_rmsdiv(lesgo_gpu_ctx* c, double* rms) {
+    // rmsdiv.f90:21-59 on the resident dudx, dvdy, dwdz
+    if (!c || !rms) return 1;
+    if (!c->red_dev) { if (dev_alloc(c, &c->red_dev, 8)) return 1; }
+    if (!c->red_host) CK(cudaMallocHost(reinterpret_cast<void**>(&c->red_host), 8 * sizeof(double)));
+    CK(cudaMemsetAsync(c->red_dev, 0, 8 * sizeof(double), c->stream));
+    LG_LAUNCH(k_abs3sum, dim3(grid1d(long(c->nx / 2) * c->ny * (c->nz - 1))), dim3(kBlock), 0, c->stream,
+              field(c, LG_DUDX), field(c, LG_DVDY), field(c, LG_DWDZ), c->lay(), c->nx, c->ny, 1, c->nz, c->red_dev + 4);
+    c->launches++;
+    CK(cudaMemcpyAsync(c->red_host, c->red_dev + 4, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    double r = c->red_host[0] / (double(c->nx) * c->ny * (c->nz - 1));
+    if (c->comm) {
+        if (c->comm->allreduce_sum(&r, c->stream)) return c->fail(c->comm->error());
+        r /= c->d.nproc;
+    }
+    *rms = r;
+    return 0;
+}
+
+int lesgo_gpu_comm_unique_id(void* id128) { return lg::Comm::unique_id(id128, &g_err); }
+
+int lesgo_gpu_comm_init(lesgo_gpu_ctx* c, const void* id128) {
+    if (!c || !id128) return 1;
+    if (c->comm) return c->fail("comm already initialised");
+    std::string e;
+    c->comm = lg::Comm::create(id128, c->d.coord, c->d.nproc, &e);
+    if (!c->comm) return c->fail(e);
+    return 0;
+}
+
+int lesgo_gpu_sync_real_array(lesgo_gpu_ctx* c, double* var, int isync) {
+    if (!c || !var) return 1;
+    if (c->d.nproc == 1) return 0;
+    if (!c->comm) return c->fail("lesgo_gpu_comm_init has not been called");
+    Staged st(c);
+    double* d = st.in(var, NFIELD, true, true);
+    if (!d) return 1;
+    if (c->comm->sync_planes(d, c->plane, c->nz, isync, c->stream)) return c->fail(c->comm->error());
+    return st.finish();
+}
+
+int lesgo_gpu_padd(lesgo_gpu_ctx* c, double* u_big, const double* u, int nplanes) {
+    if (!c || !u_big || !u || nplanes < 1) return 1;
+    Staged st(c);
+    double* du = st.in(u, size_t(c->plane) * nplanes, true, false);
+    double* db = st.in(u_big, size_t(c->plane_big) * nplanes, false, true);
+    if (!du || !db) return 1;
+    LG_LAUNCH(k_padd, dim3(grid1d(long(c->lh_big) * c->ny2 * nplanes)), dim3(kBlock), 0, c->stream, du, db, c->nx,
+              c->ny, c->ld, c->ny2, c->ld_big, nplanes);
+    c->launches++;
+    return st.finish();
+}
+
+int lesgo_gpu_unpadd(lesgo_gpu_ctx* c, double* cc, const double* cc_big, int nplanes) {
+    if (!c || !cc || !cc_big || nplanes < 1) return 1;
+    Staged st(c);
+    double* db = st.in(cc_big, size_t(c->plane_big) * nplanes, true, false);
+    double* dc = st.in(cc, size_t(c->plane) * nplanes, false, true);
+    if (!dc || !db) return 1;
+    LG_LAUNCH(k_unpadd, dim3(grid1d(long(c->lh) * c->ny * nplanes)), dim3(kBlock), 0, c->stream, dc, db, c->nx,
+              c->ny, c->ld, c->ny2, c->ld_big, nplanes);
+    c->launches++;
+    return st.finish();
+}
+
+int lesgo_gpu_test_filter(lesgo_gpu_ctx* c, double* f, const double* G, int nplanes) {
+    // test_filtermodule.f90:126-146: r2c, multiply by the real kernel G(lh, ny), c2r
+    if (!c || !f || !G || nplanes < 1) return 1;
+    if (nplanes > c->nz + 1) return c->fail("test_filter: at most nz+1 planes per call");
+    if (need_small(c, 2)) return 1;
+    Staged st(c);
+    double* df = st.in(f, size_t(c->plane) * nplanes, true, true);
+    double* dg = st.in(G, size_t(c->lh) * c->ny, true, false);
+    if (!df || !dg) return 1;
+    ProScale ps; ps.src[0] = df; ps.lay = c->lay(); ps.scale = 1.0;
+    double* d0[1] = {c->sa[0]};
+    if (xfwd(c, false, ps, 1, d0, c->plane, c->ld, c->nx / 2, c->ny, 0, nplanes)) return 1;
+    YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, c->nx / 2, 0);
+    a.fld[0].src = c->sa[0]; a.fld[0].out[0] = YOutSpec{c->sa[1], Y_TABLE};
+    a.table = dg; a.table_row = c->lh;
+    if (ypass(c, c->ny, c->ny, a, 1, 0, nplanes)) return 1;
+    const double* s0[1] = {c->sa[1]};
+    double* o0[1] = {df};
+    if (xinv(c, false, s0, c->plane, c->ld, c->nx / 2, 1, o0, c->lay(), c->ny, 0, nplanes)) return 1;
+    return st.finish();
+}
+
+int lesgo_gpu_tridag_array(lesgo_gpu_ctx* c, const double* a, const double* b, const double* cc, const double* r,
+                           double* u, int n) {
+    if (!c || !a || !b || !cc || !r || !u || n < 2) return 1;
+    Staged st(c);
+    const size_t nc = size_t(c->lh) * c->ny * n, nr = size_t(c->plane) * n;
+    double* da = st.in(a, nc, true, false);
+    double* db = st.in(b, nc, true, false);
+    double* dc = st.in(cc, nc, true, false);
+    double* dr = st.in(r, nr, true, false);
+    double* du = st.in(u, nr, true, true);
+    if (!da || !db || !dc || !dr || !du) return 1;
+    void* work = nullptr;
+    CK(cudaMalloc(&work, nc * sizeof(double) + 16));
+    int* flag = reinterpret_cast<int*>(static_cast<double*>(work) + nc);
+    CK(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+    const int nm = (c->lh - 1) * c->ny;
+    LG_LAUNCH(k_tridag_general, dim3((nm + 127) / 128), dim3(128), 0, c->stream, c->lh, c->ny, n, c->ld, da, db, dc,
+              dr, du, static_cast<double*>(work), flag);
+    c->launches++;
+    int hflag = 0;
+    CK(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int rc = st.finish();
+    cudaStreamSynchronize(c->stream);
+    cudaFree(work);
+    if (rc) return rc;
+    if (hflag) return c->fail("tridag_array failed: zero pivot (tridag_array.f90:55-60,101-108)");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,475 @@
+// ops.h -- prologue / epilogue functors fused into the x passes, and the pointwise
+// z-direction kernels (finite differences, tridiagonal sweeps, time-stepping glue).
+#pragma once
+#include "fft_kernels.h"
+
+namespace lg {
+
+// Products are formed without FMA contraction where the reference's expression order
+// matters for parity with the (non-FMA) CPU restatement.
+#ifdef LESGO_EMUL
+LG_HD double dmul(double a, double b) { return a * b; }
+LG_HD double dadd(double a, double b) { return a + b; }
+LG_HD double dsub(double a, double b) { return a - b; }
+LG_HD double ddiv(double a, double b) { return a / b; }
+#else
+LG_D double dmul(double a, double b) { return __dmul_rn(a, b); }
+LG_D double dadd(double a, double b) { return __dadd_rn(a, b); }
+LG_D double dsub(double a, double b) { return __dsub_rn(a, b); }
+LG_D double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+#endif
+
+struct Lay {          // addressing of a (row, plane)-strided real array
+    long plane;       // doubles between z planes
+    int row;          // doubles between y rows
+    LG_HD long at(int k, int y, int i) const { return long(k) * plane + long(y) * row + i; }
+};
+
+LG_HD double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// ---- x-forward prologues ---------------------------------------------------------
+// scale * f   (derivatives.f90:185-190, convec.f90:75-77, press_stag_array.f90:78-80)
+struct ProScale {
+    const double* src[kMaxFields];
+    Lay lay;
+    double scale;
+    LG_D double2 load(int fld, int k, int y, int j) const {
+        double2 v = ld2(src[fld] + lay.at(k, y, 2 * j));
+        return make_double2(dmul(scale, v.x), dmul(scale, v.y));
+    }
+};
+
+// vorticity with the wall-plane special cases (convec.f90:97-153); fields 0,1,2 = RHSx,y,z
+struct ProVort {
+    const double *dudy, *dudz, *dvdx, *dvdz, *dwdx, *dwdy;
+    Lay lay;
+    double scale;
+    int nz, bottom, top, lbc_mom, ubc_mom;   // bottom = (coord == 0), top = (coord == nproc-1)
+    LG_D double2 load(int fld, int k, int y, int j) const {
+        const long o = lay.at(k, y, 2 * j);
+        if (fld == 2) {
+            double2 a = ld2(dvdx + o), b = ld2(dudy + o);
+            return make_double2(dmul(scale, dsub(a.x, b.x)), dmul(scale, dsub(a.y, b.y)));
+        }
+        const bool sb = bottom && k == 1;
+        const bool st = top && k == nz && ubc_mom > 0;
+        if (sb && lbc_mom == 0) return make_double2(0.0, 0.0);
+        if (sb || st) {
+            // 0.5*(dw(k1)+dw(k2)) -/+ d(u|v)dz(kz)
+            const int k1 = sb ? 1 : nz - 1, k2 = sb ? 2 : nz, kz = sb ? 1 : nz - 1;
+            const long o1 = lay.at(k1, y, 2 * j), o2 = lay.at(k2, y, 2 * j), oz = lay.at(kz, y, 2 * j);
+            if (fld == 0) {
+                double2 a = ld2(dwdy + o1), b = ld2(dwdy + o2), c = ld2(dvdz + oz);
+                return make_double2(dmul(scale, dsub(dmul(0.5, dadd(a.x, b.x)), c.x)),
+                                    dmul(scale, dsub(dmul(0.5, dadd(a.y, b.y)), c.y)));
+            } else {
+                double2 a = ld2(dwdx + o1), b = ld2(dwdx + o2), c = ld2(dudz + oz);
+                return make_double2(dmul(scale, dsub(c.x, dmul(0.5, dadd(a.x, b.x)))),
+                                    dmul(scale, dsub(c.y, dmul(0.5, dadd(a.y, b.y)))));
+            }
+        }
+        if (fld == 0) {
+            double2 a = ld2(dwdy + o), b = ld2(dvdz + o);
+            return make_double2(dmul(scale, dsub(a.x, b.x)), dmul(scale, dsub(a.y, b.y)));
+        }
+        double2 a = ld2(dudz + o), b = ld2(dwdx + o);
+        return make_double2(dmul(scale, dsub(a.x, b.x)), dmul(scale, dsub(a.y, b.y)));
+    }
+};
+
+// u x omega on the 3/2 grid (convec.f90:172-305); fields 0,1,2 = cx, cy, cz
+struct ProConvec {
+    const double *u, *v, *w, *o1, *o2, *o3;   // *_big arrays, planes 0..nz
+    Lay lay;
+    double scale;                              // 1/(nx2*ny2)
+    int nz, bottom, top, jzLo;
+    LG_D double2 load(int fld, int k, int y, int j) const {
+        const long o = lay.at(k, y, 2 * j);
+        const bool sb = bottom && k == 1;
+        const bool st = top && k == nz - 1;
+        double2 r;
+        if (fld == 2) {
+            if (sb || k == nz) return make_double2(0.0, 0.0);
+            const long om = lay.at(k - 1, y, 2 * j);
+            double2 uu = ld2(u + o), um = ld2(u + om), vv = ld2(v + o), vm = ld2(v + om);
+            double2 w1 = ld2(o1 + o), w2 = ld2(o2 + o);
+            r.x = dmul(dmul(scale, 0.5), dadd(dmul(dadd(uu.x, um.x), -w2.x), dmul(dadd(vv.x, vm.x), w1.x)));
+            r.y = dmul(dmul(scale, 0.5), dadd(dmul(dadd(uu.y, um.y), -w2.y), dmul(dadd(vv.y, vm.y), w1.y)));
+            return r;
+        }
+        if (k == nz) return make_double2(0.0, 0.0);     // plane nz of cx, cy is never valid
+        // first term: cx: v*(-o3), cy: u*o3
+        double2 f = ld2((fld == 0 ? v : u) + o), z3 = ld2(o3 + o);
+        const double sg = fld == 0 ? -1.0 : 1.0;        // sign on o3 (cx) / on o1 (cy) below is opposite
+        double2 t1 = make_double2(dmul(f.x, sg * z3.x), dmul(f.y, sg * z3.y));
+        const double* oz = fld == 0 ? o2 : o1;          // cx uses +o2, cy uses -o1
+        const double so = fld == 0 ? 1.0 : -1.0;
+        double2 t2;
+        if (st) {
+            // top rank, plane nz-1: 0.5*w(nz-1)*o(jzHi = nz-1)   (:186-189, :229-232)
+            double2 ww = ld2(w + o), zz = ld2(oz + o);
+            t2 = make_double2(dmul(dmul(0.5, ww.x), so * zz.x), dmul(dmul(0.5, ww.y), so * zz.y));
+        } else if (sb) {
+            // bottom rank, plane 1: 0.5*w(2)*o(jzLo)             (:174-177, :217-220)
+            double2 ww = ld2(w + lay.at(2, y, 2 * j)), zz = ld2(oz + lay.at(jzLo, y, 2 * j));
+            t2 = make_double2(dmul(dmul(0.5, ww.x), so * zz.x), dmul(dmul(0.5, ww.y), so * zz.y));
+        } else {
+            const long op = lay.at(k + 1, y, 2 * j);
+            double2 wp = ld2(w + op), zp = ld2(oz + op), ww = ld2(w + o), zz = ld2(oz + o);
+            t2 = make_double2(dmul(0.5, dadd(dmul(wp.x, so * zp.x), dmul(ww.x, so * zz.x))),
+                              dmul(0.5, dadd(dmul(wp.y, so * zp.y), dmul(ww.y, so * zz.y))));
+        }
+        return make_double2(dmul(scale, dadd(t1.x, t2.x)), dmul(scale, dadd(t1.y, t2.y)));
+    }
+};
+
+// ---- x-inverse epilogue ------------------------------------------------------------
+struct EpiStore {
+    double* dst[kMaxFields];
+    Lay lay;
+    int nx;          // real row length; the two pad reals are zeroed when pad != 0
+    int pad;
+    LG_D void store(int fld, int k, int y, int j, double2 v) const {
+        *reinterpret_cast<double2*>(dst[fld] + lay.at(k, y, 2 * j)) = v;
+    }
+    LG_D void finish_row(int fld, int k, int y) const {
+        if (pad) *reinterpret_cast<double2*>(dst[fld] + lay.at(k, y, nx)) = make_double2(0.0, 0.0);
+    }
+};
+
+// ---- pointwise z kernels ------------------------------------------------------------
+// dfdz(k) = (f(k+shift_hi) - f(k+shift_lo))/dz over 1:nx   (derivatives.f90:245-251, :292-298)
+static __global__ void k_ddz(const double* __restrict__ f, double* __restrict__ dfdz, Lay lay, int nx, int ny,
+                      int k0, int k1, int lo, int hi, double inv_dz) {
+    const long n = long(nx / 2) * ny * (k1 - k0);
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        int j = int(t % (nx / 2));
+        long r = t / (nx / 2);
+        int y = int(r % ny), k = k0 + int(r / ny);
+        double2 a = ld2(f + lay.at(k + hi, y, 2 * j)), b = ld2(f + lay.at(k + lo, y, 2 * j));
+        *reinterpret_cast<double2*>(dfdz + lay.at(k, y, 2 * j)) =
+            make_double2(dmul(inv_dz, dsub(a.x, b.x)), dmul(inv_dz, dsub(a.y, b.y)));
+    }
+}
+
+// DNS wall derivatives, wallstress.f90:131-168: dudz(kdst) = sign*(u(ksrc) - uwall)/h with
+// h = dz/2 (sign = +1 bottom, -1 top), dvdz(kdst) = sign*v(ksrc)/h, over 1:nx
+static __global__ void k_wall_dns(const double* __restrict__ u, const double* __restrict__ v, double* __restrict__ dudz,
+                           double* __restrict__ dvdz, Lay lay, int nx, int ny, int ksrc, int kdst, double uwall,
+                           double sign, double h) {
+    const long n = long(nx / 2) * ny;
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        int j = int(t % (nx / 2)), y = int(t / (nx / 2));
+        double2 a = ld2(u + lay.at(ksrc, y, 2 * j)), b = ld2(v + lay.at(ksrc, y, 2 * j));
+        double2 du, dv;
+        if (sign > 0) {
+            du = make_double2(ddiv(dsub(a.x, uwall), h), ddiv(dsub(a.y, uwall), h));
+            dv = make_double2(ddiv(b.x, h), ddiv(b.y, h));
+        } else {
+            du = make_double2(ddiv(dsub(uwall, a.x), h), ddiv(dsub(uwall, a.y), h));
+            dv = make_double2(ddiv(-b.x, h), ddiv(-b.y, h));
+        }
+        *reinterpret_cast<double2*>(dudz + lay.at(kdst, y, 2 * j)) = du;
+        *reinterpret_cast<double2*>(dvdz + lay.at(kdst, y, 2 * j)) = dv;
+    }
+}
+
+// dst(k) = value on whole planes k0..k1-1 (BOGUS poisoning / zeroing)
+static __global__ void k_fill(double* __restrict__ dst, long plane, int k0, int k1, double value) {
+    const long n = plane * (k1 - k0);
+    double* p = dst + long(k0) * plane;
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) p[t] = value;
+}
+
+// Generic fused linear glue on whole planes (ld pad included, like the Fortran
+// whole-array expressions of main.f90):  mode selects the expression.
+enum GlueMode {
+    G_RHS_ASSEMBLE = 0,   // a = -a - b + c0                      main.f90:211-214,229-232
+    G_AB2 = 1,            // a = a + c0*(c1*b + c2*c)             main.f90:287-296
+    G_SUB = 2,            // a = a - b                            main.f90:321-326
+    G_COPY = 3,           // a = b
+    G_PROJECT = 4         // a = a + c0*(-c1*b)  over 1:nx only   forcing.f90:171-207
+};
+static __global__ void k_glue(int mode, double* __restrict__ a, const double* __restrict__ b,
+                       const double* __restrict__ c, Lay lay, int nxlim, int ny, int k0, int k1,
+                       double c0, double c1, double c2) {
+    const int half = lay.row / 2;
+    const long n = long(half) * ny * (k1 - k0);
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        int j = int(t % half);
+        long r = t / half;
+        int y = int(r % ny), k = k0 + int(r / ny);
+        if (2 * j >= nxlim) continue;
+        const long o = lay.at(k, y, 2 * j);
+        double2 va = ld2(a + o), vb = ld2(b + o), vc = make_double2(0.0, 0.0);
+        if (mode == G_AB2) vc = ld2(c + o);
+        double2 r2;
+        switch (mode) {
+            case G_RHS_ASSEMBLE:
+                r2 = make_double2(dadd(dsub(-va.x, vb.x), c0), dadd(dsub(-va.y, vb.y), c0));
+                break;
+            case G_AB2:
+                r2 = make_double2(dadd(va.x, dmul(c0, dadd(dmul(c1, vb.x), dmul(c2, vc.x)))),
+                                  dadd(va.y, dmul(c0, dadd(dmul(c1, vb.y), dmul(c2, vc.y)))));
+                break;
+            case G_SUB:
+                r2 = make_double2(dsub(va.x, vb.x), dsub(va.y, vb.y));
+                break;
+            case G_COPY:
+                r2 = vb;
+                break;
+            default:   // G_PROJECT
+                r2 = make_double2(dadd(va.x, dmul(c0, dmul(-c1, vb.x))), dadd(va.y, dmul(c0, dmul(-c1, vb.y))));
+                break;
+        }
+        *reinterpret_cast<double2*>(a + o) = r2;
+    }
+}
+
+// max |f| over 1:nx, 1:ny, planes k0..k1-1 -> atomicMax on the bit pattern (values >= 0)
+static __global__ void k_absmax(const double* __restrict__ f, Lay lay, int nx, int ny, int k0, int k1,
+                         unsigned long long* __restrict__ out) {
+    __shared__ double red[kBlock];
+    const long n = long(nx / 2) * ny * (k1 - k0);
+    double m = 0.0;
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        int j = int(t % (nx / 2));
+        long r = t / (nx / 2);
+        int y = int(r % ny), k = k0 + int(r / ny);
+        double2 v = ld2(f + lay.at(k, y, 2 * j));
+        m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (int(threadIdx.x) < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicMax(out, (unsigned long long)__double_as_longlong(red[0]));
+}
+
+// sum |a+b+c| over 1:nx, 1:ny, planes k0..k1-1 (rmsdiv.f90:42-50); partial sums per block
+static __global__ void k_abs3sum(const double* __restrict__ a, const double* __restrict__ b,
+                          const double* __restrict__ c, Lay lay, int nx, int ny, int k0, int k1,
+                          double* __restrict__ out) {
+    __shared__ double red[kBlock];
+    const long n = long(nx / 2) * ny * (k1 - k0);
+    double s = 0.0;
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        int j = int(t % (nx / 2));
+        long r = t / (nx / 2);
+        int y = int(r % ny), k = k0 + int(r / ny);
+        const long o = lay.at(k, y, 2 * j);
+        double2 va = ld2(a + o), vb = ld2(b + o), vc = ld2(c + o);
+        s += fabs(va.x + vb.x + vc.x) + fabs(va.y + vb.y + vc.y);
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if (int(threadIdx.x) < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out, red[0]);
+}
+
+// ---- tridiagonal solve (tridag_array.f90 + press_stag_array.f90:149-239) ------------
+// One thread per (kx, ky) mode marches the whole z column (n = nzt + 1 rows, row j <->
+// p(:,:,j-1)).  The matrix is time-invariant: a = c = 1/dz^2, b = -(k2 + 2/dz^2), with
+// the Neumann rows (b,c) = (-1, 1) at j = 1 and (a,b) = (-1, 1) at j = n, so gam(j) is
+// tabulated once (k_tridag_setup) and bet(j) is re-derived in registers.  Division and
+// multiply-subtract are kept un-contracted to follow tridag_array.f90:98-113 exactly.
+struct TriGeom {
+    int lh, ny, nzt;        // nzt = number of w levels = rows - 1
+    int row;                // doubles per y row of the spectral arrays (ld)
+    long plane;             // doubles per plane of the spectral arrays
+    long gplane;            // doubles per plane of gam (lh * ny)
+    double kxs, kys, dz;
+};
+
+LG_D double tri_k2(const TriGeom& g, int jx, int jy) {
+    double kx = g.kxs * double(jx);
+    double ky = g.kys * double(jy < g.ny / 2 ? jy : jy - g.ny);
+    if (jy == g.ny / 2) ky = 0.0, kx = 0.0;
+    return dadd(dmul(kx, kx), dmul(ky, ky));
+}
+
+// gam(j), j = 2..n  stored at gam[j*gplane + jy*lh + jx]
+static __global__ void k_tridag_setup(TriGeom g, double* __restrict__ gam) {
+    const int nm = (g.lh - 1) * g.ny;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nm) return;
+    const int jx = t % (g.lh - 1), jy = t / (g.lh - 1);
+    if (jy == g.ny / 2 || (jx == 0 && jy == 0)) return;
+    const double c3 = ddiv(1.0, dmul(g.dz, g.dz));
+    const double bb = -dadd(tri_k2(g, jx, jy), dmul(2.0, c3));
+    const int n = g.nzt + 1;
+    double bet = -1.0, cprev = 1.0;                 // row 1: b = -1, c = 1
+    for (int j = 2; j <= n; ++j) {
+        const double a = (j == n) ? -1.0 : c3;
+        const double b = (j == n) ? 1.0 : bb;
+        const double gm = ddiv(cprev, bet);
+        bet = dsub(b, dmul(a, gm));
+        gam[long(j) * g.gplane + long(jy) * g.lh + jx] = gm;
+        cprev = c3;
+    }
+}
+
+// Forward + backward sweep with the right-hand side assembled on the fly from the
+// spectra of H = u*/(tadv1 dt) (press_stag_array.f90:188-215); p_hat(k) = row k+1.
+//   Hx, Hy, Hz : (ld, ny, 0:nzt) spectra; planes 1..nzt-1 of Hx,Hy and 1..nzt of Hz used
+//   rbot, rtop : spectra of divtz at the walls (:114-126), one plane each
+static __global__ void k_tridag_fused(TriGeom g, const double* __restrict__ Hx, const double* __restrict__ Hy,
+                               const double* __restrict__ Hz, const double* __restrict__ rbot,
+                               const double* __restrict__ rtop, const double* __restrict__ gam,
+                               double* __restrict__ p) {
+    const int nm = (g.lh - 1) * g.ny;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nm) return;
+    const int jx = t % (g.lh - 1), jy = t / (g.lh - 1);
+    const long mo = long(jy) * g.row + 2 * jx;      // offset of this mode inside a plane
+    const int n = g.nzt + 1;
+    const double dz = g.dz;
+    if (jy == g.ny / 2) return;                      // never solved; zeroed by the consumer
+    if (jx == 0 && jy == 0) {
+        // zero-wavenumber chain, press_stag_array.f90:226-234
+        double2 pk = make_double2(0.0, 0.0);
+        *reinterpret_cast<double2*>(p + mo) = pk;
+        double2 rb = ld2(rbot + mo);
+        pk = make_double2(dsub(pk.x, dmul(dz, rb.x)), dsub(pk.y, dmul(dz, rb.y)));
+        *reinterpret_cast<double2*>(p + g.plane + mo) = pk;
+        for (int k = 2; k <= g.nzt; ++k) {
+            double2 h = ld2(Hz + long(k) * g.plane + mo);
+            pk = make_double2(dadd(pk.x, dmul(h.x, dz)), dadd(pk.y, dmul(h.y, dz)));
+            *reinterpret_cast<double2*>(p + long(k) * g.plane + mo) = pk;
+        }
+        return;
+    }
+    const double c3 = ddiv(1.0, dmul(dz, dz));
+    const double c4 = ddiv(1.0, dz);
+    const double kx = g.kxs * double(jx);
+    const double ky = g.kys * double(jy < g.ny / 2 ? jy : jy - g.ny);
+    const double bb = -dadd(dadd(dmul(kx, kx), dmul(ky, ky)), dmul(2.0, c3));
+    // row 1: u(1) = r(1)/b(1) = (-dz*rbottomw)/(-1)
+    double2 rb = ld2(rbot + mo);
+    double2 u = make_double2(ddiv(dmul(-dz, rb.x), -1.0), ddiv(dmul(-dz, rb.y), -1.0));
+    *reinterpret_cast<double2*>(p + mo) = u;
+    double bet = -1.0;
+    double2 hzm = ld2(Hz + g.plane + mo);            // Hz(j-1) for j = 2
+    for (int j = 2; j <= n; ++j) {
+        double a, b;
+        double2 r;
+        if (j < n) {
+            a = c3; b = bb;
+            double2 hx = ld2(Hx + long(j - 1) * g.plane + mo);
+            double2 hy = ld2(Hy + long(j - 1) * g.plane + mo);
+            double2 hz = ld2(Hz + long(j) * g.plane + mo);
+            // aH_x + aH_y + (rH_z(j) - rH_z(j-1))*const4
+            r.x = dadd(dadd(dmul(-hx.y, kx), dmul(-hy.y, ky)), dmul(dsub(hz.x, hzm.x), c4));
+            r.y = dadd(dadd(dmul(hx.x, kx), dmul(hy.x, ky)), dmul(dsub(hz.y, hzm.y), c4));
+            hzm = hz;
+        } else {
+            a = -1.0; b = 1.0;
+            double2 rt = ld2(rtop + mo);
+            r = make_double2(dmul(-dz, rt.x), dmul(-dz, rt.y));
+        }
+        const double gm = gam[long(j) * g.gplane + long(jy) * g.lh + jx];
+        bet = dsub(b, dmul(a, gm));
+        u = make_double2(ddiv(dsub(r.x, dmul(a, u.x)), bet), ddiv(dsub(r.y, dmul(a, u.y)), bet));
+        *reinterpret_cast<double2*>(p + long(j - 1) * g.plane + mo) = u;
+    }
+    // back substitution, tridag_array.f90:141-152 (j = n-1 .. 1)
+    for (int j = n - 1; j >= 1; --j) {
+        const double gm = gam[long(j + 1) * g.gplane + long(jy) * g.lh + jx];
+        double2 uj = ld2(p + long(j - 1) * g.plane + mo);
+        u = make_double2(dsub(uj.x, dmul(gm, u.x)), dsub(uj.y, dmul(gm, u.y)));
+        *reinterpret_cast<double2*>(p + long(j - 1) * g.plane + mo) = u;
+    }
+}
+
+// dpdz(k) = (p(k) - p(k-1))/dz over 1:nx (press_stag_array.f90:284-288): true division
+static __global__ void k_dpdz(const double* __restrict__ p, double* __restrict__ dpdz, Lay lay, int nx, int ny,
+                       int k0, int k1, double dz) {
+    const long n = long(nx / 2) * ny * (k1 - k0);
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        int j = int(t % (nx / 2));
+        long r = t / (nx / 2);
+        int y = int(r % ny), k = k0 + int(r / ny);
+        double2 a = ld2(p + lay.at(k, y, 2 * j)), b = ld2(p + lay.at(k - 1, y, 2 * j));
+        *reinterpret_cast<double2*>(dpdz + lay.at(k, y, 2 * j)) =
+            make_double2(ddiv(dsub(a.x, b.x), dz), ddiv(dsub(a.y, b.y), dz));
+    }
+}
+
+// padd (fft.f90:43-71) / unpadd (fft.f90:74-99) as plain spectral-array copies, for callers
+// that use them directly (scalars.f90); the convective term fuses them into the y pass.
+static __global__ void k_padd(const double* __restrict__ u, double* __restrict__ ub, int nx, int ny, int ld,
+                              int ny2, int ld_big, int nplanes) {
+    const int lhb = ld_big / 2;
+    const long n = long(lhb) * ny2 * nplanes;
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        int m = int(t % lhb);
+        long r = t / lhb;
+        int jb = int(r % ny2), k = int(r / ny2);
+        int js = -1;
+        if (jb < ny / 2) js = jb;
+        else if (jb > ny2 - ny / 2) js = jb - (ny2 - ny);
+        double2 v = make_double2(0.0, 0.0);
+        if (js >= 0 && 2 * m < nx) v = ld2(u + (long(k) * ny + js) * ld + 2 * m);
+        *reinterpret_cast<double2*>(ub + (long(k) * ny2 + jb) * ld_big + 2 * m) = v;
+    }
+}
+static __global__ void k_unpadd(double* __restrict__ cc, const double* __restrict__ cb, int nx, int ny, int ld,
+                                int ny2, int ld_big, int nplanes) {
+    const int lh = ld / 2;
+    const long n = long(lh) * ny * nplanes;
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        int m = int(t % lh);
+        long r = t / lh;
+        int j = int(r % ny), k = int(r / ny);
+        double2 v = make_double2(0.0, 0.0);
+        if (j != ny / 2 && 2 * m < nx) {
+            int jb = j < ny / 2 ? j : j + (ny2 - ny);
+            v = ld2(cb + (long(k) * ny2 + jb) * ld_big + 2 * m);
+        }
+        *reinterpret_cast<double2*>(cc + (long(k) * ny + j) * ld + 2 * m) = v;
+    }
+}
+
+// tridag_array with caller-supplied coefficients (tridag_array.f90:166-246, serial form):
+// a,b,c (lh, ny, n), r,u (ld, ny, n); gam is an (lh, ny, n) work array.
+static __global__ void k_tridag_general(int lh, int ny, int n, int ld, const double* __restrict__ a,
+                                        const double* __restrict__ b, const double* __restrict__ c,
+                                        const double* __restrict__ r, double* __restrict__ u,
+                                        double* __restrict__ gam, int* __restrict__ fail) {
+    const int nm = (lh - 1) * ny;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nm) return;
+    const int jx = t % (lh - 1), jy = t / (lh - 1);
+    const long cp = long(lh) * ny, rp = long(ld) * ny;
+    const long co = long(jy) * lh + jx, ro = long(jy) * ld + 2 * jx;
+    // row 1 for every jy, jx <= lh-1 (:193-205)
+    double bet = b[co];
+    if (bet == 0.0) { *fail = 1; return; }
+    double2 r1 = ld2(r + ro);
+    double2 uu = make_double2(ddiv(r1.x, bet), ddiv(r1.y, bet));
+    *reinterpret_cast<double2*>(u + ro) = uu;
+    if (jy == ny / 2 || (jx == 0 && jy == 0)) return;
+    for (int j = 1; j < n; ++j) {
+        const double gm = ddiv(c[(j - 1) * cp + co], bet);
+        gam[j * cp + co] = gm;
+        const double aj = a[j * cp + co];
+        bet = dsub(b[j * cp + co], dmul(aj, gm));
+        if (bet == 0.0) { *fail = 1; return; }
+        double2 rj = ld2(r + j * rp + ro);
+        uu = make_double2(ddiv(dsub(rj.x, dmul(aj, uu.x)), bet), ddiv(dsub(rj.y, dmul(aj, uu.y)), bet));
+        *reinterpret_cast<double2*>(u + j * rp + ro) = uu;
+    }
+    for (int j = n - 2; j >= 0; --j) {
+        const double gm = gam[(j + 1) * cp + co];
+        double2 uj = ld2(u + j * rp + ro);
+        uu = make_double2(dsub(uj.x, dmul(gm, uu.x)), dsub(uj.y, dmul(gm, uu.y)));
+        *reinterpret_cast<double2*>(u + j * rp + ro) = uu;
+    }
+}
+
+}  // namespace lg

@@ -1,0 +1,10 @@
+#include "xfwd_impl.h"
+namespace lg {
+#define PRO ProConvec
+template <>
+int launch_xfwd<ProConvec>(int NX, const ProConvec& pro, int nfields, const XfOut& out, int ny, int k0,
+                           int nplanes, const cplx* W, const cplx* Wh, cudaStream_t s) {
+    switch (NX) { LG_SIZE_PAIRS(LG_XFWD_CASE_BIG) }
+    return -1;
+}
+}  // namespace lg

@@ -1,0 +1,22 @@
+// shared body of the xfwd_*.cu instantiation files
+#pragma once
+#include "launch.h"
+#include "sizes.h"
+
+namespace lg {
+template <int NX, class Pro>
+static int launch_xfwd_n(const Pro& pro, int nfields, const XfOut& out, int ny, int k0, int nplanes,
+                         const cplx* W, const cplx* Wh, cudaStream_t s) {
+    typedef XCfg<NX> C;
+    static bool attr = false;
+    if (!attr) { set_smem(k_xfwd<NX, Pro>, C::smem); attr = true; }
+    const long nrows = long(ny) * nplanes;
+    if (nrows <= 0) return 0;
+    dim3 grid((unsigned)((nrows + C::NF - 1) / C::NF), nfields);
+    LG_LAUNCH((k_xfwd<NX, Pro>), grid, dim3(kBlock), C::smem, s, pro, out, ny, k0, nplanes, W, Wh);
+    return 0;
+}
+}  // namespace lg
+
+#define LG_XFWD_CASE_SMALL(S, B) case S: return launch_xfwd_n<S, PRO>(pro, nfields, out, ny, k0, nplanes, W, Wh, s);
+#define LG_XFWD_CASE_BIG(S, B) case B: return launch_xfwd_n<B, PRO>(pro, nfields, out, ny, k0, nplanes, W, Wh, s);

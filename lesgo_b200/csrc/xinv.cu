@@ -1,0 +1,34 @@
+#include "launch.h"
+#include "sizes.h"
+namespace lg {
+template <int NX>
+static int launch_xinv_n(const XiSrc& in, const EpiStore& epi, int nfields, int ny, int k0, int nplanes,
+                         const cplx* W, const cplx* Wh, cudaStream_t s) {
+    typedef XCfg<NX> C;
+    static bool attr = false;
+    if (!attr) { set_smem(k_xinv<NX, EpiStore>, C::smem); attr = true; }
+    const long nrows = long(ny) * nplanes;
+    if (nrows <= 0) return 0;
+    dim3 grid((unsigned)((nrows + C::NF - 1) / C::NF), nfields);
+    LG_LAUNCH((k_xinv<NX, EpiStore>), grid, dim3(kBlock), C::smem, s, in, epi, ny, k0, nplanes, W, Wh);
+    return 0;
+}
+#define LG_XINV_CASE_SMALL(S, B) case S: return launch_xinv_n<S>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+int launch_xinv(int NX, const XiSrc& in, const EpiStore& epi, int nfields, int ny, int k0, int nplanes,
+                const cplx* W, const cplx* Wh, cudaStream_t s) {
+    switch (NX) {
+        LG_SIZE_PAIRS(LG_XINV_CASE_SMALL)
+        case 24: return launch_xinv_n<24>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+        case 72: return launch_xinv_n<72>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+        case 120: return launch_xinv_n<120>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+        case 144: return launch_xinv_n<144>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+        case 240: return launch_xinv_n<240>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+        case 288: return launch_xinv_n<288>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+        case 480: return launch_xinv_n<480>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+        case 576: return launch_xinv_n<576>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+        case 768: return launch_xinv_n<768>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+        case 1536: return launch_xinv_n<1536>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+    }
+    return -1;
+}
+}  // namespace lg

@@ -1,0 +1,104 @@
+"""ctypes binding of the C ABI declared in include/lesgo_gpu.h."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class LibraryError(RuntimeError):
+    pass
+
+
+class DimsStruct(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("nz_tot", C.c_int),
+                ("nproc", C.c_int), ("coord", C.c_int),
+                ("L_x", C.c_double), ("L_y", C.c_double), ("dz", C.c_double),
+                ("lbc_mom", C.c_int), ("ubc_mom", C.c_int), ("sgs", C.c_int), ("device", C.c_int)]
+
+
+class StepParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("tadv1", C.c_double), ("tadv2", C.c_double),
+                ("mean_p_force_x", C.c_double), ("mean_p_force_y", C.c_double),
+                ("ubot", C.c_double), ("utop", C.c_double), ("nu_molec_nd", C.c_double),
+                ("first_step", C.c_int), ("mode", C.c_int)]
+
+
+# every symbol include/lesgo_gpu.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_D = C.c_void_p          # double* (host or device address)
+SYMBOLS = {
+    "lesgo_gpu_create": (C.c_int, [C.POINTER(DimsStruct), C.POINTER(_P)]),
+    "lesgo_gpu_destroy": (C.c_int, [_P]),
+    "lesgo_gpu_last_error": (C.c_char_p, [_P]),
+    "lesgo_gpu_set_stream": (C.c_int, [_P, _P]),
+    "lesgo_gpu_synchronize": (C.c_int, [_P]),
+    "lesgo_gpu_launch_count": (C.c_long, [_P]),
+    "lesgo_gpu_profile": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int]),
+    "lesgo_gpu_wavenumbers": (C.c_int, [_P, _D, _D, _D]),
+    "lesgo_gpu_padd": (C.c_int, [_P, _D, _D, C.c_int]),
+    "lesgo_gpu_unpadd": (C.c_int, [_P, _D, _D, C.c_int]),
+    "lesgo_gpu_fft_r2c": (C.c_int, [_P, _D, _D, C.c_int, C.c_int]),
+    "lesgo_gpu_fft_c2r": (C.c_int, [_P, _D, _D, C.c_int, C.c_int]),
+    "lesgo_gpu_ddx": (C.c_int, [_P, _D, _D]),
+    "lesgo_gpu_ddy": (C.c_int, [_P, _D, _D]),
+    "lesgo_gpu_ddxy": (C.c_int, [_P, _D, _D, _D]),
+    "lesgo_gpu_filt_da": (C.c_int, [_P, _D, _D, _D]),
+    "lesgo_gpu_ddz_uv": (C.c_int, [_P, _D, _D]),
+    "lesgo_gpu_ddz_w": (C.c_int, [_P, _D, _D]),
+    "lesgo_gpu_test_filter": (C.c_int, [_P, _D, _D, C.c_int]),
+    "lesgo_gpu_convec": (C.c_int, [_P] + [_D] * 12),
+    "lesgo_gpu_press_stag_array": (C.c_int, [_P, _D, _D, _D, _D, C.c_double, C.c_double, _D, _D, _D, _D]),
+    "lesgo_gpu_tridag_array": (C.c_int, [_P, _D, _D, _D, _D, _D, C.c_int]),
+    "lesgo_gpu_field_ptr": (_P, [_P, C.c_int]),
+    "lesgo_gpu_upload": (C.c_int, [_P, C.c_int, _D]),
+    "lesgo_gpu_download": (C.c_int, [_P, C.c_int, _D]),
+    "lesgo_gpu_step": (C.c_int, [_P, C.POINTER(StepParams)]),
+    "lesgo_gpu_max_cfl": (C.c_int, [_P, C.c_double, C.POINTER(C.c_double)]),
+    "lesgo_gpu_rmsdiv": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "lesgo_gpu_comm_unique_id": (C.c_int, [_P]),
+    "lesgo_gpu_comm_init": (C.c_int, [_P, _P]),
+    "lesgo_gpu_sync_real_array": (C.c_int, [_P, _D, C.c_int]),
+}
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "liblesgo_cuda.so")
+
+
+class Library:
+    """A loaded liblesgo_cuda.so with typed entry points."""
+
+    def __init__(self, path: str | None = None):
+        self.path = path or library_path()
+        if not os.path.exists(self.path):
+            raise LibraryError(
+                f"{self.path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  lesgo_b200 has no CPU fallback.")
+        try:
+            self.dll = C.CDLL(self.path)
+        except OSError as e:
+            raise LibraryError(f"cannot load {self.path}: {e}") from e
+        for name, (res, args) in SYMBOLS.items():
+            try:
+                fn = getattr(self.dll, name)
+            except AttributeError as e:
+                raise LibraryError(f"{self.path} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name[len("lesgo_gpu_"):], fn)
+
+    def error(self, ctx=None) -> str:
+        s = self.last_error(ctx)
+        return s.decode() if s else ""
+
+
+_LIB = None
+
+
+def load_library() -> Library:
+    global _LIB
+    if _LIB is None:
+        _LIB = Library()
+    return _LIB

@@ -1,0 +1,175 @@
+"""Shared helpers for the parity tests (CUDA library on the GPU box, kernel-logic
+emulator on the CPU-only container).  Test infrastructure only."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import lesgo_oracle as O  # noqa: E402
+import lesgo_b200  # noqa: E402
+
+EMUL_SO = os.path.join(ROOT, "tests", "emul", "_build", "liblesgo_emul.so")
+_emul_lib = None
+
+
+def emul_library():
+    """Build (once) and load the CPU kernel-logic emulator: the product .cu sources compiled
+    with g++ -DLESGO_EMUL.  Only tests use it; lesgo_b200 itself never loads it."""
+    global _emul_lib
+    if _emul_lib is None:
+        subprocess.run([os.path.join(ROOT, "tests", "emul", "build_emul.sh")], check=True,
+                       stdout=subprocess.DEVNULL)
+        _emul_lib = lesgo_b200.Library(EMUL_SO)
+    return _emul_lib
+
+
+def rel(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def make_dims(p: O.Params, device=-1):
+    return lesgo_b200.Dims(nx=p.nx, ny=p.ny, Nz=p.Nz, nproc=p.nproc, coord=p.coord, L_x=p.L_x, L_y=p.L_y,
+                           L_z=p.L_z, lbc_mom=p.lbc_mom, ubc_mom=p.ubc_mom, sgs=p.sgs, device=device)
+
+
+def random_field(p, seed, planes=None):
+    rng = np.random.default_rng(seed)
+    n = p.nz + 1 if planes is None else planes
+    f = np.zeros((n, p.ny, p.ld))
+    f[:, :, :p.nx] = rng.standard_normal((n, p.ny, p.nx))
+    return f
+
+
+def initial_state(p: O.Params, seed=11, amp=0.3):
+    """Oracle State for rank p.coord from the synthetic global channel field."""
+    u, v, w = O.synthetic_global(p.nx, p.ny, p.Nz, nproc=p.nproc, seed=seed, amp=amp, L_x=p.L_x, L_y=p.L_y,
+                                 L_z=p.L_z)
+    s = O.State(p)
+    s.u, s.v, s.w = (O.scatter_slab(f, p) for f in (u, v, w))
+    return s
+
+
+# ---- the routine-by-routine comparisons, shared by the emulator and the GPU tests -----------------
+def check_derivatives(core, p, tol=1e-13):
+    sp = O.Spectral(p)
+    nx, nz = p.nx, p.nz
+    f = random_field(p, 1)
+    out = {}
+    fx, fy = O.ddxy(f, sp)
+    gx, gy = core.empty(), core.empty()
+    core.ddxy(f.copy(), gx, gy)
+    out["ddxy_x"] = rel(gx[:, :, :nx], fx[:, :, :nx]); out["ddxy_y"] = rel(gy[:, :, :nx], fy[:, :, :nx])
+    g = core.empty(); core.ddx(f.copy(), g); out["ddx"] = rel(g[:, :, :nx], fx[:, :, :nx])
+    g = core.empty(); core.ddy(f.copy(), g); out["ddy"] = rel(g[:, :, :nx], fy[:, :, :nx])
+    ff, fx, fy = O.filt_da(f, sp)
+    h = f.copy(); core.filt_da(h, gx, gy)
+    out["filt_da_f"] = rel(h[:, :, :nx], ff[:, :, :nx])
+    out["filt_da_x"] = rel(gx[:, :, :nx], fx[:, :, :nx]); out["filt_da_y"] = rel(gy[:, :, :nx], fy[:, :, :nx])
+    d = O.ddz_uv(f, p); g = core.empty(); core.ddz_uv(f, g)
+    lo = 2 if p.coord == 0 else 1
+    hi = nz - 1 if p.coord == p.nproc - 1 else nz
+    out["ddz_uv"] = float(np.abs(g[lo:hi + 1, :, :nx] - d[lo:hi + 1, :, :nx]).max())
+    assert g[0, 0, 0] == O.BOGUS
+    d = O.ddz_w(f, p); g = core.empty(); core.ddz_w(f, g)
+    lo = 1 if p.coord == 0 else 0
+    out["ddz_w"] = float(np.abs(g[lo:nz, :, :nx] - d[lo:nz, :, :nx]).max())
+    assert g[nz, 0, 0] == O.BOGUS
+    for k, v in out.items():
+        assert v <= (0.0 if k.startswith("ddz") else tol), (k, v, out)
+    return out
+
+
+def check_fft_raw(core, p, tol=1e-14):
+    sp = O.Spectral(p)
+    out = {}
+    f = random_field(p, 2, planes=3)
+    ref = sp.forw(f)
+    got = core.fft_r2c(f.copy())
+    out["r2c"] = rel(got, ref)
+    back = core.fft_c2r(ref.copy())
+    out["c2r"] = rel(back[:, :, :p.nx], sp.back(ref)[:, :, :p.nx])
+    fb = np.zeros((2, p.ny2, p.ld_big))
+    fb[:, :, :p.nx2] = np.random.default_rng(3).standard_normal((2, p.ny2, p.nx2))
+    refb = sp.forw_big(fb)
+    out["r2c_big"] = rel(core.fft_r2c(fb.copy(), big=True), refb)
+    out["c2r_big"] = rel(core.fft_c2r(refb.copy(), big=True)[:, :, :p.nx2], sp.back_big(refb)[:, :, :p.nx2])
+    # padd / unpadd are exact copies
+    ub = np.full((3, p.ny2, p.ld_big), 7.0)
+    core.padd(ub, ref)
+    assert np.array_equal(ub, sp.padd(ref))
+    cc = np.full((2, p.ny, p.ld), 7.0)
+    core.unpadd(cc, refb)
+    assert np.array_equal(cc, sp.unpadd(refb))
+    # test_filter
+    G = O.test_filter_kernel(sp)
+    tf = core.test_filter(f.copy(), G)
+    out["test_filter"] = rel(tf[:, :, :p.nx], O.test_filter(f, sp, G)[:, :, :p.nx])
+    for k, v in out.items():
+        assert v <= tol, (k, v, out)
+    return out
+
+
+def check_convec(core, p, tol=1e-13):
+    sp = O.Spectral(p)
+    nx, nz = p.nx, p.nz
+    s = O.State(p)
+    for i, n in enumerate(("u", "v", "w", "dudy", "dudz", "dvdx", "dvdz", "dwdx", "dwdy")):
+        setattr(s, n, random_field(p, 20 + i))
+    Rx, Ry, Rz = O.convec(s, sp)
+    gx, gy, gz = core.empty(), core.empty(), core.empty()
+    core.convec(s.u, s.v, s.w, s.dudy, s.dudz, s.dvdx, s.dvdz, s.dwdx, s.dwdy, gx, gy, gz)
+    out = {"RHSx": rel(gx[1:nz, :, :nx], Rx[1:nz, :, :nx]), "RHSy": rel(gy[1:nz, :, :nx], Ry[1:nz, :, :nx])}
+    hi = nz + 1 if p.coord == p.nproc - 1 else nz
+    out["RHSz"] = rel(gz[1:hi, :, :nx], Rz[1:hi, :, :nx])
+    assert gx[0, 0, 0] == O.BOGUS and gx[nz, 0, 0] == O.BOGUS
+    for k, v in out.items():
+        assert v <= tol, (k, v, out)
+    return out
+
+
+def check_press(core, p, tol=1e-11):
+    sp = O.Spectral(p)
+    nx, nz = p.nx, p.nz
+    s = initial_state(p, seed=31)
+    s.divtz = 0.1 * random_field(p, 32)
+    pr, dpdx, dpdy, dpdz = O.press_stag_array(s, sp, O.LocalComm())
+    g = [core.empty() for _ in range(4)]
+    core.press_stag_array(s.u, s.v, s.w, s.divtz, p.dt, p.tadv1, *g)
+    out = {"p": rel(g[0][0:nz + 1, :, :nx], pr[0:nz + 1, :, :nx]),
+           "dpdx": rel(g[1][1:nz, :, :nx], dpdx[1:nz, :, :nx]),
+           "dpdy": rel(g[2][1:nz, :, :nx], dpdy[1:nz, :, :nx]),
+           "dpdz": rel(g[3][1:nz + 1, :, :nx], dpdz[1:nz + 1, :, :nx])}
+    for k, v in out.items():
+        assert v <= tol, (k, v, out)
+    return out
+
+
+def check_steps(core, p, nsteps=1, tol=1e-12, seed=41, names=("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")):
+    """nsteps of the device-resident core step vs oracle.step(mode='core') from identical fields."""
+    sp = O.Spectral(p)
+    nx, nz = p.nx, p.nz
+    s = initial_state(p, seed=seed)
+    for n in ("u", "v", "w"):
+        core.upload(n, getattr(s, n))
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+        core.upload(n, np.zeros(core.dims.shape))
+    for it in range(nsteps):
+        O.step(s, sp, O.LocalComm(), mode="core", first_step=(it == 0))
+        core.step(p.dt, p.tadv1, p.tadv2, first_step=(it == 0), mode=0, ubot=p.ubot, utop=p.utop,
+                  mean_p_force_x=p.mean_p_force_x if p.use_mean_p_force else 0.0,
+                  mean_p_force_y=p.mean_p_force_y if p.use_mean_p_force else 0.0)
+    out = {}
+    for n in names:
+        g = core.download(n)
+        r = getattr(s, n)
+        hi = nz + 1 if n in ("w", "RHSz", "p") else nz
+        out[n] = rel(g[1:hi, :, :nx], r[1:hi, :, :nx])
+    for k, v in out.items():
+        assert v <= tol, (k, v, out)
+    return out

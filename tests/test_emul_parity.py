@@ -1,0 +1,42 @@
+"""CPU-side checks of the product kernels' LOGIC: the same .cu sources compiled for the
+host (tests/emul) must reproduce the oracle.  These run in the GPU-less container; the
+real parity tests (tests/test_gpu_parity.py, -m gpu) run the sm_100a build on a B200."""
+import shutil
+
+import numpy as np
+import pytest
+
+import lesgo_b200
+from helpers import (O, check_convec, check_derivatives, check_fft_raw, check_press, check_steps,
+                     emul_library, make_dims)
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the emulator")
+
+
+def core_for(p):
+    return lesgo_b200.Core(make_dims(p), lib=emul_library())
+
+
+@pytest.mark.parametrize("nx,ny,Nz", [(16, 16, 4), (32, 16, 5), (48, 32, 3), (80, 48, 3)])
+def test_emul_derivatives_and_raw_fft(nx, ny, Nz):
+    p = O.Params(nx=nx, ny=ny, Nz=Nz, L_x=4.0, L_y=3.0)
+    c = core_for(p)
+    check_derivatives(c, p)
+    check_fft_raw(c, p)
+
+
+@pytest.mark.parametrize("bc", [(1, 1, False), (0, 0, False), (2, 2, True), (1, 0, True)])
+def test_emul_convec(bc):
+    p = O.Params(nx=16, ny=16, Nz=6, lbc_mom=bc[0], ubc_mom=bc[1], sgs=bc[2])
+    check_convec(core_for(p), p)
+
+
+def test_emul_press():
+    p = O.Params(nx=16, ny=16, Nz=8)
+    check_press(core_for(p), p)
+
+
+def test_emul_steps():
+    p = O.Params(nx=16, ny=16, Nz=8, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5,
+                 use_mean_p_force=True, mean_p_force_x=1.0)
+    check_steps(core_for(p), p, nsteps=2, tol=1e-11)

@@ -2,9 +2,81 @@
 #include "comm.h"
 
 #ifdef LESGO_EMUL
+// Emulator build: ranks are threads of one process; messages go through in-process queues.
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <vector>
 namespace lg {
-int Comm::unique_id(void* id128, std::string* err) { (void)id128; if (err) *err = "emulator build has no NCCL"; return 1; }
-Comm* Comm::create(const void*, int, int, std::string* err) { if (err) *err = "emulator build has no NCCL"; return nullptr; }
+namespace {
+struct World {
+    std::mutex m;
+    std::condition_variable cv;
+    std::map<std::pair<int, int>, std::deque<std::vector<double>>> q;   // (src, dst) -> FIFO
+};
+std::mutex g_worlds_m;
+std::map<std::string, std::shared_ptr<World>> g_worlds;
+
+class EmulComm : public Comm {
+public:
+    std::shared_ptr<World> w;
+    void put(int dst, const double* p, size_t n) {
+        std::lock_guard<std::mutex> l(w->m);
+        w->q[{rank_, dst}].emplace_back(p, p + n);
+        w->cv.notify_all();
+    }
+    void get(int src, double* p, size_t n) {
+        std::unique_lock<std::mutex> l(w->m);
+        auto& dq = w->q[{src, rank_}];
+        w->cv.wait(l, [&] { return !dq.empty(); });
+        std::memcpy(p, dq.front().data(), n * sizeof(double));
+        dq.pop_front();
+    }
+    int exchange(int n, const double* const* sendbuf, const int* dest, double* const* recvbuf, const int* src,
+                 const size_t* count, cudaStream_t) override {
+        for (int i = 0; i < n; ++i) if (dest[i] >= 0 && dest[i] < nranks_) put(dest[i], sendbuf[i], count[i]);
+        for (int i = 0; i < n; ++i) if (src[i] >= 0 && src[i] < nranks_) get(src[i], recvbuf[i], count[i]);
+        return 0;
+    }
+    int allreduce(double* v, int op, cudaStream_t) override {
+        for (int r = 0; r < nranks_; ++r) if (r != rank_) put(r, v, 1);
+        double acc = *v;
+        for (int r = 0; r < nranks_; ++r) {
+            if (r == rank_) continue;
+            double x; get(r, &x, 1);
+            acc = op == 0 ? acc + x : (op == 1 ? (x > acc ? x : acc) : (x < acc ? x : acc));
+        }
+        *v = acc;
+        return 0;
+    }
+    int alltoall(const double* sendbuf, double* recvbuf, size_t count, cudaStream_t) override {
+        for (int r = 0; r < nranks_; ++r) put(r, sendbuf + size_t(r) * count, count);
+        for (int r = 0; r < nranks_; ++r) get(r, recvbuf + size_t(r) * count, count);
+        return 0;
+    }
+    void set(int r, int n) { rank_ = r; nranks_ = n; }
+};
+}  // namespace
+int Comm::unique_id(void* id128, std::string*) {
+    std::random_device rd;
+    unsigned char* b = static_cast<unsigned char*>(id128);
+    for (int i = 0; i < 128; ++i) b[i] = static_cast<unsigned char>('a' + rd() % 26);
+    return 0;
+}
+Comm* Comm::create(const void* id128, int rank, int nranks, std::string*) {
+    std::string key(static_cast<const char*>(id128), 128);
+    EmulComm* c = new EmulComm;
+    c->set(rank, nranks);
+    std::lock_guard<std::mutex> l(g_worlds_m);
+    auto& w = g_worlds[key];
+    if (!w) w = std::make_shared<World>();
+    c->w = w;
+    return c;
+}
 }  // namespace lg
 #else
 #include <dlfcn.h>

@@ -369,7 +369,8 @@ int tridag_setup(lesgo_gpu_ctx* c, TriGeom& g) {
 
 int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, const double* divtz, double dt,
           double tadv1, double* p, double* dpdx, double* dpdy, double* dpdz) {
-    if (c->d.nproc > 1) return c->fail("press_stag_array: nproc > 1 needs lesgo_gpu_comm_init (multi-GPU path)");
+    if (c->d.nproc > 1 && !c->comm) return c->fail("press_stag_array: nproc > 1 needs lesgo_gpu_comm_init first");
+    if (c->d.nproc > 1 && (c->ny % c->d.nproc)) return c->fail("press_stag_array: ny must be divisible by nproc");
     if (need_small(c, 6)) return 1;
     const int nz = c->nz, nxh = c->nx / 2;
     const double cst = 1.0 / (double(c->nx) * double(c->ny));
@@ -401,20 +402,75 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         e.fld[0].src = c->sa[3]; e.fld[0].out[0] = YOutSpec{c->sa[3], Y_COPY};
         if (c->bottom && ypass(c, c->ny, 0, e, 1, 1, 2)) return 1;
     }
-    // (3) tridiagonal solve with fused right-hand side + k=0 chain                 :149-239
-    TriGeom g;
-    if (tridag_setup(c, g)) return 1;
-    {
+    // (3) tridiagonal solve + k=0 chain                                           :149-239
+    double* phat = c->sa[4];
+    if (c->d.nproc == 1) {
+        TriGeom g;
+        if (tridag_setup(c, g)) return 1;
         const int nm = (c->lh - 1) * c->ny;
         ProfScope ps_(c, "tridag");
         LG_LAUNCH(k_tridag_fused, dim3((nm + 127) / 128), dim3(128), 0, c->stream, g, c->sa[0], c->sa[1],
                   c->sa[2], c->sa[3] + c->plane, c->sa[3] + c->plane * nz, c->gam, c->sa[4]);
         c->launches++;
+    } else {
+        // slabs -> pencils -> Thomas -> slabs (see PencilGeom in ops.h); replaces the rank-serial
+        // pipeline of tridag_array.f90:22-162 and the halo/chain messages C4-C7.
+        PencilGeom g;
+        g.lh = c->lh; g.ny = c->ny; g.ld = c->ld; g.nz = nz; g.nproc = c->d.nproc; g.coord = c->d.coord;
+        g.cy = c->ny / c->d.nproc; g.plane = c->plane; g.kxs = c->kxs; g.kys = c->kys; g.dz = c->d.dz;
+        {   // rH_z(1) of coord+1 -> rH_z(nz) of coord                             :184-185
+            const double* sb[1] = {c->sa[2] + c->plane};
+            double* rb[1] = {c->sa[2] + c->plane * nz};
+            int dest[1] = {c->d.coord - 1}, src[1] = {c->d.coord + 1};
+            size_t cnt[1] = {size_t(c->plane)};
+            ProfScope ps_(c, "halo");
+            if (c->comm->exchange(1, sb, dest, rb, src, cnt, c->stream)) return c->fail(c->comm->error());
+        }
+        if (!c->gam) {
+            if (dev_alloc(c, &c->gam, size_t(c->nzt + 2) * g.cy * c->lh)) return 1;
+            const int nm = (c->lh - 1) * g.cy;
+            LG_LAUNCH(k_tridag_setup_pencil, dim3((nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam);
+            c->launches++;
+        }
+        {
+            ProfScope ps_(c, "press_pack");
+            LG_LAUNCH(k_press_pack, dim3(grid1d(long(c->lh - 1) * c->ny * nz)), dim3(kBlock), 0, c->stream, g, c->sa[0],
+                      c->sa[1], c->sa[2], c->sa[3] + c->plane, c->sa[3] + c->plane * nz, c->sa[4]);
+            c->launches++;
+        }
+        {
+            ProfScope ps_(c, "alltoall");
+            if (c->comm->alltoall(c->sa[4], c->sa[5], size_t(g.block()), c->stream)) return c->fail(c->comm->error());
+        }
+        {
+            const int nm = (c->lh - 1) * g.cy;
+            ProfScope ps_(c, "tridag");
+            LG_LAUNCH(k_tridag_pencil, dim3((nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, c->sa[5]);
+            c->launches++;
+        }
+        {
+            ProfScope ps_(c, "alltoall");
+            if (c->comm->alltoall(c->sa[5], c->sa[4], size_t(g.block()), c->stream)) return c->fail(c->comm->error());
+        }
+        {
+            ProfScope ps_(c, "press_unpack");
+            LG_LAUNCH(k_press_unpack, dim3(grid1d(long(c->lh) * c->ny * nz)), dim3(kBlock), 0, c->stream, g, c->sa[4], c->sa[3]);
+            c->launches++;
+        }
+        phat = c->sa[3];
+        {   // p(nz-1) of coord -> p(0) of coord+1                                  :241-246
+            const double* sb[1] = {phat + c->plane * (nz - 1)};
+            double* rb[1] = {phat};
+            int dest[1] = {c->d.coord + 1}, src[1] = {c->d.coord - 1};
+            size_t cnt[1] = {size_t(c->plane)};
+            ProfScope ps_(c, "halo");
+            if (c->comm->exchange(1, sb, dest, rb, src, cnt, c->stream)) return c->fail(c->comm->error());
+        }
     }
     // (4) y inverse of p, i kx p, i ky p (oddballs dropped), x inverse              :248-273
     {
         YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, 0);
-        a.fld[0].src = c->sa[4];
+        a.fld[0].src = phat;
         a.fld[0].out[0] = YOutSpec{c->sa[0], Y_COPY};
         a.fld[0].out[1] = YOutSpec{c->sa[1], Y_IKX};
         a.fld[0].out[2] = YOutSpec{c->sa[2], Y_IKY};

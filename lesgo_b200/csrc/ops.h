@@ -472,4 +472,155 @@ static __global__ void k_tridag_general(int lh, int ny, int n, int ld, const dou
     }
 }
 
+// ---- multi-rank pressure solve: z-slabs -> (kx,ky)-pencils and back -----------------------------
+// The tridiagonal systems couple all z-slabs.  Each rank assembles the right-hand-side rows it
+// owns, an all-to-all turns slabs into pencils (every rank gets ALL rows of ny/nproc ky-rows,
+// the layout mpi_transpose_mod.f90 sketches), the Thomas sweep runs un-split with exactly the
+// arithmetic of tridag_array.f90, and a second all-to-all returns p_hat.  Row ownership: rank 0
+// owns local rows 1..nz, every other rank rows 2..nz+1 (row nz+1 is real only on the top rank),
+// i.e. `nz` block rows per rank; block row i of rank r is local row i + (r ? 2 : 1).
+struct PencilGeom {
+    int lh, ny, ld, nz, nproc, coord;
+    int cy;                 // ky rows per pencil chunk = ny / nproc
+    long plane;             // ld * ny
+    double kxs, kys, dz;
+    LG_HD long block() const { return long(nz) * cy * ld; }     // doubles per (src, dst) block
+};
+
+// send layout: buf[dst q][block row i][jy_local][ld]
+static __global__ void k_press_pack(PencilGeom g, const double* __restrict__ Hx, const double* __restrict__ Hy,
+                                    const double* __restrict__ Hz, const double* __restrict__ rbot,
+                                    const double* __restrict__ rtop, double* __restrict__ buf) {
+    const int lhm = g.lh - 1;
+    const long n = long(lhm) * g.ny * g.nz;
+    const double c4 = ddiv(1.0, g.dz);
+    const bool bottom = g.coord == 0, top = g.coord == g.nproc - 1;
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        const int jx = int(t % lhm);
+        long r = t / lhm;
+        const int jy = int(r % g.ny), i = int(r / g.ny);
+        const int j = i + (bottom ? 1 : 2);                       // local system row
+        const long mo = long(jy) * g.ld + 2 * jx;
+        double2 v;
+        if (j == 1) {                                             // bottom Neumann row (:160)
+            double2 rb = ld2(rbot + mo);
+            v = make_double2(dmul(-g.dz, rb.x), dmul(-g.dz, rb.y));
+        } else if (j == g.nz + 1) {                               // top Neumann row (:173), top rank only
+            if (top) { double2 rt = ld2(rtop + mo); v = make_double2(dmul(-g.dz, rt.x), dmul(-g.dz, rt.y)); }
+            else v = make_double2(0.0, 0.0);
+        } else if (jx == 0 && jy == 0) {
+            v = ld2(Hz + long(j) * g.plane + mo);                 // k=0 chain needs H_z itself (:232)
+        } else {
+            const double kx = g.kxs * double(jx);
+            const double ky = g.kys * double(jy < g.ny / 2 ? jy : jy - g.ny);
+            double2 hx = ld2(Hx + long(j - 1) * g.plane + mo), hy = ld2(Hy + long(j - 1) * g.plane + mo);
+            double2 hz = ld2(Hz + long(j) * g.plane + mo), hzm = ld2(Hz + long(j - 1) * g.plane + mo);
+            v.x = dadd(dadd(dmul(-hx.y, kx), dmul(-hy.y, ky)), dmul(dsub(hz.x, hzm.x), c4));
+            v.y = dadd(dadd(dmul(hx.x, kx), dmul(hy.x, ky)), dmul(dsub(hz.y, hzm.y), c4));
+        }
+        const int q = jy / g.cy, jl = jy % g.cy;
+        *reinterpret_cast<double2*>(buf + q * g.block() + (long(i) * g.cy + jl) * g.ld + 2 * jx) = v;
+    }
+}
+
+// gam table in pencil layout: gam[global row][jy_local][jx]
+static __global__ void k_tridag_setup_pencil(PencilGeom g, int nzt, double* __restrict__ gam) {
+    const int nm = (g.lh - 1) * g.cy;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nm) return;
+    const int jx = t % (g.lh - 1), jl = t / (g.lh - 1), jy = g.coord * g.cy + jl;
+    if (jy == g.ny / 2 || (jx == 0 && jy == 0)) return;
+    const double c3 = ddiv(1.0, dmul(g.dz, g.dz));
+    const double kx = g.kxs * double(jx);
+    const double ky = g.kys * double(jy < g.ny / 2 ? jy : jy - g.ny);
+    const double bb = -dadd(dadd(dmul(kx, kx), dmul(ky, ky)), dmul(2.0, c3));
+    const int n = nzt + 1;
+    double bet = -1.0, cprev = 1.0;
+    for (int j = 2; j <= n; ++j) {
+        const double a = (j == n) ? -1.0 : c3;
+        const double b = (j == n) ? 1.0 : bb;
+        const double gm = ddiv(cprev, bet);
+        bet = dsub(b, dmul(a, gm));
+        gam[(long(j) * g.cy + jl) * g.lh + jx] = gm;
+        cprev = c3;
+    }
+}
+
+// recv layout: buf[src r][block row i][jy_local][ld]; solved in place.
+static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __restrict__ gam, double* __restrict__ buf) {
+    const int nm = (g.lh - 1) * g.cy;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nm) return;
+    const int jx = t % (g.lh - 1), jl = t / (g.lh - 1), jy = g.coord * g.cy + jl;
+    if (jy == g.ny / 2) return;
+    const int n = nzt + 1;
+    const long mo = long(jl) * g.ld + 2 * jx;
+    const long rs = long(g.cy) * g.ld;                            // doubles between block rows
+    // global row gj (1..n) -> address
+    auto at = [&](int gj) -> double* {
+        int r, i;
+        if (gj <= g.nz) { r = 0; i = gj - 1; }
+        else {
+            r = (gj - 2) / (g.nz - 1);
+            if (r > g.nproc - 1) r = g.nproc - 1;
+            i = gj - r * (g.nz - 1) - 2;
+        }
+        return buf + r * g.block() + i * rs + mo;
+    };
+    if (jx == 0 && jy == 0) {
+        // zero-wavenumber chain (press_stag_array.f90:226-234): row 1 holds -dz*rbottomw = p(1),
+        // rows 2..nzt hold H_z(0,0,k); p(k) is system row k+1.
+        double2 pk = ld2(at(1));                                  // p(1) = 0 - dz*rbottomw
+        *reinterpret_cast<double2*>(at(1)) = make_double2(0.0, 0.0);   // p(0) = 0
+        double2 carry = pk;
+        for (int k = 2; k <= nzt; ++k) {
+            double2 h = ld2(at(k));
+            *reinterpret_cast<double2*>(at(k)) = carry;           // row k = p(k-1)
+            carry = make_double2(dadd(carry.x, dmul(h.x, g.dz)), dadd(carry.y, dmul(h.y, g.dz)));
+        }
+        *reinterpret_cast<double2*>(at(n)) = carry;               // row n = p(nzt)
+        return;
+    }
+    const double c3 = ddiv(1.0, dmul(g.dz, g.dz));
+    const double kx = g.kxs * double(jx);
+    const double ky = g.kys * double(jy < g.ny / 2 ? jy : jy - g.ny);
+    const double bb = -dadd(dadd(dmul(kx, kx), dmul(ky, ky)), dmul(2.0, c3));
+    double2 r1 = ld2(at(1));
+    double2 u = make_double2(ddiv(r1.x, -1.0), ddiv(r1.y, -1.0));
+    *reinterpret_cast<double2*>(at(1)) = u;
+    double bet = -1.0;
+    for (int j = 2; j <= n; ++j) {
+        const double a = (j == n) ? -1.0 : c3;
+        const double b = (j == n) ? 1.0 : bb;
+        double* pj = at(j);
+        double2 r = ld2(pj);
+        const double gm = gam[(long(j) * g.cy + jl) * g.lh + jx];
+        bet = dsub(b, dmul(a, gm));
+        u = make_double2(ddiv(dsub(r.x, dmul(a, u.x)), bet), ddiv(dsub(r.y, dmul(a, u.y)), bet));
+        *reinterpret_cast<double2*>(pj) = u;
+    }
+    for (int j = n - 1; j >= 1; --j) {
+        const double gm = gam[(long(j + 1) * g.cy + jl) * g.lh + jx];
+        double* pj = at(j);
+        double2 uj = ld2(pj);
+        u = make_double2(dsub(uj.x, dmul(gm, u.x)), dsub(uj.y, dmul(gm, u.y)));
+        *reinterpret_cast<double2*>(pj) = u;
+    }
+}
+
+// after the return all-to-all: buf[src q = ky chunk][block row i][jy_local][ld] -> p_hat planes
+static __global__ void k_press_unpack(PencilGeom g, const double* __restrict__ buf, double* __restrict__ p) {
+    const long n = long(g.lh) * g.ny * g.nz;
+    const bool bottom = g.coord == 0;
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        const int jx = int(t % g.lh);
+        long r = t / g.lh;
+        const int jy = int(r % g.ny), i = int(r / g.ny);
+        const int k = i + (bottom ? 0 : 1);                       // plane = local row - 1
+        const int q = jy / g.cy, jl = jy % g.cy;
+        double2 v = ld2(buf + q * g.block() + (long(i) * g.cy + jl) * g.ld + 2 * jx);
+        *reinterpret_cast<double2*>(p + long(k) * g.plane + long(jy) * g.ld + 2 * jx) = v;
+    }
+}
+
 }  // namespace lg

@@ -173,3 +173,56 @@ def check_steps(core, p, nsteps=1, tol=1e-12, seed=41, names=("u", "v", "w", "p"
     for k, v in out.items():
         assert v <= tol, (k, v, out)
     return out
+
+
+def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None):
+    """nproc ranks (threads of this process, one Core each) advance `nsteps` core steps;
+    the gathered result must match the SINGLE-slab oracle (which the multi-slab oracle
+    equals, tests/test_oracle_kat.py)."""
+    import threading
+    pg = O.Params(nproc=1, **kw)
+    spg = O.Spectral(pg)
+    ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=seed, amp=0.3, L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+    sref = O.State(pg)
+    sref.u, sref.v, sref.w = (O.scatter_slab(f, pg) for f in (ug, vg, wg))
+    for it in range(nsteps):
+        O.step(sref, spg, O.LocalComm(), mode="core", first_step=(it == 0))
+    ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
+    cores = [lesgo_b200.Core(make_dims(p, device=(device_of(p.coord) if device_of else -1)), lib=lib) for p in ps]
+    ident = cores[0].comm_unique_id()
+    res, err = [None] * nproc, [None] * nproc
+
+    def work(r):
+        try:
+            p, c = ps[r], cores[r]
+            c.comm_init(ident)
+            for n, g in (("u", ug), ("v", vg), ("w", wg)):
+                c.upload(n, O.scatter_slab(g, p))
+            for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+                c.upload(n, np.zeros(c.dims.shape))
+            for it in range(nsteps):
+                c.step(p.dt, p.tadv1, p.tadv2, first_step=(it == 0), mode=0, ubot=p.ubot, utop=p.utop,
+                       mean_p_force_x=p.mean_p_force_x if p.use_mean_p_force else 0.0)
+            res[r] = {n: c.download(n) for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")}
+            res[r]["cfl"] = c.max_cfl(p.dt)
+        except BaseException as e:  # noqa
+            err[r] = e
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(nproc)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for e in err:
+        if e is not None:
+            raise e
+    out = {}
+    nzt = pg.nz_tot
+    for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz"):
+        top = n in ("w", "RHSz", "p")
+        g = O.gather_slabs([res[r][n] for r in range(nproc)], ps, top_extra=top)
+        hi = nzt if top else nzt - 1
+        out[n] = rel(g[1:hi + 1, :, :pg.nx], getattr(sref, n)[1:hi + 1, :, :pg.nx])
+    cfl_ref = O.get_max_cfl(sref, pg, O.LocalComm())
+    assert all(abs(res[r]["cfl"] - cfl_ref) <= 1e-12 * cfl_ref for r in range(nproc)), (cfl_ref, [res[r]["cfl"] for r in range(nproc)])
+    for k, v in out.items():
+        assert v <= tol, (k, v, out)
+    return out

@@ -40,3 +40,14 @@ def test_emul_steps():
     p = O.Params(nx=16, ny=16, Nz=8, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5,
                  use_mean_p_force=True, mean_p_force_x=1.0)
     check_steps(core_for(p), p, nsteps=2, tol=1e-11)
+
+
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_emul_multirank_steps(nproc):
+    """z-slab ranks as threads over the in-process comm backend: ghost-plane sync, the
+    slab->pencil transposes of the pressure solve and the k=0 chain."""
+    from helpers import check_multirank_steps
+    kw = dict(nx=16, ny=16, Nz=8, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5,
+              use_mean_p_force=True, mean_p_force_x=1.0)
+    out = check_multirank_steps(emul_library(), kw, nproc, nsteps=2)
+    print(out)

@@ -26,9 +26,9 @@ def _newest_header():
     return max(t, os.path.getmtime(inc))
 
 
-def _compile(src, log_dir):
-    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-    cmd = ["nvcc", *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+def _compile(src, log_dir, defines=()):
+    obj = os.path.join(log_dir, src.replace(".cu", ".o"))
+    cmd = ["nvcc", *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(os.path.join(log_dir, src + ".ptxas.log"), "w") as f:
         f.write(r.stdout)
@@ -37,9 +37,12 @@ def _compile(src, log_dir):
     return obj
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
+def build(force: bool = False, verbose: bool = True, defines=(), target: str = TARGET, obj_dir: str = OBJ) -> str:
+    """defines/target/obj_dir let a developer build an experimental variant next to the product library."""
     if shutil.which("nvcc") is None:
         raise RuntimeError("nvcc not found: liblesgo_cuda.so can only be built with the CUDA toolkit")
+    OBJ = obj_dir
+    TARGET = target
     os.makedirs(OBJ, exist_ok=True)
     hdr_t = _newest_header()
     todo = []
@@ -52,7 +55,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         if verbose:
             print(f"[lesgo_b200.build] nvcc sm_100a: {', '.join(todo)}", file=sys.stderr)
         with cf.ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
-            list(ex.map(lambda s: _compile(s, OBJ), todo))
+            list(ex.map(lambda s: _compile(s, OBJ, defines), todo))
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if todo or not os.path.exists(TARGET):
         cmd = ["nvcc", "-shared", "-Xlinker", "-Bsymbolic", "-o", TARGET, *objs, "-ldl"]
@@ -63,4 +66,10 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    if defs:
+        tag = "_".join(d.lower() for d in defs)
+        print(build(force="--force" in sys.argv, defines=defs, target=os.path.join(HERE, f"liblesgo_cuda.{tag}.so"),
+                    obj_dir=os.path.join(CSRC, "_obj_" + tag)))
+    else:
+        print(build(force="--force" in sys.argv))

@@ -225,7 +225,11 @@ LG_PLAN(480, 10, 8, 6, 1)
 LG_PLAN(512, 8, 8, 8, 1)
 LG_PLAN(576, 8, 12, 6, 1)
 LG_PLAN(640, 8, 10, 8, 1)
+#ifdef LG_PLAN768_4STAGE
+LG_PLAN(768, 8, 8, 4, 3)
+#else
 LG_PLAN(768, 8, 12, 8, 1)
+#endif
 LG_PLAN(1024, 8, 4, 4, 8)
 LG_PLAN(1536, 8, 6, 4, 8)
 #undef LG_PLAN
@@ -243,24 +247,29 @@ template <int N> struct PlanInfo {
 };
 
 // ---------------------------------------------------------------------------------
-// One Stockham stage for work item j (0 <= j < N/R).
+// One Stockham stage for work item j (0 <= j < N/R), split into its load+butterfly half
+// and its store half so a block can run the stage IN PLACE on one shared buffer (all
+// loads, barrier, all stores).
 //   INV = false: forward (sign -1); true: inverse (sign +1, unnormalised).
 //   ld(idx) -> cplx   : fetch logical element idx of the stage input
 //   st(idx, cplx)     : deliver logical element idx of the stage output
-//   W                 : table W_N[m] = exp(-2 pi i m / N), m = 0..N-1
+//   W                 : table W_N[m] = exp(-2 pi i m / N), m = 0..N/2-1 (shared memory)
 // ---------------------------------------------------------------------------------
-template <int N, int R, int Ns, bool INV, class Ld, class St>
-LG_HD void fft_stage(int j, const cplx* __restrict__ W, Ld ld, St st) {
+template <int N, int R, int Ns, bool INV, class Ld>
+LG_HD void stage_load(int j, const cplx* __restrict__ W, Ld ld, cplx* v) {
     constexpr int T = N / R;
-    cplx v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = ld(j + r * T);
-    const int k = (Ns == 1) ? 0 : (j % Ns);
     if (Ns > 1) {
+        const int k = j % Ns;
         constexpr int step = N / (Ns * R);
 #pragma unroll
         for (int r = 1; r < R; ++r) {
-            cplx w = W[k * r * step];
+            // half table: W[m + N/2] = -W[m]
+            const int idx = k * r * step;
+            const bool hi = idx >= N / 2;
+            cplx w = W[hi ? idx - N / 2 : idx];
+            if (hi) w = make_double2(-w.x, -w.y);
             v[r] = INV ? cmulc(v[r], w) : cmul(v[r], w);
         }
     }
@@ -273,7 +282,11 @@ LG_HD void fft_stage(int j, const cplx* __restrict__ W, Ld ld, St st) {
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = cswap(v[r]);
     }
-    const int j0 = (Ns == 1) ? j * R : ((j / Ns) * Ns * R + k);
+}
+
+template <int N, int R, int Ns, class St>
+LG_HD void stage_store(int j, St st, const cplx* v) {
+    const int j0 = (Ns == 1) ? j * R : ((j / Ns) * Ns * R + (j % Ns));
 #pragma unroll
     for (int r = 0; r < R; ++r) st(j0 + r * Ns, v[r]);
 }
@@ -283,66 +296,107 @@ LG_HD void fft_stage(int j, const cplx* __restrict__ W, Ld ld, St st) {
 LG_HD int spad(int i) { return i + (i >> 3); }
 template <int N> struct SmemLen { static constexpr int value = N + (N >> 3) + 1; };
 
-}  // namespace lg
+constexpr int kBlock = 256;     // threads per block of the pointwise kernels
 
-namespace lg {
+// ---- block geometry of a tile of NF length-N transforms -----------------------------------
+// A thread never holds more than RCAP = (largest radix of the plan) complex values: in a
+// stage of radix R it may take floor(RCAP/R) butterflies.  tile_threads<N>(NF) is the block
+// size that lets every stage finish in one such pass.
+template <int N> struct TileGeom {
+    typedef Plan<N> P;
+    static constexpr int RCAP = PlanInfo<N>::rmax;
+    static constexpr int need(int nf, int r) { return r == 1 ? 0 : (nf * (N / r) + (RCAP / r) - 1) / (RCAP / r); }
+    static constexpr int max2(int a, int b) { return a > b ? a : b; }
+    static constexpr int threads(int nf) {
+        return max2(max2(need(nf, P::R1), need(nf, P::R2)), max2(need(nf, P::R3), need(nf, P::R4)));
+    }
+    static constexpr int round32(int t) { return ((t + 31) / 32) * 32; }
+    // registers per thread the butterflies want, and the resident blocks that allows
+    static constexpr bool pow2(int r) { return r == 1 || r == 2 || r == 4 || r == 8 || r == 16; }
+    static constexpr bool pure2 = pow2(P::R1) && pow2(P::R2) && pow2(P::R3) && pow2(P::R4);
+    static constexpr int regs = RCAP <= 8 ? (pure2 ? 64 : 80) : (RCAP <= 12 ? 112 : 128);
+    static constexpr int min_blocks(int nthr) { return blocks_for(nthr, regs); }
+    // at least two resident blocks for blocks of <= 512 threads, at most 16
+    static constexpr int blocks_for(int nthr, int r) {
+        return (65536 / (nthr * r)) < (nthr <= 512 ? 2 : 1) ? (nthr <= 512 ? 2 : 1)
+                                                           : ((65536 / (nthr * r)) > 16 ? 16 : (65536 / (nthr * r)));
+    }
+};
+
 // ---------------------------------------------------------------------------------
-// Block-cooperative FFT over a tile of NF independent length-N transforms.
-//   FFT_FASTEST = true : consecutive threads take consecutive transforms (column
-//                        tiles of the y pass: the transform index is the contiguous
-//                        global-memory direction);
-//               = false: consecutive threads take consecutive butterflies of one
-//                        transform (row tiles of the x pass).
-//   ld(f, i)      : element i of transform f for the first stage (global or registers)
+// Block-cooperative FFT over a tile of NF independent length-N transforms, in place on
+// ONE shared buffer.
+//   FFT_FASTEST = true : consecutive threads take consecutive transforms (column tiles
+//                        of the y pass: the transform index is the contiguous global
+//                        direction);  false: consecutive threads take consecutive
+//                        butterflies of one transform (row tiles of the x pass).
+//   ld(f, i)      : element i of transform f for the first stage
 //   st(f, i, v)   : element i of the result (natural order) from the last stage
+//   LD_BUF/ST_BUF : ld reads / st writes the work buffer itself (adds the barriers an
+//                   in-place update then needs)
 //   sidx(f, i)    : shared-memory slot of element i of transform f
-// bufA/bufB are two shared buffers (ping-pong); every thread of the block must call
-// this function (it contains __syncthreads()).
+// Every thread of the NTHR-thread block must call this; it ends with a barrier.
 // ---------------------------------------------------------------------------------
-template <int N, int R, int Ns, bool INV, int NF, bool FFT_FASTEST, class Ld, class St>
+template <int N, int R, int Ns, bool INV, int NF, bool FFT_FASTEST, int NTHR, bool SYNC_BETWEEN, class Ld, class St>
 LG_D void tile_stage(const cplx* __restrict__ W, Ld ld, St st) {
-    constexpr int T = N / R;
-    const int nthr = blockDim.x;
-    for (int it = threadIdx.x; it < NF * T; it += nthr) {
-        int f, j;
-        if (FFT_FASTEST) { f = it % NF; j = it / NF; }
-        else             { j = it % T;  f = it / T; }
-        fft_stage<N, R, Ns, INV>(j, W,
-            [&](int i) { return ld(f, i); },
-            [&](int i, cplx v) { st(f, i, v); });
+    constexpr int T = N / R, ITEMS = NF * T, IPT = (ITEMS + NTHR - 1) / NTHR;
+    cplx v[IPT][R];
+#pragma unroll
+    for (int q = 0; q < IPT; ++q) {
+        const int it = threadIdx.x + q * NTHR;
+        if (ITEMS % NTHR == 0 || it < ITEMS) {
+            int f, j;
+            if (FFT_FASTEST) { f = it % NF; j = it / NF; }
+            else             { j = it % T;  f = it / T; }
+            stage_load<N, R, Ns, INV>(j, W, [&](int i) { return ld(f, i); }, v[q]);
+        }
+    }
+    if (SYNC_BETWEEN) __syncthreads();
+#pragma unroll
+    for (int q = 0; q < IPT; ++q) {
+        const int it = threadIdx.x + q * NTHR;
+        if (ITEMS % NTHR == 0 || it < ITEMS) {
+            int f, j;
+            if (FFT_FASTEST) { f = it % NF; j = it / NF; }
+            else             { j = it % T;  f = it / T; }
+            stage_store<N, R, Ns>(j, [&](int i, cplx x) { st(f, i, x); }, v[q]);
+        }
     }
 }
 
-template <int N, bool INV, int NF, bool FFT_FASTEST, class SIdx, class Ld, class St>
-LG_D void fft_tile(cplx* bufA, cplx* bufB, const cplx* __restrict__ W, SIdx sidx, Ld ld, St st) {
+template <int N, bool INV, int NF, bool FFT_FASTEST, int NTHR, bool LD_BUF, bool ST_BUF, class SIdx, class Ld, class St>
+LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, SIdx sidx, Ld ld, St st) {
     typedef Plan<N> P;
     constexpr int NST = PlanInfo<N>::nstages;
-    auto ldA = [&](int f, int i) { return bufA[sidx(f, i)]; };
-    auto ldB = [&](int f, int i) { return bufB[sidx(f, i)]; };
-    auto stA = [&](int f, int i, cplx v) { bufA[sidx(f, i)] = v; };
-    auto stB = [&](int f, int i, cplx v) { bufB[sidx(f, i)] = v; };
+    auto ldB = [&](int f, int i) { return buf[sidx(f, i)]; };
+    auto stB = [&](int f, int i, cplx v) { buf[sidx(f, i)] = v; };
     if constexpr (NST == 1) {
-        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST>(W, ld, st);
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF && ST_BUF>(W, ld, st);
     } else if constexpr (NST == 2) {
-        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST>(W, ld, stA);
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF>(W, ld, stB);
         __syncthreads();
-        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST>(W, ldA, st);
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W, ldB, st);
     } else if constexpr (NST == 3) {
-        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST>(W, ld, stA);
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF>(W, ld, stB);
         __syncthreads();
-        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST>(W, ldA, stB);
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true>(W, ldB, stB);
         __syncthreads();
-        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST>(W, ldB, st);
+        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W, ldB, st);
     } else {
-        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST>(W, ld, stA);
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF>(W, ld, stB);
         __syncthreads();
-        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST>(W, ldA, stB);
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true>(W, ldB, stB);
         __syncthreads();
-        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST>(W, ldB, stA);
+        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, true>(W, ldB, stB);
         __syncthreads();
-        tile_stage<N, P::R4, P::R1 * P::R2 * P::R3, INV, NF, FFT_FASTEST>(W, ldA, st);
+        tile_stage<N, P::R4, P::R1 * P::R2 * P::R3, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W, ldB, st);
     }
     __syncthreads();
+}
+
+// copy a twiddle table into shared memory (all threads; caller synchronises)
+LG_D void load_table(cplx* dst, const cplx* __restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
 }  // namespace lg

@@ -21,7 +21,6 @@
 namespace lg {
 
 constexpr int kMaxFields = 6;
-constexpr int kBlock = 256;
 
 // ---------------------------------------------------------------------------------
 // x forward:  real rows -> half spectrum rows
@@ -36,64 +35,94 @@ struct XfOut {
 
 template <int NX> struct XCfg {
     static constexpr int M = NX / 2;
-    static constexpr int NF = (2048 / M) < 1 ? 1 : ((2048 / M) > 64 ? 64 : (2048 / M));
+    typedef TileGeom<M> G;
+    // rows per tile: as many as a <= 256-thread block can take (see TileGeom)
+    static constexpr int NF0 = 256 / G::threads(1);
+    static constexpr int NF = NF0 < 1 ? 1 : (NF0 > 64 ? 64 : NF0);
+    static constexpr int NTHR = G::round32(G::threads(NF));
+    static constexpr int MINB = G::min_blocks(NTHR);
     static constexpr int SL = SmemLen<M>::value;
-    static constexpr size_t smem = size_t(2) * NF * SL * sizeof(cplx);
+    static constexpr int NWH = M / 2 + 1;
+    // work buffer + stage twiddles W_M + untangling twiddles W_NX[0..M/2]
+    static constexpr size_t smem = size_t(NF * SL + M / 2 + NWH) * sizeof(cplx);
 };
 
-// Pro: struct with   int nfields;   LG_D double2 load(int fld, int k, int y, int j) const
+// Pro: struct with  LG_D double2 load(int fld, int k, int y, int j) const
 //      returning (x[2j], x[2j+1]) of row y of plane k of field fld (already scaled).
+// Persistent blocks: each block loops over row tiles, twiddles live in shared memory.
 template <int NX, class Pro>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
 k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int ny, int k0, int nplanes,
-       const cplx* __restrict__ W, const cplx* __restrict__ Wh) {
+       const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
     typedef XCfg<NX> C;
-    constexpr int M = C::M, NF = C::NF, SL = C::SL;
+    constexpr int M = C::M, NF = C::NF, SL = C::SL, NTHR = C::NTHR;
     LG_DYN_SMEM(cplx, sm);
-    cplx* A = sm;
-    cplx* B = sm + NF * SL;
+    cplx* buf = sm;
+    cplx* W = sm + NF * SL;
+    cplx* Wh = W + M / 2;
+    __shared__ int s_k[NF], s_y[NF];
+    load_table(W, Wg, M / 2);
+    load_table(Wh, Whg, C::NWH);
     const int fld = blockIdx.y;
     const long nrows = long(ny) * nplanes;
-    const long row0 = long(blockIdx.x) * NF;
-    constexpr int NST = PlanInfo<M>::nstages;
-    cplx* Z = (NST & 1) ? A : B;   // buffer free to take the last stage's output
-
-    fft_tile<M, false, NF, false>(A, B, W,
-        [](int f, int i) { return f * SL + spad(i); },
-        [&](int f, int i) {
+    const long ntiles = (nrows + NF - 1) / NF;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long row0 = tile * NF;
+        for (int f = threadIdx.x; f < NF; f += NTHR) {
             long r = row0 + f;
-            if (r >= nrows) return make_double2(0.0, 0.0);
-            int k = k0 + int(r / ny), y = int(r % ny);
-            return pro.load(fld, k, y, i);
-        },
-        [&](int f, int i, cplx v) { Z[f * SL + spad(i)] = v; });
-
-    // untangle: X_k = E_k + W_N^k O_k,  X_{M-k} = conj(E_k - W_N^k O_k)
-    for (int it = threadIdx.x; it < NF * (M / 2 + 1); it += blockDim.x) {
-        int m = it % (M / 2 + 1), f = it / (M / 2 + 1);
-        long r = row0 + f;
-        if (r >= nrows) continue;
-        int k = k0 + int(r / ny), y = int(r % ny);
-        double* drow = out.dst[fld] + long(k) * out.plane + long(y) * out.row;
-        cplx a = Z[f * SL + spad(m)];
-        if (m == 0) {
-            if (out.ncol > 0) *reinterpret_cast<cplx*>(drow) = make_double2(a.x + a.y, 0.0);
-            if (out.write_nyq && out.ncol >= M)
-                *reinterpret_cast<cplx*>(drow + 2 * M) =
-                    make_double2(out.write_nyq == 2 ? a.x - a.y : 0.0, 0.0);
-            else if (out.write_nyq && out.ncol < M)
-                *reinterpret_cast<cplx*>(drow + 2 * out.ncol) = make_double2(0.0, 0.0);
-            continue;
+            s_k[f] = r < nrows ? k0 + int(r / ny) : -1;
+            s_y[f] = int(r % ny);
         }
-        cplx bz = Z[f * SL + spad(M - m)];
-        cplx b = make_double2(bz.x, -bz.y);
-        cplx e = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
-        cplx d = make_double2(0.5 * (a.x - b.x), 0.5 * (a.y - b.y));
-        cplx o = make_double2(d.y, -d.x);            // d / i
-        cplx t = cmul(o, Wh[m]);
-        if (m < out.ncol) *reinterpret_cast<cplx*>(drow + 2 * m) = cadd(e, t);
-        if (m != M - m && M - m < out.ncol)
-            *reinterpret_cast<cplx*>(drow + 2 * (M - m)) = make_double2(e.x - t.x, -(e.y - t.y));
+        __syncthreads();
+        fft_tile<M, false, NF, false, NTHR, false, true>(buf, W,
+            [](int f, int i) { return f * SL + spad(i); },
+            [&](int f, int i) {
+                const int k = s_k[f];
+                if (k < 0) return make_double2(0.0, 0.0);
+                return pro.load(fld, k, s_y[f], i);
+            },
+            [&](int f, int i, cplx v) { buf[f * SL + spad(i)] = v; });
+
+        // untangle: X_k = E_k + W_N^k O_k,  X_{M-k} = conj(E_k - W_N^k O_k), pairs (m, M-m)
+        constexpr int NP = M / 2 - 1;                       // pairs with 0 < m < M/2
+        constexpr int ITER = (NF * NP + NTHR - 1) / NTHR;
+#pragma unroll 2
+        for (int q = 0; q < ITER; ++q) {
+            const int it = threadIdx.x + q * NTHR;
+            if (it >= NF * NP) break;
+            const int m = 1 + it % NP, f = it / NP;
+            const int k = s_k[f];
+            if (k < 0) continue;
+            double* drow = out.dst[fld] + long(k) * out.plane + long(s_y[f]) * out.row;
+            cplx a = buf[f * SL + spad(m)];
+            cplx bz = buf[f * SL + spad(M - m)];
+            cplx b = make_double2(bz.x, -bz.y);
+            cplx e = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+            cplx d = make_double2(0.5 * (a.x - b.x), 0.5 * (a.y - b.y));
+            cplx o = make_double2(d.y, -d.x);               // d / i
+            cplx t = cmul(o, Wh[m]);
+            if (m < out.ncol) *reinterpret_cast<cplx*>(drow + 2 * m) = cadd(e, t);
+            if (M - m < out.ncol)
+                *reinterpret_cast<cplx*>(drow + 2 * (M - m)) = make_double2(e.x - t.x, -(e.y - t.y));
+        }
+        // m = 0 (DC + Nyquist) and m = M/2 (self-paired): X_{M/2} = conj(Z_{M/2})
+        for (int f = threadIdx.x; f < 2 * NF; f += NTHR) {
+            const int ff = f >> 1, k = s_k[ff];
+            if (k < 0) continue;
+            double* drow = out.dst[fld] + long(k) * out.plane + long(s_y[ff]) * out.row;
+            if (f & 1) {
+                cplx a = buf[ff * SL + spad(M / 2)];
+                if (M / 2 < out.ncol) *reinterpret_cast<cplx*>(drow + M) = make_double2(a.x, -a.y);
+            } else {
+                cplx a = buf[ff * SL];
+                if (out.ncol > 0) *reinterpret_cast<cplx*>(drow) = make_double2(a.x + a.y, 0.0);
+                if (out.write_nyq && out.ncol >= M)
+                    *reinterpret_cast<cplx*>(drow + 2 * M) = make_double2(out.write_nyq == 2 ? a.x - a.y : 0.0, 0.0);
+                else if (out.write_nyq && out.ncol < M)
+                    *reinterpret_cast<cplx*>(drow + 2 * out.ncol) = make_double2(0.0, 0.0);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -111,58 +140,92 @@ struct XiSrc {
 // Epi: struct with  LG_D void store(int fld, int k, int y, int j, double2 v) const
 //      receiving (x[2j], x[2j+1]);   LG_D void finish_row(int fld, int k, int y) const
 template <int NX, class Epi>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
 k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int ny, int k0, int nplanes,
-       const cplx* __restrict__ W, const cplx* __restrict__ Wh) {
+       const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
     typedef XCfg<NX> C;
-    constexpr int M = C::M, NF = C::NF, SL = C::SL;
+    constexpr int M = C::M, NF = C::NF, SL = C::SL, NTHR = C::NTHR;
     LG_DYN_SMEM(cplx, sm);
-    cplx* A = sm;
-    cplx* B = sm + NF * SL;
+    cplx* buf = sm;
+    cplx* W = sm + NF * SL;
+    cplx* Wh = W + M / 2;
+    __shared__ int s_k[NF], s_y[NF];
+    load_table(W, Wg, M / 2);
+    load_table(Wh, Whg, C::NWH);
     const int fld = blockIdx.y;
     const long nrows = long(ny) * nplanes;
-    const long row0 = long(blockIdx.x) * NF;
+    const long ntiles = (nrows + NF - 1) / NF;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long row0 = tile * NF;
+        for (int f = threadIdx.x; f < NF; f += NTHR) {
+            long r = row0 + f;
+            s_k[f] = r < nrows ? k0 + int(r / ny) : -1;
+            s_y[f] = int(r % ny);
+        }
+        __syncthreads();
 
-    // tangle: Z'_k = E'_k + i O'_k,  E' = X_k + conj(X_{M-k}),  O' = (X_k - conj(X_{M-k})) conj(W_N^k)
-    for (int it = threadIdx.x; it < NF * (M / 2 + 1); it += blockDim.x) {
-        int m = it % (M / 2 + 1), f = it / (M / 2 + 1);
-        long r = row0 + f;
-        cplx za = make_double2(0.0, 0.0), zb = za;
-        if (r < nrows) {
-            int k = k0 + int(r / ny), y = int(r % ny);
-            const double* srow = in.src[fld] + long(k) * in.plane + long(y) * in.row;
-            if (m == 0) {
-                double x0 = in.ncol > 0 ? srow[0] : 0.0;
-                double xm = in.ncol > M ? srow[2 * M] : 0.0;
-                za = make_double2(x0 + xm, x0 - xm);
-            } else {
-                cplx a = m < in.ncol ? *reinterpret_cast<const cplx*>(srow + 2 * m) : make_double2(0.0, 0.0);
-                cplx bz = (M - m) < in.ncol ? *reinterpret_cast<const cplx*>(srow + 2 * (M - m)) : make_double2(0.0, 0.0);
-                cplx b = make_double2(bz.x, -bz.y);
-                cplx e = cadd(a, b);
-                cplx o = cmulc(csub(a, b), Wh[m]);
-                za = make_double2(e.x - o.y, e.y + o.x);         // e + i o
-                zb = make_double2(e.x + o.y, -e.y + o.x);        // conj(e) + i conj(o)
+        // tangle: Z'_k = E'_k + i O'_k,  E' = X_k + conj(X_{M-k}),  O' = (X_k - conj(X_{M-k})) conj(W_N^k)
+        constexpr int NP = M / 2 - 1;
+        constexpr int ITER = (NF * NP + NTHR - 1) / NTHR;
+        constexpr int UN = 2;                                // global loads in flight per thread: 2*UN
+#pragma unroll 1
+        for (int q0 = 0; q0 < ITER; q0 += UN) {
+            cplx va[UN], vb[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {                   // loads first
+                const int it = threadIdx.x + (q0 + u) * NTHR;
+                va[u] = make_double2(0.0, 0.0); vb[u] = va[u];
+                if (it < NF * NP) {
+                    const int m = 1 + it % NP, f = it / NP;
+                    if (s_k[f] >= 0) {
+                        const double* srow = in.src[fld] + long(s_k[f]) * in.plane + long(s_y[f]) * in.row;
+                        if (m < in.ncol) va[u] = *reinterpret_cast<const cplx*>(srow + 2 * m);
+                        if (M - m < in.ncol) vb[u] = *reinterpret_cast<const cplx*>(srow + 2 * (M - m));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int it = threadIdx.x + (q0 + u) * NTHR;
+                if (it < NF * NP) {
+                    const int m = 1 + it % NP, f = it / NP;
+                    cplx a = va[u], b = make_double2(vb[u].x, -vb[u].y);
+                    cplx e = cadd(a, b);
+                    cplx o = cmulc(csub(a, b), Wh[m]);
+                    buf[f * SL + spad(m)] = make_double2(e.x - o.y, e.y + o.x);          // e + i o
+                    buf[f * SL + spad(M - m)] = make_double2(e.x + o.y, -e.y + o.x);     // conj(e) + i conj(o)
+                }
             }
         }
-        B[f * SL + spad(m)] = za;
-        if (m != 0 && m != M - m) B[f * SL + spad(M - m)] = zb;
-    }
-    __syncthreads();
+        for (int f = threadIdx.x; f < 2 * NF; f += NTHR) {
+            const int ff = f >> 1;
+            cplx z = make_double2(0.0, 0.0);
+            if (s_k[ff] >= 0) {
+                const double* srow = in.src[fld] + long(s_k[ff]) * in.plane + long(s_y[ff]) * in.row;
+                if (f & 1) {                                  // m = M/2: Z' = 2 conj(X_{M/2})
+                    if (M / 2 < in.ncol) { cplx a = *reinterpret_cast<const cplx*>(srow + M); z = make_double2(2.0 * a.x, -2.0 * a.y); }
+                } else {                                      // m = 0: real parts of X_0 and X_M only
+                    double x0 = in.ncol > 0 ? srow[0] : 0.0;
+                    double xm = in.ncol > M ? srow[2 * M] : 0.0;
+                    z = make_double2(x0 + xm, x0 - xm);
+                }
+            }
+            buf[ff * SL + ((f & 1) ? spad(M / 2) : 0)] = z;
+        }
+        __syncthreads();
 
-    fft_tile<M, true, NF, false>(A, B, W,
-        [](int f, int i) { return f * SL + spad(i); },
-        [&](int f, int i) { return B[f * SL + spad(i)]; },
-        [&](int f, int i, cplx v) {
-            long r = row0 + f;
-            if (r >= nrows) return;
-            int k = k0 + int(r / ny), y = int(r % ny);
-            epi.store(fld, k, y, i, v);
-        });
-    for (int f = threadIdx.x; f < NF; f += blockDim.x) {
-        long r = row0 + f;
-        if (r >= nrows) continue;
-        epi.finish_row(fld, k0 + int(r / ny), int(r % ny));
+        fft_tile<M, true, NF, false, NTHR, true, false>(buf, W,
+            [](int f, int i) { return f * SL + spad(i); },
+            [&](int f, int i) { return buf[f * SL + spad(i)]; },
+            [&](int f, int i, cplx v) {
+                if (s_k[f] < 0) return;
+                epi.store(fld, s_k[f], s_y[f], i, v);
+            });
+        for (int f = threadIdx.x; f < NF; f += NTHR) {
+            if (s_k[f] < 0) continue;
+            epi.finish_row(fld, s_k[f], s_y[f]);
+        }
+        __syncthreads();
     }
 }
 
@@ -185,7 +248,7 @@ struct YArgs {
     long src_plane, dst_plane;
     int src_row, dst_row;   // doubles
     int ncols;           // kx columns to transform
-    int k0;
+    int k0, nplanes;
     double kxs, kys;     // 2 pi / L_x, 2 pi / L_y
     const double* table; // Y_TABLE multiplier, [ns][table_row] reals
     int table_row;
@@ -193,113 +256,129 @@ struct YArgs {
     int keep_nyq_row;    // 1: raw transform (do not zero ky = ns/2)
 };
 
-template <int NIN, int NOUT> struct YCfg {
+// MULTI = several outputs per field: the spectrum is kept in its own buffer S while the
+// inverse transforms run in the work buffer; otherwise one buffer serves both.
+template <int NIN, int NOUT, bool MULTI> struct YCfg {
     static constexpr int NMAX = NIN > NOUT ? NIN : NOUT;
     static constexpr int NS = (NIN == 0) ? NOUT : ((NOUT == 0) ? NIN : (NIN < NOUT ? NIN : NOUT));  // spectral (small) length
-    static constexpr int TC = NMAX <= 512 ? 4 : 2;
+    static constexpr int max2(int a, int b) { return a > b ? a : b; }
+    template <int N> static constexpr int thr(int tc) { return TileGeom<(N > 0 ? N : 8)>::threads(tc) * (N > 0); }
+    static constexpr int TC = max2(thr<NIN>(4), thr<NOUT>(4)) <= 512 ? 4 : 2;
+    static constexpr int NTHR = ((max2(thr<NIN>(TC), thr<NOUT>(TC)) + 31) / 32) * 32;
+    static constexpr int regs = max2(TileGeom<(NIN > 0 ? NIN : 8)>::regs * (NIN > 0), TileGeom<(NOUT > 0 ? NOUT : 8)>::regs * (NOUT > 0));
+    static constexpr int MINB = TileGeom<8>::blocks_for(NTHR, regs);
     static constexpr int SL = SmemLen<NMAX>::value;
-    static constexpr int NBUF = (NIN > 0 && NOUT == 0) ? 2 : 3;
-    static constexpr size_t smem = size_t(NBUF) * TC * SL * sizeof(cplx);
+    static constexpr int NBUF = MULTI ? 2 : 1;
+    static constexpr size_t smem = size_t(NBUF * TC * SL + NIN / 2 + NOUT / 2) * sizeof(cplx);
 };
 
 // NIN  > 0: forward transform of length NIN first (input is the x-pass intermediate)
 // NOUT > 0: inverse transform(s) of length NOUT last (output feeds the x inverse pass)
 // NIN == NOUT: derivative / filter operators;  NIN < NOUT: padd;  NIN > NOUT: unpadd.
-template <int NIN, int NOUT>
-__global__ void __launch_bounds__(kBlock)
-k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Win, const cplx* __restrict__ Wout) {
-    typedef YCfg<NIN, NOUT> C;
-    constexpr int TC = C::TC, SL = C::SL, NS = C::NS;
+// Persistent blocks over (column tile, plane) pairs; blockIdx.y = field.
+template <int NIN, int NOUT, bool MULTI>
+__global__ void __launch_bounds__(YCfg<NIN, NOUT, MULTI>::NTHR, YCfg<NIN, NOUT, MULTI>::MINB)
+k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cplx* __restrict__ Woutg) {
+    typedef YCfg<NIN, NOUT, MULTI> C;
+    constexpr int TC = C::TC, SL = C::SL, NS = C::NS, NTHR = C::NTHR;
     LG_DYN_SMEM(cplx, sm);
-    cplx* S = sm;                                   // spectrum of the tile (NS rows used)
-    cplx* A = sm + TC * SL;
-    cplx* B = (C::NBUF == 3) ? sm + 2 * TC * SL : sm;
-    const int c0 = blockIdx.x * TC;
-    const int k = a.k0 + blockIdx.y;
-    const YField& F = a.fld[blockIdx.z];
+    cplx* buf = sm;                                     // work buffer
+    cplx* S = MULTI ? sm + TC * SL : sm;                // spectrum of the tile (NS rows used)
+    cplx* Win = sm + C::NBUF * TC * SL;
+    cplx* Wout = Win + NIN / 2;
+    if (NIN > 0) load_table(Win, Wing, NIN / 2);
+    if (NOUT > 0) load_table(Wout, Woutg, NOUT / 2);
+    __syncthreads();
+    const YField& F = a.fld[blockIdx.y];
     auto sidx = [](int f, int i) { return spad(i) * TC + f; };
-    const double* src = F.src + long(k) * a.src_plane + 2 * c0;
+    const int ntc = (a.ncols + TC - 1) / TC;
+    const long ntiles = long(ntc) * a.nplanes;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int c0 = int(tile % ntc) * TC;
+        const int k = a.k0 + int(tile / ntc);
+        const double* src = F.src + long(k) * a.src_plane + 2 * c0;
 
-    if constexpr (NIN > 0) {
-        if constexpr (NOUT == 0) {
-            // forward only: straight to global with Nyquist-row zeroing
-            double* dst = F.out[0].dst + long(k) * a.dst_plane + 2 * c0;
-            fft_tile<NIN, false, TC, true>(S, A, Win, sidx,
-                [&](int f, int i) {
-                    if (c0 + f >= a.ncols) return make_double2(0.0, 0.0);
-                    return *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
-                },
-                [&](int f, int i, cplx v) {
-                    if (c0 + f >= a.ncols) return;
-                    if (i == NIN / 2 && !a.keep_nyq_row) v = make_double2(0.0, 0.0);
-                    *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * f) = v;
-                });
+        if constexpr (NIN > 0) {
+            if constexpr (NOUT == 0) {
+                // forward only: straight to global with Nyquist-row zeroing
+                double* dst = F.out[0].dst + long(k) * a.dst_plane + 2 * c0;
+                fft_tile<NIN, false, TC, true, NTHR, false, false>(buf, Win, sidx,
+                    [&](int f, int i) {
+                        if (c0 + f >= a.ncols) return make_double2(0.0, 0.0);
+                        return *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
+                    },
+                    [&](int f, int i, cplx v) {
+                        if (c0 + f >= a.ncols) return;
+                        if (i == NIN / 2 && !a.keep_nyq_row) v = make_double2(0.0, 0.0);
+                        *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * f) = v;
+                    });
+            } else {
+                fft_tile<NIN, false, TC, true, NTHR, false, !MULTI>(buf, Win, sidx,
+                    [&](int f, int i) {
+                        if (c0 + f >= a.ncols) return make_double2(0.0, 0.0);
+                        return *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
+                    },
+                    [&](int f, int i, cplx v) {
+                        // keep only the NS rows of the small spectrum (unpadd, fft.f90:86-97)
+                        int is = i;
+                        if (NIN > NS) {
+                            if (i < NS / 2) is = i;
+                            else if (i > NIN - NS / 2) is = i - (NIN - NS);
+                            else return;
+                        }
+                        S[sidx(f, is)] = v;
+                    });
+            }
         } else {
-            fft_tile<NIN, false, TC, true>(A, B, Win, sidx,
-                [&](int f, int i) {
-                    if (c0 + f >= a.ncols) return make_double2(0.0, 0.0);
-                    return *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
-                },
-                [&](int f, int i, cplx v) {
-                    // keep only the NS rows of the small spectrum (unpadd, fft.f90:86-97)
-                    int is = i;
-                    if (NIN > NS) {
-                        if (i < NS / 2) is = i;
-                        else if (i > NIN - NS / 2) is = i - (NIN - NS);
-                        else return;
-                    }
-                    S[sidx(f, is)] = v;
-                });
+            for (int it = threadIdx.x; it < TC * NS; it += NTHR) {
+                int f = it % TC, i = it / TC;
+                cplx v = make_double2(0.0, 0.0);
+                if (c0 + f < a.ncols) v = *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
+                S[sidx(f, i)] = v;
+            }
+            __syncthreads();
         }
-    } else {
-        for (int it = threadIdx.x; it < TC * NS; it += blockDim.x) {
-            int f = it % TC, i = it / TC;
-            cplx v = make_double2(0.0, 0.0);
-            if (c0 + f < a.ncols) v = *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
-            S[sidx(f, i)] = v;
-        }
-        __syncthreads();
-    }
 
-    if constexpr (NOUT > 0) {
-        for (int o = 0; o < a.nout; ++o) {
-            const int mode = F.out[o].mode;
-            double* dst = F.out[o].dst + long(k) * a.dst_plane + 2 * c0;
-            fft_tile<NOUT, true, TC, true>(A, B, Wout, sidx,
-                [&](int f, int i) {
-                    // row i of the (possibly padded) output spectrum <- small row is
-                    int is = i;
-                    if (NOUT > NS) {                         // padd, fft.f90:60-69
-                        if (i < NS / 2) is = i;
-                        else if (i > NOUT - NS / 2) is = i - (NOUT - NS);
-                        else return make_double2(0.0, 0.0);
-                    }
-                    if (is == NS / 2 && !a.keep_nyq_row) return make_double2(0.0, 0.0);
-                    cplx v = S[sidx(f, is)];
-                    if (mode == Y_COPY) return v;
-                    if (mode == Y_IKX) {
-                        double kx = a.kxs * double(c0 + f);
-                        return make_double2(-v.y * kx, v.x * kx);
-                    }
-                    if (mode == Y_IKY) {
-                        double ky = a.kys * double(is < NS / 2 ? is : is - NS);
-                        return make_double2(-v.y * ky, v.x * ky);
-                    }
-                    double g = (c0 + f < a.ncols) ? a.table[long(is) * a.table_row + c0 + f] : 0.0;
-                    return make_double2(v.x * g, v.y * g);
-                },
-                [&](int f, int i, cplx v) {
-                    if (c0 + f >= a.ncols) return;
-                    *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * f) = v;
-                });
+        if constexpr (NOUT > 0) {
+            for (int o = 0; o < a.nout; ++o) {
+                const int mode = F.out[o].mode;
+                double* dst = F.out[o].dst + long(k) * a.dst_plane + 2 * c0;
+                fft_tile<NOUT, true, TC, true, NTHR, !MULTI, false>(buf, Wout, sidx,
+                    [&](int f, int i) {
+                        // row i of the (possibly padded) output spectrum <- small row is
+                        int is = i;
+                        if (NOUT > NS) {                         // padd, fft.f90:60-69
+                            if (i < NS / 2) is = i;
+                            else if (i > NOUT - NS / 2) is = i - (NOUT - NS);
+                            else return make_double2(0.0, 0.0);
+                        }
+                        if (is == NS / 2 && !a.keep_nyq_row) return make_double2(0.0, 0.0);
+                        cplx v = S[sidx(f, is)];
+                        if (mode == Y_COPY) return v;
+                        if (mode == Y_IKX) {
+                            double kx = a.kxs * double(c0 + f);
+                            return make_double2(-v.y * kx, v.x * kx);
+                        }
+                        if (mode == Y_IKY) {
+                            double ky = a.kys * double(is < NS / 2 ? is : is - NS);
+                            return make_double2(-v.y * ky, v.x * ky);
+                        }
+                        double g = (c0 + f < a.ncols) ? a.table[long(is) * a.table_row + c0 + f] : 0.0;
+                        return make_double2(v.x * g, v.y * g);
+                    },
+                    [&](int f, int i, cplx v) {
+                        if (c0 + f >= a.ncols) return;
+                        *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * f) = v;
+                    });
+            }
         }
-    }
-    if (a.zero_col >= 0 && blockIdx.x == 0) {
-        constexpr int NR = NOUT > 0 ? NOUT : NIN;
-        for (int o = 0; o < a.nout; ++o) {
-            double* dst = F.out[o].dst + long(k) * a.dst_plane;
-            for (int i = threadIdx.x; i < NR; i += blockDim.x)
-                *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * a.zero_col) = make_double2(0.0, 0.0);
+        if (a.zero_col >= 0 && c0 == 0) {
+            constexpr int NR = NOUT > 0 ? NOUT : NIN;
+            for (int o = 0; o < a.nout; ++o) {
+                double* dst = F.out[o].dst + long(k) * a.dst_plane;
+                for (int i = threadIdx.x; i < NR; i += NTHR)
+                    *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * a.zero_col) = make_double2(0.0, 0.0);
+            }
         }
     }
 }

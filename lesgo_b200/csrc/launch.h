@@ -19,4 +19,15 @@ template <class K> inline void set_smem(K kernel, size_t bytes) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
 }
 
+// persistent grids: blocks per SM that fit (shared memory / 64-register budget), times SMs
+int sm_count();
+inline int persistent_blocks(size_t smem_bytes, long ntiles, int max_per_sm) {
+    int per_sm = int((227 * 1024) / (smem_bytes + 1024));
+    if (per_sm > max_per_sm) per_sm = max_per_sm;
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    long g = long(sm_count()) * per_sm;
+    return int(g < ntiles ? g : (ntiles < 1 ? 1 : ntiles));
+}
+
 }  // namespace lg

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/lesgo_gpu.h"
@@ -513,10 +514,11 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     }
     if (sp->mode != 0) return c->fail("lesgo_gpu_step: mode 1 (wallstress/sgs/divstress on device) not built yet");
     const size_t fb = size_t(c->plane) * (nz + 1) * sizeof(double);
-    // :155-157
-    CK(cudaMemcpyAsync(F[LG_RHSX_F], F[LG_RHSX], fb, cudaMemcpyDeviceToDevice, c->stream));
-    CK(cudaMemcpyAsync(F[LG_RHSY_F], F[LG_RHSY], fb, cudaMemcpyDeviceToDevice, c->stream));
-    CK(cudaMemcpyAsync(F[LG_RHSZ_F], F[LG_RHSZ], fb, cudaMemcpyDeviceToDevice, c->stream));
+    // :155-157  RHS*_f = RHS*: the two sets trade places instead of being copied (convec
+    // rewrites every valid plane of RHS* below, main.f90:207-214)
+    std::swap(c->fields[LG_RHSX], c->fields[LG_RHSX_F]); std::swap(F[LG_RHSX], F[LG_RHSX_F]);
+    std::swap(c->fields[LG_RHSY], c->fields[LG_RHSY_F]); std::swap(F[LG_RHSY], F[LG_RHSY_F]);
+    std::swap(c->fields[LG_RHSZ], c->fields[LG_RHSZ_F]); std::swap(F[LG_RHSZ], F[LG_RHSZ_F]);
     // :161-172
     if (spectral_deriv(c, F[LG_U], F[LG_U], F[LG_DUDX], F[LG_DUDY])) return 1;
     if (spectral_deriv(c, F[LG_V], F[LG_V], F[LG_DVDX], F[LG_DVDY])) return 1;

@@ -1,16 +1,27 @@
 #include "launch.h"
 #include "sizes.h"
 namespace lg {
+template <int NIN, int NOUT, bool MULTI>
+static int launch_y_m(const YArgs& a0, int nfields, int nplanes, const cplx* Win, const cplx* Wout,
+                      cudaStream_t s) {
+    typedef YCfg<NIN, NOUT, MULTI> C;
+    static bool attr = false;
+    if (!attr) { set_smem(k_ypass<NIN, NOUT, MULTI>, C::smem); attr = true; }
+    if (nplanes <= 0 || nfields <= 0) return 0;
+    YArgs a = a0;
+    a.nplanes = nplanes;
+    const long ntiles = long((a.ncols + C::TC - 1) / C::TC) * nplanes;
+    dim3 grid(persistent_blocks(C::smem, ntiles, C::MINB), nfields);
+    LG_LAUNCH((k_ypass<NIN, NOUT, MULTI>), grid, dim3(C::NTHR), C::smem, s, a, Win, Wout);
+    return 0;
+}
 template <int NIN, int NOUT>
 static int launch_y_n(const YArgs& a, int nfields, int nplanes, const cplx* Win, const cplx* Wout,
                       cudaStream_t s) {
-    typedef YCfg<NIN, NOUT> C;
-    static bool attr = false;
-    if (!attr) { set_smem(k_ypass<NIN, NOUT>, C::smem); attr = true; }
-    if (nplanes <= 0 || nfields <= 0) return 0;
-    dim3 grid((a.ncols + C::TC - 1) / C::TC, nplanes, nfields);
-    LG_LAUNCH((k_ypass<NIN, NOUT>), grid, dim3(kBlock), C::smem, s, a, Win, Wout);
-    return 0;
+    if constexpr (NOUT > 0 && (NIN == NOUT || NIN == 0)) {
+        if (a.nout > 1) return launch_y_m<NIN, NOUT, true>(a, nfields, nplanes, Win, Wout, s);
+    }
+    return launch_y_m<NIN, NOUT, false>(a, nfields, nplanes, Win, Wout, s);
 }
 #define LG_Y_CASES(S, B)                                                                     \
     if (nin == S && nout == S) return launch_y_n<S, S>(a, nfields, nplanes, Win, Wout, s);   \
@@ -30,6 +41,20 @@ int launch_ypass(int nin, int nout, const YArgs& a, int nfields, int nplanes, co
     return -1;
 }
 #define LG_SUP(S, B) if (n == S) return true;
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+#ifdef LESGO_EMUL
+        n = 4;
+#else
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+#endif
+    }
+    return n;
+}
 bool size_supported(int n) {
     LG_SIZE_PAIRS(LG_SUP)
     return false;

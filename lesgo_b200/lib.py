@@ -64,7 +64,8 @@ SYMBOLS = {
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "liblesgo_cuda.so")
+    # LESGO_CUDA_LIB: developer override to A/B an experimental build of the same CUDA library
+    return os.environ.get("LESGO_CUDA_LIB") or os.path.join(_HERE, "liblesgo_cuda.so")
 
 
 class Library:

@@ -25,12 +25,12 @@ template <int N, bool INV> __global__ void k_fft(const cplx* in, cplx* out, cons
     LG_DYN_SMEM(cplx, sm);
     constexpr int NF = 3;
     cplx* A = sm; cplx* B = sm + NF * SmemLen<N>::value;
-    fft_tile<N, INV, NF, false>(A, B, W,
+    fft_tile<N, INV, NF, false, 64, false, false>(A, W,
         [](int f, int i) { return f * SmemLen<N>::value + spad(i); },
         [&](int f, int i) { return in[f * N + i]; },
         [&](int f, int i, cplx v) { out[f * N + i] = v; });
     // and the transform-fastest variant into the second half of out
-    fft_tile<N, INV, NF, true>(A, B, W,
+    fft_tile<N, INV, NF, true, 64, false, false>(A, W,
         [](int f, int i) { return spad(i) * NF + f; },
         [&](int f, int i) { return in[f * N + i]; },
         [&](int f, int i, cplx v) { out[(NF + f) * N + i] = v; });

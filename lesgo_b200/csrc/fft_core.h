@@ -189,8 +189,8 @@ template <> struct Dft<12> { static LG_HD void run(cplx* v) { DftPfa<4, 3>::run(
 
 // ---------------------------------------------------------------------------------
 // Plans.  LG_PLAN(N, R1, R2, R3, R4): radices multiply to N; unused stages are 1.
-// Radices are ordered so that the first and last stage (the ones touching global
-// memory or fused operators) are wide.
+// The widest / composite radix goes FIRST: the first stage has no twiddles, so its
+// registers hold only the butterfly operands.
 // ---------------------------------------------------------------------------------
 template <int N> struct Plan;
 #define LG_PLAN(N_, A_, B_, C_, D_)                                                  \
@@ -205,33 +205,29 @@ LG_PLAN(24, 6, 4, 1, 1)
 LG_PLAN(32, 8, 4, 1, 1)
 LG_PLAN(36, 6, 6, 1, 1)
 LG_PLAN(40, 10, 4, 1, 1)
-LG_PLAN(48, 8, 6, 1, 1)
+LG_PLAN(48, 6, 8, 1, 1)
 LG_PLAN(60, 10, 6, 1, 1)
 LG_PLAN(64, 8, 8, 1, 1)
 LG_PLAN(72, 12, 6, 1, 1)
 LG_PLAN(80, 10, 8, 1, 1)
 LG_PLAN(96, 12, 8, 1, 1)
-LG_PLAN(120, 12, 10, 1, 1)
+LG_PLAN(120, 6, 5, 4, 1)
 LG_PLAN(128, 8, 4, 4, 1)
-LG_PLAN(144, 12, 12, 1, 1)
+LG_PLAN(144, 6, 6, 4, 1)
 LG_PLAN(160, 10, 4, 4, 1)
-LG_PLAN(192, 8, 6, 4, 1)
+LG_PLAN(192, 6, 8, 4, 1)
 LG_PLAN(240, 10, 6, 4, 1)
 LG_PLAN(256, 8, 8, 4, 1)
-LG_PLAN(288, 8, 6, 6, 1)
-LG_PLAN(320, 8, 10, 4, 1)
-LG_PLAN(384, 8, 8, 6, 1)
+LG_PLAN(288, 6, 6, 8, 1)
+LG_PLAN(320, 10, 8, 4, 1)
+LG_PLAN(384, 6, 8, 8, 1)
 LG_PLAN(480, 10, 8, 6, 1)
 LG_PLAN(512, 8, 8, 8, 1)
-LG_PLAN(576, 8, 12, 6, 1)
-LG_PLAN(640, 8, 10, 8, 1)
-#ifdef LG_PLAN768_4STAGE
-LG_PLAN(768, 8, 8, 4, 3)
-#else
-LG_PLAN(768, 8, 12, 8, 1)
-#endif
+LG_PLAN(576, 12, 6, 8, 1)
+LG_PLAN(640, 10, 8, 8, 1)
+LG_PLAN(768, 12, 8, 8, 1)
 LG_PLAN(1024, 8, 4, 4, 8)
-LG_PLAN(1536, 8, 6, 4, 8)
+LG_PLAN(1536, 6, 8, 8, 4)
 #undef LG_PLAN
 
 // max work items of any stage / min: threads per FFT are sized to the widest radix
@@ -244,6 +240,11 @@ template <int N> struct PlanInfo {
     static constexpr int rmin = rmin_nz(rmin_nz(rmin_nz(P::R1, P::R2), P::R3), P::R4);
     static constexpr int threads = N / rmax;       // threads cooperating on one FFT
     static constexpr int nstages = 1 + (P::R2 > 1) + (P::R3 > 1) + (P::R4 > 1);
+    // per-stage twiddle tables, stage s >= 2: (R_s - 1) * Ns_s entries, concatenated
+    static constexpr int off2 = 0;
+    static constexpr int off3 = off2 + (P::R2 > 1 ? (P::R2 - 1) * P::R1 : 0);
+    static constexpr int off4 = off3 + (P::R3 > 1 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
+    static constexpr int twlen = off4 + (P::R4 > 1 ? (P::R4 - 1) * P::R1 * P::R2 * P::R3 : 0);
 };
 
 // ---------------------------------------------------------------------------------
@@ -253,23 +254,20 @@ template <int N> struct PlanInfo {
 //   INV = false: forward (sign -1); true: inverse (sign +1, unnormalised).
 //   ld(idx) -> cplx   : fetch logical element idx of the stage input
 //   st(idx, cplx)     : deliver logical element idx of the stage output
-//   W                 : table W_N[m] = exp(-2 pi i m / N), m = 0..N/2-1 (shared memory)
+//   Wst               : this stage's twiddles, Wst[(r-1)*Ns + k] (shared memory)
 // ---------------------------------------------------------------------------------
 template <int N, int R, int Ns, bool INV, class Ld>
-LG_HD void stage_load(int j, const cplx* __restrict__ W, Ld ld, cplx* v) {
+LG_HD void stage_load(int j, const cplx* __restrict__ Wst, Ld ld, cplx* v) {
     constexpr int T = N / R;
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = ld(j + r * T);
     if (Ns > 1) {
+        // Wst[(r-1)*Ns + k] = W_N^{k r N/(Ns R)}: lanes with consecutive k read consecutive
+        // entries (conflict-free), lanes with equal k broadcast
         const int k = j % Ns;
-        constexpr int step = N / (Ns * R);
 #pragma unroll
         for (int r = 1; r < R; ++r) {
-            // half table: W[m + N/2] = -W[m]
-            const int idx = k * r * step;
-            const bool hi = idx >= N / 2;
-            cplx w = W[hi ? idx - N / 2 : idx];
-            if (hi) w = make_double2(-w.x, -w.y);
+            cplx w = Wst[(r - 1) * Ns + k];
             v[r] = INV ? cmulc(v[r], w) : cmul(v[r], w);
         }
     }
@@ -314,7 +312,7 @@ template <int N> struct TileGeom {
     // registers per thread the butterflies want, and the resident blocks that allows
     static constexpr bool pow2(int r) { return r == 1 || r == 2 || r == 4 || r == 8 || r == 16; }
     static constexpr bool pure2 = pow2(P::R1) && pow2(P::R2) && pow2(P::R3) && pow2(P::R4);
-    static constexpr int regs = RCAP <= 8 ? (pure2 ? 64 : 80) : (RCAP <= 12 ? 112 : 128);
+    static constexpr int regs = RCAP <= 8 ? (pure2 ? 64 : 80) : (RCAP <= 12 ? 96 : 128);
     static constexpr int min_blocks(int nthr) { return blocks_for(nthr, regs); }
     // at least two resident blocks for blocks of <= 512 threads, at most 16
     static constexpr int blocks_for(int nthr, int r) {
@@ -367,7 +365,8 @@ LG_D void tile_stage(const cplx* __restrict__ W, Ld ld, St st) {
 template <int N, bool INV, int NF, bool FFT_FASTEST, int NTHR, bool LD_BUF, bool ST_BUF, class SIdx, class Ld, class St>
 LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, SIdx sidx, Ld ld, St st) {
     typedef Plan<N> P;
-    constexpr int NST = PlanInfo<N>::nstages;
+    typedef PlanInfo<N> PI;
+    constexpr int NST = PI::nstages;
     auto ldB = [&](int f, int i) { return buf[sidx(f, i)]; };
     auto stB = [&](int f, int i, cplx v) { buf[sidx(f, i)] = v; };
     if constexpr (NST == 1) {
@@ -375,23 +374,30 @@ LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, SIdx sidx, Ld ld, St s
     } else if constexpr (NST == 2) {
         tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF>(W, ld, stB);
         __syncthreads();
-        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W, ldB, st);
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W + PI::off2, ldB, st);
     } else if constexpr (NST == 3) {
         tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF>(W, ld, stB);
         __syncthreads();
-        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true>(W, ldB, stB);
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true>(W + PI::off2, ldB, stB);
         __syncthreads();
-        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W, ldB, st);
+        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W + PI::off3, ldB, st);
     } else {
         tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF>(W, ld, stB);
         __syncthreads();
-        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true>(W, ldB, stB);
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true>(W + PI::off2, ldB, stB);
         __syncthreads();
-        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, true>(W, ldB, stB);
+        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, true>(W + PI::off3, ldB, stB);
         __syncthreads();
-        tile_stage<N, P::R4, P::R1 * P::R2 * P::R3, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W, ldB, st);
+        tile_stage<N, P::R4, P::R1 * P::R2 * P::R3, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W + PI::off4, ldB, st);
     }
     __syncthreads();
+}
+
+// length of the concatenated stage-twiddle table of Plan<N> and its (R1..R4) for the host
+struct PlanDesc { int n, r[4], twlen; };
+template <int N> inline PlanDesc plan_desc() {
+    PlanDesc d; d.n = N; d.r[0] = Plan<N>::R1; d.r[1] = Plan<N>::R2; d.r[2] = Plan<N>::R3; d.r[3] = Plan<N>::R4;
+    d.twlen = PlanInfo<N>::twlen; return d;
 }
 
 // copy a twiddle table into shared memory (all threads; caller synchronises)

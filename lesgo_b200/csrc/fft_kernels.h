@@ -44,7 +44,8 @@ template <int NX> struct XCfg {
     static constexpr int SL = SmemLen<M>::value;
     static constexpr int NWH = M / 2 + 1;
     // work buffer + stage twiddles W_M + untangling twiddles W_NX[0..M/2]
-    static constexpr size_t smem = size_t(NF * SL + M / 2 + NWH) * sizeof(cplx);
+    static constexpr int TWL = PlanInfo<M>::twlen;
+    static constexpr size_t smem = size_t(NF * SL + TWL + NWH) * sizeof(cplx);
 };
 
 // Pro: struct with  LG_D double2 load(int fld, int k, int y, int j) const
@@ -52,22 +53,24 @@ template <int NX> struct XCfg {
 // Persistent blocks: each block loops over row tiles, twiddles live in shared memory.
 template <int NX, class Pro>
 __global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
-k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int ny, int k0, int nplanes,
+k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int nfields, int ny, int k0, int nplanes,
        const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
     typedef XCfg<NX> C;
     constexpr int M = C::M, NF = C::NF, SL = C::SL, NTHR = C::NTHR;
     LG_DYN_SMEM(cplx, sm);
     cplx* buf = sm;
     cplx* W = sm + NF * SL;
-    cplx* Wh = W + M / 2;
+    cplx* Wh = W + C::TWL;
     __shared__ int s_k[NF], s_y[NF];
-    load_table(W, Wg, M / 2);
+    load_table(W, Wg, C::TWL);
     load_table(Wh, Whg, C::NWH);
-    const int fld = blockIdx.y;
     const long nrows = long(ny) * nplanes;
     const long ntiles = (nrows + NF - 1) / NF;
-    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long row0 = tile * NF;
+    // work item = (row tile, field), field fastest: blocks resident together work on the same
+    // rows of different fields, so inputs they share (the u x omega products) are read once
+    for (long work = blockIdx.x; work < ntiles * nfields; work += gridDim.x) {
+        const int fld = int(work % nfields);
+        const long row0 = (work / nfields) * NF;
         for (int f = threadIdx.x; f < NF; f += NTHR) {
             long r = row0 + f;
             s_k[f] = r < nrows ? k0 + int(r / ny) : -1;
@@ -141,22 +144,24 @@ struct XiSrc {
 //      receiving (x[2j], x[2j+1]);   LG_D void finish_row(int fld, int k, int y) const
 template <int NX, class Epi>
 __global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
-k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int ny, int k0, int nplanes,
+k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nfields, int ny, int k0, int nplanes,
        const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
     typedef XCfg<NX> C;
     constexpr int M = C::M, NF = C::NF, SL = C::SL, NTHR = C::NTHR;
     LG_DYN_SMEM(cplx, sm);
     cplx* buf = sm;
     cplx* W = sm + NF * SL;
-    cplx* Wh = W + M / 2;
+    cplx* Wh = W + C::TWL;
     __shared__ int s_k[NF], s_y[NF];
-    load_table(W, Wg, M / 2);
+    load_table(W, Wg, C::TWL);
     load_table(Wh, Whg, C::NWH);
-    const int fld = blockIdx.y;
     const long nrows = long(ny) * nplanes;
     const long ntiles = (nrows + NF - 1) / NF;
-    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long row0 = tile * NF;
+    // work item = (row tile, field), field fastest: blocks resident together work on the same
+    // rows of different fields, so inputs they share (the u x omega products) are read once
+    for (long work = blockIdx.x; work < ntiles * nfields; work += gridDim.x) {
+        const int fld = int(work % nfields);
+        const long row0 = (work / nfields) * NF;
         for (int f = threadIdx.x; f < NF; f += NTHR) {
             long r = row0 + f;
             s_k[f] = r < nrows ? k0 + int(r / ny) : -1;
@@ -248,7 +253,7 @@ struct YArgs {
     long src_plane, dst_plane;
     int src_row, dst_row;   // doubles
     int ncols;           // kx columns to transform
-    int k0, nplanes;
+    int k0, nplanes, nfields;
     double kxs, kys;     // 2 pi / L_x, 2 pi / L_y
     const double* table; // Y_TABLE multiplier, [ns][table_row] reals
     int table_row;
@@ -269,7 +274,9 @@ template <int NIN, int NOUT, bool MULTI> struct YCfg {
     static constexpr int MINB = TileGeom<8>::blocks_for(NTHR, regs);
     static constexpr int SL = SmemLen<NMAX>::value;
     static constexpr int NBUF = MULTI ? 2 : 1;
-    static constexpr size_t smem = size_t(NBUF * TC * SL + NIN / 2 + NOUT / 2) * sizeof(cplx);
+    static constexpr int TWI = PlanInfo<(NIN > 0 ? NIN : 8)>::twlen * (NIN > 0);
+    static constexpr int TWO = PlanInfo<(NOUT > 0 ? NOUT : 8)>::twlen * (NOUT > 0);
+    static constexpr size_t smem = size_t(NBUF * TC * SL + TWI + TWO) * sizeof(cplx);
 };
 
 // NIN  > 0: forward transform of length NIN first (input is the x-pass intermediate)
@@ -285,15 +292,16 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
     cplx* buf = sm;                                     // work buffer
     cplx* S = MULTI ? sm + TC * SL : sm;                // spectrum of the tile (NS rows used)
     cplx* Win = sm + C::NBUF * TC * SL;
-    cplx* Wout = Win + NIN / 2;
-    if (NIN > 0) load_table(Win, Wing, NIN / 2);
-    if (NOUT > 0) load_table(Wout, Woutg, NOUT / 2);
+    cplx* Wout = Win + C::TWI;
+    if (NIN > 0) load_table(Win, Wing, C::TWI);
+    if (NOUT > 0) load_table(Wout, Woutg, C::TWO);
     __syncthreads();
-    const YField& F = a.fld[blockIdx.y];
     auto sidx = [](int f, int i) { return spad(i) * TC + f; };
     const int ntc = (a.ncols + TC - 1) / TC;
     const long ntiles = long(ntc) * a.nplanes;
-    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long work = blockIdx.x; work < ntiles * a.nfields; work += gridDim.x) {
+        const YField& F = a.fld[work % a.nfields];
+        const long tile = work / a.nfields;
         const int c0 = int(tile % ntc) * TC;
         const int k = a.k0 + int(tile / ntc);
         const double* src = F.src + long(k) * a.src_plane + 2 * c0;

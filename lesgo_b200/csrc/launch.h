@@ -14,6 +14,8 @@ int launch_xinv(int NX, const XiSrc& in, const EpiStore& epi, int nfields, int n
 int launch_ypass(int nin, int nout, const YArgs& a, int nfields, int nplanes, const cplx* Win,
                  const cplx* Wout, cudaStream_t s);
 bool size_supported(int n_small);
+// radices and stage-twiddle-table length of the plan for complex length n (false if none)
+bool plan_lookup(int n, PlanDesc* out);
 
 template <class K> inline void set_smem(K kernel, size_t bytes) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));

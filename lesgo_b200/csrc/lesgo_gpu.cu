@@ -96,19 +96,44 @@ int dev_alloc(lesgo_gpu_ctx* c, double** p, size_t ndoubles) {
     return 0;
 }
 
-int make_twiddle(lesgo_gpu_ctx* c, cplx** dst, int n, int count, int denom) {
-    std::vector<cplx> h(count);
-    for (int m = 0; m < count; ++m) {
-        long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)denom;
-        h[m] = make_double2((double)cosl(ang), (double)sinl(ang));
-    }
-    (void)n;
+int upload_table(lesgo_gpu_ctx* c, cplx** dst, const std::vector<cplx>& h) {
     void* q = nullptr;
-    CK(cudaMalloc(&q, sizeof(cplx) * count));
-    CK(cudaMemcpy(q, h.data(), sizeof(cplx) * count, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&q, sizeof(cplx) * (h.size() + 1)));
+    if (!h.empty()) CK(cudaMemcpy(q, h.data(), sizeof(cplx) * h.size(), cudaMemcpyHostToDevice));
     c->allocs.push_back(q);
     *dst = static_cast<cplx*>(q);
     return 0;
+}
+
+cplx unit_root(long m, long n) {   // exp(-2 pi i m / n), long double accuracy
+    long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)(m % n) / (long double)n;
+    return make_double2((double)cosl(ang), (double)sinl(ang));
+}
+
+// stage twiddles of Plan<n> in the layout fft_core.h's stage_load reads:
+// for stage s >= 2 (radix R, Ns = product of earlier radices): T[(r-1)*Ns + k] = W_n^{k r n/(Ns R)}
+int make_stage_twiddles(lesgo_gpu_ctx* c, cplx** dst, int n) {
+    PlanDesc d;
+    if (!plan_lookup(n, &d)) return c->fail("no FFT plan for length " + std::to_string(n));
+    std::vector<cplx> h;
+    int ns = d.r[0];
+    for (int s = 1; s < 4; ++s) {
+        const int R = d.r[s];
+        if (R == 1) break;
+        const long step = n / (long(ns) * R);
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < ns; ++k) h.push_back(unit_root(long(k) * r * step, n));
+        ns *= R;
+    }
+    if (int(h.size()) != d.twlen) return c->fail("internal: stage twiddle table length mismatch");
+    return upload_table(c, dst, h);
+}
+
+// W_{2m}^k, k = 0..m/2: the real<->half-complex untangling factors of a length-2m real row
+int make_half_twiddles(lesgo_gpu_ctx* c, cplx** dst, int m) {
+    std::vector<cplx> h(m / 2 + 1);
+    for (int k = 0; k <= m / 2; ++k) h[k] = unit_root(k, 2L * m);
+    return upload_table(c, dst, h);
 }
 
 int need_small(lesgo_gpu_ctx* c, int n) {
@@ -234,6 +259,16 @@ int ypass(lesgo_gpu_ctx* c, int nin, int nout, const YArgs& a, int nf, int k0, i
     auto W = [&](int n) -> const cplx* { return n == c->ny ? c->Wy : (n == c->ny2 ? c->Wyb : nullptr); };
     int rc = launch_ypass(nin, nout, a, nf, k1 - k0, nin ? W(nin) : W(nout), nout ? W(nout) : W(nin), c->stream);
     if (rc) return c->fail("unsupported ny for y pass");
+    c->launches++;
+    return 0;
+}
+
+int glue_fused(lesgo_gpu_ctx* c, int mode, double* rhs, const double* b, double* rhs_f, double* u, int k0, int k1,
+               int kproj, int first_step, double force, double dt, double t1, double t2) {
+    if (k1 <= k0) return 0;
+    ProfScope ps_(c, "glue");
+    LG_LAUNCH(k_glue_fused, dim3(grid1d(long(c->lh) * c->ny * (k1 - k0))), dim3(kBlock), 0, c->stream, mode, rhs, b, rhs_f,
+              u, c->lay(), c->nx, c->ny, k0, k1, kproj, first_step, force, dt, t1, t2);
     c->launches++;
     return 0;
 }
@@ -549,20 +584,14 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     // :207
     if (convec(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DUDY], F[LG_DUDZ], F[LG_DVDX], F[LG_DVDZ], F[LG_DWDX],
                F[LG_DWDY], F[LG_RHSX], F[LG_RHSY], F[LG_RHSZ])) return 1;
-    // :211-214, 229-232
-    glue(c, G_RHS_ASSEMBLE, F[LG_RHSX], F[LG_DIVTX], nullptr, c->ld, 1, nz, sp->mean_p_force_x, 0, 0);
-    glue(c, G_RHS_ASSEMBLE, F[LG_RHSY], F[LG_DIVTY], nullptr, c->ld, 1, nz, sp->mean_p_force_y, 0, 0);
-    glue(c, G_RHS_ASSEMBLE, F[LG_RHSZ], F[LG_DIVTZ], nullptr, c->ld, 1, c->top ? nz + 1 : nz, 0.0, 0, 0);
-    // :273-280
-    if (sp->first_step) {
-        CK(cudaMemcpyAsync(F[LG_RHSX_F], F[LG_RHSX], fb, cudaMemcpyDeviceToDevice, c->stream));
-        CK(cudaMemcpyAsync(F[LG_RHSY_F], F[LG_RHSY], fb, cudaMemcpyDeviceToDevice, c->stream));
-        CK(cudaMemcpyAsync(F[LG_RHSZ_F], F[LG_RHSZ], fb, cudaMemcpyDeviceToDevice, c->stream));
+    // :211-214, 229-232 (RHS assembly), :273-280 (Euler start), :287-296 (AB2) in one pass per component
+    {
+        const int kw = c->top ? nz + 1 : nz;
+        const int fs = sp->first_step ? 1 : 0;
+        glue_fused(c, F_RHS_AB2, F[LG_RHSX], F[LG_DIVTX], F[LG_RHSX_F], F[LG_U], 1, nz, 0, fs, sp->mean_p_force_x, sp->dt, sp->tadv1, sp->tadv2);
+        glue_fused(c, F_RHS_AB2, F[LG_RHSY], F[LG_DIVTY], F[LG_RHSY_F], F[LG_V], 1, nz, 0, fs, sp->mean_p_force_y, sp->dt, sp->tadv1, sp->tadv2);
+        glue_fused(c, F_RHS_AB2, F[LG_RHSZ], F[LG_DIVTZ], F[LG_RHSZ_F], F[LG_W], 1, kw, 0, fs, 0.0, sp->dt, sp->tadv1, sp->tadv2);
     }
-    // :287-296
-    glue(c, G_AB2, F[LG_U], F[LG_RHSX], F[LG_RHSX_F], c->ld, 1, nz, sp->dt, sp->tadv1, sp->tadv2);
-    glue(c, G_AB2, F[LG_V], F[LG_RHSY], F[LG_RHSY_F], c->ld, 1, nz, sp->dt, sp->tadv1, sp->tadv2);
-    glue(c, G_AB2, F[LG_W], F[LG_RHSZ], F[LG_RHSZ_F], c->ld, 1, c->top ? nz + 1 : nz, sp->dt, sp->tadv1, sp->tadv2);
     // :299-308
     fill(c, F[LG_U], c->plane, 0, 1, kBogus); fill(c, F[LG_V], c->plane, 0, 1, kBogus); fill(c, F[LG_W], c->plane, 0, 1, kBogus);
     fill(c, F[LG_U], c->plane, nz, nz + 1, kBogus); fill(c, F[LG_V], c->plane, nz, nz + 1, kBogus);
@@ -570,14 +599,12 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     // :317
     if (press(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DIVTZ], sp->dt, sp->tadv1, F[LG_P], F[LG_DPDX], F[LG_DPDY],
               F[LG_DPDZ])) return 1;
-    // :321-326
-    glue(c, G_SUB, F[LG_RHSX], F[LG_DPDX], nullptr, c->ld, 1, nz, 0, 0, 0);
-    glue(c, G_SUB, F[LG_RHSY], F[LG_DPDY], nullptr, c->ld, 1, nz, 0, 0, 0);
-    glue(c, G_SUB, F[LG_RHSZ], F[LG_DPDZ], nullptr, c->ld, 1, c->top ? nz + 1 : nz, 0, 0, 0);
-    // project, forcing.f90:149-244
-    glue(c, G_PROJECT, F[LG_U], F[LG_DPDX], nullptr, c->nx, 1, nz, sp->dt, sp->tadv1, 0);
-    glue(c, G_PROJECT, F[LG_V], F[LG_DPDY], nullptr, c->nx, 1, nz, sp->dt, sp->tadv1, 0);
-    glue(c, G_PROJECT, F[LG_W], F[LG_DPDZ], nullptr, c->nx, c->bottom ? 2 : 1, nz, sp->dt, sp->tadv1, 0);
+    // :321-326 (RHS -= grad p) and project (forcing.f90:171-207) in one pass per component
+    glue_fused(c, F_GRADP_PROJECT, F[LG_RHSX], F[LG_DPDX], nullptr, F[LG_U], 1, nz, 1, 0, 0.0, sp->dt, sp->tadv1, 0.0);
+    glue_fused(c, F_GRADP_PROJECT, F[LG_RHSY], F[LG_DPDY], nullptr, F[LG_V], 1, nz, 1, 0, 0.0, sp->dt, sp->tadv1, 0.0);
+    // w: RHSz gets plane nz on the top rank too, the projection stops at nz-1 and skips plane 1 at the wall
+    glue_fused(c, F_GRADP_PROJECT, F[LG_RHSZ], F[LG_DPDZ], nullptr, F[LG_W], 1, nz, c->bottom ? 2 : 1, 0, 0.0, sp->dt, sp->tadv1, 0.0);
+    if (c->top) glue(c, G_SUB, F[LG_RHSZ], F[LG_DPDZ], nullptr, c->ld, nz, nz + 1, 0, 0, 0);
     if (c->comm) {
         if (c->comm->sync_planes(F[LG_U], c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
         if (c->comm->sync_planes(F[LG_V], c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
@@ -630,12 +657,12 @@ int lesgo_gpu_create(const lesgo_gpu_dims* d, lesgo_gpu_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream create failed");
     c->own_stream = true;
     int rc = 0;
-    rc |= make_twiddle(c, &c->Wx, c->nx / 2, c->nx / 2, c->nx / 2);
-    rc |= make_twiddle(c, &c->Whx, c->nx / 2, c->nx / 4 + 1, c->nx);
-    rc |= make_twiddle(c, &c->Wxb, c->nx2 / 2, c->nx2 / 2, c->nx2 / 2);
-    rc |= make_twiddle(c, &c->Whxb, c->nx2 / 2, c->nx2 / 4 + 1, c->nx2);
-    rc |= make_twiddle(c, &c->Wy, c->ny, c->ny, c->ny);
-    rc |= make_twiddle(c, &c->Wyb, c->ny2, c->ny2, c->ny2);
+    rc |= make_stage_twiddles(c, &c->Wx, c->nx / 2);
+    rc |= make_half_twiddles(c, &c->Whx, c->nx / 2);
+    rc |= make_stage_twiddles(c, &c->Wxb, c->nx2 / 2);
+    rc |= make_half_twiddles(c, &c->Whxb, c->nx2 / 2);
+    rc |= make_stage_twiddles(c, &c->Wy, c->ny);
+    rc |= make_stage_twiddles(c, &c->Wyb, c->ny2);
     if (rc) { std::string m = c->err; return bail(m); }
     *out = c;
     return 0;

@@ -623,4 +623,41 @@ static __global__ void k_press_unpack(PencilGeom g, const double* __restrict__ b
     }
 }
 
+// Fused time-stepping glue (one pass instead of two per component):
+//  F_RHS_AB2      : rhs = -rhs - divt + force                         main.f90:211-214,229-232
+//                   [first step: rhs_f = rhs                           main.f90:273-280]
+//                   u = u + dt*(tadv1*rhs + tadv2*rhs_f)               main.f90:287-296
+//  F_GRADP_PROJECT: rhs = rhs - dpd                                    main.f90:321-326
+//                   u = u + dt*(-tadv1*dpd)  for k >= kproj, over 1:nx forcing.f90:171-207
+enum FusedMode { F_RHS_AB2 = 0, F_GRADP_PROJECT = 1 };
+static __global__ void k_glue_fused(int mode, double* __restrict__ rhs, const double* __restrict__ b,
+                                    double* __restrict__ rhs_f, double* __restrict__ u, Lay lay, int nx, int ny,
+                                    int k0, int k1, int kproj, int first_step, double force, double dt, double t1,
+                                    double t2) {
+    const int half = lay.row / 2;
+    const long n = long(half) * ny * (k1 - k0);
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        const int j = int(t % half);
+        long r = t / half;
+        const int y = int(r % ny), k = k0 + int(r / ny);
+        const long o = lay.at(k, y, 2 * j);
+        double2 vr = ld2(rhs + o), vb = ld2(b + o), vu = ld2(u + o);
+        if (mode == F_RHS_AB2) {
+            double2 nr = make_double2(dadd(dsub(-vr.x, vb.x), force), dadd(dsub(-vr.y, vb.y), force));
+            double2 vf;
+            if (first_step) { vf = nr; *reinterpret_cast<double2*>(rhs_f + o) = nr; }
+            else vf = ld2(rhs_f + o);
+            *reinterpret_cast<double2*>(rhs + o) = nr;
+            *reinterpret_cast<double2*>(u + o) =
+                make_double2(dadd(vu.x, dmul(dt, dadd(dmul(t1, nr.x), dmul(t2, vf.x)))),
+                             dadd(vu.y, dmul(dt, dadd(dmul(t1, nr.y), dmul(t2, vf.y)))));
+        } else {
+            *reinterpret_cast<double2*>(rhs + o) = make_double2(dsub(vr.x, vb.x), dsub(vr.y, vb.y));
+            if (k >= kproj && 2 * j < nx)
+                *reinterpret_cast<double2*>(u + o) = make_double2(dadd(vu.x, dmul(dt, dmul(-t1, vb.x))),
+                                                                  dadd(vu.y, dmul(dt, dmul(-t1, vb.y))));
+        }
+    }
+}
+
 }  // namespace lg

@@ -12,8 +12,8 @@ static int launch_xfwd_n(const Pro& pro, int nfields, const XfOut& out, int ny, 
     if (!attr) { set_smem(k_xfwd<NX, Pro>, C::smem); attr = true; }
     const long nrows = long(ny) * nplanes;
     if (nrows <= 0) return 0;
-    dim3 grid(persistent_blocks(C::smem, (nrows + C::NF - 1) / C::NF, C::MINB), nfields);
-    LG_LAUNCH((k_xfwd<NX, Pro>), grid, dim3(C::NTHR), C::smem, s, pro, out, ny, k0, nplanes, W, Wh);
+    dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, C::MINB));
+    LG_LAUNCH((k_xfwd<NX, Pro>), grid, dim3(C::NTHR), C::smem, s, pro, out, nfields, ny, k0, nplanes, W, Wh);
     return 0;
 }
 }  // namespace lg

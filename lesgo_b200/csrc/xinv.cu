@@ -9,8 +9,8 @@ static int launch_xinv_n(const XiSrc& in, const EpiStore& epi, int nfields, int 
     if (!attr) { set_smem(k_xinv<NX, EpiStore>, C::smem); attr = true; }
     const long nrows = long(ny) * nplanes;
     if (nrows <= 0) return 0;
-    dim3 grid(persistent_blocks(C::smem, (nrows + C::NF - 1) / C::NF, C::MINB), nfields);
-    LG_LAUNCH((k_xinv<NX, EpiStore>), grid, dim3(C::NTHR), C::smem, s, in, epi, ny, k0, nplanes, W, Wh);
+    dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, C::MINB));
+    LG_LAUNCH((k_xinv<NX, EpiStore>), grid, dim3(C::NTHR), C::smem, s, in, epi, nfields, ny, k0, nplanes, W, Wh);
     return 0;
 }
 #define LG_XINV_CASE_SMALL(S, B) case S: return launch_xinv_n<S>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);

@@ -10,8 +10,9 @@ static int launch_y_m(const YArgs& a0, int nfields, int nplanes, const cplx* Win
     if (nplanes <= 0 || nfields <= 0) return 0;
     YArgs a = a0;
     a.nplanes = nplanes;
+    a.nfields = nfields;
     const long ntiles = long((a.ncols + C::TC - 1) / C::TC) * nplanes;
-    dim3 grid(persistent_blocks(C::smem, ntiles, C::MINB), nfields);
+    dim3 grid(persistent_blocks(C::smem, ntiles * nfields, C::MINB));
     LG_LAUNCH((k_ypass<NIN, NOUT, MULTI>), grid, dim3(C::NTHR), C::smem, s, a, Win, Wout);
     return 0;
 }
@@ -41,6 +42,14 @@ int launch_ypass(int nin, int nout, const YArgs& a, int nfields, int nplanes, co
     return -1;
 }
 #define LG_SUP(S, B) if (n == S) return true;
+bool plan_lookup(int n, PlanDesc* out) {
+#define LG_PL(N) if (n == N) { *out = plan_desc<N>(); return true; }
+    LG_PL(8) LG_PL(12) LG_PL(16) LG_PL(24) LG_PL(32) LG_PL(36) LG_PL(40) LG_PL(48) LG_PL(60) LG_PL(64) LG_PL(72)
+    LG_PL(80) LG_PL(96) LG_PL(120) LG_PL(128) LG_PL(144) LG_PL(160) LG_PL(192) LG_PL(240) LG_PL(256) LG_PL(288)
+    LG_PL(320) LG_PL(384) LG_PL(480) LG_PL(512) LG_PL(576) LG_PL(640) LG_PL(768) LG_PL(1024) LG_PL(1536)
+#undef LG_PL
+    return false;
+}
 int sm_count() {
     static int n = 0;
     if (n == 0) {

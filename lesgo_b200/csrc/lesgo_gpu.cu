@@ -4,6 +4,7 @@
 // main.f90:155-344 / forcing.f90:149-244.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -33,6 +34,8 @@ struct lesgo_gpu_ctx {
     bool own_stream = false;
     std::string err;
     long launches = 0;
+    int device = 0;                    // CUDA device of this context (made current on every entry)
+    int chunk = 0;                     // planes per pipelined chunk (0 = whole slab); see lesgo_gpu_create
     // twiddles: W_n[m] = exp(-2 pi i m/n); Wh_n[m] = exp(-2 pi i m/(2n)) for the real<->complex step
     cplx *Wx = nullptr, *Whx = nullptr, *Wxb = nullptr, *Whxb = nullptr, *Wy = nullptr, *Wyb = nullptr;
     // scratch
@@ -293,13 +296,18 @@ int glue(lesgo_gpu_ctx* c, int mode, double* a, const double* b, const double* c
 
 // ---- derivatives.f90 --------------------------------------------------------------------------
 // which: bit 0 = f itself (filt_da), bit 1 = d/dx, bit 2 = d/dy
+int chunk_of(const lesgo_gpu_ctx* c, int divisor) {
+    if (c->chunk <= 0) return c->nz + 1;
+    int ch = c->chunk / divisor;
+    return ch < 1 ? 1 : ch;
+}
+
 int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx, double* dfdy) {
     if (need_small(c, 4)) return 1;
     const int nz = c->nz;
     ProScale pro;
     pro.src[0] = f; pro.lay = c->lay(); pro.scale = 1.0 / (double(c->nx) * double(c->ny));
     double* d0[1] = {c->sa[0]};
-    if (xfwd(c, false, pro, 1, d0, c->plane, c->ld, c->nx / 2, c->ny, 0, nz + 1)) return 1;
     YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, c->nx / 2, 0);
     a.fld[0].src = c->sa[0];
     const double* xs[3];
@@ -309,8 +317,17 @@ int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx
     if (dfdx) { a.fld[0].out[n] = YOutSpec{c->sa[1 + n], Y_IKX}; xs[n] = c->sa[1 + n]; xd[n] = dfdx; ++n; }
     if (dfdy) { a.fld[0].out[n] = YOutSpec{c->sa[1 + n], Y_IKY}; xs[n] = c->sa[1 + n]; xd[n] = dfdy; ++n; }
     a.nout = n;
-    if (ypass(c, c->ny, c->ny, a, 1, 0, nz + 1)) return 1;
-    return xinv(c, false, xs, c->plane, c->ld, c->nx / 2, n, xd, c->lay(), c->ny, 0, nz + 1);
+    // plane chunks: the x->y->x passes of a chunk run back to back so the two spectral
+    // intermediates are still in L2 when the next pass reads them
+    const int ch = chunk_of(c, 1);
+    for (int ka = 0; ka < nz + 1; ka += ch) {
+        const int kb = ka + ch < nz + 1 ? ka + ch : nz + 1;
+        if (xfwd(c, false, pro, 1, d0, c->plane, c->ld, c->nx / 2, c->ny, ka, kb)) return 1;
+        a.k0 = ka;
+        if (ypass(c, c->ny, c->ny, a, 1, ka, kb)) return 1;
+        if (xinv(c, false, xs, c->plane, c->ld, c->nx / 2, n, xd, c->lay(), c->ny, ka, kb)) return 1;
+    }
+    return 0;
 }
 
 int ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
@@ -347,42 +364,54 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
     if (need_small(c, 6) || need_big(c, 6)) return 1;
     const int nz = c->nz, nxh = c->nx / 2;
     const double cs = 1.0 / (double(c->nx) * double(c->ny));
-    // (1) u, v, w (planes 0..nz) and the vorticity (1..nz) to half spectra   convec.f90:73-82, 97-158
     ProScale ps;
     ps.src[0] = u; ps.src[1] = v; ps.src[2] = w; ps.lay = c->lay(); ps.scale = cs;
-    if (xfwd(c, false, ps, 3, c->sa, c->plane, c->ld, nxh, c->ny, 0, nz + 1)) return 1;
     ProVort pv;
     pv.dudy = dudy; pv.dudz = dudz; pv.dvdx = dvdx; pv.dvdz = dvdz; pv.dwdx = dwdx; pv.dwdy = dwdy;
     pv.lay = c->lay(); pv.scale = cs; pv.nz = nz; pv.bottom = c->bottom; pv.top = c->top;
     pv.lbc_mom = c->d.lbc_mom; pv.ubc_mom = c->d.ubc_mom;
-    if (xfwd(c, false, pv, 3, c->sa + 3, c->plane, c->ld, nxh, c->ny, 1, nz + 1)) return 1;
-    // (2) y forward, padd (fft.f90:43-71), y inverse on the 3/2 grid
-    {
-        YArgs a = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, 0);
-        for (int i = 0; i < 3; ++i) { a.fld[i].src = c->sa[i]; a.fld[i].out[0] = YOutSpec{c->bb[i], Y_COPY}; }
-        if (ypass(c, c->ny, c->ny2, a, 3, 0, nz + 1)) return 1;
-        YArgs b = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, 1);
-        for (int i = 0; i < 3; ++i) { b.fld[i].src = c->sa[3 + i]; b.fld[i].out[0] = YOutSpec{c->bb[3 + i], Y_COPY}; }
-        if (ypass(c, c->ny, c->ny2, b, 3, 1, nz + 1)) return 1;
-    }
-    // (3) x inverse on the 3/2 grid: only kx < nx/2 carries data                 :90-92, 165-167
-    if (xinv(c, true, c->bb, c->plane_bi, c->ld, nxh, 3, c->big, c->lay_big(), c->ny2, 0, nz + 1)) return 1;
-    if (xinv(c, true, c->bb + 3, c->plane_bi, c->ld, nxh, 3, c->big + 3, c->lay_big(), c->ny2, 1, nz + 1)) return 1;
-    // (4) products fused into the x forward pass on the 3/2 grid                 :172-305
     ProConvec pc;
     pc.u = c->big[0]; pc.v = c->big[1]; pc.w = c->big[2]; pc.o1 = c->big[3]; pc.o2 = c->big[4]; pc.o3 = c->big[5];
     pc.lay = c->lay_big(); pc.scale = 1.0 / (double(c->nx2) * double(c->ny2));
     pc.nz = nz; pc.bottom = c->bottom; pc.top = c->top; pc.jzLo = c->jzLo;
-    if (xfwd(c, true, pc, 3, c->bb, c->plane_bi, c->ld, nxh, c->ny2, 1, nz + 1)) return 1;
-    // (5) y forward on the 3/2 grid, unpadd (fft.f90:74-99), y inverse            :206-213
-    {
-        YArgs a = yargs(c, c->plane_bi, c->ld, c->plane, c->ld, nxh, 1);
-        for (int i = 0; i < 3; ++i) { a.fld[i].src = c->bb[i]; a.fld[i].out[0] = YOutSpec{c->sa[i], Y_COPY}; }
-        if (ypass(c, c->ny2, c->ny, a, 3, 1, nz + 1)) return 1;
-    }
-    // (6) x inverse -> RHS
     double* out[3] = {RHSx, RHSy, RHSz};
-    if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, 1, nz + 1)) return 1;
+    // Plane chunks, software-pipelined by one plane: the products of plane p need the 3/2-grid
+    // fields at p-1, p, p+1, so chunk [ka,kb) first brings planes [ka,kb) to the 3/2 grid and then
+    // forms the products of planes [ka-1, kb-1) -- everything a chunk touches is still in L2.
+    const int ch = chunk_of(c, 4);
+    for (int ka = 0; ka < nz + 1; ka += ch) {
+        const int kb = ka + ch < nz + 1 ? ka + ch : nz + 1;
+        const int va = ka < 1 ? 1 : ka;                 // vorticity exists on planes 1..nz
+        // (1) u, v, w and the vorticity to half spectra                          convec.f90:73-82, 97-158
+        if (xfwd(c, false, ps, 3, c->sa, c->plane, c->ld, nxh, c->ny, ka, kb)) return 1;
+        if (xfwd(c, false, pv, 3, c->sa + 3, c->plane, c->ld, nxh, c->ny, va, kb)) return 1;
+        // (2) y forward, padd (fft.f90:43-71), y inverse on the 3/2 grid
+        {
+            YArgs a = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, ka);
+            for (int i = 0; i < 3; ++i) { a.fld[i].src = c->sa[i]; a.fld[i].out[0] = YOutSpec{c->bb[i], Y_COPY}; }
+            if (ypass(c, c->ny, c->ny2, a, 3, ka, kb)) return 1;
+            YArgs b = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, va);
+            for (int i = 0; i < 3; ++i) { b.fld[i].src = c->sa[3 + i]; b.fld[i].out[0] = YOutSpec{c->bb[3 + i], Y_COPY}; }
+            if (ypass(c, c->ny, c->ny2, b, 3, va, kb)) return 1;
+        }
+        // (3) x inverse on the 3/2 grid: only kx < nx/2 carries data               :90-92, 165-167
+        if (xinv(c, true, c->bb, c->plane_bi, c->ld, nxh, 3, c->big, c->lay_big(), c->ny2, ka, kb)) return 1;
+        if (xinv(c, true, c->bb + 3, c->plane_bi, c->ld, nxh, 3, c->big + 3, c->lay_big(), c->ny2, va, kb)) return 1;
+        // products of the planes whose upper neighbour is now available
+        const int pa = ka - 1 < 1 ? 1 : ka - 1;
+        const int pb = kb == nz + 1 ? nz + 1 : kb - 1;
+        if (pb <= pa) continue;
+        // (4) products fused into the x forward pass on the 3/2 grid               :172-305
+        if (xfwd(c, true, pc, 3, c->bb, c->plane_bi, c->ld, nxh, c->ny2, pa, pb)) return 1;
+        // (5) y forward on the 3/2 grid, unpadd (fft.f90:74-99), y inverse          :206-213
+        {
+            YArgs a = yargs(c, c->plane_bi, c->ld, c->plane, c->ld, nxh, pa);
+            for (int i = 0; i < 3; ++i) { a.fld[i].src = c->bb[i]; a.fld[i].out[0] = YOutSpec{c->sa[i], Y_COPY}; }
+            if (ypass(c, c->ny2, c->ny, a, 3, pa, pb)) return 1;
+        }
+        // (6) x inverse -> RHS
+        if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, pa, pb)) return 1;
+    }
     // :319-332
     fill(c, RHSx, c->plane, 0, 1, kBogus); fill(c, RHSy, c->plane, 0, 1, kBogus); fill(c, RHSz, c->plane, 0, 1, kBogus);
     fill(c, RHSx, c->plane, nz, nz + 1, kBogus); fill(c, RHSy, c->plane, nz, nz + 1, kBogus);
@@ -412,31 +441,35 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
     const double cst = 1.0 / (double(c->nx) * double(c->ny));
     const double cst2 = cst / tadv1 / dt;                          // press_stag_array.f90:51-52
     // (1) x forward of u*/(tadv1 dt): planes 1..nz-1, + w(nz) on the top rank      :77-103
+    // (2) y forward in place, Nyquist row zeroed                                   :129-146
     ProScale ps;
     ps.src[0] = u; ps.src[1] = v; ps.src[2] = w; ps.lay = c->lay(); ps.scale = cst2;
-    if (xfwd(c, false, ps, 3, c->sa, c->plane, c->ld, nxh, c->ny, 1, nz)) return 1;
+    const int ch = chunk_of(c, 2);
+    for (int ka = 1; ka < nz; ka += ch) {
+        const int kb = ka + ch < nz ? ka + ch : nz;
+        if (xfwd(c, false, ps, 3, c->sa, c->plane, c->ld, nxh, c->ny, ka, kb)) return 1;
+        YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, ka);
+        for (int i = 0; i < 3; ++i) { a.fld[i].src = c->sa[i]; a.fld[i].out[0] = YOutSpec{c->sa[i], Y_COPY}; }
+        if (ypass(c, c->ny, 0, a, 3, ka, kb)) return 1;
+    }
+    // boundary planes: w(nz) on the top rank, divtz at the walls                    :100-126
+    ProScale pd; pd.src[0] = divtz; pd.lay = c->lay(); pd.scale = cst;
+    double* d3[1] = {c->sa[3]};
     if (c->top) {
         ProScale pw; pw.src[0] = w; pw.lay = c->lay(); pw.scale = cst2;
         double* d[1] = {c->sa[2]};
         if (xfwd(c, false, pw, 1, d, c->plane, c->ld, nxh, c->ny, nz, nz + 1)) return 1;
-    }
-    // boundary planes from divtz                                                   :114-126
-    ProScale pd; pd.src[0] = divtz; pd.lay = c->lay(); pd.scale = cst;
-    double* d3[1] = {c->sa[3]};
-    if (c->bottom && xfwd(c, false, pd, 1, d3, c->plane, c->ld, nxh, c->ny, 1, 2)) return 1;
-    if (c->top && xfwd(c, false, pd, 1, d3, c->plane, c->ld, nxh, c->ny, nz, nz + 1)) return 1;
-    // (2) y forward in place, Nyquist row zeroed                                   :129-146
-    {
-        YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, 1);
-        for (int i = 0; i < 3; ++i) { a.fld[i].src = c->sa[i]; a.fld[i].out[0] = YOutSpec{c->sa[i], Y_COPY}; }
-        if (ypass(c, c->ny, 0, a, 3, 1, nz)) return 1;
+        if (xfwd(c, false, pd, 1, d3, c->plane, c->ld, nxh, c->ny, nz, nz + 1)) return 1;
         YArgs b = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, nz);
         b.fld[0].src = c->sa[2]; b.fld[0].out[0] = YOutSpec{c->sa[2], Y_COPY};
         b.fld[1].src = c->sa[3]; b.fld[1].out[0] = YOutSpec{c->sa[3], Y_COPY};
-        if (c->top && ypass(c, c->ny, 0, b, 2, nz, nz + 1)) return 1;
+        if (ypass(c, c->ny, 0, b, 2, nz, nz + 1)) return 1;
+    }
+    if (c->bottom) {
+        if (xfwd(c, false, pd, 1, d3, c->plane, c->ld, nxh, c->ny, 1, 2)) return 1;
         YArgs e = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, 1);
         e.fld[0].src = c->sa[3]; e.fld[0].out[0] = YOutSpec{c->sa[3], Y_COPY};
-        if (c->bottom && ypass(c, c->ny, 0, e, 1, 1, 2)) return 1;
+        if (ypass(c, c->ny, 0, e, 1, 1, 2)) return 1;
     }
     // (3) tridiagonal solve + k=0 chain                                           :149-239
     double* phat = c->sa[4];
@@ -504,6 +537,7 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         }
     }
     // (4) y inverse of p, i kx p, i ky p (oddballs dropped), x inverse              :248-273
+    // (5) dpdz = (p(k) - p(k-1))/dz                                                 :276-288
     {
         YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, 0);
         a.fld[0].src = phat;
@@ -511,21 +545,26 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         a.fld[0].out[1] = YOutSpec{c->sa[1], Y_IKX};
         a.fld[0].out[2] = YOutSpec{c->sa[2], Y_IKY};
         a.nout = 3;
-        if (ypass(c, 0, c->ny, a, 1, 0, nz + 1)) return 1;
         const double* s0[1] = {c->sa[0]};
         double* o0[1] = {p};
-        if (xinv(c, false, s0, c->plane, c->ld, nxh, 1, o0, c->lay(), c->ny, 0, c->top ? nz + 1 : nz)) return 1;
         const double* s1[2] = {c->sa[1], c->sa[2]};
         double* o1[2] = {dpdx, dpdy};
-        if (xinv(c, false, s1, c->plane, c->ld, nxh, 2, o1, c->lay(), c->ny, 1, nz)) return 1;
-    }
-    // (5) dpdz                                                                       :276-288
-    {
-        const int k1 = c->top ? nz + 1 : nz;
-        ProfScope ps_(c, "dpdz");
-        LG_LAUNCH(k_dpdz, dim3(grid1d(long(nxh) * c->ny * (k1 - 1))), dim3(kBlock), 0, c->stream, p, dpdz, c->lay(),
-                  c->nx, c->ny, 1, k1, c->d.dz);
-        c->launches++;
+        const int pend = c->top ? nz + 1 : nz;          // p is transformed on planes 0..pend-1
+        for (int ka = 0; ka < nz + 1; ka += ch) {
+            const int kb = ka + ch < nz + 1 ? ka + ch : nz + 1;
+            a.k0 = ka;
+            if (ypass(c, 0, c->ny, a, 1, ka, kb)) return 1;
+            if (xinv(c, false, s0, c->plane, c->ld, nxh, 1, o0, c->lay(), c->ny, ka, kb < pend ? kb : pend)) return 1;
+            const int da = ka < 1 ? 1 : ka, db = kb < nz ? kb : nz;
+            if (xinv(c, false, s1, c->plane, c->ld, nxh, 2, o1, c->lay(), c->ny, da, db)) return 1;
+            const int za = ka < 1 ? 1 : ka, zb = kb < pend ? kb : pend;
+            if (zb > za) {
+                ProfScope ps_(c, "dpdz");
+                LG_LAUNCH(k_dpdz, dim3(grid1d(long(nxh) * c->ny * (zb - za))), dim3(kBlock), 0, c->stream, p, dpdz, c->lay(),
+                          c->nx, c->ny, za, zb, c->d.dz);
+                c->launches++;
+            }
+        }
     }
     fill(c, dpdx, c->plane, nz, nz + 1, kBogus);
     fill(c, dpdy, c->plane, nz, nz + 1, kBogus);
@@ -624,6 +663,9 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
 }  // namespace
 
 // =====================================================================================================
+// every entry point makes the context's device current for the calling thread
+#define ENTER(c) do { if (c) cudaSetDevice((c)->device); } while (0)
+
 extern "C" {
 
 const char* lesgo_gpu_last_error(const lesgo_gpu_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
@@ -641,6 +683,7 @@ int lesgo_gpu_create(const lesgo_gpu_dims* d, lesgo_gpu_ctx** out) {
         if (d->device >= ndev) return bail("device ordinal out of range");
         if (cudaSetDevice(d->device) != cudaSuccess) return bail("cudaSetDevice failed");
     }
+    cudaGetDevice(&c->device);
     if (d->nx < 16 || d->ny < 16 || d->nz < 2 || (d->nx % 4) || (d->ny % 4)) return bail("bad grid size");
     if (!size_supported(d->nx) || !size_supported(d->ny)) return bail("nx/ny not in the supported FFT size list (sizes.h)");
     if (d->nproc < 1 || d->coord < 0 || d->coord >= d->nproc) return bail("bad nproc/coord");
@@ -654,6 +697,15 @@ int lesgo_gpu_create(const lesgo_gpu_dims* d, lesgo_gpu_ctx** out) {
     c->jzLo = d->sgs ? 2 : 1;
     const double pi = 3.14159265358979323846;   // param.f90 pi
     c->kxs = 2.0 * pi / d->L_x; c->kys = 2.0 * pi / d->L_y;
+    {
+        // planes per pipelined chunk (LESGO_CHUNK_PLANES; default 0 = every pass covers the whole
+        // slab).  Measured on B200 at 512x512x257 (profiles/r1_chunk_sweep.md): chunks of 4/8/16/32
+        // planes cost 59.6/44.6/39.5/35.1 ms per step against 33.5 ms un-chunked -- the passes are
+        // latency-, not DRAM-bound, so L2 residency does not pay for the extra launches.
+        int ch = 0;
+        if (const char* e = std::getenv("LESGO_CHUNK_PLANES")) ch = std::atoi(e);
+        c->chunk = (ch <= 0 || ch >= c->nz + 1) ? 0 : ch;
+    }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream create failed");
     c->own_stream = true;
     int rc = 0;
@@ -669,6 +721,7 @@ int lesgo_gpu_create(const lesgo_gpu_dims* d, lesgo_gpu_ctx** out) {
 }
 
 int lesgo_gpu_destroy(lesgo_gpu_ctx* c) {
+    ENTER(c);
     if (!c) return 0;
     cudaStreamSynchronize(c->stream);
     if (c->comm) { delete c->comm; c->comm = nullptr; }
@@ -681,6 +734,7 @@ int lesgo_gpu_destroy(lesgo_gpu_ctx* c) {
 }
 
 int lesgo_gpu_set_stream(lesgo_gpu_ctx* c, void* s) {
+    ENTER(c);
     if (!c) return 1;
     cudaStreamSynchronize(c->stream);
     if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
@@ -689,6 +743,7 @@ int lesgo_gpu_set_stream(lesgo_gpu_ctx* c, void* s) {
 }
 
 int lesgo_gpu_synchronize(lesgo_gpu_ctx* c) {
+    ENTER(c);
     if (!c) return 1;
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
@@ -698,6 +753,7 @@ int lesgo_gpu_synchronize(lesgo_gpu_ctx* c) {
 long lesgo_gpu_launch_count(const lesgo_gpu_ctx* c) { return c ? c->launches : 0; }
 
 int lesgo_gpu_profile(lesgo_gpu_ctx* c, int enable, char* report, int report_len) {
+    ENTER(c);
     // enable = 1/0 switches per-launch event timing; a non-NULL report receives
     // "label count total_ms\n" lines for everything recorded so far and clears the records.
     if (!c) return 1;
@@ -746,6 +802,7 @@ int lesgo_gpu_wavenumbers(lesgo_gpu_ctx* c, double* kx, double* ky, double* k2) 
 #define NFIELD (size_t(c->plane) * (c->nz + 1))
 
 int lesgo_gpu_filt_da(lesgo_gpu_ctx* c, double* f, double* dfdx, double* dfdy) {
+    ENTER(c);
     if (!c || !f || !dfdx || !dfdy) return 1;
     Staged st(c);
     double* df = st.in(f, NFIELD, true, true);
@@ -757,6 +814,7 @@ int lesgo_gpu_filt_da(lesgo_gpu_ctx* c, double* f, double* dfdx, double* dfdy) {
 }
 
 int lesgo_gpu_ddx(lesgo_gpu_ctx* c, const double* f, double* dfdx) {
+    ENTER(c);
     if (!c || !f || !dfdx) return 1;
     Staged st(c);
     double* df = st.in(f, NFIELD, true, false);
@@ -767,6 +825,7 @@ int lesgo_gpu_ddx(lesgo_gpu_ctx* c, const double* f, double* dfdx) {
 }
 
 int lesgo_gpu_ddy(lesgo_gpu_ctx* c, const double* f, double* dfdy) {
+    ENTER(c);
     if (!c || !f || !dfdy) return 1;
     Staged st(c);
     double* df = st.in(f, NFIELD, true, false);
@@ -777,6 +836,7 @@ int lesgo_gpu_ddy(lesgo_gpu_ctx* c, const double* f, double* dfdy) {
 }
 
 int lesgo_gpu_ddxy(lesgo_gpu_ctx* c, const double* f, double* dfdx, double* dfdy) {
+    ENTER(c);
     if (!c || !f || !dfdx || !dfdy) return 1;
     Staged st(c);
     double* df = st.in(f, NFIELD, true, false);
@@ -788,6 +848,7 @@ int lesgo_gpu_ddxy(lesgo_gpu_ctx* c, const double* f, double* dfdx, double* dfdy
 }
 
 int lesgo_gpu_ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
+    ENTER(c);
     if (!c || !f || !dfdz) return 1;
     Staged st(c);
     double* df = st.in(f, NFIELD, true, false);
@@ -798,6 +859,7 @@ int lesgo_gpu_ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
 }
 
 int lesgo_gpu_ddz_w(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
+    ENTER(c);
     if (!c || !f || !dfdz) return 1;
     Staged st(c);
     double* df = st.in(f, NFIELD, true, false);
@@ -810,6 +872,7 @@ int lesgo_gpu_ddz_w(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
 int lesgo_gpu_convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, const double* dudy,
                      const double* dudz, const double* dvdx, const double* dvdz, const double* dwdx,
                      const double* dwdy, double* RHSx, double* RHSy, double* RHSz) {
+    ENTER(c);
     if (!c) return 1;
     Staged st(c);
     const double* in[9] = {u, v, w, dudy, dudz, dvdx, dvdz, dwdx, dwdy};
@@ -830,6 +893,7 @@ int lesgo_gpu_convec(lesgo_gpu_ctx* c, const double* u, const double* v, const d
 int lesgo_gpu_press_stag_array(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w,
                                const double* divtz, double dt, double tadv1, double* p, double* dpdx,
                                double* dpdy, double* dpdz) {
+    ENTER(c);
     if (!c || !u || !v || !w || !divtz || !p || !dpdx || !dpdy || !dpdz) return 1;
     Staged st(c);
     double* du = st.in(u, NFIELD, true, false);
@@ -846,6 +910,7 @@ int lesgo_gpu_press_stag_array(lesgo_gpu_ctx* c, const double* u, const double* 
 }
 
 int lesgo_gpu_fft_r2c(lesgo_gpu_ctx* c, const double* in, double* out, int nplanes, int bigg) {
+    ENTER(c);
     if (!c || !in || !out || nplanes < 1) return 1;
     const bool b = bigg != 0;
     const long pl = b ? c->plane_big : c->plane;
@@ -865,6 +930,7 @@ int lesgo_gpu_fft_r2c(lesgo_gpu_ctx* c, const double* in, double* out, int nplan
 }
 
 int lesgo_gpu_fft_c2r(lesgo_gpu_ctx* c, const double* in, double* out, int nplanes, int bigg) {
+    ENTER(c);
     if (!c || !in || !out || nplanes < 1) return 1;
     const bool b = bigg != 0;
     const long pl = b ? c->plane_big : c->plane;
@@ -889,9 +955,11 @@ int lesgo_gpu_fft_c2r(lesgo_gpu_ctx* c, const double* in, double* out, int nplan
     return st.finish();
 }
 
-double* lesgo_gpu_field_ptr(lesgo_gpu_ctx* c, int id) { return c ? field(c, id) : nullptr; }
+double* lesgo_gpu_field_ptr(lesgo_gpu_ctx* c, int id) {
+    ENTER(c); return c ? field(c, id) : nullptr; }
 
 int lesgo_gpu_upload(lesgo_gpu_ctx* c, int id, const double* host) {
+    ENTER(c);
     if (!c || !host) return 1;
     double* f = field(c, id);
     if (!f) return c->fail("bad field id");
@@ -901,6 +969,7 @@ int lesgo_gpu_upload(lesgo_gpu_ctx* c, int id, const double* host) {
 }
 
 int lesgo_gpu_download(lesgo_gpu_ctx* c, int id, double* host) {
+    ENTER(c);
     if (!c || !host) return 1;
     double* f = field(c, id);
     if (!f) return c->fail("bad field id");
@@ -910,6 +979,7 @@ int lesgo_gpu_download(lesgo_gpu_ctx* c, int id, double* host) {
 }
 
 int lesgo_gpu_step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
+    ENTER(c);
     if (!c || !sp) return 1;
     if (step(c, sp)) return 1;
     CK(cudaGetLastError());
@@ -917,6 +987,7 @@ int lesgo_gpu_step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
 }
 
 int lesgo_gpu_max_cfl(lesgo_gpu_ctx* c, double dt, double* cfl) {
+    ENTER(c);
     // cfl_util.f90:35-69 (local part; the caller max-reduces over ranks, or comm does)
     if (!c || !cfl) return 1;
     if (!c->red_dev) { if (dev_alloc(c, &c->red_dev, 8)) return 1; }
@@ -940,6 +1011,7 @@ int lesgo_gpu_max_cfl(lesgo_gpu_ctx* c, double dt, double* cfl) {
 }
 
 int lesgo_gpu_rmsdiv(lesgo_gpu_ctx* c, double* rms) {
+    ENTER(c);
     // rmsdiv.f90:21-59 on the resident dudx, dvdy, dwdz
     if (!c || !rms) return 1;
     if (!c->red_dev) { if (dev_alloc(c, &c->red_dev, 8)) return 1; }
@@ -962,6 +1034,7 @@ int lesgo_gpu_rmsdiv(lesgo_gpu_ctx* c, double* rms) {
 int lesgo_gpu_comm_unique_id(void* id128) { return lg::Comm::unique_id(id128, &g_err); }
 
 int lesgo_gpu_comm_init(lesgo_gpu_ctx* c, const void* id128) {
+    ENTER(c);
     if (!c || !id128) return 1;
     if (c->comm) return c->fail("comm already initialised");
     std::string e;
@@ -971,6 +1044,7 @@ int lesgo_gpu_comm_init(lesgo_gpu_ctx* c, const void* id128) {
 }
 
 int lesgo_gpu_sync_real_array(lesgo_gpu_ctx* c, double* var, int isync) {
+    ENTER(c);
     if (!c || !var) return 1;
     if (c->d.nproc == 1) return 0;
     if (!c->comm) return c->fail("lesgo_gpu_comm_init has not been called");
@@ -982,6 +1056,7 @@ int lesgo_gpu_sync_real_array(lesgo_gpu_ctx* c, double* var, int isync) {
 }
 
 int lesgo_gpu_padd(lesgo_gpu_ctx* c, double* u_big, const double* u, int nplanes) {
+    ENTER(c);
     if (!c || !u_big || !u || nplanes < 1) return 1;
     Staged st(c);
     double* du = st.in(u, size_t(c->plane) * nplanes, true, false);
@@ -994,6 +1069,7 @@ int lesgo_gpu_padd(lesgo_gpu_ctx* c, double* u_big, const double* u, int nplanes
 }
 
 int lesgo_gpu_unpadd(lesgo_gpu_ctx* c, double* cc, const double* cc_big, int nplanes) {
+    ENTER(c);
     if (!c || !cc || !cc_big || nplanes < 1) return 1;
     Staged st(c);
     double* db = st.in(cc_big, size_t(c->plane_big) * nplanes, true, false);
@@ -1006,6 +1082,7 @@ int lesgo_gpu_unpadd(lesgo_gpu_ctx* c, double* cc, const double* cc_big, int npl
 }
 
 int lesgo_gpu_test_filter(lesgo_gpu_ctx* c, double* f, const double* G, int nplanes) {
+    ENTER(c);
     // test_filtermodule.f90:126-146: r2c, multiply by the real kernel G(lh, ny), c2r
     if (!c || !f || !G || nplanes < 1) return 1;
     if (nplanes > c->nz + 1) return c->fail("test_filter: at most nz+1 planes per call");
@@ -1029,6 +1106,7 @@ int lesgo_gpu_test_filter(lesgo_gpu_ctx* c, double* f, const double* G, int npla
 
 int lesgo_gpu_tridag_array(lesgo_gpu_ctx* c, const double* a, const double* b, const double* cc, const double* r,
                            double* u, int n) {
+    ENTER(c);
     if (!c || !a || !b || !cc || !r || !u || n < 2) return 1;
     Staged st(c);
     const size_t nc = size_t(c->lh) * c->ny * n, nr = size_t(c->plane) * n;

@@ -1,0 +1,24 @@
+"""Multi-GPU parity: the z-slab ranks (one lesgo_b200.Core per GPU, here as threads of one
+process, NCCL between them) must reproduce the single-slab oracle.  Needs >= 2 GPUs."""
+import pytest
+
+import lesgo_b200
+from helpers import check_multirank_steps
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_multi_gpu_steps(nproc):
+    if _ngpu() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    kw = dict(nx=64, ny=64, Nz=32, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5,
+              use_mean_p_force=True, mean_p_force_x=1.0)
+    out = check_multirank_steps(lesgo_b200.load_library(), kw, nproc, nsteps=2, tol=1e-11,
+                                device_of=lambda coord: coord)
+    print(nproc, out)

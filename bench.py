@@ -241,6 +241,31 @@ def main():
                 "definition": "296 B/point/step (SURVEY 8d A_core) * points / step time / n_gpus; whole hot path"}
     kernels = {k: {"launches": n, "ms": round(t, 4)} for k, (n, t) in sorted(kern.items(), key=lambda kv: -kv[1][1])}
 
+    # the complete step (rows (f)-1 on the device too: equilibrium wall model, Smagorinsky stress,
+    # stress divergence), timed separately; the headline stays the core step of SURVEY 8(d)
+    full = None
+    try:
+        fkw = dict(step_kw, mode=1, sgs_model=1, nu=0.0)
+        for _ in range(2):
+            core.step(**fkw)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        nfull = max(2, args.steps // 2)
+        for _ in range(nfull):
+            core.step(**fkw)
+        f1.record(stream)
+        barrier()
+        fms = f0.elapsed_time(f1) / nfull
+        if dist is not None:
+            t = torch.tensor([fms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fms = float(t.item())
+        full = {"ms_per_step": fms, "value": points / (fms * 1e-3) / 1e6, "unit": "Mpts/s",
+                "what": "core + DNS-wall wallstress + calc_Sij + Smagorinsky sgs_stag + divstress_uv/w"}
+    except Exception as e:  # noqa
+        full = {"error": str(e)}
+
     e2e = None
     if rank == 0 and not args.no_e2e and world == 1:
         e2e = run_e2e(core, dims, u, v, w, dt, tadv1, args.e2e_steps, points)
@@ -257,7 +282,7 @@ def main():
                            "grid": [nx, ny, Nz], "decomposition": f"z-slabs x{world}",
                            "l2": "inputs larger than L2 (%.0f MB per field)" % (np.prod(dims.shape) * 8 / 1e6)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-                "clocks": clocks, "kernels": kernels, "max_cfl": cfl}
+                "clocks": clocks, "kernels": kernels, "max_cfl": cfl, "full_step": full}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

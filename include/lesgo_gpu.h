@@ -112,8 +112,14 @@ typedef struct lesgo_gpu_step_params {
     double mean_p_force_x, mean_p_force_y;   /* 0 when use_mean_p_force = .false.   */
     double ubot, utop, nu_molec_nd;     /* wallstress.f90 DNS walls: nu_molec/(z_i u_star) */
     int first_step;                     /* main.f90:273-280 Euler start                */
-    int mode;                           /* 0 = core (divt* taken from the resident fields
-                                           as given), 1 = + DNS wallstress/sgs/divstress */
+    int mode;                           /* 0 = core (divt* taken from the resident fields as given);
+                                           1 = full step: + wallstress (lbc/ubc 0, 1, 2), calc_Sij,
+                                           sgs_stag with a constant coefficient, divstress_uv/w   */
+    /* mode 1 only (sgs_param.f90, sgs_stag_util.f90:87-189, wallstress.f90, test_filtermodule.f90) */
+    int sgs_model;                      /* 1 = Smagorinsky + Mason wall damping; other: Cs_opt2 = 0.03,
+                                           l = delta (the dynamic models before DYN_init)              */
+    int ifilter;                        /* test filter of the equilibrium wall model: 1 cutoff, 2 Gaussian, 3 box */
+    double Co, wall_damp_exp, vonk, zo; /* lesgo.conf MODEL / FLOW_COND                                  */
 } lesgo_gpu_step_params;
 /* One timestep main.f90:155-344 on the resident fields, no host round trip. */
 int lesgo_gpu_step(lesgo_gpu_ctx* ctx, const lesgo_gpu_step_params* sp);

@@ -246,8 +246,12 @@ class Core:
         return int(p)
 
     def step(self, dt, tadv1=1.5, tadv2=-0.5, first_step=False, mode=0, mean_p_force_x=0.0,
-             mean_p_force_y=0.0, ubot=0.0, utop=0.0, nu=0.0):
-        sp = StepParams(dt, tadv1, tadv2, mean_p_force_x, mean_p_force_y, ubot, utop, nu, int(first_step), int(mode))
+             mean_p_force_y=0.0, ubot=0.0, utop=0.0, nu=0.0, sgs_model=1, ifilter=1, Co=0.16,
+             wall_damp_exp=2.0, vonk=0.4, zo=1e-4):
+        """One timestep main.f90:155-344 on the resident fields.  mode 0: core path (divt* as
+        resident); mode 1: full step with wallstress, constant-coefficient sgs_stag and divstress."""
+        sp = StepParams(dt, tadv1, tadv2, mean_p_force_x, mean_p_force_y, ubot, utop, nu, int(first_step), int(mode),
+                        int(sgs_model), int(ifilter), Co, wall_damp_exp, vonk, zo)
         self._ck(self.lib.step(self._ctx, C.byref(sp)), "step")
 
     def max_cfl(self, dt):

@@ -335,8 +335,13 @@ template <int N> struct TileGeom {
 //   sidx(f, i)    : shared-memory slot of element i of transform f
 // Every thread of the NTHR-thread block must call this; it ends with a barrier.
 // ---------------------------------------------------------------------------------
-template <int N, int R, int Ns, bool INV, int NF, bool FFT_FASTEST, int NTHR, bool SYNC_BETWEEN, class Ld, class St>
-LG_D void tile_stage(const cplx* __restrict__ W, Ld ld, St st) {
+// Shared-memory slot of element i of transform f: (spad(i) * ES + foff(f)), with ES = 1,
+// foff = f*SL for row tiles and ES = TC, foff = f for column tiles.  When the stride between
+// the R operands of a butterfly is a multiple of 8 the padded slots are an arithmetic
+// progression, so the stage computes one base address and uses constant offsets.
+template <int N, int R, int Ns, bool INV, int NF, bool FFT_FASTEST, int NTHR, bool SRC_SMEM, bool DST_SMEM,
+          bool SYNC_BETWEEN, int ES, class FOff, class Ld, class St>
+LG_D void tile_stage(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St st) {
     constexpr int T = N / R, ITEMS = NF * T, IPT = (ITEMS + NTHR - 1) / NTHR;
     cplx v[IPT][R];
 #pragma unroll
@@ -346,7 +351,17 @@ LG_D void tile_stage(const cplx* __restrict__ W, Ld ld, St st) {
             int f, j;
             if (FFT_FASTEST) { f = it % NF; j = it / NF; }
             else             { j = it % T;  f = it / T; }
-            stage_load<N, R, Ns, INV>(j, W, [&](int i) { return ld(f, i); }, v[q]);
+            if constexpr (SRC_SMEM) {
+                if constexpr (T % 8 == 0) {
+                    const cplx* p = buf + spad(j) * ES + foff(f);
+                    stage_load<N, R, Ns, INV>(j, W, [&](int i) { return p[((i - j) + ((i - j) >> 3)) * ES]; }, v[q]);
+                } else {
+                    const int fo = foff(f);
+                    stage_load<N, R, Ns, INV>(j, W, [&](int i) { return buf[spad(i) * ES + fo]; }, v[q]);
+                }
+            } else {
+                stage_load<N, R, Ns, INV>(j, W, [&](int i) { return ld(f, i); }, v[q]);
+            }
         }
     }
     if (SYNC_BETWEEN) __syncthreads();
@@ -357,38 +372,51 @@ LG_D void tile_stage(const cplx* __restrict__ W, Ld ld, St st) {
             int f, j;
             if (FFT_FASTEST) { f = it % NF; j = it / NF; }
             else             { j = it % T;  f = it / T; }
-            stage_store<N, R, Ns>(j, [&](int i, cplx x) { st(f, i, x); }, v[q]);
+            if constexpr (DST_SMEM) {
+                const int j0 = (Ns == 1) ? j * R : ((j / Ns) * Ns * R + (j % Ns));
+                if constexpr (Ns % 8 == 0 || (Ns == 1 && (R == 8 || R == 4 || R == 2))) {
+                    // j0 + r*Ns: (j0 + r*Ns) >> 3 == (j0 >> 3) + r*Ns/8 in both cases
+                    cplx* p = buf + spad(j0) * ES + foff(f);
+                    constexpr int step = (Ns % 8 == 0) ? (Ns + Ns / 8) : 1;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) p[r * step * ES] = v[q][r];
+                } else {
+                    const int fo = foff(f);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) buf[spad(j0 + r * Ns) * ES + fo] = v[q][r];
+                }
+            } else {
+                stage_store<N, R, Ns>(j, [&](int i, cplx x) { st(f, i, x); }, v[q]);
+            }
         }
     }
 }
 
-template <int N, bool INV, int NF, bool FFT_FASTEST, int NTHR, bool LD_BUF, bool ST_BUF, class SIdx, class Ld, class St>
-LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, SIdx sidx, Ld ld, St st) {
+template <int N, bool INV, int NF, bool FFT_FASTEST, int NTHR, bool LD_BUF, bool ST_BUF, int ES, class FOff, class Ld, class St>
+LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St st) {
     typedef Plan<N> P;
     typedef PlanInfo<N> PI;
     constexpr int NST = PI::nstages;
-    auto ldB = [&](int f, int i) { return buf[sidx(f, i)]; };
-    auto stB = [&](int f, int i, cplx v) { buf[sidx(f, i)] = v; };
     if constexpr (NST == 1) {
-        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF && ST_BUF>(W, ld, st);
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, false, false, LD_BUF && ST_BUF, ES>(buf, W, foff, ld, st);
     } else if constexpr (NST == 2) {
-        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF>(W, ld, stB);
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, false, true, LD_BUF, ES>(buf, W, foff, ld, st);
         __syncthreads();
-        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W + PI::off2, ldB, st);
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true, false, ST_BUF, ES>(buf, W + PI::off2, foff, ld, st);
     } else if constexpr (NST == 3) {
-        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF>(W, ld, stB);
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, false, true, LD_BUF, ES>(buf, W, foff, ld, st);
         __syncthreads();
-        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true>(W + PI::off2, ldB, stB);
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true, true, true, ES>(buf, W + PI::off2, foff, ld, st);
         __syncthreads();
-        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W + PI::off3, ldB, st);
+        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, true, false, ST_BUF, ES>(buf, W + PI::off3, foff, ld, st);
     } else {
-        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, LD_BUF>(W, ld, stB);
+        tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, false, true, LD_BUF, ES>(buf, W, foff, ld, st);
         __syncthreads();
-        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true>(W + PI::off2, ldB, stB);
+        tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true, true, true, ES>(buf, W + PI::off2, foff, ld, st);
         __syncthreads();
-        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, true>(W + PI::off3, ldB, stB);
+        tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, true, true, true, ES>(buf, W + PI::off3, foff, ld, st);
         __syncthreads();
-        tile_stage<N, P::R4, P::R1 * P::R2 * P::R3, INV, NF, FFT_FASTEST, NTHR, ST_BUF>(W + PI::off4, ldB, st);
+        tile_stage<N, P::R4, P::R1 * P::R2 * P::R3, INV, NF, FFT_FASTEST, NTHR, true, false, ST_BUF, ES>(buf, W + PI::off4, foff, ld, st);
     }
     __syncthreads();
 }

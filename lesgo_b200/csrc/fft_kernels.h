@@ -37,7 +37,10 @@ template <int NX> struct XCfg {
     static constexpr int M = NX / 2;
     typedef TileGeom<M> G;
     // rows per tile: as many as a <= 256-thread block can take (see TileGeom)
-    static constexpr int NF0 = 256 / G::threads(1);
+#ifndef LG_XTHREADS
+#define LG_XTHREADS 256
+#endif
+    static constexpr int NF0 = LG_XTHREADS / G::threads(1);
     static constexpr int NF = NF0 < 1 ? 1 : (NF0 > 64 ? 64 : NF0);
     static constexpr int NTHR = G::round32(G::threads(NF));
     static constexpr int MINB = G::min_blocks(NTHR);
@@ -53,7 +56,7 @@ template <int NX> struct XCfg {
 // Persistent blocks: each block loops over row tiles, twiddles live in shared memory.
 template <int NX, class Pro>
 __global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
-k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int nfields, int ny, int k0, int nplanes,
+k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int nfields, int zmajor, int ny, int k0, int nplanes,
        const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
     typedef XCfg<NX> C;
     constexpr int M = C::M, NF = C::NF, SL = C::SL, NTHR = C::NTHR;
@@ -66,9 +69,14 @@ k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int n
     load_table(Wh, Whg, C::NWH);
     const long nrows = long(ny) * nplanes;
     const long ntiles = (nrows + NF - 1) / NF;
-    // work item = (row tile, field), field fastest: blocks resident together work on the same
-    // rows of different fields, so inputs they share (the u x omega products) are read once
-    for (long work = blockIdx.x; work < ntiles * nfields; work += gridDim.x) {
+    // Work items are dealt round-robin with the field index fastest: blocks resident together
+    // work on neighbouring rows of all fields, so inputs the fields share (the u x omega
+    // products) are read from DRAM once and concurrent blocks touch adjacent DRAM pages.
+    // (Measured alternative, profiles/r1_work_order.md: a contiguous range per block, optionally
+    // walking up z, was 25 % slower.)
+    (void)zmajor;
+    const long nwork = ntiles * nfields;
+    for (long work = blockIdx.x; work < nwork; work += gridDim.x) {
         const int fld = int(work % nfields);
         const long row0 = (work / nfields) * NF;
         for (int f = threadIdx.x; f < NF; f += NTHR) {
@@ -77,8 +85,8 @@ k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int n
             s_y[f] = int(r % ny);
         }
         __syncthreads();
-        fft_tile<M, false, NF, false, NTHR, false, true>(buf, W,
-            [](int f, int i) { return f * SL + spad(i); },
+        fft_tile<M, false, NF, false, NTHR, false, true, 1>(buf, W,
+            [](int f) { return f * SL; },
             [&](int f, int i) {
                 const int k = s_k[f];
                 if (k < 0) return make_double2(0.0, 0.0);
@@ -144,7 +152,7 @@ struct XiSrc {
 //      receiving (x[2j], x[2j+1]);   LG_D void finish_row(int fld, int k, int y) const
 template <int NX, class Epi>
 __global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
-k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nfields, int ny, int k0, int nplanes,
+k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nfields, int zmajor, int ny, int k0, int nplanes,
        const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
     typedef XCfg<NX> C;
     constexpr int M = C::M, NF = C::NF, SL = C::SL, NTHR = C::NTHR;
@@ -157,9 +165,14 @@ k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nf
     load_table(Wh, Whg, C::NWH);
     const long nrows = long(ny) * nplanes;
     const long ntiles = (nrows + NF - 1) / NF;
-    // work item = (row tile, field), field fastest: blocks resident together work on the same
-    // rows of different fields, so inputs they share (the u x omega products) are read once
-    for (long work = blockIdx.x; work < ntiles * nfields; work += gridDim.x) {
+    // Work items are dealt round-robin with the field index fastest: blocks resident together
+    // work on neighbouring rows of all fields, so inputs the fields share (the u x omega
+    // products) are read from DRAM once and concurrent blocks touch adjacent DRAM pages.
+    // (Measured alternative, profiles/r1_work_order.md: a contiguous range per block, optionally
+    // walking up z, was 25 % slower.)
+    (void)zmajor;
+    const long nwork = ntiles * nfields;
+    for (long work = blockIdx.x; work < nwork; work += gridDim.x) {
         const int fld = int(work % nfields);
         const long row0 = (work / nfields) * NF;
         for (int f = threadIdx.x; f < NF; f += NTHR) {
@@ -219,8 +232,8 @@ k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nf
         }
         __syncthreads();
 
-        fft_tile<M, true, NF, false, NTHR, true, false>(buf, W,
-            [](int f, int i) { return f * SL + spad(i); },
+        fft_tile<M, true, NF, false, NTHR, true, false, 1>(buf, W,
+            [](int f) { return f * SL; },
             [&](int f, int i) { return buf[f * SL + spad(i)]; },
             [&](int f, int i, cplx v) {
                 if (s_k[f] < 0) return;
@@ -297,9 +310,11 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
     if (NOUT > 0) load_table(Wout, Woutg, C::TWO);
     __syncthreads();
     auto sidx = [](int f, int i) { return spad(i) * TC + f; };
+    auto foff = [](int f) { return f; };
     const int ntc = (a.ncols + TC - 1) / TC;
     const long ntiles = long(ntc) * a.nplanes;
-    for (long work = blockIdx.x; work < ntiles * a.nfields; work += gridDim.x) {
+    const long nwork = ntiles * a.nfields;
+    for (long work = blockIdx.x; work < nwork; work += gridDim.x) {   // round-robin: see k_xfwd
         const YField& F = a.fld[work % a.nfields];
         const long tile = work / a.nfields;
         const int c0 = int(tile % ntc) * TC;
@@ -310,7 +325,7 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
             if constexpr (NOUT == 0) {
                 // forward only: straight to global with Nyquist-row zeroing
                 double* dst = F.out[0].dst + long(k) * a.dst_plane + 2 * c0;
-                fft_tile<NIN, false, TC, true, NTHR, false, false>(buf, Win, sidx,
+                fft_tile<NIN, false, TC, true, NTHR, false, false, TC>(buf, Win, foff,
                     [&](int f, int i) {
                         if (c0 + f >= a.ncols) return make_double2(0.0, 0.0);
                         return *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
@@ -321,7 +336,7 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
                         *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * f) = v;
                     });
             } else {
-                fft_tile<NIN, false, TC, true, NTHR, false, !MULTI>(buf, Win, sidx,
+                fft_tile<NIN, false, TC, true, NTHR, false, !MULTI, TC>(buf, Win, foff,
                     [&](int f, int i) {
                         if (c0 + f >= a.ncols) return make_double2(0.0, 0.0);
                         return *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
@@ -348,10 +363,19 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
         }
 
         if constexpr (NOUT > 0) {
+            // i*kx does not depend on y, so the y-inverse of (i kx S) is i kx times the y-inverse
+            // of S: an IKX output is derived from the COPY transform instead of costing its own.
+            int o_copy = -1, o_ikx = -1;
+            for (int o = 0; o < a.nout; ++o) {
+                if (F.out[o].mode == Y_COPY) o_copy = o;
+                if (F.out[o].mode == Y_IKX) o_ikx = o;
+            }
             for (int o = 0; o < a.nout; ++o) {
                 const int mode = F.out[o].mode;
+                if (mode == Y_IKX && o_copy >= 0) continue;          // written by the COPY transform
                 double* dst = F.out[o].dst + long(k) * a.dst_plane + 2 * c0;
-                fft_tile<NOUT, true, TC, true, NTHR, !MULTI, false>(buf, Wout, sidx,
+                double* dst_x = (mode == Y_COPY && o_ikx >= 0) ? F.out[o_ikx].dst + long(k) * a.dst_plane + 2 * c0 : nullptr;
+                fft_tile<NOUT, true, TC, true, NTHR, !MULTI, false, TC>(buf, Wout, foff,
                     [&](int f, int i) {
                         // row i of the (possibly padded) output spectrum <- small row is
                         int is = i;
@@ -362,11 +386,7 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
                         }
                         if (is == NS / 2 && !a.keep_nyq_row) return make_double2(0.0, 0.0);
                         cplx v = S[sidx(f, is)];
-                        if (mode == Y_COPY) return v;
-                        if (mode == Y_IKX) {
-                            double kx = a.kxs * double(c0 + f);
-                            return make_double2(-v.y * kx, v.x * kx);
-                        }
+                        if (mode == Y_COPY || mode == Y_IKX) return v;
                         if (mode == Y_IKY) {
                             double ky = a.kys * double(is < NS / 2 ? is : is - NS);
                             return make_double2(-v.y * ky, v.x * ky);
@@ -376,7 +396,10 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
                     },
                     [&](int f, int i, cplx v) {
                         if (c0 + f >= a.ncols) return;
+                        const double kx = a.kxs * double(c0 + f);
+                        if (mode == Y_IKX) v = make_double2(-v.y * kx, v.x * kx);
                         *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * f) = v;
+                        if (dst_x) *reinterpret_cast<cplx*>(dst_x + long(i) * a.dst_row + 2 * f) = make_double2(-v.y * kx, v.x * kx);
                     });
             }
         }

@@ -43,6 +43,11 @@ struct lesgo_gpu_ctx {
     double* bb[kMaxFields] = {nullptr};    // big-y intermediates, (ld, ny2, 0:nz)
     double* big[kMaxFields] = {nullptr};   // 3/2-grid physical fields, (ld_big, ny2, 0:nz)
     double* gam = nullptr;                 // tridiagonal gam(j) table (lh, ny, 0:nzt+1)
+    double* work[13] = {nullptr};          // S11..S33, Nu_t, six stress-gradient temporaries (mode 1)
+    double* lsq = nullptr;                 // l(k)**2 of the Smagorinsky length (nz+1)
+    double* gtest = nullptr;               // test-filter kernel G_test (lh, ny)
+    double* wplane[2] = {nullptr};         // filtered wall-adjacent u, v planes
+    int sgs_cfg = -1;                      // (sgs_model, ifilter) the tables above were built for
     double* fields[LG_NFIELDS] = {nullptr};
     std::vector<double*> staging;          // device staging for host-pointer arguments
     std::vector<size_t> staging_bytes;
@@ -578,6 +583,185 @@ double* field(lesgo_gpu_ctx* c, int id) {
     return c->fields[id];
 }
 
+// ---- wallstress + sgs_stag (constant coefficient) + divstress on the device ---------
+int build_sgs_tables(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
+    const int cfg = sp->sgs_model * 16 + sp->ifilter;
+    if (c->sgs_cfg == cfg && c->lsq) return 0;
+    const int nz = c->nz;
+    const double dx = c->d.L_x / c->nx, dy = c->d.L_y / c->ny, dz = c->d.dz;
+    const double delta = std::pow(dx * dy * dz, 1.0 / 3.0);                  // sgs_param.f90:187
+    // l(k), sgs_stag_util.f90:87-179 (sgs_model 1) / :183 (l = delta otherwise)
+    std::vector<double> l(nz + 1, delta);
+    const int lb = c->d.lbc_mom, ub = c->d.ubc_mom;
+    if (sp->sgs_model == 1 && !(lb == 0 && ub == 0)) {
+        const double Co = sp->Co, n = sp->wall_damp_exp, vonk = sp->vonk;
+        auto damp = [&](double zz) { return std::pow(std::pow(Co, n) * std::pow(vonk * zz, -n) + std::pow(delta, -n), -1.0 / n); };
+        int jmin = 1, jmax = nz;
+        if (lb > 0 && c->bottom) { l[1] = damp(0.5 * dz); jmin = 2; }
+        if (ub > 0 && c->top) { l[nz] = damp(0.5 * dz); jmax = nz - 1; }
+        for (int jz = jmin; jz <= jmax; ++jz) {
+            double zz;
+            if (lb > 0 && ub == 0) zz = ((jz - 1) + c->d.coord * (nz - 1)) * dz;
+            else if (lb > 0 && ub > 0) { zz = ((jz - 1) + c->d.coord * (nz - 1)) * dz; zz = std::fmin(zz, (nz - 1) * c->d.nproc * dz - zz); }
+            else zz = ((c->d.nproc - c->d.coord) * (nz - 1) - (jz - 1)) * dz;
+            l[jz] = damp(zz);
+        }
+    }
+    for (auto& v : l) v = v * v;
+    if (!c->lsq && dev_alloc(c, &c->lsq, nz + 1)) return 1;
+    CK(cudaMemcpyAsync(c->lsq, l.data(), sizeof(double) * (nz + 1), cudaMemcpyHostToDevice, c->stream));
+    // G_test, test_filtermodule.f90:38-80 (alpha_test = 2)
+    std::vector<double> G(size_t(c->lh) * c->ny);
+    const double pi = 3.14159265358979323846;
+    const double dt_ = 2.0 * std::sqrt(dx * dy), kc2 = (pi / dt_) * (pi / dt_);
+    for (int jy = 0; jy < c->ny; ++jy)
+        for (int jx = 0; jx < c->lh; ++jx) {
+            double kx = c->kxs * jx, ky = c->kys * double(jy < c->ny / 2 ? jy : jy - c->ny);
+            if (jx == c->lh - 1 || jy == c->ny / 2) { kx = 0.0; ky = 0.0; }
+            const double k2 = kx * kx + ky * ky;
+            double g = 1.0 / (double(c->nx) * double(c->ny));
+            if (sp->ifilter == 1) { if (k2 >= kc2) g = 0.0; }
+            else if (sp->ifilter == 2) g = std::exp(-(dt_ * dt_) * k2 / (4.0 * 6.0)) * g;
+            else if (sp->ifilter == 3) g = (std::sin(kx * dt_ / 2.0) * std::sin(ky * dt_ / 2.0) + 1e-8) / (kx * dt_ / 2.0 * ky * dt_ / 2.0 + 1e-8) * g;
+            if (jx == c->lh - 1 || jy == c->ny / 2) g = 0.0;
+            G[size_t(jy) * c->lh + jx] = g;
+        }
+    if (!c->gtest && dev_alloc(c, &c->gtest, G.size())) return 1;
+    CK(cudaMemcpyAsync(c->gtest, G.data(), sizeof(double) * G.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->sgs_cfg = cfg;
+    return 0;
+}
+
+// test_filter of ONE plane (test_filtermodule.f90:126-146): src plane -> dst plane
+int filter_plane(lesgo_gpu_ctx* c, const double* src, double* dst) {
+    if (need_small(c, 2)) return 1;
+    ProScale ps; ps.src[0] = src; ps.lay = c->lay(); ps.scale = 1.0;
+    double* d0[1] = {c->sa[0]};
+    if (xfwd(c, false, ps, 1, d0, c->plane, c->ld, c->nx / 2, c->ny, 0, 1)) return 1;
+    YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, c->nx / 2, 0);
+    a.fld[0].src = c->sa[0]; a.fld[0].out[0] = YOutSpec{c->sa[1], Y_TABLE};
+    a.table = c->gtest; a.table_row = c->lh;
+    if (ypass(c, c->ny, c->ny, a, 1, 0, 1)) return 1;
+    const double* s0[1] = {c->sa[1]};
+    double* o0[1] = {dst};
+    return xinv(c, false, s0, c->plane, c->ld, c->nx / 2, 1, o0, c->lay(), c->ny, 0, 1);
+}
+
+int wallstress(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* const* F, bool with_tau) {
+    // wallstress.f90:47-255; with_tau = false (core mode) only sets dudz, dvdz on the wall planes
+    const int nz = c->nz;
+    const double h = 0.5 * c->d.dz;
+    const int g1 = grid1d(long(c->nx) * c->ny);
+    for (int side = 0; side < 2; ++side) {
+        const bool bot = side == 0;
+        if (bot ? !c->bottom : !c->top) continue;
+        const int bc = bot ? c->d.lbc_mom : c->d.ubc_mom;
+        const int ksrc = bot ? 1 : nz - 1, kdst = bot ? 1 : nz;
+        if (bc == 0) {
+            fill(c, F[LG_DUDZ], c->plane, kdst, kdst + 1, 0.0); fill(c, F[LG_DVDZ], c->plane, kdst, kdst + 1, 0.0);
+            if (with_tau) { fill(c, F[LG_TXZ], c->plane, kdst, kdst + 1, 0.0); fill(c, F[LG_TYZ], c->plane, kdst, kdst + 1, 0.0); }
+        } else if (bc == 1) {
+            ProfScope ps_(c, "wall");
+            LG_LAUNCH(k_wall_dns, dim3(grid1d(long(c->nx / 2) * c->ny)), dim3(kBlock), 0, c->stream, F[LG_U], F[LG_V],
+                      F[LG_DUDZ], F[LG_DVDZ], c->lay(), c->nx, c->ny, ksrc, kdst, bot ? sp->ubot : sp->utop, bot ? 1.0 : -1.0, h);
+            c->launches++;
+            if (with_tau) {
+                LG_LAUNCH(k_wall_tau_dns, dim3(g1), dim3(kBlock), 0, c->stream, F[LG_DUDZ], F[LG_DVDZ], F[LG_TXZ], F[LG_TYZ],
+                          c->lay(), c->nx, c->ny, kdst, sp->nu_molec_nd);
+                c->launches++;
+            }
+        } else if (bc == 2) {
+            if (!with_tau) return c->fail("lesgo_gpu_step: equilibrium wall model needs mode 1");
+            for (int i = 0; i < 2; ++i)
+                if (dev_alloc(c, &c->wplane[i], size_t(c->plane))) return 1;
+            if (filter_plane(c, F[LG_U] + c->plane * ksrc, c->wplane[0])) return 1;
+            if (filter_plane(c, F[LG_V] + c->plane * ksrc, c->wplane[1])) return 1;
+            ProfScope ps_(c, "wall");
+            LG_LAUNCH(k_wall_equil, dim3(g1), dim3(kBlock), 0, c->stream, F[LG_U], F[LG_V], c->wplane[0], c->wplane[1],
+                      F[LG_DUDZ], F[LG_DVDZ], F[LG_TXZ], F[LG_TYZ], c->lay(), c->nx, c->ny, ksrc, kdst, bot ? 1.0 : -1.0,
+                      sp->vonk, std::log(h / sp->zo), h * sp->vonk);
+            c->launches++;
+        } else {
+            return c->fail("lesgo_gpu_step: lbc_mom/ubc_mom = 3 (integral wall model) is out of scope");
+        }
+    }
+    return 0;
+}
+
+int plane_exchange(lesgo_gpu_ctx* c, const double* send, int dest, double* recv, int src) {
+    if (!c->comm) return 0;
+    const double* sb[1] = {send};
+    double* rb[1] = {recv};
+    int d[1] = {dest}, s[1] = {src};
+    size_t cnt[1] = {size_t(c->plane)};
+    ProfScope ps_(c, "halo");
+    if (c->comm->exchange(1, sb, d, rb, s, cnt, c->stream)) return c->fail(c->comm->error());
+    return 0;
+}
+
+int sum3(lesgo_gpu_ctx* c, double* out, const double* a, const double* b, const double* cc, int k0, int k1, int zero_pad) {
+    if (k1 <= k0) return 0;
+    ProfScope ps_(c, "glue");
+    LG_LAUNCH(k_sum3, dim3(grid1d(long(c->lh) * c->ny * (k1 - k0))), dim3(kBlock), 0, c->stream, out, a, b, cc, c->lay(),
+              c->nx, c->ny, k0, k1, zero_pad);
+    c->launches++;
+    return 0;
+}
+
+int sgs_and_divstress(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* const* F) {
+    const int nz = c->nz, coord = c->d.coord;
+    for (int i = 0; i < 13; ++i)
+        if (dev_alloc(c, &c->work[i], size_t(c->plane) * (nz + 1))) return 1;
+    if (build_sgs_tables(c, sp)) return 1;
+    SgsParams p;
+    p.nz = nz; p.bottom = c->bottom; p.top = c->top; p.lbc_mom = c->d.lbc_mom; p.ubc_mom = c->d.ubc_mom;
+    p.sgs = c->d.sgs; p.nu = sp->nu_molec_nd; p.Cs_opt2 = sp->sgs_model == 1 ? sp->Co * sp->Co : 0.03;
+    // calc_Sij needs dwdz(nz) = dwdz(1) of the rank above (sgs_stag_util.f90:611-614)
+    if (plane_exchange(c, F[LG_DWDZ] + c->plane, coord - 1, F[LG_DWDZ] + c->plane * nz, coord + 1)) return 1;
+    SijArgs sa;
+    sa.dudx = F[LG_DUDX]; sa.dudy = F[LG_DUDY]; sa.dudz = F[LG_DUDZ]; sa.dvdx = F[LG_DVDX]; sa.dvdy = F[LG_DVDY];
+    sa.dvdz = F[LG_DVDZ]; sa.dwdx = F[LG_DWDX]; sa.dwdy = F[LG_DWDY]; sa.dwdz = F[LG_DWDZ];
+    for (int i = 0; i < 6; ++i) sa.S[i] = c->work[i];
+    sa.Nu_t = c->work[6]; sa.lsq = c->lsq;
+    {
+        ProfScope ps_(c, "sgs");
+        LG_LAUNCH(k_sij_nut, dim3(grid1d(long(c->nx) * c->ny * nz)), dim3(kBlock), 0, c->stream, sa, p, c->lay(), c->nx, c->ny, 1, nz + 1);
+        c->launches++;
+    }
+    TauArgs ta;
+    for (int i = 0; i < 6; ++i) ta.S[i] = c->work[i];
+    ta.Nu_t = c->work[6];
+    ta.T[0] = F[LG_TXX]; ta.T[1] = F[LG_TXY]; ta.T[2] = F[LG_TXZ]; ta.T[3] = F[LG_TYY]; ta.T[4] = F[LG_TYZ]; ta.T[5] = F[LG_TZZ];
+    {
+        ProfScope ps_(c, "sgs");
+        // plane 1 on the bottom rank keeps the wall-model txz, tyz: k_tau does not write them there
+        LG_LAUNCH(k_tau, dim3(grid1d(long(c->nx) * c->ny * (nz - 1))), dim3(kBlock), 0, c->stream, ta, p, c->lay(), c->nx, c->ny, 1, nz);
+        c->launches++;
+    }
+    // txz, tyz: plane 1 of coord+1 -> plane nz of coord (sgs_stag_util.f90:437-444); tzz(nz-1) -> tzz(0) above (main.f90:194)
+    if (plane_exchange(c, F[LG_TXZ] + c->plane, coord - 1, F[LG_TXZ] + c->plane * nz, coord + 1)) return 1;
+    if (plane_exchange(c, F[LG_TYZ] + c->plane, coord - 1, F[LG_TYZ] + c->plane * nz, coord + 1)) return 1;
+    if (plane_exchange(c, F[LG_TZZ] + c->plane * (nz - 1), coord + 1, F[LG_TZZ], coord - 1)) return 1;
+    double** d = c->work + 7;
+    // divstress_uv.f90:21-86
+    if (spectral_deriv(c, F[LG_TXX], nullptr, d[0], nullptr)) return 1;          // dtxdx
+    ddz_w(c, F[LG_TXZ], d[1]);                                                    // dtzdz
+    if (spectral_deriv(c, F[LG_TYY], nullptr, nullptr, d[2])) return 1;          // dtydy2
+    ddz_w(c, F[LG_TYZ], d[3]);                                                    // dtzdz2
+    if (spectral_deriv(c, F[LG_TXY], nullptr, d[4], d[5])) return 1;             // dtxdx2, dtydy
+    sum3(c, F[LG_DIVTX], d[0], d[5], d[1], 1, nz, 1);
+    sum3(c, F[LG_DIVTY], d[4], d[2], d[3], 1, nz, 1);
+    // divstress_w.f90:21-116
+    if (spectral_deriv(c, F[LG_TXZ], nullptr, d[0], nullptr)) return 1;
+    if (spectral_deriv(c, F[LG_TYZ], nullptr, nullptr, d[1])) return 1;
+    ddz_uv(c, F[LG_TZZ], d[2]);
+    sum3(c, F[LG_DIVTZ], d[0], d[1], c->bottom ? nullptr : d[2], 1, 2, 1);
+    sum3(c, F[LG_DIVTZ], d[0], d[1], d[2], 2, nz, 1);
+    sum3(c, F[LG_DIVTZ], d[0], d[1], c->top ? nullptr : d[2], nz, nz + 1, 0);
+    return 0;
+}
+
 // ---- one timestep on the resident fields: main.f90:155-344 ----------------------------------------
 int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     const int nz = c->nz;
@@ -586,7 +770,7 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
         F[i] = field(c, i);
         if (!F[i]) return 1;
     }
-    if (sp->mode != 0) return c->fail("lesgo_gpu_step: mode 1 (wallstress/sgs/divstress on device) not built yet");
+    if (sp->mode != 0 && sp->mode != 1) return c->fail("lesgo_gpu_step: mode must be 0 (core) or 1 (full)");
     const size_t fb = size_t(c->plane) * (nz + 1) * sizeof(double);
     // :155-157  RHS*_f = RHS*: the two sets trade places instead of being copied (convec
     // rewrites every valid plane of RHS* below, main.f90:207-214)
@@ -600,26 +784,10 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     ddz_uv(c, F[LG_U], F[LG_DUDZ]);
     ddz_uv(c, F[LG_V], F[LG_DVDZ]);
     ddz_w(c, F[LG_W], F[LG_DWDZ]);
-    // wallstress (:182-184), DNS / stress-free walls: dudz, dvdz on the wall planes
-    {
-        const double h = 0.5 * c->d.dz;
-        if (c->bottom) {
-            if (c->d.lbc_mom == 0) { fill(c, F[LG_DUDZ], c->plane, 1, 2, 0.0); fill(c, F[LG_DVDZ], c->plane, 1, 2, 0.0); }
-            else if (c->d.lbc_mom == 1) {
-                LG_LAUNCH(k_wall_dns, dim3(grid1d(long(c->nx / 2) * c->ny)), dim3(kBlock), 0, c->stream, F[LG_U], F[LG_V],
-                          F[LG_DUDZ], F[LG_DVDZ], c->lay(), c->nx, c->ny, 1, 1, sp->ubot, 1.0, h);
-                c->launches++;
-            } else return c->fail("lesgo_gpu_step: lbc_mom > 1 (wall models) not on device yet");
-        }
-        if (c->top) {
-            if (c->d.ubc_mom == 0) { fill(c, F[LG_DUDZ], c->plane, nz, nz + 1, 0.0); fill(c, F[LG_DVDZ], c->plane, nz, nz + 1, 0.0); }
-            else if (c->d.ubc_mom == 1) {
-                LG_LAUNCH(k_wall_dns, dim3(grid1d(long(c->nx / 2) * c->ny)), dim3(kBlock), 0, c->stream, F[LG_U], F[LG_V],
-                          F[LG_DUDZ], F[LG_DVDZ], c->lay(), c->nx, c->ny, nz - 1, nz, sp->utop, -1.0, h);
-                c->launches++;
-            } else return c->fail("lesgo_gpu_step: ubc_mom > 1 (wall models) not on device yet");
-        }
-    }
+    // wallstress (:182-184); sgs_stag, tzz halo, divstress_uv/w (:189-203) in the full mode
+    if (sp->mode == 1 && build_sgs_tables(c, sp)) return 1;
+    if (wallstress(c, sp, F, sp->mode == 1)) return 1;
+    if (sp->mode == 1 && sgs_and_divstress(c, sp, F)) return 1;
     // :207
     if (convec(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DUDY], F[LG_DUDZ], F[LG_DVDX], F[LG_DVDZ], F[LG_DWDX],
                F[LG_DWDY], F[LG_RHSX], F[LG_RHSY], F[LG_RHSZ])) return 1;

@@ -660,4 +660,189 @@ static __global__ void k_glue_fused(int mode, double* __restrict__ rhs, const do
     }
 }
 
+// ---- wall stress, strain rate, constant-coefficient SGS stress, stress divergence ---
+struct SgsParams {
+    int nz, bottom, top, lbc_mom, ubc_mom, sgs;
+    double nu;          // nu_molec/(u_star z_i) when molec, else 0   (sgs_param.f90:188-192)
+    double Cs_opt2;     // Co**2 (sgs_model 1) or 0.03 (dynamic models before DYN_init)
+};
+
+// calc_Sij (sgs_stag_util.f90:467-634) + |S| and Nu_t (:226-235) on planes k0..k1-1 (1 <= k <= nz).
+// S[6] = S11, S12, S13, S22, S23, S33; lsq[k] = l(k)**2.
+struct SijArgs {
+    const double *dudx, *dudy, *dudz, *dvdx, *dvdy, *dvdz, *dwdx, *dwdy, *dwdz;
+    double* S[6];
+    double* Nu_t;
+    const double* lsq;
+};
+static __global__ void k_sij_nut(SijArgs a, SgsParams p, Lay lay, int nx, int ny, int k0, int k1) {
+    const long n = long(nx) * ny * (k1 - k0);
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        const int i = int(t % nx);
+        long r = t / nx;
+        const int y = int(r % ny), k = k0 + int(r / ny);
+        const long o = lay.at(k, y, i), om = lay.at(k - 1, y, i);
+        double s11, s12, s13, s22, s23, s33;
+        if (p.bottom && k == 1) {
+            if (p.lbc_mom == 0) {
+                s11 = a.dudx[o]; s12 = dmul(0.5, dadd(a.dudy[o], a.dvdx[o])); s13 = dmul(0.5, dadd(a.dudz[o], a.dwdx[o]));
+                s22 = a.dvdy[o]; s23 = dmul(0.5, dadd(a.dvdz[o], a.dwdy[o])); s33 = dmul(0.5, dadd(a.dwdz[o], 0.0));
+            } else {
+                const long o2 = lay.at(2, y, i);
+                s11 = a.dudx[o]; s12 = dmul(0.5, dadd(a.dudy[o], a.dvdx[o]));
+                const double wx = dmul(0.5, dadd(a.dwdx[o], a.dwdx[o2]));
+                s13 = dmul(0.5, dadd(a.dudz[o], wx));
+                s22 = a.dvdy[o];
+                const double wy = dmul(0.5, dadd(a.dwdy[o], a.dwdy[o2]));
+                s23 = dmul(0.5, dadd(a.dvdz[o], wy));
+                s33 = a.dwdz[o];
+            }
+        } else if (p.top && k == p.nz) {
+            if (p.ubc_mom == 0) {
+                s11 = a.dudx[om]; s12 = dmul(0.5, dadd(a.dudy[om], a.dvdx[om])); s13 = dmul(0.5, dadd(a.dudz[o], a.dwdx[o]));
+                s22 = a.dvdy[om]; s23 = dmul(0.5, dadd(a.dvdz[o], a.dwdy[o])); s33 = dmul(0.5, dadd(a.dwdz[om], 0.0));
+            } else {
+                s11 = a.dudx[om]; s12 = dmul(0.5, dadd(a.dudy[om], a.dvdx[om]));
+                const double wx = dmul(0.5, dadd(a.dwdx[om], a.dwdx[o]));
+                s13 = dmul(0.5, dadd(a.dudz[o], wx));
+                s22 = a.dvdy[om];
+                const double wy = dmul(0.5, dadd(a.dwdy[om], a.dwdy[o]));
+                s23 = dmul(0.5, dadd(a.dvdz[o], wy));
+                s33 = a.dwdz[om];
+            }
+        } else {
+            s11 = dmul(0.5, dadd(a.dudx[o], a.dudx[om]));
+            const double uy = dadd(a.dudy[o], a.dudy[om]), vx = dadd(a.dvdx[o], a.dvdx[om]);
+            s12 = dmul(0.25, dadd(uy, vx));
+            s13 = dmul(0.5, dadd(a.dudz[o], a.dwdx[o]));
+            s22 = dmul(0.5, dadd(a.dvdy[o], a.dvdy[om]));
+            s23 = dmul(0.5, dadd(a.dvdz[o], a.dwdy[o]));
+            s33 = dmul(0.5, dadd(a.dwdz[o], a.dwdz[om]));
+        }
+        a.S[0][o] = s11; a.S[1][o] = s12; a.S[2][o] = s13; a.S[3][o] = s22; a.S[4][o] = s23; a.S[5][o] = s33;
+        double nut = 0.0;
+        if (p.sgs) {
+            const double q = dadd(dadd(dadd(dmul(s11, s11), dmul(s22, s22)), dmul(s33, s33)),
+                                  dmul(2.0, dadd(dadd(dmul(s12, s12), dmul(s13, s13)), dmul(s23, s23))));
+            nut = dmul(dmul(sqrt(dmul(2.0, q)), p.Cs_opt2), a.lsq[k]);
+        }
+        a.Nu_t[o] = nut;
+    }
+}
+
+// tau_ij (sgs_stag_util.f90:237-428) on planes k0..k1-1 (1 <= k <= nz-1); T[6] = txx, txy, txz, tyy, tyz, tzz
+struct TauArgs {
+    const double* S[6];
+    const double* Nu_t;
+    double* T[6];
+};
+static __global__ void k_tau(TauArgs a, SgsParams p, Lay lay, int nx, int ny, int k0, int k1) {
+    const long n = long(nx) * ny * (k1 - k0);
+    // S index of the four "uvp-node" stresses txx, txy, tyy, tzz and their T index
+    const int sI[4] = {0, 1, 3, 5}, tI[4] = {0, 1, 3, 5};
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        const int i = int(t % nx);
+        long r = t / nx;
+        const int y = int(r % ny), k = k0 + int(r / ny);
+        const long o = lay.at(k, y, i), op = lay.at(k + 1, y, i);
+        const double nu = p.nu;
+        if (p.bottom && k == 1) {
+            // txz, tyz of plane 1 come from wallstress
+            if (p.lbc_mom == 0) {
+                const double cst = p.sgs ? dadd(dmul(0.5, dadd(a.Nu_t[o], a.Nu_t[op])), nu) : nu;
+                for (int q = 0; q < 4; ++q) a.T[tI[q]][o] = dmul(-cst, dadd(a.S[sI[q]][o], a.S[sI[q]][op]));
+            } else {
+                const double cst = p.sgs ? dmul(-2.0, dadd(a.Nu_t[o], nu)) : dmul(-2.0, nu);
+                for (int q = 0; q < 4; ++q) a.T[tI[q]][o] = dmul(cst, a.S[sI[q]][o]);
+            }
+        } else if (p.top && k == p.nz - 1) {
+            if (p.ubc_mom == 0) {
+                const double cst = p.sgs ? dadd(dmul(0.5, dadd(a.Nu_t[o], a.Nu_t[op])), nu) : nu;
+                const double cst2 = p.sgs ? dmul(2.0, dadd(a.Nu_t[o], nu)) : dmul(2.0, nu);
+                for (int q = 0; q < 4; ++q) a.T[tI[q]][o] = dmul(-cst, dadd(a.S[sI[q]][o], a.S[sI[q]][op]));
+                a.T[2][o] = dmul(-cst2, a.S[2][o]);
+                a.T[4][o] = dmul(-cst2, a.S[4][o]);
+            } else if (p.sgs) {
+                const double cst = dmul(-2.0, dadd(a.Nu_t[op], nu)), cst2 = dmul(-2.0, dadd(a.Nu_t[o], nu));
+                for (int q = 0; q < 4; ++q) a.T[tI[q]][o] = dmul(cst, a.S[sI[q]][op]);
+                a.T[2][o] = dmul(cst2, a.S[2][o]);
+                a.T[4][o] = dmul(cst2, a.S[4][o]);
+            } else {
+                // the reference's DNS branch uses Sij(nz-1) here (:353-356)
+                for (int q = 0; q < 4; ++q) a.T[tI[q]][o] = dmul(dmul(-2.0, nu), a.S[sI[q]][o]);
+                a.T[2][o] = dmul(dmul(-2.0, nu), a.S[2][o]);
+                a.T[4][o] = dmul(dmul(-2.0, nu), a.S[4][o]);
+            }
+        } else if (p.sgs) {
+            const double c3 = dmul(dmul(-2.0, nu), 0.5), c4 = dmul(-2.0, nu);
+            const double cst = dmul(-0.5, dadd(a.Nu_t[o], a.Nu_t[op])), cst2 = dmul(-2.0, a.Nu_t[o]);
+            for (int q = 0; q < 4; ++q) a.T[tI[q]][o] = dmul(dadd(cst, c3), dadd(a.S[sI[q]][o], a.S[sI[q]][op]));
+            a.T[2][o] = dmul(dadd(cst2, c4), a.S[2][o]);
+            a.T[4][o] = dmul(dadd(cst2, c4), a.S[4][o]);
+        } else {
+            for (int q = 0; q < 4; ++q) a.T[tI[q]][o] = dmul(-nu, dadd(a.S[sI[q]][o], a.S[sI[q]][op]));
+            a.T[2][o] = dmul(dmul(-2.0, nu), a.S[2][o]);
+            a.T[4][o] = dmul(dmul(-2.0, nu), a.S[4][o]);
+        }
+    }
+}
+
+// wallstress.f90:131-168 stresses of the DNS walls: t = -nu * d(u|v)/dz on plane k (1:nx)
+static __global__ void k_wall_tau_dns(const double* __restrict__ dudz, const double* __restrict__ dvdz,
+                                      double* __restrict__ txz, double* __restrict__ tyz, Lay lay, int nx, int ny,
+                                      int k, double nu) {
+    const long n = long(nx) * ny;
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        const long o = lay.at(k, int(t / nx), int(t % nx));
+        txz[o] = dmul(-nu, dudz[o]);
+        tyz[o] = dmul(-nu, dvdz[o]);
+    }
+}
+
+// equilibrium wall model, wallstress.f90:171-255.  u1, v1: test-filtered u, v of the wall-adjacent
+// plane (one plane each); sign = +1 bottom (ksrc = 1, kdst = 1), -1 top (ksrc = nz-1, kdst = nz).
+static __global__ void k_wall_equil(const double* __restrict__ u, const double* __restrict__ v,
+                                    const double* __restrict__ u1, const double* __restrict__ v1,
+                                    double* __restrict__ dudz, double* __restrict__ dvdz, double* __restrict__ txz,
+                                    double* __restrict__ tyz, Lay lay, int nx, int ny, int ksrc, int kdst, double sign,
+                                    double vonk, double denom, double hk /* 0.5*dz*vonk */) {
+    const long n = long(nx) * ny;
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        const int i = int(t % nx), y = int(t / nx);
+        const long os = lay.at(ksrc, y, i), od = lay.at(kdst, y, i), o1 = long(y) * lay.row + i;
+        const double a = u1[o1], b = v1[o1];
+        const double uavg = sqrt(dadd(dmul(a, a), dmul(b, b)));
+        const double ustar = ddiv(dmul(uavg, vonk), denom);
+        const double cst = dmul(-sign, ddiv(dmul(ustar, ustar), uavg));
+        txz[od] = dmul(cst, a);
+        tyz[od] = dmul(cst, b);
+        const double uu = u[os], vv = v[os];
+        const double g = dmul(sign, ddiv(ustar, hk));
+        dudz[od] = uu == 0.0 ? 0.0 : ddiv(dmul(g, uu), uavg);
+        dvdz[od] = vv == 0.0 ? 0.0 : ddiv(dmul(g, vv), uavg);
+    }
+}
+
+// out = (a + b) [+ c] over 1:nx of planes k0..k1-1, pad columns zeroed when zero_pad
+// (divstress_uv.f90:66-83, divstress_w.f90:74-114)
+static __global__ void k_sum3(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b,
+                              const double* __restrict__ c, Lay lay, int nx, int ny, int k0, int k1, int zero_pad) {
+    const int half = lay.row / 2;
+    const long n = long(half) * ny * (k1 - k0);
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
+        const int j = int(t % half);
+        long r = t / half;
+        const int y = int(r % ny), k = k0 + int(r / ny);
+        const long o = lay.at(k, y, 2 * j);
+        if (2 * j >= nx) {
+            if (zero_pad) *reinterpret_cast<double2*>(out + o) = make_double2(0.0, 0.0);
+            continue;
+        }
+        double2 va = ld2(a + o), vb = ld2(b + o);
+        double2 s2 = make_double2(dadd(va.x, vb.x), dadd(va.y, vb.y));
+        if (c) { double2 vc = ld2(c + o); s2 = make_double2(dadd(s2.x, vc.x), dadd(s2.y, vc.y)); }
+        *reinterpret_cast<double2*>(out + o) = s2;
+    }
+}
+
 }  // namespace lg

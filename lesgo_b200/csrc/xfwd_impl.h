@@ -4,6 +4,8 @@
 #include "sizes.h"
 
 namespace lg {
+template <class Pro> constexpr bool zmajor_for() { return false; }
+template <> constexpr bool zmajor_for<ProConvec>() { return true; }
 template <int NX, class Pro>
 static int launch_xfwd_n(const Pro& pro, int nfields, const XfOut& out, int ny, int k0, int nplanes,
                          const cplx* W, const cplx* Wh, cudaStream_t s) {
@@ -13,7 +15,7 @@ static int launch_xfwd_n(const Pro& pro, int nfields, const XfOut& out, int ny, 
     const long nrows = long(ny) * nplanes;
     if (nrows <= 0) return 0;
     dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, C::MINB));
-    LG_LAUNCH((k_xfwd<NX, Pro>), grid, dim3(C::NTHR), C::smem, s, pro, out, nfields, ny, k0, nplanes, W, Wh);
+    LG_LAUNCH((k_xfwd<NX, Pro>), grid, dim3(C::NTHR), C::smem, s, pro, out, nfields, int(zmajor_for<Pro>() && ny % C::NF == 0), ny, k0, nplanes, W, Wh);
     return 0;
 }
 }  // namespace lg

@@ -10,7 +10,7 @@ static int launch_xinv_n(const XiSrc& in, const EpiStore& epi, int nfields, int 
     const long nrows = long(ny) * nplanes;
     if (nrows <= 0) return 0;
     dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, C::MINB));
-    LG_LAUNCH((k_xinv<NX, EpiStore>), grid, dim3(C::NTHR), C::smem, s, in, epi, nfields, ny, k0, nplanes, W, Wh);
+    LG_LAUNCH((k_xinv<NX, EpiStore>), grid, dim3(C::NTHR), C::smem, s, in, epi, nfields, 0, ny, k0, nplanes, W, Wh);
     return 0;
 }
 #define LG_XINV_CASE_SMALL(S, B) case S: return launch_xinv_n<S>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);

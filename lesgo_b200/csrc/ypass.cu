@@ -20,7 +20,15 @@ template <int NIN, int NOUT>
 static int launch_y_n(const YArgs& a, int nfields, int nplanes, const cplx* Win, const cplx* Wout,
                       cudaStream_t s) {
     if constexpr (NOUT > 0 && (NIN == NOUT || NIN == 0)) {
-        if (a.nout > 1) return launch_y_m<NIN, NOUT, true>(a, nfields, nplanes, Win, Wout, s);
+        // number of inverse transforms per field: an IKX output rides on the COPY transform
+        int ntr = 0;
+        bool has_copy = false, has_ikx = false;
+        for (int o = 0; o < a.nout; ++o) {
+            const int m = a.fld[0].out[o].mode;
+            if (m == Y_COPY) has_copy = true; else if (m == Y_IKX) has_ikx = true; else ++ntr;
+        }
+        ntr += (has_copy || has_ikx) ? 1 : 0;
+        if (ntr > 1) return launch_y_m<NIN, NOUT, true>(a, nfields, nplanes, Win, Wout, s);
     }
     return launch_y_m<NIN, NOUT, false>(a, nfields, nplanes, Win, Wout, s);
 }

@@ -22,7 +22,9 @@ class StepParams(C.Structure):
     _fields_ = [("dt", C.c_double), ("tadv1", C.c_double), ("tadv2", C.c_double),
                 ("mean_p_force_x", C.c_double), ("mean_p_force_y", C.c_double),
                 ("ubot", C.c_double), ("utop", C.c_double), ("nu_molec_nd", C.c_double),
-                ("first_step", C.c_int), ("mode", C.c_int)]
+                ("first_step", C.c_int), ("mode", C.c_int),
+                ("sgs_model", C.c_int), ("ifilter", C.c_int),
+                ("Co", C.c_double), ("wall_damp_exp", C.c_double), ("vonk", C.c_double), ("zo", C.c_double)]
 
 
 # every symbol include/lesgo_gpu.h declares: name -> (restype, argtypes)

@@ -150,20 +150,28 @@ def check_press(core, p, tol=1e-11):
     return out
 
 
-def check_steps(core, p, nsteps=1, tol=1e-12, seed=41, names=("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")):
-    """nsteps of the device-resident core step vs oracle.step(mode='core') from identical fields."""
+def step_kwargs(p, it, mode):
+    return dict(dt=p.dt, tadv1=p.tadv1, tadv2=p.tadv2, first_step=(it == 0), mode=1 if mode == "full" else 0,
+                ubot=p.ubot, utop=p.utop, nu=p.nu,
+                mean_p_force_x=p.mean_p_force_x if p.use_mean_p_force else 0.0,
+                mean_p_force_y=p.mean_p_force_y if p.use_mean_p_force else 0.0,
+                sgs_model=p.sgs_model, ifilter=p.ifilter, Co=p.Co, wall_damp_exp=p.wall_damp_exp, vonk=p.vonk, zo=p.zo)
+
+
+def check_steps(core, p, nsteps=1, tol=1e-12, seed=41, names=("u", "v", "w", "p", "RHSx", "RHSy", "RHSz"), mode="core"):
+    """nsteps of the device-resident step vs oracle.step(mode) from identical fields.  mode "core":
+    scope rows (a)-(e); "full": + wallstress, constant-coefficient sgs_stag, divstress (rows (f)-1)."""
     sp = O.Spectral(p)
     nx, nz = p.nx, p.nz
+    G = O.test_filter_kernel(sp)
     s = initial_state(p, seed=seed)
     for n in ("u", "v", "w"):
         core.upload(n, getattr(s, n))
     for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
         core.upload(n, np.zeros(core.dims.shape))
     for it in range(nsteps):
-        O.step(s, sp, O.LocalComm(), mode="core", first_step=(it == 0))
-        core.step(p.dt, p.tadv1, p.tadv2, first_step=(it == 0), mode=0, ubot=p.ubot, utop=p.utop,
-                  mean_p_force_x=p.mean_p_force_x if p.use_mean_p_force else 0.0,
-                  mean_p_force_y=p.mean_p_force_y if p.use_mean_p_force else 0.0)
+        O.step(s, sp, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=G)
+        core.step(**step_kwargs(p, it, mode))
     out = {}
     for n in names:
         g = core.download(n)
@@ -175,7 +183,7 @@ def check_steps(core, p, nsteps=1, tol=1e-12, seed=41, names=("u", "v", "w", "p"
     return out
 
 
-def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None):
+def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core"):
     """nproc ranks (threads of this process, one Core each) advance `nsteps` core steps;
     the gathered result must match the SINGLE-slab oracle (which the multi-slab oracle
     equals, tests/test_oracle_kat.py)."""
@@ -185,8 +193,9 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
     ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=seed, amp=0.3, L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
     sref = O.State(pg)
     sref.u, sref.v, sref.w = (O.scatter_slab(f, pg) for f in (ug, vg, wg))
+    Gg = O.test_filter_kernel(spg)
     for it in range(nsteps):
-        O.step(sref, spg, O.LocalComm(), mode="core", first_step=(it == 0))
+        O.step(sref, spg, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=Gg)
     ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
     cores = [lesgo_b200.Core(make_dims(p, device=(device_of(p.coord) if device_of else -1)), lib=lib) for p in ps]
     ident = cores[0].comm_unique_id()
@@ -201,8 +210,7 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
             for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
                 c.upload(n, np.zeros(c.dims.shape))
             for it in range(nsteps):
-                c.step(p.dt, p.tadv1, p.tadv2, first_step=(it == 0), mode=0, ubot=p.ubot, utop=p.utop,
-                       mean_p_force_x=p.mean_p_force_x if p.use_mean_p_force else 0.0)
+                c.step(**step_kwargs(p, it, mode))
             res[r] = {n: c.download(n) for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")}
             res[r]["cfl"] = c.max_cfl(p.dt)
         except BaseException as e:  # noqa

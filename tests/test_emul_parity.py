@@ -51,3 +51,25 @@ def test_emul_multirank_steps(nproc):
               use_mean_p_force=True, mean_p_force_x=1.0)
     out = check_multirank_steps(emul_library(), kw, nproc, nsteps=2)
     print(out)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(lbc_mom=1, ubc_mom=1, sgs=False, molec=True, nu_molec=1e-2, utop=1.0, ubot=-1.0),              # DNS Couette
+    dict(lbc_mom=0, ubc_mom=0, sgs=False, molec=True, nu_molec=1e-2),                                    # stress-free DNS
+    dict(lbc_mom=2, ubc_mom=2, sgs=True, sgs_model=1, molec=False, use_mean_p_force=True, mean_p_force_x=1.0),   # LES channel
+    dict(lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=5, molec=False),                                      # half channel, Cs = 0.03
+    dict(lbc_mom=1, ubc_mom=1, sgs=True, sgs_model=1, molec=True, nu_molec=1e-3, ifilter=2),
+])
+def test_emul_full_step(cfg):
+    """Rows (f)-1 on the device: wallstress, calc_Sij, constant-coefficient sgs_stag, divstress."""
+    p = O.Params(nx=16, ny=16, Nz=8, **cfg)
+    out = check_steps(core_for(p), p, nsteps=2, tol=1e-11, mode="full")
+    print(out)
+
+
+def test_emul_multirank_full_step():
+    from helpers import check_multirank_steps
+    kw = dict(nx=16, ny=16, Nz=8, lbc_mom=2, ubc_mom=2, sgs=True, sgs_model=1, molec=False,
+              use_mean_p_force=True, mean_p_force_x=1.0)
+    out = check_multirank_steps(emul_library(), kw, 2, nsteps=2, mode="full")
+    print(out)

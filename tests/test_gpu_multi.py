@@ -22,3 +22,13 @@ def test_multi_gpu_steps(nproc):
     out = check_multirank_steps(lesgo_b200.load_library(), kw, nproc, nsteps=2, tol=1e-11,
                                 device_of=lambda coord: coord)
     print(nproc, out)
+
+
+def test_multi_gpu_full_step():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    kw = dict(nx=64, ny=64, Nz=32, lbc_mom=2, ubc_mom=2, sgs=True, sgs_model=1, molec=False,
+              use_mean_p_force=True, mean_p_force_x=1.0)
+    out = check_multirank_steps(lesgo_b200.load_library(), kw, 2, nsteps=2, tol=1e-11, mode="full",
+                                device_of=lambda coord: coord)
+    print(out)

@@ -111,3 +111,25 @@ def test_errors_are_loud():
     c = core_for(p)
     with pytest.raises(lesgo_b200.LibraryError):
         c.ddx(np.zeros((3, 3, 3)), c.empty())
+
+
+def test_full_step_dns_couette_128x128x64():
+    """BASELINE.json configs[1] for real: DNS walls + molecular stress (wallstress, calc_Sij, sgs_stag
+    with sgs = .false., divstress_uv/w on the device), 1e-12 after one step."""
+    p = O.Params(nx=128, ny=128, Nz=64, lbc_mom=1, ubc_mom=1, utop=1.0, ubot=-1.0, L_x=4 * np.pi,
+                 sgs=False, molec=True, nu_molec=1e-3)
+    out = check_steps(core_for(p), p, nsteps=1, tol=1e-12, mode="full")
+    print(out)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(lbc_mom=2, ubc_mom=2, sgs=True, sgs_model=1, molec=False, use_mean_p_force=True, mean_p_force_x=1.0),
+    dict(lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=5, molec=False),
+    dict(lbc_mom=0, ubc_mom=0, sgs=False, molec=True, nu_molec=1e-2),
+])
+def test_full_step_les_channel(cfg):
+    """LES channel with the equilibrium wall model and a constant-coefficient eddy viscosity
+    (Smagorinsky, or the Cs_opt2 = 0.03 start-up phase of the dynamic models): 10 steps, 1e-9."""
+    p = O.Params(nx=64, ny=64, Nz=32, **cfg)
+    out = check_steps(core_for(p), p, nsteps=10, tol=1e-9, mode="full")
+    print(out)

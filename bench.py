@@ -6,8 +6,9 @@
 
 One "step" = one pass of the hot path: filt_da x3, ddz_uv x2, ddz_w, wall
 derivatives, convec, RHS assembly, AB2, press_stag_array (+ tridag), RHS -= grad p,
-project -- main.f90:155-344 with the stress divergence (rows (f)-1, not yet on device)
-taken as zero -- on device-resident synthetic channel fields.  Metric: Mpts/s with
+project -- main.f90:155-344 with the stress divergence taken as zero (the SURVEY 8(d) core;
+the complete step with wall stress, Smagorinsky stress and its divergence is timed
+separately as `full_step`) -- on device-resident synthetic channel fields.  Metric: Mpts/s with
 points = nx*ny*(nz_tot-1), whole job.  The workload is the 512x512x256 channel at every
 N (strong scaling along LESGO's own z-slab decomposition); it fits one B200.
 
@@ -179,7 +180,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx, ny, Nz = (int(x) for x in args.grid.split(","))
-    dims = lesgo_b200.Dims(nx=nx, ny=ny, Nz=Nz, nproc=world, coord=rank, lbc_mom=1, ubc_mom=1, sgs=False, device=local)
+    dims = lesgo_b200.Dims(nx=nx, ny=ny, Nz=Nz, nproc=world, coord=rank, lbc_mom=1, ubc_mom=1, sgs=True, device=local)
     core = lesgo_b200.Core(dims)
     stream = torch.cuda.current_stream()
     core.set_stream(stream.cuda_stream)
@@ -245,7 +246,7 @@ def main():
     # stress divergence), timed separately; the headline stays the core step of SURVEY 8(d)
     full = None
     try:
-        fkw = dict(step_kw, mode=1, sgs_model=1, nu=0.0)
+        fkw = dict(step_kw, mode=1, sgs_model=1, nu=1e-4)
         for _ in range(2):
             core.step(**fkw)
         barrier()

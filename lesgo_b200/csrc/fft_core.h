@@ -189,8 +189,7 @@ template <> struct Dft<12> { static LG_HD void run(cplx* v) { DftPfa<4, 3>::run(
 
 // ---------------------------------------------------------------------------------
 // Plans.  LG_PLAN(N, R1, R2, R3, R4): radices multiply to N; unused stages are 1.
-// The widest / composite radix goes FIRST: the first stage has no twiddles, so its
-// registers hold only the butterfly operands.
+// Radix order and the 64-register cap were chosen by measurement (profiles/r1_plan_variants.md).
 // ---------------------------------------------------------------------------------
 template <int N> struct Plan;
 #define LG_PLAN(N_, A_, B_, C_, D_)                                                  \
@@ -220,12 +219,12 @@ LG_PLAN(240, 10, 6, 4, 1)
 LG_PLAN(256, 8, 8, 4, 1)
 LG_PLAN(288, 6, 6, 8, 1)
 LG_PLAN(320, 10, 8, 4, 1)
-LG_PLAN(384, 6, 8, 8, 1)
+LG_PLAN(384, 8, 8, 6, 1)
 LG_PLAN(480, 10, 8, 6, 1)
 LG_PLAN(512, 8, 8, 8, 1)
 LG_PLAN(576, 12, 6, 8, 1)
 LG_PLAN(640, 10, 8, 8, 1)
-LG_PLAN(768, 12, 8, 8, 1)
+LG_PLAN(768, 8, 8, 12, 1)
 LG_PLAN(1024, 8, 4, 4, 8)
 LG_PLAN(1536, 6, 8, 8, 4)
 #undef LG_PLAN
@@ -312,7 +311,11 @@ template <int N> struct TileGeom {
     // registers per thread the butterflies want, and the resident blocks that allows
     static constexpr bool pow2(int r) { return r == 1 || r == 2 || r == 4 || r == 8 || r == 16; }
     static constexpr bool pure2 = pow2(P::R1) && pow2(P::R2) && pow2(P::R3) && pow2(P::R4);
-    static constexpr int regs = RCAP <= 8 ? (pure2 ? 64 : 80) : (RCAP <= 12 ? 96 : 128);
+#ifdef LG_REGS51
+    static constexpr int regs = RCAP <= 8 ? (pure2 ? 51 : 64) : (RCAP <= 12 ? 80 : 128);
+#else
+    static constexpr int regs = RCAP <= 8 ? 64 : (RCAP <= 12 ? 80 : 128);
+#endif
     static constexpr int min_blocks(int nthr) { return blocks_for(nthr, regs); }
     // at least two resident blocks for blocks of <= 512 threads, at most 16
     static constexpr int blocks_for(int nthr, int r) {

@@ -311,11 +311,7 @@ template <int N> struct TileGeom {
     // registers per thread the butterflies want, and the resident blocks that allows
     static constexpr bool pow2(int r) { return r == 1 || r == 2 || r == 4 || r == 8 || r == 16; }
     static constexpr bool pure2 = pow2(P::R1) && pow2(P::R2) && pow2(P::R3) && pow2(P::R4);
-#ifdef LG_REGS51
-    static constexpr int regs = RCAP <= 8 ? (pure2 ? 51 : 64) : (RCAP <= 12 ? 80 : 128);
-#else
-    static constexpr int regs = RCAP <= 8 ? 64 : (RCAP <= 12 ? 80 : 128);
-#endif
+    static constexpr int regs = RCAP <= 8 ? 64 : (RCAP <= 12 ? 80 : 128);   // 51 (5 blocks/SM) measured slower
     static constexpr int min_blocks(int nthr) { return blocks_for(nthr, regs); }
     // at least two resident blocks for blocks of <= 512 threads, at most 16
     static constexpr int blocks_for(int nthr, int r) {

@@ -37,10 +37,7 @@ template <int NX> struct XCfg {
     static constexpr int M = NX / 2;
     typedef TileGeom<M> G;
     // rows per tile: as many as a <= 256-thread block can take (see TileGeom)
-#ifndef LG_XTHREADS
-#define LG_XTHREADS 256
-#endif
-    static constexpr int NF0 = LG_XTHREADS / G::threads(1);
+    static constexpr int NF0 = 256 / G::threads(1);
     static constexpr int NF = NF0 < 1 ? 1 : (NF0 > 64 ? 64 : NF0);
     static constexpr int NTHR = G::round32(G::threads(NF));
     static constexpr int MINB = G::min_blocks(NTHR);
@@ -281,6 +278,7 @@ template <int NIN, int NOUT, bool MULTI> struct YCfg {
     static constexpr int NS = (NIN == 0) ? NOUT : ((NOUT == 0) ? NIN : (NIN < NOUT ? NIN : NOUT));  // spectral (small) length
     static constexpr int max2(int a, int b) { return a > b ? a : b; }
     template <int N> static constexpr int thr(int tc) { return TileGeom<(N > 0 ? N : 8)>::threads(tc) * (N > 0); }
+    // 4 columns = 64 contiguous bytes per row; 8 columns (128 B) measured no faster (30.8 vs 30.0 ms/step)
     static constexpr int TC = max2(thr<NIN>(4), thr<NOUT>(4)) <= 512 ? 4 : 2;
     static constexpr int NTHR = ((max2(thr<NIN>(TC), thr<NOUT>(TC)) + 31) / 32) * 32;
     static constexpr int regs = max2(TileGeom<(NIN > 0 ? NIN : 8)>::regs * (NIN > 0), TileGeom<(NOUT > 0 ? NOUT : 8)>::regs * (NOUT > 0));

@@ -237,8 +237,17 @@ def main():
     kern = core.profile(False, report=True)
     peak, peak_src = hbm_peak()
     achieved = A_CORE_BYTES * points / (ms_step * 1e-3) / 1e9 / world
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("grid") == [nx, ny, Nz] and world == 1:
+            traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": A_CORE_BYTES * points,
+                "peak_source": peak_src,
                 "definition": "296 B/point/step (SURVEY 8d A_core) * points / step time / n_gpus; whole hot path"}
     kernels = {k: {"launches": n, "ms": round(t, 4)} for k, (n, t) in sorted(kern.items(), key=lambda kv: -kv[1][1])}
 

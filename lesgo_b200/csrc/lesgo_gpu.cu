@@ -233,13 +233,34 @@ int xfwd(lesgo_gpu_ctx* c, bool bigx, const Pro& pro, int nf, double* const* dst
     return 0;
 }
 
+// optional time-stepping glue fused into an x-inverse epilogue (EpiStore modes 1 and 2)
+struct Fuse {
+    int mode = 0;
+    const double* divt[3] = {nullptr, nullptr, nullptr};
+    double* rhs_f[3] = {nullptr, nullptr, nullptr};
+    double* u[3] = {nullptr, nullptr, nullptr};
+    double force[3] = {0, 0, 0};
+    int kmax[3] = {0, 0, 0};
+    int first_step = 0;
+    double dt = 0, t1 = 0, t2 = 0;
+    // dpdz fusion (press): RHSz, w and the projection range
+    double* rhsz = nullptr;
+    double* w = nullptr;
+    int kproj = 0, kproj_end = 0;
+};
+
 int xinv(lesgo_gpu_ctx* c, bool bigx, const double* const* src, long splane, int srow, int ncol, int nf,
-         double* const* dst, const Lay& dl, int nyrows, int k0, int k1, int pad = 1) {
+         double* const* dst, const Lay& dl, int nyrows, int k0, int k1, int pad = 1, const Fuse* fz = nullptr) {
     XiSrc in;
     EpiStore epi;
+    std::memset(&epi, 0, sizeof(epi));
     for (int i = 0; i < nf; ++i) { in.src[i] = src[i]; epi.dst[i] = dst[i]; }
     in.plane = splane; in.row = srow; in.ncol = ncol;
     epi.lay = dl; epi.nx = bigx ? c->nx2 : c->nx; epi.pad = pad;
+    if (fz && fz->mode) {
+        epi.mode = fz->mode; epi.first_step = fz->first_step; epi.dt = fz->dt; epi.t1 = fz->t1; epi.t2 = fz->t2;
+        for (int i = 0; i < 3; ++i) { epi.divt[i] = fz->divt[i]; epi.rhs_f[i] = fz->rhs_f[i]; epi.u[i] = fz->u[i]; epi.force[i] = fz->force[i]; epi.kmax[i] = fz->kmax[i]; }
+    }
     if (k1 <= k0) return 0;
     ProfScope ps_(c, bigx ? "xinv_big" : "xinv");
     int rc = launch_xinv(bigx ? c->nx2 : c->nx, in, epi, nf, nyrows, k0, k1 - k0,
@@ -365,7 +386,7 @@ int ddz_w(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
 // ---- convec.f90 --------------------------------------------------------------------------------
 int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, const double* dudy,
            const double* dudz, const double* dvdx, const double* dvdz, const double* dwdx,
-           const double* dwdy, double* RHSx, double* RHSy, double* RHSz) {
+           const double* dwdy, double* RHSx, double* RHSy, double* RHSz, const Fuse* fz = nullptr) {
     if (need_small(c, 6) || need_big(c, 6)) return 1;
     const int nz = c->nz, nxh = c->nx / 2;
     const double cs = 1.0 / (double(c->nx) * double(c->ny));
@@ -415,7 +436,7 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
             if (ypass(c, c->ny2, c->ny, a, 3, pa, pb)) return 1;
         }
         // (6) x inverse -> RHS
-        if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, pa, pb)) return 1;
+        if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, pa, pb, 1, fz)) return 1;
     }
     // :319-332
     fill(c, RHSx, c->plane, 0, 1, kBogus); fill(c, RHSy, c->plane, 0, 1, kBogus); fill(c, RHSz, c->plane, 0, 1, kBogus);
@@ -438,7 +459,7 @@ int tridag_setup(lesgo_gpu_ctx* c, TriGeom& g) {
 }
 
 int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, const double* divtz, double dt,
-          double tadv1, double* p, double* dpdx, double* dpdy, double* dpdz) {
+          double tadv1, double* p, double* dpdx, double* dpdy, double* dpdz, const Fuse* fz = nullptr) {
     if (c->d.nproc > 1 && !c->comm) return c->fail("press_stag_array: nproc > 1 needs lesgo_gpu_comm_init first");
     if (c->d.nproc > 1 && (c->ny % c->d.nproc)) return c->fail("press_stag_array: ny must be divisible by nproc");
     if (need_small(c, 6)) return 1;
@@ -561,12 +582,13 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
             if (ypass(c, 0, c->ny, a, 1, ka, kb)) return 1;
             if (xinv(c, false, s0, c->plane, c->ld, nxh, 1, o0, c->lay(), c->ny, ka, kb < pend ? kb : pend)) return 1;
             const int da = ka < 1 ? 1 : ka, db = kb < nz ? kb : nz;
-            if (xinv(c, false, s1, c->plane, c->ld, nxh, 2, o1, c->lay(), c->ny, da, db)) return 1;
+            if (xinv(c, false, s1, c->plane, c->ld, nxh, 2, o1, c->lay(), c->ny, da, db, 1, fz)) return 1;
             const int za = ka < 1 ? 1 : ka, zb = kb < pend ? kb : pend;
             if (zb > za) {
                 ProfScope ps_(c, "dpdz");
                 LG_LAUNCH(k_dpdz, dim3(grid1d(long(nxh) * c->ny * (zb - za))), dim3(kBlock), 0, c->stream, p, dpdz, c->lay(),
-                          c->nx, c->ny, za, zb, c->d.dz);
+                          c->nx, c->ny, za, zb, c->d.dz, fz ? fz->rhsz : nullptr, fz ? fz->w : nullptr,
+                          fz ? fz->kproj : 0, fz ? fz->kproj_end : 0, fz ? fz->dt : 0.0, fz ? fz->t1 : 0.0);
                 c->launches++;
             }
         }
@@ -788,30 +810,44 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     if (sp->mode == 1 && build_sgs_tables(c, sp)) return 1;
     if (wallstress(c, sp, F, sp->mode == 1)) return 1;
     if (sp->mode == 1 && sgs_and_divstress(c, sp, F)) return 1;
-    // :207
-    if (convec(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DUDY], F[LG_DUDZ], F[LG_DVDX], F[LG_DVDZ], F[LG_DWDX],
-               F[LG_DWDY], F[LG_RHSX], F[LG_RHSY], F[LG_RHSZ])) return 1;
-    // :211-214, 229-232 (RHS assembly), :273-280 (Euler start), :287-296 (AB2) in one pass per component
+    // :207 convec, with :211-214/229-232 (RHS assembly), :273-280 (Euler start) and :287-296 (AB2)
+    // fused into the epilogue of its last x pass
     {
-        const int kw = c->top ? nz + 1 : nz;
-        const int fs = sp->first_step ? 1 : 0;
-        glue_fused(c, F_RHS_AB2, F[LG_RHSX], F[LG_DIVTX], F[LG_RHSX_F], F[LG_U], 1, nz, 0, fs, sp->mean_p_force_x, sp->dt, sp->tadv1, sp->tadv2);
-        glue_fused(c, F_RHS_AB2, F[LG_RHSY], F[LG_DIVTY], F[LG_RHSY_F], F[LG_V], 1, nz, 0, fs, sp->mean_p_force_y, sp->dt, sp->tadv1, sp->tadv2);
-        glue_fused(c, F_RHS_AB2, F[LG_RHSZ], F[LG_DIVTZ], F[LG_RHSZ_F], F[LG_W], 1, kw, 0, fs, 0.0, sp->dt, sp->tadv1, sp->tadv2);
+        Fuse fz;
+        fz.mode = 1; fz.first_step = sp->first_step ? 1 : 0; fz.dt = sp->dt; fz.t1 = sp->tadv1; fz.t2 = sp->tadv2;
+        fz.divt[0] = F[LG_DIVTX]; fz.divt[1] = F[LG_DIVTY]; fz.divt[2] = F[LG_DIVTZ];
+        fz.rhs_f[0] = F[LG_RHSX_F]; fz.rhs_f[1] = F[LG_RHSY_F]; fz.rhs_f[2] = F[LG_RHSZ_F];
+        fz.u[0] = F[LG_U]; fz.u[1] = F[LG_V]; fz.u[2] = F[LG_W];
+        fz.force[0] = sp->mean_p_force_x; fz.force[1] = sp->mean_p_force_y; fz.force[2] = 0.0;
+        fz.kmax[0] = nz - 1; fz.kmax[1] = nz - 1; fz.kmax[2] = c->top ? nz : nz - 1;
+        // convec reads u, v, w only in its first passes (to the 3/2 grid), all finished before the
+        // epilogue of the last pass updates them -- but only when the whole slab is one chunk
+        const Fuse* use = c->chunk == 0 ? &fz : nullptr;
+        if (convec(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DUDY], F[LG_DUDZ], F[LG_DVDX], F[LG_DVDZ], F[LG_DWDX],
+                   F[LG_DWDY], F[LG_RHSX], F[LG_RHSY], F[LG_RHSZ], use)) return 1;
+        if (!use) {
+            const int kw = c->top ? nz + 1 : nz;
+            glue_fused(c, F_RHS_AB2, F[LG_RHSX], F[LG_DIVTX], F[LG_RHSX_F], F[LG_U], 1, nz, 0, fz.first_step, sp->mean_p_force_x, sp->dt, sp->tadv1, sp->tadv2);
+            glue_fused(c, F_RHS_AB2, F[LG_RHSY], F[LG_DIVTY], F[LG_RHSY_F], F[LG_V], 1, nz, 0, fz.first_step, sp->mean_p_force_y, sp->dt, sp->tadv1, sp->tadv2);
+            glue_fused(c, F_RHS_AB2, F[LG_RHSZ], F[LG_DIVTZ], F[LG_RHSZ_F], F[LG_W], 1, kw, 0, fz.first_step, 0.0, sp->dt, sp->tadv1, sp->tadv2);
+        }
     }
     // :299-308
     fill(c, F[LG_U], c->plane, 0, 1, kBogus); fill(c, F[LG_V], c->plane, 0, 1, kBogus); fill(c, F[LG_W], c->plane, 0, 1, kBogus);
     fill(c, F[LG_U], c->plane, nz, nz + 1, kBogus); fill(c, F[LG_V], c->plane, nz, nz + 1, kBogus);
     if (!c->top) fill(c, F[LG_W], c->plane, nz, nz + 1, kBogus);
-    // :317
-    if (press(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DIVTZ], sp->dt, sp->tadv1, F[LG_P], F[LG_DPDX], F[LG_DPDY],
-              F[LG_DPDZ])) return 1;
-    // :321-326 (RHS -= grad p) and project (forcing.f90:171-207) in one pass per component
-    glue_fused(c, F_GRADP_PROJECT, F[LG_RHSX], F[LG_DPDX], nullptr, F[LG_U], 1, nz, 1, 0, 0.0, sp->dt, sp->tadv1, 0.0);
-    glue_fused(c, F_GRADP_PROJECT, F[LG_RHSY], F[LG_DPDY], nullptr, F[LG_V], 1, nz, 1, 0, 0.0, sp->dt, sp->tadv1, 0.0);
-    // w: RHSz gets plane nz on the top rank too, the projection stops at nz-1 and skips plane 1 at the wall
-    glue_fused(c, F_GRADP_PROJECT, F[LG_RHSZ], F[LG_DPDZ], nullptr, F[LG_W], 1, nz, c->bottom ? 2 : 1, 0, 0.0, sp->dt, sp->tadv1, 0.0);
-    if (c->top) glue(c, G_SUB, F[LG_RHSZ], F[LG_DPDZ], nullptr, c->ld, nz, nz + 1, 0, 0, 0);
+    // :317 press_stag_array, with :321-326 (RHS -= grad p) and project (forcing.f90:171-207) fused into
+    // the epilogues of its last passes.  press reads u, v, w only in its first pass.
+    {
+        Fuse fz;
+        fz.mode = 2; fz.dt = sp->dt; fz.t1 = sp->tadv1;
+        fz.rhs_f[0] = F[LG_RHSX]; fz.rhs_f[1] = F[LG_RHSY];      // mode 2 updates RHS in place
+        fz.u[0] = F[LG_U]; fz.u[1] = F[LG_V];
+        fz.rhsz = F[LG_RHSZ]; fz.w = F[LG_W];
+        fz.kproj = c->bottom ? 2 : 1; fz.kproj_end = nz;
+        if (press(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DIVTZ], sp->dt, sp->tadv1, F[LG_P], F[LG_DPDX], F[LG_DPDY],
+                  F[LG_DPDZ], &fz)) return 1;
+    }
     if (c->comm) {
         if (c->comm->sync_planes(F[LG_U], c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
         if (c->comm->sync_planes(F[LG_V], c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());

@@ -124,16 +124,71 @@ struct ProConvec {
 };
 
 // ---- x-inverse epilogue ------------------------------------------------------------
+// mode 0: plain store.
+// mode 1: the value is the convective term cc; fuses the RHS assembly, the Euler start and the
+//         AB2 update (main.f90:211-214, 229-232, 273-280, 287-296):
+//             rhs = -cc - divt + force;  [first step: rhs_f = rhs];  u += dt*(tadv1*rhs + tadv2*rhs_f)
+//         on planes k <= kmax[fld] (the other planes just get the plain store).
+// mode 2: the value is a pressure-gradient component; fuses main.f90:321-326 and project
+//         (forcing.f90:171-207):  dpd = value;  rhs -= value;  u += dt*(-tadv1*value)
 struct EpiStore {
     double* dst[kMaxFields];
     Lay lay;
     int nx;          // real row length; the two pad reals are zeroed when pad != 0
     int pad;
+    int mode;
+    const double* divt[3];
+    double* rhs_f[3];
+    double* u[3];
+    double force[3];
+    int kmax[3];
+    int first_step;
+    double dt, t1, t2;
     LG_D void store(int fld, int k, int y, int j, double2 v) const {
-        *reinterpret_cast<double2*>(dst[fld] + lay.at(k, y, 2 * j)) = v;
+        const long o = lay.at(k, y, 2 * j);
+        if (mode == 1 && k <= kmax[fld]) {
+            double2 vb = ld2(divt[fld] + o), vu = ld2(u[fld] + o);
+            const double f = force[fld];
+            double2 nr = make_double2(dadd(dsub(-v.x, vb.x), f), dadd(dsub(-v.y, vb.y), f));
+            double2 vf;
+            if (first_step) { vf = nr; *reinterpret_cast<double2*>(rhs_f[fld] + o) = nr; }
+            else vf = ld2(rhs_f[fld] + o);
+            *reinterpret_cast<double2*>(dst[fld] + o) = nr;
+            *reinterpret_cast<double2*>(u[fld] + o) =
+                make_double2(dadd(vu.x, dmul(dt, dadd(dmul(t1, nr.x), dmul(t2, vf.x)))),
+                             dadd(vu.y, dmul(dt, dadd(dmul(t1, nr.y), dmul(t2, vf.y)))));
+            return;
+        }
+        *reinterpret_cast<double2*>(dst[fld] + o) = v;
+        if (mode == 2) {
+            double2 vr = ld2(rhs_f[fld] + o), vu = ld2(u[fld] + o);      // rhs_f[] holds RHS here
+            *reinterpret_cast<double2*>(rhs_f[fld] + o) = make_double2(dsub(vr.x, v.x), dsub(vr.y, v.y));
+            *reinterpret_cast<double2*>(u[fld] + o) = make_double2(dadd(vu.x, dmul(dt, dmul(-t1, v.x))),
+                                                                   dadd(vu.y, dmul(dt, dmul(-t1, v.y))));
+        }
     }
     LG_D void finish_row(int fld, int k, int y) const {
-        if (pad) *reinterpret_cast<double2*>(dst[fld] + lay.at(k, y, nx)) = make_double2(0.0, 0.0);
+        if (!pad) return;
+        const long o = lay.at(k, y, nx);
+        if (mode == 1 && k <= kmax[fld]) {
+            // whole-row semantics of the Fortran array expressions on the two pad reals
+            double2 vb = ld2(divt[fld] + o), vu = ld2(u[fld] + o);
+            const double f = force[fld];
+            double2 nr = make_double2(dadd(dsub(-0.0, vb.x), f), dadd(dsub(-0.0, vb.y), f));
+            double2 vf;
+            if (first_step) { vf = nr; *reinterpret_cast<double2*>(rhs_f[fld] + o) = nr; }
+            else vf = ld2(rhs_f[fld] + o);
+            *reinterpret_cast<double2*>(dst[fld] + o) = nr;
+            *reinterpret_cast<double2*>(u[fld] + o) =
+                make_double2(dadd(vu.x, dmul(dt, dadd(dmul(t1, nr.x), dmul(t2, vf.x)))),
+                             dadd(vu.y, dmul(dt, dadd(dmul(t1, nr.y), dmul(t2, vf.y)))));
+            return;
+        }
+        *reinterpret_cast<double2*>(dst[fld] + o) = make_double2(0.0, 0.0);
+        if (mode == 2) {
+            double2 vr = ld2(rhs_f[fld] + o);
+            *reinterpret_cast<double2*>(rhs_f[fld] + o) = make_double2(dsub(vr.x, 0.0), dsub(vr.y, 0.0));
+        }
     }
 };
 
@@ -386,17 +441,30 @@ static __global__ void k_tridag_fused(TriGeom g, const double* __restrict__ Hx, 
     }
 }
 
-// dpdz(k) = (p(k) - p(k-1))/dz over 1:nx (press_stag_array.f90:284-288): true division
+// dpdz(k) = (p(k) - p(k-1))/dz over 1:nx (press_stag_array.f90:284-288): true division.
+// With rhs != nullptr also RHSz -= dpdz (main.f90:323) and, for kproj <= k < kproj_end,
+// w += dt*(-tadv1*dpdz) (forcing.f90:195-207).
 static __global__ void k_dpdz(const double* __restrict__ p, double* __restrict__ dpdz, Lay lay, int nx, int ny,
-                       int k0, int k1, double dz) {
+                              int k0, int k1, double dz, double* __restrict__ rhs, double* __restrict__ w,
+                              int kproj, int kproj_end, double dt, double t1) {
     const long n = long(nx / 2) * ny * (k1 - k0);
     for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
         int j = int(t % (nx / 2));
         long r = t / (nx / 2);
         int y = int(r % ny), k = k0 + int(r / ny);
-        double2 a = ld2(p + lay.at(k, y, 2 * j)), b = ld2(p + lay.at(k - 1, y, 2 * j));
-        *reinterpret_cast<double2*>(dpdz + lay.at(k, y, 2 * j)) =
-            make_double2(ddiv(dsub(a.x, b.x), dz), ddiv(dsub(a.y, b.y), dz));
+        const long o = lay.at(k, y, 2 * j);
+        double2 a = ld2(p + o), b = ld2(p + lay.at(k - 1, y, 2 * j));
+        double2 v = make_double2(ddiv(dsub(a.x, b.x), dz), ddiv(dsub(a.y, b.y), dz));
+        *reinterpret_cast<double2*>(dpdz + o) = v;
+        if (rhs) {
+            double2 vr = ld2(rhs + o);
+            *reinterpret_cast<double2*>(rhs + o) = make_double2(dsub(vr.x, v.x), dsub(vr.y, v.y));
+            if (k >= kproj && k < kproj_end) {
+                double2 vu = ld2(w + o);
+                *reinterpret_cast<double2*>(w + o) = make_double2(dadd(vu.x, dmul(dt, dmul(-t1, v.x))),
+                                                                  dadd(vu.y, dmul(dt, dmul(-t1, v.y))));
+            }
+        }
     }
 }
 

@@ -317,7 +317,7 @@ def run_e2e(core, dims, u, v, w, dt, tadv1, nsteps, points):
                                "RHSz", "divtz", "p", "dpdx", "dpdy", "dpdz")}
     F["u"], F["v"], F["w"] = pinned(u), pinned(v), pinned(w)
     nb = float(np.prod(dims.shape) * 8)
-    h2d = nb * (3 * 1 + 3 * 2 + 9 + 4 + 3)      # filt_da in; ddz in + out(staged inout); convec in; press in + 3 staged
+    h2d = nb * (3 * 1 + 3 * 1 + 9 + 4)          # filt_da in; ddz in; convec in; press in (outputs are not uploaded)
     d2h = nb * (3 * 3 + 3 + 3 + 4)
 
     def one():

@@ -82,7 +82,9 @@ int lesgo_gpu_convec(lesgo_gpu_ctx* ctx, const double* u, const double* v, const
 
 /* ---- press_stag_array (press_stag_array.f90:21-290) ------------------------------------
  * reads u, v, w (1:nz-1, + w(nz) on the top rank), divtz(1) on coord 0, divtz(nz) on the
- * top rank; writes p (0:nz), dpdx, dpdy, dpdz (all passed as (ld, ny, 0:nz) arrays; planes
+ * top rank; writes p (0:nz), dpdx, dpdy, dpdz (all ADDRESSED as (ld, ny, 0:nz) arrays -- pass the
+ * address of plane 1 minus one plane for the three 1:nz arrays; their plane 0 is never read, written
+ * or copied; planes
  * 1:nz-1 valid, + nz of p/dpdz on the top rank).  Includes tridag_array and, for
  * nproc > 1, the halo / transpose communication (lesgo_gpu_comm_init first). */
 int lesgo_gpu_press_stag_array(lesgo_gpu_ctx* ctx, const double* u, const double* v,

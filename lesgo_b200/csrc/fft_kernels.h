@@ -279,7 +279,7 @@ template <int NIN, int NOUT, bool MULTI> struct YCfg {
     static constexpr int max2(int a, int b) { return a > b ? a : b; }
     template <int N> static constexpr int thr(int tc) { return TileGeom<(N > 0 ? N : 8)>::threads(tc) * (N > 0); }
     // 4 columns = 64 contiguous bytes per row; 8 columns (128 B) measured no faster (30.8 vs 30.0 ms/step)
-    static constexpr int TC = max2(thr<NIN>(4), thr<NOUT>(4)) <= 512 ? 4 : 2;
+    static constexpr int TC = max2(thr<NIN>(4), thr<NOUT>(4)) <= 512 ? 4 : 2;   // (2 columns for the 768 passes: 30.8 ms)
     static constexpr int NTHR = ((max2(thr<NIN>(TC), thr<NOUT>(TC)) + 31) / 32) * 32;
     static constexpr int regs = max2(TileGeom<(NIN > 0 ? NIN : 8)>::regs * (NIN > 0), TileGeom<(NOUT > 0 ? NOUT : 8)>::regs * (NOUT > 0));
     static constexpr int MINB = TileGeom<8>::blocks_for(NTHR, regs);

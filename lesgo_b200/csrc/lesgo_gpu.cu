@@ -172,12 +172,14 @@ bool is_device_ptr(const void* p) {
 
 struct Staged {
     lesgo_gpu_ctx* c;
-    struct Item { double* host; double* dev; size_t bytes; bool out; };
+    struct Item { double* host; double* dev; size_t bytes; bool out; size_t skip; };
     std::vector<Item> items;
     size_t next_slot = 0;
     explicit Staged(lesgo_gpu_ctx* c_) : c(c_) {}
-    // returns the device pointer to use for user pointer p holding `n` doubles
-    double* in(const double* p, size_t n, bool copy_in, bool copy_out) {
+    // returns the device pointer to use for user pointer p holding `n` doubles; the first `skip`
+    // doubles are never copied in either direction (arrays the reference declares 1:nz are passed
+    // shifted down by one plane, so their "plane 0" is not the caller's memory)
+    double* in(const double* p, size_t n, bool copy_in, bool copy_out, size_t skip = 0) {
         if (!p) return nullptr;
         if (is_device_ptr(p)) return const_cast<double*>(p);
         // same host array passed twice (in and out) shares one slot
@@ -193,14 +195,15 @@ struct Staged {
             c->staging_bytes[slot] = n * sizeof(double);
         }
         double* d = c->staging[slot];
-        if (copy_in) cudaMemcpyAsync(d, p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
-        items.push_back(Item{const_cast<double*>(p), d, n * sizeof(double), copy_out});
+        if (copy_in) cudaMemcpyAsync(d + skip, p + skip, (n - skip) * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        else if (copy_out) cudaMemsetAsync(d, 0, n * sizeof(double), c->stream);   // pure output: defined pads, no H2D
+        items.push_back(Item{const_cast<double*>(p), d, n * sizeof(double), copy_out, skip});
         return d;
     }
     int finish() {
         bool any = false;
         for (auto& it : items)
-            if (it.out) { cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, c->stream); any = true; }
+            if (it.out) { cudaMemcpyAsync(it.host + it.skip, it.dev + it.skip, it.bytes - it.skip * sizeof(double), cudaMemcpyDeviceToHost, c->stream); any = true; }
         if (any || !items.empty()) {
             cudaError_t e = cudaStreamSynchronize(c->stream);
             if (e != cudaSuccess) return c->fail(std::string("stream sync: ") + cudaGetErrorString(e));
@@ -540,7 +543,7 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         {
             const int nm = (c->lh - 1) * g.cy;
             ProfScope ps_(c, "tridag");
-            LG_LAUNCH(k_tridag_pencil, dim3((nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, c->sa[5]);
+            LG_LAUNCH(k_tridag_pencil, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, c->sa[5]);
             c->launches++;
         }
         {
@@ -1056,7 +1059,7 @@ int lesgo_gpu_ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
     if (!c || !f || !dfdz) return 1;
     Staged st(c);
     double* df = st.in(f, NFIELD, true, false);
-    double* dz = st.in(dfdz, NFIELD, true, true);
+    double* dz = st.in(dfdz, NFIELD, false, true);
     if (!df || !dz) return 1;
     if (ddz_uv(c, df, dz)) return 1;
     return st.finish();
@@ -1067,7 +1070,7 @@ int lesgo_gpu_ddz_w(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
     if (!c || !f || !dfdz) return 1;
     Staged st(c);
     double* df = st.in(f, NFIELD, true, false);
-    double* dz = st.in(dfdz, NFIELD, true, true);
+    double* dz = st.in(dfdz, NFIELD, false, true);
     if (!df || !dz) return 1;
     if (ddz_w(c, df, dz)) return 1;
     return st.finish();
@@ -1105,9 +1108,10 @@ int lesgo_gpu_press_stag_array(lesgo_gpu_ctx* c, const double* u, const double* 
     double* dw = st.in(w, NFIELD, true, false);
     double* dd = st.in(divtz, NFIELD, true, false);
     double* op = st.in(p, NFIELD, false, true);
-    double* ox = st.in(dpdx, NFIELD, true, true);
-    double* oy = st.in(dpdy, NFIELD, true, true);
-    double* oz = st.in(dpdz, NFIELD, true, true);
+    // dpdx, dpdy, dpdz are (1:nz) in the reference: plane 0 of the passed address is not theirs
+    double* ox = st.in(dpdx, NFIELD, false, true, size_t(c->plane));
+    double* oy = st.in(dpdy, NFIELD, false, true, size_t(c->plane));
+    double* oz = st.in(dpdz, NFIELD, false, true, size_t(c->plane));
     if (!du || !dv || !dw || !dd || !op || !ox || !oy || !oz) return 1;
     if (press(c, du, dv, dw, dd, dt, tadv1, op, ox, oy, oz)) return 1;
     return st.finish();

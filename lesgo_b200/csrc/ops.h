@@ -614,15 +614,18 @@ static __global__ void k_tridag_setup_pencil(PencilGeom g, int nzt, double* __re
     }
 }
 
-// recv layout: buf[src r][block row i][jy_local][ld]; solved in place.
+// recv layout: buf[src r][block row i][jy_local][ld]; solved in place.  The matrix is real, so the
+// real and imaginary parts of a mode are independent systems: one thread each (same arithmetic,
+// twice the parallelism for the short pencils of a many-rank run).
 static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __restrict__ gam, double* __restrict__ buf) {
     const int nm = (g.lh - 1) * g.cy;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nm) return;
+    const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t2 >= 2 * nm) return;
+    const int t = t2 >> 1, part = t2 & 1;
     const int jx = t % (g.lh - 1), jl = t / (g.lh - 1), jy = g.coord * g.cy + jl;
     if (jy == g.ny / 2) return;
     const int n = nzt + 1;
-    const long mo = long(jl) * g.ld + 2 * jx;
+    const long mo = long(jl) * g.ld + 2 * jx + part;
     const long rs = long(g.cy) * g.ld;                            // doubles between block rows
     // global row gj (1..n) -> address
     auto at = [&](int gj) -> double* {
@@ -638,41 +641,38 @@ static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __re
     if (jx == 0 && jy == 0) {
         // zero-wavenumber chain (press_stag_array.f90:226-234): row 1 holds -dz*rbottomw = p(1),
         // rows 2..nzt hold H_z(0,0,k); p(k) is system row k+1.
-        double2 pk = ld2(at(1));                                  // p(1) = 0 - dz*rbottomw
-        *reinterpret_cast<double2*>(at(1)) = make_double2(0.0, 0.0);   // p(0) = 0
-        double2 carry = pk;
+        double carry = *at(1);                                    // p(1) = 0 - dz*rbottomw
+        *at(1) = 0.0;                                             // p(0) = 0
         for (int k = 2; k <= nzt; ++k) {
-            double2 h = ld2(at(k));
-            *reinterpret_cast<double2*>(at(k)) = carry;           // row k = p(k-1)
-            carry = make_double2(dadd(carry.x, dmul(h.x, g.dz)), dadd(carry.y, dmul(h.y, g.dz)));
+            const double h = *at(k);
+            *at(k) = carry;                                       // row k = p(k-1)
+            carry = dadd(carry, dmul(h, g.dz));
         }
-        *reinterpret_cast<double2*>(at(n)) = carry;               // row n = p(nzt)
+        *at(n) = carry;                                           // row n = p(nzt)
         return;
     }
     const double c3 = ddiv(1.0, dmul(g.dz, g.dz));
     const double kx = g.kxs * double(jx);
     const double ky = g.kys * double(jy < g.ny / 2 ? jy : jy - g.ny);
     const double bb = -dadd(dadd(dmul(kx, kx), dmul(ky, ky)), dmul(2.0, c3));
-    double2 r1 = ld2(at(1));
-    double2 u = make_double2(ddiv(r1.x, -1.0), ddiv(r1.y, -1.0));
-    *reinterpret_cast<double2*>(at(1)) = u;
+    double u = ddiv(*at(1), -1.0);
+    *at(1) = u;
     double bet = -1.0;
     for (int j = 2; j <= n; ++j) {
         const double a = (j == n) ? -1.0 : c3;
         const double b = (j == n) ? 1.0 : bb;
         double* pj = at(j);
-        double2 r = ld2(pj);
+        const double r = *pj;
         const double gm = gam[(long(j) * g.cy + jl) * g.lh + jx];
         bet = dsub(b, dmul(a, gm));
-        u = make_double2(ddiv(dsub(r.x, dmul(a, u.x)), bet), ddiv(dsub(r.y, dmul(a, u.y)), bet));
-        *reinterpret_cast<double2*>(pj) = u;
+        u = ddiv(dsub(r, dmul(a, u)), bet);
+        *pj = u;
     }
     for (int j = n - 1; j >= 1; --j) {
         const double gm = gam[(long(j + 1) * g.cy + jl) * g.lh + jx];
         double* pj = at(j);
-        double2 uj = ld2(pj);
-        u = make_double2(dsub(uj.x, dmul(gm, u.x)), dsub(uj.y, dmul(gm, u.y)));
-        *reinterpret_cast<double2*>(pj) = u;
+        u = dsub(*pj, dmul(gm, u));
+        *pj = u;
     }
 }
 

@@ -185,9 +185,8 @@ def main():
     stream = torch.cuda.current_stream()
     core.set_stream(stream.cuda_stream)
     if world > 1:
-        ident = [core.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ident, src=0)
-        core.comm_init(ident[0])
+        from lesgo_b200 import slab
+        slab.bootstrap_comm(core, dist)
     dt, tadv1, tadv2 = 2e-4, 1.5, -0.5
     u, v, w = synthetic_slab(dims)
     for n, a in (("u", u), ("v", v), ("w", w)):

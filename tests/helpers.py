@@ -212,6 +212,19 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
             for it in range(nsteps):
                 c.step(**step_kwargs(p, it, mode))
             res[r] = {n: c.download(n) for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")}
+            # mpi_sync_real_array (mpi_defs.f90:245-262) on a host array
+            var = np.zeros(c.dims.shape)
+            for k in range(p.nz + 1):
+                var[k] = 100.0 * r + k
+            c.sync_real_array(var, 3)
+            if r > 0:
+                assert np.all(var[0] == 100.0 * (r - 1) + p.nz - 1), "SYNC_UP"
+            else:
+                assert np.all(var[0] == 0.0)
+            if r < nproc - 1:
+                assert np.all(var[p.nz] == 100.0 * (r + 1) + 1), "SYNC_DOWN"
+            else:
+                assert np.all(var[p.nz] == 100.0 * r + p.nz)
             res[r]["cfl"] = c.max_cfl(p.dt)
         except BaseException as e:  # noqa
             err[r] = e
@@ -234,3 +247,33 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
     for k, v in out.items():
         assert v <= tol, (k, v, out)
     return out
+
+
+def check_misc(core, p):
+    """wavenumbers (fft.f90:130-160), tridag_array with caller-supplied coefficients
+    (tridag_array.f90:166-246) and its zero-pivot error path."""
+    sp = O.Spectral(p)
+    kx, ky, k2 = core.wavenumbers()
+    assert np.array_equal(kx, sp.kx) and np.array_equal(ky, sp.ky) and np.array_equal(k2, sp.k2)
+    n = p.nz + 1
+    rng = np.random.default_rng(77)
+    a = rng.uniform(0.5, 1.0, (n, p.ny, p.lh)); c = rng.uniform(0.5, 1.0, (n, p.ny, p.lh))
+    b = -(a + c + rng.uniform(0.1, 1.0, (n, p.ny, p.lh)))
+    r = np.zeros((n, p.ny, p.ld)); r[:, :, :] = rng.standard_normal((n, p.ny, p.ld))
+    u = np.zeros_like(r)
+    core.tridag_array(a, b, c, r, u)
+    # oracle layout: row j at index j (index 0 unused), n rows = nz + 1
+    pad = lambda x: np.concatenate([np.zeros((1,) + x.shape[1:]), x])
+    uo = pad(np.zeros_like(r))
+    po = O.Params(nx=p.nx, ny=p.ny, Nz=p.Nz, nproc=1)
+    O.tridag_array(pad(a), pad(b), pad(c), pad(r), uo, po, O.LocalComm())
+    M = np.zeros((p.ny, p.lh), bool); M[:, :p.lh - 1] = True; M[p.ny // 2] = False; M[0, 0] = False
+    got = u.view(np.complex128)[:, M]; ref = uo[1:].view(np.complex128)[:, M]
+    assert rel(got, ref) < 1e-14, rel(got, ref)
+    b0 = b.copy(); b0[0, 1, 1] = 0.0
+    try:
+        core.tridag_array(a, b0, c, r, u)
+        raise AssertionError("zero pivot not reported")
+    except lesgo_b200.LibraryError as e:
+        assert "zero pivot" in str(e)
+    return True

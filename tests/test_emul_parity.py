@@ -31,6 +31,12 @@ def test_emul_convec(bc):
     check_convec(core_for(p), p)
 
 
+def test_emul_misc():
+    from helpers import check_misc
+    p = O.Params(nx=16, ny=16, Nz=6, L_x=3.0)
+    check_misc(core_for(p), p)
+
+
 def test_emul_press():
     p = O.Params(nx=16, ny=16, Nz=8)
     check_press(core_for(p), p)

@@ -133,3 +133,17 @@ def test_full_step_les_channel(cfg):
     p = O.Params(nx=64, ny=64, Nz=32, **cfg)
     out = check_steps(core_for(p), p, nsteps=10, tol=1e-9, mode="full")
     print(out)
+
+
+def test_misc_entry_points():
+    from helpers import check_misc
+    p = O.Params(nx=64, ny=32, Nz=12, L_x=3.0)
+    c = core_for(p)
+    check_misc(c, p)
+    # profiling facility + launch counter
+    f = random_field(p, 3)
+    n0 = c.launch_count
+    c.profile(True)
+    c.ddx(f, c.empty())
+    rep = c.profile(False, report=True)
+    assert c.launch_count - n0 == 3 and set(rep) == {"xfwd", "ypass_deriv", "xinv"}

@@ -79,3 +79,20 @@ def test_emul_multirank_full_step():
               use_mean_p_force=True, mean_p_force_x=1.0)
     out = check_multirank_steps(emul_library(), kw, 2, nsteps=2, mode="full")
     print(out)
+
+
+@pytest.mark.parametrize("Nz,mode", [(2, "core"), (2, "full"), (3, "full")])
+def test_emul_minimal_slab(Nz, mode):
+    """Smallest slabs: bottom and top special planes adjacent (nz = 3 or 4)."""
+    p = O.Params(nx=16, ny=16, Nz=Nz, lbc_mom=1, ubc_mom=1, utop=0.3, ubot=-0.3, sgs=(mode == "full"),
+                 sgs_model=1, molec=True, nu_molec=1e-2)
+    check_steps(core_for(p), p, nsteps=2, tol=1e-11, mode=mode)
+    check_convec(core_for(p), p)
+
+
+def test_emul_multirank_thin_slabs():
+    """Four ranks with two owned planes each (nz = 3)."""
+    from helpers import check_multirank_steps
+    kw = dict(nx=16, ny=16, Nz=8, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5, sgs=True, sgs_model=1,
+              molec=True, nu_molec=1e-2)
+    check_multirank_steps(emul_library(), kw, 4, nsteps=2, mode="full")

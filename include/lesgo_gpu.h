@@ -104,7 +104,9 @@ enum lesgo_gpu_field {
     LG_P, LG_DPDX, LG_DPDY, LG_DPDZ, LG_DIVTX, LG_DIVTY, LG_DIVTZ,
     LG_TXX, LG_TXY, LG_TXZ, LG_TYY, LG_TYZ, LG_TZZ, LG_NFIELDS
 };
-/* device pointer of a resident field ((ld, ny, 0:nz) doubles); allocated on first use */
+/* device pointer of a resident field ((ld, ny, 0:nz) doubles); allocated on first use.  NOTE:
+ * lesgo_gpu_step makes RHS* and RHS*_f trade places every step instead of copying (main.f90:155-157),
+ * so re-query the pointers of those six fields after a step; upload/download always follow the ids. */
 double* lesgo_gpu_field_ptr(lesgo_gpu_ctx* ctx, int field);
 int lesgo_gpu_upload(lesgo_gpu_ctx* ctx, int field, const double* host);
 int lesgo_gpu_download(lesgo_gpu_ctx* ctx, int field, double* host);

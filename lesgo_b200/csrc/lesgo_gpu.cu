@@ -20,7 +20,6 @@ namespace {
 const double kBogus = -1234567890.0;   // param.f90:93
 thread_local std::string g_err;
 
-struct HostDevArg;
 }  // namespace
 
 struct lesgo_gpu_ctx {
@@ -309,16 +308,6 @@ int fill(lesgo_gpu_ctx* c, double* f, long plane, int k0, int k1, double v) {
     if (k1 <= k0) return 0;
     ProfScope ps_(c, "fill");
     LG_LAUNCH(k_fill, dim3(grid1d(plane * (k1 - k0))), dim3(kBlock), 0, c->stream, f, plane, k0, k1, v);
-    c->launches++;
-    return 0;
-}
-
-int glue(lesgo_gpu_ctx* c, int mode, double* a, const double* b, const double* cc, int nxlim, int k0, int k1,
-         double c0, double c1, double c2) {
-    if (k1 <= k0) return 0;
-    ProfScope ps_(c, "glue");
-    LG_LAUNCH(k_glue, dim3(grid1d(long(c->lh) * c->ny * (k1 - k0))), dim3(kBlock), 0, c->stream, mode, a, b, cc,
-              c->lay(), nxlim, c->ny, k0, k1, c0, c1, c2);
     c->launches++;
     return 0;
 }
@@ -796,7 +785,6 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
         if (!F[i]) return 1;
     }
     if (sp->mode != 0 && sp->mode != 1) return c->fail("lesgo_gpu_step: mode must be 0 (core) or 1 (full)");
-    const size_t fb = size_t(c->plane) * (nz + 1) * sizeof(double);
     // :155-157  RHS*_f = RHS*: the two sets trade places instead of being copied (convec
     // rewrites every valid plane of RHS* below, main.f90:207-214)
     std::swap(c->fields[LG_RHSX], c->fields[LG_RHSX_F]); std::swap(F[LG_RHSX], F[LG_RHSX_F]);

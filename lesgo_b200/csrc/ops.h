@@ -236,51 +236,6 @@ static __global__ void k_fill(double* __restrict__ dst, long plane, int k0, int 
     for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) p[t] = value;
 }
 
-// Generic fused linear glue on whole planes (ld pad included, like the Fortran
-// whole-array expressions of main.f90):  mode selects the expression.
-enum GlueMode {
-    G_RHS_ASSEMBLE = 0,   // a = -a - b + c0                      main.f90:211-214,229-232
-    G_AB2 = 1,            // a = a + c0*(c1*b + c2*c)             main.f90:287-296
-    G_SUB = 2,            // a = a - b                            main.f90:321-326
-    G_COPY = 3,           // a = b
-    G_PROJECT = 4         // a = a + c0*(-c1*b)  over 1:nx only   forcing.f90:171-207
-};
-static __global__ void k_glue(int mode, double* __restrict__ a, const double* __restrict__ b,
-                       const double* __restrict__ c, Lay lay, int nxlim, int ny, int k0, int k1,
-                       double c0, double c1, double c2) {
-    const int half = lay.row / 2;
-    const long n = long(half) * ny * (k1 - k0);
-    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) {
-        int j = int(t % half);
-        long r = t / half;
-        int y = int(r % ny), k = k0 + int(r / ny);
-        if (2 * j >= nxlim) continue;
-        const long o = lay.at(k, y, 2 * j);
-        double2 va = ld2(a + o), vb = ld2(b + o), vc = make_double2(0.0, 0.0);
-        if (mode == G_AB2) vc = ld2(c + o);
-        double2 r2;
-        switch (mode) {
-            case G_RHS_ASSEMBLE:
-                r2 = make_double2(dadd(dsub(-va.x, vb.x), c0), dadd(dsub(-va.y, vb.y), c0));
-                break;
-            case G_AB2:
-                r2 = make_double2(dadd(va.x, dmul(c0, dadd(dmul(c1, vb.x), dmul(c2, vc.x)))),
-                                  dadd(va.y, dmul(c0, dadd(dmul(c1, vb.y), dmul(c2, vc.y)))));
-                break;
-            case G_SUB:
-                r2 = make_double2(dsub(va.x, vb.x), dsub(va.y, vb.y));
-                break;
-            case G_COPY:
-                r2 = vb;
-                break;
-            default:   // G_PROJECT
-                r2 = make_double2(dadd(va.x, dmul(c0, dmul(-c1, vb.x))), dadd(va.y, dmul(c0, dmul(-c1, vb.y))));
-                break;
-        }
-        *reinterpret_cast<double2*>(a + o) = r2;
-    }
-}
-
 // max |f| over 1:nx, 1:ny, planes k0..k1-1 -> atomicMax on the bit pattern (values >= 0)
 static __global__ void k_absmax(const double* __restrict__ f, Lay lay, int nx, int ny, int k0, int k1,
                          unsigned long long* __restrict__ out) {

@@ -87,34 +87,70 @@ def synthetic_slab(dims, seed=20240607):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every ~5 ms when
+    pynvml is importable, else `nvidia-smi` polling (the recipe's query line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self._stop_evt = index, threading.Event()
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(x) for x in vis.split(",") if x.strip().isdigit()]
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(ids[index] if index < len(ids) else index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                          ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                          ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                            "-i", str(self.index)], capture_output=True, text=True, timeout=5)
+        if r.returncode == 0 and r.stdout.strip():
+            row = [x.strip() for x in r.stdout.strip().split(",")]
+            self.sm.append(float(row[1])); self.mx.append(float(row[2]))
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], row[4:8]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5)
-                if r.returncode == 0 and r.stdout.strip():
-                    self.rows.append([x.strip() for x in r.stdout.strip().split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.005 if self.nvml else 0.1)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "power_w_max": max(self.power) if self.power else None,
+                "how": "pynvml, 5 ms" if self.nvml else "nvidia-smi polling"}
 
 
 def cpu_core_step_rate(nx, ny, workers, budget_s=20.0):

@@ -54,6 +54,8 @@ struct lesgo_gpu_ctx {
     double* red_host = nullptr;
     lg::Comm* comm = nullptr;
     std::vector<void*> allocs;
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host-pointer pipeline
+    void* hp_ = nullptr;                            // Staged pipeline of the API call in progress (host arrays)
     // optional per-launch timing (lesgo_gpu_profile): CUDA events around every launch
     bool prof = false;
     struct ProfRec { const char* label; cudaEvent_t a, b; };
@@ -169,12 +171,45 @@ bool is_device_ptr(const void* p) {
 #endif
 }
 
+// Host arrays are mirrored in device staging buffers.  Plain mode: whole-array H2D before, D2H after.
+// Pipelined mode (field-shaped arrays of the big routines): inputs are uploaded in plane chunks on a
+// copy stream, the compute stream waits only for the planes a pass needs (need()), and finished
+// output planes are downloaded on a second copy stream while later planes are still being computed
+// (done()), so H2D, compute and D2H overlap (PCIe is full duplex).
 struct Staged {
     lesgo_gpu_ctx* c;
-    struct Item { double* host; double* dev; size_t bytes; bool out; size_t skip; };
+    struct Item {
+        double* host; double* dev; size_t bytes; bool in, out; size_t skip;
+        std::vector<char> sent;            // pipelined: planes already downloaded
+    };
     std::vector<Item> items;
     size_t next_slot = 0;
-    explicit Staged(lesgo_gpu_ctx* c_) : c(c_) {}
+    bool pipelined = false;
+    int ch = 0;                            // planes per pipeline chunk
+    int nplanes = 0;
+    std::vector<cudaEvent_t> ev_in;        // ev_in[i]: input planes of chunk i are on the device
+    std::vector<cudaEvent_t> ev_tmp;
+    int waited = -1;                       // highest input chunk the compute stream already waits for
+    explicit Staged(lesgo_gpu_ctx* c_, bool pipe = false) : c(c_) {
+#ifndef LESGO_EMUL
+        if (pipe && !std::getenv("LESGO_NO_PIPELINE")) {
+            pipelined = true;
+            nplanes = c->nz + 1;
+            ch = nplanes > 64 ? 16 : (nplanes > 16 ? 8 : nplanes);
+            if (!c->s_in) {
+                cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+                cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+            }
+        }
+#else
+        (void)pipe;
+#endif
+    }
+    ~Staged() {
+        for (auto e : ev_in) cudaEventDestroy(e);
+        for (auto e : ev_tmp) cudaEventDestroy(e);
+        if (c->hp_ == this) c->hp_ = nullptr;
+    }
     // returns the device pointer to use for user pointer p holding `n` doubles; the first `skip`
     // doubles are never copied in either direction (arrays the reference declares 1:nz are passed
     // shifted down by one plane, so their "plane 0" is not the caller's memory)
@@ -194,12 +229,97 @@ struct Staged {
             c->staging_bytes[slot] = n * sizeof(double);
         }
         double* d = c->staging[slot];
-        if (copy_in) cudaMemcpyAsync(d + skip, p + skip, (n - skip) * sizeof(double), cudaMemcpyHostToDevice, c->stream);
-        else if (copy_out) cudaMemsetAsync(d, 0, n * sizeof(double), c->stream);   // pure output: defined pads, no H2D
-        items.push_back(Item{const_cast<double*>(p), d, n * sizeof(double), copy_out, skip});
+        if (!pipelined) {
+            if (copy_in) cudaMemcpyAsync(d + skip, p + skip, (n - skip) * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+            else if (copy_out) cudaMemsetAsync(d, 0, n * sizeof(double), c->stream);   // pure output: defined pads, no H2D
+        } else if (!copy_in && copy_out) {
+            cudaMemsetAsync(d, 0, n * sizeof(double), c->stream);
+        }
+        Item it{const_cast<double*>(p), d, n * sizeof(double), copy_in, copy_out, skip, {}};
+        if (pipelined) it.sent.assign(size_t(nplanes), 0);
+        items.push_back(it);
         return d;
     }
+    bool active() const { return pipelined && !items.empty(); }
+    // pipelined: enqueue every input, chunk by chunk, on the upload stream
+    void begin() {
+        if (!active()) return;
+        c->hp_ = this;
+        const size_t pl = size_t(c->plane);
+        const int nchunks = (nplanes + ch - 1) / ch;
+        ev_in.resize(size_t(nchunks));
+        for (int i = 0; i < nchunks; ++i) {
+            const int ka = i * ch, kb = ka + ch < nplanes ? ka + ch : nplanes;
+            for (auto& it : items) {
+                if (!it.in) continue;
+                size_t lo = size_t(ka) * pl, hi = size_t(kb) * pl;
+                if (lo < it.skip) lo = it.skip;
+                if (hi > lo) cudaMemcpyAsync(it.dev + lo, it.host + lo, (hi - lo) * sizeof(double), cudaMemcpyHostToDevice, c->s_in);
+            }
+            cudaEventCreateWithFlags(&ev_in[size_t(i)], cudaEventDisableTiming);
+            cudaEventRecord(ev_in[size_t(i)], c->s_in);
+        }
+    }
+    // the next launches on the compute stream read input planes <= kmax
+    void need(int kmax) {
+        if (!active() || ev_in.empty()) return;
+        if (kmax >= nplanes) kmax = nplanes - 1;
+        const int i = kmax / ch;
+        if (i <= waited) return;
+        cudaStreamWaitEvent(c->stream, ev_in[size_t(i)], 0);   // chunks are uploaded in order
+        waited = i;
+    }
+    void need_all() { need(nplanes - 1); }
+    // planes [pa, pb) of output array `dev` are final: download them behind the compute stream
+    void done(const double* dev, int pa, int pb) {
+        if (!active() || pb <= pa) return;
+        for (auto& it : items) {
+            if (it.dev != dev || !it.out) continue;
+            cudaEvent_t e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            cudaEventRecord(e, c->stream);
+            cudaStreamWaitEvent(c->s_out, e, 0);
+            ev_tmp.push_back(e);
+            const size_t pl = size_t(c->plane);
+            size_t lo = size_t(pa) * pl, hi = size_t(pb) * pl;
+            if (lo < it.skip) lo = it.skip;
+            if (hi > lo) cudaMemcpyAsync(it.host + lo, it.dev + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, c->s_out);
+            for (int k = pa; k < pb; ++k) it.sent[size_t(k)] = 1;
+        }
+    }
+    // planes [pa, pb) of `dev` were modified again (BOGUS fills): they must be (re)sent at the end
+    void touch(const double* dev, int pa, int pb) {
+        if (!active()) return;
+        for (auto& it : items)
+            if (it.dev == dev && it.out)
+                for (int k = pa; k < pb && k < nplanes; ++k) it.sent[size_t(k)] = 0;
+    }
     int finish() {
+        if (active()) {
+            // everything not downloaded yet goes out behind the compute stream
+            cudaStreamSynchronize(c->s_out);
+            const size_t pl = size_t(c->plane);
+            for (auto& it : items) {
+                if (!it.out) continue;
+                int k = 0;
+                while (k < nplanes) {
+                    if (it.sent[size_t(k)]) { ++k; continue; }
+                    int k1 = k;
+                    while (k1 < nplanes && !it.sent[size_t(k1)]) ++k1;
+                    size_t lo = size_t(k) * pl, hi = size_t(k1) * pl;
+                    if (lo < it.skip) lo = it.skip;
+                    if (hi > lo) cudaMemcpyAsync(it.host + lo, it.dev + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+                    k = k1;
+                }
+            }
+            cudaStreamSynchronize(c->s_in);
+            cudaError_t e = cudaStreamSynchronize(c->stream);
+            c->hp_ = nullptr;
+            if (e != cudaSuccess) return c->fail(std::string("stream sync: ") + cudaGetErrorString(e));
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return c->fail(std::string("kernel: ") + cudaGetErrorString(e));
+            return 0;
+        }
         bool any = false;
         for (auto& it : items)
             if (it.out) { cudaMemcpyAsync(it.host + it.skip, it.dev + it.skip, it.bytes - it.skip * sizeof(double), cudaMemcpyDeviceToHost, c->stream); any = true; }
@@ -212,6 +332,11 @@ struct Staged {
         return 0;
     }
 };
+
+Staged* HP(const lesgo_gpu_ctx* c) {
+    Staged* h = static_cast<Staged*>(c->hp_);
+    return (h && h->active()) ? h : nullptr;
+}
 
 // ---- pass wrappers ------------------------------------------------------------------------
 int grid1d(long n) {
@@ -306,6 +431,7 @@ int glue_fused(lesgo_gpu_ctx* c, int mode, double* rhs, const double* b, double*
 
 int fill(lesgo_gpu_ctx* c, double* f, long plane, int k0, int k1, double v) {
     if (k1 <= k0) return 0;
+    if (Staged* h = HP(c)) h->touch(f, k0, k1);
     ProfScope ps_(c, "fill");
     LG_LAUNCH(k_fill, dim3(grid1d(plane * (k1 - k0))), dim3(kBlock), 0, c->stream, f, plane, k0, k1, v);
     c->launches++;
@@ -315,6 +441,7 @@ int fill(lesgo_gpu_ctx* c, double* f, long plane, int k0, int k1, double v) {
 // ---- derivatives.f90 --------------------------------------------------------------------------
 // which: bit 0 = f itself (filt_da), bit 1 = d/dx, bit 2 = d/dy
 int chunk_of(const lesgo_gpu_ctx* c, int divisor) {
+    if (Staged* h = HP(c)) return h->ch;            // host-array pipeline: its chunking rules
     if (c->chunk <= 0) return c->nz + 1;
     int ch = c->chunk / divisor;
     return ch < 1 ? 1 : ch;
@@ -340,21 +467,31 @@ int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx
     const int ch = chunk_of(c, 1);
     for (int ka = 0; ka < nz + 1; ka += ch) {
         const int kb = ka + ch < nz + 1 ? ka + ch : nz + 1;
+        Staged* hp = HP(c);
+        if (hp) hp->need(kb - 1);
         if (xfwd(c, false, pro, 1, d0, c->plane, c->ld, c->nx / 2, c->ny, ka, kb)) return 1;
         a.k0 = ka;
         if (ypass(c, c->ny, c->ny, a, 1, ka, kb)) return 1;
         if (xinv(c, false, xs, c->plane, c->ld, c->nx / 2, n, xd, c->lay(), c->ny, ka, kb)) return 1;
+        if (hp) for (int i = 0; i < n; ++i) hp->done(xd[i], ka, kb);
     }
     return 0;
 }
 
 int ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
     const int nz = c->nz;
-    {
-        ProfScope ps_(c, "ddz");
-        LG_LAUNCH(k_ddz, dim3(grid1d(long(c->nx / 2) * c->ny * nz)), dim3(kBlock), 0, c->stream, f, dfdz, c->lay(),
-                  c->nx, c->ny, 1, nz + 1, -1, 0, 1.0 / c->d.dz);
-        c->launches++;
+    Staged* hp = HP(c);
+    const int ch = hp ? hp->ch : nz + 1;
+    for (int ka = 1; ka < nz + 1; ka += ch) {                       // dfdz(k) = (f(k) - f(k-1))/dz, k = 1..nz
+        const int kb = ka + ch < nz + 1 ? ka + ch : nz + 1;
+        if (hp) hp->need(kb - 1);
+        {
+            ProfScope ps_(c, "ddz");
+            LG_LAUNCH(k_ddz, dim3(grid1d(long(c->nx / 2) * c->ny * (kb - ka))), dim3(kBlock), 0, c->stream, f, dfdz, c->lay(),
+                      c->nx, c->ny, ka, kb, -1, 0, 1.0 / c->d.dz);
+            c->launches++;
+        }
+        if (hp) hp->done(dfdz, ka, kb);
     }
     fill(c, dfdz, c->plane, 0, 1, kBogus);                           // derivatives.f90:236-238
     if (c->bottom) fill(c, dfdz, c->plane, 1, 2, kBogus);            // :255-257
@@ -364,11 +501,18 @@ int ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
 
 int ddz_w(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
     const int nz = c->nz;
-    {
-        ProfScope ps_(c, "ddz");
-        LG_LAUNCH(k_ddz, dim3(grid1d(long(c->nx / 2) * c->ny * nz)), dim3(kBlock), 0, c->stream, f, dfdz, c->lay(),
-                  c->nx, c->ny, 0, nz, 0, 1, 1.0 / c->d.dz);
-        c->launches++;
+    Staged* hp = HP(c);
+    const int ch = hp ? hp->ch : nz + 1;
+    for (int ka = 0; ka < nz; ka += ch) {                           // dfdz(k) = (f(k+1) - f(k))/dz, k = 0..nz-1
+        const int kb = ka + ch < nz ? ka + ch : nz;
+        if (hp) hp->need(kb);
+        {
+            ProfScope ps_(c, "ddz");
+            LG_LAUNCH(k_ddz, dim3(grid1d(long(c->nx / 2) * c->ny * (kb - ka))), dim3(kBlock), 0, c->stream, f, dfdz, c->lay(),
+                      c->nx, c->ny, ka, kb, 0, 1, 1.0 / c->d.dz);
+            c->launches++;
+        }
+        if (hp) hp->done(dfdz, ka, kb);
     }
     if (c->bottom) fill(c, dfdz, c->plane, 0, 1, kBogus);            // :303-305
     fill(c, dfdz, c->plane, nz, nz + 1, kBogus);                     // :308
@@ -400,6 +544,7 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
     for (int ka = 0; ka < nz + 1; ka += ch) {
         const int kb = ka + ch < nz + 1 ? ka + ch : nz + 1;
         const int va = ka < 1 ? 1 : ka;                 // vorticity exists on planes 1..nz
+        if (Staged* hp = HP(c)) hp->need(kb);           // the wall-plane vorticity reads one plane up
         // (1) u, v, w and the vorticity to half spectra                          convec.f90:73-82, 97-158
         if (xfwd(c, false, ps, 3, c->sa, c->plane, c->ld, nxh, c->ny, ka, kb)) return 1;
         if (xfwd(c, false, pv, 3, c->sa + 3, c->plane, c->ld, nxh, c->ny, va, kb)) return 1;
@@ -429,6 +574,7 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
         }
         // (6) x inverse -> RHS
         if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, pa, pb, 1, fz)) return 1;
+        if (Staged* hp = HP(c)) for (int i = 0; i < 3; ++i) hp->done(out[i], pa, pb);
     }
     // :319-332
     fill(c, RHSx, c->plane, 0, 1, kBogus); fill(c, RHSy, c->plane, 0, 1, kBogus); fill(c, RHSz, c->plane, 0, 1, kBogus);
@@ -465,12 +611,14 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
     const int ch = chunk_of(c, 2);
     for (int ka = 1; ka < nz; ka += ch) {
         const int kb = ka + ch < nz ? ka + ch : nz;
+        if (Staged* hp = HP(c)) hp->need(kb - 1);
         if (xfwd(c, false, ps, 3, c->sa, c->plane, c->ld, nxh, c->ny, ka, kb)) return 1;
         YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, nxh, ka);
         for (int i = 0; i < 3; ++i) { a.fld[i].src = c->sa[i]; a.fld[i].out[0] = YOutSpec{c->sa[i], Y_COPY}; }
         if (ypass(c, c->ny, 0, a, 3, ka, kb)) return 1;
     }
     // boundary planes: w(nz) on the top rank, divtz at the walls                    :100-126
+    if (Staged* hp = HP(c)) hp->need_all();
     ProScale pd; pd.src[0] = divtz; pd.lay = c->lay(); pd.scale = cst;
     double* d3[1] = {c->sa[3]};
     if (c->top) {
@@ -572,9 +720,12 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
             const int kb = ka + ch < nz + 1 ? ka + ch : nz + 1;
             a.k0 = ka;
             if (ypass(c, 0, c->ny, a, 1, ka, kb)) return 1;
+            Staged* hp = HP(c);
             if (xinv(c, false, s0, c->plane, c->ld, nxh, 1, o0, c->lay(), c->ny, ka, kb < pend ? kb : pend)) return 1;
+            if (hp) hp->done(p, ka, kb < pend ? kb : pend);
             const int da = ka < 1 ? 1 : ka, db = kb < nz ? kb : nz;
             if (xinv(c, false, s1, c->plane, c->ld, nxh, 2, o1, c->lay(), c->ny, da, db, 1, fz)) return 1;
+            if (hp) { hp->done(dpdx, da, db); hp->done(dpdy, da, db); }
             const int za = ka < 1 ? 1 : ka, zb = kb < pend ? kb : pend;
             if (zb > za) {
                 ProfScope ps_(c, "dpdz");
@@ -582,6 +733,7 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
                           c->nx, c->ny, za, zb, c->d.dz, fz ? fz->rhsz : nullptr, fz ? fz->w : nullptr,
                           fz ? fz->kproj : 0, fz ? fz->kproj_end : 0, fz ? fz->dt : 0.0, fz ? fz->t1 : 0.0);
                 c->launches++;
+                if (hp) hp->done(dpdz, za, zb);
             }
         }
     }
@@ -923,6 +1075,7 @@ int lesgo_gpu_destroy(lesgo_gpu_ctx* c) {
     for (void* p : c->allocs) cudaFree(p);
     for (double* p : c->staging) if (p) cudaFree(p);
     if (c->red_host) cudaFreeHost(c->red_host);
+    if (c->s_in) { cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out); }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -999,11 +1152,12 @@ int lesgo_gpu_wavenumbers(lesgo_gpu_ctx* c, double* kx, double* ky, double* k2) 
 int lesgo_gpu_filt_da(lesgo_gpu_ctx* c, double* f, double* dfdx, double* dfdy) {
     ENTER(c);
     if (!c || !f || !dfdx || !dfdy) return 1;
-    Staged st(c);
+    Staged st(c, true);
     double* df = st.in(f, NFIELD, true, true);
     double* dx = st.in(dfdx, NFIELD, false, true);
     double* dy = st.in(dfdy, NFIELD, false, true);
     if (!df || !dx || !dy) return 1;
+    st.begin();
     if (spectral_deriv(c, df, df, dx, dy)) return 1;
     return st.finish();
 }
@@ -1011,10 +1165,11 @@ int lesgo_gpu_filt_da(lesgo_gpu_ctx* c, double* f, double* dfdx, double* dfdy) {
 int lesgo_gpu_ddx(lesgo_gpu_ctx* c, const double* f, double* dfdx) {
     ENTER(c);
     if (!c || !f || !dfdx) return 1;
-    Staged st(c);
+    Staged st(c, true);
     double* df = st.in(f, NFIELD, true, false);
     double* dx = st.in(dfdx, NFIELD, false, true);
     if (!df || !dx) return 1;
+    st.begin();
     if (spectral_deriv(c, df, nullptr, dx, nullptr)) return 1;
     return st.finish();
 }
@@ -1022,10 +1177,11 @@ int lesgo_gpu_ddx(lesgo_gpu_ctx* c, const double* f, double* dfdx) {
 int lesgo_gpu_ddy(lesgo_gpu_ctx* c, const double* f, double* dfdy) {
     ENTER(c);
     if (!c || !f || !dfdy) return 1;
-    Staged st(c);
+    Staged st(c, true);
     double* df = st.in(f, NFIELD, true, false);
     double* dy = st.in(dfdy, NFIELD, false, true);
     if (!df || !dy) return 1;
+    st.begin();
     if (spectral_deriv(c, df, nullptr, nullptr, dy)) return 1;
     return st.finish();
 }
@@ -1033,11 +1189,12 @@ int lesgo_gpu_ddy(lesgo_gpu_ctx* c, const double* f, double* dfdy) {
 int lesgo_gpu_ddxy(lesgo_gpu_ctx* c, const double* f, double* dfdx, double* dfdy) {
     ENTER(c);
     if (!c || !f || !dfdx || !dfdy) return 1;
-    Staged st(c);
+    Staged st(c, true);
     double* df = st.in(f, NFIELD, true, false);
     double* dx = st.in(dfdx, NFIELD, false, true);
     double* dy = st.in(dfdy, NFIELD, false, true);
     if (!df || !dx || !dy) return 1;
+    st.begin();
     if (spectral_deriv(c, df, nullptr, dx, dy)) return 1;
     return st.finish();
 }
@@ -1045,10 +1202,11 @@ int lesgo_gpu_ddxy(lesgo_gpu_ctx* c, const double* f, double* dfdx, double* dfdy
 int lesgo_gpu_ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
     ENTER(c);
     if (!c || !f || !dfdz) return 1;
-    Staged st(c);
+    Staged st(c, true);
     double* df = st.in(f, NFIELD, true, false);
     double* dz = st.in(dfdz, NFIELD, false, true);
     if (!df || !dz) return 1;
+    st.begin();
     if (ddz_uv(c, df, dz)) return 1;
     return st.finish();
 }
@@ -1056,10 +1214,11 @@ int lesgo_gpu_ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
 int lesgo_gpu_ddz_w(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
     ENTER(c);
     if (!c || !f || !dfdz) return 1;
-    Staged st(c);
+    Staged st(c, true);
     double* df = st.in(f, NFIELD, true, false);
     double* dz = st.in(dfdz, NFIELD, false, true);
     if (!df || !dz) return 1;
+    st.begin();
     if (ddz_w(c, df, dz)) return 1;
     return st.finish();
 }
@@ -1069,7 +1228,7 @@ int lesgo_gpu_convec(lesgo_gpu_ctx* c, const double* u, const double* v, const d
                      const double* dwdy, double* RHSx, double* RHSy, double* RHSz) {
     ENTER(c);
     if (!c) return 1;
-    Staged st(c);
+    Staged st(c, true);
     const double* in[9] = {u, v, w, dudy, dudz, dvdx, dvdz, dwdx, dwdy};
     double* din[9];
     for (int i = 0; i < 9; ++i) {
@@ -1081,6 +1240,7 @@ int lesgo_gpu_convec(lesgo_gpu_ctx* c, const double* u, const double* v, const d
     double* oy = st.in(RHSy, NFIELD, false, true);
     double* oz = st.in(RHSz, NFIELD, false, true);
     if (!ox || !oy || !oz) return c->fail("convec: null output");
+    st.begin();
     if (convec(c, din[0], din[1], din[2], din[3], din[4], din[5], din[6], din[7], din[8], ox, oy, oz)) return 1;
     return st.finish();
 }
@@ -1090,7 +1250,7 @@ int lesgo_gpu_press_stag_array(lesgo_gpu_ctx* c, const double* u, const double* 
                                double* dpdy, double* dpdz) {
     ENTER(c);
     if (!c || !u || !v || !w || !divtz || !p || !dpdx || !dpdy || !dpdz) return 1;
-    Staged st(c);
+    Staged st(c, true);
     double* du = st.in(u, NFIELD, true, false);
     double* dv = st.in(v, NFIELD, true, false);
     double* dw = st.in(w, NFIELD, true, false);
@@ -1101,6 +1261,7 @@ int lesgo_gpu_press_stag_array(lesgo_gpu_ctx* c, const double* u, const double* 
     double* oy = st.in(dpdy, NFIELD, false, true, size_t(c->plane));
     double* oz = st.in(dpdz, NFIELD, false, true, size_t(c->plane));
     if (!du || !dv || !dw || !dd || !op || !ox || !oy || !oz) return 1;
+    st.begin();
     if (press(c, du, dv, dw, dd, dt, tadv1, op, ox, oy, oz)) return 1;
     return st.finish();
 }

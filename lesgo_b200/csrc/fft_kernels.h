@@ -282,12 +282,15 @@ template <int NIN, int NOUT, bool MULTI> struct YCfg {
     static constexpr int TC = max2(thr<NIN>(4), thr<NOUT>(4)) <= 512 ? 4 : 2;   // (2 columns for the 768 passes: 30.8 ms)
     static constexpr int NTHR = ((max2(thr<NIN>(TC), thr<NOUT>(TC)) + 31) / 32) * 32;
     static constexpr int regs = max2(TileGeom<(NIN > 0 ? NIN : 8)>::regs * (NIN > 0), TileGeom<(NOUT > 0 ? NOUT : 8)>::regs * (NOUT > 0));
-    static constexpr int MINB = TileGeom<8>::blocks_for(NTHR, regs);
     static constexpr int SL = SmemLen<NMAX>::value;
     static constexpr int NBUF = MULTI ? 2 : 1;
     static constexpr int TWI = PlanInfo<(NIN > 0 ? NIN : 8)>::twlen * (NIN > 0);
     static constexpr int TWO = PlanInfo<(NOUT > 0 ? NOUT : 8)>::twlen * (NOUT > 0);
     static constexpr size_t smem = size_t(NBUF * TC * SL + TWI + TWO) * sizeof(cplx);
+    // resident blocks: the register budget is only capped as far as shared memory lets blocks fit
+    static constexpr int by_regs = TileGeom<8>::blocks_for(NTHR, regs);
+    static constexpr int by_smem = int((227 * 1024) / (smem + 1024)) < 1 ? 1 : int((227 * 1024) / (smem + 1024));
+    static constexpr int MINB = by_regs < by_smem ? by_regs : by_smem;
 };
 
 // NIN  > 0: forward transform of length NIN first (input is the x-pass intermediate)

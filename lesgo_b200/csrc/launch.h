@@ -11,6 +11,9 @@ int launch_xfwd(int NX, const Pro& pro, int nfields, const XfOut& out, int ny, i
                 const cplx* W, const cplx* Wh, cudaStream_t s);
 int launch_xinv(int NX, const XiSrc& in, const EpiStore& epi, int nfields, int ny, int k0, int nplanes,
                 const cplx* W, const cplx* Wh, cudaStream_t s);
+// small-grid lengths only (the fused time-stepping epilogues of lesgo_gpu_step)
+int launch_xinv_fused(int NX, const XiSrc& in, const EpiFused& epi, int nfields, int ny, int k0, int nplanes,
+                      const cplx* W, const cplx* Wh, cudaStream_t s);
 int launch_ypass(int nin, int nout, const YArgs& a, int nfields, int nplanes, const cplx* Win,
                  const cplx* Wout, cudaStream_t s);
 bool size_supported(int n_small);

@@ -379,19 +379,26 @@ struct Fuse {
 int xinv(lesgo_gpu_ctx* c, bool bigx, const double* const* src, long splane, int srow, int ncol, int nf,
          double* const* dst, const Lay& dl, int nyrows, int k0, int k1, int pad = 1, const Fuse* fz = nullptr) {
     XiSrc in;
-    EpiStore epi;
-    std::memset(&epi, 0, sizeof(epi));
-    for (int i = 0; i < nf; ++i) { in.src[i] = src[i]; epi.dst[i] = dst[i]; }
+    for (int i = 0; i < nf; ++i) in.src[i] = src[i];
     in.plane = splane; in.row = srow; in.ncol = ncol;
-    epi.lay = dl; epi.nx = bigx ? c->nx2 : c->nx; epi.pad = pad;
-    if (fz && fz->mode) {
-        epi.mode = fz->mode; epi.first_step = fz->first_step; epi.dt = fz->dt; epi.t1 = fz->t1; epi.t2 = fz->t2;
-        for (int i = 0; i < 3; ++i) { epi.divt[i] = fz->divt[i]; epi.rhs_f[i] = fz->rhs_f[i]; epi.u[i] = fz->u[i]; epi.force[i] = fz->force[i]; epi.kmax[i] = fz->kmax[i]; }
-    }
     if (k1 <= k0) return 0;
     ProfScope ps_(c, bigx ? "xinv_big" : "xinv");
-    int rc = launch_xinv(bigx ? c->nx2 : c->nx, in, epi, nf, nyrows, k0, k1 - k0,
+    int rc;
+    if (fz && fz->mode && !bigx) {
+        EpiFused epi;
+        std::memset(&epi, 0, sizeof(epi));
+        for (int i = 0; i < nf; ++i) epi.dst[i] = dst[i];
+        epi.lay = dl; epi.nx = c->nx; epi.pad = pad;
+        epi.mode = fz->mode; epi.first_step = fz->first_step; epi.dt = fz->dt; epi.t1 = fz->t1; epi.t2 = fz->t2;
+        for (int i = 0; i < 3; ++i) { epi.divt[i] = fz->divt[i]; epi.rhs_f[i] = fz->rhs_f[i]; epi.u[i] = fz->u[i]; epi.force[i] = fz->force[i]; epi.kmax[i] = fz->kmax[i]; }
+        rc = launch_xinv_fused(c->nx, in, epi, nf, nyrows, k0, k1 - k0, c->Wx, c->Whx, c->stream);
+    } else {
+        EpiStore epi;
+        for (int i = 0; i < nf; ++i) epi.dst[i] = dst[i];
+        epi.lay = dl; epi.nx = bigx ? c->nx2 : c->nx; epi.pad = pad;
+        rc = launch_xinv(bigx ? c->nx2 : c->nx, in, epi, nf, nyrows, k0, k1 - k0,
                          bigx ? c->Wxb : c->Wx, bigx ? c->Whxb : c->Whx, c->stream);
+    }
     if (rc) return c->fail("unsupported nx for x-inverse pass");
     c->launches++;
     return 0;

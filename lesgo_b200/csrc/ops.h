@@ -123,18 +123,33 @@ struct ProConvec {
     }
 };
 
-// ---- x-inverse epilogue ------------------------------------------------------------
-// mode 0: plain store.
+// ---- x-inverse epilogues ------------------------------------------------------------
+// plain store (every routine-level entry point)
+struct EpiStore {
+    double* dst[kMaxFields];
+    Lay lay;
+    int nx;          // real row length; the two pad reals are zeroed when pad != 0
+    int pad;
+    LG_D void store(int fld, int k, int y, int j, double2 v) const {
+        *reinterpret_cast<double2*>(dst[fld] + lay.at(k, y, 2 * j)) = v;
+    }
+    LG_D void finish_row(int fld, int k, int y) const {
+        if (pad) *reinterpret_cast<double2*>(dst[fld] + lay.at(k, y, nx)) = make_double2(0.0, 0.0);
+    }
+};
+
+// store + time-stepping glue, used by lesgo_gpu_step only (a separate type so the plain epilogue
+// stays lean: the extra state cost 0.5 ms in the 3/2-grid x-inverse when it lived in EpiStore).
 // mode 1: the value is the convective term cc; fuses the RHS assembly, the Euler start and the
 //         AB2 update (main.f90:211-214, 229-232, 273-280, 287-296):
 //             rhs = -cc - divt + force;  [first step: rhs_f = rhs];  u += dt*(tadv1*rhs + tadv2*rhs_f)
 //         on planes k <= kmax[fld] (the other planes just get the plain store).
 // mode 2: the value is a pressure-gradient component; fuses main.f90:321-326 and project
 //         (forcing.f90:171-207):  dpd = value;  rhs -= value;  u += dt*(-tadv1*value)
-struct EpiStore {
+struct EpiFused {
     double* dst[kMaxFields];
     Lay lay;
-    int nx;          // real row length; the two pad reals are zeroed when pad != 0
+    int nx;
     int pad;
     int mode;
     const double* divt[3];

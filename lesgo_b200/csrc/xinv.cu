@@ -1,16 +1,16 @@
 #include "launch.h"
 #include "sizes.h"
 namespace lg {
-template <int NX>
-static int launch_xinv_n(const XiSrc& in, const EpiStore& epi, int nfields, int ny, int k0, int nplanes,
+template <int NX, class Epi = EpiStore>
+static int launch_xinv_n(const XiSrc& in, const Epi& epi, int nfields, int ny, int k0, int nplanes,
                          const cplx* W, const cplx* Wh, cudaStream_t s) {
     typedef XCfg<NX> C;
     static bool attr = false;
-    if (!attr) { set_smem(k_xinv<NX, EpiStore>, C::smem); attr = true; }
+    if (!attr) { set_smem(k_xinv<NX, Epi>, C::smem); attr = true; }
     const long nrows = long(ny) * nplanes;
     if (nrows <= 0) return 0;
     dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, C::MINB));
-    LG_LAUNCH((k_xinv<NX, EpiStore>), grid, dim3(C::NTHR), C::smem, s, in, epi, nfields, 0, ny, k0, nplanes, W, Wh);
+    LG_LAUNCH((k_xinv<NX, Epi>), grid, dim3(C::NTHR), C::smem, s, in, epi, nfields, 0, ny, k0, nplanes, W, Wh);
     return 0;
 }
 #define LG_XINV_CASE_SMALL(S, B) case S: return launch_xinv_n<S>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
@@ -29,6 +29,12 @@ int launch_xinv(int NX, const XiSrc& in, const EpiStore& epi, int nfields, int n
         case 768: return launch_xinv_n<768>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
         case 1536: return launch_xinv_n<1536>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
     }
+    return -1;
+}
+#define LG_XINVF_CASE(S, B) case S: return launch_xinv_n<S, EpiFused>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+int launch_xinv_fused(int NX, const XiSrc& in, const EpiFused& epi, int nfields, int ny, int k0, int nplanes,
+                      const cplx* W, const cplx* Wh, cudaStream_t s) {
+    switch (NX) { LG_SIZE_PAIRS(LG_XINVF_CASE) }
     return -1;
 }
 }  // namespace lg

@@ -2,6 +2,7 @@
 // the many template instantiations compile in parallel).
 #pragma once
 #include "ops.h"
+#include "wfft_kernels.h"
 
 namespace lg {
 
@@ -26,6 +27,8 @@ template <class K> inline void set_smem(K kernel, size_t bytes) {
 
 // persistent grids: blocks per SM that fit (shared memory / 64-register budget), times SMs
 int sm_count();
+// warp-scope x passes (wfft_kernels.h) unless LESGO_XW=0 selects the block-cooperative round-1 kernels
+bool warp_passes();
 inline int persistent_blocks(size_t smem_bytes, long ntiles, int max_per_sm) {
     int per_sm = int((227 * 1024) / (smem_bytes + 1024));
     if (per_sm > max_per_sm) per_sm = max_per_sm;

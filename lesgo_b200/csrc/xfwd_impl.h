@@ -10,10 +10,19 @@ template <int NX, class Pro>
 static int launch_xfwd_n(const Pro& pro, int nfields, const XfOut& out, int ny, int k0, int nplanes,
                          const cplx* W, const cplx* Wh, cudaStream_t s) {
     typedef XCfg<NX> C;
-    static bool attr = false;
-    if (!attr) { set_smem(k_xfwd<NX, Pro>, C::smem); attr = true; }
     const long nrows = long(ny) * nplanes;
     if (nrows <= 0) return 0;
+    if (warp_passes()) {
+        typedef XWCfg<NX> CW;
+        static bool attr_w = false;
+        if (!attr_w) { set_smem(k_xfwd_w<NX, Pro>, CW::smem); attr_w = true; }
+        const long nwork = ((nrows + CW::NF - 1) / CW::NF) * nfields;
+        dim3 grid(persistent_blocks(CW::smem, (nwork + CW::WPB - 1) / CW::WPB, CW::MINB));
+        LG_LAUNCH((k_xfwd_w<NX, Pro>), grid, dim3(CW::NTHR), CW::smem, s, pro, out, nfields, ny, k0, nplanes, W, Wh);
+        return 0;
+    }
+    static bool attr = false;
+    if (!attr) { set_smem(k_xfwd<NX, Pro>, C::smem); attr = true; }
     dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, C::MINB));
     LG_LAUNCH((k_xfwd<NX, Pro>), grid, dim3(C::NTHR), C::smem, s, pro, out, nfields, int(zmajor_for<Pro>() && ny % C::NF == 0), ny, k0, nplanes, W, Wh);
     return 0;

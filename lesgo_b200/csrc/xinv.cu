@@ -5,10 +5,19 @@ template <int NX, class Epi = EpiStore>
 static int launch_xinv_n(const XiSrc& in, const Epi& epi, int nfields, int ny, int k0, int nplanes,
                          const cplx* W, const cplx* Wh, cudaStream_t s) {
     typedef XCfg<NX> C;
-    static bool attr = false;
-    if (!attr) { set_smem(k_xinv<NX, Epi>, C::smem); attr = true; }
     const long nrows = long(ny) * nplanes;
     if (nrows <= 0) return 0;
+    if (warp_passes()) {
+        typedef XWCfg<NX> CW;
+        static bool attr_w = false;
+        if (!attr_w) { set_smem(k_xinv_w<NX, Epi>, CW::smem); attr_w = true; }
+        const long nwork = ((nrows + CW::NF - 1) / CW::NF) * nfields;
+        dim3 grid(persistent_blocks(CW::smem, (nwork + CW::WPB - 1) / CW::WPB, CW::MINB));
+        LG_LAUNCH((k_xinv_w<NX, Epi>), grid, dim3(CW::NTHR), CW::smem, s, in, epi, nfields, ny, k0, nplanes, W, Wh);
+        return 0;
+    }
+    static bool attr = false;
+    if (!attr) { set_smem(k_xinv<NX, Epi>, C::smem); attr = true; }
     dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, C::MINB));
     LG_LAUNCH((k_xinv<NX, Epi>), grid, dim3(C::NTHR), C::smem, s, in, epi, nfields, 0, ny, k0, nplanes, W, Wh);
     return 0;

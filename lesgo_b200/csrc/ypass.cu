@@ -1,3 +1,4 @@
+#include <cstdlib>
 #include "launch.h"
 #include "sizes.h"
 namespace lg {
@@ -71,6 +72,11 @@ int sm_count() {
 #endif
     }
     return n;
+}
+bool warp_passes() {
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("LESGO_XW"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
 }
 bool size_supported(int n) {
     LG_SIZE_PAIRS(LG_SUP)

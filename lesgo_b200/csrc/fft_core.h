@@ -301,7 +301,10 @@ constexpr int kBlock = 256;     // threads per block of the pointwise kernels
 // size that lets every stage finish in one such pass.
 template <int N> struct TileGeom {
     typedef Plan<N> P;
-    static constexpr int RCAP = PlanInfo<N>::rmax;
+#ifndef LG_RCAP_MUL
+#define LG_RCAP_MUL 1
+#endif
+    static constexpr int RCAP = PlanInfo<N>::rmax * LG_RCAP_MUL;
     static constexpr int need(int nf, int r) { return r == 1 ? 0 : (nf * (N / r) + (RCAP / r) - 1) / (RCAP / r); }
     static constexpr int max2(int a, int b) { return a > b ? a : b; }
     static constexpr int threads(int nf) {
@@ -312,6 +315,7 @@ template <int N> struct TileGeom {
     static constexpr bool pow2(int r) { return r == 1 || r == 2 || r == 4 || r == 8 || r == 16; }
     static constexpr bool pure2 = pow2(P::R1) && pow2(P::R2) && pow2(P::R3) && pow2(P::R4);
     static constexpr int regs = RCAP <= 8 ? 64 : (RCAP <= 12 ? 80 : 128);   // 51 (5 blocks/SM) measured slower
+    // (LG_RCAP_MUL = 2, two butterflies per thread and half the threads: measured in profiles/r2_experiments.md)
     static constexpr int min_blocks(int nthr) { return blocks_for(nthr, regs); }
     // at least two resident blocks for blocks of <= 512 threads, at most 16
     static constexpr int blocks_for(int nthr, int r) {

@@ -31,7 +31,19 @@ struct XfOut {
     int row;                   // doubles between rows
     int ncol;                  // complex columns to write (<= nx/2); column ncol gets
     int write_nyq;             //   0: nothing, 1: zero, 2: the true Nyquist value
+    int ring;                  // > 0: dst holds only `ring` planes, plane k lives in slot k % ring
 };
+
+// plane offset of a (possibly ring-buffered) intermediate array
+LG_HD long poff(int k, long plane, int ring) { return long(ring > 0 ? k % ring : k) * plane; }
+
+// spectral intermediates are read once and may have been written by another SM moments ago
+// (plane pipeline, pipe_kernels.h): read them through L2 only
+#ifdef LESGO_EMUL
+LG_HD cplx ld_cg(const double* p) { return *reinterpret_cast<const cplx*>(p); }
+#else
+LG_D cplx ld_cg(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+#endif
 
 template <int NX> struct XCfg {
     static constexpr int M = NX / 2;
@@ -48,32 +60,15 @@ template <int NX> struct XCfg {
     static constexpr size_t smem = size_t(NF * SL + TWL + NWH) * sizeof(cplx);
 };
 
-// Pro: struct with  LG_D double2 load(int fld, int k, int y, int j) const
-//      returning (x[2j], x[2j+1]) of row y of plane k of field fld (already scaled).
-// Persistent blocks: each block loops over row tiles, twiddles live in shared memory.
+// one work item (tile of NF rows of one field) of the x-forward pass; every thread of the
+// NTHR-thread block calls it; ends with a barrier
 template <int NX, class Pro>
-__global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
-k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int nfields, int zmajor, int ny, int k0, int nplanes,
-       const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
+LG_D void xfwd_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y, const Pro& pro, const XfOut& out,
+                    int nfields, int ny, int k0, int nplanes, long work) {
     typedef XCfg<NX> C;
     constexpr int M = C::M, NF = C::NF, SL = C::SL, NTHR = C::NTHR;
-    LG_DYN_SMEM(cplx, sm);
-    cplx* buf = sm;
-    cplx* W = sm + NF * SL;
-    cplx* Wh = W + C::TWL;
-    __shared__ int s_k[NF], s_y[NF];
-    load_table(W, Wg, C::TWL);
-    load_table(Wh, Whg, C::NWH);
     const long nrows = long(ny) * nplanes;
-    const long ntiles = (nrows + NF - 1) / NF;
-    // Work items are dealt round-robin with the field index fastest: blocks resident together
-    // work on neighbouring rows of all fields, so inputs the fields share (the u x omega
-    // products) are read from DRAM once and concurrent blocks touch adjacent DRAM pages.
-    // (Measured alternative, profiles/r1_work_order.md: a contiguous range per block, optionally
-    // walking up z, was 25 % slower.)
-    (void)zmajor;
-    const long nwork = ntiles * nfields;
-    for (long work = blockIdx.x; work < nwork; work += gridDim.x) {
+    {
         const int fld = int(work % nfields);
         const long row0 = (work / nfields) * NF;
         for (int f = threadIdx.x; f < NF; f += NTHR) {
@@ -101,7 +96,7 @@ k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int n
             const int m = 1 + it % NP, f = it / NP;
             const int k = s_k[f];
             if (k < 0) continue;
-            double* drow = out.dst[fld] + long(k) * out.plane + long(s_y[f]) * out.row;
+            double* drow = out.dst[fld] + poff(k, out.plane, out.ring) + long(s_y[f]) * out.row;
             cplx a = buf[f * SL + spad(m)];
             cplx bz = buf[f * SL + spad(M - m)];
             cplx b = make_double2(bz.x, -bz.y);
@@ -117,7 +112,7 @@ k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int n
         for (int f = threadIdx.x; f < 2 * NF; f += NTHR) {
             const int ff = f >> 1, k = s_k[ff];
             if (k < 0) continue;
-            double* drow = out.dst[fld] + long(k) * out.plane + long(s_y[ff]) * out.row;
+            double* drow = out.dst[fld] + poff(k, out.plane, out.ring) + long(s_y[ff]) * out.row;
             if (f & 1) {
                 cplx a = buf[ff * SL + spad(M / 2)];
                 if (M / 2 < out.ncol) *reinterpret_cast<cplx*>(drow + M) = make_double2(a.x, -a.y);
@@ -134,6 +129,34 @@ k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int n
     }
 }
 
+// Pro: struct with  LG_D double2 load(int fld, int k, int y, int j) const
+//      returning (x[2j], x[2j+1]) of row y of plane k of field fld (already scaled).
+// Persistent blocks: each block loops over row tiles, twiddles live in shared memory.
+template <int NX, class Pro>
+__global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
+k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int nfields, int zmajor, int ny, int k0, int nplanes,
+       const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
+    typedef XCfg<NX> C;
+    constexpr int NF = C::NF, SL = C::SL;
+    LG_DYN_SMEM(cplx, sm);
+    cplx* buf = sm;
+    cplx* W = sm + NF * SL;
+    cplx* Wh = W + C::TWL;
+    __shared__ int s_k[NF], s_y[NF];
+    load_table(W, Wg, C::TWL);
+    load_table(Wh, Whg, C::NWH);
+    // Work items are dealt round-robin with the field index fastest: blocks resident together
+    // work on neighbouring rows of all fields, so inputs the fields share (the u x omega
+    // products) are read from DRAM once and concurrent blocks touch adjacent DRAM pages.
+    // (Measured alternative, profiles/r1_work_order.md: a contiguous range per block, optionally
+    // walking up z, was 25 % slower.)
+    (void)zmajor;
+    const long nrows = long(ny) * nplanes;
+    const long nwork = ((nrows + NF - 1) / NF) * nfields;
+    for (long work = blockIdx.x; work < nwork; work += gridDim.x)
+        xfwd_work<NX, Pro>(buf, W, Wh, s_k, s_y, pro, out, nfields, ny, k0, nplanes, work);
+}
+
 // ---------------------------------------------------------------------------------
 // x inverse:  half spectrum rows -> real rows
 // ---------------------------------------------------------------------------------
@@ -143,33 +166,17 @@ struct XiSrc {
     int row;
     int ncol;      // stored complex columns carrying data; columns >= ncol read as 0.
                    // ncol > nx/2 means the Nyquist column is present too.
+    int ring;      // > 0: src is a ring of `ring` planes
 };
 
-// Epi: struct with  LG_D void store(int fld, int k, int y, int j, double2 v) const
-//      receiving (x[2j], x[2j+1]);   LG_D void finish_row(int fld, int k, int y) const
+// one work item of the x-inverse pass (see xfwd_work)
 template <int NX, class Epi>
-__global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
-k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nfields, int zmajor, int ny, int k0, int nplanes,
-       const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
+LG_D void xinv_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y, const XiSrc& in, const Epi& epi,
+                    int nfields, int ny, int k0, int nplanes, long work) {
     typedef XCfg<NX> C;
     constexpr int M = C::M, NF = C::NF, SL = C::SL, NTHR = C::NTHR;
-    LG_DYN_SMEM(cplx, sm);
-    cplx* buf = sm;
-    cplx* W = sm + NF * SL;
-    cplx* Wh = W + C::TWL;
-    __shared__ int s_k[NF], s_y[NF];
-    load_table(W, Wg, C::TWL);
-    load_table(Wh, Whg, C::NWH);
     const long nrows = long(ny) * nplanes;
-    const long ntiles = (nrows + NF - 1) / NF;
-    // Work items are dealt round-robin with the field index fastest: blocks resident together
-    // work on neighbouring rows of all fields, so inputs the fields share (the u x omega
-    // products) are read from DRAM once and concurrent blocks touch adjacent DRAM pages.
-    // (Measured alternative, profiles/r1_work_order.md: a contiguous range per block, optionally
-    // walking up z, was 25 % slower.)
-    (void)zmajor;
-    const long nwork = ntiles * nfields;
-    for (long work = blockIdx.x; work < nwork; work += gridDim.x) {
+    {
         const int fld = int(work % nfields);
         const long row0 = (work / nfields) * NF;
         for (int f = threadIdx.x; f < NF; f += NTHR) {
@@ -193,9 +200,9 @@ k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nf
                 if (it < NF * NP) {
                     const int m = 1 + it % NP, f = it / NP;
                     if (s_k[f] >= 0) {
-                        const double* srow = in.src[fld] + long(s_k[f]) * in.plane + long(s_y[f]) * in.row;
-                        if (m < in.ncol) va[u] = *reinterpret_cast<const cplx*>(srow + 2 * m);
-                        if (M - m < in.ncol) vb[u] = *reinterpret_cast<const cplx*>(srow + 2 * (M - m));
+                        const double* srow = in.src[fld] + poff(s_k[f], in.plane, in.ring) + long(s_y[f]) * in.row;
+                        if (m < in.ncol) va[u] = ld_cg(srow + 2 * m);
+                        if (M - m < in.ncol) vb[u] = ld_cg(srow + 2 * (M - m));
                     }
                 }
             }
@@ -216,12 +223,12 @@ k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nf
             const int ff = f >> 1;
             cplx z = make_double2(0.0, 0.0);
             if (s_k[ff] >= 0) {
-                const double* srow = in.src[fld] + long(s_k[ff]) * in.plane + long(s_y[ff]) * in.row;
+                const double* srow = in.src[fld] + poff(s_k[ff], in.plane, in.ring) + long(s_y[ff]) * in.row;
                 if (f & 1) {                                  // m = M/2: Z' = 2 conj(X_{M/2})
-                    if (M / 2 < in.ncol) { cplx a = *reinterpret_cast<const cplx*>(srow + M); z = make_double2(2.0 * a.x, -2.0 * a.y); }
+                    if (M / 2 < in.ncol) { cplx a = ld_cg(srow + M); z = make_double2(2.0 * a.x, -2.0 * a.y); }
                 } else {                                      // m = 0: real parts of X_0 and X_M only
-                    double x0 = in.ncol > 0 ? srow[0] : 0.0;
-                    double xm = in.ncol > M ? srow[2 * M] : 0.0;
+                    double x0 = in.ncol > 0 ? ld_cg(srow).x : 0.0;
+                    double xm = in.ncol > M ? ld_cg(srow + 2 * M).x : 0.0;
                     z = make_double2(x0 + xm, x0 - xm);
                 }
             }
@@ -244,6 +251,28 @@ k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nf
     }
 }
 
+// Epi: struct with  LG_D void store(int fld, int k, int y, int j, double2 v) const
+//      receiving (x[2j], x[2j+1]);   LG_D void finish_row(int fld, int k, int y) const
+template <int NX, class Epi>
+__global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
+k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nfields, int zmajor, int ny, int k0, int nplanes,
+       const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
+    typedef XCfg<NX> C;
+    constexpr int NF = C::NF, SL = C::SL;
+    LG_DYN_SMEM(cplx, sm);
+    cplx* buf = sm;
+    cplx* W = sm + NF * SL;
+    cplx* Wh = W + C::TWL;
+    __shared__ int s_k[NF], s_y[NF];
+    load_table(W, Wg, C::TWL);
+    load_table(Wh, Whg, C::NWH);
+    (void)zmajor;   // round-robin work order, field index fastest: see k_xfwd
+    const long nrows = long(ny) * nplanes;
+    const long nwork = ((nrows + NF - 1) / NF) * nfields;
+    for (long work = blockIdx.x; work < nwork; work += gridDim.x)
+        xinv_work<NX, Epi>(buf, W, Wh, s_k, s_y, in, epi, nfields, ny, k0, nplanes, work);
+}
+
 // ---------------------------------------------------------------------------------
 // y pass
 // ---------------------------------------------------------------------------------
@@ -256,6 +285,13 @@ struct YOutSpec {
 struct YField {
     const double* src;
     YOutSpec out[3];
+    // optional linear combination formed while loading (spectral reuse in lesgo_gpu_step, where the
+    // vorticity's x spectra are combinations of x spectra filt_da already produced):
+    //     in(k) = c0 * src(k) + c1 * (src2(k) - src2(k-1)) + c2 * src3(k)
+    int combo;               // 0: in(k) = src(k)
+    const double* src2;
+    const double* src3;
+    double c0, c1, c2;
 };
 struct YArgs {
     YField fld[kMaxFields];
@@ -269,6 +305,7 @@ struct YArgs {
     int table_row;
     int zero_col;        // >= 0: also write zeros into this complex column of every output row
     int keep_nyq_row;    // 1: raw transform (do not zero ky = ns/2)
+    int src_ring, dst_ring;   // > 0: src / dst are rings of that many planes
 };
 
 // MULTI = several outputs per field: the spectrum is kept in its own buffer S while the
@@ -297,39 +334,52 @@ template <int NIN, int NOUT, bool MULTI> struct YCfg {
 // NOUT > 0: inverse transform(s) of length NOUT last (output feeds the x inverse pass)
 // NIN == NOUT: derivative / filter operators;  NIN < NOUT: padd;  NIN > NOUT: unpadd.
 // Persistent blocks over (column tile, plane) pairs; blockIdx.y = field.
+// element (row i, column f of the tile) of the y pass input, with the optional combination
+LG_D cplx y_input(const YField& F, const YArgs& a, const double* src, int k, int c0col, int i, int f) {
+    const long off = long(i) * a.src_row + 2 * f;
+    cplx v = ld_cg(src + off);
+    if (F.combo) {
+        v = make_double2(F.c0 * v.x, F.c0 * v.y);
+        if (F.src2) {
+            const double* s2 = F.src2 + poff(k, a.src_plane, a.src_ring) + 2 * c0col + off;
+            const double* s2m = F.src2 + poff(k - 1, a.src_plane, a.src_ring) + 2 * c0col + off;
+            const cplx b = ld_cg(s2), bm = ld_cg(s2m);
+            v.x += F.c1 * (b.x - bm.x);
+            v.y += F.c1 * (b.y - bm.y);
+        }
+        if (F.src3) {
+            const cplx d = ld_cg(F.src3 + poff(k, a.src_plane, a.src_ring) + 2 * c0col + off);
+            v.x += F.c2 * d.x;
+            v.y += F.c2 * d.y;
+        }
+    }
+    return v;
+}
+
+// one work item (column tile of one plane of one field) of the y pass; shared memory is free
+// again when it returns (its last transform ends with a barrier)
 template <int NIN, int NOUT, bool MULTI>
-__global__ void __launch_bounds__(YCfg<NIN, NOUT, MULTI>::NTHR, YCfg<NIN, NOUT, MULTI>::MINB)
-k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cplx* __restrict__ Woutg) {
+LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, const YArgs& a, long work) {
     typedef YCfg<NIN, NOUT, MULTI> C;
-    constexpr int TC = C::TC, SL = C::SL, NS = C::NS, NTHR = C::NTHR;
-    LG_DYN_SMEM(cplx, sm);
-    cplx* buf = sm;                                     // work buffer
-    cplx* S = MULTI ? sm + TC * SL : sm;                // spectrum of the tile (NS rows used)
-    cplx* Win = sm + C::NBUF * TC * SL;
-    cplx* Wout = Win + C::TWI;
-    if (NIN > 0) load_table(Win, Wing, C::TWI);
-    if (NOUT > 0) load_table(Wout, Woutg, C::TWO);
-    __syncthreads();
+    constexpr int TC = C::TC, NS = C::NS, NTHR = C::NTHR;
     auto sidx = [](int f, int i) { return spad(i) * TC + f; };
     auto foff = [](int f) { return f; };
     const int ntc = (a.ncols + TC - 1) / TC;
-    const long ntiles = long(ntc) * a.nplanes;
-    const long nwork = ntiles * a.nfields;
-    for (long work = blockIdx.x; work < nwork; work += gridDim.x) {   // round-robin: see k_xfwd
+    {
         const YField& F = a.fld[work % a.nfields];
         const long tile = work / a.nfields;
         const int c0 = int(tile % ntc) * TC;
         const int k = a.k0 + int(tile / ntc);
-        const double* src = F.src + long(k) * a.src_plane + 2 * c0;
+        const double* src = F.src + poff(k, a.src_plane, a.src_ring) + 2 * c0;
 
         if constexpr (NIN > 0) {
             if constexpr (NOUT == 0) {
                 // forward only: straight to global with Nyquist-row zeroing
-                double* dst = F.out[0].dst + long(k) * a.dst_plane + 2 * c0;
+                double* dst = F.out[0].dst + poff(k, a.dst_plane, a.dst_ring) + 2 * c0;
                 fft_tile<NIN, false, TC, true, NTHR, false, false, TC>(buf, Win, foff,
                     [&](int f, int i) {
                         if (c0 + f >= a.ncols) return make_double2(0.0, 0.0);
-                        return *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
+                        return y_input(F, a, src, k, c0, i, f);
                     },
                     [&](int f, int i, cplx v) {
                         if (c0 + f >= a.ncols) return;
@@ -340,7 +390,7 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
                 fft_tile<NIN, false, TC, true, NTHR, false, !MULTI, TC>(buf, Win, foff,
                     [&](int f, int i) {
                         if (c0 + f >= a.ncols) return make_double2(0.0, 0.0);
-                        return *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
+                        return y_input(F, a, src, k, c0, i, f);
                     },
                     [&](int f, int i, cplx v) {
                         // keep only the NS rows of the small spectrum (unpadd, fft.f90:86-97)
@@ -357,7 +407,7 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
             for (int it = threadIdx.x; it < TC * NS; it += NTHR) {
                 int f = it % TC, i = it / TC;
                 cplx v = make_double2(0.0, 0.0);
-                if (c0 + f < a.ncols) v = *reinterpret_cast<const cplx*>(src + long(i) * a.src_row + 2 * f);
+                if (c0 + f < a.ncols) v = ld_cg(src + long(i) * a.src_row + 2 * f);
                 S[sidx(f, i)] = v;
             }
             __syncthreads();
@@ -374,8 +424,8 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
             for (int o = 0; o < a.nout; ++o) {
                 const int mode = F.out[o].mode;
                 if (mode == Y_IKX && o_copy >= 0) continue;          // written by the COPY transform
-                double* dst = F.out[o].dst + long(k) * a.dst_plane + 2 * c0;
-                double* dst_x = (mode == Y_COPY && o_ikx >= 0) ? F.out[o_ikx].dst + long(k) * a.dst_plane + 2 * c0 : nullptr;
+                double* dst = F.out[o].dst + poff(k, a.dst_plane, a.dst_ring) + 2 * c0;
+                double* dst_x = (mode == Y_COPY && o_ikx >= 0) ? F.out[o_ikx].dst + poff(k, a.dst_plane, a.dst_ring) + 2 * c0 : nullptr;
                 fft_tile<NOUT, true, TC, true, NTHR, !MULTI, false, TC>(buf, Wout, foff,
                     [&](int f, int i) {
                         // row i of the (possibly padded) output spectrum <- small row is
@@ -407,12 +457,31 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
         if (a.zero_col >= 0 && c0 == 0) {
             constexpr int NR = NOUT > 0 ? NOUT : NIN;
             for (int o = 0; o < a.nout; ++o) {
-                double* dst = F.out[o].dst + long(k) * a.dst_plane;
+                double* dst = F.out[o].dst + poff(k, a.dst_plane, a.dst_ring);
                 for (int i = threadIdx.x; i < NR; i += NTHR)
                     *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * a.zero_col) = make_double2(0.0, 0.0);
             }
         }
     }
+}
+
+template <int NIN, int NOUT, bool MULTI>
+__global__ void __launch_bounds__(YCfg<NIN, NOUT, MULTI>::NTHR, YCfg<NIN, NOUT, MULTI>::MINB)
+k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cplx* __restrict__ Woutg) {
+    typedef YCfg<NIN, NOUT, MULTI> C;
+    constexpr int TC = C::TC, SL = C::SL;
+    LG_DYN_SMEM(cplx, sm);
+    cplx* buf = sm;                                     // work buffer
+    cplx* S = MULTI ? sm + TC * SL : sm;                // spectrum of the tile (NS rows used)
+    cplx* Win = sm + C::NBUF * TC * SL;
+    cplx* Wout = Win + C::TWI;
+    if (NIN > 0) load_table(Win, Wing, C::TWI);
+    if (NOUT > 0) load_table(Wout, Woutg, C::TWO);
+    __syncthreads();
+    const int ntc = (a.ncols + TC - 1) / TC;
+    const long nwork = long(ntc) * a.nplanes * a.nfields;
+    for (long work = blockIdx.x; work < nwork; work += gridDim.x)    // round-robin: see k_xfwd
+        ypass_work<NIN, NOUT, MULTI>(buf, S, Win, Wout, a, work);
 }
 
 }  // namespace lg

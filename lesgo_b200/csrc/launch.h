@@ -21,14 +21,28 @@ bool size_supported(int n_small);
 // radices and stage-twiddle-table length of the plan for complex length n (false if none)
 bool plan_lookup(int n, PlanDesc* out);
 
+// plane pipelines (pipe_kernels.h): 0 = launched, -1 = not available for these lengths
+struct PipeCtl;
+bool pipe_enabled();     // LESGO_PIPE=1 turns them on (off by default: measured slower, profiles/r2_experiments.md)
+int pipe_ring();         // LESGO_PIPE_RING planes (default 4)
+int launch_pipe_deriv(int nx, int ny, bool multi, const ProScale& pro, const XfOut& xo, const YArgs& ya,
+                      const XiSrc& xi, const EpiStore& epi, const PipeCtl& ctl, const cplx* Wx, const cplx* Whx,
+                      const cplx* Wy, cudaStream_t s);
+// fused 3/2-grid x pass of convec (bigx_kernels.h); nx2 = 3 nx / 2
+struct BigxArgs;
+int launch_bigx(int nx2, const BigxArgs& a, const cplx* W, const cplx* Wh, cudaStream_t s);
+// (nx, ny) pairs the pipelines are instantiated for
+#define LG_PIPE_SIZES(X) X(512, 512) X(1024, 512) X(64, 512)
+
 template <class K> inline void set_smem(K kernel, size_t bytes) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
 }
 
 // persistent grids: blocks per SM that fit (shared memory / 64-register budget), times SMs
 int sm_count();
-// warp-scope x passes (wfft_kernels.h) unless LESGO_XW=0 selects the block-cooperative round-1 kernels
-bool warp_passes();
+// warp-scope x passes (wfft_kernels.h): LESGO_XW=0 never, 1 (default) for the 3/2-grid x inverse only
+// (the one pass where they measured faster), 2 everywhere
+int warp_passes();
 inline int persistent_blocks(size_t smem_bytes, long ntiles, int max_per_sm) {
     int per_sm = int((227 * 1024) / (smem_bytes + 1024));
     if (per_sm > max_per_sm) per_sm = max_per_sm;

@@ -13,6 +13,8 @@
 #include "../../include/lesgo_gpu.h"
 #include "comm.h"
 #include "launch.h"
+#include "pipe_kernels.h"
+#include "bigx_kernels.h"
 
 using namespace lg;
 
@@ -21,6 +23,15 @@ const double kBogus = -1234567890.0;   // param.f90:93
 thread_local std::string g_err;
 
 }  // namespace
+
+// developer experiment (LESGO_EXP_ALIAS=1): every plane of an INTERMEDIATE aliases plane 0, i.e. the
+// intermediates are L2-resident by construction.  Results are garbage; the timings bound what
+// keeping intermediates in L2 can buy.
+static bool exp_alias() {
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("LESGO_EXP_ALIAS"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v != 0;
+}
 
 struct lesgo_gpu_ctx {
     lesgo_gpu_dims d;
@@ -41,6 +52,9 @@ struct lesgo_gpu_ctx {
     double* sa[kMaxFields] = {nullptr};    // small spectra / intermediates, (ld, ny, 0:nz)
     double* bb[kMaxFields] = {nullptr};    // big-y intermediates, (ld, ny2, 0:nz)
     double* big[kMaxFields] = {nullptr};   // 3/2-grid physical fields, (ld_big, ny2, 0:nz)
+    double* xs3[3] = {nullptr};            // x spectra (times ny) of the filtered u, v, w kept from filt_da to
+                                           // convec inside lesgo_gpu_step (spectral reuse)
+    double* cc[3] = {nullptr};             // big-y x spectra of the products cx, cy, cz (fused 3/2-grid x pass)
     double* gam = nullptr;                 // tridiagonal gam(j) table (lh, ny, 0:nzt+1)
     double* work[13] = {nullptr};          // S11..S33, Nu_t, six stress-gradient temporaries (mode 1)
     double* lsq = nullptr;                 // l(k)**2 of the Smagorinsky length (nz+1)
@@ -50,6 +64,7 @@ struct lesgo_gpu_ctx {
     double* fields[LG_NFIELDS] = {nullptr};
     std::vector<double*> staging;          // device staging for host-pointer arguments
     std::vector<size_t> staging_bytes;
+    int* pipe_buf = nullptr;               // ticket + completion counters of the plane pipelines
     double* red_dev = nullptr;             // reductions
     double* red_host = nullptr;
     lg::Comm* comm = nullptr;
@@ -62,7 +77,7 @@ struct lesgo_gpu_ctx {
     std::vector<ProfRec> prof_recs;
 
     Lay lay() const { return Lay{plane, ld}; }
-    Lay lay_big() const { return Lay{plane_big, ld_big}; }
+    Lay lay_big() const { return Lay{exp_alias() ? 0 : plane_big, ld_big}; }
     int fail(const std::string& m) { err = m; g_err = m; return 1; }
 };
 
@@ -350,7 +365,8 @@ int xfwd(lesgo_gpu_ctx* c, bool bigx, const Pro& pro, int nf, double* const* dst
          int ncol, int nyrows, int k0, int k1, int write_nyq = 0) {
     XfOut o;
     for (int i = 0; i < nf; ++i) o.dst[i] = dst[i];
-    o.plane = dplane; o.row = drow; o.ncol = ncol; o.write_nyq = write_nyq;
+    o.plane = dplane; o.row = drow; o.ncol = ncol; o.write_nyq = write_nyq; o.ring = 0;
+    if (exp_alias()) o.ring = 1;
     if (k1 <= k0) return 0;
     ProfScope ps_(c, bigx ? "xfwd_big" : "xfwd");
     int rc = launch_xfwd<Pro>(bigx ? c->nx2 : c->nx, pro, nf, o, nyrows, k0, k1 - k0,
@@ -380,7 +396,8 @@ int xinv(lesgo_gpu_ctx* c, bool bigx, const double* const* src, long splane, int
          double* const* dst, const Lay& dl, int nyrows, int k0, int k1, int pad = 1, const Fuse* fz = nullptr) {
     XiSrc in;
     for (int i = 0; i < nf; ++i) in.src[i] = src[i];
-    in.plane = splane; in.row = srow; in.ncol = ncol;
+    in.plane = splane; in.row = srow; in.ncol = ncol; in.ring = 0;
+    if (exp_alias()) in.ring = 1;
     if (k1 <= k0) return 0;
     ProfScope ps_(c, bigx ? "xinv_big" : "xinv");
     int rc;
@@ -420,6 +437,7 @@ int ypass(lesgo_gpu_ctx* c, int nin, int nout, const YArgs& a, int nf, int k0, i
     if (k1 <= k0) return 0;
     ProfScope ps_(c, nin == nout ? "ypass_deriv" : (nout == 0 ? "ypass_fwd" : (nin == 0 ? "ypass_inv" : (nin < nout ? "ypass_pad" : "ypass_trunc"))));
     auto W = [&](int n) -> const cplx* { return n == c->ny ? c->Wy : (n == c->ny2 ? c->Wyb : nullptr); };
+    if (exp_alias()) { YArgs b = a; b.src_ring = b.dst_ring = 1; int rc = launch_ypass(nin, nout, b, nf, k1 - k0, nin ? W(nin) : W(nout), nout ? W(nout) : W(nin), c->stream); c->launches++; return rc; }
     int rc = launch_ypass(nin, nout, a, nf, k1 - k0, nin ? W(nin) : W(nout), nout ? W(nout) : W(nin), c->stream);
     if (rc) return c->fail("unsupported ny for y pass");
     c->launches++;
@@ -445,6 +463,23 @@ int fill(lesgo_gpu_ctx* c, double* f, long plane, int k0, int k1, double v) {
     return 0;
 }
 
+// control block of a plane-pipeline launch: ticket + 3 * nplanes completion counters, zeroed
+int pipe_ctl(lesgo_gpu_ctx* c, PipeCtl* ctl, int nplanes, int k0) {
+    const size_t n = 4 + 3 * size_t(c->nz + 2);
+    if (!c->pipe_buf) {
+        void* q = nullptr;
+        CK(cudaMalloc(&q, n * sizeof(int)));
+        c->allocs.push_back(q);
+        c->pipe_buf = static_cast<int*>(q);
+    }
+    CK(cudaMemsetAsync(c->pipe_buf, 0, n * sizeof(int), c->stream));
+    std::memset(ctl, 0, sizeof(*ctl));
+    ctl->ticket = reinterpret_cast<unsigned*>(c->pipe_buf);
+    ctl->done = c->pipe_buf + 4;
+    ctl->nplanes = nplanes; ctl->k0 = k0; ctl->ring = pipe_ring();
+    return 0;
+}
+
 // ---- derivatives.f90 --------------------------------------------------------------------------
 // which: bit 0 = f itself (filt_da), bit 1 = d/dx, bit 2 = d/dy
 int chunk_of(const lesgo_gpu_ctx* c, int divisor) {
@@ -454,7 +489,9 @@ int chunk_of(const lesgo_gpu_ctx* c, int divisor) {
     return ch < 1 ? 1 : ch;
 }
 
-int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx, double* dfdy) {
+// keep != nullptr (with fout): the y-pass output for f itself, i.e. the x spectrum of the filtered field
+// times ny, is written to keep and stays valid after the call (lesgo_gpu_step hands it to convec)
+int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx, double* dfdy, double* keep = nullptr) {
     if (need_small(c, 4)) return 1;
     const int nz = c->nz;
     ProScale pro;
@@ -465,10 +502,36 @@ int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx
     const double* xs[3];
     double* xd[3];
     int n = 0;
-    if (fout) { a.fld[0].out[n] = YOutSpec{c->sa[1 + n], Y_COPY}; xs[n] = c->sa[1 + n]; xd[n] = fout; ++n; }
-    if (dfdx) { a.fld[0].out[n] = YOutSpec{c->sa[1 + n], Y_IKX}; xs[n] = c->sa[1 + n]; xd[n] = dfdx; ++n; }
-    if (dfdy) { a.fld[0].out[n] = YOutSpec{c->sa[1 + n], Y_IKY}; xs[n] = c->sa[1 + n]; xd[n] = dfdy; ++n; }
+    auto mid = [&](int i) { return (keep && i == 0 && fout) ? keep : c->sa[1 + i]; };
+    if (fout) { a.fld[0].out[n] = YOutSpec{mid(n), Y_COPY}; xs[n] = mid(n); xd[n] = fout; ++n; }
+    if (dfdx) { a.fld[0].out[n] = YOutSpec{mid(n), Y_IKX}; xs[n] = mid(n); xd[n] = dfdx; ++n; }
+    if (dfdy) { a.fld[0].out[n] = YOutSpec{mid(n), Y_IKY}; xs[n] = mid(n); xd[n] = dfdy; ++n; }
     a.nout = n;
+    // plane pipeline: all three passes in one persistent kernel, intermediates in L2-resident rings
+    if (pipe_enabled() && !keep && !HP(c) && c->chunk <= 0) {
+        int ntr = 0;
+        if (fout || dfdx) ++ntr;
+        if (dfdy) ++ntr;
+        XfOut xo;
+        xo.dst[0] = c->sa[0]; xo.plane = c->plane; xo.row = c->ld; xo.ncol = c->nx / 2; xo.write_nyq = 0;
+        xo.ring = pipe_ring();
+        YArgs ap = a;
+        ap.src_ring = ap.dst_ring = pipe_ring();
+        ap.nfields = 1; ap.nplanes = nz + 1; ap.k0 = 0;
+        XiSrc xi;
+        for (int i = 0; i < n; ++i) xi.src[i] = xs[i];
+        xi.plane = c->plane; xi.row = c->ld; xi.ncol = c->nx / 2; xi.ring = pipe_ring();
+        EpiStore epi;
+        for (int i = 0; i < n; ++i) epi.dst[i] = xd[i];
+        epi.lay = c->lay(); epi.nx = c->nx; epi.pad = 1;
+        PipeCtl ctl;
+        if (pipe_ctl(c, &ctl, nz + 1, 0)) return 1;
+        ctl.nf_f = 1; ctl.nf_i = n; ctl.ny_f = ctl.ny_i = c->ny;
+        for (int i = 0; i < n; ++i) { ctl.i_k0[i] = 0; ctl.i_k1[i] = nz + 1; }
+        ProfScope ps_(c, "pipe_deriv");
+        int rc = launch_pipe_deriv(c->nx, c->ny, ntr > 1, pro, xo, ap, xi, epi, ctl, c->Wx, c->Whx, c->Wy, c->stream);
+        if (rc == 0) { c->launches++; return 0; }
+    }
     // plane chunks: the x->y->x passes of a chunk run back to back so the two spectral
     // intermediates are still in L2 when the next pass reads them
     const int ch = chunk_of(c, 1);
@@ -526,11 +589,41 @@ int ddz_w(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
     return 0;
 }
 
+bool reuse_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("LESGO_REUSE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+bool bigx_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("LESGO_BIGX"); v = (e && e[0] == '1') ? 1 : 0; }   // opt-in, see convec()
+    return v != 0;
+}
+// planes per z chunk of the fused 3/2-grid x pass: long enough that the one-plane overlap between
+// chunks is cheap, short enough that ny2 * nchunks work items balance over the persistent blocks
+int bigx_chunk(int nz) {
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("LESGO_BIGX_CHUNK"); v = e ? std::atoi(e) : 0; }
+    if (v > 0) return v;
+    const int n = nz - 1;
+    if (n <= 40) return n < 1 ? 1 : n;
+    const int nch = (n + 63) / 64;
+    return (n + nch - 1) / nch;
+}
+
 // ---- convec.f90 --------------------------------------------------------------------------------
 int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, const double* dudy,
            const double* dudz, const double* dvdx, const double* dvdz, const double* dwdx,
-           const double* dwdy, double* RHSx, double* RHSy, double* RHSz, const Fuse* fz = nullptr) {
-    if (need_small(c, 6) || need_big(c, 6)) return 1;
+           const double* dwdy, double* RHSx, double* RHSy, double* RHSz, const Fuse* fz = nullptr,
+           double* const* xs3 = nullptr) {
+    // fused 3/2-grid x pass (LESGO_BIGX=1; off by default: 9.1 ms against 8.0 ms for the two separate passes,
+    // profiles/r2_experiments.md), never with the host-array pipeline or plane chunks
+    const bool fused_x = bigx_enabled() && !HP(c) && c->chunk <= 0 && c->nz >= 2;
+    if (need_small(c, 6)) return 1;
+    if (fused_x) {
+        for (int i = 0; i < 6; ++i) if (dev_alloc(c, &c->bb[i], size_t(c->plane_bi) * (c->nz + 1))) return 1;
+        for (int i = 0; i < 3; ++i) if (dev_alloc(c, &c->cc[i], size_t(c->plane_bi) * (c->nz + 1))) return 1;
+    } else if (need_big(c, 6)) return 1;
     const int nz = c->nz, nxh = c->nx / 2;
     const double cs = 1.0 / (double(c->nx) * double(c->ny));
     ProScale ps;
@@ -552,6 +645,24 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
         const int kb = ka + ch < nz + 1 ? ka + ch : nz + 1;
         const int va = ka < 1 ? 1 : ka;                 // vorticity exists on planes 1..nz
         if (Staged* hp = HP(c)) hp->need(kb);           // the wall-plane vorticity reads one plane up
+        if (xs3) {
+            // Spectral reuse (lesgo_gpu_step only): filt_da left the x spectra of the filtered u, v, w in
+            // xs3 (its y-pass output for the field itself), which is what step (1) would
+            // recompute from the filtered fields -- up to the factor ny of the unnormalised y round trip.
+            // (Forming the vorticity's x spectra the same way, from the kept derivative spectra and
+            // z differences, was measured: the extra strided loads in the y pass cost more than the
+            // x-forward pass they replace, profiles/r2_experiments.md.)
+            YArgs a = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, 0);
+            for (int i = 0; i < 3; ++i) {
+                a.fld[i].src = xs3[i]; a.fld[i].combo = 1; a.fld[i].c0 = 1.0 / double(c->ny);
+                a.fld[i].out[0] = YOutSpec{c->bb[i], Y_COPY};
+            }
+            if (ypass(c, c->ny, c->ny2, a, 3, 0, nz + 1)) return 1;
+            if (xfwd(c, false, pv, 3, c->sa + 3, c->plane, c->ld, nxh, c->ny, va, kb)) return 1;
+            YArgs b = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, va);
+            for (int i = 0; i < 3; ++i) { b.fld[i].src = c->sa[3 + i]; b.fld[i].out[0] = YOutSpec{c->bb[3 + i], Y_COPY}; }
+            if (ypass(c, c->ny, c->ny2, b, 3, va, kb)) return 1;
+        } else {
         // (1) u, v, w and the vorticity to half spectra                          convec.f90:73-82, 97-158
         if (xfwd(c, false, ps, 3, c->sa, c->plane, c->ld, nxh, c->ny, ka, kb)) return 1;
         if (xfwd(c, false, pv, 3, c->sa + 3, c->plane, c->ld, nxh, c->ny, va, kb)) return 1;
@@ -564,6 +675,8 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
             for (int i = 0; i < 3; ++i) { b.fld[i].src = c->sa[3 + i]; b.fld[i].out[0] = YOutSpec{c->bb[3 + i], Y_COPY}; }
             if (ypass(c, c->ny, c->ny2, b, 3, va, kb)) return 1;
         }
+        }
+        if (fused_x) continue;
         // (3) x inverse on the 3/2 grid: only kx < nx/2 carries data               :90-92, 165-167
         if (xinv(c, true, c->bb, c->plane_bi, c->ld, nxh, 3, c->big, c->lay_big(), c->ny2, ka, kb)) return 1;
         if (xinv(c, true, c->bb + 3, c->plane_bi, c->ld, nxh, 3, c->big + 3, c->lay_big(), c->ny2, va, kb)) return 1;
@@ -582,6 +695,27 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
         // (6) x inverse -> RHS
         if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, pa, pb, 1, fz)) return 1;
         if (Staged* hp = HP(c)) for (int i = 0; i < 3; ++i) hp->done(out[i], pa, pb);
+    }
+    if (fused_x) {
+        // (3)+(4) in one kernel: x inverse of the six fields, products, x forward of the three
+        // products, marching up z per 3/2-grid row (bigx_kernels.h)                 :90-92, 165-305
+        BigxArgs b;
+        for (int i = 0; i < 6; ++i) b.src[i] = c->bb[i];
+        for (int i = 0; i < 3; ++i) b.dst[i] = c->cc[i];
+        b.plane = c->plane_bi; b.row = c->ld; b.ny2 = c->ny2; b.nz = nz;
+        b.bottom = c->bottom; b.top = c->top; b.jzLo = c->jzLo;
+        b.chunk = bigx_chunk(nz); b.nchunks = (nz - 1 + b.chunk - 1) / b.chunk;
+        b.scale = 1.0 / (double(c->nx2) * double(c->ny2));
+        {
+            ProfScope ps_(c, "bigx");
+            if (launch_bigx(c->nx2, b, c->Wxb, c->Whxb, c->stream)) return c->fail("unsupported nx for the fused 3/2-grid x pass");
+            c->launches++;
+        }
+        for (int i = 0; i < 3; ++i) fill(c, c->cc[i], c->plane_bi, nz, nz + 1, 0.0);   // cc(nz) = 0, :262-268
+        YArgs a = yargs(c, c->plane_bi, c->ld, c->plane, c->ld, nxh, 1);
+        for (int i = 0; i < 3; ++i) { a.fld[i].src = c->cc[i]; a.fld[i].out[0] = YOutSpec{c->sa[i], Y_COPY}; }
+        if (ypass(c, c->ny2, c->ny, a, 3, 1, nz + 1)) return 1;
+        if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, 1, nz + 1, 1, fz)) return 1;
     }
     // :319-332
     fill(c, RHSx, c->plane, 0, 1, kBogus); fill(c, RHSy, c->plane, 0, 1, kBogus); fill(c, RHSz, c->plane, 0, 1, kBogus);
@@ -950,9 +1084,15 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     std::swap(c->fields[LG_RHSY], c->fields[LG_RHSY_F]); std::swap(F[LG_RHSY], F[LG_RHSY_F]);
     std::swap(c->fields[LG_RHSZ], c->fields[LG_RHSZ_F]); std::swap(F[LG_RHSZ], F[LG_RHSZ_F]);
     // :161-172
-    if (spectral_deriv(c, F[LG_U], F[LG_U], F[LG_DUDX], F[LG_DUDY])) return 1;
-    if (spectral_deriv(c, F[LG_V], F[LG_V], F[LG_DVDX], F[LG_DVDY])) return 1;
-    if (spectral_deriv(c, F[LG_W], F[LG_W], F[LG_DWDX], F[LG_DWDY])) return 1;
+    // spectral reuse: keep the x spectra filt_da produces for convec (LESGO_REUSE=0: off)
+    const bool reuse = reuse_enabled() && c->chunk == 0 && !HP(c);
+    if (reuse)
+        for (int i = 0; i < 3; ++i)
+            if (dev_alloc(c, &c->xs3[i], size_t(c->plane) * (nz + 1))) return 1;
+    double* const* kp = reuse ? c->xs3 : nullptr;
+    if (spectral_deriv(c, F[LG_U], F[LG_U], F[LG_DUDX], F[LG_DUDY], kp ? kp[0] : nullptr)) return 1;
+    if (spectral_deriv(c, F[LG_V], F[LG_V], F[LG_DVDX], F[LG_DVDY], kp ? kp[1] : nullptr)) return 1;
+    if (spectral_deriv(c, F[LG_W], F[LG_W], F[LG_DWDX], F[LG_DWDY], kp ? kp[2] : nullptr)) return 1;
     ddz_uv(c, F[LG_U], F[LG_DUDZ]);
     ddz_uv(c, F[LG_V], F[LG_DVDZ]);
     ddz_w(c, F[LG_W], F[LG_DWDZ]);
@@ -974,7 +1114,7 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
         // epilogue of the last pass updates them -- but only when the whole slab is one chunk
         const Fuse* use = c->chunk == 0 ? &fz : nullptr;
         if (convec(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DUDY], F[LG_DUDZ], F[LG_DVDX], F[LG_DVDZ], F[LG_DWDX],
-                   F[LG_DWDY], F[LG_RHSX], F[LG_RHSY], F[LG_RHSZ], use)) return 1;
+                   F[LG_DWDY], F[LG_RHSX], F[LG_RHSY], F[LG_RHSZ], use, kp)) return 1;
         if (!use) {
             const int kw = c->top ? nz + 1 : nz;
             glue_fused(c, F_RHS_AB2, F[LG_RHSX], F[LG_DIVTX], F[LG_RHSX_F], F[LG_U], 1, nz, 0, fz.first_step, sp->mean_p_force_x, sp->dt, sp->tadv1, sp->tadv2);

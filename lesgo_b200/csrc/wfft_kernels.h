@@ -24,9 +24,13 @@ template <int NX, bool TWREG_ = (LG_XW_TWREG != 0)> struct XWCfg {
     static constexpr bool TWREG = SMALL && TWREG_;
     static constexpr int SL = SmemLen<M>::value;
     static constexpr int WBUF = (INPLACE ? 1 : 2) * NF * SL;      // cplx per warp
-    static constexpr int WPB = 8, NTHR = 32 * WPB;
     static constexpr int TWL = PI::twlen, NWH = M / 2 + 1;
-    static constexpr size_t smem = size_t(WPB * WBUF + TWL + NWH) * sizeof(cplx) + size_t(WPB) * 2 * NF * sizeof(int);
+    static constexpr size_t smem_for(int wpb) {
+        return size_t(wpb * WBUF + TWL + NWH) * sizeof(cplx) + size_t(wpb) * 2 * NF * sizeof(int);
+    }
+    static constexpr int WPB = smem_for(8) <= 200 * 1024 ? 8 : 4;   // warps per block
+    static constexpr int NTHR = 32 * WPB;
+    static constexpr size_t smem = smem_for(WPB);
     static constexpr int by_smem = int((227 * 1024) / (smem + 1024)) < 1 ? 1 : int((227 * 1024) / (smem + 1024));
     static constexpr int by_regs = TWREG ? 2 : (M <= 256 ? 4 : 3);   // 128 / 64 / 80 registers per thread
     static constexpr int MINB = by_regs < by_smem ? by_regs : by_smem;
@@ -103,7 +107,7 @@ k_xfwd_w(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int
                 const int f = (NF == 1) ? 0 : it / NPM, m = (NF == 1) ? it : it % NPM;
                 const int k = rows.k(f);
                 if (k >= 0) {
-                    double* drow = out.dst[fld] + long(k) * out.plane + long(rows.y(f)) * out.row;
+                    double* drow = out.dst[fld] + poff(k, out.plane, out.ring) + long(rows.y(f)) * out.row;
                     const cplx a = X[f * SL + spad(m)];
                     if (m == 0) {
                         if (out.ncol > 0) *reinterpret_cast<cplx*>(drow) = make_double2(a.x + a.y, 0.0);
@@ -177,13 +181,13 @@ k_xinv_w(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int 
                     const int f = (NF == 1) ? 0 : it / NPM, m = (NF == 1) ? it : it % NPM;
                     const int k = rows.k(f);
                     if (k >= 0) {
-                        const double* srow = in.src[fld] + long(k) * in.plane + long(rows.y(f)) * in.row;
+                        const double* srow = in.src[fld] + poff(k, in.plane, in.ring) + long(rows.y(f)) * in.row;
                         if (m == 0) {                          // real parts of X_0 and X_M only
-                            va[u].x = in.ncol > 0 ? srow[0] : 0.0;
-                            va[u].y = in.ncol > M ? srow[2 * M] : 0.0;
+                            va[u].x = in.ncol > 0 ? ld_cg(srow).x : 0.0;
+                            va[u].y = in.ncol > M ? ld_cg(srow + 2 * M).x : 0.0;
                         } else {
-                            if (m < in.ncol) va[u] = *reinterpret_cast<const cplx*>(srow + 2 * m);
-                            if (m != M / 2 && M - m < in.ncol) vb[u] = *reinterpret_cast<const cplx*>(srow + 2 * (M - m));
+                            if (m < in.ncol) va[u] = ld_cg(srow + 2 * m);
+                            if (m != M / 2 && M - m < in.ncol) vb[u] = ld_cg(srow + 2 * (M - m));
                         }
                     }
                 }

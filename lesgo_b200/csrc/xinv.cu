@@ -3,11 +3,11 @@
 namespace lg {
 template <int NX, class Epi = EpiStore>
 static int launch_xinv_n(const XiSrc& in, const Epi& epi, int nfields, int ny, int k0, int nplanes,
-                         const cplx* W, const cplx* Wh, cudaStream_t s) {
+                         const cplx* W, const cplx* Wh, cudaStream_t s, bool big = false) {
     typedef XCfg<NX> C;
     const long nrows = long(ny) * nplanes;
     if (nrows <= 0) return 0;
-    if (warp_passes()) {
+    if (warp_passes() > 1 || (warp_passes() == 1 && big)) {
         typedef XWCfg<NX> CW;
         static bool attr_w = false;
         if (!attr_w) { set_smem(k_xinv_w<NX, Epi>, CW::smem); attr_w = true; }
@@ -23,20 +23,21 @@ static int launch_xinv_n(const XiSrc& in, const Epi& epi, int nfields, int ny, i
     return 0;
 }
 #define LG_XINV_CASE_SMALL(S, B) case S: return launch_xinv_n<S>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+#define LG_XINV_BIG(B) case B: return launch_xinv_n<B>(in, epi, nfields, ny, k0, nplanes, W, Wh, s, true);
 int launch_xinv(int NX, const XiSrc& in, const EpiStore& epi, int nfields, int ny, int k0, int nplanes,
                 const cplx* W, const cplx* Wh, cudaStream_t s) {
     switch (NX) {
         LG_SIZE_PAIRS(LG_XINV_CASE_SMALL)
-        case 24: return launch_xinv_n<24>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
-        case 72: return launch_xinv_n<72>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
-        case 120: return launch_xinv_n<120>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
-        case 144: return launch_xinv_n<144>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
-        case 240: return launch_xinv_n<240>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
-        case 288: return launch_xinv_n<288>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
-        case 480: return launch_xinv_n<480>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
-        case 576: return launch_xinv_n<576>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
-        case 768: return launch_xinv_n<768>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
-        case 1536: return launch_xinv_n<1536>(in, epi, nfields, ny, k0, nplanes, W, Wh, s);
+        LG_XINV_BIG(24)
+        LG_XINV_BIG(72)
+        LG_XINV_BIG(120)
+        LG_XINV_BIG(144)
+        LG_XINV_BIG(240)
+        LG_XINV_BIG(288)
+        LG_XINV_BIG(480)
+        LG_XINV_BIG(576)
+        LG_XINV_BIG(768)
+        LG_XINV_BIG(1536)
     }
     return -1;
 }

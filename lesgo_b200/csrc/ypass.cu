@@ -73,10 +73,10 @@ int sm_count() {
     }
     return n;
 }
-bool warp_passes() {
+int warp_passes() {
     static int v = -1;
-    if (v < 0) { const char* e = std::getenv("LESGO_XW"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v != 0;
+    if (v < 0) { const char* e = std::getenv("LESGO_XW"); v = e ? std::atoi(e) : 1; }
+    return v;
 }
 bool size_supported(int n) {
     LG_SIZE_PAIRS(LG_SUP)

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <sched.h>
 
 struct dim3 {
     unsigned x, y, z;

@@ -63,18 +63,21 @@ template <int NX> struct XCfg {
 // one work item (tile of NF rows of one field) of the x-forward pass; every thread of the
 // NTHR-thread block calls it; ends with a barrier
 template <int NX, class Pro>
-LG_D void xfwd_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y, const Pro& pro, const XfOut& out,
-                    int nfields, int ny, int k0, int nplanes, long work) {
+LG_D void xfwd_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y, double** s_p, const Pro& pro,
+                    const XfOut& out, int nfields, int ny, int k0, int nplanes, unsigned work) {
     typedef XCfg<NX> C;
     constexpr int M = C::M, NF = C::NF, SL = C::SL, NTHR = C::NTHR;
-    const long nrows = long(ny) * nplanes;
+    const unsigned nrows = unsigned(ny) * unsigned(nplanes);
     {
-        const int fld = int(work % nfields);
-        const long row0 = (work / nfields) * NF;
+        // 32-bit index arithmetic throughout: a 64-bit division costs ~100 instructions per thread
+        const int fld = int(work % unsigned(nfields));
+        const unsigned row0 = (work / unsigned(nfields)) * NF;
         for (int f = threadIdx.x; f < NF; f += NTHR) {
-            long r = row0 + f;
-            s_k[f] = r < nrows ? k0 + int(r / ny) : -1;
-            s_y[f] = int(r % ny);
+            const unsigned r = row0 + f;
+            const int k = r < nrows ? k0 + int(r / unsigned(ny)) : -1, y = int(r % unsigned(ny));
+            s_k[f] = k;
+            s_y[f] = y;
+            s_p[f] = out.dst[fld] + poff(k < 0 ? 0 : k, out.plane, out.ring) + long(y) * out.row;   // output row
         }
         __syncthreads();
         fft_tile<M, false, NF, false, NTHR, false, true, 1>(buf, W,
@@ -96,7 +99,7 @@ LG_D void xfwd_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y
             const int m = 1 + it % NP, f = it / NP;
             const int k = s_k[f];
             if (k < 0) continue;
-            double* drow = out.dst[fld] + poff(k, out.plane, out.ring) + long(s_y[f]) * out.row;
+            double* drow = s_p[f];
             cplx a = buf[f * SL + spad(m)];
             cplx bz = buf[f * SL + spad(M - m)];
             cplx b = make_double2(bz.x, -bz.y);
@@ -112,7 +115,7 @@ LG_D void xfwd_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y
         for (int f = threadIdx.x; f < 2 * NF; f += NTHR) {
             const int ff = f >> 1, k = s_k[ff];
             if (k < 0) continue;
-            double* drow = out.dst[fld] + poff(k, out.plane, out.ring) + long(s_y[ff]) * out.row;
+            double* drow = s_p[ff];
             if (f & 1) {
                 cplx a = buf[ff * SL + spad(M / 2)];
                 if (M / 2 < out.ncol) *reinterpret_cast<cplx*>(drow + M) = make_double2(a.x, -a.y);
@@ -143,6 +146,7 @@ k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int n
     cplx* W = sm + NF * SL;
     cplx* Wh = W + C::TWL;
     __shared__ int s_k[NF], s_y[NF];
+    __shared__ double* s_p[NF];
     load_table(W, Wg, C::TWL);
     load_table(Wh, Whg, C::NWH);
     // Work items are dealt round-robin with the field index fastest: blocks resident together
@@ -154,7 +158,7 @@ k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int n
     const long nrows = long(ny) * nplanes;
     const long nwork = ((nrows + NF - 1) / NF) * nfields;
     for (long work = blockIdx.x; work < nwork; work += gridDim.x)
-        xfwd_work<NX, Pro>(buf, W, Wh, s_k, s_y, pro, out, nfields, ny, k0, nplanes, work);
+        xfwd_work<NX, Pro>(buf, W, Wh, s_k, s_y, s_p, pro, out, nfields, ny, k0, nplanes, unsigned(work));
 }
 
 // ---------------------------------------------------------------------------------
@@ -171,18 +175,20 @@ struct XiSrc {
 
 // one work item of the x-inverse pass (see xfwd_work)
 template <int NX, class Epi>
-LG_D void xinv_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y, const XiSrc& in, const Epi& epi,
-                    int nfields, int ny, int k0, int nplanes, long work) {
+LG_D void xinv_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y, double** s_p, const XiSrc& in,
+                    const Epi& epi, int nfields, int ny, int k0, int nplanes, unsigned work) {
     typedef XCfg<NX> C;
     constexpr int M = C::M, NF = C::NF, SL = C::SL, NTHR = C::NTHR;
-    const long nrows = long(ny) * nplanes;
+    const unsigned nrows = unsigned(ny) * unsigned(nplanes);
     {
-        const int fld = int(work % nfields);
-        const long row0 = (work / nfields) * NF;
+        const int fld = int(work % unsigned(nfields));
+        const unsigned row0 = (work / unsigned(nfields)) * NF;
         for (int f = threadIdx.x; f < NF; f += NTHR) {
-            long r = row0 + f;
-            s_k[f] = r < nrows ? k0 + int(r / ny) : -1;
-            s_y[f] = int(r % ny);
+            const unsigned r = row0 + f;
+            const int k = r < nrows ? k0 + int(r / unsigned(ny)) : -1, y = int(r % unsigned(ny));
+            s_k[f] = k;
+            s_y[f] = y;
+            s_p[f] = const_cast<double*>(in.src[fld]) + poff(k < 0 ? 0 : k, in.plane, in.ring) + long(y) * in.row;   // source row
         }
         __syncthreads();
 
@@ -200,7 +206,7 @@ LG_D void xinv_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y
                 if (it < NF * NP) {
                     const int m = 1 + it % NP, f = it / NP;
                     if (s_k[f] >= 0) {
-                        const double* srow = in.src[fld] + poff(s_k[f], in.plane, in.ring) + long(s_y[f]) * in.row;
+                        const double* srow = s_p[f];
                         if (m < in.ncol) va[u] = ld_cg(srow + 2 * m);
                         if (M - m < in.ncol) vb[u] = ld_cg(srow + 2 * (M - m));
                     }
@@ -223,7 +229,7 @@ LG_D void xinv_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y
             const int ff = f >> 1;
             cplx z = make_double2(0.0, 0.0);
             if (s_k[ff] >= 0) {
-                const double* srow = in.src[fld] + poff(s_k[ff], in.plane, in.ring) + long(s_y[ff]) * in.row;
+                const double* srow = s_p[ff];
                 if (f & 1) {                                  // m = M/2: Z' = 2 conj(X_{M/2})
                     if (M / 2 < in.ncol) { cplx a = ld_cg(srow + M); z = make_double2(2.0 * a.x, -2.0 * a.y); }
                 } else {                                      // m = 0: real parts of X_0 and X_M only
@@ -264,13 +270,14 @@ k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nf
     cplx* W = sm + NF * SL;
     cplx* Wh = W + C::TWL;
     __shared__ int s_k[NF], s_y[NF];
+    __shared__ double* s_p[NF];
     load_table(W, Wg, C::TWL);
     load_table(Wh, Whg, C::NWH);
     (void)zmajor;   // round-robin work order, field index fastest: see k_xfwd
     const long nrows = long(ny) * nplanes;
     const long nwork = ((nrows + NF - 1) / NF) * nfields;
     for (long work = blockIdx.x; work < nwork; work += gridDim.x)
-        xinv_work<NX, Epi>(buf, W, Wh, s_k, s_y, in, epi, nfields, ny, k0, nplanes, work);
+        xinv_work<NX, Epi>(buf, W, Wh, s_k, s_y, s_p, in, epi, nfields, ny, k0, nplanes, unsigned(work));
 }
 
 // ---------------------------------------------------------------------------------
@@ -359,18 +366,23 @@ LG_D cplx y_input(const YField& F, const YArgs& a, const double* src, int k, int
 // one work item (column tile of one plane of one field) of the y pass; shared memory is free
 // again when it returns (its last transform ends with a barrier)
 template <int NIN, int NOUT, bool MULTI>
-LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, const YArgs& a, long work) {
+LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, const YArgs& a, unsigned work) {
     typedef YCfg<NIN, NOUT, MULTI> C;
     constexpr int TC = C::TC, NS = C::NS, NTHR = C::NTHR;
     auto sidx = [](int f, int i) { return spad(i) * TC + f; };
     auto foff = [](int f) { return f; };
     const int ntc = (a.ncols + TC - 1) / TC;
     {
-        const YField& F = a.fld[work % a.nfields];
-        const long tile = work / a.nfields;
-        const int c0 = int(tile % ntc) * TC;
-        const int k = a.k0 + int(tile / ntc);
+        const YField& F = a.fld[work % unsigned(a.nfields)];
+        const unsigned tile = work / unsigned(a.nfields);
+        const int c0 = int(tile % unsigned(ntc)) * TC;
+        const int k = a.k0 + int(tile / unsigned(ntc));
         const double* src = F.src + poff(k, a.src_plane, a.src_ring) + 2 * c0;
+        // every item of a thread lies in the same tile column (NTHR is a multiple of TC): its column
+        // checks and i*kx factor are per-tile constants
+        const int f_t = int(threadIdx.x) % TC;
+        const bool colok = c0 + f_t < a.ncols;
+        const double kx = a.kxs * double(c0 + f_t);
 
         if constexpr (NIN > 0) {
             if constexpr (NOUT == 0) {
@@ -378,18 +390,18 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
                 double* dst = F.out[0].dst + poff(k, a.dst_plane, a.dst_ring) + 2 * c0;
                 fft_tile<NIN, false, TC, true, NTHR, false, false, TC>(buf, Win, foff,
                     [&](int f, int i) {
-                        if (c0 + f >= a.ncols) return make_double2(0.0, 0.0);
+                        if (!colok) return make_double2(0.0, 0.0);
                         return y_input(F, a, src, k, c0, i, f);
                     },
                     [&](int f, int i, cplx v) {
-                        if (c0 + f >= a.ncols) return;
+                        if (!colok) return;
                         if (i == NIN / 2 && !a.keep_nyq_row) v = make_double2(0.0, 0.0);
                         *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * f) = v;
                     });
             } else {
                 fft_tile<NIN, false, TC, true, NTHR, false, !MULTI, TC>(buf, Win, foff,
                     [&](int f, int i) {
-                        if (c0 + f >= a.ncols) return make_double2(0.0, 0.0);
+                        if (!colok) return make_double2(0.0, 0.0);
                         return y_input(F, a, src, k, c0, i, f);
                     },
                     [&](int f, int i, cplx v) {
@@ -442,12 +454,11 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
                             double ky = a.kys * double(is < NS / 2 ? is : is - NS);
                             return make_double2(-v.y * ky, v.x * ky);
                         }
-                        double g = (c0 + f < a.ncols) ? a.table[long(is) * a.table_row + c0 + f] : 0.0;
+                        double g = colok ? a.table[long(is) * a.table_row + c0 + f] : 0.0;
                         return make_double2(v.x * g, v.y * g);
                     },
                     [&](int f, int i, cplx v) {
-                        if (c0 + f >= a.ncols) return;
-                        const double kx = a.kxs * double(c0 + f);
+                        if (!colok) return;
                         if (mode == Y_IKX) v = make_double2(-v.y * kx, v.x * kx);
                         *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * f) = v;
                         if (dst_x) *reinterpret_cast<cplx*>(dst_x + long(i) * a.dst_row + 2 * f) = make_double2(-v.y * kx, v.x * kx);
@@ -481,7 +492,7 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
     const int ntc = (a.ncols + TC - 1) / TC;
     const long nwork = long(ntc) * a.nplanes * a.nfields;
     for (long work = blockIdx.x; work < nwork; work += gridDim.x)    // round-robin: see k_xfwd
-        ypass_work<NIN, NOUT, MULTI>(buf, S, Win, Wout, a, work);
+        ypass_work<NIN, NOUT, MULTI>(buf, S, Win, Wout, a, unsigned(work));
 }
 
 }  // namespace lg

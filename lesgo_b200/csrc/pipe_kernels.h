@@ -105,6 +105,7 @@ k_pipe(const __grid_constant__ Pro pro, const __grid_constant__ XfOut xo, const 
     cplx* Win = Whx + CX::NWH;
     cplx* Wout = Win + CY::TWI;
     __shared__ int s_k[CX::NF], s_y[CX::NF];
+    __shared__ double* s_p[CX::NF];
     __shared__ unsigned s_t;
     load_table(Wx, Wxg, CX::TWL);
     load_table(Whx, Whxg, CX::NWH);
@@ -137,8 +138,8 @@ k_pipe(const __grid_constant__ Pro pro, const __grid_constant__ XfOut xo, const 
                 pipe_wait(done_y + p, tpy);
                 const int fld = r % ctl.nf_i, k = ctl.k0 + p;
                 if (k >= ctl.i_k0[fld] && k < ctl.i_k1[fld])
-                    xinv_work<(HI ? NXI : 16), Epi>(buf, Wx, Whx, s_k, s_y, xi, epi, ctl.nf_i, ctl.ny_i, ctl.k0, np,
-                                                   long(r) + long(p) * tpi);
+                    xinv_work<(HI ? NXI : 16), Epi>(buf, Wx, Whx, s_k, s_y, s_p, xi, epi, ctl.nf_i, ctl.ny_i, ctl.k0, np,
+                                                   unsigned(r) + unsigned(p) * unsigned(tpi));
                 pipe_signal(done_i + p);
             }
         } else if (r < tpi + tpy) {
@@ -147,7 +148,7 @@ k_pipe(const __grid_constant__ Pro pro, const __grid_constant__ XfOut xo, const 
             if (p < 0 || p >= np) continue;
             if (HF) pipe_wait(done_f + p, tpf);
             if (HI && p >= ctl.ring) pipe_wait(done_i + (p - ctl.ring), tpi);      // ring slot of the outputs is free
-            ypass_work<NIN, NOUT, MULTI>(buf, S, Win, Wout, ya, long(r) + long(p) * tpy);
+            ypass_work<NIN, NOUT, MULTI>(buf, S, Win, Wout, ya, unsigned(r) + unsigned(p) * unsigned(tpy));
             pipe_signal(done_y + p);
         } else {
             if constexpr (HF) {
@@ -155,8 +156,8 @@ k_pipe(const __grid_constant__ Pro pro, const __grid_constant__ XfOut xo, const 
                 const int p = int(s);
                 if (p >= np) continue;
                 if (p >= ctl.ring) pipe_wait(done_y + (p - ctl.ring), tpy);        // ring slot of the x spectra is free
-                xfwd_work<(HF ? NXF : 16), Pro>(buf, Wx, Whx, s_k, s_y, pro, xo, ctl.nf_f, ctl.ny_f, ctl.k0, np,
-                                               long(r) + long(p) * tpf);
+                xfwd_work<(HF ? NXF : 16), Pro>(buf, Wx, Whx, s_k, s_y, s_p, pro, xo, ctl.nf_f, ctl.ny_f, ctl.k0, np,
+                                               unsigned(r) + unsigned(p) * unsigned(tpf));
                 pipe_signal(done_f + p);
             }
         }

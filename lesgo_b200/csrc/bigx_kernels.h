@@ -33,19 +33,6 @@ struct BigxArgs {
     double scale;           // 1/(nx2*ny2), convec.f90:172
 };
 
-#ifdef LESGO_EMUL
-LG_HD void cp_async16(cplx* dst, const double* src) { *dst = *reinterpret_cast<const cplx*>(src); }
-LG_HD void cp_async_commit() {}
-LG_HD void cp_async_wait_all() {}
-#else
-LG_D void cp_async16(cplx* dst, const double* src) {
-    const unsigned d = unsigned(__cvta_generic_to_shared(dst));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-}
-LG_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-LG_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-#endif
-
 template <int NX2> struct BigxCfg {
     static constexpr int M = NX2 / 2;            // half length of a 3/2-grid row
     static constexpr int NC = NX2 / 3;           // nx/2: spectral columns that carry data

@@ -15,6 +15,10 @@
 #pragma once
 #include "portable.h"
 
+#ifndef LG_TW_PRODUCT
+#define LG_TW_PRODUCT 1
+#endif
+
 namespace lg {
 
 typedef double2 cplx;
@@ -264,11 +268,31 @@ LG_HD void stage_load(int j, const cplx* __restrict__ Wst, Ld ld, cplx* v) {
         // Wst[(r-1)*Ns + k] = W_N^{k r N/(Ns R)}: lanes with consecutive k read consecutive
         // entries (conflict-free), lanes with equal k broadcast
         const int k = j % Ns;
+#if LG_TW_PRODUCT
+        // The block-cooperative passes are bound by shared-memory bandwidth, not by the FP64 pipe
+        // (profiles/r2_experiments.md): fetch only w^1, w^2, w^4, w^8 and form the other powers as
+        // products of those (at most two multiplications deep, so no error growth along a chain).
+        // only p1, p2, p4, p8 and w^3 stay live (20 registers), each power is applied as soon as formed
+        static_assert(R <= 12, "twiddle products are written for radices up to 12");
+        const cplx p1 = Wst[k];
+        const cplx p2 = R > 2 ? Wst[Ns + k] : p1;
+        const cplx p4 = R > 4 ? Wst[3 * Ns + k] : p1;
+        const cplx p8 = R > 8 ? Wst[7 * Ns + k] : p1;
+        const cplx w3 = cmul(p2, p1);
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            const cplx hi = r >= 8 ? p8 : (r >= 4 ? p4 : (r >= 2 ? p2 : p1));
+            const int lo = r - (r >= 8 ? 8 : (r >= 4 ? 4 : (r >= 2 ? 2 : 1)));
+            const cplx w = lo == 0 ? hi : cmul(hi, lo == 1 ? p1 : (lo == 2 ? p2 : w3));
+            v[r] = INV ? cmulc(v[r], w) : cmul(v[r], w);
+        }
+#else
 #pragma unroll
         for (int r = 1; r < R; ++r) {
             cplx w = Wst[(r - 1) * Ns + k];
             v[r] = INV ? cmulc(v[r], w) : cmul(v[r], w);
         }
+#endif
     }
     if (INV) {
 #pragma unroll
@@ -395,8 +419,14 @@ LG_D void tile_stage(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St
     }
 }
 
-template <int N, bool INV, int NF, bool FFT_FASTEST, int NTHR, bool LD_BUF, bool ST_BUF, int ES, class FOff, class Ld, class St>
-LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St st) {
+struct NoHook { LG_HD void operator()() const {} };
+
+// hook(): called by every thread once the first stage has consumed its input (after the barrier
+// that follows it), e.g. to start the asynchronous prefetch of the next tile into the staging
+// buffer the first stage just read
+template <int N, bool INV, int NF, bool FFT_FASTEST, int NTHR, bool LD_BUF, bool ST_BUF, int ES, class FOff, class Ld, class St,
+          class Hook = NoHook>
+LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St st, Hook hook = Hook()) {
     typedef Plan<N> P;
     typedef PlanInfo<N> PI;
     constexpr int NST = PI::nstages;
@@ -405,16 +435,19 @@ LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St s
     } else if constexpr (NST == 2) {
         tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, false, true, LD_BUF, ES>(buf, W, foff, ld, st);
         __syncthreads();
+        hook();
         tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true, false, ST_BUF, ES>(buf, W + PI::off2, foff, ld, st);
     } else if constexpr (NST == 3) {
         tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, false, true, LD_BUF, ES>(buf, W, foff, ld, st);
         __syncthreads();
+        hook();
         tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true, true, true, ES>(buf, W + PI::off2, foff, ld, st);
         __syncthreads();
         tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, true, false, ST_BUF, ES>(buf, W + PI::off3, foff, ld, st);
     } else {
         tile_stage<N, P::R1, 1, INV, NF, FFT_FASTEST, NTHR, false, true, LD_BUF, ES>(buf, W, foff, ld, st);
         __syncthreads();
+        hook();
         tile_stage<N, P::R2, P::R1, INV, NF, FFT_FASTEST, NTHR, true, true, true, ES>(buf, W + PI::off2, foff, ld, st);
         __syncthreads();
         tile_stage<N, P::R3, P::R1 * P::R2, INV, NF, FFT_FASTEST, NTHR, true, true, true, ES>(buf, W + PI::off3, foff, ld, st);
@@ -423,6 +456,21 @@ LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St s
     }
     __syncthreads();
 }
+
+// 16-byte asynchronous global -> shared copies (LDGSTS): prefetch of the next tile while the
+// current one is being transformed
+#ifdef LESGO_EMUL
+LG_HD void cp_async16(cplx* dst, const double* src) { *dst = *reinterpret_cast<const cplx*>(src); }
+LG_HD void cp_async_commit() {}
+LG_HD void cp_async_wait_all() {}
+#else
+LG_D void cp_async16(cplx* dst, const double* src) {
+    const unsigned d = unsigned(__cvta_generic_to_shared(dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+LG_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+LG_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
 
 // length of the concatenated stage-twiddle table of Plan<N> and its (R1..R4) for the host
 struct PlanDesc { int n, r[4], twlen; };

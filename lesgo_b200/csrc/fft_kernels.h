@@ -323,14 +323,36 @@ template <int NIN, int NOUT, bool MULTI> struct YCfg {
     static constexpr int max2(int a, int b) { return a > b ? a : b; }
     template <int N> static constexpr int thr(int tc) { return TileGeom<(N > 0 ? N : 8)>::threads(tc) * (N > 0); }
     // 4 columns = 64 contiguous bytes per row; 8 columns (128 B) measured no faster (30.8 vs 30.0 ms/step)
-    static constexpr int TC = max2(thr<NIN>(4), thr<NOUT>(4)) <= 512 ? 4 : 2;   // (2 columns for the 768 passes: 30.8 ms)
+#ifndef LG_Y12_TC2
+#define LG_Y12_TC2 0
+#endif
+#ifndef LG_Y12_REGS
+#define LG_Y12_REGS 112
+#endif
+    static constexpr int regs0 = max2(TileGeom<(NIN > 0 ? NIN : 8)>::regs * (NIN > 0), TileGeom<(NOUT > 0 ? NOUT : 8)>::regs * (NOUT > 0));
+    // radix-12 plans (the 3/2-grid lengths) spill 300-700 bytes per thread under the 80-register cap;
+    // -DLG_Y12_TC2=1: two columns per tile and LG_Y12_REGS registers.  Measured with 112 (spills remain)
+    // and 160 registers (no spills, 12 warps/SM): pad 3.99 / 4.07 ms, trunc 1.73 / 1.80 ms against
+    // 3.99 / 1.81 ms -- no difference, off by default
+    static constexpr bool R12 = LG_Y12_TC2 && regs0 == 80;
+    static constexpr int TC = (max2(thr<NIN>(4), thr<NOUT>(4)) <= 512 && !R12) ? 4 : 2;   // (2 columns for the 768 passes: 30.8 ms)
     static constexpr int NTHR = ((max2(thr<NIN>(TC), thr<NOUT>(TC)) + 31) / 32) * 32;
-    static constexpr int regs = max2(TileGeom<(NIN > 0 ? NIN : 8)>::regs * (NIN > 0), TileGeom<(NOUT > 0 ? NOUT : 8)>::regs * (NOUT > 0));
+    static constexpr int regs = R12 ? LG_Y12_REGS : regs0;
     static constexpr int SL = SmemLen<NMAX>::value;
     static constexpr int NBUF = MULTI ? 2 : 1;
     static constexpr int TWI = PlanInfo<(NIN > 0 ? NIN : 8)>::twlen * (NIN > 0);
     static constexpr int TWO = PlanInfo<(NOUT > 0 ? NOUT : 8)>::twlen * (NOUT > 0);
-    static constexpr size_t smem = size_t(NBUF * TC * SL + TWI + TWO) * sizeof(cplx);
+    // PREF (-DLG_Y_PREF=1): the next tile is prefetched (cp.async) into a staging buffer while the current
+    // one is being transformed, for the 3/2-rule pad passes (where the staging buffer does not cost a
+    // resident block).  Measured: no gain (4.06 against 3.99 ms) -- the y passes are bound by the
+    // wavefronts they push through the L1/shared-memory data pipe, not by load latency
+    // (profiles/r2_experiments.md).  Off by default.
+#ifndef LG_Y_PREF
+#define LG_Y_PREF 0
+#endif
+    static constexpr bool PREF = LG_Y_PREF && NIN > 0 && NOUT > NIN && !MULTI;
+    static constexpr int STG = PREF ? NIN * TC : 0;
+    static constexpr size_t smem = size_t(NBUF * TC * SL + TWI + TWO + STG) * sizeof(cplx);
     // resident blocks: the register budget is only capped as far as shared memory lets blocks fit
     static constexpr int by_regs = TileGeom<8>::blocks_for(NTHR, regs);
     static constexpr int by_smem = int((227 * 1024) / (smem + 1024)) < 1 ? 1 : int((227 * 1024) / (smem + 1024));
@@ -365,8 +387,33 @@ LG_D cplx y_input(const YField& F, const YArgs& a, const double* src, int k, int
 
 // one work item (column tile of one plane of one field) of the y pass; shared memory is free
 // again when it returns (its last transform ends with a barrier)
+// start the asynchronous copy of work item `work`'s input tile (NIN rows x TC columns) into stg
 template <int NIN, int NOUT, bool MULTI>
-LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, const YArgs& a, unsigned work) {
+LG_D void ypass_prefetch(cplx* stg, const YArgs& a, unsigned work, unsigned nwork) {
+    typedef YCfg<NIN, NOUT, MULTI> C;
+    constexpr int TC = C::TC, NTHR = C::NTHR;
+    if (work < nwork) {
+        const int ntc = (a.ncols + TC - 1) / TC;
+        const YField& F = a.fld[work % unsigned(a.nfields)];
+        const unsigned tile = work / unsigned(a.nfields);
+        const int c0 = int(tile % unsigned(ntc)) * TC;
+        const int k = a.k0 + int(tile / unsigned(ntc));
+        const int f = int(threadIdx.x) % TC;
+        if (c0 + f < a.ncols) {
+            const double* p = F.src + poff(k, a.src_plane, a.src_ring) + 2 * (c0 + f) + long(int(threadIdx.x) / TC) * a.src_row;
+            const long step = long(NTHR / TC) * a.src_row;
+#pragma unroll 4
+            for (int it = threadIdx.x; it < NIN * TC; it += NTHR, p += step) cp_async16(stg + it, p);
+        }
+    }
+    cp_async_commit();
+}
+
+// stg != nullptr: the input tile is already in the staging buffer (ypass_prefetch), and the tile of
+// work item `next` is prefetched into it as soon as the first stage has read it
+template <int NIN, int NOUT, bool MULTI>
+LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, const YArgs& a, unsigned work,
+                     cplx* stg = nullptr, unsigned next = 0, unsigned nwork = 0) {
     typedef YCfg<NIN, NOUT, MULTI> C;
     constexpr int TC = C::TC, NS = C::NS, NTHR = C::NTHR;
     auto sidx = [](int f, int i) { return spad(i) * TC + f; };
@@ -399,21 +446,33 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
                         *reinterpret_cast<cplx*>(dst + long(i) * a.dst_row + 2 * f) = v;
                     });
             } else {
-                fft_tile<NIN, false, TC, true, NTHR, false, !MULTI, TC>(buf, Win, foff,
-                    [&](int f, int i) {
-                        if (!colok) return make_double2(0.0, 0.0);
-                        return y_input(F, a, src, k, c0, i, f);
-                    },
-                    [&](int f, int i, cplx v) {
-                        // keep only the NS rows of the small spectrum (unpadd, fft.f90:86-97)
-                        int is = i;
-                        if (NIN > NS) {
-                            if (i < NS / 2) is = i;
-                            else if (i > NIN - NS / 2) is = i - (NIN - NS);
-                            else return;
-                        }
-                        S[sidx(f, is)] = v;
-                    });
+                auto keep = [&](int f, int i, cplx v) {
+                    // keep only the NS rows of the small spectrum (unpadd, fft.f90:86-97)
+                    int is = i;
+                    if (NIN > NS) {
+                        if (i < NS / 2) is = i;
+                        else if (i > NIN - NS / 2) is = i - (NIN - NS);
+                        else return;
+                    }
+                    S[sidx(f, is)] = v;
+                };
+                if (C::PREF && stg) {
+                    const double sc = F.combo ? F.c0 : 1.0;
+                    fft_tile<NIN, false, TC, true, NTHR, false, !MULTI, TC>(buf, Win, foff,
+                        [&](int f, int i) {
+                            if (!colok) return make_double2(0.0, 0.0);
+                            const cplx v = stg[i * TC + f];
+                            return make_double2(sc * v.x, sc * v.y);
+                        },
+                        keep, [&]() { ypass_prefetch<NIN, NOUT, MULTI>(stg, a, next, nwork); });
+                } else {
+                    fft_tile<NIN, false, TC, true, NTHR, false, !MULTI, TC>(buf, Win, foff,
+                        [&](int f, int i) {
+                            if (!colok) return make_double2(0.0, 0.0);
+                            return y_input(F, a, src, k, c0, i, f);
+                        },
+                        keep);
+                }
             }
         } else {
             for (int it = threadIdx.x; it < TC * NS; it += NTHR) {
@@ -491,6 +550,21 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
     __syncthreads();
     const int ntc = (a.ncols + TC - 1) / TC;
     const long nwork = long(ntc) * a.nplanes * a.nfields;
+    if constexpr (C::PREF) {
+        // fields that need more than a scaled copy on load (y_input) take the direct path
+        bool plain = true;
+        for (int i = 0; i < a.nfields; ++i) plain = plain && !a.fld[i].src2 && !a.fld[i].src3;
+        if (plain) {
+            cplx* stg = Wout + C::TWO;
+            ypass_prefetch<NIN, NOUT, MULTI>(stg, a, blockIdx.x, unsigned(nwork));
+            for (long work = blockIdx.x; work < nwork; work += gridDim.x) {
+                cp_async_wait_all();
+                __syncthreads();
+                ypass_work<NIN, NOUT, MULTI>(buf, S, Win, Wout, a, unsigned(work), stg, unsigned(work + gridDim.x), unsigned(nwork));
+            }
+            return;
+        }
+    }
     for (long work = blockIdx.x; work < nwork; work += gridDim.x)    // round-robin: see k_xfwd
         ypass_work<NIN, NOUT, MULTI>(buf, S, Win, Wout, a, unsigned(work));
 }

@@ -6,7 +6,7 @@ set -e
 cd "$(dirname "$0")"
 mkdir -p _build
 SRC=../../lesgo_b200/csrc
-FLAGS="-O2 -std=c++17 -fPIC -DLESGO_EMUL -ffp-contract=off -I. -Wno-unused-function"
+FLAGS="-O2 -std=c++17 -fPIC -DLESGO_EMUL ${LESGO_EMUL_DEFS} -ffp-contract=off -I. -Wno-unused-function"
 pids=()
 for f in lesgo_gpu xfwd_scale xfwd_vort xfwd_convec xinv ypass pipe bigx comm extras; do
   [ -f $SRC/$f.cu ] || continue

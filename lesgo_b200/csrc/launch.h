@@ -31,6 +31,9 @@ int launch_pipe_deriv(int nx, int ny, bool multi, const ProScale& pro, const XfO
 // fused 3/2-grid x pass of convec (bigx_kernels.h); nx2 = 3 nx / 2
 struct BigxArgs;
 int launch_bigx(int nx2, const BigxArgs& a, const cplx* W, const cplx* Wh, cudaStream_t s);
+// products + forward x transform of convec, marching up z (prodfwd_kernels.h)
+struct ProdArgs;
+int launch_prodfwd(int nx2, const ProdArgs& a, const cplx* W, const cplx* Wh, cudaStream_t s);
 // (nx, ny) pairs the pipelines are instantiated for
 #define LG_PIPE_SIZES(X) X(512, 512) X(1024, 512) X(64, 512)
 

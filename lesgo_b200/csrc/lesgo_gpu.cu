@@ -15,6 +15,7 @@
 #include "launch.h"
 #include "pipe_kernels.h"
 #include "bigx_kernels.h"
+#include "prodfwd_kernels.h"
 
 using namespace lg;
 
@@ -594,6 +595,11 @@ bool reuse_enabled() {
     if (v < 0) { const char* e = std::getenv("LESGO_REUSE"); v = (e && e[0] == '0') ? 0 : 1; }
     return v != 0;
 }
+bool prodfwd_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("LESGO_PRODFWD"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
 bool bigx_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = std::getenv("LESGO_BIGX"); v = (e && e[0] == '1') ? 1 : 0; }   // opt-in, see convec()
@@ -634,7 +640,8 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
     pv.lbc_mom = c->d.lbc_mom; pv.ubc_mom = c->d.ubc_mom;
     ProConvec pc;
     pc.u = c->big[0]; pc.v = c->big[1]; pc.w = c->big[2]; pc.o1 = c->big[3]; pc.o2 = c->big[4]; pc.o3 = c->big[5];
-    pc.lay = c->lay_big(); pc.scale = 1.0 / (double(c->nx2) * double(c->ny2));
+    const double uvw_scale = xs3 ? 1.0 / double(c->ny) : 1.0;    // see the spectral-reuse branch below
+    pc.lay = c->lay_big(); pc.scale = uvw_scale / (double(c->nx2) * double(c->ny2));
     pc.nz = nz; pc.bottom = c->bottom; pc.top = c->top; pc.jzLo = c->jzLo;
     double* out[3] = {RHSx, RHSy, RHSz};
     // Plane chunks, software-pipelined by one plane: the products of plane p need the 3/2-grid
@@ -649,14 +656,13 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
             // Spectral reuse (lesgo_gpu_step only): filt_da left the x spectra of the filtered u, v, w in
             // xs3 (its y-pass output for the field itself), which is what step (1) would
             // recompute from the filtered fields -- up to the factor ny of the unnormalised y round trip.
+            // Every product of step (4) holds exactly one of u, v, w, so that factor is folded into the
+            // products' scale (uvw_scale) instead of costing a multiplication per element here.
             // (Forming the vorticity's x spectra the same way, from the kept derivative spectra and
             // z differences, was measured: the extra strided loads in the y pass cost more than the
             // x-forward pass they replace, profiles/r2_experiments.md.)
             YArgs a = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, 0);
-            for (int i = 0; i < 3; ++i) {
-                a.fld[i].src = xs3[i]; a.fld[i].combo = 1; a.fld[i].c0 = 1.0 / double(c->ny);
-                a.fld[i].out[0] = YOutSpec{c->bb[i], Y_COPY};
-            }
+            for (int i = 0; i < 3; ++i) { a.fld[i].src = xs3[i]; a.fld[i].out[0] = YOutSpec{c->bb[i], Y_COPY}; }
             if (ypass(c, c->ny, c->ny2, a, 3, 0, nz + 1)) return 1;
             if (xfwd(c, false, pv, 3, c->sa + 3, c->plane, c->ld, nxh, c->ny, va, kb)) return 1;
             YArgs b = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, va);
@@ -685,6 +691,23 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
         const int pb = kb == nz + 1 ? nz + 1 : kb - 1;
         if (pb <= pa) continue;
         // (4) products fused into the x forward pass on the 3/2 grid               :172-305
+        if (prodfwd_enabled() && !HP(c) && c->chunk <= 0 && nz >= 2) {
+            // one kernel marching up z per 3/2-grid row: every operand read once (prodfwd_kernels.h)
+            ProdArgs b;
+            for (int i = 0; i < 6; ++i) b.src[i] = c->big[i];
+            for (int i = 0; i < 3; ++i) b.dst[i] = c->bb[i];
+            const Lay lb = c->lay_big();
+            b.splane = lb.plane; b.srow = lb.row; b.dplane = c->plane_bi; b.drow = c->ld;
+            b.ny2 = c->ny2; b.nz = nz; b.bottom = c->bottom; b.top = c->top; b.jzLo = c->jzLo;
+            b.chunk = bigx_chunk(nz); b.nchunks = (nz - 1 + b.chunk - 1) / b.chunk;
+            b.scale = uvw_scale / (double(c->nx2) * double(c->ny2));
+            {
+                ProfScope ps_(c, "xfwd_big");
+                if (launch_prodfwd(c->nx2, b, c->Wxb, c->Whxb, c->stream)) return c->fail("unsupported nx for the 3/2-grid product pass");
+                c->launches++;
+            }
+            for (int i = 0; i < 3; ++i) fill(c, c->bb[i], c->plane_bi, nz, nz + 1, 0.0);   // cc(nz) = 0, :262-268
+        } else
         if (xfwd(c, true, pc, 3, c->bb, c->plane_bi, c->ld, nxh, c->ny2, pa, pb)) return 1;
         // (5) y forward on the 3/2 grid, unpadd (fft.f90:74-99), y inverse          :206-213
         {
@@ -705,7 +728,7 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
         b.plane = c->plane_bi; b.row = c->ld; b.ny2 = c->ny2; b.nz = nz;
         b.bottom = c->bottom; b.top = c->top; b.jzLo = c->jzLo;
         b.chunk = bigx_chunk(nz); b.nchunks = (nz - 1 + b.chunk - 1) / b.chunk;
-        b.scale = 1.0 / (double(c->nx2) * double(c->ny2));
+        b.scale = uvw_scale / (double(c->nx2) * double(c->ny2));
         {
             ProfScope ps_(c, "bigx");
             if (launch_bigx(c->nx2, b, c->Wxb, c->Whxb, c->stream)) return c->fail("unsupported nx for the fused 3/2-grid x pass");

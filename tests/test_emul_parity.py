@@ -96,3 +96,24 @@ def test_emul_multirank_thin_slabs():
     kw = dict(nx=16, ny=16, Nz=8, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5, sgs=True, sgs_model=1,
               molec=True, nu_molec=1e-2)
     check_multirank_steps(emul_library(), kw, 4, nsteps=2, mode="full")
+
+
+@pytest.mark.parametrize("env,grid,what", [
+    ({"LESGO_BIGX": "1"}, "16,16,6", "convec,steps,full"),
+    ({"LESGO_BIGX": "1", "LESGO_BIGX_CHUNK": "2"}, "32,16,7", "convec"),
+    ({"LESGO_PIPE": "1", "LESGO_PIPE_RING": "2"}, "64,512,5", "deriv"),
+    ({"LESGO_XW": "0"}, "16,16,6", "deriv,convec,steps"),
+    ({"LESGO_XW": "2"}, "48,32,4", "deriv,convec,press,steps"),
+    ({"LESGO_REUSE": "0"}, "16,16,6", "steps,full"),
+])
+def test_emul_variants(env, grid, what):
+    """Kernel variants behind environment switches (read once per process -> subprocess)."""
+    import os
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "variant_check.py"), "--emul", "--grid", grid, "--what", what],
+                       env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "variant_check ok" in r.stdout, (env, r.stdout[-2000:], r.stderr[-2000:])

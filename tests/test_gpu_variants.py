@@ -1,0 +1,31 @@
+"""The kernel variants selected by environment switches (read once per process, so each runs in a
+subprocess) must all reproduce the oracle on the B200: warp-scope x passes everywhere / nowhere,
+the plane-pipeline kernel, the fused 3/2-grid x pass, spectral reuse off."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+VARIANTS = [
+    ({"LESGO_XW": "0"}, "16,16,6", "deriv,convec,steps"),
+    ({"LESGO_XW": "2"}, "64,48,6", "deriv,convec,press,steps"),
+    ({"LESGO_XW": "2"}, "512,64,3", "deriv,convec"),
+    ({"LESGO_BIGX": "1"}, "32,32,9", "convec,steps,full"),
+    ({"LESGO_BIGX": "1", "LESGO_BIGX_CHUNK": "3"}, "128,64,8", "convec,steps"),
+    ({"LESGO_PIPE": "1"}, "512,512,5", "deriv"),
+    ({"LESGO_PIPE": "1", "LESGO_PIPE_RING": "2"}, "64,512,6", "deriv,steps"),
+    ({"LESGO_REUSE": "0"}, "32,32,6", "steps,full"),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env,grid,what", VARIANTS)
+def test_variant_on_gpu(env, grid, what):
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "variant_check.py"), "--grid", grid, "--what", what],
+                       env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "variant_check ok" in r.stdout, (env, r.stdout[-2000:], r.stderr[-2000:])

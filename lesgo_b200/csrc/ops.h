@@ -628,21 +628,46 @@ static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __re
     double u = ddiv(*at(1), -1.0);
     *at(1) = u;
     double bet = -1.0;
-    for (int j = 2; j <= n; ++j) {
-        const double a = (j == n) ? -1.0 : c3;
-        const double b = (j == n) ? 1.0 : bb;
-        double* pj = at(j);
-        const double r = *pj;
-        const double gm = gam[(long(j) * g.cy + jl) * g.lh + jx];
-        bet = dsub(b, dmul(a, gm));
-        u = ddiv(dsub(r, dmul(a, u)), bet);
-        *pj = u;
+    // The recurrence is serial in j but its operands are not: fetch UN rows ahead so the sweep pays one
+    // memory latency per UN rows instead of one per row (a many-rank run has too few modes per GPU to
+    // hide it with other threads).  Same arithmetic, same order.
+    constexpr int UN = 8;
+    for (int j0 = 2; j0 <= n; j0 += UN) {
+        double* pj[UN];
+        double r[UN], gm[UN];
+#pragma unroll
+        for (int q = 0; q < UN; ++q) {
+            const int j = j0 + q;
+            if (j <= n) { pj[q] = at(j); r[q] = *pj[q]; gm[q] = gam[(long(j) * g.cy + jl) * g.lh + jx]; }
+        }
+#pragma unroll
+        for (int q = 0; q < UN; ++q) {
+            const int j = j0 + q;
+            if (j <= n) {
+                const double a = (j == n) ? -1.0 : c3;
+                const double b = (j == n) ? 1.0 : bb;
+                bet = dsub(b, dmul(a, gm[q]));
+                u = ddiv(dsub(r[q], dmul(a, u)), bet);
+                *pj[q] = u;
+            }
+        }
     }
-    for (int j = n - 1; j >= 1; --j) {
-        const double gm = gam[(long(j + 1) * g.cy + jl) * g.lh + jx];
-        double* pj = at(j);
-        u = dsub(*pj, dmul(gm, u));
-        *pj = u;
+    for (int j0 = n - 1; j0 >= 1; j0 -= UN) {
+        double* pj[UN];
+        double r[UN], gm[UN];
+#pragma unroll
+        for (int q = 0; q < UN; ++q) {
+            const int j = j0 - q;
+            if (j >= 1) { pj[q] = at(j); r[q] = *pj[q]; gm[q] = gam[(long(j + 1) * g.cy + jl) * g.lh + jx]; }
+        }
+#pragma unroll
+        for (int q = 0; q < UN; ++q) {
+            const int j = j0 - q;
+            if (j >= 1) {
+                u = dsub(r[q], dmul(gm[q], u));
+                *pj[q] = u;
+            }
+        }
     }
 }
 

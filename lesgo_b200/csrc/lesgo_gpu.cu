@@ -455,9 +455,37 @@ int glue_fused(lesgo_gpu_ctx* c, int mode, double* rhs, const double* b, double*
     return 0;
 }
 
+// Consecutive fills inside a FillGroup scope are issued as ONE launch when the scope ends.
+struct FillGroup {
+    lesgo_gpu_ctx* c;
+    FillList l;
+    FillGroup* prev;
+    static thread_local FillGroup* cur;
+    explicit FillGroup(lesgo_gpu_ctx* c_) : c(c_), prev(cur) { l.count = 0; cur = this; }
+    void flush() {
+        if (l.count == 0) return;
+        long nmax = 0;
+        for (int i = 0; i < l.count; ++i) nmax = l.n[i] > nmax ? l.n[i] : nmax;
+        ProfScope ps_(c, "fill");
+        LG_LAUNCH(k_fill_multi, dim3(grid1d(nmax), l.count), dim3(kBlock), 0, c->stream, l);
+        c->launches++;
+        l.count = 0;
+    }
+    void add(double* p, long n, double v) {
+        if (l.count == FillList::kMax) flush();
+        l.p[l.count] = p; l.n[l.count] = n; l.v[l.count] = v; ++l.count;
+    }
+    ~FillGroup() { flush(); cur = prev; }
+};
+thread_local FillGroup* FillGroup::cur = nullptr;
+
 int fill(lesgo_gpu_ctx* c, double* f, long plane, int k0, int k1, double v) {
     if (k1 <= k0) return 0;
     if (Staged* h = HP(c)) h->touch(f, k0, k1);
+    if (FillGroup::cur && FillGroup::cur->c == c) {
+        FillGroup::cur->add(f + long(k0) * plane, plane * (k1 - k0), v);
+        return 0;
+    }
     ProfScope ps_(c, "fill");
     LG_LAUNCH(k_fill, dim3(grid1d(plane * (k1 - k0))), dim3(kBlock), 0, c->stream, f, plane, k0, k1, v);
     c->launches++;
@@ -564,6 +592,7 @@ int ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
         }
         if (hp) hp->done(dfdz, ka, kb);
     }
+    FillGroup fg_(c);
     fill(c, dfdz, c->plane, 0, 1, kBogus);                           // derivatives.f90:236-238
     if (c->bottom) fill(c, dfdz, c->plane, 1, 2, kBogus);            // :255-257
     if (c->top) fill(c, dfdz, c->plane, nz, nz + 1, kBogus);         // :258-260
@@ -585,6 +614,7 @@ int ddz_w(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
         }
         if (hp) hp->done(dfdz, ka, kb);
     }
+    FillGroup fg_(c);
     if (c->bottom) fill(c, dfdz, c->plane, 0, 1, kBogus);            // :303-305
     fill(c, dfdz, c->plane, nz, nz + 1, kBogus);                     // :308
     return 0;
@@ -706,7 +736,7 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
                 if (launch_prodfwd(c->nx2, b, c->Wxb, c->Whxb, c->stream)) return c->fail("unsupported nx for the 3/2-grid product pass");
                 c->launches++;
             }
-            for (int i = 0; i < 3; ++i) fill(c, c->bb[i], c->plane_bi, nz, nz + 1, 0.0);   // cc(nz) = 0, :262-268
+            { FillGroup fg_(c); for (int i = 0; i < 3; ++i) fill(c, c->bb[i], c->plane_bi, nz, nz + 1, 0.0); }   // cc(nz) = 0, :262-268
         } else
         if (xfwd(c, true, pc, 3, c->bb, c->plane_bi, c->ld, nxh, c->ny2, pa, pb)) return 1;
         // (5) y forward on the 3/2 grid, unpadd (fft.f90:74-99), y inverse          :206-213
@@ -741,6 +771,7 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
         if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, 1, nz + 1, 1, fz)) return 1;
     }
     // :319-332
+    FillGroup fg_(c);
     fill(c, RHSx, c->plane, 0, 1, kBogus); fill(c, RHSy, c->plane, 0, 1, kBogus); fill(c, RHSz, c->plane, 0, 1, kBogus);
     fill(c, RHSx, c->plane, nz, nz + 1, kBogus); fill(c, RHSy, c->plane, nz, nz + 1, kBogus);
     if (!c->top) fill(c, RHSz, c->plane, nz, nz + 1, kBogus);
@@ -901,6 +932,7 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
             }
         }
     }
+    FillGroup fg_(c);
     fill(c, dpdx, c->plane, nz, nz + 1, kBogus);
     fill(c, dpdy, c->plane, nz, nz + 1, kBogus);
     if (!c->top) { fill(c, p, c->plane, nz, nz + 1, kBogus); fill(c, dpdz, c->plane, nz, nz + 1, kBogus); }
@@ -1146,9 +1178,12 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
         }
     }
     // :299-308
-    fill(c, F[LG_U], c->plane, 0, 1, kBogus); fill(c, F[LG_V], c->plane, 0, 1, kBogus); fill(c, F[LG_W], c->plane, 0, 1, kBogus);
-    fill(c, F[LG_U], c->plane, nz, nz + 1, kBogus); fill(c, F[LG_V], c->plane, nz, nz + 1, kBogus);
-    if (!c->top) fill(c, F[LG_W], c->plane, nz, nz + 1, kBogus);
+    {
+        FillGroup fg_(c);
+        fill(c, F[LG_U], c->plane, 0, 1, kBogus); fill(c, F[LG_V], c->plane, 0, 1, kBogus); fill(c, F[LG_W], c->plane, 0, 1, kBogus);
+        fill(c, F[LG_U], c->plane, nz, nz + 1, kBogus); fill(c, F[LG_V], c->plane, nz, nz + 1, kBogus);
+        if (!c->top) fill(c, F[LG_W], c->plane, nz, nz + 1, kBogus);
+    }
     // :317 press_stag_array, with :321-326 (RHS -= grad p) and project (forcing.f90:171-207) fused into
     // the epilogues of its last passes.  press reads u, v, w only in its first pass.
     {

@@ -251,6 +251,23 @@ static __global__ void k_fill(double* __restrict__ dst, long plane, int k0, int 
     for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) p[t] = value;
 }
 
+// several plane fills in one launch (blockIdx.y = entry): the BOGUS poisoning at the end of a routine is
+// 3-6 single-plane fills, each a launch of its own otherwise (launch-bound on a many-rank slab)
+struct FillList {
+    static constexpr int kMax = 8;
+    double* p[kMax];
+    long n[kMax];
+    double v[kMax];
+    int count;
+};
+static __global__ void k_fill_multi(const FillList l) {
+    const int e = blockIdx.y;
+    double* p = l.p[e];
+    const long n = l.n[e];
+    const double v = l.v[e];
+    for (long t = long(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x) p[t] = v;
+}
+
 // max |f| over 1:nx, 1:ny, planes k0..k1-1 -> atomicMax on the bit pattern (values >= 0)
 static __global__ void k_absmax(const double* __restrict__ f, Lay lay, int nx, int ny, int k0, int k1,
                          unsigned long long* __restrict__ out) {

@@ -292,6 +292,7 @@ struct YOutSpec {
 struct YField {
     const double* src;
     YOutSpec out[3];
+    double* out2;            // NOUT2 kernels: also the 3/2-rule padded inverse transform of the spectrum (or null)
     // optional linear combination formed while loading (spectral reuse in lesgo_gpu_step, where the
     // vorticity's x spectra are combinations of x spectra filt_da already produced):
     //     in(k) = c0 * src(k) + c1 * (src2(k) - src2(k-1)) + c2 * src3(k)
@@ -313,12 +314,19 @@ struct YArgs {
     int zero_col;        // >= 0: also write zeros into this complex column of every output row
     int keep_nyq_row;    // 1: raw transform (do not zero ky = ns/2)
     int src_ring, dst_ring;   // > 0: src / dst are rings of that many planes
+    long dst2_plane;          // layout of the out2 arrays
+    int dst2_row;
 };
 
 // MULTI = several outputs per field: the spectrum is kept in its own buffer S while the
 // inverse transforms run in the work buffer; otherwise one buffer serves both.
-template <int NIN, int NOUT, bool MULTI> struct YCfg {
-    static constexpr int NMAX = NIN > NOUT ? NIN : NOUT;
+// NOUT2 > 0 (with NIN == NOUT, MULTI): one more inverse transform of the SAME spectrum, padded to length
+// NOUT2 -- lesgo_gpu_step's filt_da hands convec the 3/2-grid y transform of u, v, w directly, which
+// saves convec's own y pass over those three fields (forward transform + read of the x spectra).
+template <int NIN, int NOUT, bool MULTI, int NOUT2 = 0> struct YCfg {
+    static_assert(NOUT2 == 0 || (MULTI && NIN == NOUT && NOUT2 > NOUT), "NOUT2 rides on the same-size multi-output pass");
+    static constexpr int NMAX0 = NIN > NOUT ? NIN : NOUT;
+    static constexpr int NMAX = NMAX0 > NOUT2 ? NMAX0 : NOUT2;
     static constexpr int NS = (NIN == 0) ? NOUT : ((NOUT == 0) ? NIN : (NIN < NOUT ? NIN : NOUT));  // spectral (small) length
     static constexpr int max2(int a, int b) { return a > b ? a : b; }
     template <int N> static constexpr int thr(int tc) { return TileGeom<(N > 0 ? N : 8)>::threads(tc) * (N > 0); }
@@ -338,10 +346,14 @@ template <int NIN, int NOUT, bool MULTI> struct YCfg {
     static constexpr int TC = (max2(thr<NIN>(4), thr<NOUT>(4)) <= 512 && !R12) ? 4 : 2;   // (2 columns for the 768 passes: 30.8 ms)
     static constexpr int NTHR = ((max2(thr<NIN>(TC), thr<NOUT>(TC)) + 31) / 32) * 32;
     static constexpr int regs = R12 ? LG_Y12_REGS : regs0;
-    static constexpr int SL = SmemLen<NMAX>::value;
+    static constexpr int SL = SmemLen<NMAX>::value;          // work buffer row count (padded)
+    static constexpr int SLS = SmemLen<NS>::value;           // spectrum buffer (MULTI)
     static constexpr int NBUF = MULTI ? 2 : 1;
+    static constexpr int BUFS = TC * SL + (MULTI ? TC * (NOUT2 > 0 ? SLS : SL) : 0);
     static constexpr int TWI = PlanInfo<(NIN > 0 ? NIN : 8)>::twlen * (NIN > 0);
-    static constexpr int TWO = PlanInfo<(NOUT > 0 ? NOUT : 8)>::twlen * (NOUT > 0);
+    // with NOUT2 the forward and inverse tables of the same length are stored once (shared memory is tight)
+    static constexpr int TWO = (NOUT2 > 0) ? 0 : PlanInfo<(NOUT > 0 ? NOUT : 8)>::twlen * (NOUT > 0);
+    static constexpr int TWO2 = PlanInfo<(NOUT2 > 0 ? NOUT2 : 8)>::twlen * (NOUT2 > 0);
     // PREF (-DLG_Y_PREF=1): the next tile is prefetched (cp.async) into a staging buffer while the current
     // one is being transformed, for the 3/2-rule pad passes (where the staging buffer does not cost a
     // resident block).  Measured: no gain (4.06 against 3.99 ms) -- the y passes are bound by the
@@ -352,7 +364,7 @@ template <int NIN, int NOUT, bool MULTI> struct YCfg {
 #endif
     static constexpr bool PREF = LG_Y_PREF && NIN > 0 && NOUT > NIN && !MULTI;
     static constexpr int STG = PREF ? NIN * TC : 0;
-    static constexpr size_t smem = size_t(NBUF * TC * SL + TWI + TWO + STG) * sizeof(cplx);
+    static constexpr size_t smem = size_t(BUFS + TWI + TWO + TWO2 + STG) * sizeof(cplx);
     // resident blocks: the register budget is only capped as far as shared memory lets blocks fit
     static constexpr int by_regs = TileGeom<8>::blocks_for(NTHR, regs);
     static constexpr int by_smem = int((227 * 1024) / (smem + 1024)) < 1 ? 1 : int((227 * 1024) / (smem + 1024));
@@ -411,10 +423,10 @@ LG_D void ypass_prefetch(cplx* stg, const YArgs& a, unsigned work, unsigned nwor
 
 // stg != nullptr: the input tile is already in the staging buffer (ypass_prefetch), and the tile of
 // work item `next` is prefetched into it as soon as the first stage has read it
-template <int NIN, int NOUT, bool MULTI>
+template <int NIN, int NOUT, bool MULTI, int NOUT2 = 0>
 LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, const YArgs& a, unsigned work,
-                     cplx* stg = nullptr, unsigned next = 0, unsigned nwork = 0) {
-    typedef YCfg<NIN, NOUT, MULTI> C;
+                     cplx* stg = nullptr, unsigned next = 0, unsigned nwork = 0, const cplx* Wout2 = nullptr) {
+    typedef YCfg<NIN, NOUT, MULTI, NOUT2> C;
     constexpr int TC = C::TC, NS = C::NS, NTHR = C::NTHR;
     auto sidx = [](int f, int i) { return spad(i) * TC + f; };
     auto foff = [](int f) { return f; };
@@ -524,6 +536,24 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
                     });
             }
         }
+        if constexpr (NOUT2 > 0) {
+            if (F.out2) {
+                // padd (fft.f90:60-69) + inverse transform of length NOUT2 of the same spectrum
+                double* dst2 = F.out2 + long(k) * a.dst2_plane + 2 * c0;
+                fft_tile<NOUT2, true, TC, true, NTHR, false, false, TC>(buf, Wout2, foff,
+                    [&](int f, int i) {
+                        int is;
+                        if (i < NS / 2) is = i;
+                        else if (i > NOUT2 - NS / 2) is = i - (NOUT2 - NS);
+                        else return make_double2(0.0, 0.0);
+                        return S[sidx(f, is)];
+                    },
+                    [&](int f, int i, cplx v) {
+                        if (!colok) return;
+                        *reinterpret_cast<cplx*>(dst2 + long(i) * a.dst2_row + 2 * f) = v;
+                    });
+            }
+        }
         if (a.zero_col >= 0 && c0 == 0) {
             constexpr int NR = NOUT > 0 ? NOUT : NIN;
             for (int o = 0; o < a.nout; ++o) {
@@ -535,18 +565,21 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
     }
 }
 
-template <int NIN, int NOUT, bool MULTI>
-__global__ void __launch_bounds__(YCfg<NIN, NOUT, MULTI>::NTHR, YCfg<NIN, NOUT, MULTI>::MINB)
-k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cplx* __restrict__ Woutg) {
-    typedef YCfg<NIN, NOUT, MULTI> C;
+template <int NIN, int NOUT, bool MULTI, int NOUT2 = 0>
+__global__ void __launch_bounds__(YCfg<NIN, NOUT, MULTI, NOUT2>::NTHR, YCfg<NIN, NOUT, MULTI, NOUT2>::MINB)
+k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cplx* __restrict__ Woutg,
+        const cplx* __restrict__ Wout2g = nullptr) {
+    typedef YCfg<NIN, NOUT, MULTI, NOUT2> C;
     constexpr int TC = C::TC, SL = C::SL;
     LG_DYN_SMEM(cplx, sm);
     cplx* buf = sm;                                     // work buffer
     cplx* S = MULTI ? sm + TC * SL : sm;                // spectrum of the tile (NS rows used)
-    cplx* Win = sm + C::NBUF * TC * SL;
-    cplx* Wout = Win + C::TWI;
+    cplx* Win = sm + C::BUFS;
+    cplx* Wout = NOUT2 > 0 ? Win : Win + C::TWI;        // NOUT2: same length, same table
+    cplx* Wout2 = Win + C::TWI + C::TWO;
     if (NIN > 0) load_table(Win, Wing, C::TWI);
-    if (NOUT > 0) load_table(Wout, Woutg, C::TWO);
+    if (NOUT > 0 && NOUT2 == 0) load_table(Wout, Woutg, C::TWO);
+    if (NOUT2 > 0) load_table(Wout2, Wout2g, C::TWO2);
     __syncthreads();
     const int ntc = (a.ncols + TC - 1) / TC;
     const long nwork = long(ntc) * a.nplanes * a.nfields;
@@ -555,7 +588,7 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
         bool plain = true;
         for (int i = 0; i < a.nfields; ++i) plain = plain && !a.fld[i].src2 && !a.fld[i].src3;
         if (plain) {
-            cplx* stg = Wout + C::TWO;
+            cplx* stg = Wout2 + C::TWO2;
             ypass_prefetch<NIN, NOUT, MULTI>(stg, a, blockIdx.x, unsigned(nwork));
             for (long work = blockIdx.x; work < nwork; work += gridDim.x) {
                 cp_async_wait_all();
@@ -566,7 +599,7 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
         }
     }
     for (long work = blockIdx.x; work < nwork; work += gridDim.x)    // round-robin: see k_xfwd
-        ypass_work<NIN, NOUT, MULTI>(buf, S, Win, Wout, a, unsigned(work));
+        ypass_work<NIN, NOUT, MULTI, NOUT2>(buf, S, Win, Wout, a, unsigned(work), nullptr, 0, 0, Wout2);
 }
 
 }  // namespace lg

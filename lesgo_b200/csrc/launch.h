@@ -17,6 +17,8 @@ int launch_xinv_fused(int NX, const XiSrc& in, const EpiFused& epi, int nfields,
                       const cplx* W, const cplx* Wh, cudaStream_t s);
 int launch_ypass(int nin, int nout, const YArgs& a, int nfields, int nplanes, const cplx* Win,
                  const cplx* Wout, cudaStream_t s);
+// derivative pass of length ny that also emits the padded (3 ny / 2) inverse transform into fld[].out2
+int launch_ypass_pad2(int ny, const YArgs& a, int nfields, int nplanes, const cplx* Ws, const cplx* Wb, cudaStream_t s);
 bool size_supported(int n_small);
 // radices and stage-twiddle-table length of the plan for complex length n (false if none)
 bool plan_lookup(int n, PlanDesc* out);

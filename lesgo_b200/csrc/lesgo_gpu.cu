@@ -53,8 +53,6 @@ struct lesgo_gpu_ctx {
     double* sa[kMaxFields] = {nullptr};    // small spectra / intermediates, (ld, ny, 0:nz)
     double* bb[kMaxFields] = {nullptr};    // big-y intermediates, (ld, ny2, 0:nz)
     double* big[kMaxFields] = {nullptr};   // 3/2-grid physical fields, (ld_big, ny2, 0:nz)
-    double* xs3[3] = {nullptr};            // x spectra (times ny) of the filtered u, v, w kept from filt_da to
-                                           // convec inside lesgo_gpu_step (spectral reuse)
     double* cc[3] = {nullptr};             // big-y x spectra of the products cx, cy, cz (fused 3/2-grid x pass)
     double* gam = nullptr;                 // tridiagonal gam(j) table (lh, ny, 0:nzt+1)
     double* work[13] = {nullptr};          // S11..S33, Nu_t, six stress-gradient temporaries (mode 1)
@@ -518,9 +516,10 @@ int chunk_of(const lesgo_gpu_ctx* c, int divisor) {
     return ch < 1 ? 1 : ch;
 }
 
-// keep != nullptr (with fout): the y-pass output for f itself, i.e. the x spectrum of the filtered field
-// times ny, is written to keep and stays valid after the call (lesgo_gpu_step hands it to convec)
-int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx, double* dfdy, double* keep = nullptr) {
+// bigy != nullptr (filt_da inside lesgo_gpu_step): the y pass also writes the 3/2-rule padded inverse
+// transform of the field's spectrum -- (ld, 3ny/2, 0:nz), what convec's own pad pass would produce
+// from the filtered field -- which convec then takes over instead of transforming u, v, w again
+int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx, double* dfdy, double* bigy = nullptr) {
     if (need_small(c, 4)) return 1;
     const int nz = c->nz;
     ProScale pro;
@@ -531,13 +530,13 @@ int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx
     const double* xs[3];
     double* xd[3];
     int n = 0;
-    auto mid = [&](int i) { return (keep && i == 0 && fout) ? keep : c->sa[1 + i]; };
+    auto mid = [&](int i) { return c->sa[1 + i]; };
     if (fout) { a.fld[0].out[n] = YOutSpec{mid(n), Y_COPY}; xs[n] = mid(n); xd[n] = fout; ++n; }
     if (dfdx) { a.fld[0].out[n] = YOutSpec{mid(n), Y_IKX}; xs[n] = mid(n); xd[n] = dfdx; ++n; }
     if (dfdy) { a.fld[0].out[n] = YOutSpec{mid(n), Y_IKY}; xs[n] = mid(n); xd[n] = dfdy; ++n; }
     a.nout = n;
     // plane pipeline: all three passes in one persistent kernel, intermediates in L2-resident rings
-    if (pipe_enabled() && !keep && !HP(c) && c->chunk <= 0) {
+    if (pipe_enabled() && !bigy && !HP(c) && c->chunk <= 0) {
         int ntr = 0;
         if (fout || dfdx) ++ntr;
         if (dfdy) ++ntr;
@@ -570,7 +569,12 @@ int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx
         if (hp) hp->need(kb - 1);
         if (xfwd(c, false, pro, 1, d0, c->plane, c->ld, c->nx / 2, c->ny, ka, kb)) return 1;
         a.k0 = ka;
-        if (ypass(c, c->ny, c->ny, a, 1, ka, kb)) return 1;
+        if (bigy) {
+            a.fld[0].out2 = bigy; a.dst2_plane = c->plane_bi; a.dst2_row = c->ld;
+            ProfScope ps_(c, "ypass_deriv");
+            if (launch_ypass_pad2(c->ny, a, 1, kb - ka, c->Wy, c->Wyb, c->stream)) return c->fail("unsupported ny for y pass");
+            c->launches++;
+        } else if (ypass(c, c->ny, c->ny, a, 1, ka, kb)) return 1;
         if (xinv(c, false, xs, c->plane, c->ld, c->nx / 2, n, xd, c->lay(), c->ny, ka, kb)) return 1;
         if (hp) for (int i = 0; i < n; ++i) hp->done(xd[i], ka, kb);
     }
@@ -651,7 +655,7 @@ int bigx_chunk(int nz) {
 int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, const double* dudy,
            const double* dudz, const double* dvdx, const double* dvdz, const double* dwdx,
            const double* dwdy, double* RHSx, double* RHSy, double* RHSz, const Fuse* fz = nullptr,
-           double* const* xs3 = nullptr) {
+           bool uvw_ready = false) {
     // fused 3/2-grid x pass (LESGO_BIGX=1; off by default: 9.1 ms against 8.0 ms for the two separate passes,
     // profiles/r2_experiments.md), never with the host-array pipeline or plane chunks
     const bool fused_x = bigx_enabled() && !HP(c) && c->chunk <= 0 && c->nz >= 2;
@@ -670,8 +674,7 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
     pv.lbc_mom = c->d.lbc_mom; pv.ubc_mom = c->d.ubc_mom;
     ProConvec pc;
     pc.u = c->big[0]; pc.v = c->big[1]; pc.w = c->big[2]; pc.o1 = c->big[3]; pc.o2 = c->big[4]; pc.o3 = c->big[5];
-    const double uvw_scale = xs3 ? 1.0 / double(c->ny) : 1.0;    // see the spectral-reuse branch below
-    pc.lay = c->lay_big(); pc.scale = uvw_scale / (double(c->nx2) * double(c->ny2));
+    pc.lay = c->lay_big(); pc.scale = 1.0 / (double(c->nx2) * double(c->ny2));
     pc.nz = nz; pc.bottom = c->bottom; pc.top = c->top; pc.jzLo = c->jzLo;
     double* out[3] = {RHSx, RHSy, RHSz};
     // Plane chunks, software-pipelined by one plane: the products of plane p need the 3/2-grid
@@ -682,18 +685,14 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
         const int kb = ka + ch < nz + 1 ? ka + ch : nz + 1;
         const int va = ka < 1 ? 1 : ka;                 // vorticity exists on planes 1..nz
         if (Staged* hp = HP(c)) hp->need(kb);           // the wall-plane vorticity reads one plane up
-        if (xs3) {
-            // Spectral reuse (lesgo_gpu_step only): filt_da left the x spectra of the filtered u, v, w in
-            // xs3 (its y-pass output for the field itself), which is what step (1) would
-            // recompute from the filtered fields -- up to the factor ny of the unnormalised y round trip.
-            // Every product of step (4) holds exactly one of u, v, w, so that factor is folded into the
-            // products' scale (uvw_scale) instead of costing a multiplication per element here.
-            // (Forming the vorticity's x spectra the same way, from the kept derivative spectra and
-            // z differences, was measured: the extra strided loads in the y pass cost more than the
-            // x-forward pass they replace, profiles/r2_experiments.md.)
-            YArgs a = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, 0);
-            for (int i = 0; i < 3; ++i) { a.fld[i].src = xs3[i]; a.fld[i].out[0] = YOutSpec{c->bb[i], Y_COPY}; }
-            if (ypass(c, c->ny, c->ny2, a, 3, 0, nz + 1)) return 1;
+        if (uvw_ready) {
+            // Spectral reuse (lesgo_gpu_step only): filt_da's y pass already wrote the 3/2-grid y transforms
+            // of the filtered u, v, w into bb[0..2] (k_ypass<ny, ny, multi, 3ny/2>), i.e. what steps (1)-(2)
+            // would recompute from the filtered fields (same spectrum, same padding, same inverse
+            // transform).  Only the vorticity goes through (1)-(2).
+            // (Forming the vorticity's x spectra from kept derivative spectra and z differences was
+            // measured too: the extra strided loads in the y pass cost more than the x-forward pass
+            // they replace, profiles/r2_experiments.md.)
             if (xfwd(c, false, pv, 3, c->sa + 3, c->plane, c->ld, nxh, c->ny, va, kb)) return 1;
             YArgs b = yargs(c, c->plane, c->ld, c->plane_bi, c->ld, nxh, va);
             for (int i = 0; i < 3; ++i) { b.fld[i].src = c->sa[3 + i]; b.fld[i].out[0] = YOutSpec{c->bb[3 + i], Y_COPY}; }
@@ -730,7 +729,7 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
             b.splane = lb.plane; b.srow = lb.row; b.dplane = c->plane_bi; b.drow = c->ld;
             b.ny2 = c->ny2; b.nz = nz; b.bottom = c->bottom; b.top = c->top; b.jzLo = c->jzLo;
             b.chunk = bigx_chunk(nz); b.nchunks = (nz - 1 + b.chunk - 1) / b.chunk;
-            b.scale = uvw_scale / (double(c->nx2) * double(c->ny2));
+            b.scale = 1.0 / (double(c->nx2) * double(c->ny2));
             {
                 ProfScope ps_(c, "xfwd_big");
                 if (launch_prodfwd(c->nx2, b, c->Wxb, c->Whxb, c->stream)) return c->fail("unsupported nx for the 3/2-grid product pass");
@@ -758,7 +757,7 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
         b.plane = c->plane_bi; b.row = c->ld; b.ny2 = c->ny2; b.nz = nz;
         b.bottom = c->bottom; b.top = c->top; b.jzLo = c->jzLo;
         b.chunk = bigx_chunk(nz); b.nchunks = (nz - 1 + b.chunk - 1) / b.chunk;
-        b.scale = uvw_scale / (double(c->nx2) * double(c->ny2));
+        b.scale = 1.0 / (double(c->nx2) * double(c->ny2));
         {
             ProfScope ps_(c, "bigx");
             if (launch_bigx(c->nx2, b, c->Wxb, c->Whxb, c->stream)) return c->fail("unsupported nx for the fused 3/2-grid x pass");
@@ -1139,15 +1138,14 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     std::swap(c->fields[LG_RHSY], c->fields[LG_RHSY_F]); std::swap(F[LG_RHSY], F[LG_RHSY_F]);
     std::swap(c->fields[LG_RHSZ], c->fields[LG_RHSZ_F]); std::swap(F[LG_RHSZ], F[LG_RHSZ_F]);
     // :161-172
-    // spectral reuse: keep the x spectra filt_da produces for convec (LESGO_REUSE=0: off)
+    // spectral reuse: filt_da also emits the 3/2-grid y transforms of u, v, w for convec (LESGO_REUSE=0: off)
     const bool reuse = reuse_enabled() && c->chunk == 0 && !HP(c);
     if (reuse)
         for (int i = 0; i < 3; ++i)
-            if (dev_alloc(c, &c->xs3[i], size_t(c->plane) * (nz + 1))) return 1;
-    double* const* kp = reuse ? c->xs3 : nullptr;
-    if (spectral_deriv(c, F[LG_U], F[LG_U], F[LG_DUDX], F[LG_DUDY], kp ? kp[0] : nullptr)) return 1;
-    if (spectral_deriv(c, F[LG_V], F[LG_V], F[LG_DVDX], F[LG_DVDY], kp ? kp[1] : nullptr)) return 1;
-    if (spectral_deriv(c, F[LG_W], F[LG_W], F[LG_DWDX], F[LG_DWDY], kp ? kp[2] : nullptr)) return 1;
+            if (dev_alloc(c, &c->bb[i], size_t(c->plane_bi) * (nz + 1))) return 1;
+    if (spectral_deriv(c, F[LG_U], F[LG_U], F[LG_DUDX], F[LG_DUDY], reuse ? c->bb[0] : nullptr)) return 1;
+    if (spectral_deriv(c, F[LG_V], F[LG_V], F[LG_DVDX], F[LG_DVDY], reuse ? c->bb[1] : nullptr)) return 1;
+    if (spectral_deriv(c, F[LG_W], F[LG_W], F[LG_DWDX], F[LG_DWDY], reuse ? c->bb[2] : nullptr)) return 1;
     ddz_uv(c, F[LG_U], F[LG_DUDZ]);
     ddz_uv(c, F[LG_V], F[LG_DVDZ]);
     ddz_w(c, F[LG_W], F[LG_DWDZ]);
@@ -1169,7 +1167,7 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
         // epilogue of the last pass updates them -- but only when the whole slab is one chunk
         const Fuse* use = c->chunk == 0 ? &fz : nullptr;
         if (convec(c, F[LG_U], F[LG_V], F[LG_W], F[LG_DUDY], F[LG_DUDZ], F[LG_DVDX], F[LG_DVDZ], F[LG_DWDX],
-                   F[LG_DWDY], F[LG_RHSX], F[LG_RHSY], F[LG_RHSZ], use, kp)) return 1;
+                   F[LG_DWDY], F[LG_RHSX], F[LG_RHSY], F[LG_RHSZ], use, reuse)) return 1;
         if (!use) {
             const int kw = c->top ? nz + 1 : nz;
             glue_fused(c, F_RHS_AB2, F[LG_RHSX], F[LG_DIVTX], F[LG_RHSX_F], F[LG_U], 1, nz, 0, fz.first_step, sp->mean_p_force_x, sp->dt, sp->tadv1, sp->tadv2);

@@ -50,6 +50,26 @@ int launch_ypass(int nin, int nout, const YArgs& a, int nfields, int nplanes, co
     LG_Y_RAW(576) LG_Y_RAW(768) LG_Y_RAW(1536)
     return -1;
 }
+// same-size multi-output pass that ALSO writes the 3/2-rule padded inverse transform (fld[].out2)
+template <int NS_, int NB_>
+static int launch_y_pad2(const YArgs& a0, int nfields, int nplanes, const cplx* Ws, const cplx* Wb, cudaStream_t s) {
+    typedef YCfg<NS_, NS_, true, NB_> C;
+    static bool attr = false;
+    if (!attr) { set_smem(k_ypass<NS_, NS_, true, NB_>, C::smem); attr = true; }
+    if (nplanes <= 0 || nfields <= 0) return 0;
+    YArgs a = a0;
+    a.nplanes = nplanes;
+    a.nfields = nfields;
+    const long ntiles = long((a.ncols + C::TC - 1) / C::TC) * nplanes;
+    dim3 grid(persistent_blocks(C::smem, ntiles * nfields, C::MINB));
+    LG_LAUNCH((k_ypass<NS_, NS_, true, NB_>), grid, dim3(C::NTHR), C::smem, s, a, Ws, Ws, Wb);
+    return 0;
+}
+#define LG_Y_PAD2(S, B) if (ny == S) return launch_y_pad2<S, B>(a, nfields, nplanes, Ws, Wb, s);
+int launch_ypass_pad2(int ny, const YArgs& a, int nfields, int nplanes, const cplx* Ws, const cplx* Wb, cudaStream_t s) {
+    LG_SIZE_PAIRS(LG_Y_PAD2)
+    return -1;
+}
 #define LG_SUP(S, B) if (n == S) return true;
 bool plan_lookup(int n, PlanDesc* out) {
 #define LG_PL(N) if (n == N) { *out = plan_desc<N>(); return true; }

@@ -45,8 +45,9 @@ template <class K> inline void set_smem(K kernel, size_t bytes) {
 
 // persistent grids: blocks per SM that fit (shared memory / 64-register budget), times SMs
 int sm_count();
-// warp-scope x passes (wfft_kernels.h): LESGO_XW=0 never, 1 (default) for the 3/2-grid x inverse only
-// (the one pass where they measured faster), 2 everywhere
+// warp-scope x passes (wfft_kernels.h), LESGO_XW: 0 never; 1 for the 3/2-grid x inverse only; 2 everywhere;
+// 3 (default) every x inverse of >= 256 complex points at warp scope WITH cp.async prefetch of each warp's
+// next row (5.34 + 2.79 ms against 5.66 + 2.87 ms), the 3/2-grid x inverse at warp scope otherwise
 int warp_passes();
 inline int persistent_blocks(size_t smem_bytes, long ntiles, int max_per_sm) {
     int per_sm = int((227 * 1024) / (smem_bytes + 1024));

@@ -14,25 +14,39 @@ namespace lg {
 #define LG_XW_TWREG 1
 #endif
 
-template <int NX, bool TWREG_ = (LG_XW_TWREG != 0)> struct XWCfg {
+// PREF_: the x-inverse kernel stages the NEXT row of each warp with cp.async while the current one is
+// being transformed (one staging row of M+1 spectral columns per warp)
+template <int NX, bool TWREG_ = (LG_XW_TWREG != 0), bool PREF_ = false> struct XWCfg {
     static constexpr int M = NX / 2;
     typedef PlanInfo<M> PI;
     static constexpr int TMIN = M / PI::rmax;
     static constexpr int NF = TMIN >= 32 ? 1 : (32 / TMIN > 8 ? 8 : 32 / TMIN);   // rows per warp
     static constexpr bool SMALL = (M * NF <= 256);
+    // in place up to 8 points per lane (12-point rows in place -- two butterflies per lane held across the
+    // __syncwarp, 128 registers -- measured slower than ping-pong buffers: 2.96 against 2.76 ms)
     static constexpr bool INPLACE = SMALL;
     static constexpr bool TWREG = SMALL && TWREG_;
     static constexpr int SL = SmemLen<M>::value;
-    static constexpr int WBUF = (INPLACE ? 1 : 2) * NF * SL;      // cplx per warp
+    static constexpr bool PREF = PREF_ && NF == 1;
+    static constexpr int STG = PREF ? (M + 1) : 0;
+    static constexpr int WBUF = (INPLACE ? 1 : 2) * NF * SL + STG;      // cplx per warp
     static constexpr int TWL = PI::twlen, NWH = M / 2 + 1;
     static constexpr size_t smem_for(int wpb) {
         return size_t(wpb * WBUF + TWL + NWH) * sizeof(cplx) + size_t(wpb) * 2 * NF * sizeof(int);
     }
-    static constexpr int WPB = smem_for(8) <= 200 * 1024 ? 8 : 4;   // warps per block
+    // warps per block: the count (4..8) that lets the most warps be resident per SM
+    static constexpr int warps_per_sm(int wpb) { return wpb * int((227 * 1024) / (smem_for(wpb) + 1024)); }
+    static constexpr int best_wpb() {
+        int best = 8;
+        for (int w = 7; w >= 4; --w)
+            if (warps_per_sm(w) > warps_per_sm(best)) best = w;
+        return best;
+    }
+    static constexpr int WPB = smem_for(8) > 226 * 1024 ? 4 : best_wpb();
     static constexpr int NTHR = 32 * WPB;
     static constexpr size_t smem = smem_for(WPB);
     static constexpr int by_smem = int((227 * 1024) / (smem + 1024)) < 1 ? 1 : int((227 * 1024) / (smem + 1024));
-    static constexpr int by_regs = TWREG ? 2 : (M <= 256 ? 4 : 3);   // 128 / 64 / 80 registers per thread
+    static constexpr int by_regs = TWREG ? 2 : (PREF ? 3 : (M <= 256 ? 4 : 3));   // 128 / 80 / 64 / 80 registers per thread
     static constexpr int MINB = by_regs < by_smem ? by_regs : by_smem;
 };
 
@@ -138,11 +152,11 @@ k_xfwd_w(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int
 // ---------------------------------------------------------------------------------
 // x inverse: half spectrum rows -> real rows
 // ---------------------------------------------------------------------------------
-template <int NX, class Epi, bool TWR = (LG_XW_TWREG != 0)>
-__global__ void __launch_bounds__(XWCfg<NX, TWR>::NTHR, XWCfg<NX, TWR>::MINB)
+template <int NX, class Epi, bool TWR = (LG_XW_TWREG != 0), bool PRF = false>
+__global__ void __launch_bounds__(XWCfg<NX, TWR, PRF>::NTHR, XWCfg<NX, TWR, PRF>::MINB)
 k_xinv_w(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nfields, int ny, int k0, int nplanes,
          const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
-    typedef XWCfg<NX, TWR> C;
+    typedef XWCfg<NX, TWR, PRF> C;
     constexpr int M = C::M, NF = C::NF, SL = C::SL;
     LG_DYN_SMEM(cplx, sm);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -163,9 +177,24 @@ k_xinv_w(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int 
     const unsigned ntiles = (nrows + NF - 1) / NF;
     const unsigned nwork = ntiles * unsigned(nfields);
     const unsigned wstride = gridDim.x * C::WPB;
+    cplx* ST = A + (C::INPLACE ? 1 : 2) * NF * SL;           // PREF: this warp's staged spectral row
+    auto prefetch = [&](unsigned work) {
+        if constexpr (C::PREF) {
+            if (work < nwork) {
+                const int pf = int(work % unsigned(nfields));
+                const unsigned r = work / unsigned(nfields);
+                const double* srow = in.src[pf] + poff(k0 + int(r / unsigned(ny)), in.plane, in.ring) + long(r % unsigned(ny)) * in.row;
+                const int nc = in.ncol < M + 1 ? in.ncol : M + 1;
+                for (int m = lane; m < nc; m += 32) cp_async16(ST + m, srow + 2 * m);
+            }
+            cp_async_commit();
+        }
+    };
+    prefetch(blockIdx.x * C::WPB + wib);
     for (unsigned work = blockIdx.x * C::WPB + wib; work < nwork; work += wstride) {
         const int fld = int(work % unsigned(nfields));
         rows.set(lane, (work / unsigned(nfields)) * NF, nrows, ny, k0);
+        if constexpr (C::PREF) { cp_async_wait_all(); LG_SYNCWARP(); }
         // tangle: Z'_m = E'_m + i O'_m,  E' = X_m + conj(X_{M-m}),  O' = (X_m - conj(X_{M-m})) conj(W_N^m)
         constexpr int NPM = M / 2 + 1;
         constexpr int ITER = (NF * NPM + 31) / 32;
@@ -180,7 +209,15 @@ k_xinv_w(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int 
                 if (q0 + u < ITER && it < NF * NPM) {
                     const int f = (NF == 1) ? 0 : it / NPM, m = (NF == 1) ? it : it % NPM;
                     const int k = rows.k(f);
-                    if (k >= 0) {
+                    if (C::PREF) {
+                        if (m == 0) {
+                            va[u].x = in.ncol > 0 ? ST[0].x : 0.0;
+                            va[u].y = in.ncol > M ? ST[M].x : 0.0;
+                        } else {
+                            if (m < in.ncol) va[u] = ST[m];
+                            if (m != M / 2 && M - m < in.ncol) vb[u] = ST[M - m];
+                        }
+                    } else if (k >= 0) {
                         const double* srow = in.src[fld] + poff(k, in.plane, in.ring) + long(rows.y(f)) * in.row;
                         if (m == 0) {                          // real parts of X_0 and X_M only
                             va[u].x = in.ncol > 0 ? ld_cg(srow).x : 0.0;
@@ -212,6 +249,7 @@ k_xinv_w(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int 
             }
         }
         LG_SYNCWARP();
+        prefetch(work + wstride);                            // staging consumed: fetch this warp's next row
         fft.template run<true, false>(A, B, W, lane,
             [](int, int) { return make_double2(0.0, 0.0); },
             [&](int f, int i, cplx v) {

@@ -12,7 +12,7 @@ static int launch_xfwd_n(const Pro& pro, int nfields, const XfOut& out, int ny, 
     typedef XCfg<NX> C;
     const long nrows = long(ny) * nplanes;
     if (nrows <= 0) return 0;
-    if (warp_passes() > 1) {
+    if (warp_passes() == 2) {
         typedef XWCfg<NX> CW;
         static bool attr_w = false;
         if (!attr_w) { set_smem(k_xfwd_w<NX, Pro>, CW::smem); attr_w = true; }

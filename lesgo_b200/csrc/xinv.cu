@@ -7,7 +7,19 @@ static int launch_xinv_n(const XiSrc& in, const Epi& epi, int nfields, int ny, i
     typedef XCfg<NX> C;
     const long nrows = long(ny) * nplanes;
     if (nrows <= 0) return 0;
-    if (warp_passes() > 1 || (warp_passes() == 1 && big)) {
+    if (warp_passes() == 3) {
+        // warp-scope with cp.async prefetch of each warp's next row (rows of >= 256 complex points)
+        typedef XWCfg<NX, false, true> CW;
+        if (CW::PREF) {
+            static bool attr_p = false;
+            if (!attr_p) { set_smem(k_xinv_w<NX, Epi, false, true>, CW::smem); attr_p = true; }
+            const long nwork = nrows * nfields;
+            dim3 grid(persistent_blocks(CW::smem, (nwork + CW::WPB - 1) / CW::WPB, CW::MINB));
+            LG_LAUNCH((k_xinv_w<NX, Epi, false, true>), grid, dim3(CW::NTHR), CW::smem, s, in, epi, nfields, ny, k0, nplanes, W, Wh);
+            return 0;
+        }
+    }
+    if (warp_passes() == 2 || ((warp_passes() == 1 || warp_passes() == 3) && big)) {
         typedef XWCfg<NX> CW;
         static bool attr_w = false;
         if (!attr_w) { set_smem(k_xinv_w<NX, Epi>, CW::smem); attr_w = true; }

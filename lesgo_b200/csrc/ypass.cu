@@ -95,7 +95,7 @@ int sm_count() {
 }
 int warp_passes() {
     static int v = -1;
-    if (v < 0) { const char* e = std::getenv("LESGO_XW"); v = e ? std::atoi(e) : 1; }
+    if (v < 0) { const char* e = std::getenv("LESGO_XW"); v = e ? std::atoi(e) : 3; }
     return v;
 }
 bool size_supported(int n) {

@@ -103,6 +103,8 @@ def test_emul_multirank_thin_slabs():
     ({"LESGO_BIGX": "1", "LESGO_BIGX_CHUNK": "2"}, "32,16,7", "convec"),
     ({"LESGO_PIPE": "1", "LESGO_PIPE_RING": "2"}, "64,512,5", "deriv"),
     ({"LESGO_XW": "0"}, "16,16,6", "deriv,convec,steps"),
+    ({"LESGO_XW": "1"}, "512,16,3", "deriv,convec"),
+    ({"LESGO_XW": "3"}, "512,16,3", "deriv,convec,press"),
     ({"LESGO_XW": "2"}, "48,32,4", "deriv,convec,press,steps"),
     ({"LESGO_REUSE": "0"}, "16,16,6", "steps,full"),
 ])

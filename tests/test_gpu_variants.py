@@ -13,6 +13,8 @@ VARIANTS = [
     ({"LESGO_XW": "0"}, "16,16,6", "deriv,convec,steps"),
     ({"LESGO_XW": "2"}, "64,48,6", "deriv,convec,press,steps"),
     ({"LESGO_XW": "2"}, "512,64,3", "deriv,convec"),
+    ({"LESGO_XW": "1"}, "512,64,3", "deriv,convec,press"),
+    ({"LESGO_XW": "3"}, "1024,32,3", "deriv,convec,press,steps"),
     ({"LESGO_BIGX": "1"}, "32,32,9", "convec,steps,full"),
     ({"LESGO_BIGX": "1", "LESGO_BIGX_CHUNK": "3"}, "128,64,8", "convec,steps"),
     ({"LESGO_PIPE": "1"}, "512,512,5", "deriv"),

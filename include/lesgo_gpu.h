@@ -102,7 +102,10 @@ enum lesgo_gpu_field {
     LG_U = 0, LG_V, LG_W, LG_DUDX, LG_DUDY, LG_DUDZ, LG_DVDX, LG_DVDY, LG_DVDZ,
     LG_DWDX, LG_DWDY, LG_DWDZ, LG_RHSX, LG_RHSY, LG_RHSZ, LG_RHSX_F, LG_RHSY_F, LG_RHSZ_F,
     LG_P, LG_DPDX, LG_DPDY, LG_DPDZ, LG_DIVTX, LG_DIVTY, LG_DIVTZ,
-    LG_TXX, LG_TXY, LG_TXZ, LG_TYY, LG_TYZ, LG_TZZ, LG_NFIELDS
+    LG_TXX, LG_TXY, LG_TXZ, LG_TYY, LG_TYZ, LG_TZZ,
+    /* Lagrangian scale-dependent model state (sgs_param.f90; lagrange_Sdep.f90, interpolag_Sdep.f90):
+     * allocated only when a step with sgs_model = 5 (or an upload/download of them) asks for them */
+    LG_F_LM, LG_F_MM, LG_F_QN, LG_F_NN, LG_CS_OPT2, LG_NFIELDS
 };
 /* device pointer of a resident field ((ld, ny, 0:nz) doubles); allocated on first use.  NOTE:
  * lesgo_gpu_step makes RHS* and RHS*_f trade places every step instead of copying (main.f90:155-157),
@@ -120,10 +123,23 @@ typedef struct lesgo_gpu_step_params {
                                            1 = full step: + wallstress (lbc/ubc 0, 1, 2), calc_Sij,
                                            sgs_stag with a constant coefficient, divstress_uv/w   */
     /* mode 1 only (sgs_param.f90, sgs_stag_util.f90:87-189, wallstress.f90, test_filtermodule.f90) */
-    int sgs_model;                      /* 1 = Smagorinsky + Mason wall damping; other: Cs_opt2 = 0.03,
-                                           l = delta (the dynamic models before DYN_init)              */
+    int sgs_model;                      /* 1 = Smagorinsky + Mason wall damping; 5 = Lagrangian scale-dependent
+                                           dynamic model (Cs_opt2 is the resident field LG_CS_OPT2, driven by the
+                                           lasd_* members below); other: Cs_opt2 = 0.03, l = delta (the dynamic
+                                           models before DYN_init)                                      */
     int ifilter;                        /* test filter of the equilibrium wall model: 1 cutoff, 2 Gaussian, 3 box */
     double Co, wall_damp_exp, vonk, zo; /* lesgo.conf MODEL / FLOW_COND                                  */
+    /* sgs_model = 5 only.  The host keeps the step counters (jt, jt_total, DYN_init, cs_count, inilag) and
+     * tells the step which branch of sgs_stag_util.f90:183-216 applies:
+     *   lasd_cs_init: jt == 1 and inilag           -> Cs_opt2 = 0.03 everywhere (:187-189)
+     *   lasd_update : jt >= DYN_init and mod(jt_total, cs_count) == 0 -> lagrange_Sdep() (:192-215), i.e.
+     *                 interpolag_Sdep (semi-Lagrangian transport of F_LM, F_MM, F_QN, F_NN) + the 42 test
+     *                 filters per plane + the running averages + Cs_opt2 (lagrange_Sdep.f90:22-430)
+     *   lasd_init_F : inilag and (jt == cs_count or jt == DYN_init), first time: F_* initialised from
+     *                 MM, NN (lagrange_Sdep.f90:270-281,320-331)
+     *   lagran_dt   : sgs_stag_util.f90:73-82 (cs_count * dt for a fixed time step) */
+    int lasd_cs_init, lasd_update, lasd_init_F;
+    double lagran_dt;
 } lesgo_gpu_step_params;
 /* One timestep main.f90:155-344 on the resident fields, no host round trip. */
 int lesgo_gpu_step(lesgo_gpu_ctx* ctx, const lesgo_gpu_step_params* sp);

@@ -29,7 +29,8 @@ from .lib import DimsStruct, Library, LibraryError, StepParams, load_library
 FIELD_IDS = {n: i for i, n in enumerate(
     ["u", "v", "w", "dudx", "dudy", "dudz", "dvdx", "dvdy", "dvdz", "dwdx", "dwdy", "dwdz",
      "RHSx", "RHSy", "RHSz", "RHSx_f", "RHSy_f", "RHSz_f", "p", "dpdx", "dpdy", "dpdz",
-     "divtx", "divty", "divtz", "txx", "txy", "txz", "tyy", "tyz", "tzz"])}
+     "divtx", "divty", "divtz", "txx", "txy", "txz", "tyy", "tyz", "tzz",
+     "F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2"])}
 
 
 @dataclass
@@ -247,11 +248,14 @@ class Core:
 
     def step(self, dt, tadv1=1.5, tadv2=-0.5, first_step=False, mode=0, mean_p_force_x=0.0,
              mean_p_force_y=0.0, ubot=0.0, utop=0.0, nu=0.0, sgs_model=1, ifilter=1, Co=0.16,
-             wall_damp_exp=2.0, vonk=0.4, zo=1e-4):
+             wall_damp_exp=2.0, vonk=0.4, zo=1e-4, lasd_cs_init=False, lasd_update=False, lasd_init_F=False,
+             lagran_dt=0.0):
         """One timestep main.f90:155-344 on the resident fields.  mode 0: core path (divt* as
-        resident); mode 1: full step with wallstress, constant-coefficient sgs_stag and divstress."""
+        resident); mode 1: full step with wallstress, sgs_stag (constant coefficient, or sgs_model 5 =
+        Lagrangian scale-dependent: lasd_* select the branch of sgs_stag_util.f90:183-216) and divstress."""
         sp = StepParams(dt, tadv1, tadv2, mean_p_force_x, mean_p_force_y, ubot, utop, nu, int(first_step), int(mode),
-                        int(sgs_model), int(ifilter), Co, wall_damp_exp, vonk, zo)
+                        int(sgs_model), int(ifilter), Co, wall_damp_exp, vonk, zo, int(lasd_cs_init),
+                        int(lasd_update), int(lasd_init_F), float(lagran_dt))
         self._ck(self.lib.step(self._ctx, C.byref(sp)), "step")
 
     def max_cfl(self, dt):

@@ -16,6 +16,7 @@
 #include "pipe_kernels.h"
 #include "bigx_kernels.h"
 #include "prodfwd_kernels.h"
+#include "lasd_kernels.h"
 
 using namespace lg;
 
@@ -59,6 +60,10 @@ struct lesgo_gpu_ctx {
     double* lsq = nullptr;                 // l(k)**2 of the Smagorinsky length (nz+1)
     double* gtest = nullptr;               // test-filter kernel G_test (lh, ny)
     double* wplane[2] = {nullptr};         // filtered wall-adjacent u, v planes
+    double* gtest2 = nullptr;              // second test-filter kernel G_test_test (sgs_model 5)
+    double* lasd_buf[51] = {nullptr};      // lagrange_Sdep work fields, lasd_chunk planes each
+    double* lasd_tmp[4] = {nullptr};       // interpolag_Sdep's copies of F_LM, F_MM, F_QN, F_NN
+    int lasd_chunk = 0;
     int sgs_cfg = -1;                      // (sgs_model, ifilter) the tables above were built for
     double* fields[LG_NFIELDS] = {nullptr};
     std::vector<double*> staging;          // device staging for host-pointer arguments
@@ -971,10 +976,11 @@ int build_sgs_tables(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     for (auto& v : l) v = v * v;
     if (!c->lsq && dev_alloc(c, &c->lsq, nz + 1)) return 1;
     CK(cudaMemcpyAsync(c->lsq, l.data(), sizeof(double) * (nz + 1), cudaMemcpyHostToDevice, c->stream));
-    // G_test, test_filtermodule.f90:38-80 (alpha_test = 2)
+    // G_test (alpha_test = 2) and, for sgs_model 5, G_test_test (alpha_test_test = 4), test_filtermodule.f90:38-123
     std::vector<double> G(size_t(c->lh) * c->ny);
     const double pi = 3.14159265358979323846;
-    const double dt_ = 2.0 * std::sqrt(dx * dy), kc2 = (pi / dt_) * (pi / dt_);
+    for (int which = 0; which < (sp->sgs_model == 5 ? 2 : 1); ++which) {
+    const double dt_ = (which == 0 ? 2.0 : 4.0) * std::sqrt(dx * dy), kc2 = (pi / dt_) * (pi / dt_);
     for (int jy = 0; jy < c->ny; ++jy)
         for (int jx = 0; jx < c->lh; ++jx) {
             double kx = c->kxs * jx, ky = c->kys * double(jy < c->ny / 2 ? jy : jy - c->ny);
@@ -987,9 +993,11 @@ int build_sgs_tables(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
             if (jx == c->lh - 1 || jy == c->ny / 2) g = 0.0;
             G[size_t(jy) * c->lh + jx] = g;
         }
-    if (!c->gtest && dev_alloc(c, &c->gtest, G.size())) return 1;
-    CK(cudaMemcpyAsync(c->gtest, G.data(), sizeof(double) * G.size(), cudaMemcpyHostToDevice, c->stream));
+    double** gdst = which == 0 ? &c->gtest : &c->gtest2;
+    if (!*gdst && dev_alloc(c, gdst, G.size())) return 1;
+    CK(cudaMemcpyAsync(*gdst, G.data(), sizeof(double) * G.size(), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    }
     c->sgs_cfg = cfg;
     return 0;
 }
@@ -1070,6 +1078,113 @@ int sum3(lesgo_gpu_ctx* c, double* out, const double* a, const double* b, const 
     return 0;
 }
 
+// ---- Lagrangian scale-dependent dynamic model -------------------------------------------
+// test_filter AND test_test_filter (test_filtermodule.f90:126-168) of nf <= 3 fields on planes k0..k1-1: the
+// forward x transform is shared by the two filters.  Arrays are addressed by absolute plane index.
+int filter_fields(lesgo_gpu_ctx* c, int nf, const double* const* src, double* const* dst1, double* const* dst2, int k0, int k1) {
+    if (need_small(c, 6)) return 1;
+    ProScale ps;
+    for (int i = 0; i < nf; ++i) ps.src[i] = src[i];
+    ps.lay = c->lay(); ps.scale = 1.0;
+    double* xs[3] = {c->sa[0], c->sa[1], c->sa[2]};
+    if (xfwd(c, false, ps, nf, xs, c->plane, c->ld, c->nx / 2, c->ny, k0, k1)) return 1;
+    for (int which = 0; which < 2; ++which) {
+        YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, c->nx / 2, k0);
+        for (int i = 0; i < nf; ++i) { a.fld[i].src = c->sa[i]; a.fld[i].out[0] = YOutSpec{c->sa[3 + i], Y_TABLE}; }
+        a.table = which == 0 ? c->gtest : c->gtest2; a.table_row = c->lh;
+        if (ypass(c, c->ny, c->ny, a, nf, k0, k1)) return 1;
+        const double* s0[3] = {c->sa[3], c->sa[4], c->sa[5]};
+        if (xinv(c, false, s0, c->plane, c->ld, c->nx / 2, nf, which == 0 ? dst1 : dst2, c->lay(), c->ny, k0, k1)) return 1;
+    }
+    return 0;
+}
+
+// lagrange_Sdep (lagrange_Sdep.f90:22-430) including interpolag_Sdep (interpolag_Sdep.f90:21-268); Sij in c->work[0..5]
+int lagrange_sdep(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* const* F) {
+    const int nz = c->nz;
+    const size_t nfield = size_t(c->plane) * (nz + 1);
+    LasdGeom g;
+    g.nx = c->nx; g.ny = c->ny; g.nz = nz; g.coord = c->d.coord; g.nproc = c->d.nproc;
+    g.bottom = c->bottom; g.top = c->top; g.lbc_mom = c->d.lbc_mom; g.ubc_mom = c->d.ubc_mom;
+    g.dx = c->d.L_x / c->nx; g.dy = c->d.L_y / c->ny; g.dz = c->d.dz;
+    g.L_x = c->d.L_x; g.L_y = c->d.L_y; g.L_z = (c->d.nz_tot - 1) * c->d.dz;
+    double* FL[4] = {F[LG_F_LM], F[LG_F_MM], F[LG_F_QN], F[LG_F_NN]};
+    auto sync4 = [&]() -> int {                                   // mpi_sync_real_array(F_*, 0, MPI_SYNC_DOWNUP)
+        if (!c->comm) return 0;
+        ProfScope ps_(c, "halo");
+        for (int f = 0; f < 4; ++f)
+            if (c->comm->sync_planes(FL[f], c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
+        return 0;
+    };
+    // interpolag_Sdep.f90:69-72 copies, :84-241 backward trajectories (k = nz on the top rank only), :244-249 sync
+    {
+        LasdInterpArgs ia;
+        ia.u = F[LG_U]; ia.v = F[LG_V]; ia.w = F[LG_W]; ia.lagran_dt = sp->lagran_dt;
+        for (int f = 0; f < 4; ++f) {
+            if (dev_alloc(c, &c->lasd_tmp[f], nfield)) return 1;
+            CK(cudaMemcpyAsync(c->lasd_tmp[f], FL[f], nfield * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            ia.T[f] = c->lasd_tmp[f]; ia.F[f] = FL[f];
+        }
+        const int k1 = c->top ? nz + 1 : nz;
+        ProfScope ps_(c, "lasd");
+        LG_LAUNCH(k_interpolag, dim3(grid1d(long(c->nx) * c->ny * (k1 - 1))), dim3(kBlock), 0, c->stream, ia, g, c->lay(), 1, k1);
+        c->launches++;
+    }
+    if (sync4()) return 1;
+    // the per-plane part (:83-413), `chunk` planes at a time so the 51 work fields stay small
+    if (!c->lasd_chunk) {
+        const char* e = std::getenv("LESGO_LASD_CHUNK");
+        int ch = e ? std::atoi(e) : 32;
+        c->lasd_chunk = ch < 1 ? 1 : (ch > nz ? nz : ch);
+        for (int i = 0; i < 51; ++i)
+            if (dev_alloc(c, &c->lasd_buf[i], size_t(c->plane) * c->lasd_chunk)) return 1;
+    }
+    const double dx = g.dx, dy = g.dy;
+    const double delta = std::pow(dx * dy * g.dz, 1.0 / 3.0);     // sgs_param.f90:187
+    for (int k0 = 1; k0 <= nz; k0 += c->lasd_chunk) {
+        const int k1 = (k0 + c->lasd_chunk < nz + 1) ? k0 + c->lasd_chunk : nz + 1;
+        // work fields addressed by the absolute plane index
+        double* B[51];
+        for (int i = 0; i < 51; ++i) B[i] = c->lasd_buf[i] - long(k0) * c->plane;
+        double **A = B, **Tb = B + 9, **Th = B + 18, **Sb = B + 27, **Sh = B + 33, **SSb = B + 39, **SSh = B + 45;
+        const int g1 = grid1d(long(c->nx) * c->ny * (k1 - k0));
+        {
+            LasdPrepArgs pa;
+            pa.u = F[LG_U]; pa.v = F[LG_V]; pa.w = F[LG_W];
+            for (int i = 0; i < 9; ++i) pa.A[i] = A[i];
+            ProfScope ps_(c, "lasd");
+            LG_LAUNCH(k_lasd_prep, dim3(g1), dim3(kBlock), 0, c->stream, pa, g, c->lay(), k0, k1);
+            c->launches++;
+        }
+        for (int i = 0; i < 9; i += 3)
+            if (filter_fields(c, 3, A + i, Tb + i, Th + i, k0, k1)) return 1;
+        for (int i = 0; i < 6; i += 3)
+            if (filter_fields(c, 3, c->work + i, Sb + i, Sh + i, k0, k1)) return 1;
+        {
+            LasdSSArgs sa;
+            for (int i = 0; i < 6; ++i) { sa.S[i] = c->work[i]; sa.SS[i] = A[i]; }
+            ProfScope ps_(c, "lasd");
+            LG_LAUNCH(k_lasd_ss, dim3(g1), dim3(kBlock), 0, c->stream, sa, c->lay(), c->nx, c->ny, k0, k1);
+            c->launches++;
+        }
+        for (int i = 0; i < 6; i += 3)
+            if (filter_fields(c, 3, A + i, SSb + i, SSh + i, k0, k1)) return 1;
+        {
+            LasdFinalArgs fa;
+            for (int i = 0; i < 9; ++i) { fa.Tb[i] = Tb[i]; fa.Th[i] = Th[i]; }
+            for (int i = 0; i < 6; ++i) { fa.Sb[i] = Sb[i]; fa.Sh[i] = Sh[i]; fa.SSb[i] = SSb[i]; fa.SSh[i] = SSh[i]; }
+            fa.F_LM = FL[0]; fa.F_MM = FL[1]; fa.F_QN = FL[2]; fa.F_NN = FL[3]; fa.Cs = F[LG_CS_OPT2];
+            fa.delta = delta; fa.lagran_dt = sp->lagran_dt;
+            fa.beta_exp = std::log(2.0) / (std::log(4.0) - std::log(2.0));       // log(tf1) / (log(tf2) - log(tf1))
+            fa.init_F = sp->lasd_init_F ? 1 : 0;
+            ProfScope ps_(c, "lasd");
+            LG_LAUNCH(k_lasd_final, dim3(grid1d(long(c->ld) * c->ny * (k1 - k0))), dim3(kBlock), 0, c->stream, fa, g, c->lay(), k0, k1);
+            c->launches++;
+        }
+    }
+    return sync4();                                               // :417-420
+}
+
 int sgs_and_divstress(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* const* F) {
     const int nz = c->nz, coord = c->d.coord;
     for (int i = 0; i < 13; ++i)
@@ -1088,6 +1203,17 @@ int sgs_and_divstress(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double*
     {
         ProfScope ps_(c, "sgs");
         LG_LAUNCH(k_sij_nut, dim3(grid1d(long(c->nx) * c->ny * nz)), dim3(kBlock), 0, c->stream, sa, p, c->lay(), c->nx, c->ny, 1, nz + 1);
+        c->launches++;
+    }
+    if (c->d.sgs && sp->sgs_model == 5) {
+        // sgs_stag_util.f90:183-231 with the coefficient field
+        if (sp->lasd_cs_init) { if (fill(c, F[LG_CS_OPT2], c->plane, 0, nz + 1, 0.03)) return 1; }
+        else if (sp->lasd_update && lagrange_sdep(c, sp, F)) return 1;
+        LasdSSArgs na;
+        for (int i = 0; i < 6; ++i) { na.S[i] = c->work[i]; na.SS[i] = nullptr; }
+        ProfScope ps_(c, "sgs");
+        LG_LAUNCH(k_nut_field, dim3(grid1d(long(c->nx) * c->ny * nz)), dim3(kBlock), 0, c->stream, na, F[LG_CS_OPT2], c->lsq,
+                  c->work[6], c->lay(), c->nx, c->ny, 1, nz + 1);
         c->launches++;
     }
     TauArgs ta;
@@ -1127,9 +1253,10 @@ int sgs_and_divstress(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double*
 int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     const int nz = c->nz;
     double* F[LG_NFIELDS];
+    const bool lasd = sp->mode == 1 && c->d.sgs && sp->sgs_model == 5;
     for (int i = 0; i < LG_NFIELDS; ++i) {
-        F[i] = field(c, i);
-        if (!F[i]) return 1;
+        F[i] = (i < LG_F_LM || lasd) ? field(c, i) : nullptr;
+        if (!F[i] && (i < LG_F_LM || lasd)) return 1;
     }
     if (sp->mode != 0 && sp->mode != 1) return c->fail("lesgo_gpu_step: mode must be 0 (core) or 1 (full)");
     // :155-157  RHS*_f = RHS*: the two sets trade places instead of being copied (convec

@@ -24,7 +24,9 @@ class StepParams(C.Structure):
                 ("ubot", C.c_double), ("utop", C.c_double), ("nu_molec_nd", C.c_double),
                 ("first_step", C.c_int), ("mode", C.c_int),
                 ("sgs_model", C.c_int), ("ifilter", C.c_int),
-                ("Co", C.c_double), ("wall_damp_exp", C.c_double), ("vonk", C.c_double), ("zo", C.c_double)]
+                ("Co", C.c_double), ("wall_damp_exp", C.c_double), ("vonk", C.c_double), ("zo", C.c_double),
+                ("lasd_cs_init", C.c_int), ("lasd_update", C.c_int), ("lasd_init_F", C.c_int),
+                ("lagran_dt", C.c_double)]
 
 
 # every symbol include/lesgo_gpu.h declares: name -> (restype, argtypes)

@@ -846,10 +846,13 @@ def _smag_length(p: Params):
     return l
 
 
-def sgs_stag(s, p: Params, comm, Cs_opt2_const: Optional[float] = None):
+def sgs_stag(s, p: Params, comm, Cs_opt2_const: Optional[float] = None, lasd: Optional[dict] = None):
     """sgs_stag_util.f90:43-465 for: sgs = .false. (molecular stress only), sgs_model 1
-    (Smagorinsky, Cs_opt2 = Co**2, Mason damping), and the pre-DYN_init phase of the
-    dynamic models (Cs_opt2 = 0.03, l = delta, :187-189).  Writes txx..tzz into s."""
+    (Smagorinsky, Cs_opt2 = Co**2, Mason damping), the pre-DYN_init phase of the
+    dynamic models (Cs_opt2 = 0.03, l = delta, :187-189) and, with `lasd`, sgs_model 5
+    (:183-216): lasd = {"sp", "G_test", "G_test_test", "lagran_dt", "cs_init" (jt == 1 and
+    inilag: Cs_opt2 = 0.03), "update" (jt >= DYN_init and mod(jt_total, cs_count) == 0:
+    lagrange_Sdep), "init_F"}; Cs_opt2 is then the field s.Cs_opt2.  Writes txx..tzz into s."""
     nx, nz = p.nx, p.nz
     X = slice(0, nx)
     nu = p.nu
@@ -864,7 +867,16 @@ def sgs_stag(s, p: Params, comm, Cs_opt2_const: Optional[float] = None):
             Cs = 0.03 if Cs_opt2_const is None else Cs_opt2_const
         Smag = np.sqrt(2.0 * (S["S11"] ** 2 + S["S22"] ** 2 + S["S33"] ** 2
                               + 2.0 * (S["S12"] ** 2 + S["S13"] ** 2 + S["S23"] ** 2)))
-        Nu_t = Smag * Cs * (l ** 2)[:, None, None]
+        if lasd is not None:
+            lasd_alloc(s)
+            if lasd.get("cs_init"):
+                s.Cs_opt2[...] = 0.03
+            elif lasd.get("update"):
+                lagrange_Sdep(s, lasd["sp"], comm, lasd["G_test"], lasd["G_test_test"], lasd["lagran_dt"],
+                              init_F=bool(lasd.get("init_F")))
+            Nu_t = Smag * s.Cs_opt2 * (l ** 2)[:, None, None]
+        else:
+            Nu_t = Smag * Cs * (l ** 2)[:, None, None]
     else:
         Nu_t = np.zeros_like(s.u)
     s.Nu_t = Nu_t
@@ -929,6 +941,218 @@ def sgs_stag(s, p: Params, comm, Cs_opt2_const: Optional[float] = None):
         t[tn][0] = BOGUS
     for tn in ("txx", "txy", "tyy", "tzz"):
         t[tn][nz] = BOGUS
+
+
+# ----------------------------------------------------------------------------------
+# Lagrangian scale-dependent dynamic model: functions.f90 (trilinear_interp_w, cell_indx_w),
+# interpolag_Sdep.f90, lagrange_Sdep.f90 (no PPDYN_TN, no level set, inflow_type = 0)
+# ----------------------------------------------------------------------------------
+LASD_FIELDS = ("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2")
+LASD_ZERO = 1.0e-24          # lagrange_Sdep.f90:68
+OPFTIME = 1.5                # sgs_param.f90:53
+
+
+def lasd_alloc(s):
+    """sgs_param.f90: F_LM, F_MM, F_QN, F_NN, Cs_opt2 (ld, ny, lbz:nz), initially 0."""
+    for n in LASD_FIELDS:
+        if not hasattr(s, n):
+            setattr(s, n, np.zeros_like(s.u))
+
+
+def _grid_z(p: Params):
+    """grid.f90:80-96: z(k) on uv nodes, zw = z - dz/2, k = 0..nz (local to the rank)."""
+    k = np.arange(0, p.nz + 1, dtype=np.float64)
+    z = (p.coord * (p.nz - 1) + k - 0.5) * p.dz
+    zw = z - p.dz / 2.0
+    return z, zw
+
+
+def _cell_indx_w_xy(px, L, d, n):
+    """functions.f90:226-252, cases 'i' / 'j': returns (wrapped px, 1-based cell index)."""
+    thresh = 1.0e-9
+    px = np.mod(px, L)
+    idx = np.floor(px / d).astype(np.int64) + 1
+    idx = np.where(np.abs(px - L) / L < thresh, n, idx)
+    idx = np.where(np.abs(px) / L < thresh, 1, idx)
+    return px, idx
+
+
+def trilinear_interp_w(var, p: Params, x0, y0, z0):
+    """functions.f90:349-454 for arrays of points (x0, y0, z0); var[k, j, i], k = 0..nz."""
+    nx, ny, nz = p.nx, p.ny, p.nz
+    dx, dy, dz = p.dx, p.dy, p.dz
+    z, zw = _grid_z(p)
+    L_z = p.L_z
+    px, ist = _cell_indx_w_xy(x0, p.L_x, dx, nx)
+    py, jst = _cell_indx_w_xy(y0, p.L_y, dy, ny)
+    ist1 = np.where(ist + 1 > nx, 1, ist + 1)        # autowrap_i, grid.f90:98-104
+    jst1 = np.where(jst + 1 > ny, 1, jst + 1)
+    xdiff = px - (ist - 1) * dx
+    ydiff = py - (jst - 1) * dy
+    # general case (cell_indx_w 'k', functions.f90:254-260)
+    kst = np.floor((z0 - zw[1]) / dz).astype(np.int64) + 1
+    kst = np.where(np.abs(z0 - zw[nz]) / L_z < 1.0e-9, nz - 1, kst)
+    kst1 = kst + 1
+    zdiff = z0 - zw[np.clip(kst, 0, nz)]
+    if p.coord == 0 and p.lbc_mom > 0:
+        m = z0 < zw[2]
+        below = z0 < z[1]
+        kst = np.where(m, 1, kst)
+        kst1 = np.where(m, np.where(below, 1, 2), kst1)
+        zdiff = np.where(m, np.where(below, 0.0, 2.0 * (z0 - z[1])), zdiff)
+    else:
+        m = np.zeros(np.shape(z0), dtype=bool)
+    if p.coord == p.nproc - 1 and p.ubc_mom > 0:
+        m2 = (z0 > zw[nz - 1]) & ~m
+        above = z0 > z[nz - 1]
+        kst = np.where(m2, np.where(above, nz, nz - 1), kst)
+        kst1 = np.where(m2, nz, kst1)
+        zdiff = np.where(m2, np.where(above, 0.0, 2.0 * (z0 - zw[nz - 1])), zdiff)
+    i0, i1, j0, j1 = ist - 1, ist1 - 1, jst - 1, jst1 - 1
+    v = var
+    u1 = v[kst, j0, i0] + xdiff * (v[kst, j0, i1] - v[kst, j0, i0]) / dx
+    u2 = v[kst, j1, i0] + xdiff * (v[kst, j1, i1] - v[kst, j1, i0]) / dx
+    u3 = v[kst1, j0, i0] + xdiff * (v[kst1, j0, i1] - v[kst1, j0, i0]) / dx
+    u4 = v[kst1, j1, i0] + xdiff * (v[kst1, j1, i1] - v[kst1, j1, i0]) / dx
+    u5 = u1 + ydiff * (u2 - u1) / dy
+    u6 = u3 + ydiff * (u4 - u3) / dy
+    return u5 + zdiff * (u6 - u5) / dz
+
+
+def interpolag_Sdep(s, p: Params, comm, lagran_dt):
+    """interpolag_Sdep.f90:21-268: semi-Lagrangian transport of F_LM, F_MM, F_QN, F_NN."""
+    nx, ny, nz = p.nx, p.ny, p.nz
+    X = slice(0, nx)
+    z, zw = _grid_z(p)
+    xg = (np.arange(nx) * p.dx)[None, :] + np.zeros((ny, 1))
+    yg = (np.arange(ny) * p.dy)[:, None] + np.zeros((1, nx))
+    names = ("F_LM", "F_MM", "F_QN", "F_NN")
+    temp = {n: getattr(s, n).copy() for n in names}                  # :69-72
+    u, v, w = s.u, s.v, s.w
+
+    def put(k, x0, y0, z0):
+        for n in names:
+            getattr(s, n)[k, :, X] = trilinear_interp_w(temp[n], p, x0, y0, z0)
+
+    if p.coord == 0:                                                 # :84-149
+        k = 1
+        if p.lbc_mom == 0:
+            put(k, xg - u[k, :, X] * lagran_dt, yg - v[k, :, X] * lagran_dt, np.full((ny, nx), zw[k]))
+        else:
+            put(k, xg - u[k, :, X] * lagran_dt, yg - v[k, :, X] * lagran_dt,
+                z[k] - 0.25 * w[k + 1, :, X] * lagran_dt)
+        kmin = 2
+    else:
+        kmin = 1
+    for k in range(kmin, nz):                                        # :156-178
+        put(k, xg - 0.5 * (u[k - 1, :, X] + u[k, :, X]) * lagran_dt,
+            yg - 0.5 * (v[k - 1, :, X] + v[k, :, X]) * lagran_dt,
+            zw[k] - w[k, :, X] * lagran_dt)
+    if p.coord == p.nproc - 1:                                       # :180-241
+        k = nz
+        if p.ubc_mom == 0:
+            put(k, xg - u[k - 1, :, X] * lagran_dt, yg - v[k - 1, :, X] * lagran_dt, np.full((ny, nx), zw[k]))
+        else:
+            put(k, xg - u[k - 1, :, X] * lagran_dt, yg - v[k - 1, :, X] * lagran_dt,
+                z[k - 1] - 0.25 * w[k - 1, :, X] * lagran_dt)
+    for n in names:                                                  # :244-249
+        mpi_sync_real_array(getattr(s, n), p, comm, down=True, up=True)
+
+
+def lagrange_Sdep(s, sp: Spectral, comm, G_test, G_test_test, lagran_dt, init_F=False):
+    """lagrange_Sdep.f90:22-430.  s.S holds calc_Sij's output; F_*, Cs_opt2 are updated in place.
+    init_F = the F_LM_MM_init / F_QN_NN_init branch (:270-281, :320-331)."""
+    p = sp.p
+    nx, ny, nz, ld = p.nx, p.ny, p.nz, p.ld
+    zero = LASD_ZERO
+    delta = p.delta
+    opftdelta = OPFTIME * delta
+    powcoeff = -1.0 / 8.0
+    const = 2.0 * delta ** 2
+    tf1, tf2 = 2.0, 4.0
+    tf1_2, tf2_2 = tf1 ** 2, tf2 ** 2
+    S = s.S
+    interpolag_Sdep(s, p, comm, lagran_dt)                           # :79
+    u, v, w = s.u, s.v, s.w
+    tf = lambda a: test_filter(a, sp, G_test)
+    ttf = lambda a: test_filter(a, sp, G_test_test)
+    names6 = ("S11", "S12", "S13", "S22", "S23", "S33")
+
+    def contract(a, b):   # a11 b11 + a22 b22 + a33 b33 + 2 (a12 b12 + a13 b13 + a23 b23); order 11,12,13,22,23,33
+        return a[0] * b[0] + a[3] * b[3] + a[5] * b[5] + 2.0 * (a[1] * b[1] + a[2] * b[2] + a[4] * b[4])
+
+    def mag(a):
+        return np.sqrt(2.0 * (a[0] ** 2 + a[3] ** 2 + a[5] ** 2 + 2.0 * (a[1] ** 2 + a[2] ** 2 + a[4] ** 2)))
+
+    for jz in range(1, nz + 1):
+        # :87-115
+        if p.coord == 0 and jz == 1:
+            ub, vb = u[1].copy(), v[1].copy()
+            wb = np.zeros_like(ub) if p.lbc_mom == 0 else 0.25 * w[2]
+        elif p.coord == p.nproc - 1 and jz == nz:
+            ub, vb = u[nz - 1].copy(), v[nz - 1].copy()
+            wb = np.zeros_like(ub) if p.ubc_mom == 0 else 0.25 * w[nz - 1]
+        else:
+            ub = 0.5 * (u[jz] + u[jz - 1]); vb = 0.5 * (v[jz] + v[jz - 1]); wb = w[jz].copy()
+        prods = (ub * ub, ub * vb, ub * wb, vb * vb, vb * wb, wb * wb)       # 11,12,13,22,23,33 (:121-132)
+        u_bar, v_bar, w_bar = tf(ub), tf(vb), tf(wb)                          # :135-151
+        fb = (u_bar * u_bar, u_bar * v_bar, u_bar * w_bar, v_bar * v_bar, v_bar * w_bar, w_bar * w_bar)
+        L = [tf(q) - f for q, f in zip(prods, fb)]
+        u_hat, v_hat, w_hat = ttf(ub), ttf(vb), ttf(wb)                       # :153-168
+        fh = (u_hat * u_hat, u_hat * v_hat, u_hat * w_hat, v_hat * v_hat, v_hat * w_hat, w_hat * w_hat)
+        Q = [ttf(q) - f for q, f in zip(prods, fh)]
+        Sj = [S[n][jz] for n in names6]
+        Smag = mag(Sj)                                                        # :171-172
+        S_bar = [tf(a) for a in Sj]                                           # :176-202
+        S_hat = [ttf(a) for a in Sj]
+        Sb_mag, Sh_mag = mag(S_bar), mag(S_hat)                               # :205-210
+        SS_bar = [tf(Smag * a) for a in Sj]                                   # :213-240
+        SS_hat = [ttf(Smag * a) for a in Sj]
+        M = [const * (a - tf1_2 * Sb_mag * b) for a, b in zip(SS_bar, S_bar)]  # :243-255
+        N = [const * (a - tf2_2 * Sh_mag * b) for a, b in zip(SS_hat, S_hat)]
+        LM, MM, QN, NN = contract(L, M), contract(M, M), contract(Q, N), contract(N, N)   # :258-261
+        if init_F:                                                            # :270-281
+            s.F_MM[jz] = MM
+            s.F_LM[jz] = 0.03 * MM
+            s.F_MM[jz, :, ld - 2:] = 1.0
+            s.F_LM[jz, :, ld - 2:] = 1.0
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            Tn = np.maximum(s.F_LM[jz] * s.F_MM[jz], zero)                        # :306-310
+            Tn = opftdelta * Tn ** powcoeff
+            Tn = np.maximum(zero, Tn)
+            dumfac = lagran_dt / Tn                                               # :313-314
+            epsi = dumfac / (1.0 + dumfac)
+            s.F_LM[jz] = epsi * LM + (1.0 - epsi) * s.F_LM[jz]                    # :316-319
+            s.F_MM[jz] = epsi * MM + (1.0 - epsi) * s.F_MM[jz]
+            s.F_LM[jz] = np.maximum(zero, s.F_LM[jz])
+            Cs2 = s.F_LM[jz] / (s.F_MM[jz] + zero)                                # :323-327
+            Cs2[:, ld - 2:] = zero
+            Cs2 = np.maximum(zero, Cs2)
+            if init_F:                                                            # :330-341
+                s.F_NN[jz] = NN
+                s.F_QN[jz] = 0.03 * NN
+                s.F_NN[jz, :, ld - 2:] = 1.0
+                s.F_QN[jz, :, ld - 2:] = 1.0
+            Tn = np.maximum(s.F_QN[jz] * s.F_NN[jz], zero)                        # :350-354
+            Tn = opftdelta * Tn ** powcoeff
+            Tn = np.maximum(zero, Tn)
+            dumfac = lagran_dt / Tn                                               # :357-358
+            epsi = dumfac / (1.0 + dumfac)
+            s.F_QN[jz] = epsi * QN + (1.0 - epsi) * s.F_QN[jz]                    # :360-363
+            s.F_NN[jz] = epsi * NN + (1.0 - epsi) * s.F_NN[jz]
+            s.F_QN[jz] = np.maximum(zero, s.F_QN[jz])
+            Cs4 = s.F_QN[jz] / (s.F_NN[jz] + zero)                                # :376-380
+            Cs4[:, ld - 2:] = zero
+            Cs4 = np.maximum(zero, Cs4)
+            Beta = (Cs4 / Cs2) ** (math.log(tf1) / (math.log(tf2) - math.log(tf1)))   # :383-384
+        if (p.coord == p.nproc - 1 and jz == nz and p.ubc_mom == 0) or (p.coord == 0 and jz == 1 and p.lbc_mom == 0):
+            Beta = np.ones_like(Beta)                                         # :386-397
+        Betaclip = np.maximum(Beta, 1.0 / (tf1 * tf2))                        # :400-405
+        Cs = Cs2 / Betaclip
+        Cs[:, ld - 2:] = zero
+        s.Cs_opt2[jz] = np.maximum(zero, Cs)                                  # :410
+    for n in ("F_LM", "F_MM", "F_QN", "F_NN"):                                # :417-420
+        mpi_sync_real_array(getattr(s, n), p, comm, down=True, up=True)
 
 
 # ----------------------------------------------------------------------------------
@@ -1044,10 +1268,13 @@ class State:
         o = State(self.p)
         for n in FIELDS:
             getattr(o, n)[...] = getattr(self, n)
+        for n in LASD_FIELDS:
+            if hasattr(self, n):
+                setattr(o, n, getattr(self, n).copy())
         return o
 
 
-def step(s: State, sp: Spectral, comm, mode="full", first_step=False, G_test=None):
+def step(s: State, sp: Spectral, comm, mode="full", first_step=False, G_test=None, lasd=None):
     """One timestep, main.f90:130-344.
 
     mode = "core": the scope-table (a)-(e) path only -- derivatives, convec, AB2,
@@ -1071,7 +1298,7 @@ def step(s: State, sp: Spectral, comm, mode="full", first_step=False, G_test=Non
     if coord == 0 or coord == nproc - 1:
         wallstress(s, sp, G_test)
     if mode == "full":
-        sgs_stag(s, p, comm)                                         # :189
+        sgs_stag(s, p, comm, lasd=lasd)                              # :189
         comm.sendrecv(s.tzz[nz - 1], coord + 1, s.tzz[0], coord - 1, 6)   # :194
         s.divtx, s.divty = divstress_uv(s, sp)                       # :202
         s.divtz = divstress_w(s, sp)                                 # :203

@@ -158,6 +158,14 @@ def step_kwargs(p, it, mode):
                 sgs_model=p.sgs_model, ifilter=p.ifilter, Co=p.Co, wall_damp_exp=p.wall_damp_exp, vonk=p.vonk, zo=p.zo)
 
 
+def step_kwargs_pre_dyn(p, it, mode):
+    """sgs_model 5 before DYN_init: Cs_opt2 = 0.03 set at jt = 1 (sgs_stag_util.f90:187-189), no update."""
+    kw = step_kwargs(p, it, mode)
+    if p.sgs and p.sgs_model == 5 and mode == "full":
+        kw["lasd_cs_init"] = (it == 0)
+    return kw
+
+
 def check_steps(core, p, nsteps=1, tol=1e-12, seed=41, names=("u", "v", "w", "p", "RHSx", "RHSy", "RHSz"), mode="core"):
     """nsteps of the device-resident step vs oracle.step(mode) from identical fields.  mode "core":
     scope rows (a)-(e); "full": + wallstress, constant-coefficient sgs_stag, divstress (rows (f)-1)."""
@@ -171,7 +179,7 @@ def check_steps(core, p, nsteps=1, tol=1e-12, seed=41, names=("u", "v", "w", "p"
         core.upload(n, np.zeros(core.dims.shape))
     for it in range(nsteps):
         O.step(s, sp, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=G)
-        core.step(**step_kwargs(p, it, mode))
+        core.step(**step_kwargs_pre_dyn(p, it, mode))
     out = {}
     for n in names:
         g = core.download(n)
@@ -183,7 +191,51 @@ def check_steps(core, p, nsteps=1, tol=1e-12, seed=41, names=("u", "v", "w", "p"
     return out
 
 
-def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core"):
+def lasd_schedule(p, it, cs_count=2, dyn_init=2):
+    """Step counters of sgs_stag_util.f90:73-82,183-216 for a fresh run (inilag, jt = jt_total = it + 1,
+    fixed dt): Cs_opt2 = 0.03 at jt = 1, lagrange_Sdep every cs_count steps from DYN_init on, F_* initialised
+    the first time (jt == DYN_init)."""
+    jt = it + 1
+    return dict(lasd_cs_init=(jt == 1), lasd_update=(jt >= dyn_init and jt % cs_count == 0),
+                lasd_init_F=(jt == dyn_init), lagran_dt=cs_count * p.dt)
+
+
+def check_lasd_steps(core, p, nsteps=4, tol=1e-11, seed=61, amp=0.5):
+    """Full steps with sgs_model = 5 (Lagrangian scale-dependent dynamic model, rows (f)-2) against the oracle:
+    velocities, pressure, and the model's own state F_LM, F_MM, F_QN, F_NN, Cs_opt2."""
+    assert p.sgs and p.sgs_model == 5
+    sp = O.Spectral(p)
+    nx, nz = p.nx, p.nz
+    G = O.test_filter_kernel(sp)
+    G2 = O.test_filter_kernel(sp, alpha=4.0)
+    s = initial_state(p, seed=seed, amp=amp)
+    for n in ("u", "v", "w"):
+        core.upload(n, getattr(s, n))
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz", "F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2"):
+        core.upload(n, np.zeros(core.dims.shape))
+    for it in range(nsteps):
+        sch = lasd_schedule(p, it)
+        lasd = dict(sp=sp, G_test=G, G_test_test=G2, lagran_dt=sch["lagran_dt"], cs_init=sch["lasd_cs_init"],
+                    update=sch["lasd_update"], init_F=sch["lasd_init_F"])
+        O.step(s, sp, O.LocalComm(), mode="full", first_step=(it == 0), G_test=G, lasd=lasd)
+        core.step(**step_kwargs(p, it, "full"), **sch)
+    out = {}
+    for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz", "F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2"):
+        g = core.download(n)
+        r = getattr(s, n)
+        hi = nz + 1 if n in ("w", "RHSz", "p", "F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2") else nz
+        out[n] = rel(g[1:hi, :, :nx], r[1:hi, :, :nx])
+    for k, v in out.items():
+        # Cs_opt2 = F_LM / F_MM / clip(Cs_4d / Cs_2d) is a ratio of ratios of running averages: locally
+        # ill-conditioned where F_LM -> 0, so its own bound is looser than that of the fields it feeds
+        assert v <= (CS_TOL if k == "Cs_opt2" else tol), (k, v, out)
+    return out
+
+
+CS_TOL = 1e-9
+
+
+def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core", lasd=False):
     """nproc ranks (threads of this process, one Core each) advance `nsteps` core steps;
     the gathered result must match the SINGLE-slab oracle (which the multi-slab oracle
     equals, tests/test_oracle_kat.py)."""
@@ -194,8 +246,15 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
     sref = O.State(pg)
     sref.u, sref.v, sref.w = (O.scatter_slab(f, pg) for f in (ug, vg, wg))
     Gg = O.test_filter_kernel(spg)
+    G2g = O.test_filter_kernel(spg, alpha=4.0)
+    names = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz") + (("Cs_opt2", "F_LM", "F_NN") if lasd else ())
     for it in range(nsteps):
-        O.step(sref, spg, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=Gg)
+        ld_ = None
+        if lasd:
+            sch = lasd_schedule(pg, it)
+            ld_ = dict(sp=spg, G_test=Gg, G_test_test=G2g, lagran_dt=sch["lagran_dt"], cs_init=sch["lasd_cs_init"],
+                       update=sch["lasd_update"], init_F=sch["lasd_init_F"])
+        O.step(sref, spg, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=Gg, lasd=ld_)
     ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
     cores = [lesgo_b200.Core(make_dims(p, device=(device_of(p.coord) if device_of else -1)), lib=lib) for p in ps]
     ident = cores[0].comm_unique_id()
@@ -207,11 +266,11 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
             c.comm_init(ident)
             for n, g in (("u", ug), ("v", vg), ("w", wg)):
                 c.upload(n, O.scatter_slab(g, p))
-            for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+            for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz") + (("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2") if lasd else ()):
                 c.upload(n, np.zeros(c.dims.shape))
             for it in range(nsteps):
-                c.step(**step_kwargs(p, it, mode))
-            res[r] = {n: c.download(n) for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")}
+                c.step(**step_kwargs(p, it, mode), **(lasd_schedule(p, it) if lasd else {}))
+            res[r] = {n: c.download(n) for n in names}
             # mpi_sync_real_array (mpi_defs.f90:245-262) on a host array
             var = np.zeros(c.dims.shape)
             for k in range(p.nz + 1):
@@ -237,15 +296,15 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
             raise e
     out = {}
     nzt = pg.nz_tot
-    for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz"):
-        top = n in ("w", "RHSz", "p")
+    for n in names:
+        top = n in ("w", "RHSz", "p", "Cs_opt2", "F_LM", "F_NN")
         g = O.gather_slabs([res[r][n] for r in range(nproc)], ps, top_extra=top)
         hi = nzt if top else nzt - 1
         out[n] = rel(g[1:hi + 1, :, :pg.nx], getattr(sref, n)[1:hi + 1, :, :pg.nx])
     cfl_ref = O.get_max_cfl(sref, pg, O.LocalComm())
     assert all(abs(res[r]["cfl"] - cfl_ref) <= 1e-12 * cfl_ref for r in range(nproc)), (cfl_ref, [res[r]["cfl"] for r in range(nproc)])
     for k, v in out.items():
-        assert v <= tol, (k, v, out)
+        assert v <= (CS_TOL if k == "Cs_opt2" else tol), (k, v, out)
     return out
 
 

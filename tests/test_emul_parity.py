@@ -81,6 +81,30 @@ def test_emul_multirank_full_step():
     print(out)
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(nx=16, ny=16, Nz=8, lbc_mom=2, ubc_mom=0),               # half channel (LES_channel-like), equilibrium wall
+    dict(nx=16, ny=32, Nz=6, lbc_mom=1, ubc_mom=1, molec=True),   # two DNS-type walls
+    dict(nx=32, ny=16, Nz=6, lbc_mom=0, ubc_mom=2, ifilter=2),    # stress-free bottom, wall-modelled top, Gaussian filter
+])
+def test_emul_lasd_steps(cfg, monkeypatch):
+    """Rows (f)-2: sgs_model 5 (lagrange_Sdep + interpolag_Sdep) over four steps with DYN_init = cs_count = 2,
+    in plane chunks of 3 so the chunk seams are exercised."""
+    from helpers import check_lasd_steps
+    monkeypatch.setenv("LESGO_LASD_CHUNK", "3")
+    p = O.Params(sgs=True, sgs_model=5, dt=4e-3, **cfg)
+    out = check_lasd_steps(core_for(p), p, nsteps=4)
+    print(out)
+
+
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_emul_multirank_lasd(nproc):
+    """The semi-Lagrangian transport reads ghost planes of F_* and u, v, w across slab seams."""
+    from helpers import check_multirank_steps
+    kw = dict(nx=16, ny=16, Nz=12, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=5, dt=4e-3)
+    out = check_multirank_steps(emul_library(), kw, nproc, nsteps=4, mode="full", lasd=True)
+    print(out)
+
+
 @pytest.mark.parametrize("Nz,mode", [(2, "core"), (2, "full"), (3, "full")])
 def test_emul_minimal_slab(Nz, mode):
     """Smallest slabs: bottom and top special planes adjacent (nz = 3 or 4)."""

@@ -32,3 +32,12 @@ def test_multi_gpu_full_step():
     out = check_multirank_steps(lesgo_b200.load_library(), kw, 2, nsteps=2, tol=1e-11, mode="full",
                                 device_of=lambda coord: coord)
     print(out)
+
+
+def test_multi_gpu_lasd():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    kw = dict(nx=64, ny=64, Nz=32, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=5, dt=2e-3)
+    out = check_multirank_steps(lesgo_b200.load_library(), kw, 2, nsteps=4, tol=1e-11, mode="full", lasd=True,
+                                device_of=lambda coord: coord)
+    print(out)

@@ -135,6 +135,20 @@ def test_full_step_les_channel(cfg):
     print(out)
 
 
+@pytest.mark.parametrize("cfg,nsteps,tol", [
+    (dict(nx=64, ny=64, Nz=32, lbc_mom=2, ubc_mom=0, dt=2e-3), 10, 1e-9),     # LES half channel as LES_channel_Re1000
+    (dict(nx=64, ny=48, Nz=16, lbc_mom=1, ubc_mom=1, molec=True, dt=2e-3), 4, 1e-11),
+    (dict(nx=256, ny=256, Nz=8, lbc_mom=2, ubc_mom=2, ifilter=2, dt=1e-3), 2, 1e-11),   # BASELINE configs[2] plane size
+])
+def test_lasd_les_channel(cfg, nsteps, tol):
+    """Rows (f)-2: Lagrangian scale-dependent dynamic model (lagrange_Sdep.f90 + interpolag_Sdep.f90) inside the
+    full step, DYN_init = cs_count = 2; also checks the model's own state F_LM, F_MM, F_QN, F_NN, Cs_opt2."""
+    from helpers import check_lasd_steps
+    p = O.Params(sgs=True, sgs_model=5, **cfg)
+    out = check_lasd_steps(core_for(p), p, nsteps=nsteps, tol=tol)
+    print(out)
+
+
 def test_misc_entry_points():
     from helpers import check_misc
     p = O.Params(nx=64, ny=32, Nz=12, L_x=3.0)

@@ -17,9 +17,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--grid", default="512,512,256")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--mode", type=int, default=0)
+ap.add_argument("--lasd", type=int, default=0, help="cs_count: full step with sgs_model 5, lagrange_Sdep every cs_count steps")
 a = ap.parse_args()
 nx, ny, Nz = (int(x) for x in a.grid.split(","))
-dims = lesgo_b200.Dims(nx=nx, ny=ny, Nz=Nz, device=0)
+dims = lesgo_b200.Dims(nx=nx, ny=ny, Nz=Nz, device=0, sgs=bool(a.lasd), lbc_mom=2 if a.lasd else 1, ubc_mom=0 if a.lasd else 1)
 core = lesgo_b200.Core(dims)
 u, v, w = synthetic_slab(dims)
 for n, arr in (("u", u), ("v", v), ("w", w)):
@@ -27,6 +28,15 @@ for n, arr in (("u", u), ("v", v), ("w", w)):
 for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
     core.upload(n, np.zeros(dims.shape))
 kw = dict(dt=2e-4, tadv1=1.5, tadv2=-0.5, mode=a.mode, ubot=-1.0, utop=1.0)
+if a.lasd:
+    # LES half channel with the Lagrangian scale-dependent model: one lagrange_Sdep per timed step
+    # (the amortised cost per step is that share / cs_count)
+    for n in ("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2"):
+        core.upload(n, np.zeros(dims.shape))
+    kw.update(mode=1, sgs_model=5, lagran_dt=a.lasd * 2e-4)
+    core.step(first_step=True, lasd_cs_init=True, **kw)
+    core.step(lasd_update=True, lasd_init_F=True, **kw)
+    kw.update(lasd_update=True)
 core.step(first_step=True, **kw)
 for _ in range(2):
     core.step(**kw)

@@ -105,7 +105,10 @@ enum lesgo_gpu_field {
     LG_TXX, LG_TXY, LG_TXZ, LG_TYY, LG_TYZ, LG_TZZ,
     /* Lagrangian scale-dependent model state (sgs_param.f90; lagrange_Sdep.f90, interpolag_Sdep.f90):
      * allocated only when a step with sgs_model = 5 (or an upload/download of them) asks for them */
-    LG_F_LM, LG_F_MM, LG_F_QN, LG_F_NN, LG_CS_OPT2, LG_NFIELDS
+    LG_F_LM, LG_F_MM, LG_F_QN, LG_F_NN, LG_CS_OPT2,
+    /* applied body force of the actuator disks (sim_param.f90 fxa, fya, fza; forcing.f90:102-106):
+     * allocated by lesgo_gpu_turbines_init */
+    LG_FXA, LG_FYA, LG_FZA, LG_NFIELDS
 };
 /* device pointer of a resident field ((ld, ny, 0:nz) doubles); allocated on first use.  NOTE:
  * lesgo_gpu_step makes RHS* and RHS*_f trade places every step instead of copying (main.f90:155-157),
@@ -140,12 +143,36 @@ typedef struct lesgo_gpu_step_params {
      *   lagran_dt   : sgs_stag_util.f90:73-82 (cs_count * dt for a fixed time step) */
     int lasd_cs_init, lasd_update, lasd_init_F;
     double lagran_dt;
+    /* actuator disks (after lesgo_gpu_turbines_init): 1 = forcing_applied + main.f90:264-266 inside the step,
+     * i.e. turbines_forcing on the velocities of time level n and RHS += (fxa, fya, fza); turbines_eps is the
+     * time-filter weight (dt_dim / T_avg_dim) / (1 + dt_dim / T_avg_dim) of turbines.f90:563-567 */
+    int turbines;
+    double turbines_eps;
 } lesgo_gpu_step_params;
 /* One timestep main.f90:155-344 on the resident fields, no host round trip. */
 int lesgo_gpu_step(lesgo_gpu_ctx* ctx, const lesgo_gpu_step_params* sp);
 /* cfl_util.f90:35-69 get_max_cfl (dx, dy from L/n) and rmsdiv.f90 on resident fields */
 int lesgo_gpu_max_cfl(lesgo_gpu_ctx* ctx, double dt, double* cfl);
 int lesgo_gpu_rmsdiv(lesgo_gpu_ctx* ctx, double* rms);
+
+/* ---- actuator-disk turbines (turbines.f90) ---------------------------------------------------------
+ * The host keeps turbines_init / turbines_nodes (turbines.f90:129-462: input files, the filtered indicator
+ * function of turbine_indicator.f90, node search) and hands the result over; call again when the disks
+ * move (dyn_theta1/2).  use_rotation = .false. (turbines.f90:76) only. */
+typedef struct lesgo_gpu_turbine {
+    int num_nodes;           /* wind_farm%turbine(s)%num_nodes on THIS rank (may be 0)                   */
+    const int* nodes;        /* (num_nodes, 3) triplets i, j (1-based), k (local, 1..nz-1): %nodes(l,1:3)  */
+    const double* ind;       /* (num_nodes) normalised indicator weights %ind(l)                          */
+    double nhat[3];          /* unit normal, turbines.f90:344-346                                         */
+    double Ct_prime, dia;
+    double M;                /* %turb_ind_func%M, used when adm_correction                                */
+    double u_d_T;            /* initial running-average disk velocity (turbine_vel_init, :642-676)        */
+} lesgo_gpu_turbine;
+int lesgo_gpu_turbines_init(lesgo_gpu_ctx* ctx, int nloc, const lesgo_gpu_turbine* turbines, int adm_correction);
+/* turbines_forcing (turbines.f90:465-638) on the resident u, v, w -> resident LG_FXA, LG_FYA, LG_FZA (fza on
+ * w nodes, ghost planes synchronised).  u_d, u_d_T, f_n: optional host arrays (nloc) receiving %u_d, %u_d_T,
+ * %f_n after the update (NULL = leave everything on the device, no synchronisation). */
+int lesgo_gpu_turbines_forcing(lesgo_gpu_ctx* ctx, double eps, double* u_d, double* u_d_T, double* f_n);
 
 /* ---- multi-GPU (mpi_defs.f90 -> NCCL) --------------------------------------------------------
  * id: 128-byte ncclUniqueId made by lesgo_gpu_comm_unique_id on coord 0 and broadcast by

@@ -24,13 +24,13 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .lib import DimsStruct, Library, LibraryError, StepParams, load_library
+from .lib import DimsStruct, Library, LibraryError, StepParams, TurbineStruct, load_library
 
 FIELD_IDS = {n: i for i, n in enumerate(
     ["u", "v", "w", "dudx", "dudy", "dudz", "dvdx", "dvdy", "dvdz", "dwdx", "dwdy", "dwdz",
      "RHSx", "RHSy", "RHSz", "RHSx_f", "RHSy_f", "RHSz_f", "p", "dpdx", "dpdy", "dpdz",
      "divtx", "divty", "divtz", "txx", "txy", "txz", "tyy", "tyz", "tzz",
-     "F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2"])}
+     "F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2", "fxa", "fya", "fza"])}
 
 
 @dataclass
@@ -249,14 +249,42 @@ class Core:
     def step(self, dt, tadv1=1.5, tadv2=-0.5, first_step=False, mode=0, mean_p_force_x=0.0,
              mean_p_force_y=0.0, ubot=0.0, utop=0.0, nu=0.0, sgs_model=1, ifilter=1, Co=0.16,
              wall_damp_exp=2.0, vonk=0.4, zo=1e-4, lasd_cs_init=False, lasd_update=False, lasd_init_F=False,
-             lagran_dt=0.0):
+             lagran_dt=0.0, turbines=False, turbines_eps=1.0):
         """One timestep main.f90:155-344 on the resident fields.  mode 0: core path (divt* as
         resident); mode 1: full step with wallstress, sgs_stag (constant coefficient, or sgs_model 5 =
         Lagrangian scale-dependent: lasd_* select the branch of sgs_stag_util.f90:183-216) and divstress."""
         sp = StepParams(dt, tadv1, tadv2, mean_p_force_x, mean_p_force_y, ubot, utop, nu, int(first_step), int(mode),
                         int(sgs_model), int(ifilter), Co, wall_damp_exp, vonk, zo, int(lasd_cs_init),
-                        int(lasd_update), int(lasd_init_F), float(lagran_dt))
+                        int(lasd_update), int(lasd_init_F), float(lagran_dt), int(turbines), float(turbines_eps))
         self._ck(self.lib.step(self._ctx, C.byref(sp)), "step")
+
+    # -- actuator disks (turbines.f90) --------------------------------------------------------------
+    def turbines_init(self, farm, adm_correction=False):
+        """farm: objects with nodes (n, 3) int (1-based i, j, local k), ind (n), nhat, Ct_prime, dia, M, u_d_T --
+        what turbines_nodes (turbines.f90:275-462) leaves in wind_farm%turbine(:)."""
+        arr = (TurbineStruct * max(len(farm), 1))()
+        keep = []
+        for s, t in enumerate(farm):
+            nodes = np.ascontiguousarray(np.asarray(t.nodes, dtype=np.int32).reshape(-1, 3))
+            ind = np.ascontiguousarray(np.asarray(t.ind, dtype=np.float64))
+            keep += [nodes, ind]
+            arr[s].num_nodes = len(ind)
+            arr[s].nodes = nodes.ctypes.data
+            arr[s].ind = ind.ctypes.data
+            arr[s].nhat = (C.c_double * 3)(*[float(x) for x in t.nhat])
+            arr[s].Ct_prime, arr[s].dia, arr[s].M, arr[s].u_d_T = float(t.Ct_prime), float(t.dia), float(t.M), float(t.u_d_T)
+        self._nturb = len(farm)
+        self._ck(self.lib.turbines_init(self._ctx, len(farm), arr, int(adm_correction)), "turbines_init")
+
+    def turbines_forcing(self, eps, fetch=True):
+        """turbines_forcing (turbines.f90:465-638) on the resident fields; returns (u_d, u_d_T, f_n) per disk."""
+        n = getattr(self, "_nturb", 0)
+        if not fetch:
+            self._ck(self.lib.turbines_forcing(self._ctx, float(eps), None, None, None), "turbines_forcing")
+            return None
+        out = [np.zeros(max(n, 1)) for _ in range(3)]
+        self._ck(self.lib.turbines_forcing(self._ctx, float(eps), *[o.ctypes.data for o in out]), "turbines_forcing")
+        return tuple(o[:n] for o in out)
 
     def max_cfl(self, dt):
         v = C.c_double()

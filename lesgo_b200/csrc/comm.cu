@@ -53,6 +53,19 @@ public:
         *v = acc;
         return 0;
     }
+    int allreduce_sum_dev(double* dev, size_t n, cudaStream_t) override {
+        for (int r = 0; r < nranks_; ++r) if (r != rank_) put(r, dev, n);
+        std::vector<double> x(n);
+        // rank order, so every rank forms the same sum
+        std::vector<double> own(dev, dev + n), acc(n, 0.0);
+        for (int r = 0; r < nranks_; ++r) {
+            const double* src = own.data();
+            if (r != rank_) { get(r, x.data(), n); src = x.data(); }
+            for (size_t i = 0; i < n; ++i) acc[i] = r == 0 ? src[i] : acc[i] + src[i];
+        }
+        std::memcpy(dev, acc.data(), n * sizeof(double));
+        return 0;
+    }
     int alltoall(const double* sendbuf, double* recvbuf, size_t count, cudaStream_t) override {
         for (int r = 0; r < nranks_; ++r) put(r, sendbuf + size_t(r) * count, count);
         for (int r = 0; r < nranks_; ++r) get(r, recvbuf + size_t(r) * count, count);
@@ -157,6 +170,11 @@ public:
         cudaMemcpyAsync(hbuf, dbuf, sizeof(double), cudaMemcpyDeviceToHost, s);
         if (cudaStreamSynchronize(s) != cudaSuccess) { err_ = "allreduce sync failed"; return 1; }
         *v = *hbuf;
+        return 0;
+    }
+    int allreduce_sum_dev(double* dev, size_t n, cudaStream_t s) override {
+        int rc = api().AllReduce(dev, dev, n, ncclFloat64, ncclSum, comm, s);
+        if (rc) return fail("ncclAllReduce", rc);
         return 0;
     }
     int alltoall(const double* sendbuf, double* recvbuf, size_t count, cudaStream_t s) override {

@@ -26,6 +26,9 @@ public:
                          const int* src, const size_t* count, cudaStream_t s) = 0;
     // host scalar all-reduce (cfl_util.f90:66,107; rmsdiv.f90:54)
     virtual int allreduce(double* host_value, int op /*0 sum, 1 max, 2 min*/, cudaStream_t s) = 0;
+    // in-place sum of n doubles in DEVICE memory over all ranks, stream-ordered, no host sync
+    // (turbines.f90:553-560: MPI_Allreduce of the per-disk velocities)
+    virtual int allreduce_sum_dev(double* dev, size_t n, cudaStream_t s) = 0;
     // every rank r sends sendbuf + r*count and receives into recvbuf + r*count (transpose)
     virtual int alltoall(const double* sendbuf, double* recvbuf, size_t count, cudaStream_t s) = 0;
 

@@ -2,6 +2,7 @@
 // include/lesgo_gpu.h.  Mirrors, routine by routine, the reference's derivatives.f90,
 // convec.f90, press_stag_array.f90, tridag_array.f90, fft.f90 and the time-loop glue of
 // main.f90:155-344 / forcing.f90:149-244.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +18,7 @@
 #include "bigx_kernels.h"
 #include "prodfwd_kernels.h"
 #include "lasd_kernels.h"
+#include "turbine_kernels.h"
 
 using namespace lg;
 
@@ -64,6 +66,11 @@ struct lesgo_gpu_ctx {
     double* lasd_buf[51] = {nullptr};      // lagrange_Sdep work fields, lasd_chunk planes each
     double* lasd_tmp[4] = {nullptr};       // interpolag_Sdep's copies of F_LM, F_MM, F_QN, F_NN
     int lasd_chunk = 0;
+    // actuator disks (lesgo_gpu_turbines_init)
+    TurbSet turb;
+    bool turb_on = false, turb_fz = false;
+    int turb_adm = 0;
+    double* turb_fzuv = nullptr;           // fza before interp_to_w_grid (uv nodes)
     int sgs_cfg = -1;                      // (sgs_model, ifilter) the tables above were built for
     double* fields[LG_NFIELDS] = {nullptr};
     std::vector<double*> staging;          // device staging for host-pointer arguments
@@ -390,6 +397,8 @@ struct Fuse {
     int kmax[3] = {0, 0, 0};
     int first_step = 0;
     double dt = 0, t1 = 0, t2 = 0;
+    const double* fa[3] = {nullptr, nullptr, nullptr};   // applied body force (actuator disks)
+    int kfa = 0;
     // dpdz fusion (press): RHSz, w and the projection range
     double* rhsz = nullptr;
     double* w = nullptr;
@@ -411,7 +420,8 @@ int xinv(lesgo_gpu_ctx* c, bool bigx, const double* const* src, long splane, int
         for (int i = 0; i < nf; ++i) epi.dst[i] = dst[i];
         epi.lay = dl; epi.nx = c->nx; epi.pad = pad;
         epi.mode = fz->mode; epi.first_step = fz->first_step; epi.dt = fz->dt; epi.t1 = fz->t1; epi.t2 = fz->t2;
-        for (int i = 0; i < 3; ++i) { epi.divt[i] = fz->divt[i]; epi.rhs_f[i] = fz->rhs_f[i]; epi.u[i] = fz->u[i]; epi.force[i] = fz->force[i]; epi.kmax[i] = fz->kmax[i]; }
+        for (int i = 0; i < 3; ++i) { epi.divt[i] = fz->divt[i]; epi.rhs_f[i] = fz->rhs_f[i]; epi.u[i] = fz->u[i]; epi.force[i] = fz->force[i]; epi.kmax[i] = fz->kmax[i]; epi.fa[i] = fz->fa[i]; }
+        epi.kfa = fz->kfa;
         rc = launch_xinv_fused(c->nx, in, epi, nf, nyrows, k0, k1 - k0, c->Wx, c->Whx, c->stream);
     } else {
         EpiStore epi;
@@ -1249,15 +1259,118 @@ int sgs_and_divstress(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double*
     return 0;
 }
 
+// ---- actuator disks, turbines.f90:465-638 on the resident fields -----------------------
+int turbines_forcing(lesgo_gpu_ctx* c, double eps) {
+    if (!c->turb_on) return c->fail("lesgo_gpu_turbines_init has not been called");
+    const int nz = c->nz, nloc = c->turb.nloc;
+    double* W = field(c, LG_W);
+    double *fxa = field(c, LG_FXA), *fya = field(c, LG_FYA), *fza = field(c, LG_FZA);
+    if (!W || !fxa || !fya || !fza) return 1;
+    if (c->comm && c->comm->sync_planes(W, c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());   // :499
+    if (nloc > 0) {
+        ProfScope ps_(c, "turbines");
+        const double vol = (c->d.L_x / c->nx) * (c->d.L_y / c->ny) * c->d.dz;
+        LG_LAUNCH(k_turb_gather, dim3(nloc), dim3(kBlock), 0, c->stream, c->turb, field(c, LG_U), field(c, LG_V), W, c->plane, vol);
+        if (c->comm && c->comm->allreduce_sum_dev(c->turb.u_d, size_t(nloc), c->stream)) return c->fail(c->comm->error());   // :553-560
+        LG_LAUNCH(k_turb_update, dim3(1), dim3(64), 0, c->stream, c->turb, eps, c->turb_adm);
+        LG_LAUNCH(k_turb_scatter, dim3(nloc), dim3(kBlock), 0, c->stream, c->turb, fxa, fya, c->turb_fzuv);
+        c->launches += 3;
+    }
+    if (c->comm) {                                                 // :620-622
+        ProfScope ps_(c, "halo");
+        if (c->comm->sync_planes(fxa, c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
+        if (c->comm->sync_planes(fya, c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
+        if (c->turb_fz && c->comm->sync_planes(c->turb_fzuv, c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
+    }
+    if (c->turb_fz) {                                              // :623 interp_to_w_grid; all nhat(3) = 0: fza stays 0
+        ProfScope ps_(c, "turbines");
+        LG_LAUNCH(k_interp_w, dim3(grid1d(c->plane * nz)), dim3(kBlock), 0, c->stream, c->turb_fzuv, fza, c->plane, 1, nz + 1);
+        c->launches++;
+        if (c->comm && c->comm->sync_planes(fza, c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
+    }
+    return 0;
+}
+
+template <class T>
+int upload_vec(lesgo_gpu_ctx* c, const T** dst, const std::vector<T>& h) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (h.empty() ? 1 : h.size()) * sizeof(T)));
+    c->allocs.push_back(p);
+    if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *dst = static_cast<const T*>(p);
+    return 0;
+}
+
+int turbines_init(lesgo_gpu_ctx* c, int nloc, const lesgo_gpu_turbine* t, int adm) {
+    if (nloc < 0 || (nloc > 0 && !t)) return c->fail("lesgo_gpu_turbines_init: bad arguments");
+    const int nz = c->nz;
+    std::vector<int> start(nloc + 1, 0), owner;
+    std::vector<long> off;
+    std::vector<double> ind, nhat(3 * size_t(nloc)), Ct(nloc), dia(nloc), M(nloc), udT(nloc);
+    bool fz = false;
+    for (int s = 0; s < nloc; ++s) {
+        if (t[s].num_nodes < 0 || (t[s].num_nodes > 0 && (!t[s].nodes || !t[s].ind)))
+            return c->fail("lesgo_gpu_turbines_init: turbine without node list");
+        for (int l = 0; l < t[s].num_nodes; ++l) {
+            const int i = t[s].nodes[3 * l], j = t[s].nodes[3 * l + 1], k = t[s].nodes[3 * l + 2];
+            if (i < 1 || i > c->nx || j < 1 || j > c->ny || k < 1 || k > nz - 1)
+                return c->fail("lesgo_gpu_turbines_init: node outside 1:nx, 1:ny, 1:nz-1 (turbines.f90:423-425)");
+            off.push_back(c->lay().at(k, j - 1, i - 1));
+            ind.push_back(t[s].ind[l]);
+        }
+        start[s + 1] = int(off.size());
+        for (int q = 0; q < 3; ++q) nhat[3 * s + q] = t[s].nhat[q];
+        if (t[s].nhat[2] != 0.0) fz = true;
+        Ct[s] = t[s].Ct_prime; dia[s] = t[s].dia; M[s] = t[s].M; udT[s] = t[s].u_d_T;
+    }
+    // the reference ASSIGNS the force node by node in disk order (turbines.f90:599-606): where disks overlap the
+    // last one wins, so only the last entry of a grid point scatters
+    owner.assign(off.size(), 1);
+    {
+        std::vector<size_t> order(off.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return off[a] < off[b]; });
+        for (size_t i = 0; i + 1 < order.size(); ++i)
+            if (off[order[i]] == off[order[i + 1]]) owner[order[i]] = 0;
+    }
+    TurbSet ts;
+    ts.nloc = nloc;
+    const double *d_udT = nullptr, *d_zero = nullptr;
+    if (upload_vec(c, &ts.start, start) || upload_vec(c, &ts.off, off) || upload_vec(c, &ts.ind, ind) ||
+        upload_vec(c, &ts.owner, owner) || upload_vec(c, &ts.nhat, nhat) || upload_vec(c, &ts.Ct_prime, Ct) ||
+        upload_vec(c, &ts.dia, dia) || upload_vec(c, &ts.M, M) || upload_vec(c, &d_udT, udT)) return 1;
+    std::vector<double> z(nloc, 0.0);
+    if (upload_vec(c, &d_zero, z)) return 1;
+    ts.u_d_T = const_cast<double*>(d_udT);
+    ts.u_d = const_cast<double*>(d_zero);
+    if (upload_vec(c, &d_zero, z)) return 1;
+    ts.f_n = const_cast<double*>(d_zero);
+    c->turb = ts; c->turb_adm = adm; c->turb_fz = fz;
+    // forcing.f90:103-105: the force fields are zero away from the disks
+    const size_t nfield = size_t(c->plane) * (nz + 1);
+    if (dev_alloc(c, &c->turb_fzuv, nfield)) return 1;
+    double* f[4] = {field(c, LG_FXA), field(c, LG_FYA), field(c, LG_FZA), c->turb_fzuv};
+    for (int i = 0; i < 4; ++i) {
+        if (!f[i]) return 1;
+        CK(cudaMemsetAsync(f[i], 0, nfield * sizeof(double), c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    c->turb_on = true;
+    return 0;
+}
+
 // ---- one timestep on the resident fields: main.f90:155-344 ----------------------------------------
 int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     const int nz = c->nz;
     double* F[LG_NFIELDS];
     const bool lasd = sp->mode == 1 && c->d.sgs && sp->sgs_model == 5;
     for (int i = 0; i < LG_NFIELDS; ++i) {
-        F[i] = (i < LG_F_LM || lasd) ? field(c, i) : nullptr;
-        if (!F[i] && (i < LG_F_LM || lasd)) return 1;
+        const bool want = i < LG_F_LM || (i < LG_FXA ? lasd : c->turb_on);
+        F[i] = want ? field(c, i) : nullptr;
+        if (!F[i] && want) return 1;
     }
+    if (sp->turbines && !c->turb_on) return c->fail("lesgo_gpu_step: turbines = 1 needs lesgo_gpu_turbines_init");
+    if (sp->turbines && c->chunk != 0) return c->fail("lesgo_gpu_step: turbines need the un-chunked step (LESGO_CHUNK=0)");
     if (sp->mode != 0 && sp->mode != 1) return c->fail("lesgo_gpu_step: mode must be 0 (core) or 1 (full)");
     // :155-157  RHS*_f = RHS*: the two sets trade places instead of being copied (convec
     // rewrites every valid plane of RHS* below, main.f90:207-214)
@@ -1280,10 +1393,14 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     if (sp->mode == 1 && build_sgs_tables(c, sp)) return 1;
     if (wallstress(c, sp, F, sp->mode == 1)) return 1;
     if (sp->mode == 1 && sgs_and_divstress(c, sp, F)) return 1;
+    // :254 forcing_applied: the disks see the velocities of time level n, which the fused epilogue below
+    // advances -- so the forcing runs first; :264-266 RHS += f rides in that epilogue
+    if (sp->turbines && turbines_forcing(c, sp->turbines_eps)) return 1;
     // :207 convec, with :211-214/229-232 (RHS assembly), :273-280 (Euler start) and :287-296 (AB2)
     // fused into the epilogue of its last x pass
     {
         Fuse fz;
+        if (sp->turbines) { fz.fa[0] = F[LG_FXA]; fz.fa[1] = F[LG_FYA]; fz.fa[2] = F[LG_FZA]; fz.kfa = nz - 1; }
         fz.mode = 1; fz.first_step = sp->first_step ? 1 : 0; fz.dt = sp->dt; fz.t1 = sp->tadv1; fz.t2 = sp->tadv2;
         fz.divt[0] = F[LG_DIVTX]; fz.divt[1] = F[LG_DIVTY]; fz.divt[2] = F[LG_DIVTZ];
         fz.rhs_f[0] = F[LG_RHSX_F]; fz.rhs_f[1] = F[LG_RHSY_F]; fz.rhs_f[2] = F[LG_RHSZ_F];
@@ -1670,6 +1787,26 @@ int lesgo_gpu_step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     if (!c || !sp) return 1;
     if (step(c, sp)) return 1;
     CK(cudaGetLastError());
+    return 0;
+}
+
+int lesgo_gpu_turbines_init(lesgo_gpu_ctx* c, int nloc, const lesgo_gpu_turbine* t, int adm_correction) {
+    ENTER(c);
+    if (!c) return 1;
+    return turbines_init(c, nloc, t, adm_correction);
+}
+
+int lesgo_gpu_turbines_forcing(lesgo_gpu_ctx* c, double eps, double* u_d, double* u_d_T, double* f_n) {
+    ENTER(c);
+    if (!c) return 1;
+    if (turbines_forcing(c, eps)) return 1;
+    const size_t nb = size_t(c->turb.nloc) * sizeof(double);
+    if (nb && (u_d || u_d_T || f_n)) {
+        if (u_d) CK(cudaMemcpyAsync(u_d, c->turb.u_d, nb, cudaMemcpyDeviceToHost, c->stream));
+        if (u_d_T) CK(cudaMemcpyAsync(u_d_T, c->turb.u_d_T, nb, cudaMemcpyDeviceToHost, c->stream));
+        if (f_n) CK(cudaMemcpyAsync(f_n, c->turb.f_n, nb, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     return 0;
 }
 

@@ -159,12 +159,18 @@ struct EpiFused {
     int kmax[3];
     int first_step;
     double dt, t1, t2;
+    const double* fa[3];     // applied body force fxa, fya, fza added on planes k <= kfa (main.f90:264-266), or null
+    int kfa;
     LG_D void store(int fld, int k, int y, int j, double2 v) const {
         const long o = lay.at(k, y, 2 * j);
         if (mode == 1 && k <= kmax[fld]) {
             double2 vb = ld2(divt[fld] + o), vu = ld2(u[fld] + o);
             const double f = force[fld];
             double2 nr = make_double2(dadd(dsub(-v.x, vb.x), f), dadd(dsub(-v.y, vb.y), f));
+            if (fa[fld] && k <= kfa) {
+                const double2 va = ld2(fa[fld] + o);
+                nr = make_double2(dadd(nr.x, va.x), dadd(nr.y, va.y));
+            }
             double2 vf;
             if (first_step) { vf = nr; *reinterpret_cast<double2*>(rhs_f[fld] + o) = nr; }
             else vf = ld2(rhs_f[fld] + o);

@@ -26,7 +26,12 @@ class StepParams(C.Structure):
                 ("sgs_model", C.c_int), ("ifilter", C.c_int),
                 ("Co", C.c_double), ("wall_damp_exp", C.c_double), ("vonk", C.c_double), ("zo", C.c_double),
                 ("lasd_cs_init", C.c_int), ("lasd_update", C.c_int), ("lasd_init_F", C.c_int),
-                ("lagran_dt", C.c_double)]
+                ("lagran_dt", C.c_double), ("turbines", C.c_int), ("turbines_eps", C.c_double)]
+
+
+class TurbineStruct(C.Structure):
+    _fields_ = [("num_nodes", C.c_int), ("nodes", C.c_void_p), ("ind", C.c_void_p), ("nhat", C.c_double * 3),
+                ("Ct_prime", C.c_double), ("dia", C.c_double), ("M", C.c_double), ("u_d_T", C.c_double)]
 
 
 # every symbol include/lesgo_gpu.h declares: name -> (restype, argtypes)
@@ -61,6 +66,8 @@ SYMBOLS = {
     "lesgo_gpu_step": (C.c_int, [_P, C.POINTER(StepParams)]),
     "lesgo_gpu_max_cfl": (C.c_int, [_P, C.c_double, C.POINTER(C.c_double)]),
     "lesgo_gpu_rmsdiv": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "lesgo_gpu_turbines_init": (C.c_int, [_P, C.c_int, C.POINTER(TurbineStruct), C.c_int]),
+    "lesgo_gpu_turbines_forcing": (C.c_int, [_P, C.c_double, _D, _D, _D]),
     "lesgo_gpu_comm_unique_id": (C.c_int, [_P]),
     "lesgo_gpu_comm_init": (C.c_int, [_P, _P]),
     "lesgo_gpu_sync_real_array": (C.c_int, [_P, _D, C.c_int]),

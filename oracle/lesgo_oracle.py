@@ -1156,6 +1156,137 @@ def lagrange_Sdep(s, sp: Spectral, comm, G_test, G_test_test, lagran_dt, init_F=
 
 
 # ----------------------------------------------------------------------------------
+# Actuator disks: turbines.f90 (turbines_nodes :275-462, turbines_forcing :465-638),
+# functions.f90:51-141 (interp_to_uv_grid, interp_to_w_grid); use_rotation = .false. (:76)
+# ----------------------------------------------------------------------------------
+@dataclass
+class Turbine:
+    xloc: float
+    yloc: float
+    height: float
+    dia: float
+    thk: float
+    theta1: float = 0.0
+    theta2: float = 0.0
+    Ct_prime: float = 1.33
+    u_d_T: float = -8.0          # running average of the disk velocity (turbines.f90:655-676)
+    M: float = 0.9               # turb_ind_func%M of the ADM correction (:579-582)
+    nhat: tuple = (0.0, 0.0, 0.0)
+    nodes: np.ndarray = None     # (num_nodes, 3) 1-based i, j and LOCAL k
+    ind: np.ndarray = None
+    u_d: float = 0.0
+    f_n: float = 0.0
+
+
+def standin_indicator(dia, thk, delta1, delta2):
+    """Test stand-in for turb_ind_func%val (turbine_indicator.f90:41-63).  The reference convolves a
+    disk with a Gaussian on a 2048**2 grid at start-up (:66-169, host-side initialisation, out of scope);
+    the parity tests only need SOME smooth (r_disk, r_norm) -> weight map that both sides share, so this
+    keeps the reference's normal-direction factor R2 (erf pair) and uses an erf edge in the disk plane."""
+    from math import erf, sqrt
+    ell = 0.5 * dia
+    d1, d2, th = delta1 / ell, delta2 / ell, thk / ell
+    c = sqrt(6.0) / d1
+
+    def val(r_disk, r_norm):
+        r, x = r_disk / ell, r_norm / ell
+        R1 = 0.5 * (1.0 - erf(sqrt(6.0) / d2 * (r - 1.0))) / math.pi
+        R2 = 0.5 / th * (erf(c * (x + 0.5 * th)) - erf(c * (x - 0.5 * th)))
+        return R1 * R2 / ell ** 3
+    return val
+
+
+def turbines_nodes(p: Params, farm, val, comm, alpha=1.5, filter_cutoff=1e-2):
+    """turbines.f90:275-462: node list and normalised indicator weights of every disk on this rank."""
+    nx, ny, nz = p.nx, p.ny, p.nz
+    dx, dy, dz = p.dx, p.dy, p.dz
+    k_start, k_end = 1 + p.coord * (nz - 1), (nz - 1) * (p.coord + 1)     # :246-247
+    sumA = np.zeros(len(farm))
+    for s, t in enumerate(farm):
+        search_rad = 0.5 * t.dia + 3 * alpha * math.sqrt(dx ** 2 + dy ** 2 + dz ** 2)
+        imax = min(int(search_rad / dx + 2), nx // 2)
+        jmax = min(int(search_rad / dy + 2), ny // 2)
+        n1 = -math.cos(math.pi * t.theta1 / 180.0) * math.cos(math.pi * t.theta2 / 180.0)
+        n2 = -math.sin(math.pi * t.theta1 / 180.0) * math.cos(math.pi * t.theta2 / 180.0)
+        n3 = math.sin(math.pi * t.theta2 / 180.0)
+        t.nhat = (n1, n2, n3)
+        icp, jcp = int(round(t.xloc / dx)), int(round(t.yloc / dy))
+        filt_max = val(0.0, 0.0)
+        nodes, ind = [], []
+        for k in range(k_start, k_end + 1):
+            for j in range(jcp - jmax + 1, jcp + jmax + 1):
+                for i in range(icp - imax + 1, icp + imax + 1):
+                    i2 = (i + nx - 1) % nx + 1
+                    j2 = (j + ny - 1) % ny + 1
+                    rx = (i - 1) * dx - t.xloc          # x(i2) -/+ L_x folded back = (i - 1) dx
+                    ry = (j - 1) * dy - t.yloc
+                    rz = (k - 0.5) * dz - t.height
+                    r = math.sqrt(rx * rx + ry * ry + rz * rz)
+                    r_norm = abs(rx * n1 + ry * n2 + rz * n3)
+                    r_disk = math.sqrt(max(r * r - r_norm * r_norm, 0.0))
+                    filt = val(r_disk, r_norm)
+                    if filt > filter_cutoff * filt_max:
+                        nodes.append((i2, j2, k - p.coord * (nz - 1)))
+                        ind.append(filt)
+                        sumA[s] += filt * dx * dy * dz
+        t.nodes = np.array(nodes, dtype=np.int32).reshape(-1, 3)
+        t.ind = np.array(ind, dtype=np.float64)
+    for s, t in enumerate(farm):
+        tot = comm.allreduce(float(sumA[s]), "sum")
+        t.ind = t.ind / tot                                            # :452-455
+
+
+def interp_to_uv_grid(var, p: Params, comm):
+    """functions.f90:51-94 (MPI build, lbz = 0)."""
+    nz = p.nz
+    out = np.zeros_like(var)
+    out[1:nz] = 0.5 * (var[2:nz + 1] + var[1:nz])
+    if p.coord == p.nproc - 1:
+        out[nz] = out[nz - 1]
+    mpi_sync_real_array(out, p, comm, down=True, up=True)
+    return out
+
+
+def interp_to_w_grid(var, p: Params, comm):
+    """functions.f90:97-141 (MPI build, lbz = 0)."""
+    nz = p.nz
+    out = np.zeros_like(var)
+    out[1:nz + 1] = 0.5 * (var[0:nz] + var[1:nz + 1])
+    mpi_sync_real_array(out, p, comm, down=True, up=True)
+    return out
+
+
+def turbines_forcing(s, p: Params, comm, farm, eps, adm_correction=False):
+    """turbines.f90:465-638 (+ forcing.f90:102-106): returns fxa, fya, fza; updates u_d, u_d_T, f_n."""
+    nz = p.nz
+    fxa = np.zeros_like(s.u); fya = np.zeros_like(s.u); fza = np.zeros_like(s.u)
+    mpi_sync_real_array(s.w, p, comm, down=True, up=True)              # :499
+    w_uv = interp_to_uv_grid(s.w, p, comm)                             # :502
+    vol = p.dx * p.dy * p.dz
+    for t in farm:
+        acc = 0.0
+        for l in range(len(t.ind)):                                    # :527-536
+            i2, j2, k2 = t.nodes[l]
+            acc = acc + vol * t.ind[l] * (t.nhat[0] * s.u[k2, j2 - 1, i2 - 1] + t.nhat[1] * s.v[k2, j2 - 1, i2 - 1]
+                                          + t.nhat[2] * w_uv[k2, j2 - 1, i2 - 1])
+        t.u_d = comm.allreduce(acc, "sum")                             # :553-554
+    for t in farm:
+        if adm_correction:                                             # :579-582
+            t.u_d = t.u_d / (1 + 0.25 * (1 - t.M) * t.Ct_prime)
+        t.u_d_T = (1.0 - eps) * t.u_d_T + eps * t.u_d                  # :583
+        t.f_n = -0.5 * t.Ct_prime * abs(t.u_d_T) * t.u_d_T * 0.25 * math.pi * t.dia ** 2    # :588
+        for l in range(len(t.ind)):                                    # :599-606
+            i2, j2, k2 = t.nodes[l]
+            fxa[k2, j2 - 1, i2 - 1] = t.f_n * t.nhat[0] * t.ind[l]
+            fya[k2, j2 - 1, i2 - 1] = t.f_n * t.nhat[1] * t.ind[l]
+            fza[k2, j2 - 1, i2 - 1] = t.f_n * t.nhat[2] * t.ind[l]
+    for f in (fxa, fya, fza):                                          # :620-622
+        mpi_sync_real_array(f, p, comm, down=True, up=True)
+    fza = interp_to_w_grid(fza, p, comm)                               # :623
+    return fxa, fya, fza
+
+
+# ----------------------------------------------------------------------------------
 # divstress_uv.f90 / divstress_w.f90
 # ----------------------------------------------------------------------------------
 def divstress_uv(s, sp: Spectral):
@@ -1274,7 +1405,7 @@ class State:
         return o
 
 
-def step(s: State, sp: Spectral, comm, mode="full", first_step=False, G_test=None, lasd=None):
+def step(s: State, sp: Spectral, comm, mode="full", first_step=False, G_test=None, lasd=None, turbines=None):
     """One timestep, main.f90:130-344.
 
     mode = "core": the scope-table (a)-(e) path only -- derivatives, convec, AB2,
@@ -1315,6 +1446,13 @@ def step(s: State, sp: Spectral, comm, mode="full", first_step=False, G_test=Non
     if p.use_mean_p_force:
         s.RHSx[1:nz] = s.RHSx[1:nz] + p.mean_p_force_x
         s.RHSy[1:nz] = s.RHSy[1:nz] + p.mean_p_force_y
+    # :254-266 forcing_applied (actuator disks) -> RHS
+    if turbines is not None:
+        s.fxa, s.fya, s.fza = turbines_forcing(s, p, comm, turbines["farm"], turbines["eps"],
+                                               adm_correction=turbines.get("adm_correction", False))
+        s.RHSx[1:nz] = s.RHSx[1:nz] + s.fxa[1:nz]
+        s.RHSy[1:nz] = s.RHSy[1:nz] + s.fya[1:nz]
+        s.RHSz[1:nz] = s.RHSz[1:nz] + s.fza[1:nz]
     # :273-280
     if first_step:
         s.RHSx_f[...] = s.RHSx; s.RHSy_f[...] = s.RHSy; s.RHSz_f[...] = s.RHSz

@@ -235,7 +235,82 @@ def check_lasd_steps(core, p, nsteps=4, tol=1e-11, seed=61, amp=0.5):
 CS_TOL = 1e-9
 
 
-def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core", lasd=False):
+def make_farm(p, comm=None, tilt=True):
+    """Two actuator disks (one yawed and tilted, so all three force components are exercised) on the
+    grid of p, with the node lists turbines_nodes (turbines.f90:275-462) builds."""
+    comm = comm or O.LocalComm()
+    dia = 0.3 * p.L_y
+    h = 0.45 * p.L_z
+    dlt = 1.5 * np.sqrt(p.dx ** 2 + p.dy ** 2 + p.dz ** 2)
+    farm = [O.Turbine(xloc=0.25 * p.L_x, yloc=0.3 * p.L_y, height=h, dia=dia, thk=1.2 * p.dx, theta1=0.0, theta2=0.0,
+                      Ct_prime=1.33, u_d_T=-0.7),
+            O.Turbine(xloc=0.97 * p.L_x, yloc=0.8 * p.L_y, height=0.9 * h, dia=0.8 * dia, thk=1.2 * p.dx,
+                      theta1=20.0 if tilt else 0.0, theta2=10.0 if tilt else 0.0, Ct_prime=1.0, u_d_T=-0.5)]
+    for t in farm:
+        val = O.standin_indicator(t.dia, t.thk, dlt, dlt)
+        O.turbines_nodes(p, [t], val, comm)
+    return farm
+
+
+def check_turbines(core, p, nsteps=2, tol=1e-12, mode="core", eps=0.3, adm_correction=True):
+    """turbines_forcing standalone (force fields, per-disk scalars) and inside lesgo_gpu_step."""
+    sp = O.Spectral(p)
+    nx, nz = p.nx, p.nz
+    G = O.test_filter_kernel(sp)
+    s = initial_state(p, seed=71)
+    s.u += 1.0
+    farm = make_farm(p)
+    assert all(len(t.ind) > 10 for t in farm)
+    for n in ("u", "v", "w"):
+        core.upload(n, getattr(s, n))
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+        core.upload(n, np.zeros(core.dims.shape))
+    core.turbines_init(farm, adm_correction=adm_correction)
+    out = {}
+    # standalone call; the oracle copy keeps the running averages of the two sides in step
+    import copy
+    farm0 = copy.deepcopy(farm)
+    fx, fy, fz = O.turbines_forcing(s, p, O.LocalComm(), farm0, eps, adm_correction=adm_correction)
+    u_d, u_d_T, f_n = core.turbines_forcing(eps)
+    out["u_d"] = rel(u_d, [t.u_d for t in farm0]); out["u_d_T"] = rel(u_d_T, [t.u_d_T for t in farm0])
+    out["f_n"] = rel(f_n, [t.f_n for t in farm0])
+    for n, r in (("fxa", fx), ("fya", fy), ("fza", fz)):
+        g = core.download(n)
+        assert np.count_nonzero(r[1:nz, :, :nx]) > 0, n
+        out[n] = rel(g[1:nz, :, :nx], r[1:nz, :, :nx])
+    core.turbines_init(farm, adm_correction=adm_correction)      # reset the running averages
+    for it in range(nsteps):
+        O.step(s, sp, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=G,
+               turbines=dict(farm=farm, eps=eps, adm_correction=adm_correction))
+        core.step(**step_kwargs_pre_dyn(p, it, mode), turbines=True, turbines_eps=eps)
+    for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz"):
+        g = core.download(n)
+        r = getattr(s, n)
+        hi = nz + 1 if n in ("w", "RHSz", "p") else nz
+        out["step_" + n] = rel(g[1:hi, :, :nx], r[1:hi, :, :nx])
+    for k, v in out.items():
+        assert v <= tol, (k, v, out)
+    return out
+
+
+def farm_for_rank(farm, p):
+    """The slab of rank p.coord of a single-slab farm: nodes with global k in the rank's 1..nz-1 (turbines.f90:246-247,
+    425), same normalised weights."""
+    import copy
+    lo, hi = 1 + p.coord * (p.nz - 1), (p.nz - 1) * (p.coord + 1)
+    out = []
+    for t in farm:
+        c = copy.copy(t)
+        m = (t.nodes[:, 2] >= lo) & (t.nodes[:, 2] <= hi)
+        c.nodes = t.nodes[m].copy()
+        c.nodes[:, 2] -= p.coord * (p.nz - 1)
+        c.ind = t.ind[m].copy()
+        out.append(c)
+    return out
+
+
+def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core", lasd=False,
+                          turbines=False):
     """nproc ranks (threads of this process, one Core each) advance `nsteps` core steps;
     the gathered result must match the SINGLE-slab oracle (which the multi-slab oracle
     equals, tests/test_oracle_kat.py)."""
@@ -248,13 +323,17 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
     Gg = O.test_filter_kernel(spg)
     G2g = O.test_filter_kernel(spg, alpha=4.0)
     names = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz") + (("Cs_opt2", "F_LM", "F_NN") if lasd else ())
+    farm_g = make_farm(pg) if turbines else None
+    farm_ref = [__import__("copy").copy(t) for t in farm_g] if turbines else None
+    tkw = dict(turbines=True, turbines_eps=0.3) if turbines else {}
     for it in range(nsteps):
         ld_ = None
         if lasd:
             sch = lasd_schedule(pg, it)
             ld_ = dict(sp=spg, G_test=Gg, G_test_test=G2g, lagran_dt=sch["lagran_dt"], cs_init=sch["lasd_cs_init"],
                        update=sch["lasd_update"], init_F=sch["lasd_init_F"])
-        O.step(sref, spg, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=Gg, lasd=ld_)
+        O.step(sref, spg, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=Gg, lasd=ld_,
+               turbines=dict(farm=farm_ref, eps=0.3) if turbines else None)
     ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
     cores = [lesgo_b200.Core(make_dims(p, device=(device_of(p.coord) if device_of else -1)), lib=lib) for p in ps]
     ident = cores[0].comm_unique_id()
@@ -268,9 +347,13 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
                 c.upload(n, O.scatter_slab(g, p))
             for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz") + (("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2") if lasd else ()):
                 c.upload(n, np.zeros(c.dims.shape))
+            if turbines:
+                c.turbines_init(farm_for_rank(farm_g, p))
             for it in range(nsteps):
-                c.step(**step_kwargs(p, it, mode), **(lasd_schedule(p, it) if lasd else {}))
+                c.step(**step_kwargs(p, it, mode), **(lasd_schedule(p, it) if lasd else {}), **tkw)
             res[r] = {n: c.download(n) for n in names}
+            if turbines:
+                res[r]["u_d_T"] = c.turbines_forcing(0.3)[1]
             # mpi_sync_real_array (mpi_defs.f90:245-262) on a host array
             var = np.zeros(c.dims.shape)
             for k in range(p.nz + 1):
@@ -301,6 +384,11 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
         g = O.gather_slabs([res[r][n] for r in range(nproc)], ps, top_extra=top)
         hi = nzt if top else nzt - 1
         out[n] = rel(g[1:hi + 1, :, :pg.nx], getattr(sref, n)[1:hi + 1, :, :pg.nx])
+    if turbines:
+        # one more forcing call on both sides: every rank must hold the same (global) disk velocities
+        O.turbines_forcing(sref, pg, O.LocalComm(), farm_ref, 0.3)
+        for r in range(nproc):
+            out[f"u_d_T_rank{r}"] = rel(res[r]["u_d_T"], [t.u_d_T for t in farm_ref])
     cfl_ref = O.get_max_cfl(sref, pg, O.LocalComm())
     assert all(abs(res[r]["cfl"] - cfl_ref) <= 1e-12 * cfl_ref for r in range(nproc)), (cfl_ref, [res[r]["cfl"] for r in range(nproc)])
     for k, v in out.items():

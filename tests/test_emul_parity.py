@@ -105,6 +105,41 @@ def test_emul_multirank_lasd(nproc):
     print(out)
 
 
+@pytest.mark.parametrize("cfg,mode", [
+    (dict(nx=32, ny=32, Nz=12, lbc_mom=1, ubc_mom=1), "core"),
+    (dict(nx=32, ny=16, Nz=12, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False), "full"),
+])
+def test_emul_turbines(cfg, mode):
+    """Rows (f)-3: actuator-disk forcing (turbines.f90:465-638) standalone and inside the step."""
+    from helpers import check_turbines
+    p = O.Params(**cfg)
+    out = check_turbines(core_for(p), p, mode=mode, tol=1e-11)
+    print(out)
+
+
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_emul_multirank_turbines(nproc):
+    """Disks spanning several z slabs: per-rank node lists, all-reduced disk velocities, force halos."""
+    from helpers import check_multirank_steps
+    kw = dict(nx=32, ny=16, Nz=12, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False)
+    out = check_multirank_steps(emul_library(), kw, nproc, nsteps=2, mode="full", turbines=True)
+    print(out)
+
+
+def test_emul_turbines_errors():
+    p = O.Params(nx=16, ny=16, Nz=6)
+    c = core_for(p)
+    for n in ("u", "v", "w", "RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+        c.upload(n, np.zeros(c.dims.shape))
+    with pytest.raises(lesgo_b200.LibraryError, match="turbines_init"):
+        c.step(dt=1e-3, turbines=True)
+    bad = O.Turbine(xloc=1.0, yloc=1.0, height=0.5, dia=0.5, thk=0.1)
+    bad.nodes = np.array([[1, 1, p.nz]], dtype=np.int32)      # k = nz is not a node a rank owns
+    bad.ind = np.array([1.0])
+    with pytest.raises(lesgo_b200.LibraryError, match="node outside"):
+        c.turbines_init([bad])
+
+
 @pytest.mark.parametrize("Nz,mode", [(2, "core"), (2, "full"), (3, "full")])
 def test_emul_minimal_slab(Nz, mode):
     """Smallest slabs: bottom and top special planes adjacent (nz = 3 or 4)."""

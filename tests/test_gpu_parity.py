@@ -149,6 +149,18 @@ def test_lasd_les_channel(cfg, nsteps, tol):
     print(out)
 
 
+@pytest.mark.parametrize("cfg,mode", [
+    (dict(nx=64, ny=64, Nz=32, lbc_mom=1, ubc_mom=1), "core"),
+    (dict(nx=128, ny=64, Nz=32, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False), "full"),
+])
+def test_turbines(cfg, mode):
+    """Rows (f)-3: actuator-disk forcing (turbines.f90:465-638): force fields, disk scalars, two steps."""
+    from helpers import check_turbines
+    p = O.Params(**cfg)
+    out = check_turbines(core_for(p), p, mode=mode, tol=1e-12)
+    print(out)
+
+
 def test_misc_entry_points():
     from helpers import check_misc
     p = O.Params(nx=64, ny=32, Nz=12, L_x=3.0)

@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", default="512,512,256", help="nx,ny,Nz (lesgo.conf Nz)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the LASD and actuator-disk timings (rows (f)-2, (f)-3)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
     return ap.parse_args()
@@ -56,6 +57,41 @@ def hbm_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class _Disk:
+    pass
+
+
+def synthetic_farm(dims, rows=4, cols=6):
+    """rows x cols actuator disks (diameter 0.1 L_y... as in test-cases/turbines_ADM: hub height 0.1 L_z-ish,
+    unit normal -x) with smooth indicator weights normalised to unit volume integral: the node lists
+    turbines_nodes (turbines.f90:275-462) would hand to lesgo_gpu_turbines_init, for this rank's slab."""
+    nx, ny, nz = dims.nx, dims.ny, dims.nz
+    dx, dy, dz = dims.L_x / nx, dims.L_y / ny, dims.dz
+    dia = 0.1 * dims.L_y
+    height = 0.25 * dims.L_z
+    thk = max(1.5 * dx, 0.1 * dia)
+    base = dims.coord * (nz - 1)
+    farm = []
+    for r in range(rows):
+        for c_ in range(cols):
+            xl, yl = (c_ + 0.5) * dims.L_x / cols, (r + 0.5) * dims.L_y / rows
+            ic, jc, kc = int(round(xl / dx)), int(round(yl / dy)), int(round(height / dz + 0.5))
+            hi_, hj, hk = int(thk / dx) + 2, int(0.6 * dia / dy) + 2, int(0.6 * dia / dz) + 2
+            ii, jj, kk = np.meshgrid(np.arange(ic - hi_, ic + hi_ + 1), np.arange(jc - hj, jc + hj + 1),
+                                     np.arange(max(kc - hk, 1), min(kc + hk, dims.nz_tot - 1) + 1), indexing="ij")
+            rx, ry, rz = (ii - 1) * dx - xl, (jj - 1) * dy - yl, (kk - 0.5) * dz - height
+            wgt = np.exp(-(np.sqrt(ry ** 2 + rz ** 2) / (0.5 * dia)) ** 8) * np.exp(-(rx / (0.5 * thk)) ** 4)
+            keep = wgt > 1e-2
+            wsum = float(wgt[keep].sum() * dx * dy * dz)
+            mine = keep & (kk >= base + 1) & (kk <= base + nz - 1)
+            t = _Disk()
+            t.nodes = np.stack([(ii[mine] - 1) % nx + 1, (jj[mine] - 1) % ny + 1, kk[mine] - base], axis=1).astype(np.int32)
+            t.ind = (wgt[mine] / wsum).astype(np.float64)
+            t.nhat, t.Ct_prime, t.dia, t.M, t.u_d_T = (-1.0, 0.0, 0.0), 1.33, dia, 0.9, -1.0
+            farm.append(t)
+    return farm
 
 
 def synthetic_slab(dims, seed=20240607):
@@ -311,6 +347,53 @@ def main():
     except Exception as e:  # noqa
         full = {"error": str(e)}
 
+    # rows (f)-2 and (f)-3 of SURVEY section 8, timed the same way on the same grid: the Lagrangian
+    # scale-dependent model (one lagrange_Sdep per timed step; the reference runs it every cs_count = 5
+    # steps) and a 4 x 6 array of actuator disks
+    def timed_steps(kw, n):
+        for _ in range(2):
+            core.step(**kw)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n):
+            core.step(**kw)
+        b.record(stream)
+        barrier()
+        t_ms = a.elapsed_time(b) / n
+        if dist is not None:
+            tt = torch.tensor([t_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ms = float(tt.item())
+        return t_ms
+
+    lasd = None
+    if not args.no_extras:
+        try:
+            lkw = dict(step_kw, mode=1, sgs_model=5, nu=1e-4, lagran_dt=5 * dt)
+            core.step(lasd_cs_init=True, **lkw)
+            core.step(lasd_update=True, lasd_init_F=True, **lkw)
+            base_ms = timed_steps(lkw, 3)
+            upd_ms = timed_steps(dict(lkw, lasd_update=True), 3)
+            lasd = {"ms_per_step_with_update": upd_ms, "ms_per_step_without": base_ms,
+                    "ms_per_step_cs_count_5": base_ms + (upd_ms - base_ms) / 5.0,
+                    "value_cs_count_5": points / ((base_ms + (upd_ms - base_ms) / 5.0) * 1e-3) / 1e6, "unit": "Mpts/s",
+                    "what": "full step with sgs_model 5: + interpolag_Sdep + 42 test filters per plane + running averages"}
+        except Exception as e:  # noqa
+            lasd = {"error": str(e)}
+    turb = None
+    if not args.no_extras:
+        try:
+            farm = synthetic_farm(dims)
+            core.turbines_init(farm)
+            tkw = dict(step_kw, mode=1, sgs_model=1, nu=1e-4)
+            t_ms = timed_steps(dict(tkw, turbines=True, turbines_eps=0.1), 3)
+            turb = {"ms_per_step": t_ms, "value": points / (t_ms * 1e-3) / 1e6, "unit": "Mpts/s", "disks": len(farm),
+                    "nodes_this_rank": int(sum(len(t.ind) for t in farm)),
+                    "what": "full step (Smagorinsky) + turbines_forcing: gather, all-reduce, scatter, RHS += f"}
+        except Exception as e:  # noqa
+            turb = {"error": str(e)}
+
     e2e = None
     if rank == 0 and not args.no_e2e and world == 1:
         e2e = run_e2e(core, dims, u, v, w, dt, tadv1, args.e2e_steps, points)
@@ -327,7 +410,7 @@ def main():
                            "grid": [nx, ny, Nz], "decomposition": f"z-slabs x{world}",
                            "l2": "inputs larger than L2 (%.0f MB per field)" % (np.prod(dims.shape) * 8 / 1e6)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-                "clocks": clocks, "kernels": kernels, "max_cfl": cfl, "full_step": full}
+                "clocks": clocks, "kernels": kernels, "max_cfl": cfl, "full_step": full, "lasd_step": lasd, "turbines_step": turb}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -155,6 +155,15 @@ int lesgo_gpu_step(lesgo_gpu_ctx* ctx, const lesgo_gpu_step_params* sp);
 int lesgo_gpu_max_cfl(lesgo_gpu_ctx* ctx, double dt, double* cfl);
 int lesgo_gpu_rmsdiv(lesgo_gpu_ctx* ctx, double* rms);
 
+/* ---- restart file (io.f90:1173-1211 checkpoint, initial.f90:226-239 ic_file) ----------------------------
+ * `fname` is this rank's file (the reference's checkpoint_file // '.c' // coord, e.g. "vel.out.c0"): one
+ * Fortran sequential unformatted record with planes 1:nz of u, v, w, RHSx, RHSy, RHSz, Cs_opt2, F_LM, F_MM,
+ * F_QN, F_NN (the model fields are zero when no dynamic model ran), native byte order, gfortran subrecords
+ * above 2 GiB.  Written from / read into the resident fields; ghost planes are not part of the file, so
+ * call lesgo_gpu_sync_real_array on u, v, w (device pointers) after a read when nproc > 1. */
+int lesgo_gpu_checkpoint_write(lesgo_gpu_ctx* ctx, const char* fname);
+int lesgo_gpu_checkpoint_read(lesgo_gpu_ctx* ctx, const char* fname);
+
 /* ---- actuator-disk turbines (turbines.f90) ---------------------------------------------------------
  * The host keeps turbines_init / turbines_nodes (turbines.f90:129-462: input files, the filtered indicator
  * function of turbine_indicator.f90, node search) and hands the result over; call again when the disks

@@ -258,6 +258,13 @@ class Core:
                         int(lasd_update), int(lasd_init_F), float(lagran_dt), int(turbines), float(turbines_eps))
         self._ck(self.lib.step(self._ctx, C.byref(sp)), "step")
 
+    # -- restart file (io.f90:1173-1211, initial.f90:226-239) ------------------------------------------
+    def checkpoint_write(self, fname):
+        self._ck(self.lib.checkpoint_write(self._ctx, str(fname).encode()), "checkpoint_write")
+
+    def checkpoint_read(self, fname):
+        self._ck(self.lib.checkpoint_read(self._ctx, str(fname).encode()), "checkpoint_read")
+
     # -- actuator disks (turbines.f90) --------------------------------------------------------------
     def turbines_init(self, farm, adm_correction=False):
         """farm: objects with nodes (n, 3) int (1-based i, j, local k), ind (n), nhat, Ct_prime, dia, M, u_d_T --

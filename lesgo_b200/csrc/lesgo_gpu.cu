@@ -1790,6 +1790,101 @@ int lesgo_gpu_step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     return 0;
 }
 
+// ---- restart file of the resident state -------------------------------------------------
+// One Fortran sequential unformatted record (io.f90:1204-1211 / initial.f90:226-239) holding planes 1:nz of
+// u, v, w, RHSx, RHSy, RHSz, Cs_opt2, F_LM, F_MM, F_QN, F_NN, native byte order.  Records longer than
+// 2 GiB - 9 bytes use gfortran's subrecord convention: 4-byte signed byte counts before and after every
+// subrecord, the leading one negative when another subrecord follows, the trailing one negative when one
+// precedes (LESGO_SUBRECORD_MAX overrides the limit so tests can exercise it with small files).
+namespace {
+const int kCkptFields[11] = {LG_U, LG_V, LG_W, LG_RHSX, LG_RHSY, LG_RHSZ, LG_CS_OPT2, LG_F_LM, LG_F_MM, LG_F_QN, LG_F_NN};
+long long subrecord_max() {
+    const char* e = std::getenv("LESGO_SUBRECORD_MAX");
+    const long long v = e ? std::atoll(e) : 0;
+    return v > 0 ? v : 2147483639LL;
+}
+// streams `total` bytes of the record between the file and `io(ptr, n)`-sized pieces of payload
+struct RecordIO {
+    FILE* f; bool writing; long long total, done = 0, sub_left = 0, maxsub; bool first = true;
+    std::string err;
+    RecordIO(FILE* f_, bool w, long long tot) : f(f_), writing(w), total(tot), maxsub(subrecord_max()) {}
+    bool marker(int v, bool check_sign_only = false) {
+        if (writing) return std::fwrite(&v, 4, 1, f) == 1;
+        int r = 0;
+        if (std::fread(&r, 4, 1, f) != 1) { err = "unexpected end of file"; return false; }
+        if (r != v) { err = "record length " + std::to_string(r) + " where " + std::to_string(v) + " was expected (other grid or byte order?)"; return false; }
+        (void)check_sign_only;
+        return true;
+    }
+    bool open_sub() {
+        const long long left = total - done;
+        sub_left = left < maxsub ? left : maxsub;
+        cur = int(sub_left);
+        return marker(left > sub_left ? -cur : cur);
+    }
+    bool close_sub() { const bool ok = marker(first ? cur : -cur); first = false; return ok; }
+    int cur = 0;
+    bool xfer(char* p, long long n) {
+        while (n > 0) {
+            if (sub_left == 0 && !open_sub()) return false;
+            const long long m = n < sub_left ? n : sub_left;
+            const size_t got = writing ? std::fwrite(p, 1, size_t(m), f) : std::fread(p, 1, size_t(m), f);
+            if (got != size_t(m)) { err = writing ? "write failed" : "unexpected end of file"; return false; }
+            p += m; n -= m; done += m; sub_left -= m;
+            if (sub_left == 0 && !close_sub()) return false;
+        }
+        return true;
+    }
+};
+int checkpoint_io(lesgo_gpu_ctx* c, const char* fname, bool writing) {
+    if (!fname) return c->fail("checkpoint: no file name");
+    FILE* f = std::fopen(fname, writing ? "wb" : "rb");
+    if (!f) return c->fail(std::string("checkpoint: cannot open ") + fname);
+    const long long per_field = (long long)c->plane * c->nz * sizeof(double);
+    RecordIO rec(f, writing, 11 * per_field);
+    const size_t chunk_planes = 8;
+    const size_t chunk = size_t(c->plane) * chunk_planes;
+    double* host = nullptr;
+    if (cudaMallocHost(reinterpret_cast<void**>(&host), chunk * sizeof(double)) != cudaSuccess) { std::fclose(f); return c->fail("checkpoint: pinned buffer"); }
+    int rc = 0;
+    for (int q = 0; q < 11 && !rc; ++q) {
+        double* d = field(c, kCkptFields[q]);
+        if (!d) { rc = 1; break; }
+        for (size_t k = 1; k <= size_t(c->nz) && !rc; k += chunk_planes) {
+            const size_t np = (k + chunk_planes <= size_t(c->nz) + 1) ? chunk_planes : size_t(c->nz) + 1 - k;
+            const size_t nb = np * size_t(c->plane) * sizeof(double);
+            double* dp = d + size_t(c->plane) * k;
+            if (writing) {
+                if (cudaMemcpyAsync(host, dp, nb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = c->fail("checkpoint: device read failed"); break; }
+                if (!rec.xfer(reinterpret_cast<char*>(host), (long long)nb)) rc = c->fail("checkpoint " + std::string(fname) + ": " + rec.err);
+            } else {
+                if (!rec.xfer(reinterpret_cast<char*>(host), (long long)nb)) { rc = c->fail("checkpoint " + std::string(fname) + ": " + rec.err); break; }
+                if (cudaMemcpyAsync(dp, host, nb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) rc = c->fail("checkpoint: device write failed");
+            }
+        }
+    }
+    if (!rc && !writing) {
+        char extra;
+        if (std::fread(&extra, 1, 1, f) == 1) rc = c->fail("checkpoint " + std::string(fname) + ": trailing data after the record (other grid?)");
+    }
+    cudaFreeHost(host);
+    if (std::fclose(f) != 0 && !rc) rc = c->fail("checkpoint: close failed");
+    return rc;
+}
+}  // namespace
+
+int lesgo_gpu_checkpoint_write(lesgo_gpu_ctx* c, const char* fname) {
+    ENTER(c);
+    if (!c) return 1;
+    return checkpoint_io(c, fname, true);
+}
+
+int lesgo_gpu_checkpoint_read(lesgo_gpu_ctx* c, const char* fname) {
+    ENTER(c);
+    if (!c) return 1;
+    return checkpoint_io(c, fname, false);
+}
+
 int lesgo_gpu_turbines_init(lesgo_gpu_ctx* c, int nloc, const lesgo_gpu_turbine* t, int adm_correction) {
     ENTER(c);
     if (!c) return 1;

@@ -1481,6 +1481,35 @@ def step(s: State, sp: Spectral, comm, mode="full", first_step=False, G_test=Non
 
 
 # ----------------------------------------------------------------------------------
+# Restart file: io.f90:1204-1211 (checkpoint), initial.f90:226-239 (ic_file)
+# ----------------------------------------------------------------------------------
+CHECKPOINT_FIELDS = ("u", "v", "w", "RHSx", "RHSy", "RHSz", "Cs_opt2", "F_LM", "F_MM", "F_QN", "F_NN")
+
+
+def checkpoint_write(s, p: Params, fname):
+    """One sequential unformatted record (4-byte length markers, native byte order) with planes 1:nz of
+    the eleven arrays; valid for records below gfortran's 2 GiB subrecord limit."""
+    lasd_alloc(s)
+    nz = p.nz
+    payload = b"".join(np.ascontiguousarray(getattr(s, n)[1:nz + 1]).tobytes() for n in CHECKPOINT_FIELDS)
+    assert len(payload) < 2147483639
+    m = np.int32(len(payload)).tobytes()
+    with open(fname, "wb") as f:
+        f.write(m + payload + m)
+
+
+def checkpoint_read(s, p: Params, fname):
+    lasd_alloc(s)
+    n = p.nz * p.ny * p.ld
+    raw = np.fromfile(fname, dtype=np.uint8)
+    m0 = int(raw[:4].view(np.int32)[0]); m1 = int(raw[-4:].view(np.int32)[0])
+    assert m0 == m1 == 11 * n * 8 == raw.size - 8, (m0, m1, raw.size)
+    data = raw[4:-4].view(np.float64).reshape(11, p.nz, p.ny, p.ld)
+    for i, name in enumerate(CHECKPOINT_FIELDS):
+        getattr(s, name)[1:p.nz + 1] = data[i]
+
+
+# ----------------------------------------------------------------------------------
 # Synthetic channel fields (SURVEY 8(d)); global -> per-rank slabs with ghost planes
 # ----------------------------------------------------------------------------------
 def synthetic_global(nx, ny, Nz, nproc=1, seed=20240607, amp=0.5, L_x=2 * math.pi,

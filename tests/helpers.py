@@ -396,6 +396,59 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
     return out
 
 
+def check_checkpoint(make_core, p, tmp_path, monkeypatch):
+    """Restart file: device -> file -> oracle reader and scipy's independent Fortran-record reader; oracle writer ->
+    device; gfortran subrecords (forced small) round trip; wrong-grid files are refused."""
+    import scipy.io
+    s = O.State(p)
+    O.lasd_alloc(s)
+    for i, n in enumerate(O.CHECKPOINT_FIELDS):
+        getattr(s, n)[...] = random_field(p, 300 + i)
+    core = make_core()
+    for n in O.CHECKPOINT_FIELDS:
+        core.upload(n, getattr(s, n))
+    f1 = str(tmp_path / "vel.out.c0")
+    core.checkpoint_write(f1)
+    s2 = O.State(p)
+    O.checkpoint_read(s2, p, f1)
+    for n in O.CHECKPOINT_FIELDS:
+        assert np.array_equal(getattr(s2, n)[1:], getattr(s, n)[1:]), n
+    rec = scipy.io.FortranFile(f1, "r").read_reals(np.float64)
+    assert np.array_equal(rec.reshape(11, p.nz, p.ny, p.ld)[3], s.RHSx[1:])
+    # oracle-written file -> device
+    f2 = str(tmp_path / "vel.in.c0")
+    O.checkpoint_write(s, p, f2)
+    assert open(f1, "rb").read() == open(f2, "rb").read()
+    core2 = make_core()
+    core2.checkpoint_read(f2)
+    for n in O.CHECKPOINT_FIELDS:
+        assert np.array_equal(core2.download(n)[1:], getattr(s, n)[1:]), n
+    # subrecords: limit of 1000 bytes -> many subrecords with signed markers
+    monkeypatch.setenv("LESGO_SUBRECORD_MAX", "1000")
+    f3 = str(tmp_path / "vel.sub.c0")
+    core.checkpoint_write(f3)
+    raw = np.fromfile(f3, dtype=np.uint8)
+    nsub = -(-(11 * p.nz * p.ny * p.ld * 8) // 1000)
+    assert raw.size == 11 * p.nz * p.ny * p.ld * 8 + 8 * nsub
+    assert raw[:4].view(np.int32)[0] == -1000 and raw[1004:1008].view(np.int32)[0] == 1000      # first: more follow / none before
+    assert raw[1008:1012].view(np.int32)[0] == -1000 and raw[2012:2016].view(np.int32)[0] == -1000
+    core3 = make_core()
+    core3.checkpoint_read(f3)
+    for n in O.CHECKPOINT_FIELDS:
+        assert np.array_equal(core3.download(n)[1:], getattr(s, n)[1:]), n
+    monkeypatch.delenv("LESGO_SUBRECORD_MAX")
+    with pytest_raises_library("record length"):
+        core3.checkpoint_read(f3)                               # written with other markers than expected now
+    with pytest_raises_library("cannot open"):
+        core3.checkpoint_read(str(tmp_path / "missing"))
+    return True
+
+
+def pytest_raises_library(match):
+    import pytest
+    return pytest.raises(lesgo_b200.LibraryError, match=match)
+
+
 def check_misc(core, p):
     """wavenumbers (fft.f90:130-160), tridag_array with caller-supplied coefficients
     (tridag_array.f90:166-246) and its zero-pivot error path."""

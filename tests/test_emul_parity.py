@@ -140,6 +140,12 @@ def test_emul_turbines_errors():
         c.turbines_init([bad])
 
 
+def test_emul_checkpoint(tmp_path, monkeypatch):
+    from helpers import check_checkpoint
+    p = O.Params(nx=16, ny=16, Nz=6)
+    check_checkpoint(lambda: core_for(p), p, tmp_path, monkeypatch)
+
+
 @pytest.mark.parametrize("Nz,mode", [(2, "core"), (2, "full"), (3, "full")])
 def test_emul_minimal_slab(Nz, mode):
     """Smallest slabs: bottom and top special planes adjacent (nz = 3 or 4)."""

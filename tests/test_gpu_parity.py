@@ -161,6 +161,13 @@ def test_turbines(cfg, mode):
     print(out)
 
 
+def test_checkpoint(tmp_path, monkeypatch):
+    """Rows (f)-4: restart file of the resident state (io.f90:1204-1211 / initial.f90:226-239)."""
+    from helpers import check_checkpoint
+    p = O.Params(nx=64, ny=32, Nz=12)
+    check_checkpoint(lambda: core_for(p), p, tmp_path, monkeypatch)
+
+
 def test_misc_entry_points():
     from helpers import check_misc
     p = O.Params(nx=64, ny=32, Nz=12, L_x=3.0)

@@ -164,6 +164,21 @@ int lesgo_gpu_rmsdiv(lesgo_gpu_ctx* ctx, double* rms);
 int lesgo_gpu_checkpoint_write(lesgo_gpu_ctx* ctx, const char* fname);
 int lesgo_gpu_checkpoint_read(lesgo_gpu_ctx* ctx, const char* fname);
 
+/* ---- running time averages (time_average.f90:176-320, tavg%compute) -------------------------------------
+ * Accumulates  acc += quantity * dt  for the 26 quantities of type tavg_t from the resident fields (u, v, w, p,
+ * the stresses, the derivatives of the last step, Cs_opt2, the disk forces when turbines are initialised),
+ * including the uv<->w grid interpolations and their ghost-plane exchanges.  tavg%finalize (division by
+ * total_time, Reynolds stresses, file output, :323-480) stays with the host, which fetches an accumulator as
+ * the (nx, ny, 0:nz) array tavg_t holds; total_time may be NULL. */
+enum lesgo_gpu_tavg {
+    LG_TA_U = 0, LG_TA_V, LG_TA_W, LG_TA_W_UV, LG_TA_U_W, LG_TA_V_W, LG_TA_U2, LG_TA_V2, LG_TA_W2, LG_TA_UV, LG_TA_UW,
+    LG_TA_VW, LG_TA_TXX, LG_TA_TYY, LG_TA_TZZ, LG_TA_TXY, LG_TA_TXZ, LG_TA_TYZ, LG_TA_P, LG_TA_FX, LG_TA_FY, LG_TA_FZ,
+    LG_TA_CS_OPT2, LG_TA_VORTX, LG_TA_VORTY, LG_TA_VORTZ, LG_TA_N
+};
+int lesgo_gpu_tavg_compute(lesgo_gpu_ctx* ctx, double dt);
+int lesgo_gpu_tavg_download(lesgo_gpu_ctx* ctx, int which, double* host, double* total_time);
+int lesgo_gpu_tavg_reset(lesgo_gpu_ctx* ctx);
+
 /* ---- actuator-disk turbines (turbines.f90) ---------------------------------------------------------
  * The host keeps turbines_init / turbines_nodes (turbines.f90:129-462: input files, the filtered indicator
  * function of turbine_indicator.f90, node search) and hands the result over; call again when the disks

@@ -33,6 +33,11 @@ FIELD_IDS = {n: i for i, n in enumerate(
      "F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2", "fxa", "fya", "fza"])}
 
 
+TAVG_IDS = {n: i for i, n in enumerate(
+    ["u", "v", "w", "w_uv", "u_w", "v_w", "u2", "v2", "w2", "uv", "uw", "vw", "txx", "tyy", "tzz", "txy", "txz", "tyz",
+     "p", "fx", "fy", "fz", "cs_opt2", "vortx", "vorty", "vortz"])}
+
+
 @dataclass
 class Dims:
     """Grid / decomposition parameters, named as in param.f90 / lesgo.conf."""
@@ -264,6 +269,21 @@ class Core:
 
     def checkpoint_read(self, fname):
         self._ck(self.lib.checkpoint_read(self._ctx, str(fname).encode()), "checkpoint_read")
+
+    # -- running time averages (time_average.f90:176-320) --------------------------------------------
+    def tavg_compute(self, dt):
+        self._ck(self.lib.tavg_compute(self._ctx, float(dt)), "tavg_compute")
+
+    def tavg_download(self, name):
+        """Accumulator `name` (TAVG_IDS) as the (0:nz, ny, nx) array of tavg_t, and the accumulated time."""
+        d = self.dims
+        out = np.zeros((d.nz + 1, d.ny, d.nx))
+        tt = C.c_double()
+        self._ck(self.lib.tavg_download(self._ctx, TAVG_IDS[name], out.ctypes.data, C.byref(tt)), "tavg_download")
+        return out, tt.value
+
+    def tavg_reset(self):
+        self._ck(self.lib.tavg_reset(self._ctx), "tavg_reset")
 
     # -- actuator disks (turbines.f90) --------------------------------------------------------------
     def turbines_init(self, farm, adm_correction=False):

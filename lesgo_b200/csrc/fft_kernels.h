@@ -283,7 +283,7 @@ k_xinv(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int nf
 // ---------------------------------------------------------------------------------
 // y pass
 // ---------------------------------------------------------------------------------
-enum YMode { Y_COPY = 0, Y_IKX = 1, Y_IKY = 2, Y_TABLE = 3 };
+enum YMode { Y_COPY = 0, Y_IKX = 1, Y_IKY = 2, Y_TABLE = 3, Y_TABLE2 = 4 };
 
 struct YOutSpec {
     double* dst;
@@ -310,6 +310,7 @@ struct YArgs {
     int k0, nplanes, nfields;
     double kxs, kys;     // 2 pi / L_x, 2 pi / L_y
     const double* table; // Y_TABLE multiplier, [ns][table_row] reals
+    const double* table2; // Y_TABLE2 multiplier (second test filter of the same spectrum), same layout
     int table_row;
     int zero_col;        // >= 0: also write zeros into this complex column of every output row
     int keep_nyq_row;    // 1: raw transform (do not zero ky = ns/2)
@@ -525,7 +526,8 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
                             double ky = a.kys * double(is < NS / 2 ? is : is - NS);
                             return make_double2(-v.y * ky, v.x * ky);
                         }
-                        double g = colok ? a.table[long(is) * a.table_row + c0 + f] : 0.0;
+                        const double* tb = mode == Y_TABLE2 ? a.table2 : a.table;
+                        double g = colok ? tb[long(is) * a.table_row + c0 + f] : 0.0;
                         return make_double2(v.x * g, v.y * g);
                     },
                     [&](int f, int i, cplx v) {

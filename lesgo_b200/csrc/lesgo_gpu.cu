@@ -19,6 +19,7 @@
 #include "prodfwd_kernels.h"
 #include "lasd_kernels.h"
 #include "turbine_kernels.h"
+#include "tavg_kernels.h"
 
 using namespace lg;
 
@@ -63,9 +64,12 @@ struct lesgo_gpu_ctx {
     double* gtest = nullptr;               // test-filter kernel G_test (lh, ny)
     double* wplane[2] = {nullptr};         // filtered wall-adjacent u, v planes
     double* gtest2 = nullptr;              // second test-filter kernel G_test_test (sgs_model 5)
-    double* lasd_buf[51] = {nullptr};      // lagrange_Sdep work fields, lasd_chunk planes each
+    double* lasd_buf[54] = {nullptr};      // lagrange_Sdep work fields (51) + 3 spectral scratch, lasd_chunk planes each
     double* lasd_tmp[4] = {nullptr};       // interpolag_Sdep's copies of F_LM, F_MM, F_QN, F_NN
     int lasd_chunk = 0;
+    double* tavg_acc[TA_N] = {nullptr};    // running time averages (lesgo_gpu_tavg_compute)
+    double* tavg_tmp[5] = {nullptr};       // w_uv, u_w, v_w, vortz, fza_uv
+    double tavg_time = 0.0;
     // actuator disks (lesgo_gpu_turbines_init)
     TurbSet turb;
     bool turb_on = false, turb_fz = false;
@@ -442,7 +446,7 @@ YArgs yargs(lesgo_gpu_ctx* c, long splane, int srow, long dplane, int drow, int 
     a.src_plane = splane; a.src_row = srow; a.dst_plane = dplane; a.dst_row = drow;
     a.ncols = ncols; a.k0 = k0;
     a.kxs = c->kxs; a.kys = c->kys;
-    a.table = nullptr; a.table_row = 0;
+    a.table = nullptr; a.table2 = nullptr; a.table_row = 0;
     a.zero_col = -1; a.keep_nyq_row = 0;
     return a;
 }
@@ -1091,22 +1095,29 @@ int sum3(lesgo_gpu_ctx* c, double* out, const double* a, const double* b, const 
 // ---- Lagrangian scale-dependent dynamic model -------------------------------------------
 // test_filter AND test_test_filter (test_filtermodule.f90:126-168) of nf <= 3 fields on planes k0..k1-1: the
 // forward x transform is shared by the two filters.  Arrays are addressed by absolute plane index.
-int filter_fields(lesgo_gpu_ctx* c, int nf, const double* const* src, double* const* dst1, double* const* dst2, int k0, int k1) {
+// `sp2`: nf more spectral scratch arrays (addressed by absolute plane index like everything else here).
+int filter_fields(lesgo_gpu_ctx* c, int nf, const double* const* src, double* const* dst1, double* const* dst2,
+                  double* const* sp2, int k0, int k1) {
     if (need_small(c, 6)) return 1;
     ProScale ps;
     for (int i = 0; i < nf; ++i) ps.src[i] = src[i];
     ps.lay = c->lay(); ps.scale = 1.0;
     double* xs[3] = {c->sa[0], c->sa[1], c->sa[2]};
     if (xfwd(c, false, ps, nf, xs, c->plane, c->ld, c->nx / 2, c->ny, k0, k1)) return 1;
-    for (int which = 0; which < 2; ++which) {
-        YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, c->nx / 2, k0);
-        for (int i = 0; i < nf; ++i) { a.fld[i].src = c->sa[i]; a.fld[i].out[0] = YOutSpec{c->sa[3 + i], Y_TABLE}; }
-        a.table = which == 0 ? c->gtest : c->gtest2; a.table_row = c->lh;
-        if (ypass(c, c->ny, c->ny, a, nf, k0, k1)) return 1;
-        const double* s0[3] = {c->sa[3], c->sa[4], c->sa[5]};
-        if (xinv(c, false, s0, c->plane, c->ld, c->nx / 2, nf, which == 0 ? dst1 : dst2, c->lay(), c->ny, k0, k1)) return 1;
+    // one y pass: forward transform once, G_test and G_test_test applied to the same spectrum, two inverses
+    YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, c->nx / 2, k0);
+    a.nout = 2;
+    for (int i = 0; i < nf; ++i) {
+        a.fld[i].src = c->sa[i];
+        a.fld[i].out[0] = YOutSpec{c->sa[3 + i], Y_TABLE};
+        a.fld[i].out[1] = YOutSpec{sp2[i], Y_TABLE2};
     }
-    return 0;
+    a.table = c->gtest; a.table2 = c->gtest2; a.table_row = c->lh;
+    if (ypass(c, c->ny, c->ny, a, nf, k0, k1)) return 1;
+    const double* s0[6];
+    double* d0[6];
+    for (int i = 0; i < nf; ++i) { s0[i] = c->sa[3 + i]; d0[i] = dst1[i]; s0[nf + i] = sp2[i]; d0[nf + i] = dst2[i]; }
+    return xinv(c, false, s0, c->plane, c->ld, c->nx / 2, 2 * nf, d0, c->lay(), c->ny, k0, k1);
 }
 
 // lagrange_Sdep (lagrange_Sdep.f90:22-430) including interpolag_Sdep (interpolag_Sdep.f90:21-268); Sij in c->work[0..5]
@@ -1146,7 +1157,7 @@ int lagrange_sdep(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* con
         const char* e = std::getenv("LESGO_LASD_CHUNK");
         int ch = e ? std::atoi(e) : 32;
         c->lasd_chunk = ch < 1 ? 1 : (ch > nz ? nz : ch);
-        for (int i = 0; i < 51; ++i)
+        for (int i = 0; i < 54; ++i)
             if (dev_alloc(c, &c->lasd_buf[i], size_t(c->plane) * c->lasd_chunk)) return 1;
     }
     const double dx = g.dx, dy = g.dy;
@@ -1154,8 +1165,9 @@ int lagrange_sdep(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* con
     for (int k0 = 1; k0 <= nz; k0 += c->lasd_chunk) {
         const int k1 = (k0 + c->lasd_chunk < nz + 1) ? k0 + c->lasd_chunk : nz + 1;
         // work fields addressed by the absolute plane index
-        double* B[51];
-        for (int i = 0; i < 51; ++i) B[i] = c->lasd_buf[i] - long(k0) * c->plane;
+        double* B[54];
+        for (int i = 0; i < 54; ++i) B[i] = c->lasd_buf[i] - long(k0) * c->plane;
+        double** SP2 = B + 51;
         double **A = B, **Tb = B + 9, **Th = B + 18, **Sb = B + 27, **Sh = B + 33, **SSb = B + 39, **SSh = B + 45;
         const int g1 = grid1d(long(c->nx) * c->ny * (k1 - k0));
         {
@@ -1167,9 +1179,9 @@ int lagrange_sdep(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* con
             c->launches++;
         }
         for (int i = 0; i < 9; i += 3)
-            if (filter_fields(c, 3, A + i, Tb + i, Th + i, k0, k1)) return 1;
+            if (filter_fields(c, 3, A + i, Tb + i, Th + i, SP2, k0, k1)) return 1;
         for (int i = 0; i < 6; i += 3)
-            if (filter_fields(c, 3, c->work + i, Sb + i, Sh + i, k0, k1)) return 1;
+            if (filter_fields(c, 3, c->work + i, Sb + i, Sh + i, SP2, k0, k1)) return 1;
         {
             LasdSSArgs sa;
             for (int i = 0; i < 6; ++i) { sa.S[i] = c->work[i]; sa.SS[i] = A[i]; }
@@ -1178,7 +1190,7 @@ int lagrange_sdep(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* con
             c->launches++;
         }
         for (int i = 0; i < 6; i += 3)
-            if (filter_fields(c, 3, A + i, SSb + i, SSh + i, k0, k1)) return 1;
+            if (filter_fields(c, 3, A + i, SSb + i, SSh + i, SP2, k0, k1)) return 1;
         {
             LasdFinalArgs fa;
             for (int i = 0; i < 9; ++i) { fa.Tb[i] = Tb[i]; fa.Th[i] = Th[i]; }
@@ -1883,6 +1895,75 @@ int lesgo_gpu_checkpoint_read(lesgo_gpu_ctx* c, const char* fname) {
     ENTER(c);
     if (!c) return 1;
     return checkpoint_io(c, fname, false);
+}
+
+// ---- tavg%compute (time_average.f90:176-320) on the resident fields -------------------
+int lesgo_gpu_tavg_compute(lesgo_gpu_ctx* c, double dt) {
+    ENTER(c);
+    if (!c) return 1;
+    const int nz = c->nz;
+    const size_t nfield = size_t(c->plane) * (nz + 1);
+    for (int i = 0; i < TA_N; ++i)
+        if (dev_alloc(c, &c->tavg_acc[i], nfield)) return 1;
+    for (int i = 0; i < 5; ++i)
+        if (dev_alloc(c, &c->tavg_tmp[i], nfield)) return 1;
+    const bool forces = c->turb_on;
+    TavgInterpArgs ia;
+    ia.u = field(c, LG_U); ia.v = field(c, LG_V); ia.w = field(c, LG_W); ia.dvdx = field(c, LG_DVDX); ia.dudy = field(c, LG_DUDY);
+    ia.fza = forces ? field(c, LG_FZA) : nullptr;
+    ia.w_uv = c->tavg_tmp[0]; ia.u_w = c->tavg_tmp[1]; ia.v_w = c->tavg_tmp[2]; ia.vortz = c->tavg_tmp[3]; ia.fza_uv = c->tavg_tmp[4];
+    ia.nz = nz; ia.top = c->top;
+    {
+        ProfScope ps_(c, "tavg");
+        LG_LAUNCH(k_tavg_interp, dim3(grid1d(long(c->nx) * c->ny * nz)), dim3(kBlock), 0, c->stream, ia, c->lay(), c->nx, c->ny);
+        c->launches++;
+    }
+    if (c->comm)                                                   // the syncs inside interp_to_uv/w_grid, functions.f90:83-88,131-137
+        for (int i = 0; i < (forces ? 5 : 4); ++i)
+            if (c->comm->sync_planes(c->tavg_tmp[i], c->plane, nz, 3, c->stream)) return c->fail(c->comm->error());
+    TavgArgs a;
+    a.u = ia.u; a.v = ia.v; a.w = ia.w; a.p = field(c, LG_P);
+    a.txx = field(c, LG_TXX); a.tyy = field(c, LG_TYY); a.tzz = field(c, LG_TZZ); a.txy = field(c, LG_TXY);
+    a.txz = field(c, LG_TXZ); a.tyz = field(c, LG_TYZ);
+    a.dudz = field(c, LG_DUDZ); a.dvdz = field(c, LG_DVDZ); a.dwdx = field(c, LG_DWDX); a.dwdy = field(c, LG_DWDY);
+    a.cs = field(c, LG_CS_OPT2);
+    a.fxa = forces ? field(c, LG_FXA) : nullptr; a.fya = forces ? field(c, LG_FYA) : nullptr;
+    a.w_uv = ia.w_uv; a.u_w = ia.u_w; a.v_w = ia.v_w; a.vortz = ia.vortz; a.fza_uv = ia.fza_uv;
+    for (int i = 0; i < TA_N; ++i) a.acc[i] = c->tavg_acc[i];
+    a.dt = dt; a.nz = nz; a.bottom = c->bottom; a.top = c->top; a.lbc_mom = c->d.lbc_mom; a.ubc_mom = c->d.ubc_mom;
+    a.forces = forces ? 1 : 0;
+    if (!a.p || !a.txx || !a.cs) return 1;
+    {
+        ProfScope ps_(c, "tavg");
+        LG_LAUNCH(k_tavg_accumulate, dim3(grid1d(long(c->nx) * c->ny * (nz + 1))), dim3(kBlock), 0, c->stream, a, c->lay(), c->nx, c->ny);
+        c->launches++;
+    }
+    c->tavg_time += dt;                                            // :313
+    return 0;
+}
+
+int lesgo_gpu_tavg_download(lesgo_gpu_ctx* c, int which, double* host, double* total_time) {
+    ENTER(c);
+    if (!c) return 1;
+    if (which < 0 || which >= TA_N) return c->fail("lesgo_gpu_tavg_download: bad accumulator id");
+    if (!c->tavg_acc[which]) return c->fail("lesgo_gpu_tavg_download: lesgo_gpu_tavg_compute has not been called");
+    if (host) {
+        // device (ld, ny, 0:nz) -> host (nx, ny, lbz:nz) as tavg_t holds it (time_average.f90:98-131)
+        CK(cudaMemcpy2DAsync(host, size_t(c->nx) * sizeof(double), c->tavg_acc[which], size_t(c->ld) * sizeof(double),
+                             size_t(c->nx) * sizeof(double), size_t(c->ny) * (c->nz + 1), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    if (total_time) *total_time = c->tavg_time;
+    return 0;
+}
+
+int lesgo_gpu_tavg_reset(lesgo_gpu_ctx* c) {
+    ENTER(c);
+    if (!c) return 1;
+    for (int i = 0; i < TA_N; ++i)
+        if (c->tavg_acc[i]) CK(cudaMemsetAsync(c->tavg_acc[i], 0, size_t(c->plane) * (c->nz + 1) * sizeof(double), c->stream));
+    c->tavg_time = 0.0;
+    return 0;
 }
 
 int lesgo_gpu_turbines_init(lesgo_gpu_ctx* c, int nloc, const lesgo_gpu_turbine* t, int adm_correction) {

@@ -1481,6 +1481,58 @@ def step(s: State, sp: Spectral, comm, mode="full", first_step=False, G_test=Non
 
 
 # ----------------------------------------------------------------------------------
+# Running time averages: time_average.f90:176-320 (tavg%compute)
+# ----------------------------------------------------------------------------------
+TAVG_FIELDS = ("u", "v", "w", "w_uv", "u_w", "v_w", "u2", "v2", "w2", "uv", "uw", "vw", "txx", "tyy", "tzz",
+               "txy", "txz", "tyz", "p", "fx", "fy", "fz", "cs_opt2", "vortx", "vorty", "vortz")
+
+
+class Tavg:
+    """type tavg_t (time_average.f90:33-62): accumulators (nx, ny, lbz:nz), here [k, j, i]."""
+
+    def __init__(self, p: Params):
+        for n in TAVG_FIELDS:
+            setattr(self, n, np.zeros((p.nz + 1, p.ny, p.nx)))
+        self.total_time = 0.0
+
+
+def tavg_compute(t: Tavg, s, p: Params, comm, dt, forces=False):
+    """time_average.f90:176-320.  Plane 0 of the interpolated quantities on coord 0 is unset in the
+    reference (interp_to_*_grid allocate without initialising it); it is 0 here."""
+    nx, nz = p.nx, p.nz
+    X = slice(0, nx)
+    lasd_alloc(s)
+    w_uv = interp_to_uv_grid(s.w, p, comm)                                   # :196-198
+    u_w = interp_to_w_grid(s.u, p, comm)
+    v_w = interp_to_w_grid(s.v, p, comm)
+    pres_real = s.p - 0.5 * (s.u ** 2 + w_uv ** 2 + s.v ** 2)                # :204-208
+    vortz = interp_to_w_grid(s.dvdx - s.dudy, p, comm)                       # :213-214
+    vortx = s.dwdy - s.dvdz                                                  # :215-216
+    vorty = s.dudz - s.dwdx
+    if p.coord == 0:
+        vortz[1] = 0.0                                                       # :218-220
+        if p.lbc_mom > 0:
+            u_w[1] = 0.0; v_w[1] = 0.0                                       # :224-227
+    if p.coord == p.nproc - 1 and p.ubc_mom > 0:
+        u_w[nz] = 0.0; v_w[nz] = 0.0
+    u, v, w = s.u, s.v, s.w
+    t.u += u[:, :, X] * dt; t.v += v[:, :, X] * dt; t.w += w[:, :, X] * dt   # :229-234
+    t.w_uv += w_uv[:, :, X] * dt; t.u_w += u_w[:, :, X] * dt; t.v_w += v_w[:, :, X] * dt
+    t.u2 += u[:, :, X] * u[:, :, X] * dt; t.v2 += v[:, :, X] * v[:, :, X] * dt   # :236-241
+    t.w2 += w[:, :, X] * w[:, :, X] * dt; t.uv += u[:, :, X] * v[:, :, X] * dt
+    t.uw += u_w[:, :, X] * w[:, :, X] * dt; t.vw += v_w[:, :, X] * w[:, :, X] * dt
+    for n in ("txx", "tyy", "tzz", "txy", "txz", "tyz"):                     # :243-248
+        getattr(t, n)[...] += getattr(s, n)[:, :, X] * dt
+    t.p += pres_real[:, :, X] * dt                                           # :250
+    if forces:                                                               # :252-256
+        fza_uv = interp_to_uv_grid(s.fza, p, comm)
+        t.fx[1:] += s.fxa[1:, :, X] * dt; t.fy[1:] += s.fya[1:, :, X] * dt; t.fz[1:] += fza_uv[1:, :, X] * dt
+    t.cs_opt2[1:] += s.Cs_opt2[1:, :, X] * dt                                # :258
+    t.vortx += vortx[:, :, X] * dt; t.vorty += vorty[:, :, X] * dt; t.vortz += vortz[:, :, X] * dt   # :260-262
+    t.total_time += dt
+
+
+# ----------------------------------------------------------------------------------
 # Restart file: io.f90:1204-1211 (checkpoint), initial.f90:226-239 (ic_file)
 # ----------------------------------------------------------------------------------
 CHECKPOINT_FIELDS = ("u", "v", "w", "RHSx", "RHSy", "RHSz", "Cs_opt2", "F_LM", "F_MM", "F_QN", "F_NN")

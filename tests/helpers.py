@@ -293,6 +293,9 @@ def check_turbines(core, p, nsteps=2, tol=1e-12, mode="core", eps=0.3, adm_corre
     return out
 
 
+TAVG_SEAM = ("w_uv", "u_w", "v_w", "uw", "p", "vortz", "fz", "u2")
+
+
 def farm_for_rank(farm, p):
     """The slab of rank p.coord of a single-slab farm: nodes with global k in the rank's 1..nz-1 (turbines.f90:246-247,
     425), same normalised weights."""
@@ -310,7 +313,7 @@ def farm_for_rank(farm, p):
 
 
 def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core", lasd=False,
-                          turbines=False):
+                          turbines=False, tavg=False):
     """nproc ranks (threads of this process, one Core each) advance `nsteps` core steps;
     the gathered result must match the SINGLE-slab oracle (which the multi-slab oracle
     equals, tests/test_oracle_kat.py)."""
@@ -334,6 +337,10 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
                        update=sch["lasd_update"], init_F=sch["lasd_init_F"])
         O.step(sref, spg, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=Gg, lasd=ld_,
                turbines=dict(farm=farm_ref, eps=0.3) if turbines else None)
+        if tavg:
+            if it == 0:
+                tref = O.Tavg(pg)
+            O.tavg_compute(tref, sref, pg, O.LocalComm(), pg.dt, forces=turbines)
     ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
     cores = [lesgo_b200.Core(make_dims(p, device=(device_of(p.coord) if device_of else -1)), lib=lib) for p in ps]
     ident = cores[0].comm_unique_id()
@@ -351,7 +358,12 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
                 c.turbines_init(farm_for_rank(farm_g, p))
             for it in range(nsteps):
                 c.step(**step_kwargs(p, it, mode), **(lasd_schedule(p, it) if lasd else {}), **tkw)
+                if tavg:
+                    c.tavg_compute(p.dt)
             res[r] = {n: c.download(n) for n in names}
+            if tavg:
+                for n in TAVG_SEAM:
+                    res[r]["tavg_" + n] = c.tavg_download(n)[0]
             if turbines:
                 res[r]["u_d_T"] = c.turbines_forcing(0.3)[1]
             # mpi_sync_real_array (mpi_defs.f90:245-262) on a host array
@@ -384,6 +396,11 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
         g = O.gather_slabs([res[r][n] for r in range(nproc)], ps, top_extra=top)
         hi = nzt if top else nzt - 1
         out[n] = rel(g[1:hi + 1, :, :pg.nx], getattr(sref, n)[1:hi + 1, :, :pg.nx])
+    if tavg:
+        # the accumulators whose interpolations cross the slab seams
+        for n in TAVG_SEAM:
+            g = O.gather_slabs([res[r]["tavg_" + n] for r in range(nproc)], ps, top_extra=False)
+            out["tavg_" + n] = rel(g[1:nzt], getattr(tref, n)[1:nzt])
     if turbines:
         # one more forcing call on both sides: every rank must hold the same (global) disk velocities
         O.turbines_forcing(sref, pg, O.LocalComm(), farm_ref, 0.3)
@@ -393,6 +410,45 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
     assert all(abs(res[r]["cfl"] - cfl_ref) <= 1e-12 * cfl_ref for r in range(nproc)), (cfl_ref, [res[r]["cfl"] for r in range(nproc)])
     for k, v in out.items():
         assert v <= (CS_TOL if k == "Cs_opt2" else tol), (k, v, out)
+    return out
+
+
+def check_tavg(core, p, nsteps=2, tol=1e-12, turbines=False):
+    """tavg%compute (time_average.f90:176-320) after each of nsteps full steps: all 26 accumulators."""
+    sp = O.Spectral(p)
+    nx, nz = p.nx, p.nz
+    G = O.test_filter_kernel(sp)
+    s = initial_state(p, seed=81)
+    s.u += 1.0
+    O.lasd_alloc(s)
+    s.Cs_opt2[...] = 0.01 * np.abs(random_field(p, 82))
+    for n in ("u", "v", "w", "Cs_opt2"):
+        core.upload(n, getattr(s, n))
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+        core.upload(n, np.zeros(core.dims.shape))
+    farm = make_farm(p) if turbines else None
+    if turbines:
+        core.turbines_init(farm)
+    t = O.Tavg(p)
+    for it in range(nsteps):
+        O.step(s, sp, O.LocalComm(), mode="full", first_step=(it == 0), G_test=G,
+               turbines=dict(farm=farm, eps=0.3) if turbines else None)
+        core.step(**step_kwargs(p, it, "full"), **(dict(turbines=True, turbines_eps=0.3) if turbines else {}))
+        dt_avg = p.dt * (1 + it)                                   # variable increments, as with use_cfl_dt
+        O.tavg_compute(t, s, p, O.LocalComm(), dt_avg, forces=turbines)
+        core.tavg_compute(dt_avg)
+    out = {}
+    for n in O.TAVG_FIELDS:
+        g, tt = core.tavg_download(n)
+        r = getattr(t, n)
+        out[n] = rel(g[1:nz], r[1:nz]) if np.any(r[1:nz]) else float(np.abs(g[1:nz]).max())
+        assert abs(tt - t.total_time) < 1e-15
+    assert turbines or out["fx"] == 0.0
+    for k, v in out.items():
+        assert v <= tol, (k, v, out)
+    core.tavg_reset()
+    g, tt = core.tavg_download("u2")
+    assert tt == 0.0 and not g.any()
     return out
 
 

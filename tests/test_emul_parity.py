@@ -122,7 +122,7 @@ def test_emul_multirank_turbines(nproc):
     """Disks spanning several z slabs: per-rank node lists, all-reduced disk velocities, force halos."""
     from helpers import check_multirank_steps
     kw = dict(nx=32, ny=16, Nz=12, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False)
-    out = check_multirank_steps(emul_library(), kw, nproc, nsteps=2, mode="full", turbines=True)
+    out = check_multirank_steps(emul_library(), kw, nproc, nsteps=2, mode="full", turbines=True, tavg=True)
     print(out)
 
 
@@ -138,6 +138,17 @@ def test_emul_turbines_errors():
     bad.ind = np.array([1.0])
     with pytest.raises(lesgo_b200.LibraryError, match="node outside"):
         c.turbines_init([bad])
+
+
+@pytest.mark.parametrize("cfg,turbines", [
+    (dict(nx=16, ny=16, Nz=8, lbc_mom=1, ubc_mom=1, molec=True, nu_molec=1e-2), False),
+    (dict(nx=32, ny=16, Nz=12, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False), True),
+])
+def test_emul_tavg(cfg, turbines):
+    """Rows (f)-4: running time averages accumulated from the resident fields."""
+    from helpers import check_tavg
+    p = O.Params(**cfg)
+    print(check_tavg(core_for(p), p, turbines=turbines, tol=1e-11))
 
 
 def test_emul_checkpoint(tmp_path, monkeypatch):

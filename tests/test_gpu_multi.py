@@ -47,6 +47,6 @@ def test_multi_gpu_turbines():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     kw = dict(nx=64, ny=64, Nz=32, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False)
-    out = check_multirank_steps(lesgo_b200.load_library(), kw, 2, nsteps=2, tol=1e-11, mode="full", turbines=True,
+    out = check_multirank_steps(lesgo_b200.load_library(), kw, 2, nsteps=2, tol=1e-11, mode="full", turbines=True, tavg=True,
                                 device_of=lambda coord: coord)
     print(out)

@@ -161,6 +161,17 @@ def test_turbines(cfg, mode):
     print(out)
 
 
+@pytest.mark.parametrize("cfg,turbines", [
+    (dict(nx=64, ny=64, Nz=16, lbc_mom=1, ubc_mom=1, molec=True, nu_molec=1e-2), False),
+    (dict(nx=64, ny=32, Nz=24, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False), True),
+])
+def test_tavg(cfg, turbines):
+    """Rows (f)-4: tavg%compute (time_average.f90:176-320) from the resident fields, all 26 accumulators."""
+    from helpers import check_tavg
+    p = O.Params(**cfg)
+    print(check_tavg(core_for(p), p, turbines=turbines, tol=1e-12))
+
+
 def test_checkpoint(tmp_path, monkeypatch):
     """Rows (f)-4: restart file of the resident state (io.f90:1204-1211 / initial.f90:226-239)."""
     from helpers import check_checkpoint

@@ -310,7 +310,10 @@ def main():
     achieved = A_CORE_BYTES * points / (ms_step * 1e-3) / 1e9 / world
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+        tpath = os.path.join(ROOT, "profiles", "r3_traffic.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        with open(tpath) as f:
             tj = json.load(f)
         if tj.get("grid") == [nx, ny, Nz] and world == 1:
             traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]

@@ -396,6 +396,23 @@ def main():
                     "what": "full step (Smagorinsky) + turbines_forcing: gather, all-reduce, scatter, RHS += f"}
         except Exception as e:  # noqa
             turb = {"error": str(e)}
+    tavg = None
+    if not args.no_extras:
+        try:
+            core.tavg_compute(dt)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(3):
+                core.tavg_compute(dt)
+            b.record(stream)
+            barrier()
+            t_ms = a.elapsed_time(b) / 3
+            # 17 fields + 5 interpolated read, 26 accumulators read and written, 5 interpolated written, per point
+            tavg = {"ms_per_call": t_ms, "GBps": (17 + 5 + 2 * 26 + 5 + 7) * 8 * points / world / (t_ms * 1e-3) / 1e9,
+                    "what": "tavg%compute: interpolations + 26 accumulators (row (f)-4), algorithmic bytes / time"}
+        except Exception as e:  # noqa
+            tavg = {"error": str(e)}
 
     e2e = None
     if rank == 0 and not args.no_e2e and world == 1:
@@ -413,7 +430,7 @@ def main():
                            "grid": [nx, ny, Nz], "decomposition": f"z-slabs x{world}",
                            "l2": "inputs larger than L2 (%.0f MB per field)" % (np.prod(dims.shape) * 8 / 1e6)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-                "clocks": clocks, "kernels": kernels, "max_cfl": cfl, "full_step": full, "lasd_step": lasd, "turbines_step": turb}
+                "clocks": clocks, "kernels": kernels, "max_cfl": cfl, "full_step": full, "lasd_step": lasd, "turbines_step": turb, "tavg": tavg}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

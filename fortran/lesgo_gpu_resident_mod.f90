@@ -1,0 +1,152 @@
+!> ISO_C_BINDING declarations of the DEVICE-RESIDENT entry points of liblesgo_cuda.so
+!> (include/lesgo_gpu.h): whole-step stepping, the Lagrangian scale-dependent model switches,
+!> actuator disks, running time averages and the restart file.  Companion of lesgo_gpu_mod.f90
+!> (same context `gpu_ctx`, same error path `gpu_check`); the table in INTEGRATION.md says which
+!> reference call site each one replaces.
+!> (Not compiled in the build container: it has no Fortran compiler.  The derived types below
+!> mirror the C structs member by member; tests/test_abi.py checks the ctypes mirror of the same
+!> structs against the header.)
+module lesgo_gpu_resident_mod
+use iso_c_binding
+use lesgo_gpu_mod, only : gpu_ctx, gpu_check
+implicit none
+save
+public
+
+!> enum lesgo_gpu_field
+integer(c_int), parameter :: LG_U = 0, LG_V = 1, LG_W = 2, LG_DUDX = 3, LG_DUDY = 4, LG_DUDZ = 5,           &
+    LG_DVDX = 6, LG_DVDY = 7, LG_DVDZ = 8, LG_DWDX = 9, LG_DWDY = 10, LG_DWDZ = 11, LG_RHSX = 12,            &
+    LG_RHSY = 13, LG_RHSZ = 14, LG_RHSX_F = 15, LG_RHSY_F = 16, LG_RHSZ_F = 17, LG_P = 18, LG_DPDX = 19,     &
+    LG_DPDY = 20, LG_DPDZ = 21, LG_DIVTX = 22, LG_DIVTY = 23, LG_DIVTZ = 24, LG_TXX = 25, LG_TXY = 26,       &
+    LG_TXZ = 27, LG_TYY = 28, LG_TYZ = 29, LG_TZZ = 30, LG_F_LM = 31, LG_F_MM = 32, LG_F_QN = 33,            &
+    LG_F_NN = 34, LG_CS_OPT2 = 35, LG_FXA = 36, LG_FYA = 37, LG_FZA = 38
+
+!> struct lesgo_gpu_step_params
+type, bind(c) :: lesgo_gpu_step_params
+    real(c_double) :: dt, tadv1, tadv2
+    real(c_double) :: mean_p_force_x, mean_p_force_y
+    real(c_double) :: ubot, utop, nu_molec_nd
+    integer(c_int) :: first_step, mode
+    integer(c_int) :: sgs_model, ifilter
+    real(c_double) :: Co, wall_damp_exp, vonk, zo
+    integer(c_int) :: lasd_cs_init, lasd_update, lasd_init_F
+    real(c_double) :: lagran_dt
+    integer(c_int) :: turbines
+    real(c_double) :: turbines_eps
+end type lesgo_gpu_step_params
+
+!> struct lesgo_gpu_turbine: nodes -> c_loc(wind_farm%turbine(s)%nodes_c), an integer(c_int) array (3, num_nodes)
+!> holding transpose(%nodes(1:num_nodes, 1:3)); ind -> c_loc(%ind)
+type, bind(c) :: lesgo_gpu_turbine
+    integer(c_int) :: num_nodes
+    type(c_ptr) :: nodes
+    type(c_ptr) :: ind
+    real(c_double) :: nhat(3)
+    real(c_double) :: Ct_prime, dia, M, u_d_T
+end type lesgo_gpu_turbine
+
+interface
+    integer(c_int) function lesgo_gpu_upload(ctx, field, host) bind(c, name='lesgo_gpu_upload')
+        import
+        type(c_ptr), value :: ctx
+        integer(c_int), value :: field
+        real(c_double), intent(in) :: host(*)
+    end function
+    integer(c_int) function lesgo_gpu_download(ctx, field, host) bind(c, name='lesgo_gpu_download')
+        import
+        type(c_ptr), value :: ctx
+        integer(c_int), value :: field
+        real(c_double), intent(out) :: host(*)
+    end function
+    integer(c_int) function lesgo_gpu_step(ctx, sp) bind(c, name='lesgo_gpu_step')
+        import
+        type(c_ptr), value :: ctx
+        type(lesgo_gpu_step_params), intent(in) :: sp
+    end function
+    integer(c_int) function lesgo_gpu_max_cfl(ctx, dt, cfl) bind(c, name='lesgo_gpu_max_cfl')
+        import
+        type(c_ptr), value :: ctx
+        real(c_double), value :: dt
+        real(c_double), intent(out) :: cfl
+    end function
+    integer(c_int) function lesgo_gpu_rmsdiv(ctx, rms) bind(c, name='lesgo_gpu_rmsdiv')
+        import
+        type(c_ptr), value :: ctx
+        real(c_double), intent(out) :: rms
+    end function
+    integer(c_int) function lesgo_gpu_turbines_init(ctx, nloc, turbines, adm_correction)                    &
+        bind(c, name='lesgo_gpu_turbines_init')
+        import
+        type(c_ptr), value :: ctx
+        integer(c_int), value :: nloc, adm_correction
+        type(lesgo_gpu_turbine), intent(in) :: turbines(*)
+    end function
+    integer(c_int) function lesgo_gpu_turbines_forcing(ctx, eps, u_d, u_d_T, f_n)                           &
+        bind(c, name='lesgo_gpu_turbines_forcing')
+        import
+        type(c_ptr), value :: ctx
+        real(c_double), value :: eps
+        real(c_double), intent(out) :: u_d(*), u_d_T(*), f_n(*)
+    end function
+    integer(c_int) function lesgo_gpu_tavg_compute(ctx, dt) bind(c, name='lesgo_gpu_tavg_compute')
+        import
+        type(c_ptr), value :: ctx
+        real(c_double), value :: dt
+    end function
+    integer(c_int) function lesgo_gpu_tavg_download(ctx, which, host, total_time)                           &
+        bind(c, name='lesgo_gpu_tavg_download')
+        import
+        type(c_ptr), value :: ctx
+        integer(c_int), value :: which
+        real(c_double), intent(out) :: host(*)
+        real(c_double), intent(out) :: total_time
+    end function
+    integer(c_int) function lesgo_gpu_tavg_reset(ctx) bind(c, name='lesgo_gpu_tavg_reset')
+        import
+        type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function lesgo_gpu_checkpoint_write(ctx, fname) bind(c, name='lesgo_gpu_checkpoint_write')
+        import
+        type(c_ptr), value :: ctx
+        character(kind=c_char), intent(in) :: fname(*)
+    end function
+    integer(c_int) function lesgo_gpu_checkpoint_read(ctx, fname) bind(c, name='lesgo_gpu_checkpoint_read')
+        import
+        type(c_ptr), value :: ctx
+        character(kind=c_char), intent(in) :: fname(*)
+    end function
+end interface
+
+contains
+
+!> The `if` chain of sgs_stag_util.f90:183-216 and lagrange_Sdep.f90:270,320 as switches of the step:
+!> call once per time step before lesgo_gpu_step when sgs_model == 5.
+subroutine gpu_lasd_switches(sp, lasd_initialised)
+use param, only : jt, jt_total, DYN_init, cs_count, inilag, initu, dt
+type(lesgo_gpu_step_params), intent(inout) :: sp
+logical, intent(inout) :: lasd_initialised      !< F_LM_MM_init / F_QN_NN_init of lagrange_Sdep.f90:70-71
+sp%lasd_cs_init = 0; sp%lasd_update = 0; sp%lasd_init_F = 0
+sp%lagran_dt = cs_count * dt                     ! sgs_stag_util.f90:82 (fixed dt)
+if (jt == 1 .and. inilag) then
+    sp%lasd_cs_init = 1
+else if ((jt >= DYN_init .or. initu) .and. mod(jt_total, cs_count) == 0) then
+    sp%lasd_update = 1
+    if (inilag .and. .not. lasd_initialised .and. (jt == cs_count .or. jt == DYN_init)) then
+        sp%lasd_init_F = 1
+        lasd_initialised = .true.
+    end if
+end if
+end subroutine gpu_lasd_switches
+
+!> checkpoint (io.f90:1199-1211) / ic_file (initial.f90:226-239) with the reference's file name
+subroutine gpu_checkpoint(fname, writing)
+character(*), intent(in) :: fname
+logical, intent(in) :: writing
+if (writing) then
+    call gpu_check(lesgo_gpu_checkpoint_write(gpu_ctx, trim(fname)//c_null_char), 'lesgo_gpu_checkpoint_write')
+else
+    call gpu_check(lesgo_gpu_checkpoint_read(gpu_ctx, trim(fname)//c_null_char), 'lesgo_gpu_checkpoint_read')
+end if
+end subroutine gpu_checkpoint
+
+end module lesgo_gpu_resident_mod

@@ -56,3 +56,29 @@ def test_product_package_does_not_touch_oracle_or_emulator():
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|lesgo_oracle", src, re.M), f
                 assert "liblesgo_emul" not in src, f
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct of include/lesgo_gpu.h, taken from the C compiler, against the
+    ctypes mirrors in lesgo_b200/lib.py (the Fortran bind(C) types in fortran/ list the same members)."""
+    import ctypes as C
+    import subprocess
+    from lesgo_b200.lib import DimsStruct, StepParams, TurbineStruct
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = {"lesgo_gpu_dims": DimsStruct, "lesgo_gpu_step_params": StepParams, "lesgo_gpu_turbine": TurbineStruct}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lesgo_gpu.h"\nint main(void) {\n'
+                   + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)

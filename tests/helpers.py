@@ -235,7 +235,7 @@ def check_lasd_steps(core, p, nsteps=4, tol=1e-11, seed=61, amp=0.5):
 CS_TOL = 1e-9
 
 
-def make_farm(p, comm=None, tilt=True):
+def make_farm(p, comm=None, tilt=True, overlap=False):
     """Two actuator disks (one yawed and tilted, so all three force components are exercised) on the
     grid of p, with the node lists turbines_nodes (turbines.f90:275-462) builds."""
     comm = comm or O.LocalComm()
@@ -246,21 +246,29 @@ def make_farm(p, comm=None, tilt=True):
                       Ct_prime=1.33, u_d_T=-0.7),
             O.Turbine(xloc=0.97 * p.L_x, yloc=0.8 * p.L_y, height=0.9 * h, dia=0.8 * dia, thk=1.2 * p.dx,
                       theta1=20.0 if tilt else 0.0, theta2=10.0 if tilt else 0.0, Ct_prime=1.0, u_d_T=-0.5)]
+    if overlap:
+        # a third disk that shares grid points with the first: the reference assigns node by node in disk
+        # order (turbines.f90:599-606), so the later disk's force replaces the earlier one's there
+        farm.append(O.Turbine(xloc=0.25 * p.L_x + 1.0 * p.dx, yloc=0.3 * p.L_y + 2.0 * p.dy, height=h, dia=0.7 * dia,
+                              thk=1.2 * p.dx, Ct_prime=0.8, u_d_T=-0.4))
     for t in farm:
         val = O.standin_indicator(t.dia, t.thk, dlt, dlt)
         O.turbines_nodes(p, [t], val, comm)
     return farm
 
 
-def check_turbines(core, p, nsteps=2, tol=1e-12, mode="core", eps=0.3, adm_correction=True):
+def check_turbines(core, p, nsteps=2, tol=1e-12, mode="core", eps=0.3, adm_correction=True, overlap=False):
     """turbines_forcing standalone (force fields, per-disk scalars) and inside lesgo_gpu_step."""
     sp = O.Spectral(p)
     nx, nz = p.nx, p.nz
     G = O.test_filter_kernel(sp)
     s = initial_state(p, seed=71)
     s.u += 1.0
-    farm = make_farm(p)
+    farm = make_farm(p, overlap=overlap)
     assert all(len(t.ind) > 10 for t in farm)
+    if overlap:
+        shared = set(map(tuple, farm[0].nodes)) & set(map(tuple, farm[2].nodes))
+        assert len(shared) > 5, "the overlap case needs shared grid points"
     for n in ("u", "v", "w"):
         core.upload(n, getattr(s, n))
     for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):

@@ -161,6 +161,12 @@ def test_turbines(cfg, mode):
     print(out)
 
 
+def test_turbines_overlapping_disks():
+    from helpers import check_turbines
+    p = O.Params(nx=64, ny=64, Nz=32, lbc_mom=1, ubc_mom=1)
+    print(check_turbines(core_for(p), p, mode="core", tol=1e-12, overlap=True))
+
+
 @pytest.mark.parametrize("cfg,turbines", [
     (dict(nx=64, ny=64, Nz=16, lbc_mom=1, ubc_mom=1, molec=True, nu_molec=1e-2), False),
     (dict(nx=64, ny=32, Nz=24, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False), True),

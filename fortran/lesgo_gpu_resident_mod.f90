@@ -69,6 +69,12 @@ interface
         real(c_double), value :: dt
         real(c_double), intent(out) :: cfl
     end function
+    integer(c_int) function lesgo_gpu_cfl_dt(ctx, cfl, dt) bind(c, name='lesgo_gpu_cfl_dt')
+        import
+        type(c_ptr), value :: ctx
+        real(c_double), value :: cfl
+        real(c_double), intent(out) :: dt
+    end function
     integer(c_int) function lesgo_gpu_rmsdiv(ctx, rms) bind(c, name='lesgo_gpu_rmsdiv')
         import
         type(c_ptr), value :: ctx

@@ -153,6 +153,8 @@ typedef struct lesgo_gpu_step_params {
 int lesgo_gpu_step(lesgo_gpu_ctx* ctx, const lesgo_gpu_step_params* sp);
 /* cfl_util.f90:35-69 get_max_cfl (dx, dy from L/n) and rmsdiv.f90 on resident fields */
 int lesgo_gpu_max_cfl(lesgo_gpu_ctx* ctx, double dt, double* cfl);
+/* get_cfl_dt, cfl_util.f90:72-113: the time step that makes the maximum CFL number equal `cfl` (min over ranks) */
+int lesgo_gpu_cfl_dt(lesgo_gpu_ctx* ctx, double cfl, double* dt);
 int lesgo_gpu_rmsdiv(lesgo_gpu_ctx* ctx, double* rms);
 
 /* ---- restart file (io.f90:1173-1211 checkpoint, initial.f90:226-239 ic_file) ----------------------------

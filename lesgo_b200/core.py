@@ -318,6 +318,11 @@ class Core:
         self._ck(self.lib.max_cfl(self._ctx, float(dt), C.byref(v)), "max_cfl")
         return v.value
 
+    def cfl_dt(self, cfl):
+        v = C.c_double()
+        self._ck(self.lib.cfl_dt(self._ctx, float(cfl), C.byref(v)), "cfl_dt")
+        return v.value
+
     def rmsdiv(self):
         v = C.c_double()
         self._ck(self.lib.rmsdiv(self._ctx, C.byref(v)), "rmsdiv")

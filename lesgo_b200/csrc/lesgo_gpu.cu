@@ -1986,10 +1986,8 @@ int lesgo_gpu_turbines_forcing(lesgo_gpu_ctx* c, double eps, double* u_d, double
     return 0;
 }
 
-int lesgo_gpu_max_cfl(lesgo_gpu_ctx* c, double dt, double* cfl) {
-    ENTER(c);
-    // cfl_util.f90:35-69 (local part; the caller max-reduces over ranks, or comm does)
-    if (!c || !cfl) return 1;
+// max(|u|)/dx, max(|v|)/dy, max(|w|)/dz over 1:nx, 1:ny, 1:nz-1 of this rank (cfl_util.f90:61-63,102-104)
+static int local_inverse_dt(lesgo_gpu_ctx* c, double* m) {
     if (!c->red_dev) { if (dev_alloc(c, &c->red_dev, 8)) return 1; }
     if (!c->red_host) CK(cudaMallocHost(reinterpret_cast<void**>(&c->red_host), 8 * sizeof(double)));
     CK(cudaMemsetAsync(c->red_dev, 0, 8 * sizeof(double), c->stream));
@@ -2003,10 +2001,31 @@ int lesgo_gpu_max_cfl(lesgo_gpu_ctx* c, double dt, double* cfl) {
     CK(cudaMemcpyAsync(c->red_host, c->red_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     const double dx = c->d.L_x / c->nx, dy = c->d.L_y / c->ny;
-    double m = std::fmax(c->red_host[0] / dx, std::fmax(c->red_host[1] / dy, c->red_host[2] / c->d.dz));
+    *m = std::fmax(c->red_host[0] / dx, std::fmax(c->red_host[1] / dy, c->red_host[2] / c->d.dz));
+    return 0;
+}
+
+int lesgo_gpu_max_cfl(lesgo_gpu_ctx* c, double dt, double* cfl) {
+    ENTER(c);
+    // get_max_cfl, cfl_util.f90:35-69
+    if (!c || !cfl) return 1;
+    double m;
+    if (local_inverse_dt(c, &m)) return 1;
     double r = dt * m;
     if (c->comm && c->comm->allreduce_max(&r, c->stream)) return c->fail(c->comm->error());
     *cfl = r;
+    return 0;
+}
+
+int lesgo_gpu_cfl_dt(lesgo_gpu_ctx* c, double cfl, double* dt) {
+    ENTER(c);
+    // get_cfl_dt, cfl_util.f90:72-113
+    if (!c || !dt) return 1;
+    double m;
+    if (local_inverse_dt(c, &m)) return 1;
+    double r = cfl / m;
+    if (c->comm && c->comm->allreduce(&r, 2, c->stream)) return c->fail(c->comm->error());
+    *dt = r;
     return 0;
 }
 

@@ -65,6 +65,7 @@ SYMBOLS = {
     "lesgo_gpu_download": (C.c_int, [_P, C.c_int, _D]),
     "lesgo_gpu_step": (C.c_int, [_P, C.POINTER(StepParams)]),
     "lesgo_gpu_max_cfl": (C.c_int, [_P, C.c_double, C.POINTER(C.c_double)]),
+    "lesgo_gpu_cfl_dt": (C.c_int, [_P, C.c_double, C.POINTER(C.c_double)]),
     "lesgo_gpu_rmsdiv": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "lesgo_gpu_checkpoint_write": (C.c_int, [_P, C.c_char_p]),
     "lesgo_gpu_checkpoint_read": (C.c_int, [_P, C.c_char_p]),

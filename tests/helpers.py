@@ -388,6 +388,7 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
             else:
                 assert np.all(var[p.nz] == 100.0 * r + p.nz)
             res[r]["cfl"] = c.max_cfl(p.dt)
+            res[r]["cfl_dt"] = c.cfl_dt(0.0625)
         except BaseException as e:  # noqa
             err[r] = e
 
@@ -416,6 +417,8 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
             out[f"u_d_T_rank{r}"] = rel(res[r]["u_d_T"], [t.u_d_T for t in farm_ref])
     cfl_ref = O.get_max_cfl(sref, pg, O.LocalComm())
     assert all(abs(res[r]["cfl"] - cfl_ref) <= 1e-12 * cfl_ref for r in range(nproc)), (cfl_ref, [res[r]["cfl"] for r in range(nproc)])
+    dt_ref = O.get_cfl_dt(sref, pg, O.LocalComm(), 0.0625)
+    assert all(abs(res[r]["cfl_dt"] - dt_ref) <= 1e-12 * dt_ref for r in range(nproc)), (dt_ref, [res[r]["cfl_dt"] for r in range(nproc)])
     for k, v in out.items():
         assert v <= (CS_TOL if k == "Cs_opt2" else tol), (k, v, out)
     return out

@@ -205,6 +205,14 @@ int lesgo_gpu_turbines_forcing(lesgo_gpu_ctx* ctx, double eps, double* u_d, doub
  * the host (MPI_Bcast in the Fortran shim, torch.distributed in the Python host). */
 int lesgo_gpu_comm_unique_id(void* id128);
 int lesgo_gpu_comm_init(lesgo_gpu_ctx* ctx, const void* id128);
+/* Optional, one node: the two transposes of the pressure solve go over NVLink peer memory instead of NCCL
+ * all-to-alls -- the right-hand-side assembly kernel stores straight into the pencil buffers of the other GPUs
+ * and the Thomas kernel stores p_hat straight into the slab owners' buffers, so packing, transfer and unpacking
+ * cost no pass of their own.  Every rank exports a 128-byte blob, the host gathers them in rank order
+ * (MPI_Allgather / torch.distributed) and every rank imports all nproc blobs (after lesgo_gpu_comm_init).
+ * Ranks may be threads of one process (peer access) or separate processes (CUDA IPC). */
+int lesgo_gpu_comm_p2p_export(lesgo_gpu_ctx* ctx, void* blob128);
+int lesgo_gpu_comm_p2p_import(lesgo_gpu_ctx* ctx, const void* blobs128_times_nproc);
 /* mpi_sync_real_array(var, 0, isync), mpi_defs.f90:167-264: isync 1 = DOWN, 2 = UP, 3 = DOWNUP */
 int lesgo_gpu_sync_real_array(lesgo_gpu_ctx* ctx, double* var, int isync);
 

@@ -339,6 +339,17 @@ class Core:
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.lib.comm_init(self._ctx, buf), "comm_init")
 
+    def comm_p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.comm_p2p_export(self._ctx, buf), "comm_p2p_export")
+        return buf.raw
+
+    def comm_p2p_import(self, blobs):
+        """blobs: the nproc 128-byte exports in rank order; switches the pressure transposes to peer memory."""
+        raw = b"".join(blobs)
+        buf = C.create_string_buffer(raw, len(raw))
+        self._ck(self.lib.comm_p2p_import(self._ctx, buf), "comm_p2p_import")
+
     def sync_real_array(self, var, isync=3):
         self._ck(self.lib.sync_real_array(self._ctx, _addr(var, self.dims.shape, True), int(isync)), "sync_real_array")
         return var

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <string>
 #include <utility>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/lesgo_gpu.h"
@@ -70,6 +71,13 @@ struct lesgo_gpu_ctx {
     double* tavg_acc[TA_N] = {nullptr};    // running time averages (lesgo_gpu_tavg_compute)
     double* tavg_tmp[5] = {nullptr};       // w_uv, u_w, v_w, vortz, fza_uv
     double tavg_time = 0.0;
+    // peer-memory pressure transposes (lesgo_gpu_comm_p2p_export / _import)
+    double* p2p_buf = nullptr;             // [pencil buffer | return buffer], nproc blocks each
+    size_t p2p_half = 0;                   // doubles per half
+    double* p2p_pencil[8] = {nullptr};     // peers' pencil buffers in this rank's address space
+    double* p2p_ret[8] = {nullptr};
+    double* p2p_flag = nullptr;            // device scalar for the stream-ordered barrier
+    bool p2p_on = false;
     // actuator disks (lesgo_gpu_turbines_init)
     TurbSet turb;
     bool turb_on = false, turb_fz = false;
@@ -866,6 +874,17 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         PencilGeom g;
         g.lh = c->lh; g.ny = c->ny; g.ld = c->ld; g.nz = nz; g.nproc = c->d.nproc; g.coord = c->d.coord;
         g.cy = c->ny / c->d.nproc; g.plane = c->plane; g.kxs = c->kxs; g.kys = c->kys; g.dz = c->d.dz;
+        g.p2p = c->p2p_on ? 1 : 0;
+        for (int q = 0; q < 8; ++q) { g.pencil[q] = c->p2p_pencil[q]; g.ret[q] = c->p2p_ret[q]; }
+        // stream-ordered barrier of the peer-memory path: every rank's pushes are complete (kernel boundary)
+        // before any rank's next kernel reads them
+        auto barrier = [&]() -> int {
+            ProfScope ps_(c, "p2p_barrier");
+            if (c->comm->allreduce_sum_dev(c->p2p_flag, 1, c->stream)) return c->fail(c->comm->error());
+            return 0;
+        };
+        double* pencil = c->p2p_on ? c->p2p_buf : c->sa[5];
+        double* ret = c->p2p_on ? c->p2p_buf + c->p2p_half : c->sa[4];
         {   // rH_z(1) of coord+1 -> rH_z(nz) of coord                             :184-185
             const double* sb[1] = {c->sa[2] + c->plane};
             double* rb[1] = {c->sa[2] + c->plane * nz};
@@ -886,23 +905,25 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
                       c->sa[1], c->sa[2], c->sa[3] + c->plane, c->sa[3] + c->plane * nz, c->sa[4]);
             c->launches++;
         }
-        {
+        if (c->p2p_on) { if (barrier()) return 1; }
+        else {
             ProfScope ps_(c, "alltoall");
             if (c->comm->alltoall(c->sa[4], c->sa[5], size_t(g.block()), c->stream)) return c->fail(c->comm->error());
         }
         {
             const int nm = (c->lh - 1) * g.cy;
             ProfScope ps_(c, "tridag");
-            LG_LAUNCH(k_tridag_pencil, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, c->sa[5]);
+            LG_LAUNCH(k_tridag_pencil, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, pencil);
             c->launches++;
         }
-        {
+        if (c->p2p_on) { if (barrier()) return 1; }
+        else {
             ProfScope ps_(c, "alltoall");
             if (c->comm->alltoall(c->sa[5], c->sa[4], size_t(g.block()), c->stream)) return c->fail(c->comm->error());
         }
         {
             ProfScope ps_(c, "press_unpack");
-            LG_LAUNCH(k_press_unpack, dim3(grid1d(long(c->lh) * c->ny * nz)), dim3(kBlock), 0, c->stream, g, c->sa[4], c->sa[3]);
+            LG_LAUNCH(k_press_unpack, dim3(grid1d(long(c->lh) * c->ny * nz)), dim3(kBlock), 0, c->stream, g, ret, c->sa[3]);
             c->launches++;
         }
         phat = c->sa[3];
@@ -2059,6 +2080,88 @@ int lesgo_gpu_comm_init(lesgo_gpu_ctx* c, const void* id128) {
     std::string e;
     c->comm = lg::Comm::create(id128, c->d.coord, c->d.nproc, &e);
     if (!c->comm) return c->fail(e);
+    return 0;
+}
+
+// ---- peer-memory transposes of the pressure solve -------------------------------------------------------
+// Each rank owns one allocation [pencil | return] of 2 * nproc blocks; the other ranks map it (same
+// process: peer access; other process: CUDA IPC) and the assembly / Thomas kernels store into it directly.
+namespace {
+struct P2PBlob {                 // 128 bytes, exchanged by the host like the NCCL id
+    long long pid;
+    int device, rank;
+    unsigned long long ptr;
+    unsigned long long doubles;  // size of one half
+    unsigned char ipc[64];
+    unsigned char pad[128 - 8 - 8 - 8 - 8 - 64];
+};
+static_assert(sizeof(P2PBlob) == 128, "blob is 128 bytes");
+}  // namespace
+
+int lesgo_gpu_comm_p2p_export(lesgo_gpu_ctx* c, void* blob128) {
+    ENTER(c);
+    if (!c || !blob128) return 1;
+    if (c->d.nproc < 2 || c->d.nproc > 8) return c->fail("peer-memory transposes need 2..8 ranks on one node");
+    if (c->ny % c->d.nproc) return c->fail("press_stag_array: ny must be divisible by nproc");
+    const size_t half = size_t(c->nz) * (c->ny / c->d.nproc) * c->ld * c->d.nproc;
+    if (!c->p2p_buf) {
+        if (dev_alloc(c, &c->p2p_buf, 2 * half)) return 1;
+        if (dev_alloc(c, &c->p2p_flag, 1)) return 1;
+        c->p2p_half = half;
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    P2PBlob b;
+    std::memset(&b, 0, sizeof(b));
+    b.pid = (long long)getpid(); b.device = c->device; b.rank = c->d.coord;
+    b.ptr = (unsigned long long)(uintptr_t)c->p2p_buf; b.doubles = half;
+#ifndef LESGO_EMUL
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->p2p_buf));
+    static_assert(sizeof(h) <= sizeof(b.ipc), "ipc handle fits");
+    std::memcpy(b.ipc, &h, sizeof(h));
+#endif
+    std::memcpy(blob128, &b, sizeof(b));
+    return 0;
+}
+
+int lesgo_gpu_comm_p2p_import(lesgo_gpu_ctx* c, const void* blobs) {
+    ENTER(c);
+    if (!c || !blobs) return 1;
+    if (!c->p2p_buf) return c->fail("lesgo_gpu_comm_p2p_export first");
+    if (!c->comm) return c->fail("lesgo_gpu_comm_init first (the barrier of the peer-memory path rides on it)");
+    const P2PBlob* b = static_cast<const P2PBlob*>(blobs);
+    for (int q = 0; q < c->d.nproc; ++q) {
+        if (b[q].rank != q || b[q].doubles != c->p2p_half) return c->fail("lesgo_gpu_comm_p2p_import: blobs out of order or other grid");
+        double* base = nullptr;
+        if (q == c->d.coord) base = c->p2p_buf;
+        else if (b[q].pid == (long long)getpid()) {
+            base = reinterpret_cast<double*>(uintptr_t(b[q].ptr));
+#ifndef LESGO_EMUL
+            if (b[q].device != c->device) {
+                int ok = 0;
+                CK(cudaDeviceCanAccessPeer(&ok, c->device, b[q].device));
+                if (!ok) return c->fail("no peer access between the GPUs of ranks " + std::to_string(c->d.coord) + " and " + std::to_string(q));
+                cudaError_t e = cudaDeviceEnablePeerAccess(b[q].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return c->fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+#endif
+        } else {
+#ifndef LESGO_EMUL
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, b[q].ipc, sizeof(h));
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return c->fail(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            base = static_cast<double*>(p);
+#else
+            return c->fail("emulator: ranks must be threads of one process");
+#endif
+        }
+        c->p2p_pencil[q] = base;
+        c->p2p_ret[q] = base + c->p2p_half;
+    }
+    c->p2p_on = true;
     return 0;
 }
 

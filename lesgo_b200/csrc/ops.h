@@ -545,6 +545,11 @@ struct PencilGeom {
     int cy;                 // ky rows per pencil chunk = ny / nproc
     long plane;             // ld * ny
     double kxs, kys, dz;
+    // peer-memory transposes (lesgo_gpu_comm_p2p_import): pencil[q] / ret[q] are rank q's receive buffers of
+    // the forward / return transpose, mapped into this rank's address space (NVLink P2P); null = NCCL path
+    double* pencil[8];
+    double* ret[8];
+    int p2p;
     LG_HD long block() const { return long(nz) * cy * ld; }     // doubles per (src, dst) block
 };
 
@@ -580,7 +585,10 @@ static __global__ void k_press_pack(PencilGeom g, const double* __restrict__ Hx,
             v.y = dadd(dadd(dmul(hx.x, kx), dmul(hy.x, ky)), dmul(dsub(hz.y, hzm.y), c4));
         }
         const int q = jy / g.cy, jl = jy % g.cy;
-        *reinterpret_cast<double2*>(buf + q * g.block() + (long(i) * g.cy + jl) * g.ld + 2 * jx) = v;
+        // NCCL path: into the local send buffer, block q.  Peer-memory path: the assembly kernel IS the
+        // transpose -- the value goes straight into block `coord` of rank q's pencil buffer over NVLink.
+        double* dst = g.p2p ? g.pencil[q] + g.coord * g.block() : buf + q * g.block();
+        *reinterpret_cast<double2*>(dst + (long(i) * g.cy + jl) * g.ld + 2 * jx) = v;
     }
 }
 
@@ -631,17 +639,29 @@ static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __re
         }
         return buf + r * g.block() + i * rs + mo;
     };
+    // where the FINAL value of global row gj goes: in place (NCCL path, the return all-to-all moves it), or
+    // straight into block `coord` of the owning rank's return buffer (peer-memory path)
+    auto fin = [&](int gj) -> double* {
+        int r, i;
+        if (gj <= g.nz) { r = 0; i = gj - 1; }
+        else {
+            r = (gj - 2) / (g.nz - 1);
+            if (r > g.nproc - 1) r = g.nproc - 1;
+            i = gj - r * (g.nz - 1) - 2;
+        }
+        return (g.p2p ? g.ret[r] + g.coord * g.block() : buf + r * g.block()) + i * rs + mo;
+    };
     if (jx == 0 && jy == 0) {
         // zero-wavenumber chain (press_stag_array.f90:226-234): row 1 holds -dz*rbottomw = p(1),
         // rows 2..nzt hold H_z(0,0,k); p(k) is system row k+1.
         double carry = *at(1);                                    // p(1) = 0 - dz*rbottomw
-        *at(1) = 0.0;                                             // p(0) = 0
+        *fin(1) = 0.0;                                            // p(0) = 0
         for (int k = 2; k <= nzt; ++k) {
             const double h = *at(k);
-            *at(k) = carry;                                       // row k = p(k-1)
+            *fin(k) = carry;                                      // row k = p(k-1)
             carry = dadd(carry, dmul(h, g.dz));
         }
-        *at(n) = carry;                                           // row n = p(nzt)
+        *fin(n) = carry;                                          // row n = p(nzt)
         return;
     }
     const double c3 = ddiv(1.0, dmul(g.dz, g.dz));
@@ -675,6 +695,7 @@ static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __re
             }
         }
     }
+    if (g.p2p) *fin(n) = u;                                       // row n is final after the forward sweep
     for (int j0 = n - 1; j0 >= 1; j0 -= UN) {
         double* pj[UN];
         double r[UN], gm[UN];
@@ -688,7 +709,7 @@ static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __re
             const int j = j0 - q;
             if (j >= 1) {
                 u = dsub(r[q], dmul(gm[q], u));
-                *pj[q] = u;
+                *(g.p2p ? fin(j) : pj[q]) = u;
             }
         }
     }

@@ -76,6 +76,8 @@ SYMBOLS = {
     "lesgo_gpu_turbines_forcing": (C.c_int, [_P, C.c_double, _D, _D, _D]),
     "lesgo_gpu_comm_unique_id": (C.c_int, [_P]),
     "lesgo_gpu_comm_init": (C.c_int, [_P, _P]),
+    "lesgo_gpu_comm_p2p_export": (C.c_int, [_P, _P]),
+    "lesgo_gpu_comm_p2p_import": (C.c_int, [_P, _P]),
     "lesgo_gpu_sync_real_array": (C.c_int, [_P, _D, C.c_int]),
 }
 

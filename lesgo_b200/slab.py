@@ -113,4 +113,10 @@ def bootstrap_comm(core, dist) -> bytes:
     if not isinstance(ident[0], (bytes, bytearray)) or len(ident[0]) != 128:
         raise RuntimeError("unique id broadcast failed")
     core.comm_init(bytes(ident[0]))
+    # peer-memory pressure transposes (LESGO_P2P=0: keep the NCCL all-to-alls)
+    import os
+    if os.environ.get("LESGO_P2P", "1") != "0" and 2 <= dist.get_world_size() <= 8:
+        blobs = [None] * dist.get_world_size()
+        dist.all_gather_object(blobs, core.comm_p2p_export())
+        core.comm_p2p_import([bytes(b) for b in blobs])
     return bytes(ident[0])

@@ -321,7 +321,7 @@ def farm_for_rank(farm, p):
 
 
 def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core", lasd=False,
-                          turbines=False, tavg=False):
+                          turbines=False, tavg=False, p2p=False):
     """nproc ranks (threads of this process, one Core each) advance `nsteps` core steps;
     the gathered result must match the SINGLE-slab oracle (which the multi-slab oracle
     equals, tests/test_oracle_kat.py)."""
@@ -353,11 +353,16 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
     cores = [lesgo_b200.Core(make_dims(p, device=(device_of(p.coord) if device_of else -1)), lib=lib) for p in ps]
     ident = cores[0].comm_unique_id()
     res, err = [None] * nproc, [None] * nproc
+    blobs, bar = [None] * nproc, threading.Barrier(nproc)
 
     def work(r):
         try:
             p, c = ps[r], cores[r]
             c.comm_init(ident)
+            if p2p:     # pressure transposes over peer memory instead of NCCL all-to-alls
+                blobs[r] = c.comm_p2p_export()
+                bar.wait(timeout=600)
+                c.comm_p2p_import(blobs)
             for n, g in (("u", ug), ("v", vg), ("w", wg)):
                 c.upload(n, O.scatter_slab(g, p))
             for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz") + (("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2") if lasd else ()):

@@ -73,6 +73,16 @@ def test_emul_full_step(cfg):
     print(out)
 
 
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_emul_multirank_p2p_transposes(nproc):
+    """Pressure transposes through peer memory (remote stores from the assembly and Thomas kernels)."""
+    from helpers import check_multirank_steps
+    kw = dict(nx=16, ny=16, Nz=8, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5,
+              use_mean_p_force=True, mean_p_force_x=1.0)
+    out = check_multirank_steps(emul_library(), kw, nproc, nsteps=3, p2p=True)
+    print(out)
+
+
 def test_emul_multirank_full_step():
     from helpers import check_multirank_steps
     kw = dict(nx=16, ny=16, Nz=8, lbc_mom=2, ubc_mom=2, sgs=True, sgs_model=1, molec=False,

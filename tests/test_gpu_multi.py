@@ -50,3 +50,16 @@ def test_multi_gpu_turbines():
     out = check_multirank_steps(lesgo_b200.load_library(), kw, 2, nsteps=2, tol=1e-11, mode="full", turbines=True, tavg=True,
                                 device_of=lambda coord: coord)
     print(out)
+
+
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_multi_gpu_p2p_transposes(nproc):
+    """The pressure transposes over NVLink peer memory must give the same bits as the NCCL all-to-alls
+    (both reproduce the single-slab oracle to 1e-11)."""
+    if _ngpu() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    kw = dict(nx=64, ny=64, Nz=32, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5,
+              use_mean_p_force=True, mean_p_force_x=1.0)
+    out = check_multirank_steps(lesgo_b200.load_library(), kw, nproc, nsteps=3, tol=1e-11, p2p=True,
+                                device_of=lambda coord: coord)
+    print(nproc, out)

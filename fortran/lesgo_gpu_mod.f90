@@ -43,6 +43,16 @@ interface
         type(c_ptr), value :: ctx
         character(kind=c_char), intent(in) :: id(128)
     end function
+    integer(c_int) function lesgo_gpu_comm_p2p_export(ctx, blob) bind(c, name='lesgo_gpu_comm_p2p_export')
+        import
+        type(c_ptr), value :: ctx
+        character(kind=c_char) :: blob(128)
+    end function
+    integer(c_int) function lesgo_gpu_comm_p2p_import(ctx, blobs) bind(c, name='lesgo_gpu_comm_p2p_import')
+        import
+        type(c_ptr), value :: ctx
+        character(kind=c_char), intent(in) :: blobs(*)
+    end function
     integer(c_int) function lesgo_gpu_wavenumbers(ctx, kx, ky, k2) bind(c, name='lesgo_gpu_wavenumbers')
         import :: c_int, c_ptr, c_double
         type(c_ptr), value :: ctx
@@ -147,7 +157,7 @@ use param, only : comm, ierr
 use mpi
 #endif
 type(lesgo_gpu_dims) :: d
-character(kind=c_char) :: id(128)
+character(kind=c_char) :: id(128), blob(128), blobs(128 * 8)
 if (c_associated(gpu_ctx)) return
 d = lesgo_gpu_dims(nx, ny, nz, nz_tot, nproc, coord, L_x, L_y, dz, lbc_mom, ubc_mom,             &
     merge(1, 0, sgs), -1)
@@ -157,6 +167,12 @@ if (nproc > 1) then
     if (coord == 0) call gpu_check(lesgo_gpu_comm_unique_id(id), 'lesgo_gpu_comm_unique_id')
     call mpi_bcast(id, 128, MPI_CHARACTER, 0, comm, ierr)
     call gpu_check(lesgo_gpu_comm_init(gpu_ctx, id), 'lesgo_gpu_comm_init')
+    ! pressure transposes over NVLink peer memory (one node): gather every rank's 128-byte export
+    if (nproc <= 8) then
+        call gpu_check(lesgo_gpu_comm_p2p_export(gpu_ctx, blob), 'lesgo_gpu_comm_p2p_export')
+        call mpi_allgather(blob, 128, MPI_CHARACTER, blobs, 128, MPI_CHARACTER, comm, ierr)
+        call gpu_check(lesgo_gpu_comm_p2p_import(gpu_ctx, blobs), 'lesgo_gpu_comm_p2p_import')
+    end if
 end if
 #endif
 end subroutine gpu_require

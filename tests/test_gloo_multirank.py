@@ -37,6 +37,13 @@ class FakeCore:
     def comm_init(self, ident):
         self.got = ident
 
+    # peer-memory bootstrap: every rank must receive all exports, in rank order
+    def comm_p2p_export(self):
+        return bytes([self.rank]) * 128
+
+    def comm_p2p_import(self, blobs):
+        self.blobs = blobs
+
 
 def _worker(rank, world, port, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -46,6 +53,7 @@ def _worker(rank, world, port, tmp):
         core = FakeCore(rank)
         ident = slab.bootstrap_comm(core, dist)
         assert core.got == ident == bytes((7 * i + 3) % 256 for i in range(128))
+        assert core.blobs == [bytes([r]) * 128 for r in range(world)]
         # (2) decomposition + comm: two oracle steps over gloo
         pg = O.Params(nproc=1, **KW)
         ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=world, seed=3, amp=0.3)

@@ -428,6 +428,9 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"LES channel core timestep {nx}x{ny}x{Nz} FP64 (device-resident)",
                            "grid": [nx, ny, Nz], "decomposition": f"z-slabs x{world}",
+                           "pressure_transposes": ("n/a" if world == 1 else
+                                                   ("NVLink peer-memory stores" if getattr(core, "p2p_enabled", False)
+                                                    else "NCCL all-to-all")),
                            "l2": "inputs larger than L2 (%.0f MB per field)" % (np.prod(dims.shape) * 8 / 1e6)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "kernels": kernels, "max_cfl": cfl, "full_step": full, "lasd_step": lasd, "turbines_step": turb, "tavg": tavg}

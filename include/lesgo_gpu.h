@@ -210,7 +210,9 @@ int lesgo_gpu_comm_init(lesgo_gpu_ctx* ctx, const void* id128);
  * and the Thomas kernel stores p_hat straight into the slab owners' buffers, so packing, transfer and unpacking
  * cost no pass of their own.  Every rank exports a 128-byte blob, the host gathers them in rank order
  * (MPI_Allgather / torch.distributed) and every rank imports all nproc blobs (after lesgo_gpu_comm_init).
- * Ranks may be threads of one process (peer access) or separate processes (CUDA IPC). */
+ * Ranks may be threads of one process (peer access) or separate processes (CUDA IPC).  Importing NULL switches
+ * back to the NCCL all-to-alls (all ranks must agree: a host that sees the import fail on any rank disables it
+ * on every rank). */
 int lesgo_gpu_comm_p2p_export(lesgo_gpu_ctx* ctx, void* blob128);
 int lesgo_gpu_comm_p2p_import(lesgo_gpu_ctx* ctx, const void* blobs128_times_nproc);
 /* mpi_sync_real_array(var, 0, isync), mpi_defs.f90:167-264: isync 1 = DOWN, 2 = UP, 3 = DOWNUP */

@@ -346,9 +346,14 @@ class Core:
 
     def comm_p2p_import(self, blobs):
         """blobs: the nproc 128-byte exports in rank order; switches the pressure transposes to peer memory."""
+        if blobs is None:                       # back to the NCCL all-to-alls
+            self._ck(self.lib.comm_p2p_import(self._ctx, None), "comm_p2p_import")
+            self.p2p_enabled = False
+            return
         raw = b"".join(blobs)
         buf = C.create_string_buffer(raw, len(raw))
         self._ck(self.lib.comm_p2p_import(self._ctx, buf), "comm_p2p_import")
+        self.p2p_enabled = True
 
     def sync_real_array(self, var, isync=3):
         self._ck(self.lib.sync_real_array(self._ctx, _addr(var, self.dims.shape, True), int(isync)), "sync_real_array")

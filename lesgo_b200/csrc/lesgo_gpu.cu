@@ -2126,7 +2126,8 @@ int lesgo_gpu_comm_p2p_export(lesgo_gpu_ctx* c, void* blob128) {
 
 int lesgo_gpu_comm_p2p_import(lesgo_gpu_ctx* c, const void* blobs) {
     ENTER(c);
-    if (!c || !blobs) return 1;
+    if (!c) return 1;
+    if (!blobs) { c->p2p_on = false; return 0; }                 // back to the NCCL all-to-alls
     if (!c->p2p_buf) return c->fail("lesgo_gpu_comm_p2p_export first");
     if (!c->comm) return c->fail("lesgo_gpu_comm_init first (the barrier of the peer-memory path rides on it)");
     const P2PBlob* b = static_cast<const P2PBlob*>(blobs);

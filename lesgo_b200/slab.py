@@ -116,7 +116,27 @@ def bootstrap_comm(core, dist) -> bytes:
     # peer-memory pressure transposes (LESGO_P2P=0: keep the NCCL all-to-alls)
     import os
     if os.environ.get("LESGO_P2P", "1") != "0" and 2 <= dist.get_world_size() <= 8:
-        blobs = [None] * dist.get_world_size()
-        dist.all_gather_object(blobs, core.comm_p2p_export())
-        core.comm_p2p_import([bytes(b) for b in blobs])
+        # collective and all-or-nothing: a rank that cannot export or map a peer buffer (no peer access,
+        # IPC refused) makes EVERY rank stay on the NCCL path, otherwise the ranks would disagree and hang
+        world = dist.get_world_size()
+        try:
+            mine, err = core.comm_p2p_export(), None
+        except Exception as e:  # noqa
+            mine, err = None, str(e)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, mine)
+        ok = all(b is not None for b in blobs)
+        if ok:
+            try:
+                core.comm_p2p_import([bytes(b) for b in blobs])
+            except Exception as e:  # noqa
+                ok, err = False, str(e)
+        oks = [None] * world
+        dist.all_gather_object(oks, ok)
+        if not all(oks):
+            core.comm_p2p_import(None)
+            if dist.get_rank() == 0:
+                import sys
+                print(f"[lesgo_b200] peer-memory transposes unavailable ({err or 'another rank failed'}): "
+                      "using NCCL all-to-alls", file=sys.stderr)
     return bytes(ident[0])

@@ -42,7 +42,8 @@ class FakeCore:
         return bytes([self.rank]) * 128
 
     def comm_p2p_import(self, blobs):
-        self.blobs = blobs
+        if blobs is not None:
+            self.blobs = blobs
 
 
 def _worker(rank, world, port, tmp):

@@ -207,7 +207,7 @@ int lesgo_gpu_comm_unique_id(void* id128);
 int lesgo_gpu_comm_init(lesgo_gpu_ctx* ctx, const void* id128);
 /* Optional, one node: the two transposes of the pressure solve go over NVLink peer memory instead of NCCL
  * all-to-alls -- the right-hand-side assembly kernel stores straight into the pencil buffers of the other GPUs
- * and the Thomas kernel stores p_hat straight into the slab owners' buffers, so packing, transfer and unpacking
+ * and the unpacking kernel loads p_hat straight out of the buffers of the GPUs that solved it, so the transfers
  * cost no pass of their own.  Every rank exports a 128-byte blob, the host gathers them in rank order
  * (MPI_Allgather / torch.distributed) and every rank imports all nproc blobs (after lesgo_gpu_comm_init).
  * Ranks may be threads of one process (peer access) or separate processes (CUDA IPC).  Importing NULL switches

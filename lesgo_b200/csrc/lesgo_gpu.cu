@@ -78,6 +78,7 @@ struct lesgo_gpu_ctx {
     double* p2p_ret[8] = {nullptr};
     double* p2p_flag = nullptr;            // device scalar for the stream-ordered barrier
     bool p2p_on = false;
+    int p2p_parity = 0;
     // actuator disks (lesgo_gpu_turbines_init)
     TurbSet turb;
     bool turb_on = false, turb_fz = false;
@@ -875,7 +876,11 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         g.lh = c->lh; g.ny = c->ny; g.ld = c->ld; g.nz = nz; g.nproc = c->d.nproc; g.coord = c->d.coord;
         g.cy = c->ny / c->d.nproc; g.plane = c->plane; g.kxs = c->kxs; g.kys = c->kys; g.dz = c->d.dz;
         g.p2p = c->p2p_on ? 1 : 0;
-        for (int q = 0; q < 8; ++q) { g.pencil[q] = c->p2p_pencil[q]; g.ret[q] = c->p2p_ret[q]; }
+        // the two halves of every rank's buffer alternate from call to call: a rank may already push the next
+        // solve's rows into a peer while a third rank is still pulling the previous result out of it
+        const int par = c->p2p_parity;
+        if (c->p2p_on) c->p2p_parity ^= 1;
+        for (int q = 0; q < 8; ++q) { g.pencil[q] = par ? c->p2p_ret[q] : c->p2p_pencil[q]; g.ret[q] = nullptr; }
         // stream-ordered barrier of the peer-memory path: every rank's pushes are complete (kernel boundary)
         // before any rank's next kernel reads them
         auto barrier = [&]() -> int {
@@ -883,8 +888,8 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
             if (c->comm->allreduce_sum_dev(c->p2p_flag, 1, c->stream)) return c->fail(c->comm->error());
             return 0;
         };
-        double* pencil = c->p2p_on ? c->p2p_buf : c->sa[5];
-        double* ret = c->p2p_on ? c->p2p_buf + c->p2p_half : c->sa[4];
+        double* pencil = c->p2p_on ? c->p2p_buf + (par ? c->p2p_half : 0) : c->sa[5];
+        double* ret = c->sa[4];                                   // NCCL path only
         {   // rH_z(1) of coord+1 -> rH_z(nz) of coord                             :184-185
             const double* sb[1] = {c->sa[2] + c->plane};
             double* rb[1] = {c->sa[2] + c->plane * nz};
@@ -913,7 +918,9 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         {
             const int nm = (c->lh - 1) * g.cy;
             ProfScope ps_(c, "tridag");
-            LG_LAUNCH(k_tridag_pencil, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, pencil);
+            PencilGeom gl = g;
+            gl.p2p = 0;                                           // the sweep is local and in place on both paths
+            LG_LAUNCH(k_tridag_pencil, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, gl, c->nzt, c->gam, pencil);
             c->launches++;
         }
         if (c->p2p_on) { if (barrier()) return 1; }

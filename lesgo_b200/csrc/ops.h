@@ -725,7 +725,11 @@ static __global__ void k_press_unpack(PencilGeom g, const double* __restrict__ b
         const int jy = int(r % g.ny), i = int(r / g.ny);
         const int k = i + (bottom ? 0 : 1);                       // plane = local row - 1
         const int q = jy / g.cy, jl = jy % g.cy;
-        double2 v = ld2(buf + q * g.block() + (long(i) * g.cy + jl) * g.ld + 2 * jx);
+        // NCCL path: block q of the local return buffer.  Peer-memory path: PULL block `coord` of rank q's
+        // pencil buffer, where its Thomas sweep left p_hat in place (this kernel has the parallelism to hide
+        // the NVLink load latency; the latency-bound sweep keeps purely local accesses)
+        const double* src = g.p2p ? g.pencil[q] + g.coord * g.block() : buf + q * g.block();
+        double2 v = ld2(src + (long(i) * g.cy + jl) * g.ld + 2 * jx);
         *reinterpret_cast<double2*>(p + long(k) * g.plane + long(jy) * g.ld + 2 * jx) = v;
     }
 }

@@ -72,10 +72,10 @@ struct lesgo_gpu_ctx {
     double* tavg_tmp[5] = {nullptr};       // w_uv, u_w, v_w, vortz, fza_uv
     double tavg_time = 0.0;
     // peer-memory pressure transposes (lesgo_gpu_comm_p2p_export / _import)
-    double* p2p_buf = nullptr;             // [pencil buffer | return buffer], nproc blocks each
+    double* p2p_buf = nullptr;             // two pencil buffers (alternating between solves), nproc blocks each
     size_t p2p_half = 0;                   // doubles per half
     double* p2p_pencil[8] = {nullptr};     // peers' pencil buffers in this rank's address space
-    double* p2p_ret[8] = {nullptr};
+    double* p2p_alt[8] = {nullptr};        // ... and their second halves
     double* p2p_flag = nullptr;            // device scalar for the stream-ordered barrier
     bool p2p_on = false;
     int p2p_parity = 0;
@@ -880,7 +880,7 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         // solve's rows into a peer while a third rank is still pulling the previous result out of it
         const int par = c->p2p_parity;
         if (c->p2p_on) c->p2p_parity ^= 1;
-        for (int q = 0; q < 8; ++q) { g.pencil[q] = par ? c->p2p_ret[q] : c->p2p_pencil[q]; g.ret[q] = nullptr; }
+        for (int q = 0; q < 8; ++q) g.pencil[q] = par ? c->p2p_alt[q] : c->p2p_pencil[q];
         // stream-ordered barrier of the peer-memory path: every rank's pushes are complete (kernel boundary)
         // before any rank's next kernel reads them
         auto barrier = [&]() -> int {
@@ -918,9 +918,8 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         {
             const int nm = (c->lh - 1) * g.cy;
             ProfScope ps_(c, "tridag");
-            PencilGeom gl = g;
-            gl.p2p = 0;                                           // the sweep is local and in place on both paths
-            LG_LAUNCH(k_tridag_pencil, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, gl, c->nzt, c->gam, pencil);
+            // the sweep is local and in place on both paths
+            LG_LAUNCH(k_tridag_pencil, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, pencil);
             c->launches++;
         }
         if (c->p2p_on) { if (barrier()) return 1; }
@@ -1848,12 +1847,11 @@ struct RecordIO {
     FILE* f; bool writing; long long total, done = 0, sub_left = 0, maxsub; bool first = true;
     std::string err;
     RecordIO(FILE* f_, bool w, long long tot) : f(f_), writing(w), total(tot), maxsub(subrecord_max()) {}
-    bool marker(int v, bool check_sign_only = false) {
+    bool marker(int v) {
         if (writing) return std::fwrite(&v, 4, 1, f) == 1;
         int r = 0;
         if (std::fread(&r, 4, 1, f) != 1) { err = "unexpected end of file"; return false; }
         if (r != v) { err = "record length " + std::to_string(r) + " where " + std::to_string(v) + " was expected (other grid or byte order?)"; return false; }
-        (void)check_sign_only;
         return true;
     }
     bool open_sub() {
@@ -2091,8 +2089,9 @@ int lesgo_gpu_comm_init(lesgo_gpu_ctx* c, const void* id128) {
 }
 
 // ---- peer-memory transposes of the pressure solve -------------------------------------------------------
-// Each rank owns one allocation [pencil | return] of 2 * nproc blocks; the other ranks map it (same
-// process: peer access; other process: CUDA IPC) and the assembly / Thomas kernels store into it directly.
+// Each rank owns one allocation of two pencil buffers (nproc blocks each, alternating between solves); the other
+// ranks map it (same process: peer access; other process: CUDA IPC): the assembly kernel stores into it, the
+// unpack kernel loads from it.
 namespace {
 struct P2PBlob {                 // 128 bytes, exchanged by the host like the NCCL id
     long long pid;
@@ -2167,7 +2166,7 @@ int lesgo_gpu_comm_p2p_import(lesgo_gpu_ctx* c, const void* blobs) {
 #endif
         }
         c->p2p_pencil[q] = base;
-        c->p2p_ret[q] = base + c->p2p_half;
+        c->p2p_alt[q] = base + c->p2p_half;
     }
     c->p2p_on = true;
     return 0;

@@ -545,10 +545,9 @@ struct PencilGeom {
     int cy;                 // ky rows per pencil chunk = ny / nproc
     long plane;             // ld * ny
     double kxs, kys, dz;
-    // peer-memory transposes (lesgo_gpu_comm_p2p_import): pencil[q] / ret[q] are rank q's receive buffers of
-    // the forward / return transpose, mapped into this rank's address space (NVLink P2P); null = NCCL path
+    // peer-memory transposes (lesgo_gpu_comm_p2p_import): pencil[q] is rank q's pencil buffer of this solve,
+    // mapped into this rank's address space (NVLink P2P); p2p = 0: NCCL path
     double* pencil[8];
-    double* ret[8];
     int p2p;
     LG_HD long block() const { return long(nz) * cy * ld; }     // doubles per (src, dst) block
 };
@@ -639,29 +638,17 @@ static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __re
         }
         return buf + r * g.block() + i * rs + mo;
     };
-    // where the FINAL value of global row gj goes: in place (NCCL path, the return all-to-all moves it), or
-    // straight into block `coord` of the owning rank's return buffer (peer-memory path)
-    auto fin = [&](int gj) -> double* {
-        int r, i;
-        if (gj <= g.nz) { r = 0; i = gj - 1; }
-        else {
-            r = (gj - 2) / (g.nz - 1);
-            if (r > g.nproc - 1) r = g.nproc - 1;
-            i = gj - r * (g.nz - 1) - 2;
-        }
-        return (g.p2p ? g.ret[r] + g.coord * g.block() : buf + r * g.block()) + i * rs + mo;
-    };
     if (jx == 0 && jy == 0) {
         // zero-wavenumber chain (press_stag_array.f90:226-234): row 1 holds -dz*rbottomw = p(1),
         // rows 2..nzt hold H_z(0,0,k); p(k) is system row k+1.
         double carry = *at(1);                                    // p(1) = 0 - dz*rbottomw
-        *fin(1) = 0.0;                                            // p(0) = 0
+        *at(1) = 0.0;                                             // p(0) = 0
         for (int k = 2; k <= nzt; ++k) {
             const double h = *at(k);
-            *fin(k) = carry;                                      // row k = p(k-1)
+            *at(k) = carry;                                       // row k = p(k-1)
             carry = dadd(carry, dmul(h, g.dz));
         }
-        *fin(n) = carry;                                          // row n = p(nzt)
+        *at(n) = carry;                                           // row n = p(nzt)
         return;
     }
     const double c3 = ddiv(1.0, dmul(g.dz, g.dz));
@@ -695,7 +682,6 @@ static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __re
             }
         }
     }
-    if (g.p2p) *fin(n) = u;                                       // row n is final after the forward sweep
     for (int j0 = n - 1; j0 >= 1; j0 -= UN) {
         double* pj[UN];
         double r[UN], gm[UN];
@@ -709,7 +695,7 @@ static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __re
             const int j = j0 - q;
             if (j >= 1) {
                 u = dsub(r[q], dmul(gm[q], u));
-                *(g.p2p ? fin(j) : pj[q]) = u;
+                *pj[q] = u;
             }
         }
     }

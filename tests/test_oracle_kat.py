@@ -288,3 +288,111 @@ def test_convec_against_pointwise_cross_product():
     assert rel(Rz[1:nz, :, X], ez[1:nz, :, X]) < 1e-13
     assert np.abs(Rz[nz, :, X]).max() == 0.0 and np.abs(Rz[1, :, X]).max() == 0.0
     assert Rx[nz, 0, 0] == O.BOGUS and Rx[0, 0, 0] == O.BOGUS
+
+
+# ---- rows (f)-2 .. (f)-4: properties that do not depend on the oracle's own code path ---------------
+def test_trilinear_interp_is_exact_for_linear_fields_and_wraps():
+    """functions.f90:349-454: trilinear interpolation reproduces a + b z exactly (x, y enter only through the
+    periodic wrap) and is periodic in x and y."""
+    p = O.Params(nx=16, ny=12, Nz=8, lbc_mom=0, ubc_mom=0, L_x=3.0, L_y=2.0)
+    z, zw = O._grid_z(p)
+    var = np.zeros((p.nz + 1, p.ny, p.nx)) + (2.0 + 0.7 * zw)[:, None, None]
+    rng = np.random.default_rng(1)
+    x0 = rng.uniform(-1.0, p.L_x + 1.0, (p.ny, p.nx)); y0 = rng.uniform(-1.0, p.L_y + 1.0, (p.ny, p.nx))
+    z0 = rng.uniform(zw[1], zw[p.nz - 1], (p.ny, p.nx))
+    got = O.trilinear_interp_w(var, p, x0, y0, z0)
+    assert np.abs(got - (2.0 + 0.7 * z0)).max() < 1e-13
+    var = rng.standard_normal((p.nz + 1, p.ny, p.nx))
+    a = O.trilinear_interp_w(var, p, x0, y0, z0)
+    b = O.trilinear_interp_w(var, p, x0 + p.L_x, y0 - p.L_y, z0)
+    assert np.abs(a - b).max() < 1e-12
+    # on a grid node the value itself comes back
+    k, j, i = 3, 5, 7
+    one = O.trilinear_interp_w(var, p, np.array([[i * p.dx + 1e-13]]), np.array([[j * p.dy + 1e-13]]), np.array([[zw[k] + 1e-13]]))
+    assert abs(one[0, 0] - var[k, j, i]) < 1e-10
+
+
+def test_interpolag_without_motion_is_the_identity():
+    """interpolag_Sdep.f90: with u = v = w = 0 every departure point is the node itself."""
+    p = O.Params(nx=16, ny=16, Nz=8, lbc_mom=0, ubc_mom=0)
+    s = O.State(p)
+    O.lasd_alloc(s)
+    rng = np.random.default_rng(2)
+    for n in ("F_LM", "F_MM", "F_QN", "F_NN"):
+        getattr(s, n)[...] = rng.uniform(0.5, 1.5, s.u.shape)
+    before = {n: getattr(s, n).copy() for n in ("F_LM", "F_MM", "F_QN", "F_NN")}
+    O.interpolag_Sdep(s, p, O.LocalComm(), lagran_dt=0.01)
+    for n, b in before.items():
+        assert np.abs(getattr(s, n)[1:, :, :p.nx] - b[1:, :, :p.nx]).max() < 1e-12, n
+
+
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_lasd_multislab_equals_singleslab(nproc):
+    """lagrange_Sdep + interpolag_Sdep on 2 / 4 z-slabs (ghost planes, F_* syncs) == one slab."""
+    kw = dict(nx=16, ny=16, Nz=8, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=5, dt=4e-3)
+
+    def run(p, comm):
+        sp = O.Spectral(p)
+        G, G2 = O.test_filter_kernel(sp), O.test_filter_kernel(sp, alpha=4.0)
+        ug, vg, wg = O.synthetic_global(p.nx, p.ny, p.Nz, nproc=p.nproc, seed=9, amp=0.5)
+        s = O.State(p)
+        s.u, s.v, s.w = (O.scatter_slab(f, p) for f in (ug, vg, wg))
+        for it in range(4):
+            jt = it + 1
+            lasd = dict(sp=sp, G_test=G, G_test_test=G2, lagran_dt=2 * p.dt, cs_init=(jt == 1),
+                        update=(jt >= 2 and jt % 2 == 0), init_F=(jt == 2))
+            O.step(s, sp, comm, mode="full", first_step=(it == 0), G_test=G, lasd=lasd)
+        return s
+
+    ref = run(O.Params(nproc=1, **kw), O.LocalComm())
+    ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
+    outs = O.run_ranks(nproc, lambda c, comm: run(ps[c], comm))
+    for n in ("u", "w", "Cs_opt2", "F_LM", "F_NN"):
+        g = O.gather_slabs([getattr(o, n) for o in outs], ps, top_extra=(n != "u"))
+        hi = ps[0].nz_tot if n != "u" else ps[0].nz_tot - 1
+        assert rel(g[1:hi + 1, :, :16], getattr(ref, n)[1:hi + 1, :, :16]) < 1e-12, n
+    assert 0.0 < ref.Cs_opt2[1:, :, :16].mean() < 0.1
+
+
+def test_actuator_disk_integrals():
+    """turbines.f90: the indicator integrates to one, so in a uniform stream the disk velocity is nhat . U and the
+    volume integral of the force is f_n nhat (f_n = -Ct'/2 |u_d_T| u_d_T pi D**2 / 4)."""
+    p = O.Params(nx=32, ny=32, Nz=16, lbc_mom=1, ubc_mom=1)
+    s = O.State(p)
+    U = (1.3, -0.4, 0.0)
+    s.u[...] = U[0]; s.v[...] = U[1]; s.w[...] = U[2]
+    t = O.Turbine(xloc=0.5 * p.L_x, yloc=0.5 * p.L_y, height=0.5 * p.L_z, dia=0.3 * p.L_y, thk=1.2 * p.dx,
+                  theta1=25.0, theta2=0.0, Ct_prime=1.33, u_d_T=0.0)
+    dlt = 1.5 * math.sqrt(p.dx ** 2 + p.dy ** 2 + p.dz ** 2)
+    O.turbines_nodes(p, [t], O.standin_indicator(t.dia, t.thk, dlt, dlt), O.LocalComm())
+    vol = p.dx * p.dy * p.dz
+    assert abs(t.ind.sum() * vol - 1.0) < 1e-13
+    fx, fy, fz = O.turbines_forcing(s, p, O.LocalComm(), [t], eps=1.0)
+    un = t.nhat[0] * U[0] + t.nhat[1] * U[1]
+    assert abs(t.u_d - un) < 1e-13 and abs(t.u_d_T - un) < 1e-13
+    f_n = -0.5 * 1.33 * abs(un) * un * 0.25 * math.pi * t.dia ** 2
+    assert abs(t.f_n - f_n) < 1e-13
+    assert abs(fx[1:p.nz, :, :p.nx].sum() * vol - f_n * t.nhat[0]) < 1e-12
+    assert abs(fy[1:p.nz, :, :p.nx].sum() * vol - f_n * t.nhat[1]) < 1e-12
+    assert not fz.any()
+
+
+def test_tavg_of_steady_fields():
+    """time_average.f90:176-320: for fields that do not change, every accumulator is (quantity) x (total time)."""
+    p = O.Params(nx=16, ny=16, Nz=6, lbc_mom=0, ubc_mom=0)
+    s = O.State(p)
+    rng = np.random.default_rng(5)
+    for n in ("u", "v", "w", "p", "txx", "txz", "dudz", "dwdx", "dvdx", "dudy"):
+        getattr(s, n)[...] = rng.standard_normal(s.u.shape)
+    t = O.Tavg(p)
+    for dt in (0.1, 0.25, 0.05):
+        O.tavg_compute(t, s, p, O.LocalComm(), dt)
+    T = 0.4
+    assert abs(t.total_time - T) < 1e-15
+    X = slice(0, p.nx)
+    assert rel(t.u, s.u[:, :, X] * T) < 1e-14 and rel(t.u2, s.u[:, :, X] ** 2 * T) < 1e-14
+    assert rel(t.vorty, (s.dudz - s.dwdx)[:, :, X] * T) < 1e-14
+    w_uv = 0.5 * (s.w[2:p.nz + 1] + s.w[1:p.nz])
+    assert rel(t.w_uv[1:p.nz], w_uv[:, :, X] * T) < 1e-14
+    assert rel(t.p[1:p.nz], (s.p[1:p.nz] - 0.5 * (s.u[1:p.nz] ** 2 + w_uv ** 2 + s.v[1:p.nz] ** 2))[:, :, X] * T) < 1e-13
+    assert rel(t.uw[2:p.nz], (0.5 * (s.u[1:p.nz - 1] + s.u[2:p.nz]) * s.w[2:p.nz])[:, :, X] * T) < 1e-13

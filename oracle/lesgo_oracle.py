@@ -13,6 +13,11 @@ forward sign -1, r2c keeps kx = 0..nx/2 of the contiguous dimension, c2r ignores
 imaginary parts of the kx=0 / kx=nx/2 columns after the y pass) is restated with
 `scipy.fft.rfft2 / irfft2(norm="forward")`.
 
+Beyond the core path it restates SURVEY 8(f): wallstress / calc_Sij / sgs_stag / divstress,
+the Lagrangian scale-dependent model (lagrange_Sdep.f90, interpolag_Sdep.f90, trilinear_interp_w),
+actuator disks (turbines_nodes / turbines_forcing -- with a STAND-IN for turbine_indicator.f90's
+start-up convolution, see `standin_indicator`), tavg%compute and the restart record.
+
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl
 reference` leg may import this module.  The product path (`lesgo_b200/`) never does.
 

@@ -7,7 +7,7 @@ used by the tests and the benchmark.  There is no CPU fallback: importing works
 anywhere, but creating a `Core` without the CUDA library or without a GPU raises.
 """
 from .lib import Library, LibraryError, load_library, library_path  # noqa: F401
-from .core import Core, Dims, FIELD_IDS  # noqa: F401
+from .core import Core, Dims, FIELD_IDS, TAVG_IDS  # noqa: F401
 from . import slab  # noqa: F401
 
-__all__ = ["Library", "LibraryError", "load_library", "library_path", "Core", "Dims", "FIELD_IDS"]
+__all__ = ["Library", "LibraryError", "load_library", "library_path", "Core", "Dims", "FIELD_IDS", "TAVG_IDS"]

@@ -508,6 +508,17 @@ def check_checkpoint(make_core, p, tmp_path, monkeypatch):
     core3.checkpoint_read(f3)
     for n in O.CHECKPOINT_FIELDS:
         assert np.array_equal(core3.download(n)[1:], getattr(s, n)[1:]), n
+    # subrecord boundaries at awkward places: one byte short of the record, exactly the record, 8 bytes, a prime
+    total = 11 * p.nz * p.ny * p.ld * 8
+    for lim in (total - 1, total, total + 1, 8, 4099):
+        monkeypatch.setenv("LESGO_SUBRECORD_MAX", str(lim))
+        fx = str(tmp_path / f"vel.sub{lim}.c0")
+        core.checkpoint_write(fx)
+        assert os.path.getsize(fx) == total + 8 * (-(-total // lim)), lim
+        cx = make_core()
+        cx.checkpoint_read(fx)
+        for n in ("u", "F_NN"):
+            assert np.array_equal(cx.download(n)[1:], getattr(s, n)[1:]), (lim, n)
     monkeypatch.delenv("LESGO_SUBRECORD_MAX")
     with pytest_raises_library("record length"):
         core3.checkpoint_read(f3)                               # written with other markers than expected now

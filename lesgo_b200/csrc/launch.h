@@ -1,6 +1,7 @@
 // launch.h -- size-dispatching launchers (explicitly instantiated in x*.cu / ypass.cu so
 // the many template instantiations compile in parallel).
 #pragma once
+#include <atomic>
 #include "ops.h"
 #include "wfft_kernels.h"
 
@@ -23,25 +24,28 @@ bool size_supported(int n_small);
 // radices and stage-twiddle-table length of the plan for complex length n (false if none)
 bool plan_lookup(int n, PlanDesc* out);
 
-// plane pipelines (pipe_kernels.h): 0 = launched, -1 = not available for these lengths
-struct PipeCtl;
-bool pipe_enabled();     // LESGO_PIPE=1 turns them on (off by default: measured slower, profiles/r2_experiments.md)
-int pipe_ring();         // LESGO_PIPE_RING planes (default 4)
-int launch_pipe_deriv(int nx, int ny, bool multi, const ProScale& pro, const XfOut& xo, const YArgs& ya,
-                      const XiSrc& xi, const EpiStore& epi, const PipeCtl& ctl, const cplx* Wx, const cplx* Whx,
-                      const cplx* Wy, cudaStream_t s);
-// fused 3/2-grid x pass of convec (bigx_kernels.h); nx2 = 3 nx / 2
-struct BigxArgs;
-int launch_bigx(int nx2, const BigxArgs& a, const cplx* W, const cplx* Wh, cudaStream_t s);
 // products + forward x transform of convec, marching up z (prodfwd_kernels.h)
 struct ProdArgs;
 int launch_prodfwd(int nx2, const ProdArgs& a, const cplx* W, const cplx* Wh, cudaStream_t s);
-// (nx, ny) pairs the pipelines are instantiated for
-#define LG_PIPE_SIZES(X) X(512, 512) X(1024, 512) X(64, 512)
 
-template <class K> inline void set_smem(K kernel, size_t bytes) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several
+// GPUs (ranks as threads) must set it once on each of them.  Every call site keeps its own
+// bit mask of the device ordinals already served (one static per template instantiation).
+#ifdef LESGO_EMUL
+#define LG_SET_SMEM(kernel, bytes) do { (void)(bytes); } while (0)
+#else
+#define LG_SET_SMEM(kernel, bytes)                                                                  \
+    do {                                                                                            \
+        static std::atomic<unsigned long long> done_{0ull};                                         \
+        int dev_ = 0;                                                                               \
+        cudaGetDevice(&dev_);                                                                       \
+        const unsigned long long bit_ = 1ull << (dev_ & 63);                                        \
+        if (!(done_.load(std::memory_order_acquire) & bit_)) {                                      \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));  \
+            done_.fetch_or(bit_, std::memory_order_release);                                        \
+        }                                                                                           \
+    } while (0)
+#endif
 
 // persistent grids: blocks per SM that fit (shared memory / 64-register budget), times SMs
 int sm_count();

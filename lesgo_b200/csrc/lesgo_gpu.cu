@@ -15,8 +15,6 @@
 #include "../../include/lesgo_gpu.h"
 #include "comm.h"
 #include "launch.h"
-#include "pipe_kernels.h"
-#include "bigx_kernels.h"
 #include "prodfwd_kernels.h"
 #include "lasd_kernels.h"
 #include "turbine_kernels.h"
@@ -58,7 +56,6 @@ struct lesgo_gpu_ctx {
     double* sa[kMaxFields] = {nullptr};    // small spectra / intermediates, (ld, ny, 0:nz)
     double* bb[kMaxFields] = {nullptr};    // big-y intermediates, (ld, ny2, 0:nz)
     double* big[kMaxFields] = {nullptr};   // 3/2-grid physical fields, (ld_big, ny2, 0:nz)
-    double* cc[3] = {nullptr};             // big-y x spectra of the products cx, cy, cz (fused 3/2-grid x pass)
     double* gam = nullptr;                 // tridiagonal gam(j) table (lh, ny, 0:nzt+1)
     double* work[13] = {nullptr};          // S11..S33, Nu_t, six stress-gradient temporaries (mode 1)
     double* lsq = nullptr;                 // l(k)**2 of the Smagorinsky length (nz+1)
@@ -88,7 +85,6 @@ struct lesgo_gpu_ctx {
     double* fields[LG_NFIELDS] = {nullptr};
     std::vector<double*> staging;          // device staging for host-pointer arguments
     std::vector<size_t> staging_bytes;
-    int* pipe_buf = nullptr;               // ticket + completion counters of the plane pipelines
     double* red_dev = nullptr;             // reductions
     double* red_host = nullptr;
     lg::Comm* comm = nullptr;
@@ -518,23 +514,6 @@ int fill(lesgo_gpu_ctx* c, double* f, long plane, int k0, int k1, double v) {
     return 0;
 }
 
-// control block of a plane-pipeline launch: ticket + 3 * nplanes completion counters, zeroed
-int pipe_ctl(lesgo_gpu_ctx* c, PipeCtl* ctl, int nplanes, int k0) {
-    const size_t n = 4 + 3 * size_t(c->nz + 2);
-    if (!c->pipe_buf) {
-        void* q = nullptr;
-        CK(cudaMalloc(&q, n * sizeof(int)));
-        c->allocs.push_back(q);
-        c->pipe_buf = static_cast<int*>(q);
-    }
-    CK(cudaMemsetAsync(c->pipe_buf, 0, n * sizeof(int), c->stream));
-    std::memset(ctl, 0, sizeof(*ctl));
-    ctl->ticket = reinterpret_cast<unsigned*>(c->pipe_buf);
-    ctl->done = c->pipe_buf + 4;
-    ctl->nplanes = nplanes; ctl->k0 = k0; ctl->ring = pipe_ring();
-    return 0;
-}
-
 // ---- derivatives.f90 --------------------------------------------------------------------------
 // which: bit 0 = f itself (filt_da), bit 1 = d/dx, bit 2 = d/dy
 int chunk_of(const lesgo_gpu_ctx* c, int divisor) {
@@ -563,31 +542,6 @@ int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx
     if (dfdx) { a.fld[0].out[n] = YOutSpec{mid(n), Y_IKX}; xs[n] = mid(n); xd[n] = dfdx; ++n; }
     if (dfdy) { a.fld[0].out[n] = YOutSpec{mid(n), Y_IKY}; xs[n] = mid(n); xd[n] = dfdy; ++n; }
     a.nout = n;
-    // plane pipeline: all three passes in one persistent kernel, intermediates in L2-resident rings
-    if (pipe_enabled() && !bigy && !HP(c) && c->chunk <= 0) {
-        int ntr = 0;
-        if (fout || dfdx) ++ntr;
-        if (dfdy) ++ntr;
-        XfOut xo;
-        xo.dst[0] = c->sa[0]; xo.plane = c->plane; xo.row = c->ld; xo.ncol = c->nx / 2; xo.write_nyq = 0;
-        xo.ring = pipe_ring();
-        YArgs ap = a;
-        ap.src_ring = ap.dst_ring = pipe_ring();
-        ap.nfields = 1; ap.nplanes = nz + 1; ap.k0 = 0;
-        XiSrc xi;
-        for (int i = 0; i < n; ++i) xi.src[i] = xs[i];
-        xi.plane = c->plane; xi.row = c->ld; xi.ncol = c->nx / 2; xi.ring = pipe_ring();
-        EpiStore epi;
-        for (int i = 0; i < n; ++i) epi.dst[i] = xd[i];
-        epi.lay = c->lay(); epi.nx = c->nx; epi.pad = 1;
-        PipeCtl ctl;
-        if (pipe_ctl(c, &ctl, nz + 1, 0)) return 1;
-        ctl.nf_f = 1; ctl.nf_i = n; ctl.ny_f = ctl.ny_i = c->ny;
-        for (int i = 0; i < n; ++i) { ctl.i_k0[i] = 0; ctl.i_k1[i] = nz + 1; }
-        ProfScope ps_(c, "pipe_deriv");
-        int rc = launch_pipe_deriv(c->nx, c->ny, ntr > 1, pro, xo, ap, xi, epi, ctl, c->Wx, c->Whx, c->Wy, c->stream);
-        if (rc == 0) { c->launches++; return 0; }
-    }
     // plane chunks: the x->y->x passes of a chunk run back to back so the two spectral
     // intermediates are still in L2 when the next pass reads them
     const int ch = chunk_of(c, 1);
@@ -662,16 +616,11 @@ bool prodfwd_enabled() {
     if (v < 0) { const char* e = std::getenv("LESGO_PRODFWD"); v = (e && e[0] == '0') ? 0 : 1; }
     return v != 0;
 }
-bool bigx_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = std::getenv("LESGO_BIGX"); v = (e && e[0] == '1') ? 1 : 0; }   // opt-in, see convec()
-    return v != 0;
-}
-// planes per z chunk of the fused 3/2-grid x pass: long enough that the one-plane overlap between
+// planes per z chunk of the z-marching product pass: long enough that the one-plane overlap between
 // chunks is cheap, short enough that ny2 * nchunks work items balance over the persistent blocks
-int bigx_chunk(int nz) {
+int prod_chunk(int nz) {
     static int v = -1;
-    if (v < 0) { const char* e = std::getenv("LESGO_BIGX_CHUNK"); v = e ? std::atoi(e) : 0; }
+    if (v < 0) { const char* e = std::getenv("LESGO_PROD_CHUNK"); v = e ? std::atoi(e) : 0; }
     if (v > 0) return v;
     const int n = nz - 1;
     if (n <= 40) return n < 1 ? 1 : n;
@@ -684,14 +633,8 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
            const double* dudz, const double* dvdx, const double* dvdz, const double* dwdx,
            const double* dwdy, double* RHSx, double* RHSy, double* RHSz, const Fuse* fz = nullptr,
            bool uvw_ready = false) {
-    // fused 3/2-grid x pass (LESGO_BIGX=1; off by default: 9.1 ms against 8.0 ms for the two separate passes,
-    // profiles/r2_experiments.md), never with the host-array pipeline or plane chunks
-    const bool fused_x = bigx_enabled() && !HP(c) && c->chunk <= 0 && c->nz >= 2;
     if (need_small(c, 6)) return 1;
-    if (fused_x) {
-        for (int i = 0; i < 6; ++i) if (dev_alloc(c, &c->bb[i], size_t(c->plane_bi) * (c->nz + 1))) return 1;
-        for (int i = 0; i < 3; ++i) if (dev_alloc(c, &c->cc[i], size_t(c->plane_bi) * (c->nz + 1))) return 1;
-    } else if (need_big(c, 6)) return 1;
+    if (need_big(c, 6)) return 1;
     const int nz = c->nz, nxh = c->nx / 2;
     const double cs = 1.0 / (double(c->nx) * double(c->ny));
     ProScale ps;
@@ -739,7 +682,6 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
             if (ypass(c, c->ny, c->ny2, b, 3, va, kb)) return 1;
         }
         }
-        if (fused_x) continue;
         // (3) x inverse on the 3/2 grid: only kx < nx/2 carries data               :90-92, 165-167
         if (xinv(c, true, c->bb, c->plane_bi, c->ld, nxh, 3, c->big, c->lay_big(), c->ny2, ka, kb)) return 1;
         if (xinv(c, true, c->bb + 3, c->plane_bi, c->ld, nxh, 3, c->big + 3, c->lay_big(), c->ny2, va, kb)) return 1;
@@ -756,7 +698,7 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
             const Lay lb = c->lay_big();
             b.splane = lb.plane; b.srow = lb.row; b.dplane = c->plane_bi; b.drow = c->ld;
             b.ny2 = c->ny2; b.nz = nz; b.bottom = c->bottom; b.top = c->top; b.jzLo = c->jzLo;
-            b.chunk = bigx_chunk(nz); b.nchunks = (nz - 1 + b.chunk - 1) / b.chunk;
+            b.chunk = prod_chunk(nz); b.nchunks = (nz - 1 + b.chunk - 1) / b.chunk;
             b.scale = 1.0 / (double(c->nx2) * double(c->ny2));
             {
                 ProfScope ps_(c, "xfwd_big");
@@ -775,27 +717,6 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
         // (6) x inverse -> RHS
         if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, pa, pb, 1, fz)) return 1;
         if (Staged* hp = HP(c)) for (int i = 0; i < 3; ++i) hp->done(out[i], pa, pb);
-    }
-    if (fused_x) {
-        // (3)+(4) in one kernel: x inverse of the six fields, products, x forward of the three
-        // products, marching up z per 3/2-grid row (bigx_kernels.h)                 :90-92, 165-305
-        BigxArgs b;
-        for (int i = 0; i < 6; ++i) b.src[i] = c->bb[i];
-        for (int i = 0; i < 3; ++i) b.dst[i] = c->cc[i];
-        b.plane = c->plane_bi; b.row = c->ld; b.ny2 = c->ny2; b.nz = nz;
-        b.bottom = c->bottom; b.top = c->top; b.jzLo = c->jzLo;
-        b.chunk = bigx_chunk(nz); b.nchunks = (nz - 1 + b.chunk - 1) / b.chunk;
-        b.scale = 1.0 / (double(c->nx2) * double(c->ny2));
-        {
-            ProfScope ps_(c, "bigx");
-            if (launch_bigx(c->nx2, b, c->Wxb, c->Whxb, c->stream)) return c->fail("unsupported nx for the fused 3/2-grid x pass");
-            c->launches++;
-        }
-        for (int i = 0; i < 3; ++i) fill(c, c->cc[i], c->plane_bi, nz, nz + 1, 0.0);   // cc(nz) = 0, :262-268
-        YArgs a = yargs(c, c->plane_bi, c->ld, c->plane, c->ld, nxh, 1);
-        for (int i = 0; i < 3; ++i) { a.fld[i].src = c->cc[i]; a.fld[i].out[0] = YOutSpec{c->sa[i], Y_COPY}; }
-        if (ypass(c, c->ny2, c->ny, a, 3, 1, nz + 1)) return 1;
-        if (xinv(c, false, c->sa, c->plane, c->ld, nxh, 3, out, c->lay(), c->ny, 1, nz + 1, 1, fz)) return 1;
     }
     // :319-332
     FillGroup fg_(c);

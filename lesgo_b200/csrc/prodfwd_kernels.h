@@ -8,7 +8,7 @@
 // (prefetched with cp.async while the previous plane is being transformed), keeps what the next
 // plane needs -- u(k-1), v(k-1) and the partial sums of cx, cy -- in REGISTERS (each thread owns
 // the same row elements at every plane), forms cx(k-1), cy(k-1), cz(k) and transforms the three
-// rows as one tile.  Same wall-plane rules and the same one-plane delay as bigx_kernels.h.
+// rows as one tile.
 #pragma once
 #include "ops.h"
 

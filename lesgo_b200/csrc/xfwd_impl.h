@@ -14,15 +14,13 @@ static int launch_xfwd_n(const Pro& pro, int nfields, const XfOut& out, int ny, 
     if (nrows <= 0) return 0;
     if (warp_passes() == 2) {
         typedef XWCfg<NX> CW;
-        static bool attr_w = false;
-        if (!attr_w) { set_smem(k_xfwd_w<NX, Pro>, CW::smem); attr_w = true; }
+        LG_SET_SMEM((k_xfwd_w<NX, Pro>), CW::smem);
         const long nwork = ((nrows + CW::NF - 1) / CW::NF) * nfields;
         dim3 grid(persistent_blocks(CW::smem, (nwork + CW::WPB - 1) / CW::WPB, CW::MINB));
         LG_LAUNCH((k_xfwd_w<NX, Pro>), grid, dim3(CW::NTHR), CW::smem, s, pro, out, nfields, ny, k0, nplanes, W, Wh);
         return 0;
     }
-    static bool attr = false;
-    if (!attr) { set_smem(k_xfwd<NX, Pro>, C::smem); attr = true; }
+    LG_SET_SMEM((k_xfwd<NX, Pro>), C::smem);
     dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, C::MINB));
     LG_LAUNCH((k_xfwd<NX, Pro>), grid, dim3(C::NTHR), C::smem, s, pro, out, nfields, int(zmajor_for<Pro>() && ny % C::NF == 0), ny, k0, nplanes, W, Wh);
     return 0;

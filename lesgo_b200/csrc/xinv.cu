@@ -11,8 +11,7 @@ static int launch_xinv_n(const XiSrc& in, const Epi& epi, int nfields, int ny, i
         // warp-scope with cp.async prefetch of each warp's next row (rows of >= 256 complex points)
         typedef XWCfg<NX, false, true> CW;
         if (CW::PREF) {
-            static bool attr_p = false;
-            if (!attr_p) { set_smem(k_xinv_w<NX, Epi, false, true>, CW::smem); attr_p = true; }
+            LG_SET_SMEM((k_xinv_w<NX, Epi, false, true>), CW::smem);
             const long nwork = nrows * nfields;
             dim3 grid(persistent_blocks(CW::smem, (nwork + CW::WPB - 1) / CW::WPB, CW::MINB));
             LG_LAUNCH((k_xinv_w<NX, Epi, false, true>), grid, dim3(CW::NTHR), CW::smem, s, in, epi, nfields, ny, k0, nplanes, W, Wh);
@@ -21,15 +20,13 @@ static int launch_xinv_n(const XiSrc& in, const Epi& epi, int nfields, int ny, i
     }
     if (warp_passes() == 2 || ((warp_passes() == 1 || warp_passes() == 3) && big)) {
         typedef XWCfg<NX> CW;
-        static bool attr_w = false;
-        if (!attr_w) { set_smem(k_xinv_w<NX, Epi>, CW::smem); attr_w = true; }
+        LG_SET_SMEM((k_xinv_w<NX, Epi>), CW::smem);
         const long nwork = ((nrows + CW::NF - 1) / CW::NF) * nfields;
         dim3 grid(persistent_blocks(CW::smem, (nwork + CW::WPB - 1) / CW::WPB, CW::MINB));
         LG_LAUNCH((k_xinv_w<NX, Epi>), grid, dim3(CW::NTHR), CW::smem, s, in, epi, nfields, ny, k0, nplanes, W, Wh);
         return 0;
     }
-    static bool attr = false;
-    if (!attr) { set_smem(k_xinv<NX, Epi>, C::smem); attr = true; }
+    LG_SET_SMEM((k_xinv<NX, Epi>), C::smem);
     dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, C::MINB));
     LG_LAUNCH((k_xinv<NX, Epi>), grid, dim3(C::NTHR), C::smem, s, in, epi, nfields, 0, ny, k0, nplanes, W, Wh);
     return 0;

@@ -6,8 +6,7 @@ template <int NIN, int NOUT, bool MULTI>
 static int launch_y_m(const YArgs& a0, int nfields, int nplanes, const cplx* Win, const cplx* Wout,
                       cudaStream_t s) {
     typedef YCfg<NIN, NOUT, MULTI> C;
-    static bool attr = false;
-    if (!attr) { set_smem(k_ypass<NIN, NOUT, MULTI>, C::smem); attr = true; }
+    LG_SET_SMEM((k_ypass<NIN, NOUT, MULTI>), C::smem);
     if (nplanes <= 0 || nfields <= 0) return 0;
     YArgs a = a0;
     a.nplanes = nplanes;
@@ -54,8 +53,7 @@ int launch_ypass(int nin, int nout, const YArgs& a, int nfields, int nplanes, co
 template <int NS_, int NB_>
 static int launch_y_pad2(const YArgs& a0, int nfields, int nplanes, const cplx* Ws, const cplx* Wb, cudaStream_t s) {
     typedef YCfg<NS_, NS_, true, NB_> C;
-    static bool attr = false;
-    if (!attr) { set_smem(k_ypass<NS_, NS_, true, NB_>, C::smem); attr = true; }
+    LG_SET_SMEM((k_ypass<NS_, NS_, true, NB_>), C::smem);
     if (nplanes <= 0 || nfields <= 0) return 0;
     YArgs a = a0;
     a.nplanes = nplanes;

@@ -191,9 +191,7 @@ def test_emul_multirank_thin_slabs():
 
 
 @pytest.mark.parametrize("env,grid,what", [
-    ({"LESGO_BIGX": "1"}, "16,16,6", "convec,steps,full"),
-    ({"LESGO_BIGX": "1", "LESGO_BIGX_CHUNK": "2"}, "32,16,7", "convec"),
-    ({"LESGO_PIPE": "1", "LESGO_PIPE_RING": "2"}, "64,512,5", "deriv"),
+    ({"LESGO_PROD_CHUNK": "2"}, "32,16,7", "convec"),
     ({"LESGO_XW": "0"}, "16,16,6", "deriv,convec,steps"),
     ({"LESGO_XW": "1"}, "512,16,3", "deriv,convec"),
     ({"LESGO_XW": "3"}, "512,16,3", "deriv,convec,press"),

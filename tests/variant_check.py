@@ -1,5 +1,5 @@
 """Runs the routine- and step-level parity checks in THIS process (whose environment selects a
-kernel variant: LESGO_XW / LESGO_PIPE / LESGO_BIGX / LESGO_REUSE are read once per process).
+kernel variant: LESGO_XW / LESGO_PROD_CHUNK / LESGO_REUSE are read once per process).
 Used by test_emul_parity.py (emulator, CPU) and test_gpu_variants.py (sm_100a build, B200)."""
 import argparse
 import os

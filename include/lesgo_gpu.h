@@ -63,6 +63,30 @@ int lesgo_gpu_unpadd(lesgo_gpu_ctx* ctx, double* cc, const double* cc_big, int n
 int lesgo_gpu_fft_r2c(lesgo_gpu_ctx* ctx, const double* in, double* out, int nplanes, int big);
 int lesgo_gpu_fft_c2r(lesgo_gpu_ctx* ctx, const double* in, double* out, int nplanes, int big);
 
+/* ---- FFTW3 legacy-Fortran API (the lower boundary) --------------------------------------
+ * The library itself exports the symbols LESGO's remaining CPU routines call with the plan handles of
+ * module fft or with plans of their own (fft.f90:114-121; test_filtermodule.f90:138-167; scalars.f90:513-624;
+ * turbine_indicator.f90:130-151), so a LESGO build links WITHOUT libfftw3:
+ *     dfftw_plan_dft_r2c_2d_(plan, n_fast, n_slow, in, out, flags)      dfftw_plan_dft_c2r_2d_(...)
+ *     dfftw_execute_dft_r2c_(plan, in, out)   dfftw_execute_dft_c2r_(plan, in, out)   dfftw_destroy_plan_(plan)
+ * all arguments by reference, plan = integer*8.  In-place plans of the bound context's (nx, ny) and
+ * (3nx/2, 3ny/2) shapes run on the hot path's kernels; any other 2-3-5-smooth shape (e.g. the 2048 x 2048
+ * out-of-place transforms of the disk indicator) runs on a generic device transform; anything else, or any
+ * failure, prints and exits like `call error` (messages.f90:228-240).  The functions below are the same
+ * operations with status returns (what the tests call): in-place real rows hold 2*(n_fast/2+1) doubles,
+ * out-of-place real rows n_fast, complex rows n_fast/2+1 values (FFTW's r2c/c2r layout).
+ * lesgo_gpu_create binds the context it creates (the last one wins); dims may be NULL when ctx is NULL. */
+int lesgo_gpu_fftw_bind(lesgo_gpu_ctx* ctx, const lesgo_gpu_dims* dims);
+int lesgo_gpu_fftw_plan_2d(int c2r, int n_fast, int n_slow, int inplace, long long* plan);
+int lesgo_gpu_fftw_execute(long long plan, int c2r, double* in, double* out);
+int lesgo_gpu_fftw_destroy(long long plan);
+const char* lesgo_gpu_fftw_last_error(void);
+void dfftw_plan_dft_r2c_2d_(long long* plan, const int* n_fast, const int* n_slow, double* in, double* out, const int* flags);
+void dfftw_plan_dft_c2r_2d_(long long* plan, const int* n_fast, const int* n_slow, double* in, double* out, const int* flags);
+void dfftw_execute_dft_r2c_(const long long* plan, double* in, double* out);
+void dfftw_execute_dft_c2r_(const long long* plan, double* in, double* out);
+void dfftw_destroy_plan_(long long* plan);
+
 /* ---- module derivatives (derivatives.f90); all arrays (ld, ny, 0:nz) ------------------- */
 int lesgo_gpu_ddx(lesgo_gpu_ctx* ctx, const double* f, double* dfdx);                   /* :37  */
 int lesgo_gpu_ddy(lesgo_gpu_ctx* ctx, const double* f, double* dfdy);                   /* :79  */
@@ -204,6 +228,10 @@ int lesgo_gpu_turbines_forcing(lesgo_gpu_ctx* ctx, double eps, double* u_d, doub
  * id: 128-byte ncclUniqueId made by lesgo_gpu_comm_unique_id on coord 0 and broadcast by
  * the host (MPI_Bcast in the Fortran shim, torch.distributed in the Python host). */
 int lesgo_gpu_comm_unique_id(void* id128);
+/* id of the SINGLE-DEVICE transport instead: every rank is a thread of this process and all contexts sit on the
+ * same GPU (device-to-device copies ordered by events; NCCL refuses two ranks on one device).  It lets a one-GPU
+ * box run -- and test -- the multi-slab path: halos, pressure transposes, k = 0 chain, reductions. */
+int lesgo_gpu_comm_local_id(void* id128);
 int lesgo_gpu_comm_init(lesgo_gpu_ctx* ctx, const void* id128);
 /* Optional, one node: the two transposes of the pressure solve go over NVLink peer memory instead of NCCL
  * all-to-alls -- the right-hand-side assembly kernel stores straight into the pencil buffers of the other GPUs

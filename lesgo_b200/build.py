@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 TARGET = os.path.join(HERE, "liblesgo_cuda.so")
-SOURCES = ["lesgo_gpu.cu", "comm.cu", "xfwd_scale.cu", "xfwd_vort.cu", "xfwd_convec.cu", "xinv.cu", "ypass.cu", "prodfwd.cu"]
+SOURCES = ["lesgo_gpu.cu", "comm.cu", "xfwd_scale.cu", "xfwd_vort.cu", "xfwd_convec.cu", "xinv.cu", "ypass.cu", "prodfwd.cu", "fftw_shim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

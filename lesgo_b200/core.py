@@ -329,9 +329,11 @@ class Core:
         return v.value
 
     # -- multi-GPU ---------------------------------------------------------------------------------
-    def comm_unique_id(self) -> bytes:
+    def comm_unique_id(self, local: bool = False) -> bytes:
+        """128-byte id for comm_init: NCCL's (one rank per GPU), or with local=True the id of the
+        single-device transport (all ranks are threads of this process on ONE GPU)."""
         buf = C.create_string_buffer(128)
-        if self.lib.comm_unique_id(buf):
+        if (self.lib.comm_local_id if local else self.lib.comm_unique_id)(buf):
             raise LibraryError("comm_unique_id: " + self.lib.error(None))
         return buf.raw
 

@@ -80,6 +80,7 @@ int Comm::unique_id(void* id128, std::string*) {
     for (int i = 0; i < 128; ++i) b[i] = static_cast<unsigned char>('a' + rd() % 26);
     return 0;
 }
+int Comm::local_id(void* id128, std::string* e) { return unique_id(id128, e); }
 Comm* Comm::create(const void* id128, int rank, int nranks, std::string*) {
     std::string key(static_cast<const char*>(id128), 128);
     EmulComm* c = new EmulComm;
@@ -94,7 +95,13 @@ Comm* Comm::create(const void* id128, int rank, int nranks, std::string*) {
 #else
 #include <dlfcn.h>
 
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <random>
 #include <vector>
 
 namespace lg {
@@ -193,7 +200,120 @@ public:
     friend class Comm;
     void set(int r, int n) { rank_ = r; nranks_ = n; }
 };
+// ---- single-device transport ---------------------------------------------------------------------------------
+// The z-slab ranks are threads of ONE process that share ONE GPU (every context on the same device, each with its
+// own stream): the multi-slab path -- ghost-plane halos, slab <-> pencil transposes of the pressure solve, the
+// k = 0 chain, disk-velocity reductions -- then runs on a single B200, which is how a one-GPU box exercises it
+// (tests/test_gpu_parity.py).  Messages are device-to-device copies ordered by CUDA events; NCCL cannot do this
+// (it refuses two ranks on one device).  Selected by an id made with Comm::local_id.
+const char kLocalTag[] = "LESGO-LOCAL-COMM:";
+struct LWorld {
+    struct Msg { double* buf; size_t n; cudaEvent_t ev; };
+    std::mutex m;
+    std::condition_variable cv;
+    std::map<std::pair<int, int>, std::deque<Msg>> q;                   // (src, dst) -> device messages
+    std::map<std::pair<int, int>, std::deque<std::vector<double>>> hq;  // (src, dst) -> host scalars
+};
+std::mutex g_lworlds_m;
+std::map<std::string, std::shared_ptr<LWorld>> g_lworlds;
+
+class LocalComm : public Comm {
+public:
+    std::shared_ptr<LWorld> w;
+    void set(int r, int n) { rank_ = r; nranks_ = n; }
+    int put(int dst, const double* p, size_t n, cudaStream_t s) {
+        LWorld::Msg m{nullptr, n, nullptr};
+        if (cudaMalloc(reinterpret_cast<void**>(&m.buf), (n ? n : 1) * sizeof(double)) != cudaSuccess) { err_ = "local comm: cudaMalloc"; return 1; }
+        cudaMemcpyAsync(m.buf, p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+        cudaEventCreateWithFlags(&m.ev, cudaEventDisableTiming);
+        cudaEventRecord(m.ev, s);
+        std::lock_guard<std::mutex> l(w->m);
+        w->q[{rank_, dst}].push_back(m);
+        w->cv.notify_all();
+        return 0;
+    }
+    int get(int src, double* p, size_t n, cudaStream_t s) {
+        LWorld::Msg m;
+        {
+            std::unique_lock<std::mutex> l(w->m);
+            auto& dq = w->q[{src, rank_}];
+            w->cv.wait(l, [&] { return !dq.empty(); });
+            m = dq.front();
+            dq.pop_front();
+        }
+        if (m.n != n) { err_ = "local comm: message size mismatch"; return 1; }
+        cudaStreamWaitEvent(s, m.ev, 0);
+        cudaMemcpyAsync(p, m.buf, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+        const cudaError_t e = cudaStreamSynchronize(s);
+        cudaFree(m.buf);
+        cudaEventDestroy(m.ev);
+        if (e != cudaSuccess) { err_ = std::string("local comm: ") + cudaGetErrorString(e); return 1; }
+        return 0;
+    }
+    void hput(int dst, const std::vector<double>& v) {
+        std::lock_guard<std::mutex> l(w->m);
+        w->hq[{rank_, dst}].push_back(v);
+        w->cv.notify_all();
+    }
+    std::vector<double> hget(int src) {
+        std::unique_lock<std::mutex> l(w->m);
+        auto& dq = w->hq[{src, rank_}];
+        w->cv.wait(l, [&] { return !dq.empty(); });
+        std::vector<double> v = dq.front();
+        dq.pop_front();
+        return v;
+    }
+    int exchange(int n, const double* const* sendbuf, const int* dest, double* const* recvbuf, const int* src,
+                 const size_t* count, cudaStream_t s) override {
+        for (int i = 0; i < n; ++i) if (dest[i] >= 0 && dest[i] < nranks_) if (put(dest[i], sendbuf[i], count[i], s)) return 1;
+        for (int i = 0; i < n; ++i) if (src[i] >= 0 && src[i] < nranks_) if (get(src[i], recvbuf[i], count[i], s)) return 1;
+        return 0;
+    }
+    // the host forms the sum in rank order, so every rank holds the same bits
+    int reduce_host(std::vector<double>& v, int op) {
+        for (int r = 0; r < nranks_; ++r) if (r != rank_) hput(r, v);
+        std::vector<double> acc;
+        for (int r = 0; r < nranks_; ++r) {
+            const std::vector<double> x = r == rank_ ? v : hget(r);
+            if (r == 0) { acc = x; continue; }
+            for (size_t i = 0; i < x.size(); ++i)
+                acc[i] = op == 0 ? acc[i] + x[i] : (op == 1 ? (x[i] > acc[i] ? x[i] : acc[i]) : (x[i] < acc[i] ? x[i] : acc[i]));
+        }
+        v = acc;
+        return 0;
+    }
+    int allreduce(double* v, int op, cudaStream_t s) override {
+        if (cudaStreamSynchronize(s) != cudaSuccess) { err_ = "allreduce sync failed"; return 1; }
+        std::vector<double> x(1, *v);
+        reduce_host(x, op);
+        *v = x[0];
+        return 0;
+    }
+    int allreduce_sum_dev(double* dev, size_t n, cudaStream_t s) override {
+        std::vector<double> x(n);
+        cudaMemcpyAsync(x.data(), dev, n * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) { err_ = "allreduce sync failed"; return 1; }
+        reduce_host(x, 0);             // every rank's earlier work on its stream is complete once this returns
+        cudaMemcpyAsync(dev, x.data(), n * sizeof(double), cudaMemcpyHostToDevice, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) { err_ = "allreduce sync failed"; return 1; }
+        return 0;
+    }
+    int alltoall(const double* sendbuf, double* recvbuf, size_t count, cudaStream_t s) override {
+        for (int r = 0; r < nranks_; ++r) if (put(r, sendbuf + size_t(r) * count, count, s)) return 1;
+        for (int r = 0; r < nranks_; ++r) if (get(r, recvbuf + size_t(r) * count, count, s)) return 1;
+        return 0;
+    }
+};
 }  // namespace
+
+int Comm::local_id(void* id128, std::string*) {
+    std::random_device rd;
+    unsigned char* b = static_cast<unsigned char*>(id128);
+    std::memset(b, 0, 128);
+    std::memcpy(b, kLocalTag, sizeof(kLocalTag) - 1);
+    for (int i = int(sizeof(kLocalTag)) - 1; i < 127; ++i) b[i] = static_cast<unsigned char>('a' + rd() % 26);
+    return 0;
+}
 
 int Comm::unique_id(void* id128, std::string* err) {
     if (!api().load()) { if (err) *err = api().err; return 1; }
@@ -205,6 +325,15 @@ int Comm::unique_id(void* id128, std::string* err) {
 }
 
 Comm* Comm::create(const void* id128, int rank, int nranks, std::string* err) {
+    if (std::memcmp(id128, kLocalTag, sizeof(kLocalTag) - 1) == 0) {
+        LocalComm* c = new LocalComm;
+        c->set(rank, nranks);
+        std::lock_guard<std::mutex> l(g_lworlds_m);
+        auto& w = g_lworlds[std::string(static_cast<const char*>(id128), 128)];
+        if (!w) w = std::make_shared<LWorld>();
+        c->w = w;
+        return c;
+    }
     if (!api().load()) { if (err) *err = api().err; return nullptr; }
     ncclUniqueId id;
     std::memcpy(&id, id128, 128);

@@ -13,6 +13,8 @@ class Comm {
 public:
     // 128-byte ncclUniqueId for the host to broadcast (MPI_Bcast / torch.distributed)
     static int unique_id(void* id128, std::string* err);
+    // id of the single-device transport: all ranks are threads of one process sharing one GPU (comm.cu)
+    static int local_id(void* id128, std::string* err);
     static Comm* create(const void* id128, int rank, int nranks, std::string* err);
     virtual ~Comm() {}
     int rank() const { return rank_; }

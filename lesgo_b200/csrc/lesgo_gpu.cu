@@ -22,6 +22,8 @@
 
 using namespace lg;
 
+extern "C" lesgo_gpu_ctx* lesgo_gpu_fftw_bound(void);   // fftw_shim.cu (internal)
+
 namespace {
 const double kBogus = -1234567890.0;   // param.f90:93
 thread_local std::string g_err;
@@ -57,6 +59,7 @@ struct lesgo_gpu_ctx {
     double* bb[kMaxFields] = {nullptr};    // big-y intermediates, (ld, ny2, 0:nz)
     double* big[kMaxFields] = {nullptr};   // 3/2-grid physical fields, (ld_big, ny2, 0:nz)
     double* gam = nullptr;                 // tridiagonal gam(j) table (lh, ny, 0:nzt+1)
+    double* pen_buf[2] = {nullptr};        // NCCL-path pencil buffers of a ragged ky split (ny % nproc != 0)
     double* work[13] = {nullptr};          // S11..S33, Nu_t, six stress-gradient temporaries (mode 1)
     double* lsq = nullptr;                 // l(k)**2 of the Smagorinsky length (nz+1)
     double* gtest = nullptr;               // test-filter kernel G_test (lh, ny)
@@ -727,14 +730,26 @@ int convec(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, 
 }
 
 // ---- press_stag_array.f90 ------------------------------------------------------------------------
+// one-off (the gam table is built once per context): did any mode hit a zero pivot?
+int pivot_check(lesgo_gpu_ctx* c, const double* flag) {
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h) { c->gam = nullptr; return c->fail("tridag_array failed: zero pivot (tridag_array.f90:55-60,101-108)"); }
+    return 0;
+}
+
 int tridag_setup(lesgo_gpu_ctx* c, TriGeom& g) {
     g.lh = c->lh; g.ny = c->ny; g.nzt = c->nzt; g.row = c->ld; g.plane = c->plane;
     g.gplane = long(c->lh) * c->ny; g.kxs = c->kxs; g.kys = c->kys; g.dz = c->d.dz;
     if (!c->gam) {
         if (dev_alloc(c, &c->gam, size_t(g.gplane) * (c->nzt + 2))) return 1;
         const int nm = (c->lh - 1) * c->ny;
-        LG_LAUNCH(k_tridag_setup, dim3((nm + 127) / 128), dim3(128), 0, c->stream, g, c->gam);
+        double* flag = nullptr;
+        if (dev_alloc(c, &flag, 1)) return 1;          // zeroed
+        LG_LAUNCH(k_tridag_setup, dim3((nm + 127) / 128), dim3(128), 0, c->stream, g, c->gam, reinterpret_cast<int*>(flag));
         c->launches++;
+        if (pivot_check(c, flag)) return 1;
     }
     return 0;
 }
@@ -742,7 +757,6 @@ int tridag_setup(lesgo_gpu_ctx* c, TriGeom& g) {
 int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, const double* divtz, double dt,
           double tadv1, double* p, double* dpdx, double* dpdy, double* dpdz, const Fuse* fz = nullptr) {
     if (c->d.nproc > 1 && !c->comm) return c->fail("press_stag_array: nproc > 1 needs lesgo_gpu_comm_init first");
-    if (c->d.nproc > 1 && (c->ny % c->d.nproc)) return c->fail("press_stag_array: ny must be divisible by nproc");
     if (need_small(c, 6)) return 1;
     const int nz = c->nz, nxh = c->nx / 2;
     const double cst = 1.0 / (double(c->nx) * double(c->ny));
@@ -795,7 +809,7 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         // pipeline of tridag_array.f90:22-162 and the halo/chain messages C4-C7.
         PencilGeom g;
         g.lh = c->lh; g.ny = c->ny; g.ld = c->ld; g.nz = nz; g.nproc = c->d.nproc; g.coord = c->d.coord;
-        g.cy = c->ny / c->d.nproc; g.plane = c->plane; g.kxs = c->kxs; g.kys = c->kys; g.dz = c->d.dz;
+        g.cy = (c->ny + c->d.nproc - 1) / c->d.nproc; g.plane = c->plane; g.kxs = c->kxs; g.kys = c->kys; g.dz = c->d.dz;
         g.p2p = c->p2p_on ? 1 : 0;
         // the two halves of every rank's buffer alternate from call to call: a rank may already push the next
         // solve's rows into a peer while a third rank is still pulling the previous result out of it
@@ -809,8 +823,16 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
             if (c->comm->allreduce_sum_dev(c->p2p_flag, 1, c->stream)) return c->fail(c->comm->error());
             return 0;
         };
-        double* pencil = c->p2p_on ? c->p2p_buf + (par ? c->p2p_half : 0) : c->sa[5];
-        double* ret = c->sa[4];                                   // NCCL path only
+        // NCCL path: send / receive buffers.  The small spectra serve when ny divides evenly; a ragged
+        // split (cy * nproc > ny) pads every block to cy rows and may need more than a field's worth.
+        double *nsend = c->sa[4], *nrecv = c->sa[5];
+        if (!c->p2p_on && size_t(g.block()) * g.nproc > size_t(c->plane) * (nz + 1)) {
+            for (int i = 0; i < 2; ++i)
+                if (dev_alloc(c, &c->pen_buf[i], size_t(g.block()) * g.nproc)) return 1;
+            nsend = c->pen_buf[0]; nrecv = c->pen_buf[1];
+        }
+        double* pencil = c->p2p_on ? c->p2p_buf + (par ? c->p2p_half : 0) : nrecv;
+        double* ret = nsend;                                      // NCCL path only
         {   // rH_z(1) of coord+1 -> rH_z(nz) of coord                             :184-185
             const double* sb[1] = {c->sa[2] + c->plane};
             double* rb[1] = {c->sa[2] + c->plane * nz};
@@ -822,19 +844,22 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         if (!c->gam) {
             if (dev_alloc(c, &c->gam, size_t(c->nzt + 2) * g.cy * c->lh)) return 1;
             const int nm = (c->lh - 1) * g.cy;
-            LG_LAUNCH(k_tridag_setup_pencil, dim3((nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam);
+            double* flag = nullptr;
+            if (dev_alloc(c, &flag, 1)) return 1;      // zeroed
+            LG_LAUNCH(k_tridag_setup_pencil, dim3((nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, reinterpret_cast<int*>(flag));
             c->launches++;
+            if (pivot_check(c, flag)) return 1;
         }
         {
             ProfScope ps_(c, "press_pack");
             LG_LAUNCH(k_press_pack, dim3(grid1d(long(c->lh - 1) * c->ny * nz)), dim3(kBlock), 0, c->stream, g, c->sa[0],
-                      c->sa[1], c->sa[2], c->sa[3] + c->plane, c->sa[3] + c->plane * nz, c->sa[4]);
+                      c->sa[1], c->sa[2], c->sa[3] + c->plane, c->sa[3] + c->plane * nz, nsend);
             c->launches++;
         }
         if (c->p2p_on) { if (barrier()) return 1; }
         else {
             ProfScope ps_(c, "alltoall");
-            if (c->comm->alltoall(c->sa[4], c->sa[5], size_t(g.block()), c->stream)) return c->fail(c->comm->error());
+            if (c->comm->alltoall(nsend, nrecv, size_t(g.block()), c->stream)) return c->fail(c->comm->error());
         }
         {
             const int nm = (c->lh - 1) * g.cy;
@@ -846,7 +871,7 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         if (c->p2p_on) { if (barrier()) return 1; }
         else {
             ProfScope ps_(c, "alltoall");
-            if (c->comm->alltoall(c->sa[5], c->sa[4], size_t(g.block()), c->stream)) return c->fail(c->comm->error());
+            if (c->comm->alltoall(nrecv, nsend, size_t(g.block()), c->stream)) return c->fail(c->comm->error());
         }
         {
             ProfScope ps_(c, "press_unpack");
@@ -1346,9 +1371,9 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     if (spectral_deriv(c, F[LG_U], F[LG_U], F[LG_DUDX], F[LG_DUDY], reuse ? c->bb[0] : nullptr)) return 1;
     if (spectral_deriv(c, F[LG_V], F[LG_V], F[LG_DVDX], F[LG_DVDY], reuse ? c->bb[1] : nullptr)) return 1;
     if (spectral_deriv(c, F[LG_W], F[LG_W], F[LG_DWDX], F[LG_DWDY], reuse ? c->bb[2] : nullptr)) return 1;
-    ddz_uv(c, F[LG_U], F[LG_DUDZ]);
-    ddz_uv(c, F[LG_V], F[LG_DVDZ]);
-    ddz_w(c, F[LG_W], F[LG_DWDZ]);
+    if (ddz_uv(c, F[LG_U], F[LG_DUDZ])) return 1;
+    if (ddz_uv(c, F[LG_V], F[LG_DVDZ])) return 1;
+    if (ddz_w(c, F[LG_W], F[LG_DWDZ])) return 1;
     // wallstress (:182-184); sgs_stag, tzz halo, divstress_uv/w (:189-203) in the full mode
     if (sp->mode == 1 && build_sgs_tables(c, sp)) return 1;
     if (wallstress(c, sp, F, sp->mode == 1)) return 1;
@@ -1374,9 +1399,9 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
                    F[LG_DWDY], F[LG_RHSX], F[LG_RHSY], F[LG_RHSZ], use, reuse)) return 1;
         if (!use) {
             const int kw = c->top ? nz + 1 : nz;
-            glue_fused(c, F_RHS_AB2, F[LG_RHSX], F[LG_DIVTX], F[LG_RHSX_F], F[LG_U], 1, nz, 0, fz.first_step, sp->mean_p_force_x, sp->dt, sp->tadv1, sp->tadv2);
-            glue_fused(c, F_RHS_AB2, F[LG_RHSY], F[LG_DIVTY], F[LG_RHSY_F], F[LG_V], 1, nz, 0, fz.first_step, sp->mean_p_force_y, sp->dt, sp->tadv1, sp->tadv2);
-            glue_fused(c, F_RHS_AB2, F[LG_RHSZ], F[LG_DIVTZ], F[LG_RHSZ_F], F[LG_W], 1, kw, 0, fz.first_step, 0.0, sp->dt, sp->tadv1, sp->tadv2);
+            if (glue_fused(c, F_RHS_AB2, F[LG_RHSX], F[LG_DIVTX], F[LG_RHSX_F], F[LG_U], 1, nz, 0, fz.first_step, sp->mean_p_force_x, sp->dt, sp->tadv1, sp->tadv2)) return 1;
+            if (glue_fused(c, F_RHS_AB2, F[LG_RHSY], F[LG_DIVTY], F[LG_RHSY_F], F[LG_V], 1, nz, 0, fz.first_step, sp->mean_p_force_y, sp->dt, sp->tadv1, sp->tadv2)) return 1;
+            if (glue_fused(c, F_RHS_AB2, F[LG_RHSZ], F[LG_DIVTZ], F[LG_RHSZ_F], F[LG_W], 1, kw, 0, fz.first_step, 0.0, sp->dt, sp->tadv1, sp->tadv2)) return 1;
         }
     }
     // :299-308
@@ -1471,12 +1496,14 @@ int lesgo_gpu_create(const lesgo_gpu_dims* d, lesgo_gpu_ctx** out) {
     rc |= make_stage_twiddles(c, &c->Wyb, c->ny2);
     if (rc) { std::string m = c->err; return bail(m); }
     *out = c;
+    lesgo_gpu_fftw_bind(c, d);          // the dfftw_* symbols serve this context's plans (fftw_shim.cu)
     return 0;
 }
 
 int lesgo_gpu_destroy(lesgo_gpu_ctx* c) {
     ENTER(c);
     if (!c) return 0;
+    if (lesgo_gpu_fftw_bound() == c) lesgo_gpu_fftw_bind(nullptr, nullptr);
     cudaStreamSynchronize(c->stream);
     if (c->comm) { delete c->comm; c->comm = nullptr; }
     for (void* p : c->allocs) cudaFree(p);
@@ -1998,6 +2025,7 @@ int lesgo_gpu_rmsdiv(lesgo_gpu_ctx* c, double* rms) {
 }
 
 int lesgo_gpu_comm_unique_id(void* id128) { return lg::Comm::unique_id(id128, &g_err); }
+int lesgo_gpu_comm_local_id(void* id128) { return lg::Comm::local_id(id128, &g_err); }
 
 int lesgo_gpu_comm_init(lesgo_gpu_ctx* c, const void* id128) {
     ENTER(c);
@@ -2029,8 +2057,7 @@ int lesgo_gpu_comm_p2p_export(lesgo_gpu_ctx* c, void* blob128) {
     ENTER(c);
     if (!c || !blob128) return 1;
     if (c->d.nproc < 2 || c->d.nproc > 8) return c->fail("peer-memory transposes need 2..8 ranks on one node");
-    if (c->ny % c->d.nproc) return c->fail("press_stag_array: ny must be divisible by nproc");
-    const size_t half = size_t(c->nz) * (c->ny / c->d.nproc) * c->ld * c->d.nproc;
+    const size_t half = size_t(c->nz) * ((c->ny + c->d.nproc - 1) / c->d.nproc) * c->ld * c->d.nproc;
     if (!c->p2p_buf) {
         if (dev_alloc(c, &c->p2p_buf, 2 * half)) return 1;
         if (dev_alloc(c, &c->p2p_flag, 1)) return 1;
@@ -2158,6 +2185,11 @@ int lesgo_gpu_tridag_array(lesgo_gpu_ctx* c, const double* a, const double* b, c
                            double* u, int n) {
     ENTER(c);
     if (!c || !a || !b || !cc || !r || !u || n < 2) return 1;
+    // the serial form only (tridag_array.f90:166-246): the MPI form pipelines ONE system across the ranks, which
+    // this library replaces inside press_stag_array by the slab <-> pencil transposes
+    if (c->d.nproc > 1)
+        return c->fail("tridag_array: general-coefficient entry point is single-slab only; with nproc > 1 the "
+                       "distributed solve lives inside lesgo_gpu_press_stag_array");
     Staged st(c);
     const size_t nc = size_t(c->lh) * c->ny * n, nr = size_t(c->plane) * n;
     double* da = st.in(a, nc, true, false);
@@ -2168,6 +2200,7 @@ int lesgo_gpu_tridag_array(lesgo_gpu_ctx* c, const double* a, const double* b, c
     if (!da || !db || !dc || !dr || !du) return 1;
     void* work = nullptr;
     CK(cudaMalloc(&work, nc * sizeof(double) + 16));
+    struct Free { void* p; lesgo_gpu_ctx* c; ~Free() { cudaStreamSynchronize(c->stream); cudaFree(p); } } free_work{work, c};
     int* flag = reinterpret_cast<int*>(static_cast<double*>(work) + nc);
     CK(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
     const int nm = (c->lh - 1) * c->ny;
@@ -2177,8 +2210,7 @@ int lesgo_gpu_tridag_array(lesgo_gpu_ctx* c, const double* a, const double* b, c
     int hflag = 0;
     CK(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     int rc = st.finish();
-    cudaStreamSynchronize(c->stream);
-    cudaFree(work);
+    CK(cudaStreamSynchronize(c->stream));
     if (rc) return rc;
     if (hflag) return c->fail("tridag_array failed: zero pivot (tridag_array.f90:55-60,101-108)");
     return 0;

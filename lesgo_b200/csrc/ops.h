@@ -341,8 +341,10 @@ LG_D double tri_k2(const TriGeom& g, int jx, int jy) {
     return dadd(dmul(kx, kx), dmul(ky, ky));
 }
 
-// gam(j), j = 2..n  stored at gam[j*gplane + jy*lh + jx]
-static __global__ void k_tridag_setup(TriGeom g, double* __restrict__ gam) {
+// gam(j), j = 2..n  stored at gam[j*gplane + jy*lh + jx].  The pivots bet(j) depend only on (kx, ky, dz), so
+// the reference's zero-pivot stop (tridag_array.f90:56-59,101-108, SAFETYMODE) is checked HERE, once, for the
+// fused and pencil sweeps that reuse the table: *fail != 0 makes press_stag_array return an error.
+static __global__ void k_tridag_setup(TriGeom g, double* __restrict__ gam, int* __restrict__ fail) {
     const int nm = (g.lh - 1) * g.ny;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nm) return;
@@ -357,6 +359,7 @@ static __global__ void k_tridag_setup(TriGeom g, double* __restrict__ gam) {
         const double b = (j == n) ? 1.0 : bb;
         const double gm = ddiv(cprev, bet);
         bet = dsub(b, dmul(a, gm));
+        if (bet == 0.0) *fail = 1;
         gam[long(j) * g.gplane + long(jy) * g.lh + jx] = gm;
         cprev = c3;
     }
@@ -542,7 +545,7 @@ static __global__ void k_tridag_general(int lh, int ny, int n, int ld, const dou
 // i.e. `nz` block rows per rank; block row i of rank r is local row i + (r ? 2 : 1).
 struct PencilGeom {
     int lh, ny, ld, nz, nproc, coord;
-    int cy;                 // ky rows per pencil chunk = ny / nproc
+    int cy;                 // ky rows per pencil chunk = ceil(ny / nproc); the last rank's chunk may be ragged or empty
     long plane;             // ld * ny
     double kxs, kys, dz;
     // peer-memory transposes (lesgo_gpu_comm_p2p_import): pencil[q] is rank q's pencil buffer of this solve,
@@ -592,12 +595,12 @@ static __global__ void k_press_pack(PencilGeom g, const double* __restrict__ Hx,
 }
 
 // gam table in pencil layout: gam[global row][jy_local][jx]
-static __global__ void k_tridag_setup_pencil(PencilGeom g, int nzt, double* __restrict__ gam) {
+static __global__ void k_tridag_setup_pencil(PencilGeom g, int nzt, double* __restrict__ gam, int* __restrict__ fail) {
     const int nm = (g.lh - 1) * g.cy;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nm) return;
     const int jx = t % (g.lh - 1), jl = t / (g.lh - 1), jy = g.coord * g.cy + jl;
-    if (jy == g.ny / 2 || (jx == 0 && jy == 0)) return;
+    if (jy >= g.ny || jy == g.ny / 2 || (jx == 0 && jy == 0)) return;
     const double c3 = ddiv(1.0, dmul(g.dz, g.dz));
     const double kx = g.kxs * double(jx);
     const double ky = g.kys * double(jy < g.ny / 2 ? jy : jy - g.ny);
@@ -609,6 +612,7 @@ static __global__ void k_tridag_setup_pencil(PencilGeom g, int nzt, double* __re
         const double b = (j == n) ? 1.0 : bb;
         const double gm = ddiv(cprev, bet);
         bet = dsub(b, dmul(a, gm));
+        if (bet == 0.0) *fail = 1;
         gam[(long(j) * g.cy + jl) * g.lh + jx] = gm;
         cprev = c3;
     }
@@ -623,7 +627,7 @@ static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __re
     if (t2 >= 2 * nm) return;
     const int t = t2 >> 1, part = t2 & 1;
     const int jx = t % (g.lh - 1), jl = t / (g.lh - 1), jy = g.coord * g.cy + jl;
-    if (jy == g.ny / 2) return;
+    if (jy >= g.ny || jy == g.ny / 2) return;
     const int n = nzt + 1;
     const long mo = long(jl) * g.ld + 2 * jx + part;
     const long rs = long(g.cy) * g.ld;                            // doubles between block rows

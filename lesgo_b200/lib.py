@@ -50,6 +50,11 @@ SYMBOLS = {
     "lesgo_gpu_unpadd": (C.c_int, [_P, _D, _D, C.c_int]),
     "lesgo_gpu_fft_r2c": (C.c_int, [_P, _D, _D, C.c_int, C.c_int]),
     "lesgo_gpu_fft_c2r": (C.c_int, [_P, _D, _D, C.c_int, C.c_int]),
+    "lesgo_gpu_fftw_bind": (C.c_int, [_P, C.POINTER(DimsStruct)]),
+    "lesgo_gpu_fftw_plan_2d": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
+    "lesgo_gpu_fftw_execute": (C.c_int, [C.c_longlong, C.c_int, _D, _D]),
+    "lesgo_gpu_fftw_destroy": (C.c_int, [C.c_longlong]),
+    "lesgo_gpu_fftw_last_error": (C.c_char_p, []),
     "lesgo_gpu_ddx": (C.c_int, [_P, _D, _D]),
     "lesgo_gpu_ddy": (C.c_int, [_P, _D, _D]),
     "lesgo_gpu_ddxy": (C.c_int, [_P, _D, _D, _D]),
@@ -75,10 +80,23 @@ SYMBOLS = {
     "lesgo_gpu_turbines_init": (C.c_int, [_P, C.c_int, C.POINTER(TurbineStruct), C.c_int]),
     "lesgo_gpu_turbines_forcing": (C.c_int, [_P, C.c_double, _D, _D, _D]),
     "lesgo_gpu_comm_unique_id": (C.c_int, [_P]),
+    "lesgo_gpu_comm_local_id": (C.c_int, [_P]),
     "lesgo_gpu_comm_init": (C.c_int, [_P, _P]),
     "lesgo_gpu_comm_p2p_export": (C.c_int, [_P, _P]),
     "lesgo_gpu_comm_p2p_import": (C.c_int, [_P, _P]),
     "lesgo_gpu_sync_real_array": (C.c_int, [_P, _D, C.c_int]),
+}
+
+
+# FFTW3 legacy-Fortran symbols the library exports for the reference's remaining CPU callers (by reference)
+_LL = C.POINTER(C.c_longlong)
+_I = C.POINTER(C.c_int)
+FFTW_SYMBOLS = {
+    "dfftw_plan_dft_r2c_2d_": (None, [_LL, _I, _I, _D, _D, _I]),
+    "dfftw_plan_dft_c2r_2d_": (None, [_LL, _I, _I, _D, _D, _I]),
+    "dfftw_execute_dft_r2c_": (None, [_LL, _D, _D]),
+    "dfftw_execute_dft_c2r_": (None, [_LL, _D, _D]),
+    "dfftw_destroy_plan_": (None, [_LL]),
 }
 
 
@@ -108,6 +126,14 @@ class Library:
             fn.restype = res
             fn.argtypes = args
             setattr(self, name[len("lesgo_gpu_"):], fn)
+        for name, (res, args) in FFTW_SYMBOLS.items():
+            try:
+                fn = getattr(self.dll, name)
+            except AttributeError as e:
+                raise LibraryError(f"{self.path} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name.rstrip("_"), fn)
 
     def error(self, ctx=None) -> str:
         s = self.last_error(ctx)

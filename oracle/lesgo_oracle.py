@@ -36,6 +36,7 @@ rank, in-process queues; used by the tests and the golden-vector generator) and
 from __future__ import annotations
 
 import math
+import sys
 import queue
 import threading
 from dataclasses import dataclass, field
@@ -1373,6 +1374,20 @@ def get_cfl_dt(s, p: Params, comm, cfl):
     cv = np.abs(s.v[1:nz, :, :nx]).max() / p.dy
     cw = np.abs(s.w[1:nz, :, :nx]).max() / p.dz
     return comm.allreduce(cfl / max(cu, cv, cw), "min")
+
+
+def cfl_dt_start(s, p: Params, comm, cfl):
+    """initialize.f90:192-199: a fresh run with use_cfl_dt sets dt = get_cfl_dt() * huge(1._rprec), so that the
+    first pass through main.f90:135-144 yields tadv1 = 1, tadv2 = 0 (first-order Euler)."""
+    p.dt = get_cfl_dt(s, p, comm, cfl) * sys.float_info.max
+
+
+def cfl_dt_advance(s, p: Params, comm, cfl):
+    """main.f90:135-144 (use_cfl_dt): dt_f = dt; dt = get_cfl_dt(); tadv1 = 1 + dt/(2 dt_f); tadv2 = 1 - tadv1."""
+    dt_f = p.dt
+    p.dt = get_cfl_dt(s, p, comm, cfl)
+    p.tadv1 = 1.0 + 0.5 * p.dt / dt_f
+    p.tadv2 = 1.0 - p.tadv1
 
 
 def rmsdiv(s, p: Params, comm):

@@ -8,7 +8,7 @@ mkdir -p _build
 SRC=../../lesgo_b200/csrc
 FLAGS="-O2 -std=c++17 -fPIC -DLESGO_EMUL ${LESGO_EMUL_DEFS} -ffp-contract=off -I. -Wno-unused-function"
 pids=()
-for f in lesgo_gpu xfwd_scale xfwd_vort xfwd_convec xinv ypass prodfwd comm extras; do
+for f in lesgo_gpu xfwd_scale xfwd_vort xfwd_convec xinv ypass prodfwd fftw_shim comm extras; do
   [ -f $SRC/$f.cu ] || continue
   if [ ! -f _build/$f.o ] || [ -n "$(find $SRC ../emul -newer _build/$f.o \( -name '*.h' -o -name "$f.cu" \) | head -1)" ]; then
     g++ $FLAGS -x c++ -c $SRC/$f.cu -o _build/$f.o &

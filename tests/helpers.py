@@ -321,7 +321,7 @@ def farm_for_rank(farm, p):
 
 
 def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core", lasd=False,
-                          turbines=False, tavg=False, p2p=False):
+                          turbines=False, tavg=False, p2p=False, local=False):
     """nproc ranks (threads of this process, one Core each) advance `nsteps` core steps;
     the gathered result must match the SINGLE-slab oracle (which the multi-slab oracle
     equals, tests/test_oracle_kat.py)."""
@@ -351,7 +351,7 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
             O.tavg_compute(tref, sref, pg, O.LocalComm(), pg.dt, forces=turbines)
     ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
     cores = [lesgo_b200.Core(make_dims(p, device=(device_of(p.coord) if device_of else -1)), lib=lib) for p in ps]
-    ident = cores[0].comm_unique_id()
+    ident = cores[0].comm_unique_id(local=local)      # local: every rank on ONE GPU (single-device transport)
     res, err = [None] * nproc, [None] * nproc
     blobs, bar = [None] * nproc, threading.Barrier(nproc)
 
@@ -560,3 +560,147 @@ def check_misc(core, p):
     except lesgo_b200.LibraryError as e:
         assert "zero pivot" in str(e)
     return True
+
+
+def check_fftw_shim(lib, core, p, big_generic=None):
+    """The FFTW3 legacy-Fortran symbols the library exports (include/lesgo_gpu.h): called by
+    reference exactly as gfortran calls them -- fft.f90:114-121 (in-place plans of module fft, seven
+    arguments), turbine_indicator.f90:130-151 (out-of-place plans of another size, destroyed after use)."""
+    import ctypes as C
+    sp = O.Spectral(p)
+    out = {}
+    byref = C.byref
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    flags = C.c_int(32)                                     # FFTW_PATIENT; ignored
+
+    def plan(kind, n0, n1, a, b):
+        h = C.c_longlong(-7)
+        fn = lib.dfftw_plan_dft_r2c_2d if kind == "r2c" else lib.dfftw_plan_dft_c2r_2d
+        fn(byref(h), byref(C.c_int(n0)), byref(C.c_int(n1)), ptr(a), ptr(b), byref(flags))
+        assert h.value > 0
+        return h
+
+    # module fft's four plans: in place on (ld, ny) / (ld_big, ny2) arrays
+    data = np.zeros((p.ny, p.ld)); data_big = np.zeros((p.ny2, p.ld_big))
+    forw, back = plan("r2c", p.nx, p.ny, data, data), plan("c2r", p.nx, p.ny, data, data)
+    forw_big, back_big = plan("r2c", p.nx2, p.ny2, data_big, data_big), plan("c2r", p.nx2, p.ny2, data_big, data_big)
+    assert len({forw.value, back.value, forw_big.value, back_big.value}) == 4
+    f = random_field(p, 5, planes=1)
+    ref = sp.forw(f)
+    g = f[0].copy()
+    lib.dfftw_execute_dft_r2c(byref(forw), ptr(g), ptr(g))
+    out["forw"] = rel(g, ref[0])
+    h = ref[0].copy()
+    lib.dfftw_execute_dft_c2r(byref(back), ptr(h), ptr(h))
+    out["back"] = rel(h[:, :p.nx], sp.back(ref)[0][:, :p.nx])
+    fb = np.zeros((1, p.ny2, p.ld_big)); fb[:, :, :p.nx2] = np.random.default_rng(6).standard_normal((1, p.ny2, p.nx2))
+    refb = sp.forw_big(fb)
+    g = fb[0].copy()
+    lib.dfftw_execute_dft_r2c(byref(forw_big), ptr(g), ptr(g))
+    out["forw_big"] = rel(g, refb[0])
+    h = refb[0].copy()
+    lib.dfftw_execute_dft_c2r(byref(back_big), ptr(h), ptr(h))
+    out["back_big"] = rel(h[:, :p.nx2], sp.back_big(refb)[0][:, :p.nx2])
+
+    # plans of another shape, out of place (turbine_indicator.f90: g(N,N) -> ghat(N/2+1,N), fxhat -> fx)
+    for n0, n1 in ((40, 24), (30, 50)) + ((big_generic,) if big_generic else ()):
+        rng = np.random.default_rng(n0 + n1)
+        x = rng.standard_normal((n1, n0))
+        xh = np.zeros((n1, n0 // 2 + 1), complex)
+        pl = plan("r2c", n0, n1, x, xh)
+        lib.dfftw_execute_dft_r2c(byref(pl), ptr(x), ptr(xh))
+        lib.dfftw_destroy_plan(byref(pl))
+        assert pl.value == 0
+        out[f"gen_r2c_{n0}x{n1}"] = rel(xh, np.fft.rfft2(x))
+        # c2r of a spectrum that is NOT Hermitian in its kx = 0 / Nyquist columns: FFTW transforms y first
+        # (complex) and x last (c2r, imaginary parts of the two self-conjugate entries ignored)
+        yh = rng.standard_normal((n1, n0 // 2 + 1)) + 1j * rng.standard_normal((n1, n0 // 2 + 1))
+        y = np.zeros((n1, n0))
+        pl = plan("c2r", n0, n1, yh, y)
+        keep = yh.copy()
+        lib.dfftw_execute_dft_c2r(byref(pl), ptr(yh), ptr(y))
+        lib.dfftw_destroy_plan(byref(pl))
+        want = np.fft.irfft(np.fft.ifft(keep, axis=0), n=n0, axis=1) * (n0 * n1)
+        out[f"gen_c2r_{n0}x{n1}"] = rel(y, want)
+    # generic IN-PLACE plan (padded real rows), shape different from the context's
+    n0, n1 = 20, 12
+    z = np.zeros((n1, n0 + 2)); z[:, :n0] = np.random.default_rng(9).standard_normal((n1, n0))
+    want = np.fft.rfft2(z[:, :n0])
+    pl = plan("r2c", n0, n1, z, z)
+    lib.dfftw_execute_dft_r2c(byref(pl), ptr(z), ptr(z))
+    out["gen_inplace"] = rel(z.view(complex), want)
+    # error paths of the status-returning forms: executing out of place with an in-place plan, a destroyed plan,
+    # lengths that are not 2-3-5 smooth
+    w = np.zeros_like(z)
+    assert lib.fftw_execute(pl.value, 0, ptr(z), ptr(w)) != 0 and b"in place" in lib.fftw_last_error()
+    assert lib.fftw_execute(pl.value, 1, ptr(z), ptr(z)) != 0
+    hv = pl.value
+    lib.dfftw_destroy_plan(byref(pl))
+    assert lib.fftw_execute(hv, 0, ptr(z), ptr(z)) != 0 and b"plan handle" in lib.fftw_last_error()
+    bad = C.c_longlong(0)
+    assert lib.fftw_plan_2d(0, 14, 16, 1, byref(bad)) != 0 and bad.value == 0
+    for k, v in out.items():
+        assert v <= 1e-13, (k, v, out)
+    return out
+
+
+def check_cfl(core, p, seed=91):
+    """get_max_cfl / get_cfl_dt (cfl_util.f90:35-113) on one slab, resident fields."""
+    s = initial_state(p, seed=seed)
+    for n in ("u", "v", "w"):
+        core.upload(n, getattr(s, n))
+    c_ref = O.get_max_cfl(s, p, O.LocalComm())
+    d_ref = O.get_cfl_dt(s, p, O.LocalComm(), 0.0625)
+    c_got, d_got = core.max_cfl(p.dt), core.cfl_dt(0.0625)
+    out = {"max_cfl": abs(c_got - c_ref) / c_ref, "cfl_dt": abs(d_got - d_ref) / d_ref}
+    for k, v in out.items():
+        assert v <= 1e-15, (k, v, out)
+    # the maximum sits in one component: make each of u, v, w the binding one in turn
+    for n in ("v", "w"):
+        t = getattr(s, n).copy(); t[p.nz // 2, 3, 5] = 50.0
+        core.upload(n, t)
+        setattr(s, n, t)
+        assert abs(core.cfl_dt(0.1) - O.get_cfl_dt(s, p, O.LocalComm(), 0.1)) <= 1e-15 * core.cfl_dt(0.1), n
+    return out
+
+
+def check_variable_dt_steps(core, p, nsteps=10, cfl=0.0625, tol=1e-9, mode="core", seed=43):
+    """use_cfl_dt = .true. as LES_channel_Re1000 ships it (lesgo.conf:117): every step takes dt = get_cfl_dt(),
+    tadv1 = 1 + dt/(2 dt_f), tadv2 = 1 - tadv1 (main.f90:135-144); the first step is forced to first-order Euler by
+    dt_f = get_cfl_dt * huge (initialize.f90:192-199) and RHS_f = RHS (main.f90:273-280).  Each side computes its OWN
+    dt from its own fields (device: lesgo_gpu_cfl_dt), so the dt sequences are compared too."""
+    import dataclasses
+    p = dataclasses.replace(p)                     # the oracle driver mutates dt, tadv1, tadv2
+    sp = O.Spectral(p)
+    nx, nz = p.nx, p.nz
+    G = O.test_filter_kernel(sp)
+    s = initial_state(p, seed=seed)
+    for n in ("u", "v", "w"):
+        core.upload(n, getattr(s, n))
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+        core.upload(n, np.zeros(core.dims.shape))
+    O.cfl_dt_start(s, p, O.LocalComm(), cfl)
+    import sys as _sys
+    dt_dev = core.cfl_dt(cfl) * _sys.float_info.max
+    dts = []
+    for it in range(nsteps):
+        O.cfl_dt_advance(s, p, O.LocalComm(), cfl)
+        O.step(s, sp, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=G)
+        dt_f = dt_dev
+        dt_dev = core.cfl_dt(cfl)
+        t1 = 1.0 + 0.5 * dt_dev / dt_f
+        kw = step_kwargs_pre_dyn(p, it, mode)
+        kw.update(dt=dt_dev, tadv1=t1, tadv2=1.0 - t1)
+        core.step(**kw)
+        dts.append((dt_dev, p.dt, t1, p.tadv1))
+    assert dts[0][2] == 1.0 and dts[0][3] == 1.0, "Euler start"
+    assert len({d[0] for d in dts}) > 1, "dt must actually vary"
+    out = {"dt": max(abs(a - b) / b for a, b, _, _ in dts), "tadv1": max(abs(a - b) for _, _, a, b in dts)}
+    for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz"):
+        g = core.download(n)
+        r = getattr(s, n)
+        hi = nz + 1 if n in ("w", "RHSz", "p") else nz
+        out[n] = rel(g[1:hi, :, :nx], r[1:hi, :, :nx])
+    for k, v in out.items():
+        assert v <= tol, (k, v, out)
+    return out

@@ -34,8 +34,19 @@ def test_header_and_binding_agree():
     assert sorted(SYMBOLS) == hs
 
 
+def header_fftw_symbols():
+    txt = open(os.path.join(ROOT, "include", "lesgo_gpu.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(dfftw_[a-z0-9_]+_)\s*\(", txt)))
+
+
 def test_library_exports_every_header_symbol(lib):
     for name in header_symbols():
+        assert hasattr(lib.dll, name), name
+    from lesgo_b200.lib import FFTW_SYMBOLS
+    fs = header_fftw_symbols()
+    assert len(fs) == 5 and sorted(FFTW_SYMBOLS) == fs
+    for name in fs:                      # the gfortran-mangled FFTW3 legacy API
         assert hasattr(lib.dll, name), name
 
 

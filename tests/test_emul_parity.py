@@ -209,3 +209,32 @@ def test_emul_variants(env, grid, what):
     r = subprocess.run([sys.executable, os.path.join(here, "variant_check.py"), "--emul", "--grid", grid, "--what", what],
                        env=e, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "variant_check ok" in r.stdout, (env, r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_emul_fftw_shim():
+    """dfftw_plan_dft_r2c_2d / c2r_2d / execute / destroy_plan by reference, module fft's plans and
+    turbine_indicator's out-of-place plans of another size (generic 2-3-5 transform)."""
+    from helpers import check_fftw_shim
+    p = O.Params(nx=16, ny=32, Nz=3)
+    c = core_for(p)
+    print(check_fftw_shim(emul_library(), c, p))
+
+
+def test_emul_cfl_and_variable_dt():
+    """get_max_cfl / get_cfl_dt on one slab, and a use_cfl_dt run (Euler start, tadv1 = 1 + dt/(2 dt_f))."""
+    from helpers import check_cfl, check_variable_dt_steps
+    p = O.Params(nx=16, ny=16, Nz=8, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5)
+    check_cfl(core_for(p), p)
+    print(check_variable_dt_steps(core_for(p), p, nsteps=4, tol=1e-11))
+    p = O.Params(nx=16, ny=16, Nz=6, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False)
+    print(check_variable_dt_steps(core_for(p), p, nsteps=3, tol=1e-11, mode="full"))
+
+
+@pytest.mark.parametrize("p2p", [False, True])
+def test_emul_multirank_ragged_ky_split(p2p):
+    """ny not divisible by nproc (the reference has no such restriction): three ranks share 16 ky rows as 6 + 6 + 4."""
+    from helpers import check_multirank_steps
+    kw = dict(nx=16, ny=16, Nz=6, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5)
+    print(check_multirank_steps(emul_library(), kw, 3, nsteps=2, p2p=p2p))
+    kw = dict(nx=16, ny=16, Nz=9, lbc_mom=1, ubc_mom=0, sgs=True)     # three planes per rank: padded blocks outgrow a field
+    print(check_multirank_steps(emul_library(), kw, 3, nsteps=2, p2p=p2p))

@@ -63,3 +63,13 @@ def test_multi_gpu_p2p_transposes(nproc):
     out = check_multirank_steps(lesgo_b200.load_library(), kw, nproc, nsteps=3, tol=1e-11, p2p=True,
                                 device_of=lambda coord: coord)
     print(nproc, out)
+
+
+def test_two_gpus_large_shared_memory_kernels():
+    """Per-device kernel attributes: two ranks as threads of one process, one GPU each, at a plane size whose
+    kernels need > 48 KB of dynamic shared memory (the opt-in must have been made on BOTH devices)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    kw = dict(nx=512, ny=512, Nz=8, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5)
+    out = check_multirank_steps(lesgo_b200.load_library(), kw, 2, nsteps=1, tol=1e-12, device_of=lambda coord: coord)
+    print(out)

@@ -694,7 +694,7 @@ def check_variable_dt_steps(core, p, nsteps=10, cfl=0.0625, tol=1e-9, mode="core
         core.step(**kw)
         dts.append((dt_dev, p.dt, t1, p.tadv1))
     assert dts[0][2] == 1.0 and dts[0][3] == 1.0, "Euler start"
-    assert len({d[0] for d in dts}) > 1, "dt must actually vary"
+    assert nsteps == 1 or len({d[0] for d in dts}) > 1, "dt must actually vary"
     out = {"dt": max(abs(a - b) / b for a, b, _, _ in dts), "tadv1": max(abs(a - b) for _, _, a, b in dts)}
     for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz"):
         g = core.download(n)

@@ -150,6 +150,42 @@ template <> struct Dft<16> {
     }
 };
 
+// 32 = 2 x 16, decimation in time: X[k] = E[k] + W32^k O[k], X[k+16] = E[k] - W32^k O[k]
+template <> struct Dft<32> {
+    static LG_HD void run(cplx* v) {
+        cplx e[16], o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+        Dft<16>::run(e);
+        Dft<16>::run(o);
+        const double h = 0.70710678118654752440;
+        // cos, sin (2 pi k / 32), k = 1, 2, 3, 5, 6, 7 (k = 4 is h, h)
+        const double c1 = 0.98078528040323044913, s1 = 0.19509032201612826785;
+        const double c2 = 0.92387953251128675613, s2 = 0.38268343236508977173;
+        const double c3 = 0.83146961230254523708, s3 = 0.55557023301960222474;
+#define LG_BF32(k, t)  { const cplx t_ = (t); v[k] = cadd(e[k], t_); v[(k) + 16] = csub(e[k], t_); }
+#define LG_TW32(a, c, s) make_double2(fma((a).x, (c), (a).y * (s)), fma((a).y, (c), -(a).x * (s)))   /* a * (c - i s) */
+        LG_BF32(0, o[0])
+        LG_BF32(1, LG_TW32(o[1], c1, s1))
+        LG_BF32(2, LG_TW32(o[2], c2, s2))
+        LG_BF32(3, LG_TW32(o[3], c3, s3))
+        LG_BF32(4, make_double2(h * (o[4].x + o[4].y), h * (o[4].y - o[4].x)))
+        LG_BF32(5, LG_TW32(o[5], s3, c3))
+        LG_BF32(6, LG_TW32(o[6], s2, c2))
+        LG_BF32(7, LG_TW32(o[7], s1, c1))
+        LG_BF32(8, cmul_mi(o[8]))
+        LG_BF32(9, LG_TW32(o[9], -s1, c1))
+        LG_BF32(10, LG_TW32(o[10], -s2, c2))
+        LG_BF32(11, LG_TW32(o[11], -s3, c3))
+        LG_BF32(12, make_double2(h * (o[12].y - o[12].x), -h * (o[12].x + o[12].y)))
+        LG_BF32(13, LG_TW32(o[13], -c3, s3))
+        LG_BF32(14, LG_TW32(o[14], -c2, s2))
+        LG_BF32(15, LG_TW32(o[15], -c1, s1))
+#undef LG_BF32
+#undef LG_TW32
+    }
+};
+
 // Good-Thomas prime-factor composition for coprime N1, N2 (no twiddles):
 // input n = (N2*n1 + N1*n2) mod N, output k with k = k1 (mod N1), k = k2 (mod N2).
 template <int N1, int N2> struct DftPfa {
@@ -190,6 +226,7 @@ template <int N1, int N2> struct DftPfa {
 template <> struct Dft<6> { static LG_HD void run(cplx* v) { DftPfa<2, 3>::run(v); } };
 template <> struct Dft<10> { static LG_HD void run(cplx* v) { DftPfa<2, 5>::run(v); } };
 template <> struct Dft<12> { static LG_HD void run(cplx* v) { DftPfa<4, 3>::run(v); } };
+template <> struct Dft<24> { static LG_HD void run(cplx* v) { DftPfa<8, 3>::run(v); } };
 
 // ---------------------------------------------------------------------------------
 // Plans.  LG_PLAN(N, R1, R2, R3, R4): radices multiply to N; unused stages are 1.
@@ -455,6 +492,140 @@ LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St s
         tile_stage<N, P::R4, P::R1 * P::R2 * P::R3, INV, NF, FFT_FASTEST, NTHR, true, false, ST_BUF, ES>(buf, W + PI::off4, foff, ld, st);
     }
     __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------
+// Two-stage plans N = R1 * R2 with register butterflies of radix 16 ... 32 (column transforms of the y pass).
+// A column makes ONE round trip through shared memory instead of the two of a three-stage radix-8 plan, with
+// one block barrier inside the transform instead of two, and about half the address arithmetic per point: the
+// y passes are bound by the instructions and shared-memory wavefronts they issue per point, not by arithmetic
+// (profiles/r4_y2stage.md).
+//   stage 1 (radix R1, no twiddles):  work item j < N/R1 = R2 reads elements j + r*R2, writes slot R1*j + r
+//   stage 2 (radix R2, Ns = R1):      work item j < N/R2 = R1 reads slots j + r*R1 ( * W_N^{j r}), writes element j + r*R1
+// Shared-memory slot s of a column lives at (s + s/R1) * ES + f: the stage-1 stores of neighbouring work items are
+// (R1+1) elements apart (odd -> the two halves of a 128-byte wavefront), the stage-2 loads are contiguous in j.
+// Twiddles: W_N^{j r} = T_hi[r & ~7][j] * T_lo[r & 7][j] from a table of 7 + (R2-1)/8 rows of R1 entries (one
+// multiplication deep).
+// ---------------------------------------------------------------------------------
+#ifndef LG_Y2STAGE
+#define LG_Y2STAGE 1
+#endif
+template <int N> struct Plan2 { static constexpr bool on = false; static constexpr int R1 = 1, R2 = 1; };
+#if LG_Y2STAGE
+template <> struct Plan2<512> { static constexpr bool on = true; static constexpr int R1 = 16, R2 = 32; };
+template <> struct Plan2<768> { static constexpr bool on = true; static constexpr int R1 = 32, R2 = 24; };
+#endif
+template <int N> struct Plan2Info {
+    typedef Plan2<N> P;
+    static constexpr int RMAX = P::R1 > P::R2 ? P::R1 : P::R2;
+    static constexpr int T1 = N / P::R1, T2 = N / P::R2;
+    static constexpr int per1 = RMAX / P::R1;                            // stage-1 butterflies a thread may hold
+    static constexpr int tpf1 = (T1 + per1 - 1) / per1;
+    static constexpr int tpf = tpf1 > T2 ? tpf1 : T2;                    // threads per transform
+    static constexpr int nrows = 7 + (P::R2 - 1) / 8;
+    static constexpr int twlen = nrows * P::R1;
+    static constexpr int slots = N + N / P::R1 + 1;                      // padded column length
+};
+
+template <int N, bool INV, int NF, int NTHR, bool LD_BUF, bool ST_BUF, int ES, class FOff, class Ld, class St,
+          class Hook = NoHook>
+LG_D void fft_tile2(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St st, Hook hook = Hook()) {
+    typedef Plan2<N> P;
+    constexpr int R1 = P::R1, R2 = P::R2, T1 = N / R1, T2 = N / R2;
+    static_assert(T1 == R2 && T2 == R1, "two-stage plan");
+    {
+        constexpr int ITEMS = NF * T1, IPT = (ITEMS + NTHR - 1) / NTHR;
+        cplx v[IPT][R1];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int it = threadIdx.x + q * NTHR;
+            if (ITEMS % NTHR == 0 || it < ITEMS) {
+                const int f = it % NF, j = it / NF;
+#pragma unroll
+                for (int r = 0; r < R1; ++r) v[q][r] = ld(f, j + r * T1);
+                if (INV) {
+#pragma unroll
+                    for (int r = 0; r < R1; ++r) v[q][r] = cswap(v[q][r]);
+                }
+                Dft<R1>::run(v[q]);
+                if (INV) {
+#pragma unroll
+                    for (int r = 0; r < R1; ++r) v[q][r] = cswap(v[q][r]);
+                }
+            }
+        }
+        if (LD_BUF) __syncthreads();
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int it = threadIdx.x + q * NTHR;
+            if (ITEMS % NTHR == 0 || it < ITEMS) {
+                const int f = it % NF, j = it / NF;
+                cplx* p = buf + (R1 + 1) * j * ES + foff(f);
+#pragma unroll
+                for (int r = 0; r < R1; ++r) p[r * ES] = v[q][r];
+            }
+        }
+    }
+    __syncthreads();
+    hook();
+    {
+        constexpr int ITEMS = NF * T2, IPT = (ITEMS + NTHR - 1) / NTHR;
+        cplx v[IPT][R2];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int it = threadIdx.x + q * NTHR;
+            if (ITEMS % NTHR == 0 || it < ITEMS) {
+                const int f = it % NF, j = it / NF;
+                const cplx* p = buf + j * ES + foff(f);
+#pragma unroll
+                for (int r = 0; r < R2; ++r) v[q][r] = p[r * (R1 + 1) * ES];
+                // twiddles W_N^{j r}: rows 0..6 hold r = 1..7, rows 7.. hold r = 8, 16, 24
+                cplx lo[8];
+#pragma unroll
+                for (int m = 1; m < 8 && m < R2; ++m) lo[m] = W[(m - 1) * R1 + j];
+#pragma unroll
+                for (int hb = 0; hb < R2; hb += 8) {
+                    cplx hi = make_double2(1.0, 0.0);
+                    if (hb > 0) hi = W[(6 + hb / 8) * R1 + j];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const int r = hb + m;
+                        if (r == 0 || r >= R2) continue;
+                        const cplx w = hb == 0 ? lo[m] : (m == 0 ? hi : cmul(hi, lo[m]));
+                        v[q][r] = INV ? cmulc(v[q][r], w) : cmul(v[q][r], w);
+                    }
+                }
+                if (INV) {
+#pragma unroll
+                    for (int r = 0; r < R2; ++r) v[q][r] = cswap(v[q][r]);
+                }
+                Dft<R2>::run(v[q]);
+                if (INV) {
+#pragma unroll
+                    for (int r = 0; r < R2; ++r) v[q][r] = cswap(v[q][r]);
+                }
+            }
+        }
+        if (ST_BUF) __syncthreads();
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int it = threadIdx.x + q * NTHR;
+            if (ITEMS % NTHR == 0 || it < ITEMS) {
+                const int f = it % NF, j = it / NF;
+#pragma unroll
+                for (int r = 0; r < R2; ++r) st(f, j + r * R1, v[q][r]);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// column tiles of the y pass: the two-stage plan (USE2, chosen per kernel by YCfg) or the Stockham stages above
+template <int N, bool INV, int NF, int NTHR, bool LD_BUF, bool ST_BUF, int ES, bool USE2, class FOff, class Ld, class St,
+          class Hook = NoHook>
+LG_D void fft_tile_cols(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St st, Hook hook = Hook()) {
+    if constexpr (USE2) fft_tile2<N, INV, NF, NTHR, LD_BUF, ST_BUF, ES>(buf, W, foff, ld, st, hook);
+    else fft_tile<N, INV, NF, true, NTHR, LD_BUF, ST_BUF, ES>(buf, W, foff, ld, st, hook);
 }
 
 // 16-byte asynchronous global -> shared copies (LDGSTS): prefetch of the next tile while the

@@ -330,7 +330,28 @@ template <int NIN, int NOUT, bool MULTI, int NOUT2 = 0> struct YCfg {
     static constexpr int NMAX = NMAX0 > NOUT2 ? NMAX0 : NOUT2;
     static constexpr int NS = (NIN == 0) ? NOUT : ((NOUT == 0) ? NIN : (NIN < NOUT ? NIN : NOUT));  // spectral (small) length
     static constexpr int max2(int a, int b) { return a > b ? a : b; }
-    template <int N> static constexpr int thr(int tc) { return TileGeom<(N > 0 ? N : 8)>::threads(tc) * (N > 0); }
+    // Two-stage column plans (fft_core.h Plan2) per kernel, by measurement on B200 at 512 x 512 x 256
+    // (profiles/r4_y2stage.md): they win for the forward-only pass and for filt_da's pass with the padded second
+    // output, with 8 columns per tile; the pad / truncate passes keep the three-stage plans (the radix-32
+    // butterflies cost 255 registers, which leaves one or two resident blocks).  LG_Y2_POLICY bits: 1 forward only,
+    // 2 same-size + padded output, 4 inverse only with several outputs, 8 everything else.
+#ifndef LG_Y2_POLICY
+#define LG_Y2_POLICY 3
+#endif
+    static constexpr bool ALL2 = (NIN <= 0 || Plan2<(NIN > 0 ? NIN : 8)>::on) && (NOUT <= 0 || Plan2<(NOUT > 0 ? NOUT : 8)>::on) &&
+                                 (NOUT2 <= 0 || Plan2<(NOUT2 > 0 ? NOUT2 : 8)>::on);
+    static constexpr int KIND = (NOUT == 0) ? 1 : (NOUT2 > 0 ? 2 : ((NIN == 0 && MULTI) ? 4 : 8));
+    static constexpr bool USE2 = ALL2 && (LG_Y2_POLICY & KIND) != 0;
+    template <int N> static constexpr int thr(int tc) {
+        return N <= 0 ? 0 : (USE2 ? tc * Plan2Info<(N > 0 ? N : 8)>::tpf : TileGeom<(N > 0 ? N : 8)>::threads(tc));
+    }
+    template <int N> static constexpr int twl() {
+        return N <= 0 ? 0 : (USE2 ? Plan2Info<(N > 0 ? N : 8)>::twlen : PlanInfo<(N > 0 ? N : 8)>::twlen);
+    }
+    // offset of the table a kernel reads inside the per-length device table (Stockham stage tables first)
+    static constexpr int TWOFF_IN = (NIN > 0 && USE2) ? PlanInfo<(NIN > 0 ? NIN : 8)>::twlen : 0;
+    static constexpr int TWOFF_OUT = (NOUT > 0 && USE2) ? PlanInfo<(NOUT > 0 ? NOUT : 8)>::twlen : 0;
+    static constexpr int TWOFF_OUT2 = (NOUT2 > 0 && USE2) ? PlanInfo<(NOUT2 > 0 ? NOUT2 : 8)>::twlen : 0;
     // 4 columns = 64 contiguous bytes per row; 8 columns (128 B) measured no faster (30.8 vs 30.0 ms/step)
 #ifndef LG_Y12_TC2
 #define LG_Y12_TC2 0
@@ -344,17 +365,23 @@ template <int NIN, int NOUT, bool MULTI, int NOUT2 = 0> struct YCfg {
     // and 160 registers (no spills, 12 warps/SM): pad 3.99 / 4.07 ms, trunc 1.73 / 1.80 ms against
     // 3.99 / 1.81 ms -- no difference, off by default
     static constexpr bool R12 = LG_Y12_TC2 && regs0 == 80;
-    static constexpr int TC = (max2(thr<NIN>(4), thr<NOUT>(4)) <= 512 && !R12) ? 4 : 2;   // (2 columns for the 768 passes: 30.8 ms)
-    static constexpr int NTHR = ((max2(thr<NIN>(TC), thr<NOUT>(TC)) + 31) / 32) * 32;
-    static constexpr int regs = R12 ? LG_Y12_REGS : regs0;
+#ifndef LG_Y2_TC
+#define LG_Y2_TC 8
+#endif
+#ifndef LG_Y2_REGS
+#define LG_Y2_REGS 200
+#endif
+    static constexpr int TC = USE2 ? LG_Y2_TC : ((max2(thr<NIN>(4), thr<NOUT>(4)) <= 512 && !R12) ? 4 : 2);   // (2 columns for the 768 passes: 30.8 ms)
+    static constexpr int NTHR = ((max2(max2(thr<NIN>(TC), thr<NOUT>(TC)), USE2 ? thr<NOUT2>(TC) : 0) + 31) / 32) * 32;
+    static constexpr int regs = USE2 ? LG_Y2_REGS : (R12 ? LG_Y12_REGS : regs0);
     static constexpr int SL = SmemLen<NMAX>::value;          // work buffer row count (padded)
     static constexpr int SLS = SmemLen<NS>::value;           // spectrum buffer (MULTI)
     static constexpr int NBUF = MULTI ? 2 : 1;
     static constexpr int BUFS = TC * SL + (MULTI ? TC * (NOUT2 > 0 ? SLS : SL) : 0);
-    static constexpr int TWI = PlanInfo<(NIN > 0 ? NIN : 8)>::twlen * (NIN > 0);
+    static constexpr int TWI = twl<NIN>();
     // with NOUT2 the forward and inverse tables of the same length are stored once (shared memory is tight)
-    static constexpr int TWO = (NOUT2 > 0) ? 0 : PlanInfo<(NOUT > 0 ? NOUT : 8)>::twlen * (NOUT > 0);
-    static constexpr int TWO2 = PlanInfo<(NOUT2 > 0 ? NOUT2 : 8)>::twlen * (NOUT2 > 0);
+    static constexpr int TWO = (NOUT2 > 0) ? 0 : twl<NOUT>();
+    static constexpr int TWO2 = twl<NOUT2>();
     // PREF (-DLG_Y_PREF=1): the next tile is prefetched (cp.async) into a staging buffer while the current
     // one is being transformed, for the 3/2-rule pad passes (where the staging buffer does not cost a
     // resident block).  Measured: no gain (4.06 against 3.99 ms) -- the y passes are bound by the
@@ -363,7 +390,7 @@ template <int NIN, int NOUT, bool MULTI, int NOUT2 = 0> struct YCfg {
 #ifndef LG_Y_PREF
 #define LG_Y_PREF 0
 #endif
-    static constexpr bool PREF = LG_Y_PREF && NIN > 0 && NOUT > NIN && !MULTI;
+    static constexpr bool PREF = LG_Y_PREF && NIN > 0 && NOUT > NIN && !MULTI && !USE2;
     static constexpr int STG = PREF ? NIN * TC : 0;
     static constexpr size_t smem = size_t(BUFS + TWI + TWO + TWO2 + STG) * sizeof(cplx);
     // resident blocks: the register budget is only capped as far as shared memory lets blocks fit
@@ -448,7 +475,7 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
             if constexpr (NOUT == 0) {
                 // forward only: straight to global with Nyquist-row zeroing
                 double* dst = F.out[0].dst + poff(k, a.dst_plane, a.dst_ring) + 2 * c0;
-                fft_tile<NIN, false, TC, true, NTHR, false, false, TC>(buf, Win, foff,
+                fft_tile_cols<NIN, false, TC, NTHR, false, false, TC, C::USE2>(buf, Win, foff,
                     [&](int f, int i) {
                         if (!colok) return make_double2(0.0, 0.0);
                         return y_input(F, a, src, k, c0, i, f);
@@ -471,7 +498,7 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
                 };
                 if (C::PREF && stg) {
                     const double sc = F.combo ? F.c0 : 1.0;
-                    fft_tile<NIN, false, TC, true, NTHR, false, !MULTI, TC>(buf, Win, foff,
+                    fft_tile_cols<NIN, false, TC, NTHR, false, !MULTI, TC, C::USE2>(buf, Win, foff,
                         [&](int f, int i) {
                             if (!colok) return make_double2(0.0, 0.0);
                             const cplx v = stg[i * TC + f];
@@ -479,7 +506,7 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
                         },
                         keep, [&]() { ypass_prefetch<NIN, NOUT, MULTI>(stg, a, next, nwork); });
                 } else {
-                    fft_tile<NIN, false, TC, true, NTHR, false, !MULTI, TC>(buf, Win, foff,
+                    fft_tile_cols<NIN, false, TC, NTHR, false, !MULTI, TC, C::USE2>(buf, Win, foff,
                         [&](int f, int i) {
                             if (!colok) return make_double2(0.0, 0.0);
                             return y_input(F, a, src, k, c0, i, f);
@@ -488,6 +515,7 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
                 }
             }
         } else {
+#pragma unroll 8
             for (int it = threadIdx.x; it < TC * NS; it += NTHR) {
                 int f = it % TC, i = it / TC;
                 cplx v = make_double2(0.0, 0.0);
@@ -510,7 +538,7 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
                 if (mode == Y_IKX && o_copy >= 0) continue;          // written by the COPY transform
                 double* dst = F.out[o].dst + poff(k, a.dst_plane, a.dst_ring) + 2 * c0;
                 double* dst_x = (mode == Y_COPY && o_ikx >= 0) ? F.out[o_ikx].dst + poff(k, a.dst_plane, a.dst_ring) + 2 * c0 : nullptr;
-                fft_tile<NOUT, true, TC, true, NTHR, !MULTI, false, TC>(buf, Wout, foff,
+                fft_tile_cols<NOUT, true, TC, NTHR, !MULTI, false, TC, C::USE2>(buf, Wout, foff,
                     [&](int f, int i) {
                         // row i of the (possibly padded) output spectrum <- small row is
                         int is = i;
@@ -542,7 +570,7 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
             if (F.out2) {
                 // padd (fft.f90:60-69) + inverse transform of length NOUT2 of the same spectrum
                 double* dst2 = F.out2 + long(k) * a.dst2_plane + 2 * c0;
-                fft_tile<NOUT2, true, TC, true, NTHR, false, false, TC>(buf, Wout2, foff,
+                fft_tile_cols<NOUT2, true, TC, NTHR, false, false, TC, C::USE2>(buf, Wout2, foff,
                     [&](int f, int i) {
                         int is;
                         if (i < NS / 2) is = i;
@@ -579,9 +607,9 @@ k_ypass(const __grid_constant__ YArgs a, const cplx* __restrict__ Wing, const cp
     cplx* Win = sm + C::BUFS;
     cplx* Wout = NOUT2 > 0 ? Win : Win + C::TWI;        // NOUT2: same length, same table
     cplx* Wout2 = Win + C::TWI + C::TWO;
-    if (NIN > 0) load_table(Win, Wing, C::TWI);
-    if (NOUT > 0 && NOUT2 == 0) load_table(Wout, Woutg, C::TWO);
-    if (NOUT2 > 0) load_table(Wout2, Wout2g, C::TWO2);
+    if (NIN > 0) load_table(Win, Wing + C::TWOFF_IN, C::TWI);
+    if (NOUT > 0 && NOUT2 == 0) load_table(Wout, Woutg + C::TWOFF_OUT, C::TWO);
+    if (NOUT2 > 0) load_table(Wout2, Wout2g + C::TWOFF_OUT2, C::TWO2);
     __syncthreads();
     const int ntc = (a.ncols + TC - 1) / TC;
     const long nwork = long(ntc) * a.nplanes * a.nfields;

@@ -23,6 +23,8 @@ int launch_ypass_pad2(int ny, const YArgs& a, int nfields, int nplanes, const cp
 bool size_supported(int n_small);
 // radices and stage-twiddle-table length of the plan for complex length n (false if none)
 bool plan_lookup(int n, PlanDesc* out);
+// two-stage column plan (fft_core.h Plan2) of the y passes for length n, if one exists
+bool plan2_lookup(int n, int* r1, int* r2);
 
 // products + forward x transform of convec, marching up z (prodfwd_kernels.h)
 struct ProdArgs;

@@ -159,7 +159,7 @@ cplx unit_root(long m, long n) {   // exp(-2 pi i m / n), long double accuracy
 
 // stage twiddles of Plan<n> in the layout fft_core.h's stage_load reads:
 // for stage s >= 2 (radix R, Ns = product of earlier radices): T[(r-1)*Ns + k] = W_n^{k r n/(Ns R)}
-int make_stage_twiddles(lesgo_gpu_ctx* c, cplx** dst, int n) {
+int make_stage_twiddles(lesgo_gpu_ctx* c, cplx** dst, int n, bool columns = false) {
     PlanDesc d;
     if (!plan_lookup(n, &d)) return c->fail("no FFT plan for length " + std::to_string(n));
     std::vector<cplx> h;
@@ -173,6 +173,15 @@ int make_stage_twiddles(lesgo_gpu_ctx* c, cplx** dst, int n) {
         ns *= R;
     }
     if (int(h.size()) != d.twlen) return c->fail("internal: stage twiddle table length mismatch");
+    int r1 = 0, r2 = 0;
+    if (columns && plan2_lookup(n, &r1, &r2)) {
+        // y passes: the table of the two-stage column plan (fft_core.h fft_tile2) follows the Stockham stage tables:
+        // rows r = 1..7, then r = 8, 16, 24 of W_n^{j r}, j < R1
+        for (int r = 1; r < 8; ++r)
+            for (int j = 0; j < r1; ++j) h.push_back(unit_root(long(j) * r, n));
+        for (int r = 8; r < r2; r += 8)
+            for (int j = 0; j < r1; ++j) h.push_back(unit_root(long(j) * r, n));
+    }
     return upload_table(c, dst, h);
 }
 
@@ -1492,8 +1501,8 @@ int lesgo_gpu_create(const lesgo_gpu_dims* d, lesgo_gpu_ctx** out) {
     rc |= make_half_twiddles(c, &c->Whx, c->nx / 2);
     rc |= make_stage_twiddles(c, &c->Wxb, c->nx2 / 2);
     rc |= make_half_twiddles(c, &c->Whxb, c->nx2 / 2);
-    rc |= make_stage_twiddles(c, &c->Wy, c->ny);
-    rc |= make_stage_twiddles(c, &c->Wyb, c->ny2);
+    rc |= make_stage_twiddles(c, &c->Wy, c->ny, true);
+    rc |= make_stage_twiddles(c, &c->Wyb, c->ny2, true);
     if (rc) { std::string m = c->err; return bail(m); }
     *out = c;
     lesgo_gpu_fftw_bind(c, d);          // the dfftw_* symbols serve this context's plans (fftw_shim.cu)

@@ -69,6 +69,12 @@ int launch_ypass_pad2(int ny, const YArgs& a, int nfields, int nplanes, const cp
     return -1;
 }
 #define LG_SUP(S, B) if (n == S) return true;
+bool plan2_lookup(int n, int* r1, int* r2) {
+#define LG_PL2(N) if (n == N && Plan2<N>::on) { *r1 = Plan2<N>::R1; *r2 = Plan2<N>::R2; return true; }
+    LG_PL2(512) LG_PL2(768)
+#undef LG_PL2
+    return false;
+}
 bool plan_lookup(int n, PlanDesc* out) {
 #define LG_PL(N) if (n == N) { *out = plan_desc<N>(); return true; }
     LG_PL(8) LG_PL(12) LG_PL(16) LG_PL(24) LG_PL(32) LG_PL(36) LG_PL(40) LG_PL(48) LG_PL(60) LG_PL(64) LG_PL(72)

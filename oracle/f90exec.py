@@ -1,0 +1,1619 @@
+"""f90exec -- a small Fortran-90 subset interpreter, TEST INFRASTRUCTURE ONLY.
+
+Why it exists.  The parity oracle (oracle/lesgo_oracle.py) is a hand-written restatement of the reference
+and no Fortran compiler, FFTW or MPI exists in this container or on the GPU boxes (probes in BASELINE.md), so
+the restatement could never be compared with the reference itself.  This module executes the REFERENCE'S OWN
+SOURCE FILES, statement by statement, where they lie under /root/reference: it preprocesses (cpp #ifdef with
+the reference's default build flags), parses and interprets the subset of Fortran 90 those files use -- modules,
+subroutines / functions, explicit- and assumed-shape arrays with arbitrary lower bounds, array sections, whole-
+array expressions, do / if / select case, user-defined operators, SAVE variables, allocate -- on NumPy arrays in
+IEEE double precision, in the reference's statement and evaluation order.  What it does NOT reproduce: FFTW's
+internal rounding (the dfftw_execute_* calls are bound by the caller, to pocketfft) and gfortran's code
+generation.  oracle/make_reference_fixtures.py uses it to run the reference's derivatives.f90, convec.f90,
+press_stag_array.f90, tridag_array.f90, fft.f90, emul_complex.f90, forcing.f90 (project), cfl_util.f90 and the
+time-loop body of main.f90, and freezes the outputs under tests/golden/ref_*.npz, which pin the oracle and the
+CUDA path.  Nothing is copied from the reference: its text is read at run time and never stored in this repo.
+
+Only tests/ and oracle/ may import this module (like the rest of oracle/).
+"""
+from __future__ import annotations
+
+import math
+import re
+import sys
+
+import numpy as np
+
+
+class FortranError(RuntimeError):
+    pass
+
+
+class FStop(Exception):
+    pass
+
+
+# ------------------------------------------------------------------------------------------------
+# arrays with Fortran bounds
+# ------------------------------------------------------------------------------------------------
+class FArray:
+    """A Fortran array: NumPy storage (column-major views) plus one lower bound per dimension."""
+    __slots__ = ("a", "lb", "kind")
+
+    def __init__(self, a, lb=None, kind="real"):
+        self.a = a
+        self.lb = tuple(lb) if lb is not None else (1,) * a.ndim
+        self.kind = kind
+
+    @staticmethod
+    def alloc(shape, lb, kind="real", fill=0.0):
+        dt = {"real": np.float64, "integer": np.int64, "logical": np.bool_, "complex": np.complex128}[kind]
+        a = np.empty(tuple(shape), dtype=dt, order="F")
+        a[...] = fill if kind in ("real", "complex") else 0
+        return FArray(a, lb, kind)
+
+    def index(self, subs):
+        """subs: ints or (lo, hi, step) tuples with None for defaults -> (numpy index tuple, all_scalar)."""
+        if len(subs) != self.a.ndim:
+            raise FortranError(f"rank mismatch: {len(subs)} subscripts for rank {self.a.ndim}")
+        idx = []
+        scalar = True
+        for s, lb, n in zip(subs, self.lb, self.a.shape):
+            if isinstance(s, tuple):
+                scalar = False
+                lo, hi, st = s
+                lo = lb if lo is None else lo
+                hi = lb + n - 1 if hi is None else hi
+                st = 1 if st is None else st
+                if st > 0:
+                    if hi < lo:
+                        idx.append(slice(0, 0))
+                        continue
+                    if lo < lb or hi > lb + n - 1:
+                        raise FortranError(f"section {lo}:{hi} outside bounds {lb}:{lb + n - 1}")
+                    idx.append(slice(lo - lb, hi - lb + 1, st))
+                else:
+                    if lo < hi:
+                        idx.append(slice(0, 0))
+                        continue
+                    stop = hi - lb - 1
+                    idx.append(slice(lo - lb, stop if stop >= 0 else None, st))
+            elif isinstance(s, np.ndarray):
+                scalar = False
+                idx.append(s.astype(np.int64) - lb)
+            else:
+                s = int(s)
+                if s < lb or s > lb + n - 1:
+                    raise FortranError(f"subscript {s} outside bounds {lb}:{lb + n - 1}")
+                idx.append(s - lb)
+        return tuple(idx), scalar
+
+
+# ------------------------------------------------------------------------------------------------
+# source -> logical lines
+# ------------------------------------------------------------------------------------------------
+def _cpp_eval(expr, defines):
+    e = re.sub(r"defined\s*\(\s*(\w+)\s*\)", lambda m: " True " if m.group(1) in defines else " False ", expr)
+    e = re.sub(r"defined\s+(\w+)", lambda m: " True " if m.group(1) in defines else " False ", e)
+    e = e.replace("&&", " and ").replace("||", " or ").replace("!", " not ")
+    e = re.sub(r"\b([A-Za-z_]\w*)\b", lambda m: m.group(1) if m.group(1) in ("True", "False", "and", "or", "not") else "False", e)
+    return bool(eval(e))
+
+
+def logical_lines(path, defines):
+    """cpp conditionals, comments, continuations -> [(lineno, lowercased statement text)]."""
+    out = []
+    stack = []                      # (taken_before, active)
+    cur, cur_line = "", 0
+    with open(path, errors="replace") as f:
+        raw = f.read().split("\n")
+    for no, line in enumerate(raw, 1):
+        s = line.strip()
+        if s.startswith("#"):
+            d = s[1:].strip()
+            active = all(a for _, a in stack)
+            if d.startswith("ifdef"):
+                c = d.split()[1] in defines
+                stack.append((c, c))
+            elif d.startswith("ifndef"):
+                c = d.split()[1] not in defines
+                stack.append((c, c))
+            elif d.startswith("if"):
+                c = _cpp_eval(d[2:], defines)
+                stack.append((c, c))
+            elif d.startswith("elif"):
+                t, _ = stack.pop()
+                c = (not t) and _cpp_eval(d[4:], defines)
+                stack.append((t or c, c))
+            elif d.startswith("else"):
+                t, _ = stack.pop()
+                stack.append((True, not t))
+            elif d.startswith("endif"):
+                stack.pop()
+            elif d.startswith(("define", "include", "undef")):
+                pass
+            else:
+                raise FortranError(f"{path}:{no}: cpp directive {s!r}")
+            continue
+        if not all(a for _, a in stack):
+            continue
+        # strip comment (outside strings), lowercase outside strings
+        res, q = [], None
+        for ch in line:
+            if q:
+                res.append(ch)
+                if ch == q:
+                    q = None
+            elif ch in "'\"":
+                q = ch
+                res.append(ch)
+            elif ch == "!":
+                break
+            else:
+                res.append(ch.lower())
+        s = "".join(res).strip()
+        if not s:
+            continue
+        if s.startswith("&"):
+            s = s[1:].lstrip()
+        if not cur:
+            cur_line = no
+        if s.endswith("&"):
+            cur += s[:-1].rstrip() + " "
+            continue
+        cur += s
+        for part in _split_semicolons(cur):
+            if part.strip():
+                out.append((cur_line, part.strip()))
+        cur = ""
+    return out
+
+
+def _split_semicolons(s):
+    if ";" not in s:
+        return [s]
+    parts, q, depth, last = [], None, 0, 0
+    for i, ch in enumerate(s):
+        if q:
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+        elif ch == ";":
+            parts.append(s[last:i])
+            last = i + 1
+    parts.append(s[last:])
+    return parts
+
+
+# ------------------------------------------------------------------------------------------------
+# expressions
+# ------------------------------------------------------------------------------------------------
+_TOK = re.compile(r"""\s*(?:
+    (?P<num>(?:\d+\.(?![a-z]+\.)\d*|\.\d+|\d+)(?:[ed][+-]?\d+)?(?:_\w+)?)
+  | (?P<dot>\.[a-z_]+\.)
+  | (?P<name>[a-z_]\w*)
+  | (?P<str>'(?:[^']|'')*'|"(?:[^"]|"")*")
+  | (?P<op>\*\*|//|==|/=|<=|>=|=>|\(/|/\)|[-+*/()<>,:=%\[\]])
+)""", re.X)
+
+_REL = {"==": "==", "/=": "!=", "<": "<", "<=": "<=", ">": ">", ">=": ">=",
+        ".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
+_BUILTIN_DOT = set(_REL) | {".and.", ".or.", ".not.", ".true.", ".false.", ".eqv.", ".neqv."}
+
+
+def tokenize(s):
+    toks, pos = [], 0
+    while pos < len(s):
+        m = _TOK.match(s, pos)
+        if not m or m.end() == pos:
+            if s[pos:].strip() == "":
+                break
+            raise FortranError(f"cannot tokenize {s[pos:]!r} in {s!r}")
+        pos = m.end()
+        k = m.lastgroup
+        toks.append((k, m.group(k)))
+    return toks
+
+
+class Parser:
+    def __init__(self, text):
+        self.t = tokenize(text)
+        self.i = 0
+        self.text = text
+
+    def peek(self):
+        return self.t[self.i] if self.i < len(self.t) else (None, None)
+
+    def next(self):
+        tok = self.peek()
+        self.i += 1
+        return tok
+
+    def accept(self, val):
+        if self.peek()[1] == val:
+            self.i += 1
+            return True
+        return False
+
+    def expect(self, val):
+        if not self.accept(val):
+            raise FortranError(f"expected {val!r} at token {self.i} of {self.text!r}")
+
+    def done(self):
+        return self.i >= len(self.t)
+
+    # lowest: defined binary operators
+    def expr(self):
+        a = self.p_eqv()
+        while True:
+            k, v = self.peek()
+            if k == "dot" and v not in _BUILTIN_DOT:
+                self.i += 1
+                b = self.p_eqv()
+                a = ("defop", v, a, b)
+            else:
+                return a
+
+    def p_eqv(self):
+        a = self.p_or()
+        while self.peek()[1] in (".eqv.", ".neqv."):
+            op = self.next()[1]
+            b = self.p_or()
+            a = ("bin", op, a, b)
+        return a
+
+    def p_or(self):
+        a = self.p_and()
+        while self.accept(".or."):
+            a = ("bin", ".or.", a, self.p_and())
+        return a
+
+    def p_and(self):
+        a = self.p_not()
+        while self.accept(".and."):
+            a = ("bin", ".and.", a, self.p_not())
+        return a
+
+    def p_not(self):
+        if self.accept(".not."):
+            return ("un", ".not.", self.p_not())
+        return self.p_rel()
+
+    def p_rel(self):
+        a = self.p_add()
+        if self.peek()[1] in _REL:
+            op = _REL[self.next()[1]]
+            return ("bin", op, a, self.p_add())
+        return a
+
+    def p_add(self):
+        if self.peek()[1] in ("+", "-"):
+            op = self.next()[1]
+            a = self.p_mul()
+            if op == "-":
+                a = ("un", "-", a)
+        else:
+            a = self.p_mul()
+        while self.peek()[1] in ("+", "-"):
+            op = self.next()[1]
+            a = ("bin", op, a, self.p_mul())
+        return a
+
+    def p_mul(self):
+        a = self.p_pow()
+        while self.peek()[1] in ("*", "/"):
+            op = self.next()[1]
+            a = ("bin", op, a, self.p_pow())
+        return a
+
+    def p_pow(self):
+        a = self.p_primary()
+        if self.accept("**"):
+            if self.peek()[1] in ("+", "-"):          # a ** -b (extension gfortran accepts)
+                op = self.next()[1]
+                b = self.p_pow()
+                b = ("un", "-", b) if op == "-" else b
+            else:
+                b = self.p_pow()
+            return ("bin", "**", a, b)
+        return a
+
+    def p_primary(self):
+        k, v = self.next()
+        if k == "num":
+            return ("num", _number(v))
+        if k == "str":
+            return ("str", v[1:-1])
+        if k == "dot":
+            if v == ".true.":
+                return ("num", True)
+            if v == ".false.":
+                return ("num", False)
+            raise FortranError(f"unexpected {v} in {self.text!r}")
+        if v == "(":
+            e = self.expr()
+            self.expect(")")
+            return ("paren", e)
+        if v in ("(/", "["):
+            items = []
+            close = "/)" if v == "(/" else "]"
+            while not self.accept(close):
+                items.append(self.expr())
+                self.accept(",")
+            return ("array", items)
+        if k == "name":
+            node = ("name", v)
+            while True:
+                if self.accept("("):
+                    args = self.arglist()
+                    node = ("call", node, args)
+                elif self.accept("%"):
+                    node = ("comp", node, self.next()[1])
+                else:
+                    return node
+        raise FortranError(f"unexpected token {v!r} in {self.text!r}")
+
+    def arglist(self):
+        args = []
+        if self.accept(")"):
+            return args
+        while True:
+            # keyword argument?
+            if self.peek()[0] == "name" and self.i + 1 < len(self.t) and self.t[self.i + 1][1] == "=" :
+                kw = self.next()[1]
+                self.next()
+                args.append(("kw", kw, self.expr()))
+            else:
+                args.append(self.subscript())
+            if self.accept(")"):
+                return args
+            self.expect(",")
+
+    def subscript(self):
+        lo = hi = st = None
+        if self.peek()[1] != ":":
+            lo = self.expr()
+            if self.peek()[1] != ":":
+                return lo
+        self.expect(":")
+        if self.peek()[1] not in (":", ",", ")"):
+            hi = self.expr()
+        if self.accept(":"):
+            st = self.expr()
+        return ("range", lo, hi, st)
+
+
+def _number(v):
+    v = re.sub(r"_\w+$", "", v)
+    if re.fullmatch(r"\d+", v):
+        return int(v)
+    return float(v.replace("d", "e"))
+
+
+def parse_expr(text):
+    p = Parser(text)
+    e = p.expr()
+    if not p.done():
+        raise FortranError(f"trailing tokens in expression {text!r}")
+    return e
+
+
+# ------------------------------------------------------------------------------------------------
+# statements and program units
+# ------------------------------------------------------------------------------------------------
+_TYPE_RE = re.compile(r"^(real|integer|logical|complex|character|double\s*precision|type\s*\(|class\s*\()")
+_PROC_RE = re.compile(r"^(?:(?:recursive|pure|elemental)\s+)*(?:(?:real|integer|logical|complex|double\s*precision)\s*(?:\([^)]*\))?\s+)?"
+                      r"(subroutine|function)\s+(\w+)\s*(?:\(([^)]*)\))?\s*(?:result\s*\(\s*(\w+)\s*\))?\s*(?:bind.*)?$")
+
+
+def _match_paren(s, start):
+    depth, q = 0, None
+    for i in range(start, len(s)):
+        ch = s[i]
+        if q:
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+        elif ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+            if depth == 0:
+                return i
+    raise FortranError(f"unbalanced parentheses in {s!r}")
+
+
+def _split_top(s, sep=","):
+    parts, depth, q, last = [], 0, None, 0
+    i = 0
+    while i < len(s):
+        ch = s[i]
+        if q:
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+        elif ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        elif ch == sep and depth == 0:
+            parts.append(s[last:i])
+            last = i + 1
+        i += 1
+    parts.append(s[last:])
+    return [p.strip() for p in parts]
+
+
+def _find_assign(s):
+    depth, q = 0, None
+    for i, ch in enumerate(s):
+        if q:
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+        elif ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        elif ch == "=" and depth == 0:
+            prev, nxt = s[i - 1] if i else "", s[i + 1] if i + 1 < len(s) else ""
+            if prev in "=/<>" or nxt in "=>":
+                continue
+            return i
+    return -1
+
+
+class Proc:
+    def __init__(self, kind, name, args, result, module, path):
+        self.kind, self.name, self.args, self.result = kind, name, args, result
+        self.module, self.path = module, path
+        self.decls = {}           # name -> Decl
+        self.uses = []            # (module, only-dict or None)
+        self.body = []
+        self.saved = {}           # SAVE variables (persist between calls)
+
+
+class Decl:
+    def __init__(self, kind, dims, attrs, init):
+        self.kind, self.dims, self.attrs, self.init = kind, dims, attrs, init
+
+
+class Module:
+    def __init__(self, name):
+        self.name = name
+        self.decls = {}
+        self.vars = {}
+        self.uses = []
+        self.procs = {}
+        self.operators = {}       # '.muli.' -> [proc names]
+        self.generics = {}        # generic name -> [proc names]
+        self.initialised = False
+
+
+def _parse_decl(text, where):
+    """type-spec [, attrs] [::] entities -> (kind, attrs, [(name, dims, init)])."""
+    m = _TYPE_RE.match(text)
+    kind = m.group(1).replace(" ", "")
+    if kind.startswith(("type", "class")):
+        kind = "derived"
+    if kind == "doubleprecision":
+        kind = "real"
+    rest = text[m.end():] if not kind == "derived" else text[m.end() - 1:]
+    rest = rest.strip()
+    if rest.startswith("("):                     # kind selector / type name
+        e = _match_paren(rest, 0)
+        rest = rest[e + 1:].strip()
+    elif rest.startswith("*"):
+        rest = re.sub(r"^\*\s*\d+", "", rest).strip()
+    if "::" in rest:
+        attr_txt, ent_txt = rest.split("::", 1)
+    else:
+        attr_txt, ent_txt = "", rest
+    attrs = {}
+    for a in _split_top(attr_txt.strip().lstrip(",")):
+        if not a:
+            continue
+        if a.startswith("dimension"):
+            attrs["dimension"] = _split_top(a[a.index("(") + 1:_match_paren(a, a.index("("))])
+        elif a.startswith("intent"):
+            attrs["intent"] = a
+        else:
+            attrs[a.split("(")[0].strip()] = True
+    ents = []
+    for e in _split_top(ent_txt):
+        if not e:
+            continue
+        init = None
+        k = _find_assign(e)
+        if k >= 0:
+            init = e[k + 1:].strip()
+            e = e[:k].strip()
+        elif "=>" in e:
+            e = e.split("=>")[0].strip()
+        dims = attrs.get("dimension")
+        if "(" in e:
+            p = e.index("(")
+            dims = _split_top(e[p + 1:_match_paren(e, p)])
+            e = e[:p].strip()
+        e = re.sub(r"\*\s*\d+$", "", e).strip()
+        ents.append((e, dims, init))
+    return kind, attrs, ents
+
+
+class Interpreter:
+    def __init__(self, defines=("PPMPI", "PPSAFETYMODE"), alloc_fill=0.0):
+        self.defines = set(defines)
+        self.modules = {}
+        self.procs = {}               # external procedures
+        self.externals = {}           # name -> python callable(interp, args)
+        self.alloc_fill = alloc_fill
+        self.trace = False
+        self.nstmt = 0
+
+    # ---- loading -----------------------------------------------------------------------------
+    def load(self, path):
+        lines = logical_lines(path, self.defines)
+        i = 0
+        while i < len(lines):
+            no, s = lines[i]
+            m = re.match(r"^module\s+(\w+)$", s)
+            if m and not s.startswith("module procedure"):
+                i = self._load_module(lines, i, path)
+                continue
+            if _PROC_RE.match(s):
+                pr, i = self._load_proc(lines, i, None, path)
+                self.procs[pr.name] = pr
+                continue
+            if s.startswith("program"):
+                # keep the main program's body as a pseudo procedure (line-range execution uses it)
+                pr = Proc("program", "program", [], None, None, path)
+                i += 1
+                body = []
+                while not re.match(r"^end\s*program", lines[i][1]) and lines[i][1] != "end":
+                    body.append(lines[i])
+                    i += 1
+                pr.raw = body
+                self.procs["program:" + path] = pr
+                i += 1
+                continue
+            raise FortranError(f"{path}:{no}: unexpected top-level statement {s!r}")
+
+    def _load_module(self, lines, i, path):
+        name = lines[i][1].split()[1]
+        mod = self.modules.setdefault(name, Module(name))
+        i += 1
+        in_contains = False
+        while True:
+            no, s = lines[i]
+            if re.match(r"^end\s*module", s) or s == "end":
+                return i + 1
+            if s == "contains":
+                in_contains = True
+                i += 1
+                continue
+            if in_contains:
+                if _PROC_RE.match(s):
+                    pr, i = self._load_proc(lines, i, mod, path)
+                    mod.procs[pr.name] = pr
+                    continue
+                raise FortranError(f"{path}:{no}: {s!r} in contains part")
+            m = re.match(r"^interface\s*(.*)$", s)
+            if m:
+                gen = m.group(1).strip()
+                names = []
+                i += 1
+                while not re.match(r"^end\s*interface", lines[i][1]):
+                    mm = re.match(r"^module\s+procedure\s+(.*)$", lines[i][1])
+                    if mm:
+                        names += [x.strip() for x in mm.group(1).split(",")]
+                    i += 1
+                i += 1
+                mo = re.match(r"^operator\s*\(\s*(\.\w+\.)\s*\)$", gen)
+                if mo:
+                    mod.operators.setdefault(mo.group(1), []).extend(names)
+                elif gen and names:
+                    mod.generics.setdefault(gen, []).extend(names)
+                continue
+            if re.match(r"^type\b(?!\s*\()", s):         # derived-type definition: not supported, skipped
+                while not re.match(r"^end\s*type", lines[i][1]):
+                    i += 1
+                i += 1
+                continue
+            self._spec(mod, s, path, no)
+            i += 1
+
+    def _spec(self, unit, s, path, no):
+        """one specification statement of a module or procedure; returns False if s is executable."""
+        if re.match(r"^(implicit|save|private|public|protected|external|intrinsic|include|data|equivalence|common|namelist)\b", s):
+            if s.startswith("save") and isinstance(unit, Proc):
+                unit.save_all = True
+            return True
+        m = re.match(r"^use\s+(\w+)\s*(?:,\s*only\s*:\s*(.*))?$", s)
+        if m:
+            only = None
+            if m.group(2) is not None:
+                only = {}
+                for it in _split_top(m.group(2)):
+                    if not it:
+                        continue
+                    if "=>" in it:
+                        loc, rem = [x.strip() for x in it.split("=>")]
+                        only[loc] = rem
+                    else:
+                        only[it] = it
+            unit.uses.append((m.group(1), only))
+            return True
+        if _TYPE_RE.match(s) and ("::" in s or re.match(r"^(real|integer|logical|complex|character|double\s*precision)\b[^=]*$", s)):
+            kind, attrs, ents = _parse_decl(s, f"{path}:{no}")
+            for name, dims, init in ents:
+                unit.decls[name] = Decl(kind, dims, attrs, init)
+            return True
+        if re.match(r"^parameter\s*\(", s):
+            return True
+        return False
+
+    def _load_proc(self, lines, i, mod, path):
+        no, s = lines[i]
+        m = _PROC_RE.match(s)
+        kind, name, args, result = m.group(1), m.group(2), m.group(3), m.group(4)
+        args = [a.strip() for a in args.split(",")] if args and args.strip() else []
+        pr = Proc(kind, name, args, result or (name if kind == "function" else None), mod, path)
+        pr.save_all = False
+        pr.line = no
+        i += 1
+        # specification part
+        while True:
+            no, s = lines[i]
+            if re.match(r"^end\s*(subroutine|function)?\b", s) and not re.match(r"^end\s*(do|if|select|where|type|interface)", s) and not s.startswith("endif") and not s.startswith("enddo"):
+                break
+            if re.match(r"^interface\b", s):
+                while not re.match(r"^end\s*interface", lines[i][1]):
+                    i += 1
+                i += 1
+                continue
+            if not self._spec(pr, s, path, no):
+                break
+            i += 1
+        # executable part
+        body_lines = []
+        depth_contains = False
+        while True:
+            no, s = lines[i]
+            if re.match(r"^end\s*(subroutine|function)\b", s) or s == "end":
+                i += 1
+                break
+            if s == "contains":
+                depth_contains = True
+            body_lines.append((no, s))
+            i += 1
+        if depth_contains:
+            raise FortranError(f"{path}: internal procedures of {name} not supported")
+        pr.body = self._block(body_lines, path)
+        return pr, i
+
+    # ---- statement parsing ---------------------------------------------------------------------
+    def _block(self, lines, path):
+        stmts, i = [], 0
+        while i < len(lines):
+            st, i = self._stmt(lines, i, path)
+            if st is not None:
+                stmts.append(st)
+        return stmts
+
+    def _collect(self, lines, i, open_re, close_re):
+        """lines[i] opened a construct; return (inner lines, index after the closing line), nesting aware."""
+        depth, j = 1, i + 1
+        while j < len(lines):
+            s = lines[j][1]
+            if open_re(s):
+                depth += 1
+            elif close_re(s):
+                depth -= 1
+                if depth == 0:
+                    return lines[i + 1:j], j + 1
+            j += 1
+        raise FortranError(f"{path_of(lines, i)}: unterminated construct {lines[i][1]!r}")
+
+    def _stmt(self, lines, i, path):
+        no, s = lines[i]
+        loc = (path, no)
+        s = re.sub(r"^\w+\s*:\s*(?=do\b|if\b|select\b)", "", s)          # construct names
+        is_do = lambda t: re.match(r"^(?:\w+\s*:\s*)?do\b(?!\w)", t) is not None
+        is_enddo = lambda t: re.match(r"^end\s*do\b", t) is not None
+        is_ifthen = lambda t: re.match(r"^(?:\w+\s*:\s*)?if\s*\(", t) is not None and t.rstrip().endswith("then") and _if_is_block(t)
+        is_endif = lambda t: re.match(r"^end\s*if\b", t) is not None
+        if is_do(s):
+            inner, j = self._collect(lines, i, is_do, is_enddo)
+            hdr = s[2:].strip()
+            body = self._block(inner, path)
+            if not hdr:
+                return ("doinf", loc, body), j
+            mw = re.match(r"^while\s*\((.*)\)$", hdr)
+            if mw:
+                return ("dowhile", loc, parse_expr(mw.group(1)), body), j
+            k = _find_assign(hdr)
+            var = hdr[:k].strip()
+            parts = _split_top(hdr[k + 1:])
+            ex = [parse_expr(p) for p in parts]
+            return ("do", loc, var, ex[0], ex[1], ex[2] if len(ex) > 2 else None, body), j
+        if re.match(r"^if\s*\(", s):
+            e = _match_paren(s, s.index("("))
+            cond, rest = s[s.index("(") + 1:e], s[e + 1:].strip()
+            if rest == "then":
+                # block if: split into branches at depth 1
+                branches, cur_cond, cur, depth, j = [], parse_expr(cond), [], 1, i + 1
+                else_block = None
+                while True:
+                    t = lines[j][1]
+                    if is_ifthen(t):
+                        depth += 1
+                    elif is_endif(t):
+                        depth -= 1
+                        if depth == 0:
+                            break
+                    elif depth == 1 and re.match(r"^else\s*if\s*\(", t):
+                        branches.append((cur_cond, self._block(cur, path)))
+                        ee = _match_paren(t, t.index("("))
+                        cur_cond, cur = parse_expr(t[t.index("(") + 1:ee]), []
+                        j += 1
+                        continue
+                    elif depth == 1 and re.match(r"^else\b(?!\s*if)", t):
+                        branches.append((cur_cond, self._block(cur, path)))
+                        cur_cond, cur = None, []
+                        j += 1
+                        continue
+                    cur.append(lines[j])
+                    j += 1
+                if cur_cond is None:
+                    else_block = self._block(cur, path)
+                else:
+                    branches.append((cur_cond, self._block(cur, path)))
+                return ("if", loc, branches, else_block), j + 1
+            inner, _ = self._stmt([(no, rest)], 0, path)
+            return ("if", loc, [(parse_expr(cond), [inner] if inner else [])], None), i + 1
+        m = re.match(r"^select\s*case\s*\((.*)\)$", s)
+        if m:
+            is_sel = lambda t: re.match(r"^select\s*case", t) is not None
+            is_endsel = lambda t: re.match(r"^end\s*select", t) is not None
+            inner, j = self._collect(lines, i, is_sel, is_endsel)
+            cases, cur_sel, cur, depth = [], None, [], 0
+            for ln in inner:
+                t = ln[1]
+                if is_sel(t):
+                    depth += 1
+                elif is_endsel(t):
+                    depth -= 1
+                mc = re.match(r"^case\s*(default|\(.*\))$", t) if depth == 0 else None
+                if mc:
+                    if cur_sel is not None:
+                        cases.append((cur_sel, self._block(cur, path)))
+                    if mc.group(1) == "default":
+                        cur_sel = "default"
+                    else:
+                        sel = []
+                        for item in _split_top(mc.group(1)[1:-1]):
+                            if ":" in item:
+                                lo, hi = item.split(":")
+                                sel.append(("range", parse_expr(lo) if lo.strip() else None, parse_expr(hi) if hi.strip() else None))
+                            else:
+                                sel.append(("val", parse_expr(item)))
+                        cur_sel = sel
+                    cur = []
+                else:
+                    cur.append(ln)
+            if cur_sel is not None:
+                cases.append((cur_sel, self._block(cur, path)))
+            return ("select", loc, parse_expr(m.group(1)), cases), j
+        m = re.match(r"^call\s+(\w+)\s*(\(.*\))?$", s)
+        if m:
+            args = []
+            if m.group(2):
+                p = Parser(m.group(2))
+                p.expect("(")
+                args = p.arglist()
+            return ("call", loc, m.group(1), args), i + 1
+        m = re.match(r"^allocate\s*\((.*)\)$", s)
+        if m:
+            items = []
+            for it in _split_top(m.group(1)):
+                if re.match(r"^(stat|source|mold)\s*=", it):
+                    continue
+                p = it.index("(")
+                items.append((it[:p].strip(), [_parse_dim(d) for d in _split_top(it[p + 1:_match_paren(it, p)])]))
+            return ("allocate", loc, items), i + 1
+        m = re.match(r"^deallocate\s*\((.*)\)$", s)
+        if m:
+            return ("deallocate", loc, [x.strip() for x in _split_top(m.group(1))]), i + 1
+        if s in ("cycle", "exit", "return", "continue") or re.match(r"^(cycle|exit)\s+\w+$", s):
+            return (s.split()[0], loc), i + 1
+        if re.match(r"^stop\b", s):
+            return ("stop", loc, s), i + 1
+        if re.match(r"^(write|print|flush|format|\d+\s+format)\b", s):
+            return None, i + 1
+        if re.match(r"^(read|open|close|rewind|inquire|backspace)\b", s):
+            return ("unsupported", loc, s), i + 1
+        k = _find_assign(s)
+        if k > 0:
+            return ("assign", loc, parse_expr(s[:k]), parse_expr(s[k + 1:])), i + 1
+        raise FortranError(f"{path}:{no}: cannot parse statement {s!r}")
+
+    # ---- module initialisation -------------------------------------------------------------------
+    def module(self, name):
+        if name not in self.modules:
+            self.modules[name] = Module(name)
+        mod = self.modules[name]
+        if not mod.initialised:
+            mod.initialised = True
+            fr = Frame(self, mod, None)
+            for vname, d in mod.decls.items():
+                if vname in mod.vars:
+                    continue
+                mod.vars[vname] = self._initial(d, fr, vname)
+        return mod
+
+    def _initial(self, d, fr, vname):
+        if d.dims and not d.attrs.get("allocatable") and not d.attrs.get("pointer"):
+            try:
+                shape, lb = self._dims(d.dims, fr)
+            except FortranError:
+                return None                  # bounds not known yet (set by the host before use)
+            arr = FArray.alloc(shape, lb, d.kind if d.kind in ("real", "integer", "logical", "complex") else "real", self.alloc_fill)
+            if d.init is not None:
+                arr.a[...] = np.asarray(fr.eval(parse_expr(d.init)))
+            return arr
+        if d.dims:
+            return None                      # unallocated
+        if d.init is not None:
+            try:
+                v = fr.eval(parse_expr(d.init))
+            except FortranError:
+                return None
+            return _coerce(v, d.kind)
+        return None
+
+    def _dims(self, dims, fr):
+        shape, lb = [], []
+        for d in dims:
+            lo, hi = _parse_dim(d)
+            if hi is None or hi == "*":
+                raise FortranError("deferred / assumed dimension")
+            lo_v = 1 if lo is None else int(fr.eval(lo))
+            hi_v = int(fr.eval(hi))
+            lb.append(lo_v)
+            shape.append(max(hi_v - lo_v + 1, 0))
+        return shape, lb
+
+    # ---- public helpers --------------------------------------------------------------------------
+    def set(self, module, name, value):
+        self.module(module).vars[name.lower()] = value
+
+    def get(self, module, name):
+        return self.module(module).vars[name.lower()]
+
+    def find_proc(self, name, frame=None):
+        name = name.lower()
+        if frame is not None:
+            for modname, only in frame.all_uses():
+                mod = self.modules.get(modname)
+                if mod is None:
+                    continue
+                target = name
+                if only is not None:
+                    if name not in only:
+                        continue
+                    target = only[name]
+                if target in mod.procs:
+                    return mod.procs[target]
+                if target in mod.generics:
+                    return [mod.procs[n] for n in mod.generics[target]]
+            if frame.module is not None and name in frame.module.procs:
+                return frame.module.procs[name]
+        if name in self.procs:
+            return self.procs[name]
+        return None
+
+    def call(self, name, *args, module=None):
+        """Call a loaded subroutine / function from Python; args are FArrays or scalars."""
+        pr = self.modules[module].procs[name.lower()] if module else self.procs[name.lower()]
+        return self.invoke(pr, [("py", a) for a in args], None)
+
+    def exec_lines(self, path, lo, hi, module_uses, local=None):
+        """Execute the statements of `path` whose line numbers fall in [lo, hi] (e.g. the time-loop glue of main.f90)
+        in a frame that `use`s the given modules; `local` seeds local scalars."""
+        lines = [ln for ln in logical_lines(path, self.defines) if lo <= ln[0] <= hi]
+        body = self._block(lines, path)
+        pr = Proc("subroutine", f"lines_{lo}_{hi}", [], None, None, path)
+        pr.uses = [(m, None) for m in module_uses]
+        fr = Frame(self, None, pr)
+        if local:
+            fr.vars.update(local)
+        fr.run(body)
+        return fr.vars
+
+    # ---- procedure invocation --------------------------------------------------------------------
+    def invoke(self, pr, args, caller):
+        fr = Frame(self, pr.module, pr)
+        if len(args) > len(pr.args):
+            raise FortranError(f"{pr.name}: {len(args)} arguments for {len(pr.args)} dummies")
+        writeback = []
+        passed = {}
+        for pos, a in enumerate(args):
+            if a[0] == "kw":
+                passed[a[1]] = ("ast", a[2])
+            else:
+                passed[pr.args[pos]] = a if a[0] == "py" else ("ast", a)
+        # scalars first: array dummies' bounds may depend on them
+        actuals = {}
+        for dummy in pr.args:
+            if dummy not in passed:
+                fr.absent.add(dummy)
+                continue
+            tag, a = passed[dummy]
+            if tag == "py":
+                actuals[dummy] = (a, None)
+            else:
+                actuals[dummy] = caller.reference(a)
+        for dummy, (val, ref) in actuals.items():
+            d = pr.decls.get(dummy)
+            if d is None or not d.dims:
+                if isinstance(val, FArray) and d is not None and not d.dims:
+                    raise FortranError(f"{pr.name}: array passed to scalar dummy {dummy}")
+                fr.vars[dummy] = val
+                if ref is not None:
+                    writeback.append((dummy, ref))
+        for dummy, (val, ref) in actuals.items():
+            d = pr.decls.get(dummy)
+            if d is not None and d.dims:
+                fr.vars[dummy] = self._bind_array(pr, dummy, d, val, fr)
+        # locals
+        for name, d in pr.decls.items():
+            if name in fr.vars or name in pr.args:
+                continue
+            if d.attrs.get("save") or pr.save_all or d.init is not None and not d.attrs.get("parameter"):
+                if name not in pr.saved:
+                    pr.saved[name] = Cell(self._initial(d, fr, name))
+                fr.cells[name] = pr.saved[name]
+                continue
+            if d.attrs.get("parameter"):
+                fr.vars[name] = self._initial(d, fr, name)
+                continue
+            if d.dims and not d.attrs.get("allocatable"):
+                shape, lb = self._dims(d.dims, fr)
+                fr.vars[name] = FArray.alloc(shape, lb, d.kind if d.kind != "derived" else "real", self.alloc_fill)
+            else:
+                fr.vars[name] = None
+        try:
+            fr.run(pr.body)
+        except _Return:
+            pass
+        for dummy, ref in writeback:
+            if dummy in fr.vars and not isinstance(fr.vars[dummy], FArray):
+                ref(fr.vars[dummy])
+        if pr.kind == "function":
+            return fr.lookup(pr.result)
+        return None
+
+    def _bind_array(self, pr, dummy, d, val, fr):
+        if not isinstance(val, FArray):
+            raise FortranError(f"{pr.name}: scalar passed to array dummy {dummy}")
+        dims = [_parse_dim(x) for x in d.dims]
+        if all(hi is None for lo, hi in dims):             # assumed shape (:, :, lbz:)
+            if len(dims) != val.a.ndim:
+                raise FortranError(f"{pr.name}: rank mismatch for assumed-shape dummy {dummy}")
+            lb = [1 if lo is None else int(fr.eval(lo)) for lo, hi in dims]
+            return FArray(val.a, lb, val.kind)
+        # explicit shape: sequence association over the same storage
+        shape, lb = [], []
+        for n, (lo, hi) in enumerate(dims):
+            lo_v = 1 if lo is None else int(fr.eval(lo))
+            if hi == "*":
+                done = int(np.prod(shape)) if shape else 1
+                shape.append(val.a.size // done)
+            else:
+                shape.append(int(fr.eval(hi)) - lo_v + 1)
+            lb.append(lo_v)
+        if tuple(shape) == val.a.shape:
+            return FArray(val.a, lb, val.kind)
+        need = int(np.prod(shape))
+        flat = val.a.reshape(-1, order="F") if val.a.flags.f_contiguous else None
+        if flat is None or not np.shares_memory(flat, val.a):
+            raise FortranError(f"{pr.name}: actual argument for {dummy} is not contiguous")
+        if need > flat.size:
+            raise FortranError(f"{pr.name}: dummy {dummy} larger than the actual argument")
+        return FArray(flat[:need].reshape(shape, order="F"), lb, val.kind)
+
+
+def path_of(lines, i):
+    return f"line {lines[i][0]}"
+
+
+def _if_is_block(t):
+    e = _match_paren(t, t.index("("))
+    return t[e + 1:].strip() == "then"
+
+
+def _parse_dim(d):
+    d = d.strip()
+    if d == ":":
+        return (None, None)
+    if d == "*":
+        return (None, "*")
+    parts = _split_top(d, ":")
+    if len(parts) == 1:
+        return (None, parse_expr(parts[0]))
+    lo = parse_expr(parts[0]) if parts[0] else None
+    hi = None if parts[1] == "" else ("*" if parts[1] == "*" else parse_expr(parts[1]))
+    return (lo, hi)
+
+
+def _coerce(v, kind):
+    if v is None or isinstance(v, (FArray, np.ndarray)):
+        return v
+    if kind == "real":
+        return float(v)
+    if kind == "integer":
+        return int(v)
+    if kind == "logical":
+        return bool(v)
+    return v
+
+
+class Cell:
+    __slots__ = ("v",)
+
+    def __init__(self, v):
+        self.v = v
+
+
+class _Return(Exception):
+    pass
+
+
+class _Cycle(Exception):
+    pass
+
+
+class _Exit(Exception):
+    pass
+
+
+def _is_int(x):
+    return isinstance(x, (int, np.integer)) and not isinstance(x, (bool, np.bool_))
+
+
+def _int_array(x):
+    return isinstance(x, np.ndarray) and x.dtype.kind in "iu"
+
+
+class Frame:
+    def __init__(self, interp, module, proc):
+        self.I = interp
+        self.module = module
+        self.proc = proc
+        self.vars = {}
+        self.cells = {}
+        self.absent = set()
+
+    def all_uses(self):
+        if self.proc is not None:
+            for u in self.proc.uses:
+                yield u
+        if self.module is not None:
+            yield (self.module.name, None)
+            for u in self.module.uses:
+                yield u
+
+    # ---- name resolution -------------------------------------------------------------------------
+    def _find(self, name):
+        """-> (container dict or Cell, key) or None"""
+        if name in self.vars:
+            return self.vars, name
+        if name in self.cells:
+            return self.cells[name], None
+        for modname, only in self.all_uses():
+            target = name
+            if only is not None:
+                if name not in only:
+                    continue
+                target = only[name]
+            mod = self.I.module(modname)
+            if target in mod.vars:
+                return mod.vars, target
+            if target in mod.decls:
+                mod.vars.setdefault(target, None)
+                return mod.vars, target
+            # public entities a module re-exports from the modules it uses
+            for m2, only2 in mod.uses:
+                t2 = target
+                if only2 is not None:
+                    if target not in only2:
+                        continue
+                    t2 = only2[target]
+                mod2 = self.I.module(m2)
+                if t2 in mod2.vars or t2 in mod2.decls:
+                    mod2.vars.setdefault(t2, None)
+                    return mod2.vars, t2
+        return None
+
+    def lookup(self, name):
+        f = self._find(name)
+        if f is None:
+            raise FortranError(f"undefined name {name!r} in {self.proc.name if self.proc else self.module.name}")
+        c, k = f
+        v = c.v if k is None else c[k]
+        return v
+
+    def store(self, name, value):
+        f = self._find(name)
+        if f is None:
+            if self.proc is not None and (name in self.proc.decls or self.proc.name.startswith("lines_")):
+                self.vars[name] = value
+                return
+            raise FortranError(f"assignment to undeclared name {name!r}")
+        c, k = f
+        if k is None:
+            c.v = value
+        else:
+            c[k] = value
+
+    def kind_of(self, name):
+        if self.proc is not None and name in self.proc.decls:
+            return self.proc.decls[name].kind
+        for modname, only in self.all_uses():
+            target = name if only is None else only.get(name)
+            if target is None:
+                continue
+            mod = self.I.module(modname)
+            if target in mod.decls:
+                return mod.decls[target].kind
+        return None
+
+    # ---- references (call by reference) ----------------------------------------------------------
+    def reference(self, ast):
+        """actual argument -> (value, writeback-or-None).  Arrays and sections are views."""
+        if ast[0] == "name":
+            v = self.lookup(ast[1]) if self._find(ast[1]) is not None else None
+            if v is None and self._find(ast[1]) is None:
+                # a procedure name or an unknown external entity
+                return ("procname", ast[1]), None
+            if isinstance(v, FArray):
+                return v, None
+            return v, (lambda val, n=ast[1]: self.store(n, val))
+        if ast[0] == "call" and ast[1][0] == "name" and self._find(ast[1][1]) is not None:
+            base = self.lookup(ast[1][1])
+            if isinstance(base, FArray):
+                subs = [self.subscript(a) for a in ast[2]]
+                idx, scalar = base.index(subs)
+                if scalar:
+                    # element: pass the storage sequence starting there (sequence association)
+                    return ElemRef(base, idx), None
+                view = base.a[idx]
+                return FArray(view, None, base.kind), None
+        return self.eval(ast), None
+
+    def subscript(self, a):
+        if a[0] == "range":
+            return (None if a[1] is None else int(self.eval(a[1])), None if a[2] is None else int(self.eval(a[2])),
+                    None if a[3] is None else int(self.eval(a[3])))
+        v = self.eval(a)
+        if isinstance(v, np.ndarray):
+            return v
+        return int(v)
+
+    # ---- expression evaluation -------------------------------------------------------------------
+    def eval(self, e):
+        t = e[0]
+        if t == "num":
+            return e[1]
+        if t == "paren":
+            return self.eval(e[1])
+        if t == "str":
+            return e[1]
+        if t == "name":
+            v = self.lookup(e[1])
+            if isinstance(v, FArray):
+                return v.a
+            if v is None:
+                raise FortranError(f"{e[1]} used before it has a value")
+            return v
+        if t == "un":
+            v = self.eval(e[2])
+            if e[1] == "-":
+                return -v
+            return np.logical_not(v) if isinstance(v, np.ndarray) else (not v)
+        if t == "bin":
+            return self.binop(e[1], self.eval(e[2]), self.eval(e[3]))
+        if t == "array":
+            vals = [self.eval(x) for x in e[1]]
+            flat = []
+            for v in vals:
+                if isinstance(v, np.ndarray):
+                    flat.extend(v.reshape(-1, order="F").tolist())
+                else:
+                    flat.append(v)
+            return np.array(flat, dtype=np.int64 if all(_is_int(v) for v in flat) else np.float64)
+        if t == "call":
+            return self.call_or_index(e)
+        if t == "defop":
+            return self.defined_op(e[1], e[2], e[3])
+        raise FortranError(f"cannot evaluate {e!r}")
+
+    def binop(self, op, a, b):
+        if op == "+":
+            return a + b
+        if op == "-":
+            return a - b
+        if op == "*":
+            return a * b
+        if op == "/":
+            ia = _is_int(a) or _int_array(a)
+            ib = _is_int(b) or _int_array(b)
+            if ia and ib:
+                if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+                    return np.trunc(np.asarray(a) / np.asarray(b)).astype(np.int64)
+                q = abs(a) // abs(b)
+                return int(q if (a >= 0) == (b >= 0) else -q)
+            return a / b
+        if op == "**":
+            if _is_int(a) and _is_int(b) and b >= 0:
+                return int(a) ** int(b)
+            if _is_int(b):
+                # x**n with integer n: repeated multiplication as gfortran's powi for small n
+                if b == 2:
+                    return a * a
+                if b == 3:
+                    return a * a * a
+                return a ** int(b) if not isinstance(a, np.ndarray) else np.power(a, int(b))
+            return a ** b if not isinstance(a, np.ndarray) else np.power(a, b)
+        if op in ("==", "!=", "<", "<=", ">", ">="):
+            if op == "==":
+                return a == b
+            if op == "!=":
+                return a != b
+            if op == "<":
+                return a < b
+            if op == "<=":
+                return a <= b
+            if op == ">":
+                return a > b
+            return a >= b
+        if op == ".and.":
+            return np.logical_and(a, b) if isinstance(a, np.ndarray) or isinstance(b, np.ndarray) else (bool(a) and bool(b))
+        if op == ".or.":
+            return np.logical_or(a, b) if isinstance(a, np.ndarray) or isinstance(b, np.ndarray) else (bool(a) or bool(b))
+        if op == ".eqv.":
+            return bool(a) == bool(b)
+        if op == ".neqv.":
+            return bool(a) != bool(b)
+        raise FortranError(f"operator {op}")
+
+    def call_or_index(self, e):
+        head, args = e[1], e[2]
+        if head[0] != "name":
+            raise FortranError(f"unsupported reference {e!r}")
+        name = head[1]
+        f = self._find(name)
+        if f is not None:
+            base = self.lookup(name)
+            if isinstance(base, FArray):
+                subs = [self.subscript(a) for a in args]
+                idx, scalar = base.index(subs)
+                v = base.a[idx]
+                if scalar:
+                    return v.item() if hasattr(v, "item") else v
+                return v
+            if base is None:
+                raise FortranError(f"{name} referenced before allocation")
+        pr = self.I.find_proc(name, self)
+        if pr is not None:
+            if isinstance(pr, list):
+                pr = self.resolve_generic(pr, args)
+            return self.I.invoke(pr, args, self)
+        if name in self.I.externals:
+            return self.I.externals[name](self, [self.reference(a)[0] if a[0] != "kw" else ("kw", a[1], self.eval(a[2])) for a in args])
+        return self.intrinsic(name, args)
+
+    def resolve_generic(self, cands, args):
+        vals = [self.reference(a)[0] for a in args if a[0] != "kw"]
+        for pr in cands:
+            ok = len(vals) <= len(pr.args)
+            for v, dn in zip(vals, pr.args):
+                d = pr.decls.get(dn)
+                rank = len(d.dims) if d is not None and d.dims else 0
+                vrank = v.a.ndim if isinstance(v, FArray) else (v.ndim if isinstance(v, np.ndarray) else 0)
+                if rank != vrank:
+                    ok = False
+                if ok and d is not None and d.kind == "complex" and not (isinstance(v, FArray) and v.kind == "complex"):
+                    ok = False
+            if ok:
+                return pr
+        raise FortranError("no specific procedure matches the generic reference")
+
+    def defined_op(self, op, a, b):
+        for modname, only in self.all_uses():
+            mod = self.I.modules.get(modname)
+            if mod is None or op not in mod.operators:
+                continue
+            av, bv = self.eval(a), self.eval(b)
+            wrap = lambda v: FArray(np.asfortranarray(v), None, "complex" if v.dtype.kind == "c" else "real") if isinstance(v, np.ndarray) else v
+            avw, bvw = wrap(av), wrap(bv)
+            for pn in mod.operators[op]:
+                pr = mod.procs[pn]
+                ok = True
+                for v, dn in zip((avw, bvw), pr.args):
+                    d = pr.decls[dn]
+                    rank = len(d.dims) if d.dims else 0
+                    vrank = v.a.ndim if isinstance(v, FArray) else 0
+                    if rank != vrank or (d.kind == "complex") != (isinstance(v, FArray) and v.kind == "complex"):
+                        ok = False
+                if ok:
+                    r = self.I.invoke(pr, [("py", avw), ("py", bvw)], self)
+                    return r.a if isinstance(r, FArray) else r
+        raise FortranError(f"no procedure for operator {op}")
+
+    def intrinsic(self, name, args):
+        kw = {a[1]: a[2] for a in args if a[0] == "kw"}
+        pos = [a for a in args if a[0] != "kw"]
+        ev = lambda i: self.eval(pos[i])
+        if name in ("real", "dble", "float"):
+            v = ev(0)
+            return v.astype(np.float64) if isinstance(v, np.ndarray) else float(v)
+        if name == "int":
+            v = ev(0)
+            return np.trunc(v).astype(np.int64) if isinstance(v, np.ndarray) else int(v)
+        if name == "nint":
+            v = ev(0)
+            return int(math.floor(abs(v) + 0.5) * (1 if v >= 0 else -1))
+        if name == "floor":
+            v = ev(0)
+            return np.floor(v).astype(np.int64) if isinstance(v, np.ndarray) else int(math.floor(v))
+        if name == "ceiling":
+            v = ev(0)
+            return np.ceil(v).astype(np.int64) if isinstance(v, np.ndarray) else int(math.ceil(v))
+        if name == "abs":
+            v = ev(0)
+            return np.abs(v) if isinstance(v, np.ndarray) else abs(v)
+        if name in ("sqrt", "exp", "log", "sin", "cos", "tan", "tanh", "atan", "acos", "asin", "log10", "erf"):
+            v = ev(0)
+            fn = getattr(np, {"atan": "arctan", "acos": "arccos", "asin": "arcsin"}.get(name, name), None)
+            if name == "erf":
+                return math.erf(v)
+            return fn(v) if isinstance(v, np.ndarray) else float(fn(v))
+        if name in ("max", "min"):
+            vals = [self.eval(a) for a in pos]
+            r = vals[0]
+            for v in vals[1:]:
+                if isinstance(r, np.ndarray) or isinstance(v, np.ndarray):
+                    r = np.maximum(r, v) if name == "max" else np.minimum(r, v)
+                else:
+                    r = max(r, v) if name == "max" else min(r, v)
+            return r
+        if name in ("maxval", "minval", "sum", "product"):
+            v = np.asarray(ev(0))
+            fn = {"maxval": np.max, "minval": np.min, "sum": None, "product": np.prod}[name]
+            dim = kw.get("dim") or (pos[1] if len(pos) > 1 else None)
+            if name == "sum":
+                # Fortran sums in array element order; NumPy's pairwise summation differs in the last bits, so
+                # accumulate sequentially in storage order
+                if dim is not None:
+                    ax = int(self.eval(dim)) - 1
+                    return np.add.reduce(v, axis=ax)
+                flat = v.reshape(-1, order="F")
+                if flat.dtype.kind in "iu":
+                    return int(flat.sum())
+                return float(np.add.accumulate(flat)[-1]) if flat.size else 0.0
+            if dim is not None:
+                return fn(v, axis=int(self.eval(dim)) - 1)
+            r = fn(v)
+            return int(r) if v.dtype.kind in "iu" else float(r)
+        if name == "mod":
+            a, b = ev(0), ev(1)
+            if _is_int(a) and _is_int(b):
+                return int(math.fmod(a, b))
+            return math.fmod(a, b)
+        if name == "modulo":
+            a, b = ev(0), ev(1)
+            return a - math.floor(a / b) * b if not (_is_int(a) and _is_int(b)) else a % b
+        if name == "size":
+            ref = self.reference(pos[0])[0]
+            arr = ref.a if isinstance(ref, FArray) else np.asarray(ref)
+            if len(pos) > 1 or "dim" in kw:
+                return int(arr.shape[int(self.eval(pos[1] if len(pos) > 1 else kw["dim"])) - 1])
+            return int(arr.size)
+        if name in ("lbound", "ubound"):
+            ref = self.reference(pos[0])[0]
+            d = int(self.eval(pos[1] if len(pos) > 1 else kw["dim"])) - 1
+            return ref.lb[d] if name == "lbound" else ref.lb[d] + ref.a.shape[d] - 1
+        if name == "huge":
+            v = ev(0)
+            return sys.float_info.max if isinstance(v, float) else 2147483647
+        if name == "epsilon":
+            return sys.float_info.epsilon
+        if name == "tiny":
+            return sys.float_info.min
+        if name == "merge":
+            a, b, m = ev(0), ev(1), ev(2)
+            return np.where(m, a, b) if isinstance(m, np.ndarray) else (a if m else b)
+        if name == "sign":
+            a, b = ev(0), ev(1)
+            return abs(a) if b >= 0 else -abs(a)
+        if name == "present":
+            return pos[0][1] not in self.absent
+        if name == "allocated":
+            return self.lookup(pos[0][1]) is not None
+        if name in ("any", "all", "count"):
+            v = np.asarray(ev(0))
+            return bool(v.any()) if name == "any" else (bool(v.all()) if name == "all" else int(v.sum()))
+        if name == "cmplx":
+            return complex(ev(0), ev(1) if len(pos) > 1 else 0.0)
+        if name in ("aimag", "imag"):
+            v = ev(0)
+            return v.imag
+        if name == "conjg":
+            return np.conj(ev(0))
+        if name in ("trim", "adjustl"):
+            return str(ev(0)).strip()
+        if name == "spacing":
+            return float(np.spacing(ev(0)))
+        raise FortranError(f"unknown function or unallocated array {name!r} (in {self.proc.name if self.proc else '?'})")
+
+    # ---- execution -------------------------------------------------------------------------------
+    def run(self, body):
+        for st in body:
+            self.exec(st)
+
+    def exec(self, st):
+        self.I.nstmt += 1
+        t = st[0]
+        try:
+            if t == "assign":
+                self.assign(st[2], st[3])
+            elif t == "if":
+                for cond, block in st[2]:
+                    if self.eval(cond):
+                        self.run(block)
+                        return
+                if st[3] is not None:
+                    self.run(st[3])
+            elif t == "do":
+                _, _, var, e0, e1, e2, body = st
+                lo, hi = self.eval(e0), self.eval(e1)
+                step = 1 if e2 is None else self.eval(e2)
+                n = max((hi - lo + step) // step, 0)
+                v = lo
+                for _ in range(n):
+                    self.store(var, v)
+                    try:
+                        self.run(body)
+                    except _Cycle:
+                        pass
+                    except _Exit:
+                        v = self.lookup(var)
+                        break
+                    v = self.lookup(var) + step
+                self.store(var, v)
+            elif t == "dowhile":
+                while self.eval(st[2]):
+                    try:
+                        self.run(st[3])
+                    except _Cycle:
+                        continue
+                    except _Exit:
+                        break
+            elif t == "doinf":
+                while True:
+                    try:
+                        self.run(st[2])
+                    except _Cycle:
+                        continue
+                    except _Exit:
+                        break
+            elif t == "select":
+                v = self.eval(st[2])
+                default = None
+                for sel, block in st[3]:
+                    if sel == "default":
+                        default = block
+                        continue
+                    for item in sel:
+                        if item[0] == "val":
+                            hit = v == self.eval(item[1])
+                        else:
+                            hit = (item[1] is None or v >= self.eval(item[1])) and (item[2] is None or v <= self.eval(item[2]))
+                        if hit:
+                            self.run(block)
+                            return
+                if default is not None:
+                    self.run(default)
+            elif t == "call":
+                self.call(st[2], st[3])
+            elif t == "allocate":
+                for name, dims in st[2]:
+                    shape, lb = [], []
+                    for lo, hi in dims:
+                        lo_v = 1 if lo is None else int(self.eval(lo))
+                        hi_v = int(self.eval(hi))
+                        lb.append(lo_v)
+                        shape.append(max(hi_v - lo_v + 1, 0))
+                    k = self.kind_of(name) or "real"
+                    self.store(name, FArray.alloc(shape, lb, k if k in ("real", "integer", "logical", "complex") else "real", self.I.alloc_fill))
+            elif t == "deallocate":
+                for name in st[2]:
+                    self.store(name, None)
+            elif t == "cycle":
+                raise _Cycle()
+            elif t == "exit":
+                raise _Exit()
+            elif t == "return":
+                raise _Return()
+            elif t == "continue":
+                pass
+            elif t == "stop":
+                raise FStop(f"{st[1][0]}:{st[1][1]}: {st[2]}")
+            elif t == "unsupported":
+                raise FortranError(f"unsupported statement {st[2]!r}")
+            else:
+                raise FortranError(f"statement kind {t}")
+        except (_Cycle, _Exit, _Return, FStop):
+            raise
+        except FortranError as ex:
+            if not getattr(ex, "located", False):
+                ex.args = (f"{st[1][0]}:{st[1][1]}: {ex.args[0]}",)
+                ex.located = True
+            raise
+
+    def assign(self, lhs, rhs):
+        val = self.eval(rhs)
+        if lhs[0] == "name":
+            cur = self.lookup(lhs[1]) if self._find(lhs[1]) is not None else None
+            if isinstance(cur, FArray):
+                cur.a[...] = val
+                return
+            if isinstance(val, np.ndarray) and val.ndim > 0:
+                # allocatable result / automatic (re)allocation on assignment
+                k = self.kind_of(lhs[1]) or "real"
+                self.store(lhs[1], FArray(np.array(val, order="F"), None, k))
+                return
+            self.store(lhs[1], _coerce(val, self.kind_of(lhs[1])))
+            return
+        if lhs[0] == "call" and lhs[1][0] == "name":
+            base = self.lookup(lhs[1][1])
+            if not isinstance(base, FArray):
+                raise FortranError(f"{lhs[1][1]} is not an (allocated) array")
+            subs = [self.subscript(a) for a in lhs[2]]
+            idx, _ = base.index(subs)
+            base.a[idx] = val
+            return
+        raise FortranError(f"unsupported assignment target {lhs!r}")
+
+    def call(self, name, args):
+        pr = self.I.find_proc(name, self)
+        if pr is not None:
+            if isinstance(pr, list):
+                pr = self.resolve_generic(pr, args)
+            self.I.invoke(pr, args, self)
+            return
+        if name in self.I.externals:
+            refs = []
+            for a in args:
+                if a[0] == "kw":
+                    refs.append(("kw", a[1], self.eval(a[2])))
+                else:
+                    refs.append(self.reference(a))
+            self.I.externals[name](self, refs)
+            return
+        raise FortranError(f"call to unknown procedure {name!r}")
+
+
+class ElemRef:
+    """An array element passed as an actual argument: the storage sequence that starts there."""
+
+    def __init__(self, base, idx):
+        self.base, self.idx = base, idx
+
+    def value(self):
+        return self.base.a[self.idx]

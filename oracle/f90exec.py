@@ -281,10 +281,16 @@ class Parser:
         return self.p_rel()
 
     def p_rel(self):
-        a = self.p_add()
+        a = self.p_cat()
         if self.peek()[1] in _REL:
             op = _REL[self.next()[1]]
-            return ("bin", op, a, self.p_add())
+            return ("bin", op, a, self.p_cat())
+        return a
+
+    def p_cat(self):
+        a = self.p_add()
+        while self.accept("//"):
+            a = ("bin", "//", a, self.p_add())
         return a
 
     def p_add(self):
@@ -475,6 +481,7 @@ class Proc:
         self.uses = []            # (module, only-dict or None)
         self.body = []
         self.saved = {}           # SAVE variables (persist between calls)
+        self.internal = {}        # internal procedures (after CONTAINS), which see the host's variables
 
 
 class Decl:
@@ -680,18 +687,19 @@ class Interpreter:
             i += 1
         # executable part
         body_lines = []
-        depth_contains = False
         while True:
             no, s = lines[i]
             if re.match(r"^end\s*(subroutine|function)\b", s) or s == "end":
                 i += 1
                 break
             if s == "contains":
-                depth_contains = True
+                i += 1
+                while not (re.match(r"^end\s*(subroutine|function)\b", lines[i][1]) or lines[i][1] == "end"):
+                    ip, i = self._load_proc(lines, i, mod, path)
+                    pr.internal[ip.name] = ip
+                continue
             body_lines.append((no, s))
             i += 1
-        if depth_contains:
-            raise FortranError(f"{path}: internal procedures of {name} not supported")
         pr.body = self._block(body_lines, path)
         return pr, i
 
@@ -775,6 +783,25 @@ class Interpreter:
                 return ("if", loc, branches, else_block), j + 1
             inner, _ = self._stmt([(no, rest)], 0, path)
             return ("if", loc, [(parse_expr(cond), [inner] if inner else [])], None), i + 1
+        if re.match(r"^where\s*\(", s):
+            e = _match_paren(s, s.index("("))
+            rest = s[e + 1:].strip()
+            if not rest:
+                raise FortranError(f"{path}:{no}: block WHERE not supported")
+            k = _find_assign(rest)
+            return ("where", loc, parse_expr(s[s.index("(") + 1:e]), parse_expr(rest[:k]), parse_expr(rest[k + 1:])), i + 1
+        if re.match(r"^forall\s*\(", s):
+            e = _match_paren(s, s.index("("))
+            rest = s[e + 1:].strip()
+            specs = []
+            for it in _split_top(s[s.index("(") + 1:e]):
+                k = _find_assign(it)
+                lo, hi = _split_top(it[k + 1:], ":")[:2]
+                specs.append((it[:k].strip(), parse_expr(lo), parse_expr(hi)))
+            k = _find_assign(rest)
+            return ("forall", loc, specs, parse_expr(rest[:k]), parse_expr(rest[k + 1:])), i + 1
+        if re.match(r"^nullify\s*\(", s):
+            return None, i + 1
         m = re.match(r"^select\s*case\s*\((.*)\)$", s)
         if m:
             is_sel = lambda t: re.match(r"^select\s*case", t) is not None
@@ -808,6 +835,8 @@ class Interpreter:
             if cur_sel is not None:
                 cases.append((cur_sel, self._block(cur, path)))
             return ("select", loc, parse_expr(m.group(1)), cases), j
+        if re.match(r"^call\s+\w+\s*%", s):
+            return None, i + 1
         m = re.match(r"^call\s+(\w+)\s*(\(.*\))?$", s)
         if m:
             args = []
@@ -896,6 +925,11 @@ class Interpreter:
 
     def find_proc(self, name, frame=None):
         name = name.lower()
+        fr = frame
+        while fr is not None:
+            if fr.proc is not None and name in fr.proc.internal:
+                return fr.proc.internal[name]
+            fr = fr.host
         if frame is not None:
             for modname, only in frame.all_uses():
                 mod = self.modules.get(modname)
@@ -937,6 +971,13 @@ class Interpreter:
     # ---- procedure invocation --------------------------------------------------------------------
     def invoke(self, pr, args, caller):
         fr = Frame(self, pr.module, pr)
+        if caller is not None:
+            h = caller
+            while h is not None:                       # internal procedure: host association
+                if h.proc is not None and pr.name in h.proc.internal and h.proc.internal[pr.name] is pr:
+                    fr.host = h
+                    break
+                h = h.host
         if len(args) > len(pr.args):
             raise FortranError(f"{pr.name}: {len(args)} arguments for {len(pr.args)} dummies")
         writeback = []
@@ -1097,6 +1138,7 @@ class Frame:
         self.vars = {}
         self.cells = {}
         self.absent = set()
+        self.host = None
 
     def all_uses(self):
         if self.proc is not None:
@@ -1114,6 +1156,10 @@ class Frame:
             return self.vars, name
         if name in self.cells:
             return self.cells[name], None
+        if self.host is not None:
+            f = self.host._find(name)
+            if f is not None:
+                return f
         for modname, only in self.all_uses():
             target = name
             if only is not None:
@@ -1243,6 +1289,8 @@ class Frame:
         raise FortranError(f"cannot evaluate {e!r}")
 
     def binop(self, op, a, b):
+        if op == "//":
+            return str(a) + str(b)
         if op == "+":
             return a + b
         if op == "-":
@@ -1531,6 +1579,24 @@ class Frame:
                     self.run(default)
             elif t == "call":
                 self.call(st[2], st[3])
+            elif t == "where":
+                mask = np.asarray(self.eval(st[2]))
+                val = self.eval(st[4])
+                tgt = self.reference(st[3])[0]
+                if isinstance(val, np.ndarray):
+                    tgt.a[mask] = val[mask]
+                else:
+                    tgt.a[mask] = val
+            elif t == "forall":
+                def rec(k):
+                    if k == len(st[2]):
+                        self.assign(st[3], st[4])
+                        return
+                    var, lo, hi = st[2][k]
+                    for v in range(int(self.eval(lo)), int(self.eval(hi)) + 1):
+                        self.vars[var] = v
+                        rec(k + 1)
+                rec(0)
             elif t == "allocate":
                 for name, dims in st[2]:
                     shape, lb = [], []

@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ref_*.npz: outputs of the REFERENCE'S OWN SOURCES (under /root/reference), executed by
+oracle/f90exec.py through oracle/refrun.py.  Run in the development container (the GPU boxes have no
+/root/reference):
+
+    python oracle/make_reference_fixtures.py
+
+Each fixture stores the Params it was made with, the initial u, v, w, and the reference's fields after the
+recorded steps; tests/test_reference_pin.py compares the oracle (CPU suite) and the CUDA path (-m gpu) with them.
+The FFTs inside the reference run are pocketfft (FFTW3 is not available anywhere), everything else is
+the reference's text: index ranges, wall-plane cases, BOGUS planes, operation order, the time-loop glue of
+main.f90, project, cfl_util.
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import lesgo_oracle as O          # noqa: E402
+from oracle import refrun                      # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+STEP_FIELDS = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")
+
+STEP_CASES = {
+    # BASELINE configs[1] in miniature: DNS Couette walls, core path only (rows a-e)
+    "ref_core_couette_32x32x8": dict(kw=dict(nx=32, ny=32, Nz=8, lbc_mom=1, ubc_mom=1, utop=1.0, ubot=-1.0, L_x=4 * np.pi),
+                                     mode="core", record=(1, 10)),
+    # the same with the molecular stress: wallstress (DNS), calc_Sij, sgs_stag (sgs = .false.), divstress_uv/w
+    "ref_full_couette_16x16x8": dict(kw=dict(nx=16, ny=16, Nz=8, lbc_mom=1, ubc_mom=1, utop=1.0, ubot=-1.0, sgs=False, molec=True,
+                                             nu_molec=1e-2), mode="full", record=(1, 10)),
+    # LES half channel as LES_channel_Re1000: equilibrium wall model below, stress-free lid, Smagorinsky + Mason damping
+    "ref_full_les_channel_16x32x8": dict(kw=dict(nx=16, ny=32, Nz=8, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False,
+                                                 use_mean_p_force=True, mean_p_force_x=1.0, L_y=np.pi), mode="full", record=(1, 10)),
+    # stress-free on both sides, LES branch of convec (jzLo = 2), core path
+    "ref_core_free_slip_les_16x16x6": dict(kw=dict(nx=16, ny=16, Nz=6, lbc_mom=0, ubc_mom=0, sgs=True, L_x=4.0, L_y=3.0),
+                                           mode="core", record=(1, 4)),
+    # use_cfl_dt as the shipped LES_channel_Re1000 (lesgo.conf:117): sgs_model 5 before DYN_init, variable dt
+    "ref_full_cfl_dt_sgs5_16x16x8": dict(kw=dict(nx=16, ny=16, Nz=8, lbc_mom=2, ubc_mom=2, sgs=True, sgs_model=5, molec=False),
+                                         mode="full", record=(1, 10), cfl=0.0625),
+}
+
+
+def initial_fields(p, seed=41, amp=0.3):
+    u, v, w = O.synthetic_global(p.nx, p.ny, p.Nz, nproc=1, seed=seed, amp=amp, L_x=p.L_x, L_y=p.L_y, L_z=p.L_z)
+    return tuple(O.scatter_slab(f, p) for f in (u, v, w))
+
+
+def params_record(p):
+    return {k: getattr(p, k) for k, f in p.__dataclass_fields__.items() if f.init}
+
+
+def run_step_case(name, kw, mode, record, cfl=None):
+    p = O.Params(**kw)
+    R = refrun.Reference(p)
+    u, v, w = initial_fields(p)
+    out = {"u0": u, "v0": v, "w0": w}
+    for n, a in (("u", u), ("v", v), ("w", w)):
+        R.put(n, a)
+    dts = []
+    if cfl is not None:
+        # initialize.f90:192-200, from the reference text: dt = get_cfl_dt() * huge (forces an Euler first step)
+        R.I.set("param", "cfl", float(cfl)); R.I.set("param", "use_cfl_dt", True); R.I.set("param", "cfl_f", 0.0)
+        R.I.exec_lines(os.path.join(refrun.REF, "initialize.f90"), 192, 200, ["types", "param", "sim_param", "cfl_util"],
+                       local={"dt_dim": 0.0})
+    t0 = time.time()
+    for it in range(1, max(record) + 1):
+        if cfl is not None:
+            R.cfl_dt_step_setup()                                  # main.f90:135-144
+            dts.append((R.I.get("param", "dt"), R.I.get("param", "tadv1"), R.I.get("param", "tadv2")))
+        R.step(it, mode=mode)
+        if it in record:
+            for n in STEP_FIELDS:
+                out[f"{n}_{it}"] = R.get(n)
+    if dts:
+        out["dts"] = np.array(dts)
+    meta = dict(params=params_record(p), mode=mode, record=list(record), cfl=cfl,
+                made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py",
+                statements=R.I.nstmt)
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: {max(record)} steps, {R.I.nstmt} reference statements, {time.time() - t0:.1f} s")
+
+
+def run_routines(name="ref_routines_16x16x6"):
+    """Routine by routine on seeded random fields: ddx, ddy, ddxy, filt_da, ddz_uv, ddz_w, padd / unpadd, convec for the
+    four wall-condition combinations the tests use, press_stag_array, test_filter, get_max_cfl / get_cfl_dt."""
+    from helpers import random_field
+    out = {}
+    kw = dict(nx=16, ny=16, Nz=6, L_x=4.0, L_y=3.0)
+    p = O.Params(**kw)
+    R = refrun.Reference(p)
+    I = R.I
+    f = random_field(p, 1)
+    out["f"] = f
+    D = "derivatives"
+    uses = ["types", "param", "sim_param", "derivatives", "fft", "test_filtermodule", "cfl_util"]
+    main_like = lambda text: None
+    # the calls are made exactly as main.f90 / divstress make them: module arrays of sim_param as actual arguments
+    R.put("u", f)
+    I.call("ddx", I.get("sim_param", "u"), I.get("sim_param", "dudx"), 0, module=D); out["ddx"] = R.get("dudx")
+    I.call("ddy", I.get("sim_param", "u"), I.get("sim_param", "dudy"), 0, module=D); out["ddy"] = R.get("dudy")
+    I.call("ddxy", I.get("sim_param", "u"), I.get("sim_param", "dvdx"), I.get("sim_param", "dvdy"), 0, module=D)
+    out["ddxy_x"], out["ddxy_y"] = R.get("dvdx"), R.get("dvdy")
+    I.call("ddz_uv", I.get("sim_param", "u"), I.get("sim_param", "dudz"), 0, module=D); out["ddz_uv"] = R.get("dudz")
+    I.call("ddz_w", I.get("sim_param", "u"), I.get("sim_param", "dwdz"), 0, module=D); out["ddz_w"] = R.get("dwdz")
+    I.call("filt_da", I.get("sim_param", "u"), I.get("sim_param", "dudx"), I.get("sim_param", "dudy"), 0, module=D)
+    out["filt_da_f"], out["filt_da_x"], out["filt_da_y"] = R.get("u"), R.get("dudx"), R.get("dudy")
+    # test_filter(f) on one plane, in place (test_filtermodule.f90:126-146)
+    pl = refrun.F.FArray(np.asfortranarray(f[2].T.copy()), (1, 1))
+    I.call("test_filter", pl, module="test_filtermodule")
+    out["test_filter_plane2"] = pl.a.T.copy()
+    # cfl_util on a seeded state
+    u, v, w = initial_fields(p, seed=91)
+    for n, a in (("u", u), ("v", v), ("w", w)):
+        R.put(n, a)
+    out["cfl_u"], out["cfl_v"], out["cfl_w"] = u, v, w
+    I.set("param", "cfl", 0.0625)
+    out["max_cfl"] = np.array(I.call("get_max_cfl", module="cfl_util"))
+    out["cfl_dt"] = np.array(I.call("get_cfl_dt", module="cfl_util"))
+    # convec and press_stag_array for several wall conditions
+    for tag, bc in (("11d", (1, 1, False)), ("00d", (0, 0, False)), ("22l", (2, 2, True)), ("10l", (1, 0, True))):
+        pc = O.Params(lbc_mom=bc[0], ubc_mom=bc[1], sgs=bc[2], **kw)
+        Rc = refrun.Reference(pc, files=[x for x in refrun.FILES if x not in ("sgs_stag_util.f90", "wallstress.f90", "divstress_uv.f90", "divstress_w.f90")])
+        names = ("u", "v", "w", "dudy", "dudz", "dvdx", "dvdz", "dwdx", "dwdy")
+        for i, n in enumerate(names):
+            Rc.put(n, random_field(pc, 20 + i))
+        Rc.call("convec")
+        for n in ("RHSx", "RHSy", "RHSz"):
+            out[f"convec_{tag}_{n}"] = Rc.get(n)
+    pp = O.Params(**kw)
+    Rp = refrun.Reference(pp)
+    u, v, w = initial_fields(pp, seed=31)
+    for n, a in (("u", u), ("v", v), ("w", w)):
+        Rp.put(n, a)
+    dz = 0.1 * random_field(pp, 32)
+    Rp.put("divtz", dz)
+    out["press_u"], out["press_v"], out["press_w"], out["press_divtz"] = u, v, w, dz
+    Rp.call("press_stag_array")
+    for n in ("p", "dpdx", "dpdy", "dpdz"):
+        out[f"press_{n}"] = Rp.get(n)
+    meta = dict(params=params_record(p), made_by="oracle/make_reference_fixtures.py")
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: done")
+
+
+if __name__ == "__main__":
+    if not refrun.available():
+        sys.exit("the reference sources are not at " + refrun.REF)
+    os.makedirs(GOLD, exist_ok=True)
+    only = sys.argv[1:]
+    if not only or "routines" in only:
+        run_routines()
+    for name, c in STEP_CASES.items():
+        if not only or name in only:
+            run_step_case(name, **c)

@@ -1,0 +1,162 @@
+"""refrun -- drive the reference's OWN Fortran sources (under /root/reference) through oracle/f90exec.py.
+
+TEST INFRASTRUCTURE ONLY.  This is the closest thing to "the reference itself run here" that a container
+without any Fortran compiler allows (probes: BASELINE.md): the statements of fft.f90, emul_complex.f90,
+derivatives.f90, convec.f90, press_stag_array.f90, tridag_array.f90, forcing.f90 (project), cfl_util.f90,
+mpi_defs.f90, wallstress.f90, sgs_stag_util.f90, divstress_uv/w.f90, sim_param.f90 and the time-loop body of
+main.f90 are interpreted as they stand, with the reference's default build flags (USE_MPI, USE_SAFETYMODE;
+CMakeLists.txt:22-31), one rank (an MPI build run with -np 1: lbz = 0, neighbours MPI_PROC_NULL).  Bound by this
+file, because they live outside the reference's sources:
+  * FFTW3 (dfftw_plan_dft_*_2d, dfftw_execute_dft_r2c / c2r): pocketfft through the oracle's r2c / c2r, so that
+    a difference between this run and the oracle isolates the restated LOGIC, not FFT rounding;
+  * MPI (mpi_sendrecv / send / recv to MPI_PROC_NULL are no-ops, mpi_allreduce over one rank is a copy);
+  * lesgo.conf parsing (input_util.f90): the derived sizes of input_util.f90:197-235 are set from Params.
+Nothing is copied: the reference text is read at run time.  /root/reference does not exist on the GPU boxes, so
+only oracle/make_reference_fixtures.py (run here) imports this; tests use the frozen tests/golden/ref_*.npz.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import f90exec as F
+from . import lesgo_oracle as O
+
+REF = os.environ.get("LESGO_REFERENCE_DIR", "/root/reference")
+FILES = ["types.f90", "param.f90", "sim_param.f90", "messages.f90", "emul_complex.f90", "fft.f90", "derivatives.f90",
+         "convec.f90", "tridag_array.f90", "press_stag_array.f90", "cfl_util.f90", "forcing.f90", "mpi_defs.f90",
+         "sgs_param.f90", "test_filtermodule.f90", "wallstress.f90", "sgs_stag_util.f90", "divstress_uv.f90",
+         "divstress_w.f90"]
+MPI_PROC_NULL = -2
+
+
+def available():
+    return os.path.isdir(REF) and os.path.exists(os.path.join(REF, "convec.f90"))
+
+
+class Reference:
+    """One rank of the reference, interpreted.  Fields are the module arrays of sim_param (Fortran bounds kept)."""
+
+    def __init__(self, p: O.Params, files=FILES, alloc_fill=0.0):
+        assert p.nproc == 1, "one rank (an MPI build run with -np 1)"
+        self.p = p
+        I = self.I = F.Interpreter(defines=("PPMPI", "PPSAFETYMODE"), alloc_fill=alloc_fill)
+        for f in files:
+            I.load(os.path.join(REF, f))
+        self.plans = {}
+        self._externals()
+        S = lambda n, v: I.set("param", n, v)
+        # input_util.f90:197-235 (derived sizes) and the lesgo.conf blocks this path reads
+        S("nproc", 1); S("coord", 0); S("rank", 0)
+        S("nx", p.nx); S("ny", p.ny); S("nz", p.nz); S("nz_tot", p.nz_tot)
+        S("nx2", p.nx2); S("ny2", p.ny2); S("lh", p.lh); S("ld", p.ld); S("lh_big", p.lh_big); S("ld_big", p.ld_big)
+        S("l_x", p.L_x); S("l_y", p.L_y); S("l_z", p.L_z); S("z_i", p.z_i)
+        S("dx", p.dx); S("dy", p.dy); S("dz", p.dz)
+        S("dt", p.dt); S("tadv1", p.tadv1); S("tadv2", p.tadv2); S("dt_f", p.dt)
+        S("lbc_mom", p.lbc_mom); S("ubc_mom", p.ubc_mom); S("sgs", bool(p.sgs)); S("molec", bool(p.molec))
+        S("sgs_model", p.sgs_model); S("nu_molec", p.nu_molec); S("u_star", p.u_star); S("co", p.Co)
+        S("wall_damp_exp", p.wall_damp_exp); S("vonk", p.vonk); S("zo", p.zo); S("ifilter", p.ifilter)
+        S("ubot", p.ubot); S("utop", p.utop)
+        S("use_mean_p_force", bool(p.use_mean_p_force)); S("mean_p_force_x", p.mean_p_force_x); S("mean_p_force_y", p.mean_p_force_y)
+        S("up", MPI_PROC_NULL); S("down", MPI_PROC_NULL); S("comm", 0); S("ierr", 0); S("mpi_rprec", 0)
+        S("status", F.FArray.alloc((8,), (1,), "integer"))
+        S("initu", False); S("jt_total", 0); S("jt", 0); S("use_cfl_dt", False); S("cfl", 0.0625)
+        I.call("sim_param_init", module="sim_param")              # sim_param.f90: allocates the 33 module arrays
+        if "sgs_param" in I.modules and "sgs_param_init" in I.modules["sgs_param"].procs:
+            I.call("sgs_param_init", module="sgs_param")          # initialize.f90:129
+        I.call("init_fft", module="fft")                          # initialize.f90:172; fft.f90:102-160: plans + wavenumbers
+        if "test_filtermodule" in I.modules and "test_filter_init" in I.modules["test_filtermodule"].procs:
+            I.call("test_filter_init", module="test_filtermodule")   # initialize.f90:176
+
+    # ---- what lives outside the reference's own sources ---------------------------------------------
+    def _externals(self):
+        I = self.I
+        plans = self.plans
+
+        def plan(kind):
+            def f(fr, a):
+                h = len(plans) + 1
+                plans[h] = (kind, int(a[1][0]), int(a[2][0]))
+                a[0][1](h)                                           # integer*8 plan handle, by reference
+            return f
+
+        def execute(kind):
+            def f(fr, a):
+                k, n0, n1 = plans[int(a[0][0])]
+                assert k == kind, "plan direction"
+                src, dst = a[1][0], a[2][0]
+                x = src.a.T                                          # (n_slow, 2*(n_fast/2+1)), C order view
+                assert x.shape == (n1, 2 * (n0 // 2 + 1)), (x.shape, n0, n1)
+                y = O.r2c(np.ascontiguousarray(x)[None], n0)[0] if kind == "r2c" else O.c2r(np.ascontiguousarray(x)[None], n0)[0]
+                dst.a.T[...] = y
+            return f
+
+        def sendrecv(fr, a):
+            dest, src = int(a[3][0]), int(a[8][0])
+            if dest != MPI_PROC_NULL or src != MPI_PROC_NULL:
+                raise F.FortranError("one rank only: neighbours must be MPI_PROC_NULL")
+
+        def send_or_recv(fr, a):
+            if int(a[3][0]) != MPI_PROC_NULL:
+                raise F.FortranError("one rank only: neighbours must be MPI_PROC_NULL")
+
+        def allreduce(fr, a):
+            a[1][1](a[0][0])                                         # recvbuf = sendbuf over one rank
+
+        def error(fr, a):
+            raise F.FortranError("reference called error(): " + " ".join(str(x[0]) for x in a))
+
+        I.externals.update({
+            "dfftw_plan_dft_r2c_2d": plan("r2c"), "dfftw_plan_dft_c2r_2d": plan("c2r"),
+            "dfftw_execute_dft_r2c": execute("r2c"), "dfftw_execute_dft_c2r": execute("c2r"),
+            "mpi_sendrecv": sendrecv, "mpi_send": send_or_recv, "mpi_recv": send_or_recv, "mpi_allreduce": allreduce,
+            "error": error, "apply_inflow": lambda fr, a: None, "mpi_barrier": lambda fr, a: None,
+        })
+
+    # ---- fields ---------------------------------------------------------------------------------------
+    def farray(self, name):
+        return self.I.get("sim_param", name)
+
+    def get(self, name):
+        """module array `name` as the oracle lays fields out: (0:nz, ny, ld); arrays declared 1:nz get a zero plane 0."""
+        fa = self.farray(name)
+        out = np.zeros((self.p.nz + 1, self.p.ny, self.p.ld))
+        k0 = fa.lb[2]
+        out[k0:k0 + fa.a.shape[2]] = fa.a.transpose(2, 1, 0)
+        return out
+
+    def put(self, name, arr):
+        fa = self.farray(name)
+        k0 = fa.lb[2]
+        fa.a[...] = np.asarray(arr)[k0:k0 + fa.a.shape[2]].transpose(2, 1, 0)
+
+    def set_dt(self, dt, tadv1, tadv2):
+        self.I.set("param", "dt", float(dt)); self.I.set("param", "tadv1", float(tadv1)); self.I.set("param", "tadv2", float(tadv2))
+
+    # ---- routines -------------------------------------------------------------------------------------
+    def call(self, name, *args, module=None):
+        return self.I.call(name, *args, module=module)
+
+    def step(self, jt_total, mode="core"):
+        """One pass through the time-loop body of main.f90 (lines cited are the reference's): RHS_f = RHS, filt_da,
+        ddz, wallstress, [sgs_stag, tzz halo, divstress], convec, RHS assembly, mean pressure forcing, Euler start,
+        AB2, BOGUS, press_stag_array, RHS -= grad p, project.  mode "core" skips :189-203 (divt* stay as they are),
+        like the oracle's core mode."""
+        I = self.I
+        main = os.path.join(REF, "main.f90")
+        uses = ["types", "param", "sim_param", "derivatives", "forcing", "fft", "sgs_stag_util", "cfl_util"]
+        I.set("param", "jt_total", int(jt_total)); I.set("param", "jt", int(jt_total))     # main.f90:147-148, fresh run
+        I.exec_lines(main, 155, 184, uses)
+        if mode == "full":
+            I.exec_lines(main, 189, 203, uses)
+        I.exec_lines(main, 207, 214, uses)
+        I.exec_lines(main, 229, 232, uses)
+        I.exec_lines(main, 273, 326, uses)
+        I.exec_lines(main, 344, 344, uses)
+
+    def cfl_dt_step_setup(self):
+        """main.f90:135-144 (use_cfl_dt): executed from the reference text."""
+        main = os.path.join(REF, "main.f90")
+        self.I.set("param", "use_cfl_dt", True)
+        self.I.exec_lines(main, 135, 144, ["types", "param", "sim_param", "cfl_util"], local={"dt_dim": 0.0})

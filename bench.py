@@ -34,16 +34,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 A_CORE_BYTES = 296.0          # 37 FP64 words per point per step
+A_STEP_BYTES = 976.0          # the whole device-resident step in the reference's dataflow (122 words)
 FALLBACK_HBM_GBS = 6650.0     # B200_PROFILING.md fallback
+# BASELINE.json configs[3] (headline), configs[2], configs[4]
+WORKLOADS = {
+    "core512": dict(grid=(512, 512, 256), kind="core", text="LES channel core timestep 512x512x256 FP64 (device-resident)"),
+    "lasd256": dict(grid=(256, 256, 128), kind="lasd", text="LES channel 256x256x128, full step with the Lagrangian "
+                    "scale-dependent SGS model (lagrange_Sdep every cs_count = 5 steps), FP64, device-resident"),
+    "adm1024": dict(grid=(1024, 512, 256), kind="adm", text="turbines_ADM wind-farm channel 1024x512x256, full LES step "
+                    "(Smagorinsky) with 24 actuator disks, FP64, device-resident"),
+}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grid", default="512,512,256", help="nx,ny,Nz (lesgo.conf Nz)")
+    ap.add_argument("--workload", default="core512", choices=sorted(WORKLOADS),
+                    help="core512 (default, the headline of BASELINE.json): core step at 512x512x256; lasd256: configs[2], "
+                         "256x256x128 full LES step with the Lagrangian scale-dependent model (update every cs_count = 5 "
+                         "steps); adm1024: configs[4], 1024x512x256 full LES step with 24 actuator disks")
+    ap.add_argument("--grid", default=None, help="nx,ny,Nz (lesgo.conf Nz); overrides the workload's grid")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank-vs-oracle parity check before the timing")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the LASD and actuator-disk timings (rows (f)-2, (f)-3)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -215,22 +229,88 @@ def cpu_core_step_rate(nx, ny, workers, budget_s=20.0):
     return pts / dt / 1e6, f"{nx}x{ny}x{Nz} z-sample of the workload, {n} core steps, scipy.fft workers={workers}", dt
 
 
+def grid_of(args):
+    if args.grid:
+        return tuple(int(x) for x in args.grid.split(","))
+    return WORKLOADS[args.workload]["grid"]
+
+
 def run_reference(args, rank, world):
+    """CPU arm: the reference's algorithm for this path on the box's host cores.  The reference itself (Fortran +
+    FFTW3 + MPI) cannot be built on any box of this pool (no Fortran compiler), so this is the oracle
+    port -- the restatement that tests/test_reference_pin.py pins to the reference's source text -- with
+    multi-threaded pocketfft, on a bounded z-sample of the workload's plane size."""
     if rank != 0:
         return
-    nx, ny, Nz = (int(x) for x in args.grid.split(","))
+    nx, ny, Nz = grid_of(args)
     cores = os.cpu_count() or 1
-    # K steps, each a bounded sample
     v, sample, dt = cpu_core_step_rate(nx, ny, cores, budget_s=max(5.0, min(60.0, 4.0 * (args.steps + args.warmup))))
     line = {"impl": "reference", "metric": "grid-point updates/sec", "value": v, "unit": "Mpts/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"LES channel core step {nx}x{ny}x{Nz} (CPU: bounded z-sample)", "grid": [nx, ny, Nz]},
+            "config": {"workload": WORKLOADS[args.workload]["text"] + " (CPU: bounded z-sample, core step)", "grid": [nx, ny, Nz]},
             "cpu_baseline": {"value": v, "unit": "Mpts/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference cannot be built here (no gfortran/FFTW3/MPI): this is the oracle port of its "
-                    "algorithm with multi-threaded pocketfft, per-step time %.3f s on the sample" % dt}
+            "note": "reference cannot be built on this pool (no gfortran/FFTW3/MPI, BASELINE.md): oracle port of its "
+                    "algorithm, pinned to the reference's source text by tests/test_reference_pin.py; per-step time "
+                    "%.3f s on the sample" % dt}
     print(json.dumps(line), flush=True)
+
+
+def parity_check(dist, rank, world, local):
+    """Driver-visible multi-rank parity (outside every timed region): the `world` z-slab ranks of THIS launch advance a
+    small channel two core steps through the library (halos, slab <-> pencil transposes, k = 0 chain over NCCL /
+    peer memory, exactly the benchmarked code path) and rank 0 compares the gathered fields with the SINGLE-slab
+    oracle.  The oracle is used here only as the checker."""
+    import lesgo_b200
+    from lesgo_b200 import slab
+    from oracle import lesgo_oracle as O
+    kw = dict(nx=64, ny=64, Nz=8 * world, lbc_mom=1, ubc_mom=1, utop=1.0, ubot=-1.0)
+    pr = O.Params(nproc=world, coord=rank, **kw)
+    dims = lesgo_b200.Dims(nx=pr.nx, ny=pr.ny, Nz=pr.Nz, nproc=world, coord=rank, lbc_mom=1, ubc_mom=1, sgs=False, device=local)
+    core = lesgo_b200.Core(dims)
+    if world > 1:
+        slab.bootstrap_comm(core, dist)
+    ug, vg, wg = O.synthetic_global(pr.nx, pr.ny, pr.Nz, nproc=world, seed=7, amp=0.3)
+    for n, g in (("u", ug), ("v", vg), ("w", wg)):
+        core.upload(n, O.scatter_slab(g, pr))
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+        core.upload(n, np.zeros(dims.shape))
+    nsteps = 2
+    for it in range(nsteps):
+        core.step(dt=pr.dt, tadv1=1.5, tadv2=-0.5, first_step=(it == 0), mode=0, ubot=-1.0, utop=1.0)
+    names = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")
+    mine = {n: core.download(n) for n in names}
+    mine["cfl"] = core.max_cfl(pr.dt)
+    alls = [mine]
+    if world > 1:
+        alls = [None] * world
+        dist.all_gather_object(alls, mine)
+    out = None
+    if rank == 0:
+        pg = O.Params(nproc=1, **kw)
+        spg = O.Spectral(pg)
+        s = O.State(pg)
+        s.u, s.v, s.w = (O.scatter_slab(f, pg) for f in (ug, vg, wg))
+        for it in range(nsteps):
+            O.step(s, spg, O.LocalComm(), mode="core", first_step=(it == 0))
+        ps = [O.Params(nproc=world, coord=r, **kw) for r in range(world)]
+        worst = {}
+        for n in names:
+            top = n in ("w", "RHSz", "p")
+            g = O.gather_slabs([alls[r][n] for r in range(world)], ps, top_extra=top)
+            hi = pg.nz_tot if top else pg.nz_tot - 1
+            a, b = g[1:hi + 1, :, :pg.nx], getattr(s, n)[1:hi + 1, :, :pg.nx]
+            worst[n] = float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))
+        cfl_ref = O.get_max_cfl(s, pg, O.LocalComm())
+        out = {"nranks": world, "grid": [pg.nx, pg.ny, pg.Nz], "steps": nsteps, "max_rel_l2": max(worst.values()),
+               "rel_l2": worst, "max_cfl_rel_err": max(abs(alls[r]["cfl"] - cfl_ref) / cfl_ref for r in range(world)),
+               "gate": 1e-12, "pass": bool(max(worst.values()) <= 1e-12),
+               "checker": "single-slab oracle (oracle/lesgo_oracle.py, pinned to the reference sources by "
+                          "tests/test_reference_pin.py); transposes: " +
+                          ("n/a" if world == 1 else ("NVLink peer memory" if getattr(core, "p2p_enabled", False) else "NCCL"))}
+    del core
+    return out
 
 
 def main():
@@ -251,8 +331,21 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nx, ny, Nz = (int(x) for x in args.grid.split(","))
-    dims = lesgo_b200.Dims(nx=nx, ny=ny, Nz=Nz, nproc=world, coord=rank, lbc_mom=1, ubc_mom=1, sgs=True, device=local)
+    wl = WORKLOADS[args.workload]
+    kind = wl["kind"] if not args.grid else "core"
+    nx, ny, Nz = grid_of(args)
+
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_check(dist, rank, world, local)
+        except Exception as e:  # noqa
+            parity = {"error": str(e)}
+        if rank == 0 and parity and parity.get("pass") is False:
+            raise SystemExit(f"bench.py: {world}-rank parity check failed: {parity}")
+
+    wall = dict(lbc_mom=1, ubc_mom=1) if kind == "core" else dict(lbc_mom=2, ubc_mom=0)
+    dims = lesgo_b200.Dims(nx=nx, ny=ny, Nz=Nz, nproc=world, coord=rank, sgs=True, device=local, **wall)
     core = lesgo_b200.Core(dims)
     stream = torch.cuda.current_stream()
     core.set_stream(stream.cuda_stream)
@@ -267,92 +360,104 @@ def main():
     for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
         core.upload(n, zero)
     step_kw = dict(dt=dt, tadv1=tadv1, tadv2=tadv2, mode=0, ubot=-1.0, utop=1.0)
+    farm = None
+    if kind == "lasd":
+        for n in ("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2"):
+            core.upload(n, zero)
+        step_kw = dict(step_kw, mode=1, sgs_model=5, nu=1e-4, lagran_dt=5 * dt)
+    elif kind == "adm":
+        farm = synthetic_farm(dims)
+        core.turbines_init(farm)
+        step_kw = dict(step_kw, mode=1, sgs_model=1, nu=1e-4, turbines=True, turbines_eps=0.1)
+    del zero
+    jt = [0]
+
+    def one_step():
+        """One timestep of the workload; the LASD workload runs lagrange_Sdep on every fifth step (cs_count = 5,
+        sgs_stag_util.f90:192), as the shipped LES_channel_Re1000 does."""
+        jt[0] += 1
+        if kind == "lasd":
+            if jt[0] == 1:
+                core.step(first_step=True, lasd_cs_init=True, **step_kw)
+            elif jt[0] == 2:
+                core.step(lasd_update=True, lasd_init_F=True, **step_kw)
+            else:
+                core.step(lasd_update=(jt[0] % 5 == 0), **step_kw)
+        else:
+            core.step(first_step=(jt[0] == 1), **step_kw)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    core.step(first_step=True, **step_kw)
-    for _ in range(max(args.warmup - 1, 2)):
-        core.step(**step_kw)
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nwarm = max(args.warmup, 3)
+    if kind == "lasd":
+        nwarm = max(nwarm, 5)
+        while (nwarm % 5) != 0:
+            nwarm += 1                       # the timed region starts at a multiple of cs_count
+    for _ in range(nwarm):
+        one_step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     l0 = core.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        core.step(**step_kw)
-    e1.record(stream)
+    for i in range(args.steps):
+        ev[i].record(stream)
+        one_step()
+    ev[args.steps].record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = ev[0].elapsed_time(ev[args.steps])
+    per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
     launches = core.launch_count - l0
     clocks = sampler.stop() if sampler else None
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = allmax(ms)
     cfl = core.max_cfl(dt)
     if not math.isfinite(cfl) or cfl <= 0.0 or cfl > 10.0:
         raise SystemExit(f"bench.py: simulation state is not sane after the timed steps (CFL = {cfl})")
     ms_step = ms / args.steps
+    med = allmax(per_step[len(per_step) // 2])
     points = nx * ny * (dims.nz_tot - 1)
     value = points / (ms_step * 1e-3) / 1e6
 
     # per-pass breakdown: one instrumented step outside the timed region
     core.profile(True)
-    core.step(**step_kw)
+    one_step()
     kern = core.profile(False, report=True)
     peak, peak_src = hbm_peak()
-    achieved = A_CORE_BYTES * points / (ms_step * 1e-3) / 1e9 / world
+    abytes = A_CORE_BYTES if kind == "core" else A_STEP_BYTES
+    achieved = abytes * points / (ms_step * 1e-3) / 1e9 / world
     traffic, traffic_src = None, None
     try:
-        tpath = os.path.join(ROOT, "profiles", "r3_traffic.json")
-        if not os.path.exists(tpath):
-            tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
-        with open(tpath) as f:
-            tj = json.load(f)
-        if tj.get("grid") == [nx, ny, Nz] and world == 1:
-            traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
+        for tname in ("r4_traffic.json", "r3_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                if tj.get("grid") == [nx, ny, Nz] and world == 1 and kind == "core":
+                    traffic = tj["dram_bytes_per_step"]
+                    traffic_src = "FROM FILE profiles/%s, not measured in this run: %s" % (tname, tj["source"])
+                break
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": A_CORE_BYTES * points,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": abytes * points,
                 "peak_source": peak_src,
-                "definition": "296 B/point/step (SURVEY 8d A_core) * points / step time / n_gpus; whole hot path"}
+                "definition": ("296 B/point/step (SURVEY 8d A_core)" if kind == "core" else
+                               "976 B/point/step (SURVEY 8d A_step, the whole device-resident step in the reference's dataflow)")
+                + " * points / step time / n_gpus; whole hot path, all kernels of the step"}
     kernels = {k: {"launches": n, "ms": round(t, 4)} for k, (n, t) in sorted(kern.items(), key=lambda kv: -kv[1][1])}
 
-    # the complete step (rows (f)-1 on the device too: equilibrium wall model, Smagorinsky stress,
-    # stress divergence), timed separately; the headline stays the core step of SURVEY 8(d)
-    full = None
-    try:
-        fkw = dict(step_kw, mode=1, sgs_model=1, nu=1e-4)
-        for _ in range(2):
-            core.step(**fkw)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        nfull = max(2, args.steps // 2)
-        for _ in range(nfull):
-            core.step(**fkw)
-        f1.record(stream)
-        barrier()
-        fms = f0.elapsed_time(f1) / nfull
-        if dist is not None:
-            t = torch.tensor([fms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            fms = float(t.item())
-        full = {"ms_per_step": fms, "value": points / (fms * 1e-3) / 1e6, "unit": "Mpts/s",
-                "what": "core + DNS-wall wallstress + calc_Sij + Smagorinsky sgs_stag + divstress_uv/w"}
-    except Exception as e:  # noqa
-        full = {"error": str(e)}
-
-    # rows (f)-2 and (f)-3 of SURVEY section 8, timed the same way on the same grid: the Lagrangian
-    # scale-dependent model (one lagrange_Sdep per timed step; the reference runs it every cs_count = 5
-    # steps) and a 4 x 6 array of actuator disks
     def timed_steps(kw, n):
         for _ in range(2):
             core.step(**kw)
@@ -363,15 +468,17 @@ def main():
             core.step(**kw)
         b.record(stream)
         barrier()
-        t_ms = a.elapsed_time(b) / n
-        if dist is not None:
-            tt = torch.tensor([t_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_ms = float(tt.item())
-        return t_ms
+        return allmax(a.elapsed_time(b) / n)
 
-    lasd = None
-    if not args.no_extras:
+    # the complete step and rows (f)-2 ... (f)-4 of SURVEY section 8 on the headline grid, timed separately
+    full = lasd = turb = tavg = None
+    if kind == "core" and not args.no_extras:
+        try:
+            fms = timed_steps(dict(step_kw, mode=1, sgs_model=1, nu=1e-4), max(2, args.steps // 4))
+            full = {"ms_per_step": fms, "value": points / (fms * 1e-3) / 1e6, "unit": "Mpts/s",
+                    "what": "core + DNS-wall wallstress + calc_Sij + Smagorinsky sgs_stag + divstress_uv/w"}
+        except Exception as e:  # noqa
+            full = {"error": str(e)}
         try:
             lkw = dict(step_kw, mode=1, sgs_model=5, nu=1e-4, lagran_dt=5 * dt)
             core.step(lasd_cs_init=True, **lkw)
@@ -384,20 +491,15 @@ def main():
                     "what": "full step with sgs_model 5: + interpolag_Sdep + 42 test filters per plane + running averages"}
         except Exception as e:  # noqa
             lasd = {"error": str(e)}
-    turb = None
-    if not args.no_extras:
         try:
             farm = synthetic_farm(dims)
             core.turbines_init(farm)
-            tkw = dict(step_kw, mode=1, sgs_model=1, nu=1e-4)
-            t_ms = timed_steps(dict(tkw, turbines=True, turbines_eps=0.1), 3)
+            t_ms = timed_steps(dict(step_kw, mode=1, sgs_model=1, nu=1e-4, turbines=True, turbines_eps=0.1), 3)
             turb = {"ms_per_step": t_ms, "value": points / (t_ms * 1e-3) / 1e6, "unit": "Mpts/s", "disks": len(farm),
                     "nodes_this_rank": int(sum(len(t.ind) for t in farm)),
                     "what": "full step (Smagorinsky) + turbines_forcing: gather, all-reduce, scatter, RHS += f"}
         except Exception as e:  # noqa
             turb = {"error": str(e)}
-    tavg = None
-    if not args.no_extras:
         try:
             core.tavg_compute(dt)
             barrier()
@@ -415,24 +517,27 @@ def main():
             tavg = {"error": str(e)}
 
     e2e = None
-    if rank == 0 and not args.no_e2e and world == 1:
-        e2e = run_e2e(core, dims, u, v, w, dt, tadv1, args.e2e_steps, points)
+    if not args.no_e2e:
+        e2e = run_e2e(core, dims, u, v, w, dt, tadv1, args.e2e_steps, points, kind, step_kw, barrier, allmax, world)
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu and world == 1:
         cores = os.cpu_count() or 1
         cv, sample, _ = cpu_core_step_rate(nx, ny, cores, budget_s=15.0)
         cpu = {"value": cv, "unit": "Mpts/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
         line = {"metric": "grid-point updates/sec", "value": value, "unit": "Mpts/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "steps": args.steps, "warmup": nwarm, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"LES channel core timestep {nx}x{ny}x{Nz} FP64 (device-resident)",
+                "config": {"workload": wl["text"] if not args.grid else f"LES channel core timestep {nx}x{ny}x{Nz} FP64 (device-resident)",
+                           "name": args.workload if not args.grid else "custom-grid core step",
                            "grid": [nx, ny, Nz], "decomposition": f"z-slabs x{world}",
                            "pressure_transposes": ("n/a" if world == 1 else
                                                    ("NVLink peer-memory stores" if getattr(core, "p2p_enabled", False)
                                                     else "NCCL all-to-all")),
                            "l2": "inputs larger than L2 (%.0f MB per field)" % (np.prod(dims.shape) * 8 / 1e6)},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                "per_step_ms": {"median": med, "min": per_step[0], "max": per_step[-1],
+                                "how": "one CUDA event pair per step inside the same timed region (rank 0; median = max over ranks)"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "parity": parity,
                 "clocks": clocks, "kernels": kernels, "max_cfl": cfl, "full_step": full, "lasd_step": lasd, "turbines_step": turb, "tavg": tavg}
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -440,54 +545,80 @@ def main():
         dist.destroy_process_group()
 
 
-def run_e2e(core, dims, u, v, w, dt, tadv1, nsteps, points):
-    """The same hot path through the reference-facing per-routine C ABI with HOST buffers
-    (pinned), i.e. what the Fortran shim does when LESGO keeps its module arrays on the
-    host: every call stages its inputs H2D and its outputs D2H inside the timed region."""
+def run_e2e(core, dims, u, v, w, dt, tadv1, nsteps, points, kind, step_kw, barrier, allmax, world):
+    """The same metric end to end through the reference-facing C ABI with HOST buffers, every rank on its own slab,
+    host<->device copies inside the timed region (wall clock around synchronised calls, max over ranks).
+
+    core workload -- the per-routine entry points the Fortran shims bind (filt_da x3, ddz_uv x2, ddz_w, convec,
+    press_stag_array), each staging its inputs H2D and its outputs D2H, measured three ways: the arrays page-locked
+    with lesgo_gpu_host_register as fortran/lesgo_gpu_mod.f90 does for the module arrays (the headline `value`),
+    plain pageable arrays (what an unmodified host would pass), and for reference torch-pinned arrays.
+    Every workload -- `whole_step_api`: the resident-state entry (upload u, v, w, RHS*; lesgo_gpu_step; download the
+    seven result fields), which is what the shims' resident module uses and the headline for the full-step workloads.
+    """
     import torch
 
-    def pinned(a=None):
-        t = torch.empty(dims.shape, dtype=torch.float64, pin_memory=True)
-        if a is None:
-            t.zero_()
-        else:
-            t.copy_(torch.from_numpy(a))
-        return t.numpy()
+    def host_arrays(mode, names, init):
+        out = {}
+        for n in names:
+            if mode == "pinned":
+                t = torch.empty(dims.shape, dtype=torch.float64, pin_memory=True)
+                a = t.numpy()
+                out["_t_" + n] = t                   # keeps the pinned allocation alive
+            else:
+                a = np.empty(dims.shape)
+            a[...] = init.get(n, 0.0)
+            if mode == "registered":
+                core.host_register(a)
+            out[n] = a
+        return out
 
-    F = {n: pinned() for n in ("dudx", "dudy", "dudz", "dvdx", "dvdy", "dvdz", "dwdx", "dwdy", "dwdz", "RHSx", "RHSy",
-                               "RHSz", "divtz", "p", "dpdx", "dpdy", "dpdz")}
-    F["u"], F["v"], F["w"] = pinned(u), pinned(v), pinned(w)
     nb = float(np.prod(dims.shape) * 8)
-    h2d = nb * (3 * 1 + 3 * 1 + 9 + 4)          # filt_da in; ddz in; convec in; press in (outputs are not uploaded)
-    d2h = nb * (3 * 3 + 3 + 3 + 4)
+    res = {}
+    if kind == "core":
+        names = ("dudx", "dudy", "dudz", "dvdx", "dvdy", "dvdz", "dwdx", "dwdy", "dwdz", "RHSx", "RHSy", "RHSz", "divtz",
+                 "p", "dpdx", "dpdy", "dpdz", "u", "v", "w")
+        h2d = nb * (3 * 1 + 3 * 1 + 9 + 4)          # filt_da in; ddz in; convec in; press in (outputs are not uploaded)
+        d2h = nb * (3 * 3 + 3 + 3 + 4)
+        variants = {}
+        for mode in ("registered", "pageable", "pinned"):
+            F = host_arrays(mode, names, {"u": u, "v": v, "w": w})
 
-    def one():
-        core.filt_da(F["u"], F["dudx"], F["dudy"])
-        core.filt_da(F["v"], F["dvdx"], F["dvdy"])
-        core.filt_da(F["w"], F["dwdx"], F["dwdy"])
-        core.ddz_uv(F["u"], F["dudz"])
-        core.ddz_uv(F["v"], F["dvdz"])
-        core.ddz_w(F["w"], F["dwdz"])
-        core.convec(F["u"], F["v"], F["w"], F["dudy"], F["dudz"], F["dvdx"], F["dvdz"], F["dwdx"], F["dwdy"],
-                    F["RHSx"], F["RHSy"], F["RHSz"])
-        core.press_stag_array(F["u"], F["v"], F["w"], F["divtz"], dt, tadv1, F["p"], F["dpdx"], F["dpdy"], F["dpdz"])
+            def one():
+                core.filt_da(F["u"], F["dudx"], F["dudy"])
+                core.filt_da(F["v"], F["dvdx"], F["dvdy"])
+                core.filt_da(F["w"], F["dwdx"], F["dwdy"])
+                core.ddz_uv(F["u"], F["dudz"])
+                core.ddz_uv(F["v"], F["dvdz"])
+                core.ddz_w(F["w"], F["dwdz"])
+                core.convec(F["u"], F["v"], F["w"], F["dudy"], F["dudz"], F["dvdx"], F["dvdz"], F["dwdx"], F["dwdy"],
+                            F["RHSx"], F["RHSy"], F["RHSz"])
+                core.press_stag_array(F["u"], F["v"], F["w"], F["divtz"], dt, tadv1, F["p"], F["dpdx"], F["dpdy"], F["dpdz"])
 
-    one()                                   # warm-up (allocates the staging buffers)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(nsteps):
-        one()
-    torch.cuda.synchronize()
-    t = (time.perf_counter() - t0) / nsteps
-    out = {"value": points / t / 1e6, "unit": "Mpts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": t * 1e3, "api": "per-routine C ABI (filt_da x3, ddz_uv x2, ddz_w, convec, press_stag_array), "
-           "pinned host arrays"}
-    # for comparison, NOT the headline: the whole-step entry with the state held by the host -- upload
-    # u, v, w, RHSx, RHSy, RHSz, one lesgo_gpu_step, download u, v, w, p, RHSx, RHSy, RHSz, every step
+            one()                                   # warm-up (allocates the staging buffers)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(nsteps):
+                one()
+            barrier()
+            t = allmax((time.perf_counter() - t0) / nsteps)
+            variants[mode] = {"value": points / t / 1e6, "ms_per_step": t * 1e3}
+            if mode == "registered":
+                for n in names:
+                    core.host_unregister(F[n])
+            del F
+        res = {"value": variants["registered"]["value"], "unit": "Mpts/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": variants["registered"]["ms_per_step"],
+               "api": "per-routine C ABI (filt_da x3, ddz_uv x2, ddz_w, convec, press_stag_array) on host arrays page-locked "
+                      "with lesgo_gpu_host_register, as fortran/lesgo_gpu_mod.f90 registers the sim_param arrays",
+               "host_memory": variants, "n_gpus": world}
+    # the whole-step entry with the state held by the host: upload u, v, w, RHSx, RHSy, RHSz, one lesgo_gpu_step,
+    # download u, v, w, p, RHSx, RHSy, RHSz, every step
     try:
-        S = {n: pinned() for n in ("RHSx", "RHSy", "RHSz", "p")}
-        S["u"], S["v"], S["w"] = pinned(u), pinned(v), pinned(w)
-        kw = dict(dt=dt, tadv1=tadv1, tadv2=-0.5, mode=0, ubot=-1.0, utop=1.0)
+        S = host_arrays("registered", ("RHSx", "RHSy", "RHSz", "p", "u", "v", "w"), {"u": u, "v": v, "w": w})
+        kw = dict(step_kw)
+        if kind == "lasd":
+            kw["lasd_update"] = False
 
         def one_step(first=False):
             for n in ("u", "v", "w", "RHSx", "RHSy", "RHSz"):
@@ -497,18 +628,26 @@ def run_e2e(core, dims, u, v, w, dt, tadv1, nsteps, points):
                 core.download(n, S[n])
 
         one_step(True)
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(nsteps):
             one_step()
-        torch.cuda.synchronize()
-        ts = (time.perf_counter() - t0) / nsteps
-        out["whole_step_api"] = {"value": points / ts / 1e6, "unit": "Mpts/s", "ms_per_step": ts * 1e3,
-                                 "h2d_bytes_per_step": 6 * nb, "d2h_bytes_per_step": 7 * nb,
-                                 "api": "lesgo_gpu_upload x6 + lesgo_gpu_step + lesgo_gpu_download x7, pinned host arrays"}
+        barrier()
+        ts = allmax((time.perf_counter() - t0) / nsteps)
+        ws = {"value": points / ts / 1e6, "unit": "Mpts/s", "ms_per_step": ts * 1e3,
+              "h2d_bytes_per_step": 6 * nb * world, "d2h_bytes_per_step": 7 * nb * world,
+              "api": "lesgo_gpu_upload x6 + lesgo_gpu_step + lesgo_gpu_download x7, host arrays page-locked with "
+                     "lesgo_gpu_host_register (fortran/lesgo_gpu_resident_mod.f90)"}
+        for n in ("RHSx", "RHSy", "RHSz", "p", "u", "v", "w"):
+            core.host_unregister(S[n])
     except Exception as e:  # noqa
-        out["whole_step_api"] = {"error": str(e)}
-    return out
+        ws = {"error": str(e)}
+    if kind == "core":
+        res["whole_step_api"] = ws
+    else:
+        res = dict(ws)
+        res["n_gpus"] = world
+    return res
 
 
 if __name__ == "__main__":

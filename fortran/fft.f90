@@ -1,8 +1,10 @@
 !> Drop-in replacement for module fft (reference fft.f90:24-162): same public names.
-!> The four FFTW plan handles become tags understood by the dfftw_* shims at the bottom,
-!> so callers outside the hot path that still use the legacy FFTW API with these plans
-!> (test_filtermodule.f90:138,144; scalars.f90; turbine_indicator.f90:130-151) keep
-!> working without FFTW being linked.
+!> init_fft makes its four plans exactly as the reference does (fft.f90:114-121) -- but the symbols
+!> dfftw_plan_dft_r2c_2d / dfftw_plan_dft_c2r_2d / dfftw_execute_dft_r2c / dfftw_execute_dft_c2r /
+!> dfftw_destroy_plan now resolve to liblesgo_cuda.so (include/lesgo_gpu.h, csrc/fftw_shim.cu), so callers
+!> outside the hot path that still use the legacy FFTW API with these handles or with plans of their own
+!> (test_filtermodule.f90:138,144; scalars.f90:513-624; turbine_indicator.f90:130-151) keep working and
+!> libfftw3 is no longer linked.
 module fft
 use types, only : rprec
 use param, only : ld, lh, ny, ld_big, ny2
@@ -13,13 +15,23 @@ public :: padd, unpadd, init_fft
 public :: kx, ky, k2
 public :: forw, back, forw_big, back_big
 real(rprec), allocatable, dimension(:,:) :: kx, ky, k2
-integer*8 :: forw = 1, back = 2, forw_big = 3, back_big = 4
+integer*8 :: forw, back, forw_big, back_big
 contains
 
 subroutine init_fft()
+use param, only : nx, ny, nx2, ny2
+real(rprec), allocatable, dimension(:,:) :: data, data_big
+integer, parameter :: FFTW_PATIENT = 32, FFTW_UNALIGNED = 2     ! fftw3.f; ignored by the library
 call gpu_require()
+allocate(data(ld, ny), data_big(ld_big, ny2))
+call dfftw_plan_dft_r2c_2d(forw, nx, ny, data, data, FFTW_PATIENT, FFTW_UNALIGNED)
+call dfftw_plan_dft_c2r_2d(back, nx, ny, data, data, FFTW_PATIENT, FFTW_UNALIGNED)
+call dfftw_plan_dft_r2c_2d(forw_big, nx2, ny2, data_big, data_big, FFTW_PATIENT, FFTW_UNALIGNED)
+call dfftw_plan_dft_c2r_2d(back_big, nx2, ny2, data_big, data_big, FFTW_PATIENT, FFTW_UNALIGNED)
+deallocate(data, data_big)
 allocate(kx(lh, ny), ky(lh, ny), k2(lh, ny))
 call gpu_check(lesgo_gpu_wavenumbers(gpu_ctx, kx, ky, k2), 'init_fft')
+call gpu_pin_sim_param()       ! sim_param_init ran before init_fft (initialize.f90:126,172)
 end subroutine init_fft
 
 subroutine padd(u_big, u)
@@ -35,20 +47,3 @@ call gpu_check(lesgo_gpu_unpadd(gpu_ctx, cc, cc_big, 1), 'unpadd')
 end subroutine unpadd
 
 end module fft
-
-!> FFTW legacy-Fortran entry points for the four plans above (one plane per call).
-subroutine dfftw_execute_dft_r2c(plan, a, b)
-use lesgo_gpu_mod
-implicit none
-integer*8, intent(in) :: plan
-real(c_double) :: a(*), b(*)
-call gpu_check(lesgo_gpu_fft_r2c(gpu_ctx, a, b, 1, merge(1, 0, plan == 3)), 'dfftw_execute_dft_r2c')
-end subroutine dfftw_execute_dft_r2c
-
-subroutine dfftw_execute_dft_c2r(plan, a, b)
-use lesgo_gpu_mod
-implicit none
-integer*8, intent(in) :: plan
-real(c_double) :: a(*), b(*)
-call gpu_check(lesgo_gpu_fft_c2r(gpu_ctx, a, b, 1, merge(1, 0, plan == 4)), 'dfftw_execute_dft_c2r')
-end subroutine dfftw_execute_dft_c2r

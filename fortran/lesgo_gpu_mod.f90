@@ -53,6 +53,22 @@ interface
         type(c_ptr), value :: ctx
         character(kind=c_char), intent(in) :: blobs(*)
     end function
+    integer(c_int) function lesgo_gpu_host_register(ctx, host, bytes) bind(c, name='lesgo_gpu_host_register')
+        import
+        type(c_ptr), value :: ctx
+        type(c_ptr), value :: host
+        integer(c_size_t), value :: bytes
+    end function
+    integer(c_int) function lesgo_gpu_host_unregister(ctx, host) bind(c, name='lesgo_gpu_host_unregister')
+        import
+        type(c_ptr), value :: ctx
+        type(c_ptr), value :: host
+    end function
+    integer(c_int) function lesgo_gpu_comm_p2p_import_null(ctx, nothing) bind(c, name='lesgo_gpu_comm_p2p_import')
+        import
+        type(c_ptr), value :: ctx
+        type(c_ptr), value :: nothing          ! c_null_ptr: back to the NCCL all-to-alls
+    end function
     integer(c_int) function lesgo_gpu_wavenumbers(ctx, kx, ky, k2) bind(c, name='lesgo_gpu_wavenumbers')
         import :: c_int, c_ptr, c_double
         type(c_ptr), value :: ctx
@@ -148,34 +164,77 @@ end interface
 contains
 
 !> Create the device context on first use (after read_input_conf and initialize_mpi):
-!> one rank = one GPU, device = local rank.  The NCCL id is made on coord 0 and
-!> broadcast with the MPI communicator LESGO already owns (mpi_defs.f90:77-87).
+!> one rank = one GPU.  The device is the NODE-LOCAL rank (MPI_Comm_split_type over shared
+!> memory) modulo the device count, so `mpirun -np 8 lesgo-mpi` on one 8-GPU box lands every rank on its
+!> own GPU without a CUDA_VISIBLE_DEVICES wrapper.  The NCCL id is made on coord 0 and broadcast with the
+!> MPI communicator LESGO already owns (mpi_defs.f90:77-87).
+!> The library addresses every field as (ld, ny, 0:nz), the layout of the MPI build (param.f90:68-72):
+!> a serial build has lbz = 1 and would be shifted by one plane, so it is refused here.
 subroutine gpu_require()
-use param, only : nx, ny, nz, nz_tot, nproc, coord, L_x, L_y, dz, lbc_mom, ubc_mom, sgs
+use param, only : nx, ny, nz, nz_tot, nproc, coord, L_x, L_y, dz, lbc_mom, ubc_mom, sgs, lbz
+use messages, only : error
 #ifdef PPMPI
 use param, only : comm, ierr
 use mpi
 #endif
 type(lesgo_gpu_dims) :: d
 character(kind=c_char) :: id(128), blob(128), blobs(128 * 8)
+integer :: device, local_comm, local_rank, p2p_ok, p2p_all
 if (c_associated(gpu_ctx)) return
+#ifndef PPMPI
+call error('lesgo_gpu.gpu_require', 'liblesgo_cuda needs the MPI build of LESGO (USE_MPI, lbz = 0); run it with -np 1 for one GPU')
+#endif
+if (lbz /= 0) call error('lesgo_gpu.gpu_require', 'lbz must be 0 (MPI build): the library addresses fields as (ld, ny, 0:nz)')
+device = -1
+#ifdef PPMPI
+call mpi_comm_split_type(comm, MPI_COMM_TYPE_SHARED, 0, MPI_INFO_NULL, local_comm, ierr)
+call mpi_comm_rank(local_comm, local_rank, ierr)
+call mpi_comm_free(local_comm, ierr)
+device = -2 - local_rank        ! lesgo_gpu_create maps -2 - r to device mod(r, device count)
+#endif
 d = lesgo_gpu_dims(nx, ny, nz, nz_tot, nproc, coord, L_x, L_y, dz, lbc_mom, ubc_mom,             &
-    merge(1, 0, sgs), -1)
+    merge(1, 0, sgs), device)
 call gpu_check(lesgo_gpu_create(d, gpu_ctx), 'lesgo_gpu_create')
 #ifdef PPMPI
 if (nproc > 1) then
     if (coord == 0) call gpu_check(lesgo_gpu_comm_unique_id(id), 'lesgo_gpu_comm_unique_id')
     call mpi_bcast(id, 128, MPI_CHARACTER, 0, comm, ierr)
     call gpu_check(lesgo_gpu_comm_init(gpu_ctx, id), 'lesgo_gpu_comm_init')
-    ! pressure transposes over NVLink peer memory (one node): gather every rank's 128-byte export
+    ! Pressure transposes over NVLink peer memory (one node, <= 8 ranks).  Optional and COLLECTIVE: a rank that
+    ! cannot export or map a peer buffer (ranks on several nodes, GPUs without P2P) makes every rank stay on the
+    ! NCCL all-to-alls -- the decision is all-reduced so the ranks never disagree.
     if (nproc <= 8) then
-        call gpu_check(lesgo_gpu_comm_p2p_export(gpu_ctx, blob), 'lesgo_gpu_comm_p2p_export')
-        call mpi_allgather(blob, 128, MPI_CHARACTER, blobs, 128, MPI_CHARACTER, comm, ierr)
-        call gpu_check(lesgo_gpu_comm_p2p_import(gpu_ctx, blobs), 'lesgo_gpu_comm_p2p_import')
+        p2p_ok = merge(1, 0, lesgo_gpu_comm_p2p_export(gpu_ctx, blob) == 0)
+        call mpi_allreduce(p2p_ok, p2p_all, 1, MPI_INTEGER, MPI_MIN, comm, ierr)
+        if (p2p_all == 1) then
+            call mpi_allgather(blob, 128, MPI_CHARACTER, blobs, 128, MPI_CHARACTER, comm, ierr)
+            p2p_ok = merge(1, 0, lesgo_gpu_comm_p2p_import(gpu_ctx, blobs) == 0)
+            call mpi_allreduce(p2p_ok, p2p_all, 1, MPI_INTEGER, MPI_MIN, comm, ierr)
+        end if
+        if (p2p_all /= 1) call gpu_check(lesgo_gpu_comm_p2p_import_null(gpu_ctx, c_null_ptr), 'lesgo_gpu_comm_p2p_import')
     end if
 end if
 #endif
 end subroutine gpu_require
+
+!> Page-lock a module array that is handed to the per-routine entry points every step (sim_param.f90:52-82
+!> allocatables are pageable): call once after sim_param_init, e.g. `call gpu_pin(u)`.
+subroutine gpu_pin(a)
+real(c_double), dimension(:,:,:), contiguous, target, intent(in) :: a
+call gpu_require()
+call gpu_check(lesgo_gpu_host_register(gpu_ctx, c_loc(a), int(size(a), c_size_t) * 8_c_size_t), 'lesgo_gpu_host_register')
+end subroutine gpu_pin
+
+!> Pin the arrays of the hot path (main.f90:161-172, 207, 317): called by the replacement init_fft.
+subroutine gpu_pin_sim_param()
+use sim_param
+call gpu_pin(u); call gpu_pin(v); call gpu_pin(w)
+call gpu_pin(dudx); call gpu_pin(dudy); call gpu_pin(dudz)
+call gpu_pin(dvdx); call gpu_pin(dvdy); call gpu_pin(dvdz)
+call gpu_pin(dwdx); call gpu_pin(dwdy); call gpu_pin(dwdz)
+call gpu_pin(RHSx); call gpu_pin(RHSy); call gpu_pin(RHSz)
+call gpu_pin(p); call gpu_pin(dpdx); call gpu_pin(dpdy); call gpu_pin(dpdz); call gpu_pin(divtz)
+end subroutine gpu_pin_sim_param
 
 !> Non-zero return code -> the reference's fatal-error path (messages.f90:228-240).
 subroutine gpu_check(rc, where)

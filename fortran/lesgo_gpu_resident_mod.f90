@@ -128,15 +128,25 @@ contains
 !> The `if` chain of sgs_stag_util.f90:183-216 and lagrange_Sdep.f90:270,320 as switches of the step:
 !> call once per time step before lesgo_gpu_step when sgs_model == 5.
 subroutine gpu_lasd_switches(sp, lasd_initialised)
-use param, only : jt, jt_total, DYN_init, cs_count, inilag, initu, dt
+use param, only : jt, jt_total, DYN_init, cs_count, inilag, initu, dt, use_cfl_dt
 type(lesgo_gpu_step_params), intent(inout) :: sp
 logical, intent(inout) :: lasd_initialised      !< F_LM_MM_init / F_QN_NN_init of lagrange_Sdep.f90:70-71
+real(c_double), save :: lagran_dt_acc = 0._c_double
 sp%lasd_cs_init = 0; sp%lasd_update = 0; sp%lasd_init_F = 0
-sp%lagran_dt = cs_count * dt                     ! sgs_stag_util.f90:82 (fixed dt)
+! sgs_stag_util.f90:73-82: with use_cfl_dt the Lagrangian time interval is ACCUMULATED, lagran_dt += dt on every
+! step from DYN_init - cs_count + 1 on (or initu), and reset after lagrange_Sdep (lagrange_Sdep.f90:430); with a
+! fixed time step it is cs_count * dt
+if (use_cfl_dt) then
+    if (jt >= DYN_init - cs_count + 1 .or. initu) lagran_dt_acc = lagran_dt_acc + dt
+    sp%lagran_dt = lagran_dt_acc
+else
+    sp%lagran_dt = cs_count * dt
+end if
 if (jt == 1 .and. inilag) then
     sp%lasd_cs_init = 1
 else if ((jt >= DYN_init .or. initu) .and. mod(jt_total, cs_count) == 0) then
     sp%lasd_update = 1
+    lagran_dt_acc = 0._c_double                  ! lagrange_Sdep.f90:430 (after this step has used sp%lagran_dt)
     if (inilag .and. .not. lasd_initialised .and. (jt == cs_count .or. jt == DYN_init)) then
         sp%lasd_init_F = 1
         lasd_initialised = .true.

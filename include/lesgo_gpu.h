@@ -23,6 +23,8 @@
 #ifndef LESGO_GPU_H
 #define LESGO_GPU_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -36,7 +38,8 @@ typedef struct lesgo_gpu_dims {
     double L_x, L_y, dz;     /* fft.f90:154-155 wavenumber scaling; input_util.f90:235  */
     int lbc_mom, ubc_mom;    /* wall types: select convec.f90:101-151 special planes    */
     int sgs;                 /* convec.f90:47-53: jzLo = 2 when LES, 1 when DNS         */
-    int device;              /* CUDA device ordinal, or -1 = current device             */
+    int device;              /* CUDA device ordinal; -1 = current device; -2 - r = node-local
+                                rank r, mapped to ordinal r mod (device count)          */
 } lesgo_gpu_dims;
 
 /* ---- lifetime (replaces init_fft, fft.f90:102-127) -------------------------------- */
@@ -44,6 +47,11 @@ int lesgo_gpu_create(const lesgo_gpu_dims* dims, lesgo_gpu_ctx** ctx);
 int lesgo_gpu_destroy(lesgo_gpu_ctx* ctx);
 const char* lesgo_gpu_last_error(const lesgo_gpu_ctx* ctx);   /* ctx may be NULL */
 int lesgo_gpu_set_stream(lesgo_gpu_ctx* ctx, void* cuda_stream);
+/* Page-lock (cudaHostRegister) / release a host array that is passed to the per-routine entry points again and
+ * again -- the Fortran shim does it for the module arrays of sim_param (sim_param.f90:52-82), which are pageable
+ * allocations: staged copies then run at PCIe rate and overlap with the kernels.  Idempotent. */
+int lesgo_gpu_host_register(lesgo_gpu_ctx* ctx, void* host, size_t bytes);
+int lesgo_gpu_host_unregister(lesgo_gpu_ctx* ctx, void* host);
 int lesgo_gpu_synchronize(lesgo_gpu_ctx* ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 long lesgo_gpu_launch_count(const lesgo_gpu_ctx* ctx);

@@ -328,6 +328,13 @@ class Core:
         self._ck(self.lib.rmsdiv(self._ctx, C.byref(v)), "rmsdiv")
         return v.value
 
+    def host_register(self, arr):
+        """Page-lock a numpy array that will be passed to the per-routine entry points repeatedly."""
+        self._ck(self.lib.host_register(self._ctx, arr.ctypes.data, arr.nbytes), "host_register")
+
+    def host_unregister(self, arr):
+        self._ck(self.lib.host_unregister(self._ctx, arr.ctypes.data), "host_unregister")
+
     # -- multi-GPU ---------------------------------------------------------------------------------
     def comm_unique_id(self, local: bool = False) -> bytes:
         """128-byte id for comm_init: NCCL's (one rank per GPU), or with local=True the id of the

@@ -1467,11 +1467,17 @@ int lesgo_gpu_create(const lesgo_gpu_dims* d, lesgo_gpu_ctx** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         return bail("no CUDA device: liblesgo_cuda has no CPU fallback");
-    if (d->device >= 0) {
-        if (d->device >= ndev) return bail("device ordinal out of range");
-        if (cudaSetDevice(d->device) != cudaSuccess) return bail("cudaSetDevice failed");
+    // device >= 0: that ordinal; -1: the calling thread's current device; <= -2: node-local rank r = -2 - device,
+    // mapped to ordinal r mod (device count) -- what the Fortran shim passes under mpirun, where every rank is its
+    // own process whose current device would otherwise be 0
+    int want = d->device;
+    if (want <= -2) want = (-2 - want) % ndev;
+    if (want >= 0) {
+        if (want >= ndev) return bail("device ordinal out of range");
+        if (cudaSetDevice(want) != cudaSuccess) return bail("cudaSetDevice failed");
     }
     cudaGetDevice(&c->device);
+    c->d.device = c->device;
     if (d->nx < 16 || d->ny < 16 || d->nz < 2 || (d->nx % 4) || (d->ny % 4)) return bail("bad grid size");
     if (!size_supported(d->nx) || !size_supported(d->ny)) return bail("nx/ny not in the supported FFT size list (sizes.h)");
     if (d->nproc < 1 || d->coord < 0 || d->coord >= d->nproc) return bail("bad nproc/coord");
@@ -1505,7 +1511,7 @@ int lesgo_gpu_create(const lesgo_gpu_dims* d, lesgo_gpu_ctx** out) {
     rc |= make_stage_twiddles(c, &c->Wyb, c->ny2, true);
     if (rc) { std::string m = c->err; return bail(m); }
     *out = c;
-    lesgo_gpu_fftw_bind(c, d);          // the dfftw_* symbols serve this context's plans (fftw_shim.cu)
+    lesgo_gpu_fftw_bind(c, &c->d);      // the dfftw_* symbols serve this context's plans (fftw_shim.cu)
     return 0;
 }
 
@@ -1521,6 +1527,31 @@ int lesgo_gpu_destroy(lesgo_gpu_ctx* c) {
     if (c->s_in) { cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out); }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
+    return 0;
+}
+
+// Page-lock a host array the caller keeps passing to the per-routine entry points (the Fortran module arrays of
+// sim_param are ordinary pageable allocations): staged copies then run at full PCIe rate and truly overlap with
+// the kernels of the chunk pipeline.  Idempotent; unregister before the array is deallocated.
+int lesgo_gpu_host_register(lesgo_gpu_ctx* c, void* host, size_t bytes) {
+    ENTER(c);
+    if (!c || !host || bytes == 0) return 1;
+#ifndef LESGO_EMUL
+    cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { cudaGetLastError(); return c->fail(std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+#endif
+    return 0;
+}
+
+int lesgo_gpu_host_unregister(lesgo_gpu_ctx* c, void* host) {
+    ENTER(c);
+    if (!c || !host) return 1;
+#ifndef LESGO_EMUL
+    cudaError_t e = cudaHostUnregister(host);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return c->fail(std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
+    cudaGetLastError();
+#endif
     return 0;
 }
 

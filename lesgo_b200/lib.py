@@ -42,6 +42,8 @@ SYMBOLS = {
     "lesgo_gpu_destroy": (C.c_int, [_P]),
     "lesgo_gpu_last_error": (C.c_char_p, [_P]),
     "lesgo_gpu_set_stream": (C.c_int, [_P, _P]),
+    "lesgo_gpu_host_register": (C.c_int, [_P, _P, C.c_size_t]),
+    "lesgo_gpu_host_unregister": (C.c_int, [_P, _P]),
     "lesgo_gpu_synchronize": (C.c_int, [_P]),
     "lesgo_gpu_launch_count": (C.c_long, [_P]),
     "lesgo_gpu_profile": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int]),

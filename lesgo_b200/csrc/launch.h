@@ -25,6 +25,9 @@ bool size_supported(int n_small);
 bool plan_lookup(int n, PlanDesc* out);
 // two-stage column plan (fft_core.h Plan2) of the y passes for length n, if one exists
 bool plan2_lookup(int n, int* r1, int* r2);
+// two-stage warp-scope x-inverse plan (wfft2_kernels.h) for rows of m complex points, if one exists
+bool xplan2_lookup(int m, int* r1, int* r2);
+bool xw2_enabled();      // LESGO_XW2=0 switches the two-stage x inverse off
 
 // products + forward x transform of convec, marching up z (prodfwd_kernels.h)
 struct ProdArgs;

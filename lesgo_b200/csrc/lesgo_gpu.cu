@@ -174,6 +174,14 @@ int make_stage_twiddles(lesgo_gpu_ctx* c, cplx** dst, int n, bool columns = fals
     }
     if (int(h.size()) != d.twlen) return c->fail("internal: stage twiddle table length mismatch");
     int r1 = 0, r2 = 0;
+    if (!columns && xplan2_lookup(n, &r1, &r2)) {
+        // x passes: the table of the two-stage warp-scope inverse (wfft2_kernels.h) follows the Stockham stage tables:
+        // rows r = 1..7, then r = 8, 16 of W_n^{j r}, j < 16
+        for (int r = 1; r < 8; ++r)
+            for (int j = 0; j < 16; ++j) h.push_back(unit_root(long(j) * r, n));
+        for (int r = 8; r < r2; r += 8)
+            for (int j = 0; j < 16; ++j) h.push_back(unit_root(long(j) * r, n));
+    }
     if (columns && plan2_lookup(n, &r1, &r2)) {
         // y passes: the table of the two-stage column plan (fft_core.h fft_tile2) follows the Stockham stage tables:
         // rows r = 1..7, then r = 8, 16, 24 of W_n^{j r}, j < R1

@@ -1,17 +1,20 @@
 """CPU oracle for the LESGO per-timestep pseudo-spectral core.  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the reference (lesgo-jhu/lesgo, Fortran + FFTW3 + MPI) cannot be
-built or run in this container (no Fortran compiler, no FFTW3, no MPI) and ships no
-golden vectors / known-answer tests for this path (its test strategy is a
-compile-and-run smoke matrix, `test-lesgo:72-73,125`).  This file is therefore a
-*restatement* of the reference algorithm, line-cited below, validated by the analytic
-known-answer tests in `tests/test_oracle_*.py` (single Fourier modes, discrete Poisson
-eigenfunctions, scipy banded solves, multi-slab == single-slab).  Third-party
-arithmetic on the path is FFTW3 (unvendored, unpinned: `CMakeLists.txt:63-66`,
-3.3.6-pl2 / 3.3.8 named at `:112-154`), whose published definition (unnormalised DFT,
-forward sign -1, r2c keeps kx = 0..nx/2 of the contiguous dimension, c2r ignores the
-imaginary parts of the kx=0 / kx=nx/2 columns after the y pass) is restated with
-`scipy.fft.rfft2 / irfft2(norm="forward")`.
+PARITY: pinned to the reference's own source text, FFTW3's internal rounding excepted.  The reference
+(lesgo-jhu/lesgo, Fortran + FFTW3 + MPI) cannot be built anywhere in this pool (no Fortran compiler, no
+FFTW3, no MPI: BASELINE.md) and ships no golden vectors for this path (`test-lesgo:72-73,125` is a
+compile-and-run smoke matrix), so this file is a line-cited *restatement*.  Since round 2 it is checked
+against the reference itself as far as that is possible here: `oracle/f90exec.py` interprets the reference's
+Fortran sources statement by statement (`oracle/refrun.py`; fixtures `tests/golden/ref_*.npz`), and
+`tests/test_reference_pin.py` holds this restatement to them -- bit-equal routine by routine for the
+derivatives, test filter, convec and the wavenumbers, 2e-16 for press_stag_array + tridag_array, 3e-16 after one
+whole step and <= 9e-13 after ten, core and full mode.  Third-party arithmetic on the path is FFTW3 (unvendored,
+unpinned: `CMakeLists.txt:63-66`, 3.3.6-pl2 / 3.3.8 named at `:112-154`), whose published definition
+(unnormalised DFT, forward sign -1, r2c keeps kx = 0..nx/2 of the contiguous dimension, c2r ignores the
+imaginary parts of the kx=0 / kx=nx/2 columns after the y pass) is restated with `scipy.fft.rfft2 /
+irfft2(norm="forward")` and pinned against numbers FFTW produced, Intel MKL and cuFFT (`tests/test_fft_pins.py`).
+NOT covered by a reference-source run (restatement + analytic known-answer tests only, `tests/test_oracle_kat.py`):
+lagrange_Sdep / interpolag_Sdep / trilinear_interp_w, turbines_forcing, tavg%compute, the restart record.
 
 Beyond the core path it restates SURVEY 8(f): wallstress / calc_Sij / sgs_stag / divstress,
 the Lagrangian scale-dependent model (lagrange_Sdep.f90, interpolag_Sdep.f90, trilinear_interp_w),

@@ -197,6 +197,8 @@ def test_emul_multirank_thin_slabs():
     ({"LESGO_XW": "3"}, "512,16,3", "deriv,convec,press"),
     ({"LESGO_XW": "2"}, "48,32,4", "deriv,convec,press,steps"),
     ({"LESGO_REUSE": "0"}, "16,16,6", "steps,full"),
+    ({"LESGO_XW2": "7"}, "512,16,3", "deriv,convec,press,steps"),     # two-stage x inverse on every x-inverse launch
+    ({"LESGO_XW2": "0"}, "512,16,3", "convec"),                       # ... and on none
 ])
 def test_emul_variants(env, grid, what):
     """Kernel variants behind environment switches (read once per process -> subprocess)."""

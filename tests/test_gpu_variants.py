@@ -17,6 +17,8 @@ VARIANTS = [
     ({"LESGO_XW": "3"}, "1024,32,3", "deriv,convec,press,steps"),
     ({"LESGO_PROD_CHUNK": "3"}, "128,64,8", "convec,steps"),
     ({"LESGO_REUSE": "0"}, "32,32,6", "steps,full"),
+    ({"LESGO_XW2": "7"}, "512,64,3", "deriv,convec,press,steps,full"),    # two-stage x inverse on every x-inverse launch
+    ({"LESGO_XW2": "0"}, "512,64,3", "convec,steps"),                     # ... and on none
 ]
 
 

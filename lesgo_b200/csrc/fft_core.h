@@ -512,6 +512,8 @@ LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St s
 #endif
 template <int N> struct Plan2 { static constexpr bool on = false; static constexpr int R1 = 1, R2 = 1; };
 #if LG_Y2STAGE
+template <> struct Plan2<256> { static constexpr bool on = true; static constexpr int R1 = 16, R2 = 16; };
+template <> struct Plan2<384> { static constexpr bool on = true; static constexpr int R1 = 16, R2 = 24; };
 template <> struct Plan2<512> { static constexpr bool on = true; static constexpr int R1 = 16, R2 = 32; };
 template <> struct Plan2<768> { static constexpr bool on = true; static constexpr int R1 = 32, R2 = 24; };
 #endif

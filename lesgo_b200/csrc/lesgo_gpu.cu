@@ -79,6 +79,7 @@ struct lesgo_gpu_ctx {
     double* p2p_flag = nullptr;            // device scalar for the stream-ordered barrier
     bool p2p_on = false;
     int p2p_parity = 0;
+    std::vector<void*> ipc_opened;         // peers' buffers mapped with cudaIpcOpenMemHandle (closed in destroy)
     // actuator disks (lesgo_gpu_turbines_init)
     TurbSet turb;
     bool turb_on = false, turb_fz = false;
@@ -1529,6 +1530,9 @@ int lesgo_gpu_destroy(lesgo_gpu_ctx* c) {
     if (lesgo_gpu_fftw_bound() == c) lesgo_gpu_fftw_bind(nullptr, nullptr);
     cudaStreamSynchronize(c->stream);
     if (c->comm) { delete c->comm; c->comm = nullptr; }
+#ifndef LESGO_EMUL
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+#endif
     for (void* p : c->allocs) cudaFree(p);
     for (double* p : c->staging) if (p) cudaFree(p);
     if (c->red_host) cudaFreeHost(c->red_host);
@@ -2157,6 +2161,7 @@ int lesgo_gpu_comm_p2p_import(lesgo_gpu_ctx* c, const void* blobs) {
             cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) return c->fail(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
             base = static_cast<double*>(p);
+            c->ipc_opened.push_back(p);
 #else
             return c->fail("emulator: ranks must be threads of one process");
 #endif

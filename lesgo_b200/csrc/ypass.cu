@@ -71,7 +71,7 @@ int launch_ypass_pad2(int ny, const YArgs& a, int nfields, int nplanes, const cp
 #define LG_SUP(S, B) if (n == S) return true;
 bool plan2_lookup(int n, int* r1, int* r2) {
 #define LG_PL2(N) if (n == N && Plan2<N>::on) { *r1 = Plan2<N>::R1; *r2 = Plan2<N>::R2; return true; }
-    LG_PL2(512) LG_PL2(768)
+    LG_PL2(256) LG_PL2(384) LG_PL2(512) LG_PL2(768)
 #undef LG_PL2
     return false;
 }

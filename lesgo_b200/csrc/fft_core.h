@@ -499,7 +499,7 @@ LG_D void fft_tile(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St s
 // A column makes ONE round trip through shared memory instead of the two of a three-stage radix-8 plan, with
 // one block barrier inside the transform instead of two, and about half the address arithmetic per point: the
 // y passes are bound by the instructions and shared-memory wavefronts they issue per point, not by arithmetic
-// (profiles/r4_y2stage.md).
+// (profiles/r4_experiments.md).
 //   stage 1 (radix R1, no twiddles):  work item j < N/R1 = R2 reads elements j + r*R2, writes slot R1*j + r
 //   stage 2 (radix R2, Ns = R1):      work item j < N/R2 = R1 reads slots j + r*R1 ( * W_N^{j r}), writes element j + r*R1
 // Shared-memory slot s of a column lives at (s + s/R1) * ES + f: the stage-1 stores of neighbouring work items are

@@ -331,7 +331,7 @@ template <int NIN, int NOUT, bool MULTI, int NOUT2 = 0> struct YCfg {
     static constexpr int NS = (NIN == 0) ? NOUT : ((NOUT == 0) ? NIN : (NIN < NOUT ? NIN : NOUT));  // spectral (small) length
     static constexpr int max2(int a, int b) { return a > b ? a : b; }
     // Two-stage column plans (fft_core.h Plan2) per kernel, by measurement on B200 at 512 x 512 x 256
-    // (profiles/r4_y2stage.md): they win for the forward-only pass and for filt_da's pass with the padded second
+    // (profiles/r4_experiments.md): they win for the forward-only pass and for filt_da's pass with the padded second
     // output, with 8 columns per tile; the pad / truncate passes keep the three-stage plans (the radix-32
     // butterflies cost 255 registers, which leaves one or two resident blocks).  LG_Y2_POLICY bits: 1 forward only,
     // 2 same-size + padded output, 4 inverse only with several outputs, 8 everything else.

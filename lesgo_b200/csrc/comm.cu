@@ -222,8 +222,10 @@ public:
     std::shared_ptr<LWorld> w;
     void set(int r, int n) { rank_ = r; nranks_ = n; }
     int put(int dst, const double* p, size_t n, cudaStream_t s) {
+        // stream-ordered allocation: no call on this path may synchronise the DEVICE, because another rank's
+        // flag-barrier kernel may be spinning on it until this rank gets to launch its own (ops.h k_p2p_barrier)
         LWorld::Msg m{nullptr, n, nullptr};
-        if (cudaMalloc(reinterpret_cast<void**>(&m.buf), (n ? n : 1) * sizeof(double)) != cudaSuccess) { err_ = "local comm: cudaMalloc"; return 1; }
+        if (cudaMallocAsync(reinterpret_cast<void**>(&m.buf), (n ? n : 1) * sizeof(double), s) != cudaSuccess) { err_ = "local comm: cudaMallocAsync"; return 1; }
         cudaMemcpyAsync(m.buf, p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
         cudaEventCreateWithFlags(&m.ev, cudaEventDisableTiming);
         cudaEventRecord(m.ev, s);
@@ -244,8 +246,7 @@ public:
         if (m.n != n) { err_ = "local comm: message size mismatch"; return 1; }
         cudaStreamWaitEvent(s, m.ev, 0);
         cudaMemcpyAsync(p, m.buf, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
-        const cudaError_t e = cudaStreamSynchronize(s);
-        cudaFree(m.buf);
+        const cudaError_t e = cudaFreeAsync(m.buf, s);          // after the copy, in stream order
         cudaEventDestroy(m.ev);
         if (e != cudaSuccess) { err_ = std::string("local comm: ") + cudaGetErrorString(e); return 1; }
         return 0;

@@ -529,7 +529,9 @@ template <int N> struct Plan2Info {
     static constexpr int slots = N + N / P::R1 + 1;                      // padded column length
 };
 
-template <int N, bool INV, int NF, int NTHR, bool LD_BUF, bool ST_BUF, int ES, class FOff, class Ld, class St,
+// F_FAST: consecutive threads take consecutive transforms (column tiles); else consecutive butterflies of one
+// transform (row tiles, ES = 1: keeps the stage-1 stores of a warp (R1+1) slots apart = conflict-free)
+template <int N, bool INV, int NF, int NTHR, bool LD_BUF, bool ST_BUF, int ES, bool F_FAST = true, class FOff, class Ld, class St,
           class Hook = NoHook>
 LG_D void fft_tile2(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St st, Hook hook = Hook()) {
     typedef Plan2<N> P;
@@ -542,7 +544,7 @@ LG_D void fft_tile2(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St 
         for (int q = 0; q < IPT; ++q) {
             const int it = threadIdx.x + q * NTHR;
             if (ITEMS % NTHR == 0 || it < ITEMS) {
-                const int f = it % NF, j = it / NF;
+                const int f = F_FAST ? it % NF : it / (ITEMS / NF), j = F_FAST ? it / NF : it % (ITEMS / NF);
 #pragma unroll
                 for (int r = 0; r < R1; ++r) v[q][r] = ld(f, j + r * T1);
                 if (INV) {
@@ -561,7 +563,7 @@ LG_D void fft_tile2(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St 
         for (int q = 0; q < IPT; ++q) {
             const int it = threadIdx.x + q * NTHR;
             if (ITEMS % NTHR == 0 || it < ITEMS) {
-                const int f = it % NF, j = it / NF;
+                const int f = F_FAST ? it % NF : it / (ITEMS / NF), j = F_FAST ? it / NF : it % (ITEMS / NF);
                 cplx* p = buf + (R1 + 1) * j * ES + foff(f);
 #pragma unroll
                 for (int r = 0; r < R1; ++r) p[r * ES] = v[q][r];
@@ -577,7 +579,7 @@ LG_D void fft_tile2(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St 
         for (int q = 0; q < IPT; ++q) {
             const int it = threadIdx.x + q * NTHR;
             if (ITEMS % NTHR == 0 || it < ITEMS) {
-                const int f = it % NF, j = it / NF;
+                const int f = F_FAST ? it % NF : it / (ITEMS / NF), j = F_FAST ? it / NF : it % (ITEMS / NF);
                 const cplx* p = buf + j * ES + foff(f);
 #pragma unroll
                 for (int r = 0; r < R2; ++r) v[q][r] = p[r * (R1 + 1) * ES];
@@ -613,7 +615,7 @@ LG_D void fft_tile2(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St 
         for (int q = 0; q < IPT; ++q) {
             const int it = threadIdx.x + q * NTHR;
             if (ITEMS % NTHR == 0 || it < ITEMS) {
-                const int f = it % NF, j = it / NF;
+                const int f = F_FAST ? it % NF : it / (ITEMS / NF), j = F_FAST ? it / NF : it % (ITEMS / NF);
 #pragma unroll
                 for (int r = 0; r < R2; ++r) st(f, j + r * R1, v[q][r]);
             }
@@ -626,7 +628,7 @@ LG_D void fft_tile2(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St 
 template <int N, bool INV, int NF, int NTHR, bool LD_BUF, bool ST_BUF, int ES, bool USE2, class FOff, class Ld, class St,
           class Hook = NoHook>
 LG_D void fft_tile_cols(cplx* buf, const cplx* __restrict__ W, FOff foff, Ld ld, St st, Hook hook = Hook()) {
-    if constexpr (USE2) fft_tile2<N, INV, NF, NTHR, LD_BUF, ST_BUF, ES>(buf, W, foff, ld, st, hook);
+    if constexpr (USE2) fft_tile2<N, INV, NF, NTHR, LD_BUF, ST_BUF, ES, true>(buf, W, foff, ld, st, hook);
     else fft_tile<N, INV, NF, true, NTHR, LD_BUF, ST_BUF, ES>(buf, W, foff, ld, st, hook);
 }
 

@@ -20,7 +20,7 @@
 
 namespace lg {
 
-constexpr int kMaxFields = 6;
+constexpr int kMaxFields = 9;     // filt_da of u, v, w in one go: nine x-inverse outputs
 
 // ---------------------------------------------------------------------------------
 // x forward:  real rows -> half spectrum rows

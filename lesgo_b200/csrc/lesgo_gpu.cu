@@ -56,6 +56,7 @@ struct lesgo_gpu_ctx {
     cplx *Wx = nullptr, *Whx = nullptr, *Wxb = nullptr, *Whxb = nullptr, *Wy = nullptr, *Wyb = nullptr;
     // scratch
     double* sa[kMaxFields] = {nullptr};    // small spectra / intermediates, (ld, ny, 0:nz)
+    double* sd[12] = {nullptr};            // lesgo_gpu_step's batched filt_da: 3 x spectra + 9 y-pass outputs
     double* bb[kMaxFields] = {nullptr};    // big-y intermediates, (ld, ny2, 0:nz)
     double* big[kMaxFields] = {nullptr};   // 3/2-grid physical fields, (ld_big, ny2, 0:nz)
     double* gam = nullptr;                 // tridiagonal gam(j) table (lh, ny, 0:nzt+1)
@@ -76,7 +77,10 @@ struct lesgo_gpu_ctx {
     size_t p2p_half = 0;                   // doubles per half
     double* p2p_pencil[8] = {nullptr};     // peers' pencil buffers in this rank's address space
     double* p2p_alt[8] = {nullptr};        // ... and their second halves
-    double* p2p_flag = nullptr;            // device scalar for the stream-ordered barrier
+    double* p2p_flag = nullptr;            // device scalar for the stream-ordered barrier (NCCL all-reduce form)
+    unsigned long long* p2p_sig[8] = {nullptr};   // peers' signal slots (16 per rank, after the two pencil halves)
+    unsigned long long p2p_epoch = 0;      // barriers passed so far (the value the next barrier signals)
+    bool p2p_flags_on = false;             // peer-memory flag barrier instead of the one-double NCCL all-reduce
     bool p2p_on = false;
     int p2p_parity = 0;
     std::vector<void*> ipc_opened;         // peers' buffers mapped with cudaIpcOpenMemHandle (closed in destroy)
@@ -584,6 +588,45 @@ int spectral_deriv(lesgo_gpu_ctx* c, const double* f, double* fout, double* dfdx
     return 0;
 }
 
+bool batch_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("LESGO_BATCH"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
+// main.f90:161-163 in one go: filt_da of u, v and w as ONE x-forward launch (3 fields), ONE y pass (3 fields, 3 + 1
+// outputs each) and ONE x-inverse launch (9 fields) instead of three of each.  Same kernels, same arithmetic; the
+// point is the tail of the persistent grids and the launch count, which matter most on the short slabs of a
+// many-GPU run (profiles/r4_experiments.md).
+int spectral_deriv_uvw(lesgo_gpu_ctx* c, double* const* F, bool bigy) {
+    const int nz = c->nz;
+    for (int i = 0; i < 12; ++i)
+        if (dev_alloc(c, &c->sd[i], size_t(c->plane) * (nz + 1))) return 1;
+    ProScale pro;
+    pro.src[0] = F[LG_U]; pro.src[1] = F[LG_V]; pro.src[2] = F[LG_W];
+    pro.lay = c->lay(); pro.scale = 1.0 / (double(c->nx) * double(c->ny));
+    if (xfwd(c, false, pro, 3, c->sd, c->plane, c->ld, c->nx / 2, c->ny, 0, nz + 1)) return 1;
+    YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, c->nx / 2, 0);
+    for (int f = 0; f < 3; ++f) {
+        a.fld[f].src = c->sd[f];
+        a.fld[f].out[0] = YOutSpec{c->sd[3 + 3 * f], Y_COPY};
+        a.fld[f].out[1] = YOutSpec{c->sd[4 + 3 * f], Y_IKX};
+        a.fld[f].out[2] = YOutSpec{c->sd[5 + 3 * f], Y_IKY};
+        if (bigy) a.fld[f].out2 = c->bb[f];
+    }
+    a.nout = 3;
+    if (bigy) {
+        a.dst2_plane = c->plane_bi; a.dst2_row = c->ld;
+        ProfScope ps_(c, "ypass_deriv");
+        if (launch_ypass_pad2(c->ny, a, 3, nz + 1, c->Wy, c->Wyb, c->stream)) return c->fail("unsupported ny for y pass");
+        c->launches++;
+    } else if (ypass(c, c->ny, c->ny, a, 3, 0, nz + 1)) return 1;
+    const double* xs[9];
+    for (int i = 0; i < 9; ++i) xs[i] = c->sd[3 + i];
+    double* xd[9] = {F[LG_U], F[LG_DUDX], F[LG_DUDY], F[LG_V], F[LG_DVDX], F[LG_DVDY], F[LG_W], F[LG_DWDX], F[LG_DWDY]};
+    return xinv(c, false, xs, c->plane, c->ld, c->nx / 2, 9, xd, c->lay(), c->ny, 0, nz + 1);
+}
+
 int ddz_uv(lesgo_gpu_ctx* c, const double* f, double* dfdz) {
     const int nz = c->nz;
     Staged* hp = HP(c);
@@ -838,6 +881,15 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
         // before any rank's next kernel reads them
         auto barrier = [&]() -> int {
             ProfScope ps_(c, "p2p_barrier");
+            if (c->p2p_flags_on) {
+                // flag barrier in peer memory: signal every rank's slot [coord] with the new epoch, wait for all of ours
+                P2PSig sg;
+                for (int q = 0; q < 8; ++q) sg.peer[q] = c->p2p_sig[q];
+                sg.rank = c->d.coord; sg.nproc = c->d.nproc; sg.epoch = ++c->p2p_epoch;
+                LG_LAUNCH(k_p2p_barrier, dim3(1), dim3(32), 0, c->stream, sg);
+                c->launches++;
+                return 0;
+            }
             if (c->comm->allreduce_sum_dev(c->p2p_flag, 1, c->stream)) return c->fail(c->comm->error());
             return 0;
         };
@@ -1386,9 +1438,13 @@ int step(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     if (reuse)
         for (int i = 0; i < 3; ++i)
             if (dev_alloc(c, &c->bb[i], size_t(c->plane_bi) * (nz + 1))) return 1;
-    if (spectral_deriv(c, F[LG_U], F[LG_U], F[LG_DUDX], F[LG_DUDY], reuse ? c->bb[0] : nullptr)) return 1;
-    if (spectral_deriv(c, F[LG_V], F[LG_V], F[LG_DVDX], F[LG_DVDY], reuse ? c->bb[1] : nullptr)) return 1;
-    if (spectral_deriv(c, F[LG_W], F[LG_W], F[LG_DWDX], F[LG_DWDY], reuse ? c->bb[2] : nullptr)) return 1;
+    if (batch_enabled() && c->chunk == 0 && !HP(c)) {
+        if (spectral_deriv_uvw(c, F, reuse)) return 1;
+    } else {
+        if (spectral_deriv(c, F[LG_U], F[LG_U], F[LG_DUDX], F[LG_DUDY], reuse ? c->bb[0] : nullptr)) return 1;
+        if (spectral_deriv(c, F[LG_V], F[LG_V], F[LG_DVDX], F[LG_DVDY], reuse ? c->bb[1] : nullptr)) return 1;
+        if (spectral_deriv(c, F[LG_W], F[LG_W], F[LG_DWDX], F[LG_DWDY], reuse ? c->bb[2] : nullptr)) return 1;
+    }
     if (ddz_uv(c, F[LG_U], F[LG_DUDZ])) return 1;
     if (ddz_uv(c, F[LG_V], F[LG_DVDZ])) return 1;
     if (ddz_w(c, F[LG_W], F[LG_DWDZ])) return 1;
@@ -2111,7 +2167,7 @@ int lesgo_gpu_comm_p2p_export(lesgo_gpu_ctx* c, void* blob128) {
     if (c->d.nproc < 2 || c->d.nproc > 8) return c->fail("peer-memory transposes need 2..8 ranks on one node");
     const size_t half = size_t(c->nz) * ((c->ny + c->d.nproc - 1) / c->d.nproc) * c->ld * c->d.nproc;
     if (!c->p2p_buf) {
-        if (dev_alloc(c, &c->p2p_buf, 2 * half)) return 1;
+        if (dev_alloc(c, &c->p2p_buf, 2 * half + 16)) return 1;      // + 16 signal slots of the flag barrier (zeroed)
         if (dev_alloc(c, &c->p2p_flag, 1)) return 1;
         c->p2p_half = half;
         CK(cudaStreamSynchronize(c->stream));
@@ -2168,8 +2224,14 @@ int lesgo_gpu_comm_p2p_import(lesgo_gpu_ctx* c, const void* blobs) {
         }
         c->p2p_pencil[q] = base;
         c->p2p_alt[q] = base + c->p2p_half;
+        c->p2p_sig[q] = reinterpret_cast<unsigned long long*>(base + 2 * c->p2p_half);
     }
     c->p2p_on = true;
+    {
+        // LESGO_P2P_FLAGS=0: keep the one-double NCCL all-reduce as the barrier of the peer-memory transposes
+        const char* e = std::getenv("LESGO_P2P_FLAGS");
+        c->p2p_flags_on = !(e && e[0] == '0');
+    }
     return 0;
 }
 

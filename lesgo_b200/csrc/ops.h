@@ -594,6 +594,39 @@ static __global__ void k_press_pack(PencilGeom g, const double* __restrict__ Hx,
     }
 }
 
+// Stream-ordered barrier of the peer-memory transposes without a collective: every rank's kernel stores the epoch
+// into slot [rank] of EVERY rank's signal array (remote stores over NVLink, after a system-scope fence: the preceding
+// kernel of this stream -- the one whose remote stores / in-place sweep the barrier protects -- has completed) and
+// then waits until all nproc slots of its OWN array carry that epoch.  One block of 32 threads; replaces a one-double
+// ncclAllReduce (~50 us at 8 GPUs) per barrier.
+struct P2PSig {
+    unsigned long long* peer[8];
+    int rank, nproc;
+    unsigned long long epoch;
+};
+static __global__ void k_p2p_barrier(P2PSig sg) {
+    const int q = threadIdx.x;
+#ifdef LESGO_EMUL
+    if (q == 0) {      // the emulator runs a block's threads one after the other: signal everybody first, then wait
+        for (int p = 0; p < sg.nproc; ++p) __atomic_store_n(&sg.peer[p][sg.rank], sg.epoch, __ATOMIC_RELEASE);
+        for (int p = 0; p < sg.nproc; ++p)
+            while (__atomic_load_n(&sg.peer[sg.rank][p], __ATOMIC_ACQUIRE) < sg.epoch) sched_yield();
+    }
+#else
+    __threadfence_system();
+    if (q < sg.nproc) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sg.peer[q] + sg.rank), "l"(sg.epoch) : "memory");
+        unsigned long long v = 0;
+        const unsigned long long* mine = sg.peer[sg.rank] + q;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        } while (v < sg.epoch);
+    }
+    __syncwarp();
+    __threadfence_system();
+#endif
+}
+
 // gam table in pencil layout: gam[global row][jy_local][jx]
 static __global__ void k_tridag_setup_pencil(PencilGeom g, int nzt, double* __restrict__ gam, int* __restrict__ fail) {
     const int nm = (g.lh - 1) * g.cy;

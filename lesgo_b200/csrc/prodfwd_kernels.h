@@ -25,17 +25,30 @@ struct ProdArgs {
     double scale;           // 1/(nx2*ny2), convec.f90:172
 };
 
+// LG_PROD2 = 1: two-stage row transform with LG_PROD2_THR threads.  Measured SLOWER on B200 (512 x 512 x 256: 5.92 / 5.03 /
+// 4.30 ms with 64 / 96 / 128 threads against 3.76 ms for the three-stage version with 160 threads): this kernel lives
+// on thread-level parallelism across its barriers, profiles/r4_experiments.md.  Off.
+#ifndef LG_PROD2
+#define LG_PROD2 0
+#endif
+#ifndef LG_PROD2_THR
+#define LG_PROD2_THR 96
+#endif
 template <int NX2> struct ProdCfg {
     static constexpr int M = NX2 / 2;
     static constexpr int NC = NX2 / 3;           // nx/2 spectral columns kept
     typedef TileGeom<M> G;
-    static constexpr int NTHR = G::round32(G::threads(3));
+    // two-stage row transform (fft_core.h fft_tile2: radix 16 x 24 for the 3/2 grid of 512) with few, fat threads --
+    // the three-stage version issues ~380 instructions per real point and waits on ~9 barriers per plane
+    static constexpr bool USE2 = LG_PROD2 && Plan2<M>::on && Plan2<M>::R1 == 16;
+    static constexpr int NTHR = USE2 ? LG_PROD2_THR : G::round32(G::threads(3));
     static constexpr int EPT = (M + NTHR - 1) / NTHR;     // row elements (complex pairs) per thread
     static constexpr int SL = SmemLen<M>::value;
-    static constexpr int TWL = PlanInfo<M>::twlen, NWH = M / 2 + 1;
+    static constexpr int TWL = USE2 ? Plan2Info<M>::twlen : PlanInfo<M>::twlen, NWH = M / 2 + 1;
+    static constexpr int TWOFF = USE2 ? PlanInfo<M>::twlen : 0;    // the two-stage rows follow the Stockham tables (lesgo_gpu.cu)
     static constexpr size_t smem = size_t(3 * SL + 6 * M + TWL + NWH) * sizeof(cplx);
     static constexpr int by_smem = int((227 * 1024) / (smem + 1024)) < 1 ? 1 : int((227 * 1024) / (smem + 1024));
-    static constexpr int by_regs = 65536 / (NTHR * 104) < 1 ? 1 : 65536 / (NTHR * 104);
+    static constexpr int by_regs = 65536 / (NTHR * (USE2 ? 200 : 104)) < 1 ? 1 : 65536 / (NTHR * (USE2 ? 200 : 104));
     static constexpr int MINB0 = by_smem < by_regs ? by_smem : by_regs;
     static constexpr int MINB = MINB0 > 4 ? 4 : MINB0;
 };
@@ -50,7 +63,7 @@ k_prodfwd(const __grid_constant__ ProdArgs a, const cplx* __restrict__ Wg, const
     cplx* stg = sm + 3 * SL;                     // staging: six physical rows of M complex pairs
     cplx* W = stg + 6 * M;
     cplx* Wh = W + C::TWL;
-    load_table(W, Wg, C::TWL);
+    load_table(W, Wg + C::TWOFF, C::TWL);
     load_table(Wh, Whg, C::NWH);
     __syncthreads();
 
@@ -148,6 +161,11 @@ k_prodfwd(const __grid_constant__ ProdArgs a, const cplx* __restrict__ Wg, const
             if (k < ka) continue;
 
             // forward transforms of cx(k-1), cy(k-1), cz(k) and the untangled store of nx/2 columns
+            if constexpr (C::USE2)
+                fft_tile2<M, false, 3, NTHR, true, true, 1, false>(rows, W, [](int f) { return f * SL; },
+                    [&](int f, int i) { return rows[f * SL + spad(i)]; },
+                    [&](int f, int i, cplx v) { rows[f * SL + spad(i)] = v; });
+            else
             fft_tile<M, false, 3, false, NTHR, true, true, 1>(rows, W, [](int f) { return f * SL; },
                 [&](int f, int i) { return rows[f * SL + spad(i)]; },
                 [&](int f, int i, cplx v) { rows[f * SL + spad(i)] = v; });

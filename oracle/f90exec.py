@@ -6,11 +6,13 @@ the restatement could never be compared with the reference itself.  This module 
 SOURCE FILES, statement by statement, where they lie under /root/reference: it preprocesses (cpp #ifdef with
 the reference's default build flags), parses and interprets the subset of Fortran 90 those files use -- modules,
 subroutines / functions, explicit- and assumed-shape arrays with arbitrary lower bounds, array sections, whole-
-array expressions, do / if / select case, user-defined operators, SAVE variables, allocate -- on NumPy arrays in
+array expressions, do / if / select case / where / forall, user-defined operators, internal procedures, derived
+types with pointer components, pointer association, SAVE variables, allocate, sequence association -- on NumPy arrays in
 IEEE double precision, in the reference's statement and evaluation order.  What it does NOT reproduce: FFTW's
 internal rounding (the dfftw_execute_* calls are bound by the caller, to pocketfft) and gfortran's code
 generation.  oracle/make_reference_fixtures.py uses it to run the reference's derivatives.f90, convec.f90,
-press_stag_array.f90, tridag_array.f90, fft.f90, emul_complex.f90, forcing.f90 (project), cfl_util.f90 and the
+press_stag_array.f90, tridag_array.f90, fft.f90, emul_complex.f90, forcing.f90 (project), cfl_util.f90, wallstress.f90,
+sgs_stag_util.f90, divstress_uv/w.f90, lagrange_Sdep.f90, interpolag_Sdep.f90, functions.f90, grid.f90 and the
 time-loop body of main.f90, and freezes the outputs under tests/golden/ref_*.npz, which pin the oracle and the
 CUDA path.  Nothing is copied from the reference: its text is read at run time and never stored in this repo.
 
@@ -489,9 +491,25 @@ class Decl:
         self.kind, self.dims, self.attrs, self.init = kind, dims, attrs, init
 
 
+class TypeDef:
+    def __init__(self, name):
+        self.name = name
+        self.members = {}
+
+
+class FStruct:
+    """An instance of a derived type: members by name (scalars, FArrays or None for unallocated / unassociated)."""
+
+    def __init__(self, typedef):
+        self.__dict__["_type"] = typedef
+        for n, d in typedef.members.items():
+            self.__dict__[n] = None
+
+
 class Module:
     def __init__(self, name):
         self.name = name
+        self.types = {}
         self.decls = {}
         self.vars = {}
         self.uses = []
@@ -505,8 +523,10 @@ def _parse_decl(text, where):
     """type-spec [, attrs] [::] entities -> (kind, attrs, [(name, dims, init)])."""
     m = _TYPE_RE.match(text)
     kind = m.group(1).replace(" ", "")
+    tname = None
     if kind.startswith(("type", "class")):
         kind = "derived"
+        tname = text[m.end():text.index(")", m.end())].strip()
     if kind == "doubleprecision":
         kind = "real"
     rest = text[m.end():] if not kind == "derived" else text[m.end() - 1:]
@@ -521,6 +541,8 @@ def _parse_decl(text, where):
     else:
         attr_txt, ent_txt = "", rest
     attrs = {}
+    if tname:
+        attrs["typename"] = tname
     for a in _split_top(attr_txt.strip().lstrip(",")):
         if not a:
             continue
@@ -625,10 +647,23 @@ class Interpreter:
                 elif gen and names:
                     mod.generics.setdefault(gen, []).extend(names)
                 continue
-            if re.match(r"^type\b(?!\s*\()", s):         # derived-type definition: not supported, skipped
+            mt = re.match(r"^type\b(?!\s*\()(?:\s*,[^:]*)?(?:\s*::)?\s*(\w+)$", s)
+            if mt:                                        # derived-type definition: data members only
+                td = TypeDef(mt.group(1))
+                i += 1
                 while not re.match(r"^end\s*type", lines[i][1]):
+                    t = lines[i][1]
+                    if t == "contains":
+                        while not re.match(r"^end\s*type", lines[i][1]):
+                            i += 1
+                        break
+                    if _TYPE_RE.match(t) and "::" in t:
+                        kind, attrs, ents = _parse_decl(t, path)
+                        for name, dims, init in ents:
+                            td.members[name] = Decl(kind, dims, attrs, init)
                     i += 1
                 i += 1
+                mod.types[td.name] = td
                 continue
             self._spec(mod, s, path, no)
             i += 1
@@ -851,7 +886,17 @@ class Interpreter:
             for it in _split_top(m.group(1)):
                 if re.match(r"^(stat|source|mold)\s*=", it):
                     continue
-                p = it.index("(")
+                p = it.rindex("(") if it.rstrip().endswith(")") else it.index("(")
+                # the dimension list is the LAST parenthesised group (the target may be a component: this%x(n))
+                depth, p = 0, len(it) - 1
+                for q in range(len(it) - 1, -1, -1):
+                    if it[q] == ")":
+                        depth += 1
+                    elif it[q] == "(":
+                        depth -= 1
+                        if depth == 0:
+                            p = q
+                            break
                 items.append((it[:p].strip(), [_parse_dim(d) for d in _split_top(it[p + 1:_match_paren(it, p)])]))
             return ("allocate", loc, items), i + 1
         m = re.match(r"^deallocate\s*\((.*)\)$", s)
@@ -865,6 +910,9 @@ class Interpreter:
             return None, i + 1
         if re.match(r"^(read|open|close|rewind|inquire|backspace)\b", s):
             return ("unsupported", loc, s), i + 1
+        if "=>" in s and _find_assign(s) < 0:
+            lhs, rhs = s.split("=>", 1)
+            return ("ptrassign", loc, parse_expr(lhs.strip()), parse_expr(rhs.strip())), i + 1
         k = _find_assign(s)
         if k > 0:
             return ("assign", loc, parse_expr(s[:k]), parse_expr(s[k + 1:])), i + 1
@@ -896,6 +944,11 @@ class Interpreter:
             return arr
         if d.dims:
             return None                      # unallocated
+        if d.kind == "derived" and d.attrs.get("typename"):
+            for mod in self.modules.values():
+                if d.attrs["typename"] in mod.types:
+                    return FStruct(mod.types[d.attrs["typename"]])
+            return None
         if d.init is not None:
             try:
                 v = fr.eval(parse_expr(d.init))
@@ -1001,6 +1054,11 @@ class Interpreter:
         for dummy, (val, ref) in actuals.items():
             d = pr.decls.get(dummy)
             if d is None or not d.dims:
+                if isinstance(val, ElemRef):             # array element to a scalar dummy: by reference
+                    er = val
+                    val = er.value()
+                    val = val.item() if hasattr(val, "item") else val
+                    ref = (lambda x, er=er: er.base.a.__setitem__(er.idx, x))
                 if isinstance(val, FArray) and d is not None and not d.dims:
                     raise FortranError(f"{pr.name}: array passed to scalar dummy {dummy}")
                 fr.vars[dummy] = val
@@ -1022,11 +1080,13 @@ class Interpreter:
             if d.attrs.get("parameter"):
                 fr.vars[name] = self._initial(d, fr, name)
                 continue
-            if d.dims and not d.attrs.get("allocatable"):
+            if d.dims and not d.attrs.get("allocatable") and not d.attrs.get("pointer"):
                 shape, lb = self._dims(d.dims, fr)
                 fr.vars[name] = FArray.alloc(shape, lb, d.kind if d.kind != "derived" else "real", self.alloc_fill)
             else:
                 fr.vars[name] = None
+        if pr.kind == "function" and pr.result not in fr.vars and pr.result not in fr.cells:
+            fr.vars[pr.result] = None            # `integer function f(...)`: the result is typed by the prefix
         try:
             fr.run(pr.body)
         except _Return:
@@ -1039,6 +1099,10 @@ class Interpreter:
         return None
 
     def _bind_array(self, pr, dummy, d, val, fr):
+        if isinstance(val, ElemRef):
+            flat = val.base.a.reshape(-1, order="F")
+            start = int(np.ravel_multi_index(val.idx, val.base.a.shape, order="F"))
+            val = FArray(flat[start:], None, val.base.kind)
         if not isinstance(val, FArray):
             raise FortranError(f"{pr.name}: scalar passed to array dummy {dummy}")
         dims = [_parse_dim(x) for x in d.dims]
@@ -1229,6 +1293,8 @@ class Frame:
             if isinstance(v, FArray):
                 return v, None
             return v, (lambda val, n=ast[1]: self.store(n, val))
+        if ast[0] == "comp":
+            return self.eval_object(ast), None
         if ast[0] == "call" and ast[1][0] == "name" and self._find(ast[1][1]) is not None:
             base = self.lookup(ast[1][1])
             if isinstance(base, FArray):
@@ -1284,9 +1350,26 @@ class Frame:
             return np.array(flat, dtype=np.int64 if all(_is_int(v) for v in flat) else np.float64)
         if t == "call":
             return self.call_or_index(e)
+        if t == "comp":
+            v = self.eval_object(e)
+            if isinstance(v, FArray):
+                return v.a
+            if v is None:
+                raise FortranError(f"component {e[2]} used before it has a value")
+            return v
         if t == "defop":
             return self.defined_op(e[1], e[2], e[3])
         raise FortranError(f"cannot evaluate {e!r}")
+
+    def eval_object(self, e):
+        """a name or component reference -> the object itself (FArray / FStruct / scalar), no copy."""
+        if e[0] == "name":
+            return self.lookup(e[1])
+        if e[0] == "comp":
+            return getattr(self.eval_object(e[1]), e[2])
+        if e[0] == "paren":
+            return self.eval_object(e[1])
+        raise FortranError(f"not an object reference: {e!r}")
 
     def binop(self, op, a, b):
         if op == "//":
@@ -1341,6 +1424,13 @@ class Frame:
 
     def call_or_index(self, e):
         head, args = e[1], e[2]
+        if head[0] == "comp":
+            base = self.eval_object(head)
+            if not isinstance(base, FArray):
+                raise FortranError(f"component {head[2]} is not an (allocated) array")
+            idx, scalar = base.index([self.subscript(a) for a in args])
+            v = base.a[idx]
+            return (v.item() if hasattr(v, "item") else v) if scalar else v
         if head[0] != "name":
             raise FortranError(f"unsupported reference {e!r}")
         name = head[1]
@@ -1605,8 +1695,22 @@ class Frame:
                         hi_v = int(self.eval(hi))
                         lb.append(lo_v)
                         shape.append(max(hi_v - lo_v + 1, 0))
+                    if "%" in name:
+                        tgt = parse_expr(name)
+                        obj = self.eval_object(tgt[1])
+                        md = obj._type.members.get(tgt[2])
+                        k = md.kind if md is not None else "real"
+                        setattr(obj, tgt[2], FArray.alloc(shape, lb, k if k in ("real", "integer", "logical", "complex") else "real", self.I.alloc_fill))
+                        continue
                     k = self.kind_of(name) or "real"
                     self.store(name, FArray.alloc(shape, lb, k if k in ("real", "integer", "logical", "complex") else "real", self.I.alloc_fill))
+            elif t == "ptrassign":
+                src = st[3]
+                val = self.eval_object(src) if src[0] in ("comp", "name") else self.reference(src)[0]
+                if st[2][0] == "name":
+                    self.store(st[2][1], val)
+                else:
+                    setattr(self.eval_object(st[2][1]), st[2][2], val)
             elif t == "deallocate":
                 for name in st[2]:
                     self.store(name, None)
@@ -1645,6 +1749,20 @@ class Frame:
                 self.store(lhs[1], FArray(np.array(val, order="F"), None, k))
                 return
             self.store(lhs[1], _coerce(val, self.kind_of(lhs[1])))
+            return
+        if lhs[0] == "comp":
+            obj = self.eval_object(lhs[1])
+            cur = getattr(obj, lhs[2])
+            if isinstance(cur, FArray):
+                cur.a[...] = val
+            else:
+                md = obj._type.members.get(lhs[2])
+                setattr(obj, lhs[2], _coerce(val, md.kind if md is not None else None))
+            return
+        if lhs[0] == "call" and lhs[1][0] == "comp":
+            base = self.eval_object(lhs[1])
+            idx, _ = base.index([self.subscript(a) for a in lhs[2]])
+            base.a[idx] = val
             return
         if lhs[0] == "call" and lhs[1][0] == "name":
             base = self.lookup(lhs[1][1])

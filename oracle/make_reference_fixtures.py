@@ -49,6 +49,36 @@ STEP_CASES = {
 }
 
 
+LASD_FIELDS = ("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2")
+
+
+def run_lasd_case(name="ref_full_lasd_16x16x6", nsteps=4):
+    """Rows (f)-2 from the reference text: lagrange_Sdep.f90 + interpolag_Sdep.f90 + trilinear_interp_w / cell_indx_w
+    (functions.f90) + grid_m, inside full steps with sgs_model = 5, DYN_init = cs_count = 2 (Cs_opt2 = 0.03 at jt = 1,
+    updates at jt = 2 and 4, F_* initialised at jt = 2)."""
+    kw = dict(nx=16, ny=16, Nz=6, L_x=4.0, L_y=3.0, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=5, molec=False, dt=2e-3)
+    p = O.Params(**kw)
+    R = refrun.Reference(p, files=refrun.LASD_FILES, dyn_init=2, cs_count=2)
+    u, v, w = initial_fields(p, seed=61, amp=0.5)
+    out = {"u0": u, "v0": v, "w0": w}
+    for n, a in (("u", u), ("v", v), ("w", w)):
+        R.put(n, a)
+    t0 = time.time()
+    for it in range(1, nsteps + 1):
+        R.step(it, mode="full")
+        if it in (2, nsteps):
+            for n in STEP_FIELDS:
+                out[f"{n}_{it}"] = R.get(n)
+            for n in LASD_FIELDS:
+                out[f"{n}_{it}"] = R.get(n.lower(), module="sgs_param")
+    meta = dict(params=params_record(p), mode="full", record=[2, nsteps], cfl=None, dyn_init=2, cs_count=2,
+                made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py",
+                statements=R.I.nstmt)
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: {nsteps} steps, {R.I.nstmt} reference statements, {time.time() - t0:.1f} s")
+
+
 def initial_fields(p, seed=41, amp=0.3):
     u, v, w = O.synthetic_global(p.nx, p.ny, p.Nz, nproc=1, seed=seed, amp=amp, L_x=p.L_x, L_y=p.L_y, L_z=p.L_z)
     return tuple(O.scatter_slab(f, p) for f in (u, v, w))
@@ -163,3 +193,5 @@ if __name__ == "__main__":
     for name, c in STEP_CASES.items():
         if not only or name in only:
             run_step_case(name, **c)
+    if not only or "lasd" in only:
+        run_lasd_case()

@@ -28,6 +28,9 @@ FILES = ["types.f90", "param.f90", "sim_param.f90", "messages.f90", "emul_comple
          "convec.f90", "tridag_array.f90", "press_stag_array.f90", "cfl_util.f90", "forcing.f90", "mpi_defs.f90",
          "sgs_param.f90", "test_filtermodule.f90", "wallstress.f90", "sgs_stag_util.f90", "divstress_uv.f90",
          "divstress_w.f90"]
+# + the Lagrangian scale-dependent dynamic model (rows (f)-2): grid_m (derived type with pointer components),
+# trilinear_interp_w / cell_indx in functions.f90, lagrange_Sdep.f90, interpolag_Sdep.f90
+LASD_FILES = FILES + ["grid.f90", "functions.f90", "lagrange_Sdep.f90", "interpolag_Sdep.f90"]
 MPI_PROC_NULL = -2
 
 
@@ -38,7 +41,7 @@ def available():
 class Reference:
     """One rank of the reference, interpreted.  Fields are the module arrays of sim_param (Fortran bounds kept)."""
 
-    def __init__(self, p: O.Params, files=FILES, alloc_fill=0.0):
+    def __init__(self, p: O.Params, files=FILES, alloc_fill=0.0, dyn_init=100, cs_count=5):
         assert p.nproc == 1, "one rank (an MPI build run with -np 1)"
         self.p = p
         I = self.I = F.Interpreter(defines=("PPMPI", "PPSAFETYMODE"), alloc_fill=alloc_fill)
@@ -62,10 +65,13 @@ class Reference:
         S("up", MPI_PROC_NULL); S("down", MPI_PROC_NULL); S("comm", 0); S("ierr", 0); S("mpi_rprec", 0)
         S("status", F.FArray.alloc((8,), (1,), "integer"))
         S("initu", False); S("jt_total", 0); S("jt", 0); S("use_cfl_dt", False); S("cfl", 0.0625)
+        S("inilag", True); S("dyn_init", int(dyn_init)); S("cs_count", int(cs_count))
         I.call("sim_param_init", module="sim_param")              # sim_param.f90: allocates the 33 module arrays
         if "sgs_param" in I.modules and "sgs_param_init" in I.modules["sgs_param"].procs:
             I.call("sgs_param_init", module="sgs_param")          # initialize.f90:129
         I.call("init_fft", module="fft")                          # initialize.f90:172; fft.f90:102-160: plans + wavenumbers
+        if "grid_m" in I.modules and "build" in I.modules["grid_m"].procs:
+            I.call("build", I.get("grid_m", "grid"), module="grid_m")     # initialize.f90:132 call grid%build()
         if "test_filtermodule" in I.modules and "test_filter_init" in I.modules["test_filtermodule"].procs:
             I.call("test_filter_init", module="test_filtermodule")   # initialize.f90:176
 
@@ -118,9 +124,9 @@ class Reference:
     def farray(self, name):
         return self.I.get("sim_param", name)
 
-    def get(self, name):
+    def get(self, name, module="sim_param"):
         """module array `name` as the oracle lays fields out: (0:nz, ny, ld); arrays declared 1:nz get a zero plane 0."""
-        fa = self.farray(name)
+        fa = self.I.get(module, name)
         out = np.zeros((self.p.nz + 1, self.p.ny, self.p.ld))
         k0 = fa.lb[2]
         out[k0:k0 + fa.a.shape[2]] = fa.a.transpose(2, 1, 0)

@@ -22,7 +22,9 @@ import lesgo_b200
 from helpers import O, make_dims, rel, step_kwargs_pre_dyn
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-STEP_FIXTURES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "ref_*.npz")) if "routines" not in f)
+STEP_FIXTURES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "ref_*.npz"))
+                       if "routines" not in f and "lasd" not in f)
+LASD_FIELDS = ("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2")
 FIELDS = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")
 
 
@@ -39,6 +41,7 @@ def valid(p, n, a):
 
 def test_fixtures_exist():
     assert len(STEP_FIXTURES) >= 5 and os.path.exists(os.path.join(GOLD, "ref_routines_16x16x6.npz"))
+    assert os.path.exists(os.path.join(GOLD, "ref_full_lasd_16x16x6.npz"))
 
 
 @pytest.mark.parametrize("name", STEP_FIXTURES)
@@ -144,6 +147,75 @@ def test_live_reference_sources_when_present():
         for n in FIELDS + ("txz", "divtx"):
             assert rel(valid(p, n, getattr(s, n)), valid(p, n, R.get(n))) <= 1e-13, (cfg, n)
         assert R.I.nstmt > 10000                           # the reference's statements really ran
+
+
+def lasd_schedule_ref(it, meta):
+    """Step counters of sgs_stag_util.f90:183-216 for the fixture's DYN_init / cs_count (fresh run, jt = jt_total = it)."""
+    dyn, cs = meta["dyn_init"], meta["cs_count"]
+    return dict(lasd_cs_init=(it == 1), lasd_update=(it >= dyn and it % cs == 0), lasd_init_F=(it == dyn))
+
+
+def test_oracle_lasd_matches_reference_sources():
+    """lagrange_Sdep.f90 + interpolag_Sdep.f90 + trilinear_interp_w as the reference wrote them vs the oracle's
+    restatement: velocities, pressure and the model state F_LM, F_MM, F_QN, F_NN, Cs_opt2 after 2 and 4 steps."""
+    d, meta, p = load("ref_full_lasd_16x16x6")
+    sp = O.Spectral(p)
+    G, G2 = O.test_filter_kernel(sp), O.test_filter_kernel(sp, alpha=4.0)
+    s = O.State(p)
+    O.lasd_alloc(s)
+    s.u, s.v, s.w = d["u0"].copy(), d["v0"].copy(), d["w0"].copy()
+    worst = {}
+    for it in range(1, max(meta["record"]) + 1):
+        sch = lasd_schedule_ref(it, meta)
+        lasd = dict(sp=sp, G_test=G, G_test_test=G2, lagran_dt=meta["cs_count"] * p.dt, cs_init=sch["lasd_cs_init"],
+                    update=sch["lasd_update"], init_F=sch["lasd_init_F"])
+        O.step(s, sp, O.LocalComm(), mode="full", first_step=(it == 1), G_test=G, lasd=lasd)
+        if it in meta["record"]:
+            for n in FIELDS:
+                worst[(it, n)] = rel(valid(p, n, getattr(s, n)), valid(p, n, d[f"{n}_{it}"]))
+            for n in LASD_FIELDS:
+                worst[(it, n)] = rel(getattr(s, n)[1:p.nz + 1, :, :p.nx], d[f"{n}_{it}"][1:p.nz + 1, :, :p.nx])
+    print({k: f"{v:.1e}" for k, v in worst.items()})
+    for (it, n), v in worst.items():
+        assert v <= (1e-11 if n == "Cs_opt2" else 1e-12), (it, n, v)
+
+
+def run_core_on_lasd_fixture(core):
+    d, meta, p = load("ref_full_lasd_16x16x6")
+    for n in ("u", "v", "w"):
+        core.upload(n, d[n + "0"])
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz") + LASD_FIELDS:
+        core.upload(n, np.zeros(core.dims.shape))
+    worst = {}
+    for it in range(1, max(meta["record"]) + 1):
+        from helpers import step_kwargs
+        core.step(**step_kwargs(p, it - 1, "full"), **lasd_schedule_ref(it, meta), lagran_dt=meta["cs_count"] * p.dt)
+        if it in meta["record"]:
+            for n in FIELDS:
+                worst[(it, n)] = rel(valid(p, n, core.download(n)), valid(p, n, d[f"{n}_{it}"]))
+            for n in LASD_FIELDS:
+                worst[(it, n)] = rel(core.download(n)[1:p.nz + 1, :, :p.nx], d[f"{n}_{it}"][1:p.nz + 1, :, :p.nx])
+    return worst
+
+
+@pytest.mark.gpu
+def test_cuda_lasd_matches_reference_sources():
+    _, _, p = load("ref_full_lasd_16x16x6")
+    worst = run_core_on_lasd_fixture(lesgo_b200.Core(make_dims(p, device=0)))
+    print({k: f"{v:.1e}" for k, v in worst.items()})
+    for (it, n), v in worst.items():
+        assert v <= (1e-9 if n == "Cs_opt2" else 1e-11), (it, n, v)
+
+
+def test_kernel_logic_lasd_matches_reference_sources():
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    from helpers import emul_library
+    _, _, p = load("ref_full_lasd_16x16x6")
+    worst = run_core_on_lasd_fixture(lesgo_b200.Core(make_dims(p), lib=emul_library()))
+    for (it, n), v in worst.items():
+        assert v <= (1e-9 if n == "Cs_opt2" else 1e-11), (it, n, v)
 
 
 # ---- the CUDA path against the reference-source fixtures --------------------------------------------------------

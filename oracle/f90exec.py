@@ -49,9 +49,10 @@ class FArray:
 
     @staticmethod
     def alloc(shape, lb, kind="real", fill=0.0):
-        dt = {"real": np.float64, "integer": np.int64, "logical": np.bool_, "complex": np.complex128}[kind]
+        dt = {"real": np.float64, "integer": np.int64, "logical": np.bool_, "complex": np.complex128, "object": object}[kind]
         a = np.empty(tuple(shape), dtype=dt, order="F")
-        a[...] = fill if kind in ("real", "complex") else 0
+        if kind != "object":
+            a[...] = fill if kind in ("real", "complex") else 0
         return FArray(a, lb, kind)
 
     def index(self, subs):
@@ -742,7 +743,11 @@ class Interpreter:
     def _block(self, lines, path):
         stmts, i = [], 0
         while i < len(lines):
-            st, i = self._stmt(lines, i, path)
+            try:
+                st, i = self._stmt(lines, i, path)
+            except FortranError as ex:
+                # syntax outside the supported subset: it only matters if control ever reaches the statement
+                st, i = ("unsupported", (path, lines[i][0]), f"{lines[i][1]!r}: {ex}"), i + 1
             if st is not None:
                 stmts.append(st)
         return stmts
@@ -886,7 +891,8 @@ class Interpreter:
             for it in _split_top(m.group(1)):
                 if re.match(r"^(stat|source|mold)\s*=", it):
                     continue
-                p = it.rindex("(") if it.rstrip().endswith(")") else it.index("(")
+                if "(" not in it:
+                    continue                              # deferred-length character etc.: not modelled
                 # the dimension list is the LAST parenthesised group (the target may be a component: this%x(n))
                 depth, p = 0, len(it) - 1
                 for q in range(len(it) - 1, -1, -1):
@@ -906,9 +912,9 @@ class Interpreter:
             return (s.split()[0], loc), i + 1
         if re.match(r"^stop\b", s):
             return ("stop", loc, s), i + 1
-        if re.match(r"^(write|print|flush|format|\d+\s+format)\b", s):
+        if re.match(r"^(write|print|flush|format|\d+\s+format|open|close)\b", s):
             return None, i + 1
-        if re.match(r"^(read|open|close|rewind|inquire|backspace)\b", s):
+        if re.match(r"^(read|rewind|inquire|backspace)\b", s):
             return ("unsupported", loc, s), i + 1
         if "=>" in s and _find_assign(s) < 0:
             lhs, rhs = s.split("=>", 1)
@@ -916,7 +922,7 @@ class Interpreter:
         k = _find_assign(s)
         if k > 0:
             return ("assign", loc, parse_expr(s[:k]), parse_expr(s[k + 1:])), i + 1
-        raise FortranError(f"{path}:{no}: cannot parse statement {s!r}")
+        return ("unsupported", loc, s), i + 1
 
     # ---- module initialisation -------------------------------------------------------------------
     def module(self, name):
@@ -1327,6 +1333,8 @@ class Frame:
             return e[1]
         if t == "name":
             v = self.lookup(e[1])
+            if isinstance(v, PtrRef):
+                v = v.get()
             if isinstance(v, FArray):
                 return v.a
             if v is None:
@@ -1369,6 +1377,12 @@ class Frame:
             return getattr(self.eval_object(e[1]), e[2])
         if e[0] == "paren":
             return self.eval_object(e[1])
+        if e[0] == "call":
+            base = self.eval_object(e[1])
+            if isinstance(base, FArray):
+                idx, scalar = base.index([self.subscript(a) for a in e[2]])
+                v = base.a[idx]
+                return v if scalar else FArray(v, None, base.kind)
         raise FortranError(f"not an object reference: {e!r}")
 
     def binop(self, op, a, b):
@@ -1450,7 +1464,8 @@ class Frame:
         if pr is not None:
             if isinstance(pr, list):
                 pr = self.resolve_generic(pr, args)
-            return self.I.invoke(pr, args, self)
+            r = self.I.invoke(pr, args, self)
+            return r.a if isinstance(r, FArray) else r
         if name in self.I.externals:
             return self.I.externals[name](self, [self.reference(a)[0] if a[0] != "kw" else ("kw", a[1], self.eval(a[2])) for a in args])
         return self.intrinsic(name, args)
@@ -1706,7 +1721,14 @@ class Frame:
                     self.store(name, FArray.alloc(shape, lb, k if k in ("real", "integer", "logical", "complex") else "real", self.I.alloc_fill))
             elif t == "ptrassign":
                 src = st[3]
-                val = self.eval_object(src) if src[0] in ("comp", "name") else self.reference(src)[0]
+                if src[0] == "call" and src[1] == ("name", "null"):
+                    val = None
+                elif src[0] in ("comp", "name"):
+                    val = self.eval_object(src)
+                    if src[0] == "comp" and not isinstance(val, (FArray, FStruct)):
+                        val = PtrRef(self.eval_object(src[1]), src[2])      # pointer to a scalar component
+                else:
+                    val = self.reference(src)[0]
                 if st[2][0] == "name":
                     self.store(st[2][1], val)
                 else:
@@ -1740,6 +1762,9 @@ class Frame:
         val = self.eval(rhs)
         if lhs[0] == "name":
             cur = self.lookup(lhs[1]) if self._find(lhs[1]) is not None else None
+            if isinstance(cur, PtrRef):
+                cur.set(_coerce(val, "real") if isinstance(cur.get(), float) else val)
+                return
             if isinstance(cur, FArray):
                 cur.a[...] = val
                 return
@@ -1791,6 +1816,19 @@ class Frame:
             self.I.externals[name](self, refs)
             return
         raise FortranError(f"call to unknown procedure {name!r}")
+
+
+class PtrRef:
+    """A scalar POINTER associated with a component of a derived-type object: reads and assignments go through."""
+
+    def __init__(self, obj, attr):
+        self.obj, self.attr = obj, attr
+
+    def get(self):
+        return getattr(self.obj, self.attr)
+
+    def set(self, v):
+        setattr(self.obj, self.attr, v)
 
 
 class ElemRef:

@@ -14,8 +14,9 @@ unpinned: `CMakeLists.txt:63-66`, 3.3.6-pl2 / 3.3.8 named at `:112-154`), whose 
 imaginary parts of the kx=0 / kx=nx/2 columns after the y pass) is restated with `scipy.fft.rfft2 /
 irfft2(norm="forward")` and pinned against numbers FFTW produced, Intel MKL and cuFFT (`tests/test_fft_pins.py`).
 lagrange_Sdep / interpolag_Sdep / trilinear_interp_w are pinned the same way (F_* 1e-15, Cs_opt2 1e-13 after two
-updates).  NOT covered by a reference-source run (restatement + analytic known-answer tests only,
-`tests/test_oracle_kat.py`): turbines_forcing, tavg%compute, the restart record.
+updates), and so are turbines_forcing (force fields bit-equal) and tavg%compute (26 accumulators, 1e-15).  NOT covered
+by a reference-source run: the restart record (checked against scipy.io.FortranFile instead) and the start-up routines
+turbines_init / turbines_nodes, whose node lists both sides are handed.
 
 Beyond the core path it restates SURVEY 8(f): wallstress / calc_Sij / sgs_stag / divstress,
 the Lagrangian scale-dependent model (lagrange_Sdep.f90, interpolag_Sdep.f90, trilinear_interp_w),

@@ -79,6 +79,69 @@ def run_lasd_case(name="ref_full_lasd_16x16x6", nsteps=4):
     print(f"{name}: {nsteps} steps, {R.I.nstmt} reference statements, {time.time() - t0:.1f} s")
 
 
+def run_turbine_case(name="ref_turbines_32x32x8", nsteps=2, eps=0.3):
+    """Rows (f)-3 from the reference text: turbines_forcing (turbines.f90:465-638) through forcing_applied
+    (forcing.f90:102-106) and main.f90:263-267 inside two core steps, USE_TURBINES build; two disks (one yawed and
+    tilted), adm_correction on.  The node lists / indicator weights are start-up data handed to both sides."""
+    from helpers import make_farm
+    kw = dict(nx=32, ny=32, Nz=8, lbc_mom=1, ubc_mom=1)
+    p = O.Params(**kw)
+    R = refrun.Reference(p, files=refrun.TURBINE_FILES, turbines=True)
+    farm = make_farm(p)
+    for t in farm:
+        t.M = 0.9
+    R.farm_set(farm, eps, adm_correction=True)
+    u, v, w = initial_fields(p, seed=71)
+    u = u + 1.0
+    out = {"u0": u, "v0": v, "w0": w}
+    for n, a in (("u", u), ("v", v), ("w", w)):
+        R.put(n, a)
+    for it in range(1, nsteps + 1):
+        R.step(it, mode="core")
+    for n in STEP_FIELDS + ("fxa", "fya", "fza"):
+        out[f"{n}_{nsteps}"] = R.get(n)
+    assert np.count_nonzero(out[f"fxa_{nsteps}"]) > 100 and np.count_nonzero(out[f"fza_{nsteps}"]) > 100
+    for n in ("u_d", "u_d_t", "f_n"):
+        out["disk_" + n] = np.array(R.farm_get(n))
+    for i, t in enumerate(farm):
+        out[f"farm{i}_nodes"], out[f"farm{i}_ind"] = np.asarray(t.nodes), np.asarray(t.ind)
+        out[f"farm{i}_scalars"] = np.array([t.Ct_prime, t.dia, t.M, t.u_d_T, *t.nhat])
+    meta = dict(params=params_record(p), mode="core", nsteps=nsteps, eps=eps, ndisks=len(farm), adm_correction=True,
+                made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py", statements=R.I.nstmt)
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: done, {R.I.nstmt} reference statements")
+
+
+def run_tavg_case(name="ref_tavg_16x16x6", nsteps=2):
+    """Rows (f)-4 from the reference text: tavg%compute (time_average.f90:176-320, interp_to_uv_grid / interp_to_w_grid of
+    functions.f90) after each of two full DNS steps, with a seeded Cs_opt2 field and growing averaging intervals."""
+    from helpers import random_field
+    kw = dict(nx=16, ny=16, Nz=6, L_x=4.0, L_y=3.0, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5, sgs=False, molec=True, nu_molec=1e-2)
+    p = O.Params(**kw)
+    R = refrun.Reference(p, files=refrun.TAVG_FILES)
+    u, v, w = initial_fields(p, seed=81)
+    u = u + 1.0
+    cs = 0.01 * np.abs(random_field(p, 82))
+    out = {"u0": u, "v0": v, "w0": w, "cs_opt2_0": cs}
+    for n, a in (("u", u), ("v", v), ("w", w)):
+        R.put(n, a)
+    fa = R.I.get("sgs_param", "cs_opt2")
+    fa.a[...] = cs[1:].transpose(2, 1, 0)
+    t = R.tavg_new()
+    for it in range(1, nsteps + 1):
+        R.step(it, mode="full")
+        R.tavg_compute(t, p.dt * it)
+    for n in O.TAVG_FIELDS:
+        out["tavg_" + n] = getattr(t, n).a.transpose(2, 1, 0).copy()
+    out["total_time"] = np.array(t.total_time)
+    meta = dict(params=params_record(p), mode="full", nsteps=nsteps,
+                made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py", statements=R.I.nstmt)
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: done, {R.I.nstmt} reference statements")
+
+
 def initial_fields(p, seed=41, amp=0.3):
     u, v, w = O.synthetic_global(p.nx, p.ny, p.Nz, nproc=1, seed=seed, amp=amp, L_x=p.L_x, L_y=p.L_y, L_z=p.L_z)
     return tuple(O.scatter_slab(f, p) for f in (u, v, w))
@@ -195,3 +258,7 @@ if __name__ == "__main__":
             run_step_case(name, **c)
     if not only or "lasd" in only:
         run_lasd_case()
+    if not only or "tavg" in only:
+        run_tavg_case()
+    if not only or "turbines" in only:
+        run_turbine_case()

@@ -31,6 +31,14 @@ FILES = ["types.f90", "param.f90", "sim_param.f90", "messages.f90", "emul_comple
 # + the Lagrangian scale-dependent dynamic model (rows (f)-2): grid_m (derived type with pointer components),
 # trilinear_interp_w / cell_indx in functions.f90, lagrange_Sdep.f90, interpolag_Sdep.f90
 LASD_FILES = FILES + ["grid.f90", "functions.f90", "lagrange_Sdep.f90", "interpolag_Sdep.f90"]
+# + the running time averages (rows (f)-4): tavg%compute of time_average.f90 (a derived type with 26 allocatable components)
+TAVG_FILES = LASD_FILES + ["stat_defs.f90", "time_average.f90"]
+# + actuator disks (rows (f)-3): turbines_forcing of turbines.f90 (arrays of derived types, scalar pointers), needs the
+# PPTURBINES build flag (USE_TURBINES, CMakeLists.txt:27) for sim_param's fxa, fya, fza and forcing_applied
+TURBINE_FILES = ["types.f90", "param.f90", "sim_param.f90", "messages.f90", "emul_complex.f90", "fft.f90", "derivatives.f90",
+                 "convec.f90", "tridag_array.f90", "press_stag_array.f90", "cfl_util.f90", "mpi_defs.f90", "sgs_param.f90",
+                 "test_filtermodule.f90", "wallstress.f90", "sgs_stag_util.f90", "divstress_uv.f90", "divstress_w.f90",
+                 "grid.f90", "functions.f90", "turbine_indicator.f90", "stat_defs.f90", "turbines.f90", "forcing.f90"]
 MPI_PROC_NULL = -2
 
 
@@ -41,10 +49,11 @@ def available():
 class Reference:
     """One rank of the reference, interpreted.  Fields are the module arrays of sim_param (Fortran bounds kept)."""
 
-    def __init__(self, p: O.Params, files=FILES, alloc_fill=0.0, dyn_init=100, cs_count=5):
+    def __init__(self, p: O.Params, files=FILES, alloc_fill=0.0, dyn_init=100, cs_count=5, turbines=False):
         assert p.nproc == 1, "one rank (an MPI build run with -np 1)"
         self.p = p
-        I = self.I = F.Interpreter(defines=("PPMPI", "PPSAFETYMODE"), alloc_fill=alloc_fill)
+        self.turbines = turbines
+        I = self.I = F.Interpreter(defines=("PPMPI", "PPSAFETYMODE") + (("PPTURBINES",) if turbines else ()), alloc_fill=alloc_fill)
         for f in files:
             I.load(os.path.join(REF, f))
         self.plans = {}
@@ -108,7 +117,10 @@ class Reference:
                 raise F.FortranError("one rank only: neighbours must be MPI_PROC_NULL")
 
         def allreduce(fr, a):
-            a[1][1](a[0][0])                                         # recvbuf = sendbuf over one rank
+            if isinstance(a[0][0], F.FArray):
+                a[1][0].a[...] = a[0][0].a                           # array buffers (turbines.f90:553-560)
+            else:
+                a[1][1](a[0][0])                                     # recvbuf = sendbuf over one rank
 
         def error(fr, a):
             raise F.FortranError("reference called error(): " + " ".join(str(x[0]) for x in a))
@@ -137,6 +149,60 @@ class Reference:
         k0 = fa.lb[2]
         fa.a[...] = np.asarray(arr)[k0:k0 + fa.a.shape[2]].transpose(2, 1, 0)
 
+    def farm_set(self, farm, eps, adm_correction=False):
+        """wind_farm as turbines_init / turbines_nodes leave it (turbines.f90:129-462 are host start-up work fed from input
+        files; both sides are handed the same node lists): nloc disks with %nodes, %ind, %nhat, %Ct_prime, %dia, %u_d_T,
+        %turb_ind_func%M.  eps enters through T_avg_dim and dt_dim exactly as turbines.f90:563-567 forms it."""
+        I, p = self.I, self.p
+        sd = I.modules["stat_defs"].types
+        wf = I.get("stat_defs", "wind_farm")
+        arr = F.FArray.alloc((len(farm),), (1,), "object")
+        for s_, t in enumerate(farm):
+            o = F.FStruct(sd["turbine_t"])
+            n = len(t.ind)
+            o.num_nodes = n
+            o.nodes = F.FArray(np.asfortranarray(np.asarray(t.nodes, dtype=np.int64).reshape(n, 3)), (1, 1), "integer")
+            o.ind = F.FArray(np.array(t.ind, dtype=np.float64), (1,))
+            o.nhat = F.FArray(np.array(t.nhat, dtype=np.float64), (1,))
+            o.ct_prime, o.dia, o.u_d_t, o.u_d, o.f_n = float(t.Ct_prime), float(t.dia), float(t.u_d_T), 0.0, 0.0
+            o.theta1, o.theta2 = float(getattr(t, "theta1", 0.0)), float(getattr(t, "theta2", 0.0))
+            o.icp = o.jcp = o.kcp = 1
+            o.center_in_proc = False
+            tif = F.FStruct(I.modules["turbine_indicator"].types["turb_ind_func_t"])
+            tif.m = float(getattr(t, "M", 1.0))
+            o.turb_ind_func = tif
+            arr.a[s_] = o
+        wf.turbine = arr
+        T = lambda n, v: I.set("turbines", n, v)
+        T("nloc", len(farm)); T("dyn_theta1", False); T("dyn_theta2", False); T("dyn_ct_prime", False)
+        T("adm_correction", bool(adm_correction)); T("use_rotation", False); T("tbase", 10 ** 9)
+        # eps = (dt_dim / T_avg_dim) / (1 + dt_dim / T_avg_dim)  ->  dt_dim / T_avg_dim = eps / (1 - eps)
+        I.set("param", "dt_dim", float(eps / (1.0 - eps))); T("t_avg_dim", 1.0)
+        I.set("param", "total_time_dim", 0.0); I.set("param", "total_time", 0.0)
+        T("vel_top_dat", "vel_top.dat"); T("forcing_fid", F.FArray.alloc((len(farm),), (1,), "integer"))
+        self.farm_objs = arr
+
+    def farm_get(self, name):
+        return [getattr(o, name) for o in self.farm_objs.a]
+
+    def tavg_new(self):
+        """A tavg_t as tavg%init leaves it (time_average.f90:77-170 minus the file I/O): zeroed accumulators
+        (nx, ny, lbz:nz), total_time = 0, plus the module's work arrays w_uv ... vortz."""
+        p, I = self.p, self.I
+        t = F.FStruct(I.modules["time_average"].types["tavg_t"])
+        mk = lambda: F.FArray.alloc((p.nx, p.ny, p.nz + 1), (1, 1, 0))
+        for n, d in t._type.members.items():
+            if d.dims:
+                setattr(t, n, mk())
+        t.total_time, t.dt, t.initialized = 0.0, 0.0, True
+        for n in ("w_uv", "u_w", "v_w", "vortx", "vorty", "vortz", "pres_real"):
+            I.set("time_average", n, mk())
+        return t
+
+    def tavg_compute(self, t, dt):
+        t.dt = float(dt)                                   # io.f90 output_loop sets tavg%dt before tavg%compute
+        self.I.call("compute", t, module="time_average")
+
     def set_dt(self, dt, tadv1, tadv2):
         self.I.set("param", "dt", float(dt)); self.I.set("param", "tadv1", float(tadv1)); self.I.set("param", "tadv2", float(tadv2))
 
@@ -158,6 +224,9 @@ class Reference:
             I.exec_lines(main, 189, 203, uses)
         I.exec_lines(main, 207, 214, uses)
         I.exec_lines(main, 229, 232, uses)
+        if self.turbines:
+            I.exec_lines(main, 254, 254, uses)                      # call forcing_applied() -> turbines_forcing
+            I.exec_lines(main, 263, 267, uses)                      # RHS += fxa, fya, fza
         I.exec_lines(main, 273, 326, uses)
         I.exec_lines(main, 344, 344, uses)
 

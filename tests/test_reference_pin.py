@@ -23,7 +23,7 @@ from helpers import O, make_dims, rel, step_kwargs_pre_dyn
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STEP_FIXTURES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "ref_*.npz"))
-                       if "routines" not in f and "lasd" not in f)
+                       if "routines" not in f and "lasd" not in f and "tavg" not in f and "turbines" not in f)
 LASD_FIELDS = ("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2")
 FIELDS = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")
 
@@ -216,6 +216,132 @@ def test_kernel_logic_lasd_matches_reference_sources():
     worst = run_core_on_lasd_fixture(lesgo_b200.Core(make_dims(p), lib=emul_library()))
     for (it, n), v in worst.items():
         assert v <= (1e-9 if n == "Cs_opt2" else 1e-11), (it, n, v)
+
+
+def test_oracle_tavg_matches_reference_sources():
+    """tavg%compute (time_average.f90:176-320) as the reference wrote it vs the oracle's restatement: 26 accumulators."""
+    d, meta, p = load("ref_tavg_16x16x6")
+    sp = O.Spectral(p)
+    G = O.test_filter_kernel(sp)
+    s = O.State(p)
+    O.lasd_alloc(s)
+    s.u, s.v, s.w = d["u0"].copy(), d["v0"].copy(), d["w0"].copy()
+    s.Cs_opt2[...] = d["cs_opt2_0"]
+    t = O.Tavg(p)
+    for it in range(1, meta["nsteps"] + 1):
+        O.step(s, sp, O.LocalComm(), mode="full", first_step=(it == 1), G_test=G)
+        O.tavg_compute(t, s, p, O.LocalComm(), p.dt * it, forces=False)
+    assert abs(t.total_time - float(d["total_time"])) <= 1e-18
+    for n in O.TAVG_FIELDS:
+        ref, got = d["tavg_" + n][1:p.nz], getattr(t, n)[1:p.nz]
+        v = rel(got, ref) if np.any(ref) else float(np.abs(got).max())
+        assert v <= 1e-13, (n, v)
+        assert n in ("fx", "fy", "fz") or np.any(ref), n
+
+
+def run_core_on_tavg_fixture(core):
+    from helpers import step_kwargs
+    d, meta, p = load("ref_tavg_16x16x6")
+    for n in ("u", "v", "w"):
+        core.upload(n, d[n + "0"])
+    core.upload("Cs_opt2", d["cs_opt2_0"])
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+        core.upload(n, np.zeros(core.dims.shape))
+    for it in range(1, meta["nsteps"] + 1):
+        core.step(**step_kwargs(p, it - 1, "full"))
+        core.tavg_compute(p.dt * it)
+    worst = {}
+    for n in O.TAVG_FIELDS:
+        g, tt = core.tavg_download(n)
+        ref = d["tavg_" + n][1:p.nz]
+        worst[n] = rel(g[1:p.nz], ref) if np.any(ref) else float(np.abs(g[1:p.nz]).max())
+        assert abs(tt - float(d["total_time"])) <= 1e-15
+    return worst
+
+
+@pytest.mark.gpu
+def test_cuda_tavg_matches_reference_sources():
+    _, _, p = load("ref_tavg_16x16x6")
+    worst = run_core_on_tavg_fixture(lesgo_b200.Core(make_dims(p, device=0)))
+    print({k: f"{v:.1e}" for k, v in worst.items()})
+    assert max(worst.values()) <= 1e-12, worst
+
+
+def test_kernel_logic_tavg_matches_reference_sources():
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    from helpers import emul_library
+    _, _, p = load("ref_tavg_16x16x6")
+    worst = run_core_on_tavg_fixture(lesgo_b200.Core(make_dims(p), lib=emul_library()))
+    assert max(worst.values()) <= 1e-12, worst
+
+
+def farm_from_fixture(d, meta):
+    farm = []
+    for i in range(meta["ndisks"]):
+        ct, dia, M, udt, n1, n2, n3 = d[f"farm{i}_scalars"]
+        t = O.Turbine(xloc=0.0, yloc=0.0, height=0.0, dia=float(dia), thk=0.0, Ct_prime=float(ct), u_d_T=float(udt))
+        t.nodes, t.ind, t.nhat, t.M = d[f"farm{i}_nodes"].copy(), d[f"farm{i}_ind"].copy(), (float(n1), float(n2), float(n3)), float(M)
+        farm.append(t)
+    return farm
+
+
+def test_oracle_turbines_match_reference_sources():
+    """turbines_forcing (turbines.f90:465-638) + forcing_applied + main.f90:263-267 as the reference wrote them vs the
+    oracle: force fields bit for bit, disk velocities and thrust, two core steps."""
+    d, meta, p = load("ref_turbines_32x32x8")
+    sp = O.Spectral(p)
+    s = O.State(p)
+    s.u, s.v, s.w = d["u0"].copy(), d["v0"].copy(), d["w0"].copy()
+    farm = farm_from_fixture(d, meta)
+    n = meta["nsteps"]
+    for it in range(1, n + 1):
+        O.step(s, sp, O.LocalComm(), mode="core", first_step=(it == 1),
+               turbines=dict(farm=farm, eps=meta["eps"], adm_correction=meta["adm_correction"]))
+    for name in ("fxa", "fya", "fza"):
+        ref = d[f"{name}_{n}"]
+        assert np.count_nonzero(ref[1:p.nz, :, :p.nx]) > 100
+        assert np.array_equal(getattr(s, name)[1:p.nz, :, :p.nx], ref[1:p.nz, :, :p.nx]), name
+    assert rel([t.u_d_T for t in farm], d["disk_u_d_t"]) <= 1e-15 and rel([t.f_n for t in farm], d["disk_f_n"]) <= 1e-15
+    for name in FIELDS:
+        assert rel(valid(p, name, getattr(s, name)), valid(p, name, d[f"{name}_{n}"])) <= 1e-13, name
+
+
+def run_core_on_turbine_fixture(core):
+    d, meta, p = load("ref_turbines_32x32x8")
+    for n in ("u", "v", "w"):
+        core.upload(n, d[n + "0"])
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+        core.upload(n, np.zeros(core.dims.shape))
+    core.turbines_init(farm_from_fixture(d, meta), adm_correction=meta["adm_correction"])
+    n = meta["nsteps"]
+    for it in range(1, n + 1):
+        core.step(**step_kwargs_pre_dyn(p, it - 1, "core"), turbines=True, turbines_eps=meta["eps"])
+    worst = {}
+    for name in FIELDS:
+        worst[name] = rel(valid(p, name, core.download(name)), valid(p, name, d[f"{name}_{n}"]))
+    for name in ("fxa", "fya", "fza"):
+        worst[name] = rel(core.download(name)[1:p.nz, :, :p.nx], d[f"{name}_{n}"][1:p.nz, :, :p.nx])
+    return worst
+
+
+@pytest.mark.gpu
+def test_cuda_turbines_match_reference_sources():
+    _, _, p = load("ref_turbines_32x32x8")
+    worst = run_core_on_turbine_fixture(lesgo_b200.Core(make_dims(p, device=0)))
+    print({k: f"{v:.1e}" for k, v in worst.items()})
+    assert max(worst.values()) <= 1e-12, worst
+
+
+def test_kernel_logic_turbines_match_reference_sources():
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    from helpers import emul_library
+    _, _, p = load("ref_turbines_32x32x8")
+    worst = run_core_on_turbine_fixture(lesgo_b200.Core(make_dims(p), lib=emul_library()))
+    assert max(worst.values()) <= 1e-12, worst
 
 
 # ---- the CUDA path against the reference-source fixtures --------------------------------------------------------

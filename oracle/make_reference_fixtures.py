@@ -113,6 +113,41 @@ def run_turbine_case(name="ref_turbines_32x32x8", nsteps=2, eps=0.3):
     print(f"{name}: done, {R.I.nstmt} reference statements")
 
 
+def run_mpi_case(name="ref_mpi4_full_16x16x8", nproc=4, nsteps=2, seed=51):
+    """The reference's MPI code path from the reference text: FOUR ranks (one interpreter per rank, in-process
+    mailboxes for mpi_sendrecv / send / recv / allreduce): mpi_sync_real_array halos (mpi_defs.f90:167-264), the
+    rank-pipelined tridag_array (tridag_array.f90:22-162), press_stag_array's exchanges and k = 0 chain (:175-246), the tzz
+    halo of main.f90:193-197, cfl all-reduce -- two full steps (DNS walls + molecular stress), gathered to global fields."""
+    kw = dict(nx=16, ny=16, Nz=8, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5, L_x=4.0, L_y=3.0, use_mean_p_force=True,
+              mean_p_force_x=1.0, sgs=False, molec=True, nu_molec=1e-2)
+    pg = O.Params(nproc=1, **kw)
+    ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=seed, amp=0.3, L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+
+    def fn(ref, r):
+        for n, g in (("u", ug), ("v", vg), ("w", wg)):
+            ref.put(n, O.scatter_slab(g, ref.p))
+        for it in range(1, nsteps + 1):
+            ref.step(it, mode="full")
+        o = {n: ref.get(n) for n in STEP_FIELDS}
+        o["cfl"] = ref.I.call("get_max_cfl", module="cfl_util")
+        o["nstmt"] = ref.I.nstmt
+        return o
+
+    res = refrun.run_ranks(kw, nproc, fn)
+    ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
+    out = {}
+    for n in STEP_FIELDS:
+        out[n] = O.gather_slabs([res[r][n] for r in range(nproc)], ps, top_extra=n in ("w", "RHSz", "p"))
+    out["max_cfl"] = np.array(res[0]["cfl"])
+    assert all(res[r]["cfl"] == res[0]["cfl"] for r in range(nproc))
+    meta = dict(kw=kw, nproc=nproc, nsteps=nsteps, seed=seed, amp=0.3, mode="full",
+                made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py, 4 ranks",
+                statements=int(sum(res[r]["nstmt"] for r in range(nproc))))
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: done, {meta['statements']} reference statements on {nproc} ranks")
+
+
 def run_tavg_case(name="ref_tavg_16x16x6", nsteps=2):
     """Rows (f)-4 from the reference text: tavg%compute (time_average.f90:176-320, interp_to_uv_grid / interp_to_w_grid of
     functions.f90) after each of two full DNS steps, with a seeded Cs_opt2 field and growing averaging intervals."""
@@ -262,3 +297,5 @@ if __name__ == "__main__":
         run_tavg_case()
     if not only or "turbines" in only:
         run_turbine_case()
+    if not only or "mpi" in only:
+        run_mpi_case()

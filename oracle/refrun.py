@@ -49,9 +49,11 @@ def available():
 class Reference:
     """One rank of the reference, interpreted.  Fields are the module arrays of sim_param (Fortran bounds kept)."""
 
-    def __init__(self, p: O.Params, files=FILES, alloc_fill=0.0, dyn_init=100, cs_count=5, turbines=False):
-        assert p.nproc == 1, "one rank (an MPI build run with -np 1)"
+    def __init__(self, p: O.Params, files=FILES, alloc_fill=0.0, dyn_init=100, cs_count=5, turbines=False, boxes=None):
+        """boxes: shared mailbox dict of a multi-rank run (run_ranks below); None = one rank."""
+        assert p.nproc == 1 or boxes is not None, "several ranks need the shared mailboxes of run_ranks()"
         self.p = p
+        self.boxes = boxes
         self.turbines = turbines
         I = self.I = F.Interpreter(defines=("PPMPI", "PPSAFETYMODE") + (("PPTURBINES",) if turbines else ()), alloc_fill=alloc_fill)
         for f in files:
@@ -60,7 +62,7 @@ class Reference:
         self._externals()
         S = lambda n, v: I.set("param", n, v)
         # input_util.f90:197-235 (derived sizes) and the lesgo.conf blocks this path reads
-        S("nproc", 1); S("coord", 0); S("rank", 0)
+        S("nproc", p.nproc); S("coord", p.coord); S("rank", p.coord)
         S("nx", p.nx); S("ny", p.ny); S("nz", p.nz); S("nz_tot", p.nz_tot)
         S("nx2", p.nx2); S("ny2", p.ny2); S("lh", p.lh); S("ld", p.ld); S("lh_big", p.lh_big); S("ld_big", p.ld_big)
         S("l_x", p.L_x); S("l_y", p.L_y); S("l_z", p.L_z); S("z_i", p.z_i)
@@ -71,7 +73,9 @@ class Reference:
         S("wall_damp_exp", p.wall_damp_exp); S("vonk", p.vonk); S("zo", p.zo); S("ifilter", p.ifilter)
         S("ubot", p.ubot); S("utop", p.utop)
         S("use_mean_p_force", bool(p.use_mean_p_force)); S("mean_p_force_x", p.mean_p_force_x); S("mean_p_force_y", p.mean_p_force_y)
-        S("up", MPI_PROC_NULL); S("down", MPI_PROC_NULL); S("comm", 0); S("ierr", 0); S("mpi_rprec", 0)
+        # mpi_defs.f90:77-87: 1-D chain, MPI_PROC_NULL beyond the ends
+        S("up", p.coord + 1 if p.coord + 1 < p.nproc else MPI_PROC_NULL)
+        S("down", p.coord - 1 if p.coord > 0 else MPI_PROC_NULL); S("comm", 0); S("ierr", 0); S("mpi_rprec", 0)
         S("status", F.FArray.alloc((8,), (1,), "integer"))
         S("initu", False); S("jt_total", 0); S("jt", 0); S("use_cfl_dt", False); S("cfl", 0.0625)
         S("inilag", True); S("dyn_init", int(dyn_init)); S("cs_count", int(cs_count))
@@ -107,20 +111,61 @@ class Reference:
                 dst.a.T[...] = y
             return f
 
-        def sendrecv(fr, a):
-            dest, src = int(a[3][0]), int(a[8][0])
-            if dest != MPI_PROC_NULL or src != MPI_PROC_NULL:
-                raise F.FortranError("one rank only: neighbours must be MPI_PROC_NULL")
+        me, nproc, boxes = self.p.coord, self.p.nproc, self.boxes
 
-        def send_or_recv(fr, a):
-            if int(a[3][0]) != MPI_PROC_NULL:
-                raise F.FortranError("one rank only: neighbours must be MPI_PROC_NULL")
+        def flat(x, count):
+            """the `count` storage units an MPI buffer argument designates: a section (view) or the sequence that starts
+            at an array element (sequence association, e.g. rH_x(1, 1, nz-1))"""
+            if isinstance(x, F.ElemRef):
+                f_ = x.base.a.reshape(-1, order="F")
+                assert np.shares_memory(f_, x.base.a)
+                start = int(np.ravel_multi_index(x.idx, x.base.a.shape, order="F"))
+                return f_[start:start + count]
+            f_ = x.a.reshape(-1, order="F")
+            assert np.shares_memory(f_, x.a), "MPI buffer must be contiguous"
+            return f_[:count]
+
+        def box(src, dst, tag):
+            import queue
+            with boxes["lock"]:
+                return boxes.setdefault((src, dst, tag), queue.Queue())
+
+        def valid(r):
+            return r != MPI_PROC_NULL and 0 <= r < nproc
+
+        def send_to(buf, count, dest, tag):
+            if valid(dest):
+                box(me, dest, tag).put(np.array(flat(buf, count), copy=True))
+
+        def recv_from(buf, count, src, tag):
+            if valid(src):
+                flat(buf, count)[...] = box(src, me, tag).get(timeout=600)
+
+        def sendrecv(fr, a):
+            send_to(a[0][0], int(a[1][0]), int(a[3][0]), int(a[4][0]))
+            recv_from(a[5][0], int(a[6][0]), int(a[8][0]), int(a[9][0]))
+
+        def send(fr, a):
+            send_to(a[0][0], int(a[1][0]), int(a[3][0]), int(a[4][0]))
+
+        def recv(fr, a):
+            recv_from(a[0][0], int(a[1][0]), int(a[3][0]), int(a[4][0]))
 
         def allreduce(fr, a):
-            if isinstance(a[0][0], F.FArray):
-                a[1][0].a[...] = a[0][0].a                           # array buffers (turbines.f90:553-560)
+            op = a[4][0][1] if isinstance(a[4][0], tuple) else "mpi_sum"
+            mine = np.array(a[0][0].a, copy=True) if isinstance(a[0][0], F.FArray) else np.array(a[0][0])
+            acc = None
+            for r in range(nproc):
+                if r != me:
+                    box(me, r, ("ar", op)).put(mine)
+            for r in range(nproc):                                # rank order: every rank forms the same result
+                x = mine if r == me else box(r, me, ("ar", op)).get(timeout=600)
+                acc = x if acc is None else (np.maximum(acc, x) if op == "mpi_max" else
+                                             (np.minimum(acc, x) if op == "mpi_min" else acc + x))
+            if isinstance(a[1][0], F.FArray):
+                a[1][0].a[...] = acc
             else:
-                a[1][1](a[0][0])                                     # recvbuf = sendbuf over one rank
+                a[1][1](float(acc))
 
         def error(fr, a):
             raise F.FortranError("reference called error(): " + " ".join(str(x[0]) for x in a))
@@ -128,7 +173,7 @@ class Reference:
         I.externals.update({
             "dfftw_plan_dft_r2c_2d": plan("r2c"), "dfftw_plan_dft_c2r_2d": plan("c2r"),
             "dfftw_execute_dft_r2c": execute("r2c"), "dfftw_execute_dft_c2r": execute("c2r"),
-            "mpi_sendrecv": sendrecv, "mpi_send": send_or_recv, "mpi_recv": send_or_recv, "mpi_allreduce": allreduce,
+            "mpi_sendrecv": sendrecv, "mpi_send": send, "mpi_recv": recv, "mpi_allreduce": allreduce,
             "error": error, "apply_inflow": lambda fr, a: None, "mpi_barrier": lambda fr, a: None,
         })
 
@@ -235,3 +280,27 @@ class Reference:
         main = os.path.join(REF, "main.f90")
         self.I.set("param", "use_cfl_dt", True)
         self.I.exec_lines(main, 135, 144, ["types", "param", "sim_param", "cfl_util"], local={"dt_dim": 0.0})
+
+
+def run_ranks(kw, nproc, fn, **ref_kw):
+    """The reference on `nproc` ranks: one interpreter per rank, each in its own thread, MPI calls carried by in-process
+    mailboxes (blocking, tag-matched, like the MPI the reference uses).  fn(ref, coord) runs on every rank; returns the
+    list of its results in rank order."""
+    import threading
+    boxes = {"lock": threading.Lock()}
+    res, err = [None] * nproc, [None] * nproc
+
+    def work(r):
+        try:
+            ref = Reference(O.Params(nproc=nproc, coord=r, **kw), boxes=boxes, **ref_kw)
+            res[r] = fn(ref, r)
+        except BaseException as e:  # noqa
+            err[r] = e
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(nproc)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for e in err:
+        if e is not None:
+            raise e
+    return res

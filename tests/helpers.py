@@ -321,7 +321,7 @@ def farm_for_rank(farm, p):
 
 
 def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core", lasd=False,
-                          turbines=False, tavg=False, p2p=False, local=False):
+                          turbines=False, tavg=False, p2p=False, local=False, ref_global=None):
     """nproc ranks (threads of this process, one Core each) advance `nsteps` core steps;
     the gathered result must match the SINGLE-slab oracle (which the multi-slab oracle
     equals, tests/test_oracle_kat.py)."""
@@ -410,6 +410,8 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
         g = O.gather_slabs([res[r][n] for r in range(nproc)], ps, top_extra=top)
         hi = nzt if top else nzt - 1
         out[n] = rel(g[1:hi + 1, :, :pg.nx], getattr(sref, n)[1:hi + 1, :, :pg.nx])
+        if ref_global is not None:         # ... and against fields the reference's own MPI code path produced
+            out["ref_" + n] = rel(g[1:hi + 1, :, :pg.nx], ref_global[n][1:hi + 1, :, :pg.nx])
     if tavg:
         # the accumulators whose interpolations cross the slab seams
         for n in TAVG_SEAM:

@@ -23,7 +23,7 @@ from helpers import O, make_dims, rel, step_kwargs_pre_dyn
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STEP_FIXTURES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "ref_*.npz"))
-                       if "routines" not in f and "lasd" not in f and "tavg" not in f and "turbines" not in f)
+                       if not any(t in f for t in ("routines", "lasd", "tavg", "turbines", "mpi")))
 LASD_FIELDS = ("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2")
 FIELDS = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")
 
@@ -41,7 +41,8 @@ def valid(p, n, a):
 
 def test_fixtures_exist():
     assert len(STEP_FIXTURES) >= 5 and os.path.exists(os.path.join(GOLD, "ref_routines_16x16x6.npz"))
-    assert os.path.exists(os.path.join(GOLD, "ref_full_lasd_16x16x6.npz"))
+    for f in ("ref_full_lasd_16x16x6", "ref_tavg_16x16x6", "ref_turbines_32x32x8", "ref_mpi4_full_16x16x8"):
+        assert os.path.exists(os.path.join(GOLD, f + ".npz")), f
 
 
 @pytest.mark.parametrize("name", STEP_FIXTURES)
@@ -342,6 +343,68 @@ def test_kernel_logic_turbines_match_reference_sources():
     _, _, p = load("ref_turbines_32x32x8")
     worst = run_core_on_turbine_fixture(lesgo_b200.Core(make_dims(p), lib=emul_library()))
     assert max(worst.values()) <= 1e-12, worst
+
+
+def load_mpi():
+    d = np.load(os.path.join(GOLD, "ref_mpi4_full_16x16x8.npz"))
+    return d, ast.literal_eval(str(d["meta"]))
+
+
+def test_oracle_matches_reference_mpi_run():
+    """The reference's MPI code path (four interpreted ranks: halos, rank-pipelined tridag_array, k = 0 chain, tzz halo)
+    vs the oracle on ONE slab and on four emulated slabs."""
+    d, meta = load_mpi()
+    kw, nproc, nsteps = meta["kw"], meta["nproc"], meta["nsteps"]
+    pg = O.Params(nproc=1, **kw)
+    ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=meta["seed"], amp=meta["amp"], L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+
+    def run(p, comm):
+        sp = O.Spectral(p)
+        s = O.State(p)
+        s.u, s.v, s.w = (O.scatter_slab(f, p) for f in (ug, vg, wg))
+        for it in range(nsteps):
+            O.step(s, sp, comm, mode=meta["mode"], first_step=(it == 0), G_test=O.test_filter_kernel(sp))
+        return s
+
+    one = run(pg, O.LocalComm())
+    ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
+    many = O.run_ranks(nproc, lambda coord, comm: run(ps[coord], comm))
+    for n in FIELDS:
+        top = n in ("w", "RHSz", "p")
+        hi = pg.nz_tot if top else pg.nz_tot - 1
+        ref = d[n][1:hi + 1, :, :pg.nx]
+        assert rel(getattr(one, n)[1:hi + 1, :, :pg.nx], ref) <= 1e-13, n
+        g = O.gather_slabs([getattr(many[r], n) for r in range(nproc)], ps, top_extra=top)
+        assert rel(g[1:hi + 1, :, :pg.nx], ref) <= 1e-13, n
+    assert abs(O.get_max_cfl(one, pg, O.LocalComm()) - float(d["max_cfl"])) <= 1e-14 * float(d["max_cfl"])
+
+
+def _slabs_vs_reference_mpi(lib, local, device_of=None, p2p=False):
+    from helpers import check_multirank_steps
+    d, meta = load_mpi()
+    out = check_multirank_steps(lib, meta["kw"], meta["nproc"], nsteps=meta["nsteps"], tol=1e-12, seed=meta["seed"],
+                                mode=meta["mode"], local=local, device_of=device_of, p2p=p2p,
+                                ref_global={n: d[n] for n in FIELDS})
+    assert all(("ref_" + n) in out for n in FIELDS)
+    return out
+
+
+def test_kernel_logic_slabs_match_reference_mpi_run():
+    """Four z-slab ranks of the product kernels (emulator, in-process comm) vs the reference's own four-rank MPI run."""
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    from helpers import emul_library
+    print(_slabs_vs_reference_mpi(emul_library(), local=False))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p2p", [False, True])
+def test_cuda_slabs_match_reference_mpi_run(p2p):
+    """Four z-slab ranks on one B200 (single-device transport; transposes NCCL-style and over peer memory) vs the
+    reference's own four-rank MPI run: halos (mpi_defs.f90:245-262), the slab <-> pencil transposes that replace the
+    pipelined tridag_array.f90:85-157, the k = 0 chain (press_stag_array.f90:221-244)."""
+    print(_slabs_vs_reference_mpi(lesgo_b200.load_library(), local=True, device_of=lambda coord: 0, p2p=p2p))
 
 
 # ---- the CUDA path against the reference-source fixtures --------------------------------------------------------

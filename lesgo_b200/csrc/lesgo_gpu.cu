@@ -935,7 +935,10 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
             const int nm = (c->lh - 1) * g.cy;
             ProfScope ps_(c, "tridag");
             // the sweep is local and in place on both paths
-            LG_LAUNCH(k_tridag_pencil, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, pencil);
+            // LESGO_PENCIL_PIPE=0: the sweep without the one-batch-ahead operand prefetch
+            static const bool pipe = !(std::getenv("LESGO_PENCIL_PIPE") && std::getenv("LESGO_PENCIL_PIPE")[0] == '0');
+            if (pipe) LG_LAUNCH(k_tridag_pencil<true>, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, pencil);
+            else LG_LAUNCH(k_tridag_pencil<false>, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, pencil);
             c->launches++;
         }
         if (c->p2p_on) { if (barrier()) return 1; }

@@ -654,6 +654,7 @@ static __global__ void k_tridag_setup_pencil(PencilGeom g, int nzt, double* __re
 // recv layout: buf[src r][block row i][jy_local][ld]; solved in place.  The matrix is real, so the
 // real and imaginary parts of a mode are independent systems: one thread each (same arithmetic,
 // twice the parallelism for the short pencils of a many-rank run).
+template <bool PIPE>
 static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __restrict__ gam, double* __restrict__ buf) {
     const int nm = (g.lh - 1) * g.cy;
     const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -697,44 +698,71 @@ static __global__ void k_tridag_pencil(PencilGeom g, int nzt, const double* __re
     double bet = -1.0;
     // The recurrence is serial in j but its operands are not: fetch UN rows ahead so the sweep pays one
     // memory latency per UN rows instead of one per row (a many-rank run has too few modes per GPU to
-    // hide it with other threads).  Same arithmetic, same order.
+    // hide it with other threads).  PIPE: the operands of batch i+1 are requested BEFORE batch i is
+    // processed (two register sets), so that latency also overlaps the division chain of the batch in hand.
+    // Same arithmetic, same order.
     constexpr int UN = 8;
-    for (int j0 = 2; j0 <= n; j0 += UN) {
-        double* pj[UN];
-        double r[UN], gm[UN];
+    double* pj[2][UN];
+    double r[2][UN], gm[2][UN];
+    auto ldf = [&](const int s, int j0) {
 #pragma unroll
         for (int q = 0; q < UN; ++q) {
             const int j = j0 + q;
-            if (j <= n) { pj[q] = at(j); r[q] = *pj[q]; gm[q] = gam[(long(j) * g.cy + jl) * g.lh + jx]; }
+            if (j <= n) { pj[s][q] = at(j); r[s][q] = *pj[s][q]; gm[s][q] = gam[(long(j) * g.cy + jl) * g.lh + jx]; }
         }
+    };
+    auto cpf = [&](const int s, int j0) {
 #pragma unroll
         for (int q = 0; q < UN; ++q) {
             const int j = j0 + q;
             if (j <= n) {
                 const double a = (j == n) ? -1.0 : c3;
                 const double b = (j == n) ? 1.0 : bb;
-                bet = dsub(b, dmul(a, gm[q]));
-                u = ddiv(dsub(r[q], dmul(a, u)), bet);
-                *pj[q] = u;
+                bet = dsub(b, dmul(a, gm[s][q]));
+                u = ddiv(dsub(r[s][q], dmul(a, u)), bet);
+                *pj[s][q] = u;
             }
         }
+    };
+    if (PIPE) {
+        ldf(0, 2);
+        for (int j0 = 2; j0 <= n; j0 += 2 * UN) {
+            ldf(1, j0 + UN);
+            cpf(0, j0);
+            ldf(0, j0 + 2 * UN);
+            cpf(1, j0 + UN);
+        }
+    } else {
+        for (int j0 = 2; j0 <= n; j0 += UN) { ldf(0, j0); cpf(0, j0); }
     }
-    for (int j0 = n - 1; j0 >= 1; j0 -= UN) {
-        double* pj[UN];
-        double r[UN], gm[UN];
+    auto ldb = [&](const int s, int j0) {
 #pragma unroll
         for (int q = 0; q < UN; ++q) {
             const int j = j0 - q;
-            if (j >= 1) { pj[q] = at(j); r[q] = *pj[q]; gm[q] = gam[(long(j + 1) * g.cy + jl) * g.lh + jx]; }
+            if (j >= 1) { pj[s][q] = at(j); r[s][q] = *pj[s][q]; gm[s][q] = gam[(long(j + 1) * g.cy + jl) * g.lh + jx]; }
         }
+    };
+    auto cpb = [&](const int s, int j0) {
 #pragma unroll
         for (int q = 0; q < UN; ++q) {
             const int j = j0 - q;
             if (j >= 1) {
-                u = dsub(r[q], dmul(gm[q], u));
-                *pj[q] = u;
+                u = dsub(r[s][q], dmul(gm[s][q], u));
+                *pj[s][q] = u;
             }
         }
+    };
+    if (PIPE) {
+        // the first backward batch re-reads rows the forward sweep has just written: same thread, program order
+        ldb(0, n - 1);
+        for (int j0 = n - 1; j0 >= 1; j0 -= 2 * UN) {
+            ldb(1, j0 - UN);
+            cpb(0, j0);
+            ldb(0, j0 - 2 * UN);
+            cpb(1, j0 - UN);
+        }
+    } else {
+        for (int j0 = n - 1; j0 >= 1; j0 -= UN) { ldb(0, j0); cpb(0, j0); }
     }
 }
 

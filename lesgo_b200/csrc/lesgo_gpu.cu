@@ -935,8 +935,11 @@ int press(lesgo_gpu_ctx* c, const double* u, const double* v, const double* w, c
             const int nm = (c->lh - 1) * g.cy;
             ProfScope ps_(c, "tridag");
             // the sweep is local and in place on both paths
-            // LESGO_PENCIL_PIPE=0: the sweep without the one-batch-ahead operand prefetch
-            static const bool pipe = !(std::getenv("LESGO_PENCIL_PIPE") && std::getenv("LESGO_PENCIL_PIPE")[0] == '0');
+            // LESGO_PENCIL_PIPE=1: request the operands of the next batch of rows before processing the one in hand.
+            // Measured SLOWER on 8 B200s (0.318 against 0.240 ms): the sweep is bound by its dependent instruction
+            // chain (address arithmetic + an FP64 division per row) on ~7 warps per SM, not by the loads, and the
+            // second register set only lengthens it (profiles/r4_experiments.md).  Off by default.
+            static const bool pipe = std::getenv("LESGO_PENCIL_PIPE") && std::getenv("LESGO_PENCIL_PIPE")[0] == '1';
             if (pipe) LG_LAUNCH(k_tridag_pencil<true>, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, pencil);
             else LG_LAUNCH(k_tridag_pencil<false>, dim3((2 * nm + 127) / 128), dim3(128), 0, c->stream, g, c->nzt, c->gam, pencil);
             c->launches++;

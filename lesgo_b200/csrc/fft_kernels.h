@@ -16,6 +16,7 @@
 // consumer on this path zeroes it, so the y pass works on nx/2 columns and writes 0
 // there.  Transforms are unnormalised like FFTW's.
 #pragma once
+#include <type_traits>
 #include "fft_core.h"
 
 namespace lg {
@@ -60,6 +61,11 @@ template <int NX> struct XCfg {
     static constexpr size_t smem = size_t(NF * SL + TWL + NWH) * sizeof(cplx);
 };
 
+// A prologue may split load() into row() (per-row case analysis) and load_row() (straight-line element reads)
+struct NoRow {};
+template <class Pro, class = void> struct ProRow { typedef NoRow type; static constexpr bool value = false; };
+template <class Pro> struct ProRow<Pro, std::void_t<typename Pro::Row>> { typedef typename Pro::Row type; static constexpr bool value = true; };
+
 // one work item (tile of NF rows of one field) of the x-forward pass; every thread of the
 // NTHR-thread block calls it; ends with a barrier
 template <int NX, class Pro>
@@ -72,22 +78,31 @@ LG_D void xfwd_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y
         // 32-bit index arithmetic throughout: a 64-bit division costs ~100 instructions per thread
         const int fld = int(work % unsigned(nfields));
         const unsigned row0 = (work / unsigned(nfields)) * NF;
+        __shared__ typename ProRow<Pro>::type s_row[NF];
         for (int f = threadIdx.x; f < NF; f += NTHR) {
             const unsigned r = row0 + f;
             const int k = r < nrows ? k0 + int(r / unsigned(ny)) : -1, y = int(r % unsigned(ny));
             s_k[f] = k;
             s_y[f] = y;
             s_p[f] = out.dst[fld] + poff(k < 0 ? 0 : k, out.plane, out.ring) + long(y) * out.row;   // output row
+            if constexpr (ProRow<Pro>::value) s_row[f] = pro.row(fld, k, y);
         }
         __syncthreads();
-        fft_tile<M, false, NF, false, NTHR, false, true, 1>(buf, W,
-            [](int f) { return f * SL; },
-            [&](int f, int i) {
-                const int k = s_k[f];
-                if (k < 0) return make_double2(0.0, 0.0);
-                return pro.load(fld, k, s_y[f], i);
-            },
-            [&](int f, int i, cplx v) { buf[f * SL + spad(i)] = v; });
+        if constexpr (ProRow<Pro>::value) {
+            fft_tile<M, false, NF, false, NTHR, false, true, 1>(buf, W,
+                [](int f) { return f * SL; },
+                [&](int f, int i) { return pro.load_row(s_row[f], i); },
+                [&](int f, int i, cplx v) { buf[f * SL + spad(i)] = v; });
+        } else {
+            fft_tile<M, false, NF, false, NTHR, false, true, 1>(buf, W,
+                [](int f) { return f * SL; },
+                [&](int f, int i) {
+                    const int k = s_k[f];
+                    if (k < 0) return make_double2(0.0, 0.0);
+                    return pro.load(fld, k, s_y[f], i);
+                },
+                [&](int f, int i, cplx v) { buf[f * SL + spad(i)] = v; });
+        }
 
         // untangle: X_k = E_k + W_N^k O_k,  X_{M-k} = conj(E_k - W_N^k O_k), pairs (m, M-m)
         constexpr int NP = M / 2 - 1;                       // pairs with 0 < m < M/2
@@ -307,6 +322,7 @@ struct YArgs {
     long src_plane, dst_plane;
     int src_row, dst_row;   // doubles
     int ncols;           // kx columns to transform
+    int ncols2;          // > 0: Y_TABLE2 outputs only for column tiles that start below it (table2 is zero beyond)
     int k0, nplanes, nfields;
     double kxs, kys;     // 2 pi / L_x, 2 pi / L_y
     const double* table; // Y_TABLE multiplier, [ns][table_row] reals
@@ -536,6 +552,7 @@ LG_D void ypass_work(cplx* buf, cplx* S, const cplx* Win, const cplx* Wout, cons
             for (int o = 0; o < a.nout; ++o) {
                 const int mode = F.out[o].mode;
                 if (mode == Y_IKX && o_copy >= 0) continue;          // written by the COPY transform
+                if (mode == Y_TABLE2 && a.ncols2 > 0 && c0 >= a.ncols2) continue;   // nobody reads those columns
                 double* dst = F.out[o].dst + poff(k, a.dst_plane, a.dst_ring) + 2 * c0;
                 double* dst_x = (mode == Y_COPY && o_ikx >= 0) ? F.out[o_ikx].dst + poff(k, a.dst_plane, a.dst_ring) + 2 * c0 : nullptr;
                 fft_tile_cols<NOUT, true, TC, NTHR, !MULTI, false, TC, C::USE2>(buf, Wout, foff,

@@ -188,6 +188,9 @@ struct LasdInterpArgs {
 LG_D double lasd_z(const LasdGeom& g, int k) { return dmul(double(g.coord * (g.nz - 1) + k) - 0.5, g.dz); }
 LG_D double lasd_zw(const LasdGeom& g, int k) { return dsub(lasd_z(g, k), g.dz / 2.0); }
 
+#ifndef LG_LASD_EXACT_DIV
+#define LG_LASD_EXACT_DIV 0
+#endif
 static __global__ void k_interpolag(LasdInterpArgs a, LasdGeom g, Lay lay, int k0, int k1) {
     const long n = long(g.nx) * g.ny * (k1 - k0);
     const int nz = g.nz;
@@ -242,6 +245,7 @@ static __global__ void k_interpolag(LasdInterpArgs a, LasdGeom g, Lay lay, int k
         const long o00a = lay.at(kst, jst - 1, ist - 1), o10a = lay.at(kst, jst - 1, ist1 - 1);
         const long o01a = lay.at(kst, jst1 - 1, ist - 1), o11a = lay.at(kst, jst1 - 1, ist1 - 1);
         const long dk = long(kst1 - kst) * lay.plane;
+#if LG_LASD_EXACT_DIV
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
             const double* v = a.T[f];
@@ -253,6 +257,23 @@ static __global__ void k_interpolag(LasdInterpArgs a, LasdGeom g, Lay lay, int k
             const double u6 = dadd(u3, ddiv(dmul(ydiff, dsub(u4, u3)), g.dy));
             a.F[f][o] = dadd(u5, ddiv(dmul(zdiff, dsub(u6, u5)), g.dz));
         }
+#else
+        // The reference divides each of the 28 increments by dx, dy or dz (functions.f90:445-452); here the three
+        // weights are divided once and multiplied in: the same value to within one rounding of each increment, and
+        // 3 FP64 divisions per point instead of 28 (the kernel is bound by them: 6.8 ms per call at 512 x 512 x 256).
+        const double wx = ddiv(xdiff, g.dx), wy = ddiv(ydiff, g.dy), wz = ddiv(zdiff, g.dz);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const double* v = a.T[f];
+            const double u1 = dadd(v[o00a], dmul(wx, dsub(v[o10a], v[o00a])));
+            const double u2 = dadd(v[o01a], dmul(wx, dsub(v[o11a], v[o01a])));
+            const double u3 = dadd(v[o00a + dk], dmul(wx, dsub(v[o10a + dk], v[o00a + dk])));
+            const double u4 = dadd(v[o01a + dk], dmul(wx, dsub(v[o11a + dk], v[o01a + dk])));
+            const double u5 = dadd(u1, dmul(wy, dsub(u2, u1)));
+            const double u6 = dadd(u3, dmul(wy, dsub(u4, u3)));
+            a.F[f][o] = dadd(u5, dmul(wz, dsub(u6, u5)));
+        }
+#endif
     }
 }
 

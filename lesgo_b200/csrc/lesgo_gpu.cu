@@ -66,6 +66,7 @@ struct lesgo_gpu_ctx {
     double* gtest = nullptr;               // test-filter kernel G_test (lh, ny)
     double* wplane[2] = {nullptr};         // filtered wall-adjacent u, v planes
     double* gtest2 = nullptr;              // second test-filter kernel G_test_test (sgs_model 5)
+    int gcut[2] = {0, 0};                  // kx columns >= gcut[i] of kernel i are zero for every ky (sharp cut-off)
     double* lasd_buf[54] = {nullptr};      // lagrange_Sdep work fields (51) + 3 spectral scratch, lasd_chunk planes each
     double* lasd_tmp[4] = {nullptr};       // interpolag_Sdep's copies of F_LM, F_MM, F_QN, F_NN
     int lasd_chunk = 0;
@@ -1056,6 +1057,13 @@ int build_sgs_tables(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
             if (jx == c->lh - 1 || jy == c->ny / 2) g = 0.0;
             G[size_t(jy) * c->lh + jx] = g;
         }
+    // columns of the kernel that are zero for every ky: the filtered spectrum is zero there, so the passes
+    // neither compute nor move them (spectral cut-off: 3/4 resp. 7/8 of the half spectrum)
+    int cut = 0;
+    for (int jy = 0; jy < c->ny; ++jy)
+        for (int jx = cut; jx < c->lh; ++jx)
+            if (G[size_t(jy) * c->lh + jx] != 0.0) cut = jx + 1;
+    c->gcut[which] = cut < 1 ? 1 : (cut > c->nx / 2 ? c->nx / 2 : cut);
     double** gdst = which == 0 ? &c->gtest : &c->gtest2;
     if (!*gdst && dev_alloc(c, gdst, G.size())) return 1;
     CK(cudaMemcpyAsync(*gdst, G.data(), sizeof(double) * G.size(), cudaMemcpyHostToDevice, c->stream));
@@ -1065,19 +1073,26 @@ int build_sgs_tables(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp) {
     return 0;
 }
 
+// LESGO_FILTER_PRUNE=0: transform and move the kernels' all-zero kx columns too (A/B and test switch)
+static bool prune_enabled() {
+    static const bool on = [] { const char* e = std::getenv("LESGO_FILTER_PRUNE"); return !e || std::atoi(e) != 0; }();
+    return on;
+}
+
 // test_filter of ONE plane (test_filtermodule.f90:126-146): src plane -> dst plane
 int filter_plane(lesgo_gpu_ctx* c, const double* src, double* dst) {
     if (need_small(c, 2)) return 1;
     ProScale ps; ps.src[0] = src; ps.lay = c->lay(); ps.scale = 1.0;
     double* d0[1] = {c->sa[0]};
-    if (xfwd(c, false, ps, 1, d0, c->plane, c->ld, c->nx / 2, c->ny, 0, 1)) return 1;
-    YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, c->nx / 2, 0);
+    const int nc = prune_enabled() ? c->gcut[0] : c->nx / 2;
+    if (xfwd(c, false, ps, 1, d0, c->plane, c->ld, nc, c->ny, 0, 1)) return 1;
+    YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, nc, 0);
     a.fld[0].src = c->sa[0]; a.fld[0].out[0] = YOutSpec{c->sa[1], Y_TABLE};
     a.table = c->gtest; a.table_row = c->lh;
     if (ypass(c, c->ny, c->ny, a, 1, 0, 1)) return 1;
     const double* s0[1] = {c->sa[1]};
     double* o0[1] = {dst};
-    return xinv(c, false, s0, c->plane, c->ld, c->nx / 2, 1, o0, c->lay(), c->ny, 0, 1);
+    return xinv(c, false, s0, c->plane, c->ld, nc, 1, o0, c->lay(), c->ny, 0, 1);
 }
 
 int wallstress(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* const* F, bool with_tau) {
@@ -1152,10 +1167,15 @@ int filter_fields(lesgo_gpu_ctx* c, int nf, const double* const* src, double* co
     for (int i = 0; i < nf; ++i) ps.src[i] = src[i];
     ps.lay = c->lay(); ps.scale = 1.0;
     double* xs[3] = {c->sa[0], c->sa[1], c->sa[2]};
-    if (xfwd(c, false, ps, nf, xs, c->plane, c->ld, c->nx / 2, c->ny, k0, k1)) return 1;
+    // kx columns where a kernel vanishes for every ky are neither transformed nor moved: the x transform writes
+    // nc1 columns, the y pass inverts nc1 (G_test) and nc2 (G_test_test) of them, the x inverses read that many
+    const bool prune = prune_enabled();
+    const int nc1 = prune ? (c->gcut[0] > c->gcut[1] ? c->gcut[0] : c->gcut[1]) : c->nx / 2;
+    const int nc2 = prune ? c->gcut[1] : c->nx / 2;
+    if (xfwd(c, false, ps, nf, xs, c->plane, c->ld, nc1, c->ny, k0, k1)) return 1;
     // one y pass: forward transform once, G_test and G_test_test applied to the same spectrum, two inverses
-    YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, c->nx / 2, k0);
-    a.nout = 2;
+    YArgs a = yargs(c, c->plane, c->ld, c->plane, c->ld, nc1, k0);
+    a.nout = 2; a.ncols2 = nc2;
     for (int i = 0; i < nf; ++i) {
         a.fld[i].src = c->sa[i];
         a.fld[i].out[0] = YOutSpec{c->sa[3 + i], Y_TABLE};
@@ -1166,7 +1186,9 @@ int filter_fields(lesgo_gpu_ctx* c, int nf, const double* const* src, double* co
     const double* s0[6];
     double* d0[6];
     for (int i = 0; i < nf; ++i) { s0[i] = c->sa[3 + i]; d0[i] = dst1[i]; s0[nf + i] = sp2[i]; d0[nf + i] = dst2[i]; }
-    return xinv(c, false, s0, c->plane, c->ld, c->nx / 2, 2 * nf, d0, c->lay(), c->ny, k0, k1);
+    if (nc1 == nc2) return xinv(c, false, s0, c->plane, c->ld, nc1, 2 * nf, d0, c->lay(), c->ny, k0, k1);
+    if (xinv(c, false, s0, c->plane, c->ld, nc1, nf, d0, c->lay(), c->ny, k0, k1)) return 1;
+    return xinv(c, false, s0 + nf, c->plane, c->ld, nc2, nf, d0 + nf, c->lay(), c->ny, k0, k1);
 }
 
 // lagrange_Sdep (lagrange_Sdep.f90:22-430) including interpolag_Sdep (interpolag_Sdep.f90:21-268); Sij in c->work[0..5]
@@ -1196,7 +1218,7 @@ int lagrange_sdep(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* con
             ia.T[f] = c->lasd_tmp[f]; ia.F[f] = FL[f];
         }
         const int k1 = c->top ? nz + 1 : nz;
-        ProfScope ps_(c, "lasd");
+        ProfScope ps_(c, "lasd_interp");
         LG_LAUNCH(k_interpolag, dim3(grid1d(long(c->nx) * c->ny * (k1 - 1))), dim3(kBlock), 0, c->stream, ia, g, c->lay(), 1, k1);
         c->launches++;
     }
@@ -1223,7 +1245,7 @@ int lagrange_sdep(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* con
             LasdPrepArgs pa;
             pa.u = F[LG_U]; pa.v = F[LG_V]; pa.w = F[LG_W];
             for (int i = 0; i < 9; ++i) pa.A[i] = A[i];
-            ProfScope ps_(c, "lasd");
+            ProfScope ps_(c, "lasd_prep");
             LG_LAUNCH(k_lasd_prep, dim3(g1), dim3(kBlock), 0, c->stream, pa, g, c->lay(), k0, k1);
             c->launches++;
         }
@@ -1234,7 +1256,7 @@ int lagrange_sdep(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* con
         {
             LasdSSArgs sa;
             for (int i = 0; i < 6; ++i) { sa.S[i] = c->work[i]; sa.SS[i] = A[i]; }
-            ProfScope ps_(c, "lasd");
+            ProfScope ps_(c, "lasd_ss");
             LG_LAUNCH(k_lasd_ss, dim3(g1), dim3(kBlock), 0, c->stream, sa, c->lay(), c->nx, c->ny, k0, k1);
             c->launches++;
         }
@@ -1248,7 +1270,7 @@ int lagrange_sdep(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double* con
             fa.delta = delta; fa.lagran_dt = sp->lagran_dt;
             fa.beta_exp = std::log(2.0) / (std::log(4.0) - std::log(2.0));       // log(tf1) / (log(tf2) - log(tf1))
             fa.init_F = sp->lasd_init_F ? 1 : 0;
-            ProfScope ps_(c, "lasd");
+            ProfScope ps_(c, "lasd_final");
             LG_LAUNCH(k_lasd_final, dim3(grid1d(long(c->ld) * c->ny * (k1 - k0))), dim3(kBlock), 0, c->stream, fa, g, c->lay(), k0, k1);
             c->launches++;
         }

@@ -45,36 +45,43 @@ struct ProVort {
     Lay lay;
     double scale;
     int nz, bottom, top, lbc_mom, ubc_mom;   // bottom = (coord == 0), top = (coord == nproc-1)
-    LG_D double2 load(int fld, int k, int y, int j) const {
-        const long o = lay.at(k, y, 2 * j);
-        if (fld == 2) {
-            double2 a = ld2(dvdx + o), b = ld2(dudy + o);
-            return make_double2(dmul(scale, dsub(a.x, b.x)), dmul(scale, dsub(a.y, b.y)));
-        }
+    // The case analysis depends on (field, plane) only, so a pass does it once per ROW (row()) and then reads the
+    // row's elements with straight-line code (load_row()): with the analysis inside load() every element was a
+    // load -> branch -> use chain of its own and a thread's 8 elements cost 8 DRAM round trips instead of one.
+    //   kind 0: 0;  1: scale*(a - b);  2: scale*(0.5*(a + b) - c);  3: scale*(c - 0.5*(a + b))
+    struct Row { const double *pa, *pb, *pc; int kind; };
+    LG_D Row row(int fld, int k, int y) const {          // k < 0: a row past the end, reads as zeros
+        Row r;
+        r.pa = r.pb = r.pc = nullptr; r.kind = 0;
+        if (k < 0) return r;
+        const long o = lay.at(k, y, 0);
+        if (fld == 2) { r.pa = dvdx + o; r.pb = dudy + o; r.kind = 1; return r; }
         const bool sb = bottom && k == 1;
         const bool st = top && k == nz && ubc_mom > 0;
-        if (sb && lbc_mom == 0) return make_double2(0.0, 0.0);
+        if (sb && lbc_mom == 0) return r;
         if (sb || st) {
             // 0.5*(dw(k1)+dw(k2)) -/+ d(u|v)dz(kz)
             const int k1 = sb ? 1 : nz - 1, k2 = sb ? 2 : nz, kz = sb ? 1 : nz - 1;
-            const long o1 = lay.at(k1, y, 2 * j), o2 = lay.at(k2, y, 2 * j), oz = lay.at(kz, y, 2 * j);
-            if (fld == 0) {
-                double2 a = ld2(dwdy + o1), b = ld2(dwdy + o2), c = ld2(dvdz + oz);
-                return make_double2(dmul(scale, dsub(dmul(0.5, dadd(a.x, b.x)), c.x)),
-                                    dmul(scale, dsub(dmul(0.5, dadd(a.y, b.y)), c.y)));
-            } else {
-                double2 a = ld2(dwdx + o1), b = ld2(dwdx + o2), c = ld2(dudz + oz);
-                return make_double2(dmul(scale, dsub(c.x, dmul(0.5, dadd(a.x, b.x)))),
-                                    dmul(scale, dsub(c.y, dmul(0.5, dadd(a.y, b.y)))));
-            }
+            const long o1 = lay.at(k1, y, 0), o2 = lay.at(k2, y, 0), oz = lay.at(kz, y, 0);
+            if (fld == 0) { r.pa = dwdy + o1; r.pb = dwdy + o2; r.pc = dvdz + oz; r.kind = 2; }
+            else { r.pa = dwdx + o1; r.pb = dwdx + o2; r.pc = dudz + oz; r.kind = 3; }
+            return r;
         }
-        if (fld == 0) {
-            double2 a = ld2(dwdy + o), b = ld2(dvdz + o);
-            return make_double2(dmul(scale, dsub(a.x, b.x)), dmul(scale, dsub(a.y, b.y)));
-        }
-        double2 a = ld2(dudz + o), b = ld2(dwdx + o);
-        return make_double2(dmul(scale, dsub(a.x, b.x)), dmul(scale, dsub(a.y, b.y)));
+        if (fld == 0) { r.pa = dwdy + o; r.pb = dvdz + o; }
+        else { r.pa = dudz + o; r.pb = dwdx + o; }
+        r.kind = 1;
+        return r;
     }
+    LG_D double2 load_row(const Row& r, int j) const {
+        double2 a = make_double2(0.0, 0.0), b = a, c = a;
+        if (r.kind >= 1) { a = ld2(r.pa + 2 * j); b = ld2(r.pb + 2 * j); }
+        if (r.kind >= 2) c = ld2(r.pc + 2 * j);
+        const double2 h = make_double2(dmul(0.5, dadd(a.x, b.x)), dmul(0.5, dadd(a.y, b.y)));
+        const double2 p = r.kind == 1 ? a : (r.kind == 2 ? h : c);
+        const double2 q = r.kind == 1 ? b : (r.kind == 2 ? c : h);
+        return make_double2(dmul(scale, dsub(p.x, q.x)), dmul(scale, dsub(p.y, q.y)));      // kind 0: scale*(0 - 0)
+    }
+    LG_D double2 load(int fld, int k, int y, int j) const { return load_row(row(fld, k, y), j); }
 };
 
 // u x omega on the 3/2 grid (convec.f90:172-305); fields 0,1,2 = cx, cy, cz
@@ -161,19 +168,35 @@ struct EpiFused {
     double dt, t1, t2;
     const double* fa[3];     // applied body force fxa, fya, fza added on planes k <= kfa (main.f90:264-266), or null
     int kfa;
-    LG_D void store(int fld, int k, int y, int j, double2 v) const {
+    // The operands of one output element.  load() and apply() are separate so that a pass can issue the loads of
+    // ALL the elements a lane is about to produce before it stores any of them: with load-use-store per element
+    // the possibly-aliasing stores serialise the loads, one DRAM round trip per element (8 per row and lane).
+    struct Ops { double2 a, b, c, d; };
+    LG_D Ops load(int fld, int k, int y, int j) const {
+        Ops p;
+        p.a = p.b = p.c = p.d = make_double2(0.0, 0.0);
         const long o = lay.at(k, y, 2 * j);
         if (mode == 1 && k <= kmax[fld]) {
-            double2 vb = ld2(divt[fld] + o), vu = ld2(u[fld] + o);
+            p.a = ld2(divt[fld] + o);
+            p.b = ld2(u[fld] + o);
+            if (!first_step) p.c = ld2(rhs_f[fld] + o);
+            if (fa[fld] && k <= kfa) p.d = ld2(fa[fld] + o);
+        } else if (mode == 2) {
+            p.a = ld2(rhs_f[fld] + o);                                   // rhs_f[] holds RHS here
+            p.b = ld2(u[fld] + o);
+        }
+        return p;
+    }
+    LG_D void apply(int fld, int k, int y, int j, double2 v, const Ops& p) const {
+        const long o = lay.at(k, y, 2 * j);
+        if (mode == 1 && k <= kmax[fld]) {
+            const double2 vb = p.a, vu = p.b;
             const double f = force[fld];
             double2 nr = make_double2(dadd(dsub(-v.x, vb.x), f), dadd(dsub(-v.y, vb.y), f));
-            if (fa[fld] && k <= kfa) {
-                const double2 va = ld2(fa[fld] + o);
-                nr = make_double2(dadd(nr.x, va.x), dadd(nr.y, va.y));
-            }
+            if (fa[fld] && k <= kfa) nr = make_double2(dadd(nr.x, p.d.x), dadd(nr.y, p.d.y));
             double2 vf;
             if (first_step) { vf = nr; *reinterpret_cast<double2*>(rhs_f[fld] + o) = nr; }
-            else vf = ld2(rhs_f[fld] + o);
+            else vf = p.c;
             *reinterpret_cast<double2*>(dst[fld] + o) = nr;
             *reinterpret_cast<double2*>(u[fld] + o) =
                 make_double2(dadd(vu.x, dmul(dt, dadd(dmul(t1, nr.x), dmul(t2, vf.x)))),
@@ -182,12 +205,13 @@ struct EpiFused {
         }
         *reinterpret_cast<double2*>(dst[fld] + o) = v;
         if (mode == 2) {
-            double2 vr = ld2(rhs_f[fld] + o), vu = ld2(u[fld] + o);      // rhs_f[] holds RHS here
+            const double2 vr = p.a, vu = p.b;
             *reinterpret_cast<double2*>(rhs_f[fld] + o) = make_double2(dsub(vr.x, v.x), dsub(vr.y, v.y));
             *reinterpret_cast<double2*>(u[fld] + o) = make_double2(dadd(vu.x, dmul(dt, dmul(-t1, v.x))),
                                                                    dadd(vu.y, dmul(dt, dmul(-t1, v.y))));
         }
     }
+    LG_D void store(int fld, int k, int y, int j, double2 v) const { apply(fld, k, y, j, v, load(fld, k, y, j)); }
     LG_D void finish_row(int fld, int k, int y) const {
         if (!pad) return;
         const long o = lay.at(k, y, nx);

@@ -12,6 +12,7 @@
 //   * larger rows ping-pong between two buffers (one butterfly at a time: load, twiddle,
 //     DFT, store), twiddles read from the per-stage shared-memory tables.
 #pragma once
+#include <type_traits>
 #include "fft_core.h"
 
 namespace lg {
@@ -39,6 +40,12 @@ struct WTw {
     }
 };
 
+// A store functor may offer pre(f, i, slot) / put(f, i, slot, v) next to operator(): the stage then calls pre for
+// the R outputs of a butterfly BEFORE it computes them and put afterwards, so an epilogue that reads operands
+// (EpiFused) has all its loads in flight at once instead of one load-use-store chain per element.
+template <class T, class = void> struct HasPre : std::false_type {};
+template <class T> struct HasPre<T, std::void_t<decltype(&T::pre)>> : std::true_type {};
+
 // One stage over the warp's NF rows.
 //   SRC / DST = 0: functor ld(f, i) / st(f, i, v);  1: padded shared buffer (row f at f*SL)
 //   MIDSYNC   : source and destination are the same buffer -> hold every butterfly of the lane
@@ -62,6 +69,9 @@ LG_D void wstage(int lane, const cplx* sbuf, cplx* dbuf, const cplx* __restrict_
 #pragma unroll
                 for (int r = 0; r < R; ++r) dbuf[f * SL + spad(j0 + r * Ns)] = vv[r];
             }
+        } else if constexpr (HasPre<St>::value) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) st.put(f, j0 + r * Ns, r, vv[r]);
         } else {
 #pragma unroll
             for (int r = 0; r < R; ++r) st(f, j0 + r * Ns, vv[r]);
@@ -73,6 +83,11 @@ LG_D void wstage(int lane, const cplx* sbuf, cplx* dbuf, const cplx* __restrict_
         cplx* vv = v[MIDSYNC ? q : 0];
         if (ITEMS % 32 == 0 || it < ITEMS) {
             const int f = (NF == 1) ? 0 : it / T, j = (NF == 1) ? it : it % T;
+            if constexpr (DST == 0 && HasPre<St>::value) {
+                const int j0 = (Ns == 1) ? j * R : ((j / Ns) * Ns * R + (j % Ns));
+#pragma unroll
+                for (int r = 0; r < R; ++r) st.pre(f, j0 + r * Ns, r);
+            }
             if constexpr (SRC == 1) {
                 if constexpr (T % 8 == 0) {
                     const cplx* p = sbuf + f * SL + spad(j);

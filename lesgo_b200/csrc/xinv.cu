@@ -45,7 +45,7 @@ static int launch_xinv_n(const XiSrc& in, const Epi& epi, int nfields, int ny, i
         if (CW::PREF) {
             LG_SET_SMEM((k_xinv_w<NX, Epi, false, true>), CW::smem);
             const long nwork = nrows * nfields;
-            dim3 grid(persistent_blocks(CW::smem, (nwork + CW::WPB - 1) / CW::WPB, CW::MINB));
+            dim3 grid(persistent_blocks(CW::smem, (nwork + CW::WPB - 1) / CW::WPB, XWMinB<Epi, CW>::value));
             LG_LAUNCH((k_xinv_w<NX, Epi, false, true>), grid, dim3(CW::NTHR), CW::smem, s, in, epi, nfields, ny, k0, nplanes, W, Wh);
             return 0;
         }
@@ -54,7 +54,7 @@ static int launch_xinv_n(const XiSrc& in, const Epi& epi, int nfields, int ny, i
         typedef XWCfg<NX> CW;
         LG_SET_SMEM((k_xinv_w<NX, Epi>), CW::smem);
         const long nwork = ((nrows + CW::NF - 1) / CW::NF) * nfields;
-        dim3 grid(persistent_blocks(CW::smem, (nwork + CW::WPB - 1) / CW::WPB, CW::MINB));
+        dim3 grid(persistent_blocks(CW::smem, (nwork + CW::WPB - 1) / CW::WPB, XWMinB<Epi, CW>::value));
         LG_LAUNCH((k_xinv_w<NX, Epi>), grid, dim3(CW::NTHR), CW::smem, s, in, epi, nfields, ny, k0, nplanes, W, Wh);
         return 0;
     }

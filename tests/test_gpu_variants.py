@@ -19,6 +19,7 @@ VARIANTS = [
     ({"LESGO_REUSE": "0"}, "32,32,6", "steps,full"),
     ({"LESGO_XW2": "7"}, "512,64,3", "deriv,convec,press,steps,full"),    # two-stage x inverse on every x-inverse launch
     ({"LESGO_XW2": "0"}, "512,64,3", "convec,steps"),                     # ... and on none
+    ({"LESGO_FILTER_PRUNE": "0"}, "64,64,8", "lasd,full"),                # test filters without the zero-column pruning
 ]
 
 

@@ -10,8 +10,8 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
 
 import lesgo_b200  # noqa: E402
-from helpers import (O, check_convec, check_derivatives, check_press, check_steps, emul_library,  # noqa: E402
-                     make_dims)
+from helpers import (O, check_convec, check_derivatives, check_lasd_steps, check_press, check_steps,  # noqa: E402
+                     emul_library, make_dims)
 
 
 def main():
@@ -46,6 +46,9 @@ def main():
         p = O.Params(nx=nx, ny=ny, Nz=Nz, lbc_mom=2, ubc_mom=2, sgs=True, sgs_model=1, molec=False, use_mean_p_force=True,
                      mean_p_force_x=1.0)
         worst = max(worst, max(check_steps(core(p), p, nsteps=2, tol=1e-11, mode="full").values()))
+    if "lasd" in what:
+        p = O.Params(nx=nx, ny=ny, Nz=Nz, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=5, dt=2e-3)
+        worst = max(worst, max(check_lasd_steps(core(p), p, nsteps=4, tol=1e-11).values()))
     print(f"variant_check ok worst={worst:.3e}")
 
 

@@ -439,7 +439,7 @@ def main():
     achieved = abytes * points / (ms_step * 1e-3) / 1e9 / world
     traffic, traffic_src = None, None
     try:
-        for tname in ("r4_traffic.json", "r3_traffic.json"):
+        for tname in ("r5_traffic.json", "r4_traffic.json", "r3_traffic.json"):
             tpath = os.path.join(ROOT, "profiles", tname)
             if os.path.exists(tpath):
                 with open(tpath) as f:

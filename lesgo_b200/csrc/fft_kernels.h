@@ -150,8 +150,17 @@ LG_D void xfwd_work(cplx* buf, const cplx* W, const cplx* Wh, int* s_k, int* s_y
 // Pro: struct with  LG_D double2 load(int fld, int k, int y, int j) const
 //      returning (x[2j], x[2j+1]) of row y of plane k of field fld (already scaled).
 // Persistent blocks: each block loops over row tiles, twiddles live in shared memory.
+// resident blocks asked of the compiler for prologues with a row plan (several operand loads per element): fewer
+// blocks = more registers for loads in flight
+#ifndef LG_XFV_MINB
+#define LG_XFV_MINB 0
+#endif
+template <class Pro, class C> struct XFMinB {
+    static constexpr int value = (ProRow<Pro>::value && LG_XFV_MINB > 0 && LG_XFV_MINB < C::MINB) ? LG_XFV_MINB : C::MINB;
+};
+
 template <int NX, class Pro>
-__global__ void __launch_bounds__(XCfg<NX>::NTHR, XCfg<NX>::MINB)
+__global__ void __launch_bounds__(XCfg<NX>::NTHR, XFMinB<Pro, XCfg<NX>>::value)
 k_xfwd(const __grid_constant__ Pro pro, const __grid_constant__ XfOut out, int nfields, int zmajor, int ny, int k0, int nplanes,
        const cplx* __restrict__ Wg, const cplx* __restrict__ Whg) {
     typedef XCfg<NX> C;

@@ -21,7 +21,7 @@ static int launch_xfwd_n(const Pro& pro, int nfields, const XfOut& out, int ny, 
         return 0;
     }
     LG_SET_SMEM((k_xfwd<NX, Pro>), C::smem);
-    dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, C::MINB));
+    dim3 grid(persistent_blocks(C::smem, ((nrows + C::NF - 1) / C::NF) * nfields, XFMinB<Pro, C>::value));
     LG_LAUNCH((k_xfwd<NX, Pro>), grid, dim3(C::NTHR), C::smem, s, pro, out, nfields, int(zmajor_for<Pro>() && ny % C::NF == 0), ny, k0, nplanes, W, Wh);
     return 0;
 }

@@ -87,6 +87,16 @@ interface
         integer(c_int), value :: nloc, adm_correction
         type(lesgo_gpu_turbine), intent(in) :: turbines(*)
     end function
+    !> ind_t(s) -> c_loc(%ind_t), e_theta(s) -> c_loc of a real(c_double) array (3, num_nodes) holding
+    !> transpose(%e_theta(1:num_nodes, 1:3))
+    integer(c_int) function lesgo_gpu_turbines_rotation(ctx, nloc, ind_t, e_theta, tip_speed_ratio)         &
+        bind(c, name='lesgo_gpu_turbines_rotation')
+        import
+        type(c_ptr), value :: ctx
+        integer(c_int), value :: nloc
+        type(c_ptr), intent(in) :: ind_t(*), e_theta(*)
+        real(c_double), value :: tip_speed_ratio
+    end function
     integer(c_int) function lesgo_gpu_turbines_forcing(ctx, eps, u_d, u_d_T, f_n)                           &
         bind(c, name='lesgo_gpu_turbines_forcing')
         import
@@ -153,6 +163,48 @@ else if ((jt >= DYN_init .or. initu) .and. mod(jt_total, cs_count) == 0) then
     end if
 end if
 end subroutine gpu_lasd_switches
+
+!> Hand wind_farm over after turbines_init / turbines_nodes (turbines.f90:129-462), and again whenever
+!> turbines_nodes re-meshes the disks (dyn_theta1 / dyn_theta2, turbines.f90:506-515).  With use_rotation
+!> (turbines.f90:76) the tangential weights and unit vectors go along (turbines.f90:419-429, :456, :607-615).
+subroutine gpu_turbines_set(wind_farm, nloc, adm_correction, use_rotation, tip_speed_ratio)
+use stat_defs, only : wind_farm_t
+type(wind_farm_t), intent(in), target :: wind_farm
+integer, intent(in) :: nloc
+logical, intent(in) :: adm_correction, use_rotation
+real(c_double), intent(in) :: tip_speed_ratio
+type(lesgo_gpu_turbine), allocatable :: t(:)
+type(c_ptr), allocatable :: pt(:), pe(:)
+integer(c_int), allocatable, target :: nodes_c(:,:,:)
+real(c_double), allocatable, target :: eth_c(:,:,:)
+integer :: s, n, nmax
+nmax = 1
+do s = 1, nloc
+    nmax = max(nmax, wind_farm%turbine(s)%num_nodes)
+end do
+allocate(t(nloc), pt(nloc), pe(nloc), nodes_c(3, nmax, nloc), eth_c(3, nmax, nloc))
+do s = 1, nloc
+    n = wind_farm%turbine(s)%num_nodes
+    nodes_c(:, 1:n, s) = transpose(wind_farm%turbine(s)%nodes(1:n, 1:3))
+    t(s)%num_nodes = n
+    t(s)%nodes = c_loc(nodes_c(1, 1, s))
+    t(s)%ind = c_loc(wind_farm%turbine(s)%ind(1))
+    t(s)%nhat = wind_farm%turbine(s)%nhat
+    t(s)%Ct_prime = wind_farm%turbine(s)%Ct_prime
+    t(s)%dia = wind_farm%turbine(s)%dia
+    t(s)%M = wind_farm%turbine(s)%turb_ind_func%M
+    t(s)%u_d_T = wind_farm%turbine(s)%u_d_T
+    if (use_rotation) then
+        eth_c(:, 1:n, s) = transpose(wind_farm%turbine(s)%e_theta(1:n, 1:3))
+        pt(s) = c_loc(wind_farm%turbine(s)%ind_t(1))
+        pe(s) = c_loc(eth_c(1, 1, s))
+    end if
+end do
+call gpu_check(lesgo_gpu_turbines_init(gpu_ctx, int(nloc, c_int), t, merge(1_c_int, 0_c_int, adm_correction)),        &
+    'lesgo_gpu_turbines_init')
+if (use_rotation) call gpu_check(lesgo_gpu_turbines_rotation(gpu_ctx, int(nloc, c_int), pt, pe, tip_speed_ratio),     &
+    'lesgo_gpu_turbines_rotation')
+end subroutine gpu_turbines_set
 
 !> checkpoint (io.f90:1199-1211) / ic_file (initial.f90:226-239) with the reference's file name
 subroutine gpu_checkpoint(fname, writing)

@@ -216,7 +216,7 @@ int lesgo_gpu_tavg_reset(lesgo_gpu_ctx* ctx);
 /* ---- actuator-disk turbines (turbines.f90) ---------------------------------------------------------
  * The host keeps turbines_init / turbines_nodes (turbines.f90:129-462: input files, the filtered indicator
  * function of turbine_indicator.f90, node search) and hands the result over; call again when the disks
- * move (dyn_theta1/2).  use_rotation = .false. (turbines.f90:76) only. */
+ * move (dyn_theta1/2).  use_rotation (turbines.f90:76, :607-615): lesgo_gpu_turbines_rotation below. */
 typedef struct lesgo_gpu_turbine {
     int num_nodes;           /* wind_farm%turbine(s)%num_nodes on THIS rank (may be 0)                   */
     const int* nodes;        /* (num_nodes, 3) triplets i, j (1-based), k (local, 1..nz-1): %nodes(l,1:3)  */
@@ -227,6 +227,13 @@ typedef struct lesgo_gpu_turbine {
     double u_d_T;            /* initial running-average disk velocity (turbine_vel_init, :642-676)        */
 } lesgo_gpu_turbine;
 int lesgo_gpu_turbines_init(lesgo_gpu_ctx* ctx, int nloc, const lesgo_gpu_turbine* turbines, int adm_correction);
+/* ADM with rotation (use_rotation = .true., turbines.f90:607-615): after lesgo_gpu_turbines_init, hand over what
+ * turbines_nodes (turbines.f90:419-429, :456) also leaves in wind_farm%turbine(s): ind_t[s] = %ind_t(1:num_nodes),
+ * e_theta[s] = %e_theta(l, 1:3) as (num_nodes, 3) triplets like `nodes`; tip_speed_ratio as turbines.f90:78.  The
+ * scatter then adds f_n * e_theta * ind_t / tip_speed_ratio to the three force components.  nloc must match the
+ * init call; lesgo_gpu_turbines_init switches rotation off again. */
+int lesgo_gpu_turbines_rotation(lesgo_gpu_ctx* ctx, int nloc, const double* const* ind_t, const double* const* e_theta,
+                                double tip_speed_ratio);
 /* turbines_forcing (turbines.f90:465-638) on the resident u, v, w -> resident LG_FXA, LG_FYA, LG_FZA (fza on
  * w nodes, ghost planes synchronised).  u_d, u_d_T, f_n: optional host arrays (nloc) receiving %u_d, %u_d_T,
  * %f_n after the update (NULL = leave everything on the device, no synchronisation). */

@@ -286,9 +286,10 @@ class Core:
         self._ck(self.lib.tavg_reset(self._ctx), "tavg_reset")
 
     # -- actuator disks (turbines.f90) --------------------------------------------------------------
-    def turbines_init(self, farm, adm_correction=False):
+    def turbines_init(self, farm, adm_correction=False, use_rotation=False, tip_speed_ratio=7.0):
         """farm: objects with nodes (n, 3) int (1-based i, j, local k), ind (n), nhat, Ct_prime, dia, M, u_d_T --
-        what turbines_nodes (turbines.f90:275-462) leaves in wind_farm%turbine(:)."""
+        what turbines_nodes (turbines.f90:275-462) leaves in wind_farm%turbine(:).  use_rotation (turbines.f90:76,
+        :607-615): the objects also carry ind_t (n) and e_theta (n, 3)."""
         arr = (TurbineStruct * max(len(farm), 1))()
         keep = []
         for s, t in enumerate(farm):
@@ -302,6 +303,17 @@ class Core:
             arr[s].Ct_prime, arr[s].dia, arr[s].M, arr[s].u_d_T = float(t.Ct_prime), float(t.dia), float(t.M), float(t.u_d_T)
         self._nturb = len(farm)
         self._ck(self.lib.turbines_init(self._ctx, len(farm), arr, int(adm_correction)), "turbines_init")
+        if use_rotation:
+            n = max(len(farm), 1)
+            it, et = (C.c_void_p * n)(), (C.c_void_p * n)()
+            for s, t in enumerate(farm):
+                a = np.ascontiguousarray(np.asarray(t.ind_t, dtype=np.float64))
+                b = np.ascontiguousarray(np.asarray(t.e_theta, dtype=np.float64).reshape(-1, 3))
+                if len(a) != arr[s].num_nodes or len(b) != arr[s].num_nodes:
+                    raise ValueError("ind_t / e_theta must have one entry per node")
+                keep += [a, b]
+                it[s], et[s] = a.ctypes.data, b.ctypes.data
+            self._ck(self.lib.turbines_rotation(self._ctx, len(farm), it, et, float(tip_speed_ratio)), "turbines_rotation")
 
     def turbines_forcing(self, eps, fetch=True):
         """turbines_forcing (turbines.f90:465-638) on the resident fields; returns (u_d, u_d_T, f_n) per disk."""

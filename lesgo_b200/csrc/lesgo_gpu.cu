@@ -89,6 +89,7 @@ struct lesgo_gpu_ctx {
     TurbSet turb;
     bool turb_on = false, turb_fz = false;
     int turb_adm = 0;
+    std::vector<int> turb_nodes;           // prefix offsets of the disks' node lists (host copy of TurbSet::start)
     double* turb_fzuv = nullptr;           // fza before interp_to_w_grid (uv nodes)
     int sgs_cfg = -1;                      // (sgs_model, ifilter) the tables above were built for
     double* fields[LG_NFIELDS] = {nullptr};
@@ -1428,6 +1429,8 @@ int turbines_init(lesgo_gpu_ctx* c, int nloc, const lesgo_gpu_turbine* t, int ad
     ts.u_d = const_cast<double*>(d_zero);
     if (upload_vec(c, &d_zero, z)) return 1;
     ts.f_n = const_cast<double*>(d_zero);
+    ts.ind_t = nullptr; ts.e_theta = nullptr; ts.tip_speed_ratio = 1.0;
+    c->turb_nodes.assign(start.begin(), start.end());
     c->turb = ts; c->turb_adm = adm; c->turb_fz = fz;
     // forcing.f90:103-105: the force fields are zero away from the disks
     const size_t nfield = size_t(c->plane) * (nz + 1);
@@ -2080,6 +2083,28 @@ int lesgo_gpu_turbines_init(lesgo_gpu_ctx* c, int nloc, const lesgo_gpu_turbine*
     ENTER(c);
     if (!c) return 1;
     return turbines_init(c, nloc, t, adm_correction);
+}
+
+int lesgo_gpu_turbines_rotation(lesgo_gpu_ctx* c, int nloc, const double* const* ind_t, const double* const* e_theta,
+                                double tip_speed_ratio) {
+    ENTER(c);
+    if (!c) return 1;
+    if (!c->turb_on) return c->fail("lesgo_gpu_turbines_rotation: call lesgo_gpu_turbines_init first");
+    if (nloc != c->turb.nloc || (nloc > 0 && (!ind_t || !e_theta)))
+        return c->fail("lesgo_gpu_turbines_rotation: nloc and the per-disk arrays must match lesgo_gpu_turbines_init");
+    if (!(tip_speed_ratio != 0.0)) return c->fail("lesgo_gpu_turbines_rotation: tip_speed_ratio must be non-zero");
+    std::vector<double> it, et;
+    for (int s = 0; s < nloc; ++s) {
+        const int n = c->turb_nodes[size_t(s) + 1] - c->turb_nodes[size_t(s)];
+        if (n > 0 && (!ind_t[s] || !e_theta[s])) return c->fail("lesgo_gpu_turbines_rotation: disk without ind_t / e_theta");
+        it.insert(it.end(), ind_t[s], ind_t[s] + n);
+        et.insert(et.end(), e_theta[s], e_theta[s] + 3 * size_t(n));
+    }
+    if (upload_vec(c, &c->turb.ind_t, it) || upload_vec(c, &c->turb.e_theta, et)) return 1;
+    c->turb.tip_speed_ratio = tip_speed_ratio;
+    c->turb_fz = true;                     // e_theta has a z component: fza needs the interpolation to w nodes
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 int lesgo_gpu_turbines_forcing(lesgo_gpu_ctx* c, double eps, double* u_d, double* u_d_T, double* f_n) {

@@ -21,6 +21,10 @@ struct TurbSet {
     double* u_d;             // (nloc) out: disk-averaged velocity
     double* u_d_T;           // (nloc) inout: its running average
     double* f_n;             // (nloc) out
+    // ADM with rotation (use_rotation, turbines.f90:607-615): per node tangential weight and unit vector, or null
+    const double* ind_t;     // per node
+    const double* e_theta;   // per node, 3 components
+    double tip_speed_ratio;
 };
 
 // turbines.f90:521-548: disk_avg_vel(s) = sum_l dx dy dz ind(l) (nhat . (u, v, w_uv)); one block per disk
@@ -60,7 +64,8 @@ static __global__ void k_turb_update(TurbSet t, double eps, int adm_correction) 
     }
 }
 
-// turbines.f90:599-606: f = f_n nhat ind at the disk's nodes (fz still on uv nodes)
+// turbines.f90:599-615: f = f_n nhat ind (+ f_n e_theta ind_t / tip_speed_ratio with use_rotation) at the disk's nodes
+// (fz still on uv nodes)
 static __global__ void k_turb_scatter(TurbSet t, double* __restrict__ fxa, double* __restrict__ fya, double* __restrict__ fz_uv) {
     const int s = blockIdx.x;
     const double fn = t.f_n[s];
@@ -69,7 +74,14 @@ static __global__ void k_turb_scatter(TurbSet t, double* __restrict__ fxa, doubl
         if (!t.owner[l]) continue;
         const long o = t.off[l];
         const double a = t.ind[l];
-        fxa[o] = dmul(f0, a); fya[o] = dmul(f1, a); fz_uv[o] = dmul(f2, a);
+        double gx = dmul(f0, a), gy = dmul(f1, a), gz = dmul(f2, a);
+        if (t.ind_t) {
+            const double b = t.ind_t[l];
+            gx = dadd(gx, ddiv(dmul(dmul(fn, t.e_theta[3 * l]), b), t.tip_speed_ratio));
+            gy = dadd(gy, ddiv(dmul(dmul(fn, t.e_theta[3 * l + 1]), b), t.tip_speed_ratio));
+            gz = dadd(gz, ddiv(dmul(dmul(fn, t.e_theta[3 * l + 2]), b), t.tip_speed_ratio));
+        }
+        fxa[o] = gx; fya[o] = gy; fz_uv[o] = gz;
     }
 }
 

@@ -80,6 +80,7 @@ SYMBOLS = {
     "lesgo_gpu_tavg_download": (C.c_int, [_P, C.c_int, _D, C.POINTER(C.c_double)]),
     "lesgo_gpu_tavg_reset": (C.c_int, [_P]),
     "lesgo_gpu_turbines_init": (C.c_int, [_P, C.c_int, C.POINTER(TurbineStruct), C.c_int]),
+    "lesgo_gpu_turbines_rotation": (C.c_int, [_P, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double]),
     "lesgo_gpu_turbines_forcing": (C.c_int, [_P, C.c_double, _D, _D, _D]),
     "lesgo_gpu_comm_unique_id": (C.c_int, [_P]),
     "lesgo_gpu_comm_local_id": (C.c_int, [_P]),

@@ -1168,7 +1168,7 @@ def lagrange_Sdep(s, sp: Spectral, comm, G_test, G_test_test, lagran_dt, init_F=
 
 # ----------------------------------------------------------------------------------
 # Actuator disks: turbines.f90 (turbines_nodes :275-462, turbines_forcing :465-638),
-# functions.f90:51-141 (interp_to_uv_grid, interp_to_w_grid); use_rotation = .false. (:76)
+# functions.f90:51-141 (interp_to_uv_grid, interp_to_w_grid); use_rotation (:76, :419-429, :607-615) optional
 # ----------------------------------------------------------------------------------
 @dataclass
 class Turbine:
@@ -1187,6 +1187,8 @@ class Turbine:
     ind: np.ndarray = None
     u_d: float = 0.0
     f_n: float = 0.0
+    ind_t: np.ndarray = None     # use_rotation: tangential indicator weights (turbines.f90:419, :456)
+    e_theta: np.ndarray = None   # use_rotation: (num_nodes, 3) azimuthal unit vectors (:420-429)
 
 
 def standin_indicator(dia, thk, delta1, delta2):
@@ -1204,6 +1206,13 @@ def standin_indicator(dia, thk, delta1, delta2):
         R1 = 0.5 * (1.0 - erf(sqrt(6.0) / d2 * (r - 1.0))) / math.pi
         R2 = 0.5 / th * (erf(c * (x + 0.5 * th)) - erf(c * (x - 0.5 * th)))
         return R1 * R2 / ell ** 3
+
+    def val_t(r_disk, r_norm):
+        # stand-in for Rval_t (turbine_indicator.f90:57-62; the reference filters a (1/pi) y / r**2 disk for its
+        # tangential table R2_t, :111-113, :159-163).  As for val, the tests only need SOME smooth weight both sides
+        # share that differs from val: the same factors times r / ell.
+        return val(r_disk, r_norm) * (r_disk / ell)
+    val.tangential = val_t
     return val
 
 
@@ -1224,6 +1233,8 @@ def turbines_nodes(p: Params, farm, val, comm, alpha=1.5, filter_cutoff=1e-2):
         icp, jcp = int(round(t.xloc / dx)), int(round(t.yloc / dy))
         filt_max = val(0.0, 0.0)
         nodes, ind = [], []
+        ind_t, e_theta = [], []
+        val_t = getattr(val, "tangential", None)
         for k in range(k_start, k_end + 1):
             for j in range(jcp - jmax + 1, jcp + jmax + 1):
                 for i in range(icp - imax + 1, icp + imax + 1):
@@ -1239,12 +1250,23 @@ def turbines_nodes(p: Params, farm, val, comm, alpha=1.5, filter_cutoff=1e-2):
                     if filt > filter_cutoff * filt_max:
                         nodes.append((i2, j2, k - p.coord * (nz - 1)))
                         ind.append(filt)
+                        if val_t is not None:                          # :419-429
+                            ind_t.append(val_t(r_disk, r_norm))
+                            tv = (rx - r_norm * n1, ry - r_norm * n2, rz - r_norm * n3)
+                            e = (n2 * tv[2] - n3 * tv[1], n3 * tv[0] - n1 * tv[2], n1 * tv[1] - n2 * tv[0])
+                            nrm = math.sqrt(e[0] ** 2 + e[1] ** 2 + e[2] ** 2)
+                            e_theta.append((e[0] / nrm, e[1] / nrm, e[2] / nrm) if nrm > 0.0 else (math.nan,) * 3)
                         sumA[s] += filt * dx * dy * dz
         t.nodes = np.array(nodes, dtype=np.int32).reshape(-1, 3)
         t.ind = np.array(ind, dtype=np.float64)
+        if val_t is not None:
+            t.ind_t = np.array(ind_t, dtype=np.float64)
+            t.e_theta = np.array(e_theta, dtype=np.float64).reshape(-1, 3)
     for s, t in enumerate(farm):
         tot = comm.allreduce(float(sumA[s]), "sum")
         t.ind = t.ind / tot                                            # :452-455
+        if t.ind_t is not None:
+            t.ind_t = t.ind_t / tot                                    # :456
 
 
 def interp_to_uv_grid(var, p: Params, comm):
@@ -1267,7 +1289,7 @@ def interp_to_w_grid(var, p: Params, comm):
     return out
 
 
-def turbines_forcing(s, p: Params, comm, farm, eps, adm_correction=False):
+def turbines_forcing(s, p: Params, comm, farm, eps, adm_correction=False, use_rotation=False, tip_speed_ratio=7.0):
     """turbines.f90:465-638 (+ forcing.f90:102-106): returns fxa, fya, fza; updates u_d, u_d_T, f_n."""
     nz = p.nz
     fxa = np.zeros_like(s.u); fya = np.zeros_like(s.u); fza = np.zeros_like(s.u)
@@ -1291,6 +1313,9 @@ def turbines_forcing(s, p: Params, comm, farm, eps, adm_correction=False):
             fxa[k2, j2 - 1, i2 - 1] = t.f_n * t.nhat[0] * t.ind[l]
             fya[k2, j2 - 1, i2 - 1] = t.f_n * t.nhat[1] * t.ind[l]
             fza[k2, j2 - 1, i2 - 1] = t.f_n * t.nhat[2] * t.ind[l]
+            if use_rotation:                                           # :607-615
+                for f, c in ((fxa, 0), (fya, 1), (fza, 2)):
+                    f[k2, j2 - 1, i2 - 1] = f[k2, j2 - 1, i2 - 1] + t.f_n * t.e_theta[l, c] * t.ind_t[l] / tip_speed_ratio
     for f in (fxa, fya, fza):                                          # :620-622
         mpi_sync_real_array(f, p, comm, down=True, up=True)
     fza = interp_to_w_grid(fza, p, comm)                               # :623
@@ -1474,7 +1499,9 @@ def step(s: State, sp: Spectral, comm, mode="full", first_step=False, G_test=Non
     # :254-266 forcing_applied (actuator disks) -> RHS
     if turbines is not None:
         s.fxa, s.fya, s.fza = turbines_forcing(s, p, comm, turbines["farm"], turbines["eps"],
-                                               adm_correction=turbines.get("adm_correction", False))
+                                               adm_correction=turbines.get("adm_correction", False),
+                                               use_rotation=turbines.get("use_rotation", False),
+                                               tip_speed_ratio=turbines.get("tip_speed_ratio", 7.0))
         s.RHSx[1:nz] = s.RHSx[1:nz] + s.fxa[1:nz]
         s.RHSy[1:nz] = s.RHSy[1:nz] + s.fya[1:nz]
         s.RHSz[1:nz] = s.RHSz[1:nz] + s.fza[1:nz]

@@ -79,10 +79,11 @@ def run_lasd_case(name="ref_full_lasd_16x16x6", nsteps=4):
     print(f"{name}: {nsteps} steps, {R.I.nstmt} reference statements, {time.time() - t0:.1f} s")
 
 
-def run_turbine_case(name="ref_turbines_32x32x8", nsteps=2, eps=0.3):
+def run_turbine_case(name="ref_turbines_32x32x8", nsteps=2, eps=0.3, use_rotation=False, tip_speed_ratio=7.0):
     """Rows (f)-3 from the reference text: turbines_forcing (turbines.f90:465-638) through forcing_applied
     (forcing.f90:102-106) and main.f90:263-267 inside two core steps, USE_TURBINES build; two disks (one yawed and
-    tilted), adm_correction on.  The node lists / indicator weights are start-up data handed to both sides."""
+    tilted), adm_correction on.  The node lists / indicator weights are start-up data handed to both sides.
+    use_rotation: the ADM with rotation (turbines.f90:607-615), %ind_t and %e_theta handed over as well."""
     from helpers import make_farm
     kw = dict(nx=32, ny=32, Nz=8, lbc_mom=1, ubc_mom=1)
     p = O.Params(**kw)
@@ -90,7 +91,9 @@ def run_turbine_case(name="ref_turbines_32x32x8", nsteps=2, eps=0.3):
     farm = make_farm(p)
     for t in farm:
         t.M = 0.9
-    R.farm_set(farm, eps, adm_correction=True)
+    if use_rotation:
+        assert all(t.ind_t is not None and np.isfinite(t.e_theta).all() for t in farm)
+    R.farm_set(farm, eps, adm_correction=True, use_rotation=use_rotation, tip_speed_ratio=tip_speed_ratio)
     u, v, w = initial_fields(p, seed=71)
     u = u + 1.0
     out = {"u0": u, "v0": v, "w0": w}
@@ -106,7 +109,10 @@ def run_turbine_case(name="ref_turbines_32x32x8", nsteps=2, eps=0.3):
     for i, t in enumerate(farm):
         out[f"farm{i}_nodes"], out[f"farm{i}_ind"] = np.asarray(t.nodes), np.asarray(t.ind)
         out[f"farm{i}_scalars"] = np.array([t.Ct_prime, t.dia, t.M, t.u_d_T, *t.nhat])
+        if use_rotation:
+            out[f"farm{i}_ind_t"], out[f"farm{i}_e_theta"] = np.asarray(t.ind_t), np.asarray(t.e_theta)
     meta = dict(params=params_record(p), mode="core", nsteps=nsteps, eps=eps, ndisks=len(farm), adm_correction=True,
+                use_rotation=bool(use_rotation), tip_speed_ratio=float(tip_speed_ratio),
                 made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py", statements=R.I.nstmt)
     out["meta"] = np.array(repr(meta))
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
@@ -297,5 +303,7 @@ if __name__ == "__main__":
         run_tavg_case()
     if not only or "turbines" in only:
         run_turbine_case()
+    if not only or "turbines_rot" in only:
+        run_turbine_case(name="ref_turbines_rot_32x32x8", use_rotation=True, tip_speed_ratio=5.5)
     if not only or "mpi" in only:
         run_mpi_case()

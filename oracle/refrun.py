@@ -194,7 +194,7 @@ class Reference:
         k0 = fa.lb[2]
         fa.a[...] = np.asarray(arr)[k0:k0 + fa.a.shape[2]].transpose(2, 1, 0)
 
-    def farm_set(self, farm, eps, adm_correction=False):
+    def farm_set(self, farm, eps, adm_correction=False, use_rotation=False, tip_speed_ratio=7.0):
         """wind_farm as turbines_init / turbines_nodes leave it (turbines.f90:129-462 are host start-up work fed from input
         files; both sides are handed the same node lists): nloc disks with %nodes, %ind, %nhat, %Ct_prime, %dia, %u_d_T,
         %turb_ind_func%M.  eps enters through T_avg_dim and dt_dim exactly as turbines.f90:563-567 forms it."""
@@ -209,6 +209,9 @@ class Reference:
             o.nodes = F.FArray(np.asfortranarray(np.asarray(t.nodes, dtype=np.int64).reshape(n, 3)), (1, 1), "integer")
             o.ind = F.FArray(np.array(t.ind, dtype=np.float64), (1,))
             o.nhat = F.FArray(np.array(t.nhat, dtype=np.float64), (1,))
+            if use_rotation:                                          # %ind_t, %e_theta: turbines.f90:419-429, :456
+                o.ind_t = F.FArray(np.array(t.ind_t, dtype=np.float64), (1,))
+                o.e_theta = F.FArray(np.asfortranarray(np.asarray(t.e_theta, dtype=np.float64).reshape(n, 3)), (1, 1))
             o.ct_prime, o.dia, o.u_d_t, o.u_d, o.f_n = float(t.Ct_prime), float(t.dia), float(t.u_d_T), 0.0, 0.0
             o.theta1, o.theta2 = float(getattr(t, "theta1", 0.0)), float(getattr(t, "theta2", 0.0))
             o.icp = o.jcp = o.kcp = 1
@@ -220,7 +223,8 @@ class Reference:
         wf.turbine = arr
         T = lambda n, v: I.set("turbines", n, v)
         T("nloc", len(farm)); T("dyn_theta1", False); T("dyn_theta2", False); T("dyn_ct_prime", False)
-        T("adm_correction", bool(adm_correction)); T("use_rotation", False); T("tbase", 10 ** 9)
+        T("adm_correction", bool(adm_correction)); T("use_rotation", bool(use_rotation)); T("tbase", 10 ** 9)
+        T("tip_speed_ratio", float(tip_speed_ratio))
         # eps = (dt_dim / T_avg_dim) / (1 + dt_dim / T_avg_dim)  ->  dt_dim / T_avg_dim = eps / (1 - eps)
         I.set("param", "dt_dim", float(eps / (1.0 - eps))); T("t_avg_dim", 1.0)
         I.set("param", "total_time_dim", 0.0); I.set("param", "total_time", 0.0)

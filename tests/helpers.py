@@ -257,8 +257,10 @@ def make_farm(p, comm=None, tilt=True, overlap=False):
     return farm
 
 
-def check_turbines(core, p, nsteps=2, tol=1e-12, mode="core", eps=0.3, adm_correction=True, overlap=False):
-    """turbines_forcing standalone (force fields, per-disk scalars) and inside lesgo_gpu_step."""
+def check_turbines(core, p, nsteps=2, tol=1e-12, mode="core", eps=0.3, adm_correction=True, overlap=False, rotation=None):
+    """turbines_forcing standalone (force fields, per-disk scalars) and inside lesgo_gpu_step.
+    rotation = tip speed ratio: the ADM with rotation (use_rotation, turbines.f90:607-615)."""
+    rkw = dict(use_rotation=True, tip_speed_ratio=float(rotation)) if rotation else {}
     sp = O.Spectral(p)
     nx, nz = p.nx, p.nz
     G = O.test_filter_kernel(sp)
@@ -273,12 +275,12 @@ def check_turbines(core, p, nsteps=2, tol=1e-12, mode="core", eps=0.3, adm_corre
         core.upload(n, getattr(s, n))
     for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
         core.upload(n, np.zeros(core.dims.shape))
-    core.turbines_init(farm, adm_correction=adm_correction)
+    core.turbines_init(farm, adm_correction=adm_correction, **rkw)
     out = {}
     # standalone call; the oracle copy keeps the running averages of the two sides in step
     import copy
     farm0 = copy.deepcopy(farm)
-    fx, fy, fz = O.turbines_forcing(s, p, O.LocalComm(), farm0, eps, adm_correction=adm_correction)
+    fx, fy, fz = O.turbines_forcing(s, p, O.LocalComm(), farm0, eps, adm_correction=adm_correction, **rkw)
     u_d, u_d_T, f_n = core.turbines_forcing(eps)
     out["u_d"] = rel(u_d, [t.u_d for t in farm0]); out["u_d_T"] = rel(u_d_T, [t.u_d_T for t in farm0])
     out["f_n"] = rel(f_n, [t.f_n for t in farm0])
@@ -286,10 +288,10 @@ def check_turbines(core, p, nsteps=2, tol=1e-12, mode="core", eps=0.3, adm_corre
         g = core.download(n)
         assert np.count_nonzero(r[1:nz, :, :nx]) > 0, n
         out[n] = rel(g[1:nz, :, :nx], r[1:nz, :, :nx])
-    core.turbines_init(farm, adm_correction=adm_correction)      # reset the running averages
+    core.turbines_init(farm, adm_correction=adm_correction, **rkw)      # reset the running averages
     for it in range(nsteps):
         O.step(s, sp, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=G,
-               turbines=dict(farm=farm, eps=eps, adm_correction=adm_correction))
+               turbines=dict(farm=farm, eps=eps, adm_correction=adm_correction, **rkw))
         core.step(**step_kwargs_pre_dyn(p, it, mode), turbines=True, turbines_eps=eps)
     for n in ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz"):
         g = core.download(n)
@@ -316,6 +318,8 @@ def farm_for_rank(farm, p):
         c.nodes = t.nodes[m].copy()
         c.nodes[:, 2] -= p.coord * (p.nz - 1)
         c.ind = t.ind[m].copy()
+        if t.ind_t is not None:
+            c.ind_t, c.e_theta = t.ind_t[m].copy(), t.e_theta[m].copy()
         out.append(c)
     return out
 

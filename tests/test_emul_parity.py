@@ -133,6 +133,12 @@ def test_emul_turbines_overlapping_disks():
     print(check_turbines(core_for(p), p, mode="core", tol=1e-11, overlap=True))
 
 
+def test_emul_turbines_with_rotation():
+    from helpers import check_turbines
+    p = O.Params(nx=32, ny=32, Nz=12, lbc_mom=1, ubc_mom=1)
+    print(check_turbines(core_for(p), p, mode="core", tol=1e-11, overlap=True, rotation=6.0))
+
+
 @pytest.mark.parametrize("nproc", [2, 4])
 def test_emul_multirank_turbines(nproc):
     """Disks spanning several z slabs: per-rank node lists, all-reduced disk velocities, force halos."""

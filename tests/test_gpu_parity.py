@@ -167,6 +167,14 @@ def test_turbines_overlapping_disks():
     print(check_turbines(core_for(p), p, mode="core", tol=1e-12, overlap=True))
 
 
+def test_turbines_with_rotation():
+    """use_rotation (turbines.f90:76, :607-615): the tangential force f_n e_theta ind_t / tip_speed_ratio, overlapping
+    disks included (the last disk's assignment wins, rotation term and all)."""
+    from helpers import check_turbines
+    p = O.Params(nx=64, ny=64, Nz=32, lbc_mom=1, ubc_mom=1)
+    print(check_turbines(core_for(p), p, mode="core", tol=1e-12, overlap=True, rotation=6.0))
+
+
 @pytest.mark.parametrize("cfg,turbines", [
     (dict(nx=64, ny=64, Nz=16, lbc_mom=1, ubc_mom=1, molec=True, nu_molec=1e-2), False),
     (dict(nx=64, ny=32, Nz=24, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False), True),

@@ -41,7 +41,7 @@ def valid(p, n, a):
 
 def test_fixtures_exist():
     assert len(STEP_FIXTURES) >= 5 and os.path.exists(os.path.join(GOLD, "ref_routines_16x16x6.npz"))
-    for f in ("ref_full_lasd_16x16x6", "ref_tavg_16x16x6", "ref_turbines_32x32x8", "ref_mpi4_full_16x16x8"):
+    for f in ("ref_full_lasd_16x16x6", "ref_tavg_16x16x6", "ref_turbines_32x32x8", "ref_turbines_rot_32x32x8", "ref_mpi4_full_16x16x8"):
         assert os.path.exists(os.path.join(GOLD, f + ".npz")), f
 
 
@@ -284,14 +284,24 @@ def farm_from_fixture(d, meta):
         ct, dia, M, udt, n1, n2, n3 = d[f"farm{i}_scalars"]
         t = O.Turbine(xloc=0.0, yloc=0.0, height=0.0, dia=float(dia), thk=0.0, Ct_prime=float(ct), u_d_T=float(udt))
         t.nodes, t.ind, t.nhat, t.M = d[f"farm{i}_nodes"].copy(), d[f"farm{i}_ind"].copy(), (float(n1), float(n2), float(n3)), float(M)
+        if meta.get("use_rotation"):
+            t.ind_t, t.e_theta = d[f"farm{i}_ind_t"].copy(), d[f"farm{i}_e_theta"].copy()
         farm.append(t)
     return farm
 
 
-def test_oracle_turbines_match_reference_sources():
+TURBINE_FIXTURES = ["ref_turbines_32x32x8", "ref_turbines_rot_32x32x8"]     # the second: use_rotation (turbines.f90:607-615)
+
+
+def rotation_kw(meta):
+    return dict(use_rotation=bool(meta.get("use_rotation", False)), tip_speed_ratio=float(meta.get("tip_speed_ratio", 7.0)))
+
+
+@pytest.mark.parametrize("fixture", TURBINE_FIXTURES)
+def test_oracle_turbines_match_reference_sources(fixture):
     """turbines_forcing (turbines.f90:465-638) + forcing_applied + main.f90:263-267 as the reference wrote them vs the
     oracle: force fields bit for bit, disk velocities and thrust, two core steps."""
-    d, meta, p = load("ref_turbines_32x32x8")
+    d, meta, p = load(fixture)
     sp = O.Spectral(p)
     s = O.State(p)
     s.u, s.v, s.w = d["u0"].copy(), d["v0"].copy(), d["w0"].copy()
@@ -299,7 +309,7 @@ def test_oracle_turbines_match_reference_sources():
     n = meta["nsteps"]
     for it in range(1, n + 1):
         O.step(s, sp, O.LocalComm(), mode="core", first_step=(it == 1),
-               turbines=dict(farm=farm, eps=meta["eps"], adm_correction=meta["adm_correction"]))
+               turbines=dict(farm=farm, eps=meta["eps"], adm_correction=meta["adm_correction"], **rotation_kw(meta)))
     for name in ("fxa", "fya", "fza"):
         ref = d[f"{name}_{n}"]
         assert np.count_nonzero(ref[1:p.nz, :, :p.nx]) > 100
@@ -309,13 +319,13 @@ def test_oracle_turbines_match_reference_sources():
         assert rel(valid(p, name, getattr(s, name)), valid(p, name, d[f"{name}_{n}"])) <= 1e-13, name
 
 
-def run_core_on_turbine_fixture(core):
-    d, meta, p = load("ref_turbines_32x32x8")
+def run_core_on_turbine_fixture(core, fixture):
+    d, meta, p = load(fixture)
     for n in ("u", "v", "w"):
         core.upload(n, d[n + "0"])
     for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
         core.upload(n, np.zeros(core.dims.shape))
-    core.turbines_init(farm_from_fixture(d, meta), adm_correction=meta["adm_correction"])
+    core.turbines_init(farm_from_fixture(d, meta), adm_correction=meta["adm_correction"], **rotation_kw(meta))
     n = meta["nsteps"]
     for it in range(1, n + 1):
         core.step(**step_kwargs_pre_dyn(p, it - 1, "core"), turbines=True, turbines_eps=meta["eps"])
@@ -328,20 +338,22 @@ def run_core_on_turbine_fixture(core):
 
 
 @pytest.mark.gpu
-def test_cuda_turbines_match_reference_sources():
-    _, _, p = load("ref_turbines_32x32x8")
-    worst = run_core_on_turbine_fixture(lesgo_b200.Core(make_dims(p, device=0)))
+@pytest.mark.parametrize("fixture", TURBINE_FIXTURES)
+def test_cuda_turbines_match_reference_sources(fixture):
+    _, _, p = load(fixture)
+    worst = run_core_on_turbine_fixture(lesgo_b200.Core(make_dims(p, device=0)), fixture)
     print({k: f"{v:.1e}" for k, v in worst.items()})
     assert max(worst.values()) <= 1e-12, worst
 
 
-def test_kernel_logic_turbines_match_reference_sources():
+@pytest.mark.parametrize("fixture", TURBINE_FIXTURES)
+def test_kernel_logic_turbines_match_reference_sources(fixture):
     import shutil
     if shutil.which("g++") is None:
         pytest.skip("needs g++")
     from helpers import emul_library
-    _, _, p = load("ref_turbines_32x32x8")
-    worst = run_core_on_turbine_fixture(lesgo_b200.Core(make_dims(p), lib=emul_library()))
+    _, _, p = load(fixture)
+    worst = run_core_on_turbine_fixture(lesgo_b200.Core(make_dims(p), lib=emul_library()), fixture)
     assert max(worst.values()) <= 1e-12, worst
 
 

@@ -647,6 +647,34 @@ LG_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"
 LG_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #endif
 
+// Bulk asynchronous copies (the TMA engine's 1-D form, cp.async.bulk -> UBLKCP) of whole contiguous rows into
+// shared memory, completion counted in bytes on an mbarrier: one thread issues, everybody waits on the phase parity.
+// src, dst and bytes must be multiples of 16.
+#ifndef LESGO_EMUL
+LG_D void mbar_init(unsigned long long* bar, unsigned count) {
+    const unsigned a = unsigned(__cvta_generic_to_shared(bar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+LG_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    const unsigned a = unsigned(__cvta_generic_to_shared(bar));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+LG_D void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    const unsigned d = unsigned(__cvta_generic_to_shared(dst)), a = unsigned(__cvta_generic_to_shared(bar));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(a) : "memory");
+}
+LG_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = unsigned(__cvta_generic_to_shared(bar));
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+#endif
+
 // length of the concatenated stage-twiddle table of Plan<N> and its (R1..R4) for the host
 struct PlanDesc { int n, r[4], twlen; };
 template <int N> inline PlanDesc plan_desc() {

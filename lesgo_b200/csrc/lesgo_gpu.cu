@@ -2284,6 +2284,16 @@ int lesgo_gpu_comm_p2p_import(lesgo_gpu_ctx* c, const void* blobs) {
         // LESGO_P2P_FLAGS=0: keep the one-double NCCL all-reduce as the barrier of the peer-memory transposes
         const char* e = std::getenv("LESGO_P2P_FLAGS");
         c->p2p_flags_on = !(e && e[0] == '0');
+#ifndef LESGO_EMUL
+        // The flag barrier is a kernel that spins until every peer's barrier kernel has run, which needs the peers'
+        // kernels to be able to run WHILE it spins.  That holds with one rank per GPU.  Ranks that share a device
+        // (the single-device transport of the tests) also share its few hardware launch queues, where a peer's
+        // pending kernels can sit behind the spinning one: there the host-ordered barrier of the transport is used.
+        // (decided from the blobs every rank holds, so all ranks decide alike)
+        for (int q = 0; q < c->d.nproc; ++q)
+            for (int r = q + 1; r < c->d.nproc; ++r)
+                if (b[q].pid == b[r].pid && b[q].device == b[r].device) c->p2p_flags_on = false;   // threads of one process on one GPU
+#endif
     }
     return 0;
 }

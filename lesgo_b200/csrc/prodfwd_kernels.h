@@ -34,6 +34,15 @@ struct ProdArgs {
 #ifndef LG_PROD2_THR
 #define LG_PROD2_THR 96
 #endif
+// LG_PROD_TMA = 1: the six physical rows of a plane are fetched by bulk asynchronous copies (cp.async.bulk, one 6 KB
+// row each, issued by one thread, completion counted on an mbarrier) instead of 14 cp.async per thread.
+#ifndef LG_PROD_TMA
+#define LG_PROD_TMA 1
+#endif
+#ifdef LESGO_EMUL
+#undef LG_PROD_TMA
+#define LG_PROD_TMA 0
+#endif
 template <int NX2> struct ProdCfg {
     static constexpr int M = NX2 / 2;
     static constexpr int NC = NX2 / 3;           // nx/2 spectral columns kept
@@ -65,6 +74,12 @@ k_prodfwd(const __grid_constant__ ProdArgs a, const cplx* __restrict__ Wg, const
     cplx* Wh = W + C::TWL;
     load_table(W, Wg + C::TWOFF, C::TWL);
     load_table(Wh, Whg, C::NWH);
+#if LG_PROD_TMA
+    __shared__ __align__(8) unsigned long long mbar;
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    unsigned phase = 0;
+    bool pending = false;
+#endif
     __syncthreads();
 
     const int nwork = a.ny2 * a.nchunks;
@@ -85,6 +100,18 @@ k_prodfwd(const __grid_constant__ ProdArgs a, const cplx* __restrict__ Wg, const
         auto issue = [&](int k) {
             const int mask = mask_of(k);
             const bool stash = sbchunk && k == ka - 1;
+#if LG_PROD_TMA
+            pending = mask != 0;
+            if (threadIdx.x == 0 && mask != 0) {
+                mbar_expect_tx(&mbar, unsigned(__popc(unsigned(mask))) * unsigned(M * sizeof(cplx)));
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    if (!((mask >> r) & 1)) continue;
+                    const double* srow = (stash ? a.src[2] + 2 * a.splane : a.src[r] + long(k) * a.splane) + syoff;
+                    bulk_g2s(stg + r * M, srow, unsigned(M * sizeof(cplx)), &mbar);
+                }
+            }
+#else
             for (int i = threadIdx.x; i < 6 * M; i += NTHR) {
                 const int r = i / M, cidx = i - r * M;
                 if (!((mask >> r) & 1)) continue;
@@ -92,6 +119,7 @@ k_prodfwd(const __grid_constant__ ProdArgs a, const cplx* __restrict__ Wg, const
                 cp_async16(stg + i, srow + 2 * cidx);
             }
             cp_async_commit();
+#endif
         };
 
         cplx up[EPT], vp[EPT], px[EPT], py[EPT];          // carried from plane to plane
@@ -101,7 +129,11 @@ k_prodfwd(const __grid_constant__ ProdArgs a, const cplx* __restrict__ Wg, const
         bool noA = false;
         for (int k = ka - 1; k <= kb; ++k) {
             const int mask = mask_of(k);
+#if LG_PROD_TMA
+            if (pending) { mbar_wait(&mbar, phase); phase ^= 1u; }
+#else
             cp_async_wait_all();
+#endif
             __syncthreads();
             const bool main = k >= ka && k < kb;
             const bool out_prev = k > ka;

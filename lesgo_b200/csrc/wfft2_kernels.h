@@ -77,6 +77,11 @@ k_xinv_w2(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int
     cplx* Wh = sm + C::WPB * C::WBUF;
     load_table(Wh, Whg, C::NWH);
     for (int m = j; m < C::STG; m += 16) ST[m] = make_double2(0.0, 0.0);     // columns >= ncol stay zero
+#if LG_XW_TMA
+    __shared__ __align__(8) unsigned long long mbar[C::WPB];
+    if (lane == 0) mbar_init(&mbar[wib], 1);
+    unsigned phase = 0;
+#endif
     // stage-2 twiddles W_M^{j r} depend only on the lane: r = 1..7 and r = 8, 16 in registers for the whole loop
     cplx lo[8], hi[C::NHI + 1];
 #pragma unroll
@@ -91,6 +96,21 @@ k_xinv_w2(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int
     const unsigned wstride = gridDim.x * C::WPB;
     const int nc = in.ncol < M + 1 ? in.ncol : M + 1;
     auto prefetch = [&](unsigned work) {
+#if LG_XW_TMA
+        // lane 0 fetches both rows of the pair; a pair past the end or an empty row still completes the phase
+        if (lane == 0 && work < nwork) {
+            const unsigned ra = (work / unsigned(nfields)) * 2;
+            const int pf = int(work % unsigned(nfields));
+            const unsigned nlive = (ra < nrows ? 1u : 0u) + (ra + 1 < nrows ? 1u : 0u);
+            mbar_expect_tx(&mbar[wib], nlive * unsigned(nc) * unsigned(sizeof(cplx)));
+            for (unsigned ff = 0; ff < 2 && nc > 0; ++ff) {
+                const unsigned r = ra + ff;
+                if (r >= nrows) continue;
+                const double* srow = in.src[pf] + poff(k0 + int(r / unsigned(ny)), in.plane, in.ring) + long(r % unsigned(ny)) * in.row;
+                bulk_g2s(sm + wib * C::WBUF + ff * (C::SLOTS + C::STG) + C::SLOTS, srow, unsigned(nc) * unsigned(sizeof(cplx)), &mbar[wib]);
+            }
+        }
+#else
         if (work < nwork) {
             const unsigned r = (work / unsigned(nfields)) * 2 + f;
             if (r < nrows) {
@@ -100,6 +120,7 @@ k_xinv_w2(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int
             }
         }
         cp_async_commit();
+#endif
     };
     prefetch(blockIdx.x * C::WPB + wib);
     for (unsigned work = blockIdx.x * C::WPB + wib; work < nwork; work += wstride) {
@@ -107,7 +128,12 @@ k_xinv_w2(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int
         const unsigned r0 = (work / unsigned(nfields)) * 2 + f;
         const bool live = r0 < nrows;
         const int k = k0 + int(r0 / unsigned(ny)), y = int(r0 % unsigned(ny));
+#if LG_XW_TMA
+        mbar_wait(&mbar[wib], phase);
+        phase ^= 1u;
+#else
         cp_async_wait_all();
+#endif
         LG_SYNCWARP();
         // ---- stage 1: radix R1 on Z'_{it + T1 r}, no twiddles; slot R1*it + r (padded: (R1+1)*it + r) --------
 #pragma unroll

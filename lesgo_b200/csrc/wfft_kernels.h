@@ -8,6 +8,17 @@
 #include "fft_kernels.h"
 #include "wfft.h"
 
+// LG_XW_TMA = 1: a staged spectral row arrives by ONE bulk asynchronous copy (cp.async.bulk, completion counted on the
+// warp's mbarrier) instead of 16-byte cp.async pieces issued by every lane
+#ifndef LG_XW_TMA
+#define LG_XW_TMA 1
+#endif
+#ifdef LESGO_EMUL
+#undef LG_XW_TMA
+#define LG_XW_TMA 0
+#endif
+
+
 namespace lg {
 
 #ifndef LG_XW_TWREG
@@ -208,6 +219,12 @@ k_xinv_w(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int 
     __syncthreads();
     WarpFft<M, NF, true, C::INPLACE, C::TWREG> fft;
     fft.init(W, lane);
+#if LG_XW_TMA
+    __shared__ __align__(8) unsigned long long mbar[C::WPB];     // PREF: one per warp (wfft2_kernels.h: LG_XW_TMA)
+    if (C::PREF && lane == 0) mbar_init(&mbar[wib], 1);
+    unsigned phase = 0;
+    __syncthreads();
+#endif
 
     const unsigned nrows = unsigned(ny) * unsigned(nplanes);
     const unsigned ntiles = (nrows + NF - 1) / NF;
@@ -216,6 +233,16 @@ k_xinv_w(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int 
     cplx* ST = A + (C::INPLACE ? 1 : 2) * NF * SL;           // PREF: this warp's staged spectral row
     auto prefetch = [&](unsigned work) {
         if constexpr (C::PREF) {
+#if LG_XW_TMA
+            if (lane == 0 && work < nwork) {                 // one bulk copy of the row, counted on the warp's mbarrier
+                const int pf = int(work % unsigned(nfields));
+                const unsigned r = work / unsigned(nfields);
+                const double* srow = in.src[pf] + poff(k0 + int(r / unsigned(ny)), in.plane, in.ring) + long(r % unsigned(ny)) * in.row;
+                const int nc = in.ncol < M + 1 ? in.ncol : M + 1;
+                mbar_expect_tx(&mbar[wib], unsigned(nc > 0 ? nc : 0) * unsigned(sizeof(cplx)));
+                if (nc > 0) bulk_g2s(ST, srow, unsigned(nc) * unsigned(sizeof(cplx)), &mbar[wib]);
+            }
+#else
             if (work < nwork) {
                 const int pf = int(work % unsigned(nfields));
                 const unsigned r = work / unsigned(nfields);
@@ -224,13 +251,18 @@ k_xinv_w(const __grid_constant__ XiSrc in, const __grid_constant__ Epi epi, int 
                 for (int m = lane; m < nc; m += 32) cp_async16(ST + m, srow + 2 * m);
             }
             cp_async_commit();
+#endif
         }
     };
     prefetch(blockIdx.x * C::WPB + wib);
     for (unsigned work = blockIdx.x * C::WPB + wib; work < nwork; work += wstride) {
         const int fld = int(work % unsigned(nfields));
         rows.set(lane, (work / unsigned(nfields)) * NF, nrows, ny, k0);
+#if LG_XW_TMA
+        if constexpr (C::PREF) { mbar_wait(&mbar[wib], phase); phase ^= 1u; LG_SYNCWARP(); }
+#else
         if constexpr (C::PREF) { cp_async_wait_all(); LG_SYNCWARP(); }
+#endif
         // tangle: Z'_m = E'_m + i O'_m,  E' = X_m + conj(X_{M-m}),  O' = (X_m - conj(X_{M-m})) conj(W_N^m)
         constexpr int NPM = M / 2 + 1;
         constexpr int ITER = (NF * NPM + 31) / 32;

@@ -144,7 +144,8 @@ def test_emul_multirank_turbines(nproc):
     """Disks spanning several z slabs: per-rank node lists, all-reduced disk velocities, force halos."""
     from helpers import check_multirank_steps
     kw = dict(nx=32, ny=16, Nz=12, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False)
-    out = check_multirank_steps(emul_library(), kw, nproc, nsteps=2, mode="full", turbines=True, tavg=True)
+    out = check_multirank_steps(emul_library(), kw, nproc, nsteps=2, mode="full", turbines=True, tavg=True,
+                                rotation=6.0 if nproc == 4 else None)      # 4 ranks: the ADM with rotation
     print(out)
 
 

@@ -50,6 +50,17 @@ def test_one_step_dns_couette_128x128x64():
     print(out)
 
 
+@pytest.mark.parametrize("nx,ny,Nz", [(96, 80, 6), (384, 320, 4), (160, 192, 5)])
+def test_steps_on_mixed_radix_grids(nx, ny, Nz):
+    """The 3 * 2**a and 5 * 2**a transform lengths (sizes.h) through the whole step -- convec's 3/2 grids are then
+    144 x 120, 576 x 480, 240 x 288 -- core and full (Smagorinsky, wall model) modes, two steps."""
+    p = O.Params(nx=nx, ny=ny, Nz=Nz, lbc_mom=1, ubc_mom=1, utop=0.5, ubot=-0.5, L_x=4.0, L_y=3.0, use_mean_p_force=True,
+                 mean_p_force_x=1.0)
+    print(check_steps(core_for(p), p, nsteps=2, tol=1e-11))
+    p = O.Params(nx=nx, ny=ny, Nz=Nz, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False, L_x=4.0, L_y=3.0)
+    print(check_steps(core_for(p), p, nsteps=2, tol=1e-11, mode="full"))
+
+
 def test_ten_steps_1e9():
     p = O.Params(nx=64, ny=64, Nz=32, lbc_mom=1, ubc_mom=1, utop=1.0, ubot=-1.0,
                  use_mean_p_force=True, mean_p_force_x=1.0)
@@ -274,7 +285,7 @@ def test_many_slabs_on_one_gpu_full_models():
                                 device_of=lambda coord: 0))
     kw = dict(nx=64, ny=64, Nz=32, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False)
     print(check_multirank_steps(lesgo_b200.load_library(), kw, 4, nsteps=2, tol=1e-11, mode="full", turbines=True, tavg=True,
-                                local=True, p2p=True, device_of=lambda coord: 0))
+                                local=True, p2p=True, device_of=lambda coord: 0, rotation=6.0))
 
 
 def test_eight_slabs_512x512_planes_on_one_gpu():

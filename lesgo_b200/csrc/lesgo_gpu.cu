@@ -90,6 +90,7 @@ struct lesgo_gpu_ctx {
     bool turb_on = false, turb_fz = false;
     int turb_adm = 0;
     std::vector<int> turb_nodes;           // prefix offsets of the disks' node lists (host copy of TurbSet::start)
+    std::vector<void*> turb_allocs;        // the disks' device arrays: released when the disks are handed over again
     double* turb_fzuv = nullptr;           // fza before interp_to_w_grid (uv nodes)
     int sgs_cfg = -1;                      // (sgs_model, ifilter) the tables above were built for
     double* fields[LG_NFIELDS] = {nullptr};
@@ -1376,10 +1377,10 @@ int turbines_forcing(lesgo_gpu_ctx* c, double eps) {
 }
 
 template <class T>
-int upload_vec(lesgo_gpu_ctx* c, const T** dst, const std::vector<T>& h) {
+int upload_vec(lesgo_gpu_ctx* c, const T** dst, const std::vector<T>& h, std::vector<void*>* owner = nullptr) {
     void* p = nullptr;
     CK(cudaMalloc(&p, (h.empty() ? 1 : h.size()) * sizeof(T)));
-    c->allocs.push_back(p);
+    (owner ? *owner : c->allocs).push_back(p);
     if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
     *dst = static_cast<const T*>(p);
     return 0;
@@ -1388,6 +1389,14 @@ int upload_vec(lesgo_gpu_ctx* c, const T** dst, const std::vector<T>& h) {
 int turbines_init(lesgo_gpu_ctx* c, int nloc, const lesgo_gpu_turbine* t, int adm) {
     if (nloc < 0 || (nloc > 0 && !t)) return c->fail("lesgo_gpu_turbines_init: bad arguments");
     const int nz = c->nz;
+    // a re-meshed farm (dyn_theta1/2: turbines.f90:506-515 calls turbines_nodes every step) replaces the old arrays
+    if (!c->turb_allocs.empty()) {
+        CK(cudaStreamSynchronize(c->stream));
+        for (void* q : c->turb_allocs) cudaFree(q);
+        c->turb_allocs.clear();
+        c->turb_on = false;
+    }
+    std::vector<void*>* TA = &c->turb_allocs;
     std::vector<int> start(nloc + 1, 0), owner;
     std::vector<long> off;
     std::vector<double> ind, nhat(3 * size_t(nloc)), Ct(nloc), dia(nloc), M(nloc), udT(nloc);
@@ -1420,14 +1429,14 @@ int turbines_init(lesgo_gpu_ctx* c, int nloc, const lesgo_gpu_turbine* t, int ad
     TurbSet ts;
     ts.nloc = nloc;
     const double *d_udT = nullptr, *d_zero = nullptr;
-    if (upload_vec(c, &ts.start, start) || upload_vec(c, &ts.off, off) || upload_vec(c, &ts.ind, ind) ||
-        upload_vec(c, &ts.owner, owner) || upload_vec(c, &ts.nhat, nhat) || upload_vec(c, &ts.Ct_prime, Ct) ||
-        upload_vec(c, &ts.dia, dia) || upload_vec(c, &ts.M, M) || upload_vec(c, &d_udT, udT)) return 1;
+    if (upload_vec(c, &ts.start, start, TA) || upload_vec(c, &ts.off, off, TA) || upload_vec(c, &ts.ind, ind, TA) ||
+        upload_vec(c, &ts.owner, owner, TA) || upload_vec(c, &ts.nhat, nhat, TA) || upload_vec(c, &ts.Ct_prime, Ct, TA) ||
+        upload_vec(c, &ts.dia, dia, TA) || upload_vec(c, &ts.M, M, TA) || upload_vec(c, &d_udT, udT, TA)) return 1;
     std::vector<double> z(nloc, 0.0);
-    if (upload_vec(c, &d_zero, z)) return 1;
+    if (upload_vec(c, &d_zero, z, TA)) return 1;
     ts.u_d_T = const_cast<double*>(d_udT);
     ts.u_d = const_cast<double*>(d_zero);
-    if (upload_vec(c, &d_zero, z)) return 1;
+    if (upload_vec(c, &d_zero, z, TA)) return 1;
     ts.f_n = const_cast<double*>(d_zero);
     ts.ind_t = nullptr; ts.e_theta = nullptr; ts.tip_speed_ratio = 1.0;
     c->turb_nodes.assign(start.begin(), start.end());
@@ -1621,6 +1630,7 @@ int lesgo_gpu_destroy(lesgo_gpu_ctx* c) {
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
 #endif
     for (void* p : c->allocs) cudaFree(p);
+    for (void* p : c->turb_allocs) cudaFree(p);
     for (double* p : c->staging) if (p) cudaFree(p);
     if (c->red_host) cudaFreeHost(c->red_host);
     if (c->s_in) { cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out); }
@@ -2100,7 +2110,7 @@ int lesgo_gpu_turbines_rotation(lesgo_gpu_ctx* c, int nloc, const double* const*
         it.insert(it.end(), ind_t[s], ind_t[s] + n);
         et.insert(et.end(), e_theta[s], e_theta[s] + 3 * size_t(n));
     }
-    if (upload_vec(c, &c->turb.ind_t, it) || upload_vec(c, &c->turb.e_theta, et)) return 1;
+    if (upload_vec(c, &c->turb.ind_t, it, &c->turb_allocs) || upload_vec(c, &c->turb.e_theta, et, &c->turb_allocs)) return 1;
     c->turb.tip_speed_ratio = tip_speed_ratio;
     c->turb_fz = true;                     // e_theta has a z component: fza needs the interpolation to w nodes
     CK(cudaStreamSynchronize(c->stream));

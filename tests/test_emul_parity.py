@@ -161,6 +161,22 @@ def test_emul_turbines_errors():
     bad.ind = np.array([1.0])
     with pytest.raises(lesgo_b200.LibraryError, match="node outside"):
         c.turbines_init([bad])
+    # use_rotation: the per-node arrays must follow an init call and match it
+    import ctypes as C
+    one = (C.c_void_p * 1)()
+    with pytest.raises(lesgo_b200.LibraryError, match="turbines_init first"):
+        c._ck(c.lib.turbines_rotation(c._ctx, 1, one, one, 7.0), "turbines_rotation")
+    good = O.Turbine(xloc=1.0, yloc=1.0, height=0.5, dia=0.5, thk=0.1)
+    good.nodes = np.array([[1, 1, 1], [2, 1, 1]], dtype=np.int32)
+    good.ind = np.array([0.5, 0.5])
+    c.turbines_init([good])
+    with pytest.raises(lesgo_b200.LibraryError, match="must match"):
+        c._ck(c.lib.turbines_rotation(c._ctx, 2, one, one, 7.0), "turbines_rotation")
+    good.ind_t, good.e_theta = np.array([0.1, 0.2]), np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    with pytest.raises(lesgo_b200.LibraryError, match="tip_speed_ratio"):
+        c.turbines_init([good], use_rotation=True, tip_speed_ratio=0.0)
+    c.turbines_init([good], use_rotation=True, tip_speed_ratio=7.0)
+    c.turbines_init([good])                  # handing the farm over again releases the old arrays and rotation
 
 
 @pytest.mark.parametrize("cfg,turbines", [

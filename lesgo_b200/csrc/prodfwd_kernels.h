@@ -74,6 +74,7 @@ k_prodfwd(const __grid_constant__ ProdArgs a, const cplx* __restrict__ Wg, const
     cplx* Wh = W + C::TWL;
     load_table(W, Wg + C::TWOFF, C::TWL);
     load_table(Wh, Whg, C::NWH);
+    __shared__ double* s_drow[3];
 #if LG_PROD_TMA
     __shared__ __align__(8) unsigned long long mbar;
     if (threadIdx.x == 0) mbar_init(&mbar, 1);
@@ -135,6 +136,10 @@ k_prodfwd(const __grid_constant__ ProdArgs a, const cplx* __restrict__ Wg, const
             cp_async_wait_all();
 #endif
             __syncthreads();
+            // the three output rows of this step are the same for every thread and item of the untangling loop below:
+            // formed once here (the loop read them back per item otherwise, ~35 integer instructions each time)
+            if (threadIdx.x < 3 && k >= ka)
+                s_drow[threadIdx.x] = a.dst[threadIdx.x] + long(threadIdx.x < 2 ? k - 1 : k) * a.dplane + dyoff;
             const bool main = k >= ka && k < kb;
             const bool out_prev = k > ka;
             const bool sb = a.bottom && k == 1;
@@ -206,7 +211,7 @@ k_prodfwd(const __grid_constant__ ProdArgs a, const cplx* __restrict__ Wg, const
                 const int f = it / NPM, m = it - f * NPM;
                 if (f < 2 ? !out_prev : !main) continue;
                 const cplx* X = rows + f * SL;
-                double* drow = a.dst[f] + long(f < 2 ? k - 1 : k) * a.dplane + dyoff;
+                double* drow = s_drow[f];
                 const cplx za = X[spad(m)];
                 if (m == 0) {
                     *reinterpret_cast<cplx*>(drow) = make_double2(za.x + za.y, 0.0);

@@ -119,6 +119,32 @@ def run_turbine_case(name="ref_turbines_32x32x8", nsteps=2, eps=0.3, use_rotatio
     print(f"{name}: done, {R.I.nstmt} reference statements")
 
 
+def run_filter_kernels(name="ref_filter_kernels_16x32"):
+    """test_filter_init (test_filtermodule.f90:38-123) for the three filter types: the kernels G_test (2 Delta) and,
+    with sgs_model 5, G_test_test (4 Delta) as the reference builds them, plus one plane filtered with each."""
+    from helpers import random_field
+    out = {}
+    kw = dict(nx=16, ny=32, Nz=4, L_x=4.0, L_y=3.0, sgs=True, sgs_model=5)
+    for ifilter in (1, 2, 3):
+        p = O.Params(ifilter=ifilter, **kw)
+        R = refrun.Reference(p, files=refrun.LASD_FILES)
+        I = R.I
+        out[f"G_test_{ifilter}"] = np.asarray(I.get("test_filtermodule", "g_test").a).T.copy()
+        out[f"G_test_test_{ifilter}"] = np.asarray(I.get("test_filtermodule", "g_test_test").a).T.copy()
+        f = random_field(p, 7)
+        pl = refrun.F.FArray(np.asfortranarray(f[2].T.copy()), (1, 1))
+        I.call("test_filter", pl, module="test_filtermodule")
+        out[f"filtered_{ifilter}"] = pl.a.T.copy()
+        pl = refrun.F.FArray(np.asfortranarray(f[2].T.copy()), (1, 1))
+        I.call("test_test_filter", pl, module="test_filtermodule")
+        out[f"filtered2_{ifilter}"] = pl.a.T.copy()
+        out["f"] = f
+    meta = dict(kw=kw, made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py")
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: done")
+
+
 def run_mpi_case(name="ref_mpi4_full_16x16x8", nproc=4, nsteps=2, seed=51):
     """The reference's MPI code path from the reference text: FOUR ranks (one interpreter per rank, in-process
     mailboxes for mpi_sendrecv / send / recv / allreduce): mpi_sync_real_array halos (mpi_defs.f90:167-264), the
@@ -307,3 +333,5 @@ if __name__ == "__main__":
         run_turbine_case(name="ref_turbines_rot_32x32x8", use_rotation=True, tip_speed_ratio=5.5)
     if not only or "mpi" in only:
         run_mpi_case()
+    if not only or "filters" in only:
+        run_filter_kernels()

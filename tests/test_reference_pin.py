@@ -23,7 +23,7 @@ from helpers import O, make_dims, rel, step_kwargs_pre_dyn
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STEP_FIXTURES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "ref_*.npz"))
-                       if not any(t in f for t in ("routines", "lasd", "tavg", "turbines", "mpi")))
+                       if not any(t in f for t in ("routines", "lasd", "tavg", "turbines", "mpi", "filter_kernels")))
 LASD_FIELDS = ("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2")
 FIELDS = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")
 
@@ -41,7 +41,8 @@ def valid(p, n, a):
 
 def test_fixtures_exist():
     assert len(STEP_FIXTURES) >= 5 and os.path.exists(os.path.join(GOLD, "ref_routines_16x16x6.npz"))
-    for f in ("ref_full_lasd_16x16x6", "ref_tavg_16x16x6", "ref_turbines_32x32x8", "ref_turbines_rot_32x32x8", "ref_mpi4_full_16x16x8"):
+    for f in ("ref_full_lasd_16x16x6", "ref_tavg_16x16x6", "ref_turbines_32x32x8", "ref_turbines_rot_32x32x8", "ref_mpi4_full_16x16x8",
+              "ref_filter_kernels_16x32"):
         assert os.path.exists(os.path.join(GOLD, f + ".npz")), f
 
 
@@ -355,6 +356,53 @@ def test_kernel_logic_turbines_match_reference_sources(fixture):
     _, _, p = load(fixture)
     worst = run_core_on_turbine_fixture(lesgo_b200.Core(make_dims(p), lib=emul_library()), fixture)
     assert max(worst.values()) <= 1e-12, worst
+
+
+def load_filters():
+    d = np.load(os.path.join(GOLD, "ref_filter_kernels_16x32.npz"))
+    return d, ast.literal_eval(str(d["meta"]))
+
+
+@pytest.mark.parametrize("ifilter", [1, 2, 3])
+def test_oracle_filter_kernels_match_reference_sources(ifilter):
+    """test_filter_init (test_filtermodule.f90:38-123) as the reference builds G_test and G_test_test for the sharp
+    cut-off, Gaussian and top-hat filters vs the oracle's kernels, and one plane through test_filter / test_test_filter."""
+    d, meta = load_filters()
+    p = O.Params(ifilter=ifilter, **meta["kw"])
+    sp = O.Spectral(p)
+    for alpha, gname, fname in ((2.0, "G_test", "filtered"), (4.0, "G_test_test", "filtered2")):
+        G = O.test_filter_kernel(sp, alpha=alpha)
+        ref = d[f"{gname}_{ifilter}"]
+        assert np.count_nonzero(ref) > 5 and rel(G, ref) <= 1e-15, (ifilter, gname)
+        out = O.test_filter(d["f"][2:3], sp, G)[0]
+        assert rel(out[:, :p.nx], d[f"{fname}_{ifilter}"][:, :p.nx]) <= 1e-14, (ifilter, fname)
+
+
+def run_core_on_filter_fixture(core_of):
+    """lesgo_gpu_test_filter with the reference's own kernels vs the planes the reference filtered."""
+    d, meta = load_filters()
+    worst = 0.0
+    for ifilter in (1, 2, 3):
+        p = O.Params(ifilter=ifilter, **meta["kw"])
+        core = core_of(p)
+        for gname, fname in (("G_test", "filtered"), ("G_test_test", "filtered2")):
+            f = np.ascontiguousarray(d["f"][2:3].copy())
+            core.test_filter(f, np.ascontiguousarray(d[f"{gname}_{ifilter}"]))
+            worst = max(worst, rel(f[0][:, :p.nx], d[f"{fname}_{ifilter}"][:, :p.nx]))
+    return worst
+
+
+@pytest.mark.gpu
+def test_cuda_test_filter_matches_reference_sources():
+    assert run_core_on_filter_fixture(lambda p: lesgo_b200.Core(make_dims(p, device=0))) <= 1e-13
+
+
+def test_kernel_logic_test_filter_matches_reference_sources():
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    from helpers import emul_library
+    assert run_core_on_filter_fixture(lambda p: lesgo_b200.Core(make_dims(p), lib=emul_library())) <= 1e-13
 
 
 def load_mpi():

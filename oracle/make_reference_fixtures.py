@@ -119,6 +119,40 @@ def run_turbine_case(name="ref_turbines_32x32x8", nsteps=2, eps=0.3, use_rotatio
     print(f"{name}: done, {R.I.nstmt} reference statements")
 
 
+def run_mpi_lasd_case(name="ref_mpi2_lasd_16x16x8", nproc=2, nsteps=4, seed=53):
+    """Rows (f)-2 through the reference's MPI code path: TWO ranks, sgs_model 5 with DYN_init = cs_count = 2, so that
+    interpolag_Sdep's halo exchange of F_LM ... F_NN (interpolag_Sdep.f90:244-249), lagrange_Sdep's (:417-420), the
+    txz / tyz / tzz halos of sgs_stag and main.f90 and the wall model on rank 0 only all run from the reference text;
+    gathered to global fields."""
+    kw = dict(nx=16, ny=16, Nz=8, L_x=4.0, L_y=3.0, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=5, molec=False, dt=2e-3)
+    pg = O.Params(nproc=1, **kw)
+    ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=seed, amp=0.3, L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+
+    def fn(ref, r):
+        for n, g in (("u", ug), ("v", vg), ("w", wg)):
+            ref.put(n, O.scatter_slab(g, ref.p))
+        for it in range(1, nsteps + 1):
+            ref.step(it, mode="full")
+        o = {n: ref.get(n) for n in STEP_FIELDS}
+        for n in LASD_FIELDS:
+            o[n] = ref.get(n.lower(), module="sgs_param")
+        o["nstmt"] = ref.I.nstmt
+        return o
+
+    t0 = time.time()
+    res = refrun.run_ranks(kw, nproc, fn, files=refrun.LASD_FILES, dyn_init=2, cs_count=2)
+    ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
+    out = {}
+    for n in STEP_FIELDS + LASD_FIELDS:
+        out[n] = O.gather_slabs([res[r][n] for r in range(nproc)], ps, top_extra=n in ("w", "RHSz", "p") + LASD_FIELDS)
+    meta = dict(kw=kw, nproc=nproc, nsteps=nsteps, seed=seed, amp=0.3, mode="full", dyn_init=2, cs_count=2,
+                made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py, 2 ranks",
+                statements=int(sum(res[r]["nstmt"] for r in range(nproc))))
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: done, {meta['statements']} reference statements on {nproc} ranks, {time.time() - t0:.1f} s")
+
+
 def run_filter_kernels(name="ref_filter_kernels_16x32"):
     """test_filter_init (test_filtermodule.f90:38-123) for the three filter types: the kernels G_test (2 Delta) and,
     with sgs_model 5, G_test_test (4 Delta) as the reference builds them, plus one plane filtered with each."""
@@ -335,3 +369,5 @@ if __name__ == "__main__":
         run_mpi_case()
     if not only or "filters" in only:
         run_filter_kernels()
+    if not only or "mpi_lasd" in only:
+        run_mpi_lasd_case()

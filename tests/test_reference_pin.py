@@ -42,7 +42,7 @@ def valid(p, n, a):
 def test_fixtures_exist():
     assert len(STEP_FIXTURES) >= 5 and os.path.exists(os.path.join(GOLD, "ref_routines_16x16x6.npz"))
     for f in ("ref_full_lasd_16x16x6", "ref_tavg_16x16x6", "ref_turbines_32x32x8", "ref_turbines_rot_32x32x8", "ref_mpi4_full_16x16x8",
-              "ref_filter_kernels_16x32"):
+              "ref_filter_kernels_16x32", "ref_mpi2_lasd_16x16x8"):
         assert os.path.exists(os.path.join(GOLD, f + ".npz")), f
 
 
@@ -465,6 +465,62 @@ def test_cuda_slabs_match_reference_mpi_run(p2p):
     reference's own four-rank MPI run: halos (mpi_defs.f90:245-262), the slab <-> pencil transposes that replace the
     pipelined tridag_array.f90:85-157, the k = 0 chain (press_stag_array.f90:221-244)."""
     print(_slabs_vs_reference_mpi(lesgo_b200.load_library(), local=True, device_of=lambda coord: 0, p2p=p2p))
+
+
+def load_mpi_lasd():
+    d = np.load(os.path.join(GOLD, "ref_mpi2_lasd_16x16x8.npz"))
+    return d, ast.literal_eval(str(d["meta"]))
+
+
+def _slabs_vs_reference_mpi_lasd(lib, local, device_of=None, p2p=False):
+    """Two z-slab ranks with the Lagrangian scale-dependent model vs the reference's own two-rank MPI run of it (the F_*
+    halos of interpolag_Sdep.f90:244-249 and lagrange_Sdep.f90:417-420, the stress halos, the wall model on rank 0)."""
+    from helpers import check_multirank_steps, CS_TOL
+    d, meta = load_mpi_lasd()
+    names = FIELDS + ("Cs_opt2", "F_LM", "F_NN")
+    out = check_multirank_steps(lib, meta["kw"], meta["nproc"], nsteps=meta["nsteps"], tol=1e-11, seed=meta["seed"],
+                                mode="full", lasd=True, local=local, device_of=device_of, p2p=p2p,
+                                ref_global={n: d[n] for n in names})
+    assert all(("ref_" + n) in out for n in names)
+    return out
+
+
+def test_oracle_matches_reference_mpi_lasd_run():
+    """The reference's two-rank MPI run with sgs_model 5 (DYN_init = cs_count = 2, four steps, two model updates) vs the
+    oracle on ONE slab: velocities, pressure, right-hand sides, and the model's F_LM, F_MM, F_QN, F_NN, Cs_opt2."""
+    from helpers import lasd_schedule, CS_TOL
+    d, meta = load_mpi_lasd()
+    kw, nproc, nsteps = meta["kw"], meta["nproc"], meta["nsteps"]
+    pg = O.Params(nproc=1, **kw)
+    sp = O.Spectral(pg)
+    ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=meta["seed"], amp=meta["amp"], L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+    s = O.State(pg)
+    s.u, s.v, s.w = (O.scatter_slab(f, pg) for f in (ug, vg, wg))
+    G, G2 = O.test_filter_kernel(sp), O.test_filter_kernel(sp, alpha=4.0)
+    for it in range(nsteps):
+        sch = lasd_schedule(pg, it, cs_count=meta["cs_count"], dyn_init=meta["dyn_init"])
+        O.step(s, sp, O.LocalComm(), mode="full", first_step=(it == 0), G_test=G,
+               lasd=dict(sp=sp, G_test=G, G_test_test=G2, lagran_dt=sch["lagran_dt"], cs_init=sch["lasd_cs_init"],
+                         update=sch["lasd_update"], init_F=sch["lasd_init_F"]))
+    nzt = pg.nz_tot
+    for n in FIELDS + LASD_FIELDS:
+        top = n in ("w", "RHSz", "p") + LASD_FIELDS
+        hi = nzt if top else nzt - 1
+        e = rel(getattr(s, n)[1:hi + 1, :, :pg.nx], d[n][1:hi + 1, :, :pg.nx])
+        assert e <= (CS_TOL if n == "Cs_opt2" else 1e-12), (n, e)
+
+
+def test_kernel_logic_slabs_match_reference_mpi_lasd_run():
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    from helpers import emul_library
+    print(_slabs_vs_reference_mpi_lasd(emul_library(), local=False))
+
+
+@pytest.mark.gpu
+def test_cuda_slabs_match_reference_mpi_lasd_run():
+    print(_slabs_vs_reference_mpi_lasd(lesgo_b200.load_library(), local=True, device_of=lambda coord: 0, p2p=True))
 
 
 # ---- the CUDA path against the reference-source fixtures --------------------------------------------------------

@@ -91,6 +91,7 @@ struct lesgo_gpu_ctx {
     int turb_adm = 0;
     std::vector<int> turb_nodes;           // prefix offsets of the disks' node lists (host copy of TurbSet::start)
     std::vector<void*> turb_allocs;        // the disks' device arrays: released when the disks are handed over again
+    double cs_const = -1.0;                // value the whole Cs_opt2 field currently holds by assignment (< 0: unknown)
     double* turb_fzuv = nullptr;           // fza before interp_to_w_grid (uv nodes)
     int sgs_cfg = -1;                      // (sgs_model, ifilter) the tables above were built for
     double* fields[LG_NFIELDS] = {nullptr};
@@ -1300,6 +1301,18 @@ int sgs_and_divstress(lesgo_gpu_ctx* c, const lesgo_gpu_step_params* sp, double*
         LG_LAUNCH(k_sij_nut, dim3(grid1d(long(c->nx) * c->ny * nz)), dim3(kBlock), 0, c->stream, sa, p, c->lay(), c->nx, c->ny, 1, nz + 1);
         c->launches++;
     }
+    if (c->d.sgs && sp->sgs_model == 1) {
+        // sgs_stag_util.f90:94 assigns the whole ARRAY Cs_opt2 = Co**2 every step: tavg%compute (time_average.f90:258)
+        // and the restart file (io.f90:1204-1211) see that field.  The value is constant: written when it changes.
+        const double cs = sp->Co * sp->Co;
+        if (c->cs_const != cs) {
+            double* f = field(c, LG_CS_OPT2);
+            if (!f || fill(c, f, c->plane, 0, nz + 1, cs)) return 1;
+            c->cs_const = cs;
+        }
+    } else {
+        c->cs_const = -1.0;
+    }
     if (c->d.sgs && sp->sgs_model == 5) {
         // sgs_stag_util.f90:183-231 with the coefficient field
         if (sp->lasd_cs_init) { if (fill(c, F[LG_CS_OPT2], c->plane, 0, nz + 1, 0.03)) return 1; }
@@ -1903,6 +1916,7 @@ int lesgo_gpu_upload(lesgo_gpu_ctx* c, int id, const double* host) {
     if (!c || !host) return 1;
     double* f = field(c, id);
     if (!f) return c->fail("bad field id");
+    if (id == LG_CS_OPT2) c->cs_const = -1.0;
     CK(cudaMemcpyAsync(f, host, NFIELD * sizeof(double), cudaMemcpyDefault, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -2017,6 +2031,7 @@ int lesgo_gpu_checkpoint_write(lesgo_gpu_ctx* c, const char* fname) {
 int lesgo_gpu_checkpoint_read(lesgo_gpu_ctx* c, const char* fname) {
     ENTER(c);
     if (!c) return 1;
+    c->cs_const = -1.0;                                            // the file's Cs_opt2 replaces the field
     return checkpoint_io(c, fname, false);
 }
 

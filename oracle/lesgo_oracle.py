@@ -873,6 +873,8 @@ def sgs_stag(s, p: Params, comm, Cs_opt2_const: Optional[float] = None, lasd: Op
         if p.sgs_model == 1:
             l = _smag_length(p)
             Cs = p.Co ** 2
+            lasd_alloc(s)
+            s.Cs_opt2[...] = Cs                                                # :94, the whole array (tavg, restart file)
         else:
             l = np.full(nz + 1, p.delta)
             Cs = 0.03 if Cs_opt2_const is None else Cs_opt2_const

@@ -153,6 +153,45 @@ def run_mpi_lasd_case(name="ref_mpi2_lasd_16x16x8", nproc=2, nsteps=4, seed=53):
     print(f"{name}: done, {meta['statements']} reference statements on {nproc} ranks, {time.time() - t0:.1f} s")
 
 
+def run_mpi_tavg_case(name="ref_mpi2_tavg_16x16x8", nproc=2, nsteps=2, seed=57):
+    """Rows (f)-4 through the reference's MPI code path: tavg%compute (time_average.f90:176-320) on TWO ranks after each
+    of two full steps (Smagorinsky, wall model below, stress-free lid), so that the halos inside interp_to_uv_grid /
+    interp_to_w_grid (functions.f90:51-141) and the rank-dependent bounds of the accumulators run from the reference
+    text; accumulators gathered to global arrays."""
+    kw = dict(nx=16, ny=16, Nz=8, L_x=4.0, L_y=3.0, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=1, molec=False)
+    pg = O.Params(nproc=1, **kw)
+    ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=seed, amp=0.3, L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+
+    def fn(ref, r):
+        for n, g in (("u", ug), ("v", vg), ("w", wg)):
+            ref.put(n, O.scatter_slab(g, ref.p))
+        t = ref.tavg_new()
+        for it in range(1, nsteps + 1):
+            ref.step(it, mode="full")
+            ref.tavg_compute(t, ref.p.dt)
+        o = {n: ref.get(n) for n in STEP_FIELDS}
+        for n in O.TAVG_FIELDS:
+            o["tavg_" + n] = getattr(t, n).a.transpose(2, 1, 0).copy()
+        o["total_time"] = float(t.total_time)
+        o["nstmt"] = ref.I.nstmt
+        return o
+
+    res = refrun.run_ranks(kw, nproc, fn, files=refrun.TAVG_FILES)
+    ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
+    out = {}
+    for n in STEP_FIELDS:
+        out[n] = O.gather_slabs([res[r][n] for r in range(nproc)], ps, top_extra=n in ("w", "RHSz", "p"))
+    for n in O.TAVG_FIELDS:
+        out["tavg_" + n] = O.gather_slabs([res[r]["tavg_" + n] for r in range(nproc)], ps, top_extra=False)
+    out["total_time"] = np.array(res[0]["total_time"])
+    meta = dict(kw=kw, nproc=nproc, nsteps=nsteps, seed=seed, amp=0.3, mode="full",
+                made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py, 2 ranks",
+                statements=int(sum(res[r]["nstmt"] for r in range(nproc))))
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: done, {meta['statements']} reference statements on {nproc} ranks")
+
+
 def run_filter_kernels(name="ref_filter_kernels_16x32"):
     """test_filter_init (test_filtermodule.f90:38-123) for the three filter types: the kernels G_test (2 Delta) and,
     with sgs_model 5, G_test_test (4 Delta) as the reference builds them, plus one plane filtered with each."""
@@ -371,3 +410,5 @@ if __name__ == "__main__":
         run_filter_kernels()
     if not only or "mpi_lasd" in only:
         run_mpi_lasd_case()
+    if not only or "mpi_tavg" in only:
+        run_mpi_tavg_case()

@@ -325,7 +325,7 @@ def farm_for_rank(farm, p):
 
 
 def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core", lasd=False,
-                          turbines=False, tavg=False, p2p=False, local=False, ref_global=None, rotation=None):
+                          turbines=False, tavg=False, p2p=False, local=False, ref_global=None, rotation=None, ref_tavg=None):
     """nproc ranks (threads of this process, one Core each) advance `nsteps` core steps;
     the gathered result must match the SINGLE-slab oracle (which the multi-slab oracle
     equals, tests/test_oracle_kat.py)."""
@@ -422,6 +422,8 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
         for n in TAVG_SEAM:
             g = O.gather_slabs([res[r]["tavg_" + n] for r in range(nproc)], ps, top_extra=False)
             out["tavg_" + n] = rel(g[1:nzt], getattr(tref, n)[1:nzt])
+            if ref_tavg is not None:       # ... and against the accumulators of the reference's own MPI run
+                out["ref_tavg_" + n] = rel(g[1:nzt], ref_tavg[n][1:nzt])
     if turbines:
         # one more forcing call on both sides: every rank must hold the same (global) disk velocities
         O.turbines_forcing(sref, pg, O.LocalComm(), farm_ref, 0.3, **rkw)

@@ -42,7 +42,8 @@ def valid(p, n, a):
 def test_fixtures_exist():
     assert len(STEP_FIXTURES) >= 5 and os.path.exists(os.path.join(GOLD, "ref_routines_16x16x6.npz"))
     for f in ("ref_full_lasd_16x16x6", "ref_tavg_16x16x6", "ref_turbines_32x32x8", "ref_turbines_rot_32x32x8", "ref_mpi4_full_16x16x8",
-              "ref_filter_kernels_16x32", "ref_mpi2_lasd_16x16x8"):
+              "ref_filter_kernels_16x32", "ref_mpi2_lasd_16x16x8",
+              "ref_mpi2_tavg_16x16x8"):
         assert os.path.exists(os.path.join(GOLD, f + ".npz")), f
 
 
@@ -521,6 +522,58 @@ def test_kernel_logic_slabs_match_reference_mpi_lasd_run():
 @pytest.mark.gpu
 def test_cuda_slabs_match_reference_mpi_lasd_run():
     print(_slabs_vs_reference_mpi_lasd(lesgo_b200.load_library(), local=True, device_of=lambda coord: 0, p2p=True))
+
+
+def load_mpi_tavg():
+    d = np.load(os.path.join(GOLD, "ref_mpi2_tavg_16x16x8.npz"))
+    return d, ast.literal_eval(str(d["meta"]))
+
+
+def test_oracle_matches_reference_mpi_tavg_run():
+    """tavg%compute on the reference's two interpreted MPI ranks (the halos inside interp_to_uv_grid / interp_to_w_grid)
+    vs the oracle on ONE slab: all 26 accumulators on levels 1..nz_tot-1."""
+    d, meta = load_mpi_tavg()
+    kw, nproc, nsteps = meta["kw"], meta["nproc"], meta["nsteps"]
+    pg = O.Params(nproc=1, **kw)
+    sp = O.Spectral(pg)
+    ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=meta["seed"], amp=meta["amp"], L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+    s = O.State(pg)
+    s.u, s.v, s.w = (O.scatter_slab(f, pg) for f in (ug, vg, wg))
+    t = O.Tavg(pg)
+    for it in range(nsteps):
+        O.step(s, sp, O.LocalComm(), mode="full", first_step=(it == 0), G_test=O.test_filter_kernel(sp))
+        O.tavg_compute(t, s, pg, O.LocalComm(), pg.dt)
+    nzt = pg.nz_tot
+    assert abs(t.total_time - float(d["total_time"])) <= 1e-15
+    for n in O.TAVG_FIELDS:
+        ref = d["tavg_" + n][1:nzt]
+        if not np.any(ref):
+            assert not np.any(getattr(t, n)[1:nzt]), n
+            continue
+        assert rel(getattr(t, n)[1:nzt], ref) <= 1e-12, n
+
+
+def _slabs_vs_reference_mpi_tavg(lib, local, device_of=None, p2p=False):
+    from helpers import check_multirank_steps, TAVG_SEAM
+    d, meta = load_mpi_tavg()
+    out = check_multirank_steps(lib, meta["kw"], meta["nproc"], nsteps=meta["nsteps"], tol=1e-11, seed=meta["seed"],
+                                mode="full", tavg=True, local=local, device_of=device_of, p2p=p2p,
+                                ref_global={n: d[n] for n in FIELDS}, ref_tavg={n: d["tavg_" + n] for n in TAVG_SEAM})
+    assert all(("ref_tavg_" + n) in out for n in TAVG_SEAM)
+    return out
+
+
+def test_kernel_logic_slabs_match_reference_mpi_tavg_run():
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    from helpers import emul_library
+    print(_slabs_vs_reference_mpi_tavg(emul_library(), local=False))
+
+
+@pytest.mark.gpu
+def test_cuda_slabs_match_reference_mpi_tavg_run():
+    print(_slabs_vs_reference_mpi_tavg(lesgo_b200.load_library(), local=True, device_of=lambda coord: 0, p2p=True))
 
 
 # ---- the CUDA path against the reference-source fixtures --------------------------------------------------------

@@ -79,6 +79,41 @@ def run_lasd_case(name="ref_full_lasd_16x16x6", nsteps=4):
     print(f"{name}: {nsteps} steps, {R.I.nstmt} reference statements, {time.time() - t0:.1f} s")
 
 
+def run_lasd_cfl_case(name="ref_full_lasd_cfl_dt_16x16x6", nsteps=6, cfl=0.0625, dyn_init=2, cs_count=2):
+    """Rows (f)-2 with use_cfl_dt as the shipped lesgo.conf runs it: the time step varies, so lagran_dt is ACCUMULATED
+    (sgs_stag_util.f90:73-82: + dt on every step from jt = DYN_init - cs_count + 1 on, zeroed by lagrange_Sdep.f90:430)
+    instead of being cs_count * dt.  DYN_init = cs_count = 2, six steps: updates at jt = 2 (lagran_dt = dt1 + dt2, F_*
+    initialised), jt = 4 (dt3 + dt4) and jt = 6 (dt5 + dt6)."""
+    kw = dict(nx=16, ny=16, Nz=6, L_x=4.0, L_y=3.0, lbc_mom=2, ubc_mom=0, sgs=True, sgs_model=5, molec=False)
+    p = O.Params(**kw)
+    R = refrun.Reference(p, files=refrun.LASD_FILES, dyn_init=dyn_init, cs_count=cs_count)
+    u, v, w = initial_fields(p, seed=63, amp=0.5)
+    out = {"u0": u, "v0": v, "w0": w}
+    for n, a in (("u", u), ("v", v), ("w", w)):
+        R.put(n, a)
+    R.I.set("param", "cfl", float(cfl)); R.I.set("param", "use_cfl_dt", True); R.I.set("param", "cfl_f", 0.0)
+    R.I.exec_lines(os.path.join(refrun.REF, "initialize.f90"), 192, 200, ["types", "param", "sim_param", "cfl_util"],
+                   local={"dt_dim": 0.0})
+    dts = []
+    record = (dyn_init, nsteps)
+    for it in range(1, nsteps + 1):
+        R.cfl_dt_step_setup()                                      # main.f90:135-144
+        dts.append((R.I.get("param", "dt"), R.I.get("param", "tadv1"), R.I.get("param", "tadv2")))
+        R.step(it, mode="full")
+        if it in record:
+            for n in STEP_FIELDS:
+                out[f"{n}_{it}"] = R.get(n)
+            for n in LASD_FIELDS:
+                out[f"{n}_{it}"] = R.get(n.lower(), module="sgs_param")
+    out["dts"] = np.array(dts)
+    meta = dict(params=params_record(p), mode="full", record=list(record), cfl=cfl, dyn_init=dyn_init, cs_count=cs_count,
+                made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py",
+                statements=R.I.nstmt)
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: {nsteps} steps, {R.I.nstmt} reference statements")
+
+
 def run_turbine_case(name="ref_turbines_32x32x8", nsteps=2, eps=0.3, use_rotation=False, tip_speed_ratio=7.0):
     """Rows (f)-3 from the reference text: turbines_forcing (turbines.f90:465-638) through forcing_applied
     (forcing.f90:102-106) and main.f90:263-267 inside two core steps, USE_TURBINES build; two disks (one yawed and
@@ -398,6 +433,8 @@ if __name__ == "__main__":
             run_step_case(name, **c)
     if not only or "lasd" in only:
         run_lasd_case()
+    if not only or "lasd_cfl" in only:
+        run_lasd_cfl_case()
     if not only or "tavg" in only:
         run_tavg_case()
     if not only or "turbines" in only:

@@ -200,6 +200,33 @@ def lasd_schedule(p, it, cs_count=2, dyn_init=2):
                 lasd_init_F=(jt == dyn_init), lagran_dt=cs_count * p.dt)
 
 
+class LasdClock:
+    """The step counters AND the Lagrangian time interval of sgs_stag_util.f90:73-82,183-216 / lagrange_Sdep.f90:266-267,
+    430 for a fresh run (inilag; jt = jt_total), as fortran/lesgo_gpu_resident_mod.f90: gpu_lasd_switches keeps them for
+    lesgo_gpu_step: with use_cfl_dt lagran_dt is ACCUMULATED (+ dt on every step from jt = DYN_init - cs_count + 1 on)
+    and zeroed by the step that runs lagrange_Sdep; otherwise it is cs_count * dt."""
+
+    def __init__(self, cs_count, dyn_init, use_cfl_dt):
+        self.cs_count, self.dyn_init, self.use_cfl_dt = cs_count, dyn_init, use_cfl_dt
+        self.acc, self.initialised = 0.0, False
+
+    def switches(self, jt, dt):
+        if self.use_cfl_dt:
+            if jt >= self.dyn_init - self.cs_count + 1:
+                self.acc += dt
+            lagran_dt = self.acc
+        else:
+            lagran_dt = self.cs_count * dt
+        out = dict(lasd_cs_init=(jt == 1), lasd_update=False, lasd_init_F=False, lagran_dt=lagran_dt)
+        if jt != 1 and jt >= self.dyn_init and jt % self.cs_count == 0:
+            out["lasd_update"] = True
+            self.acc = 0.0
+            if not self.initialised and (jt == self.cs_count or jt == self.dyn_init):
+                out["lasd_init_F"] = True
+                self.initialised = True
+        return out
+
+
 def check_lasd_steps(core, p, nsteps=4, tol=1e-11, seed=61, amp=0.5):
     """Full steps with sgs_model = 5 (Lagrangian scale-dependent dynamic model, rows (f)-2) against the oracle:
     velocities, pressure, and the model's own state F_LM, F_MM, F_QN, F_NN, Cs_opt2."""

@@ -43,7 +43,7 @@ def test_fixtures_exist():
     assert len(STEP_FIXTURES) >= 5 and os.path.exists(os.path.join(GOLD, "ref_routines_16x16x6.npz"))
     for f in ("ref_full_lasd_16x16x6", "ref_tavg_16x16x6", "ref_turbines_32x32x8", "ref_turbines_rot_32x32x8", "ref_mpi4_full_16x16x8",
               "ref_filter_kernels_16x32", "ref_mpi2_lasd_16x16x8",
-              "ref_mpi2_tavg_16x16x8"):
+              "ref_mpi2_tavg_16x16x8", "ref_full_lasd_cfl_dt_16x16x6"):
         assert os.path.exists(os.path.join(GOLD, f + ".npz")), f
 
 
@@ -181,6 +181,95 @@ def test_oracle_lasd_matches_reference_sources():
     print({k: f"{v:.1e}" for k, v in worst.items()})
     for (it, n), v in worst.items():
         assert v <= (1e-11 if n == "Cs_opt2" else 1e-12), (it, n, v)
+
+
+def _lasd_cfl_fixture_run(stepper):
+    """Drive `stepper(it, dt, tadv1, tadv2, switches)` through the variable-dt LASD fixture with the reference's own dt
+    sequence; the Lagrangian interval comes from LasdClock (the rule the Fortran shim implements)."""
+    from helpers import LasdClock
+    d, meta, p = load("ref_full_lasd_cfl_dt_16x16x6")
+    clock = LasdClock(meta["cs_count"], meta["dyn_init"], use_cfl_dt=True)
+    acc = []
+    for it in range(1, max(meta["record"]) + 1):
+        dt, t1, t2 = (float(x) for x in d["dts"][it - 1])
+        sw = clock.switches(it, dt)
+        if sw["lasd_update"]:
+            acc.append(sw["lagran_dt"])
+        stepper(it, dt, t1, t2, sw)
+    # updates at jt = 2, 4, 6 with dt1 + dt2, dt3 + dt4, dt5 + dt6
+    dts = d["dts"][:, 0]
+    assert np.allclose(acc, [dts[0] + dts[1], dts[2] + dts[3], dts[4] + dts[5]], rtol=1e-15)
+    return d, meta, p
+
+
+def test_oracle_lasd_with_cfl_dt_matches_reference_sources():
+    """use_cfl_dt + sgs_model 5 as the shipped lesgo.conf runs: lagran_dt accumulated over the steps between two
+    lagrange_Sdep calls (sgs_stag_util.f90:73-82, lagrange_Sdep.f90:430), from the reference text, vs the oracle driven
+    by LasdClock: fields and model state after the first and the third update."""
+    d0, meta0, p = load("ref_full_lasd_cfl_dt_16x16x6")
+    sp = O.Spectral(p)
+    G, G2 = O.test_filter_kernel(sp), O.test_filter_kernel(sp, alpha=4.0)
+    s = O.State(p)
+    O.lasd_alloc(s)
+    s.u, s.v, s.w = d0["u0"].copy(), d0["v0"].copy(), d0["w0"].copy()
+    worst = {}
+
+    def stepper(it, dt, t1, t2, sw):
+        p.dt, p.tadv1, p.tadv2 = dt, t1, t2
+        O.step(s, sp, O.LocalComm(), mode="full", first_step=(it == 1), G_test=G,
+               lasd=dict(sp=sp, G_test=G, G_test_test=G2, lagran_dt=sw["lagran_dt"], cs_init=sw["lasd_cs_init"],
+                         update=sw["lasd_update"], init_F=sw["lasd_init_F"]))
+        if it in meta0["record"]:
+            for n in FIELDS:
+                worst[(it, n)] = rel(valid(p, n, getattr(s, n)), valid(p, n, d0[f"{n}_{it}"]))
+            for n in LASD_FIELDS:
+                worst[(it, n)] = rel(getattr(s, n)[1:p.nz + 1, :, :p.nx], d0[f"{n}_{it}"][1:p.nz + 1, :, :p.nx])
+
+    _lasd_cfl_fixture_run(stepper)
+    print({k: f"{v:.1e}" for k, v in worst.items()})
+    for (it, n), v in worst.items():
+        assert v <= (1e-10 if n == "Cs_opt2" else 1e-11), (it, n, v)
+
+
+def run_core_on_lasd_cfl_fixture(core):
+    d0, meta0, p = load("ref_full_lasd_cfl_dt_16x16x6")
+    for n in ("u", "v", "w"):
+        core.upload(n, d0[n + "0"])
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz") + LASD_FIELDS:
+        core.upload(n, np.zeros(core.dims.shape))
+    worst = {}
+
+    def stepper(it, dt, t1, t2, sw):
+        from helpers import step_kwargs
+        kw = step_kwargs(p, it - 1, "full")
+        kw.update(dt=dt, tadv1=t1, tadv2=t2, **sw)
+        core.step(**kw)
+        if it in meta0["record"]:
+            for n in FIELDS:
+                worst[(it, n)] = rel(valid(p, n, core.download(n)), valid(p, n, d0[f"{n}_{it}"]))
+            for n in LASD_FIELDS:
+                worst[(it, n)] = rel(core.download(n)[1:p.nz + 1, :, :p.nx], d0[f"{n}_{it}"][1:p.nz + 1, :, :p.nx])
+
+    _lasd_cfl_fixture_run(stepper)
+    return worst
+
+
+@pytest.mark.gpu
+def test_cuda_lasd_with_cfl_dt_matches_reference_sources():
+    worst = run_core_on_lasd_cfl_fixture(lesgo_b200.Core(make_dims(load("ref_full_lasd_cfl_dt_16x16x6")[2], device=0)))
+    print({k: f"{v:.1e}" for k, v in worst.items()})
+    for (it, n), v in worst.items():
+        assert v <= (1e-10 if n == "Cs_opt2" else 1e-11), (it, n, v)
+
+
+def test_kernel_logic_lasd_with_cfl_dt_matches_reference_sources():
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    from helpers import emul_library
+    worst = run_core_on_lasd_cfl_fixture(lesgo_b200.Core(make_dims(load("ref_full_lasd_cfl_dt_16x16x6")[2]), lib=emul_library()))
+    for (it, n), v in worst.items():
+        assert v <= (1e-10 if n == "Cs_opt2" else 1e-11), (it, n, v)
 
 
 def run_core_on_lasd_fixture(core):

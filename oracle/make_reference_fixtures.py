@@ -227,6 +227,52 @@ def run_mpi_tavg_case(name="ref_mpi2_tavg_16x16x8", nproc=2, nsteps=2, seed=57):
     print(f"{name}: done, {meta['statements']} reference statements on {nproc} ranks")
 
 
+def run_mpi_turbine_case(name="ref_mpi2_turbines_32x32x8", nproc=2, nsteps=2, eps=0.3, seed=59):
+    """Rows (f)-3 through the reference's MPI code path: two disks that span BOTH z slabs of a two-rank run, so that the
+    per-rank partial sums and the MPI_Allreduce of the disk velocities (turbines.f90:549-560), the force-field halos
+    (:620-622) and interp_to_w_grid across the slab seam run from the reference text, inside two core steps."""
+    from helpers import make_farm, farm_for_rank
+    kw = dict(nx=32, ny=32, Nz=8, lbc_mom=1, ubc_mom=1)
+    pg = O.Params(nproc=1, **kw)
+    ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=seed, amp=0.3, L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+    ug = ug + 1.0
+    farm_g = make_farm(pg)
+    for t in farm_g:
+        t.M = 0.9
+    ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
+    assert all(len(farm_for_rank(farm_g, p)[0].ind) > 5 for p in ps), "the first disk must have nodes on both ranks"
+
+    def fn(ref, r):
+        ref.farm_set(farm_for_rank(farm_g, ref.p), eps, adm_correction=True)
+        for n, g in (("u", ug), ("v", vg), ("w", wg)):
+            ref.put(n, O.scatter_slab(g, ref.p))
+        for it in range(1, nsteps + 1):
+            ref.step(it, mode="core")
+        o = {n: ref.get(n) for n in STEP_FIELDS + ("fxa", "fya", "fza")}
+        for n in ("u_d", "u_d_t", "f_n"):
+            o["disk_" + n] = np.array(ref.farm_get(n))
+        o["nstmt"] = ref.I.nstmt
+        return o
+
+    res = refrun.run_ranks(kw, nproc, fn, files=refrun.TURBINE_FILES, turbines=True)
+    out = {"ug": ug, "vg": vg, "wg": wg}
+    for n in STEP_FIELDS + ("fxa", "fya", "fza"):
+        out[n] = O.gather_slabs([res[r][n] for r in range(nproc)], ps, top_extra=n in ("w", "RHSz", "p", "fza"))
+    for n in ("u_d", "u_d_t", "f_n"):
+        assert all(np.array_equal(res[r]["disk_" + n], res[0]["disk_" + n]) for r in range(nproc)), n
+        out["disk_" + n] = res[0]["disk_" + n]
+    for i, t in enumerate(farm_g):
+        out[f"farm{i}_nodes"], out[f"farm{i}_ind"] = np.asarray(t.nodes), np.asarray(t.ind)
+        out[f"farm{i}_scalars"] = np.array([t.Ct_prime, t.dia, t.M, t.u_d_T, *t.nhat])
+    meta = dict(kw=kw, nproc=nproc, nsteps=nsteps, seed=seed, amp=0.3, mode="core", eps=eps, ndisks=len(farm_g),
+                adm_correction=True,
+                made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py, 2 ranks",
+                statements=int(sum(res[r]["nstmt"] for r in range(nproc))))
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: done, {meta['statements']} reference statements on {nproc} ranks")
+
+
 def run_filter_kernels(name="ref_filter_kernels_16x32"):
     """test_filter_init (test_filtermodule.f90:38-123) for the three filter types: the kernels G_test (2 Delta) and,
     with sgs_model 5, G_test_test (4 Delta) as the reference builds them, plus one plane filtered with each."""
@@ -449,3 +495,5 @@ if __name__ == "__main__":
         run_mpi_lasd_case()
     if not only or "mpi_tavg" in only:
         run_mpi_tavg_case()
+    if not only or "mpi_turbines" in only:
+        run_mpi_turbine_case()

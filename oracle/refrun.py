@@ -122,7 +122,11 @@ class Reference:
                 start = int(np.ravel_multi_index(x.idx, x.base.a.shape, order="F"))
                 return f_[start:start + count]
             f_ = x.a.reshape(-1, order="F")
-            assert np.shares_memory(f_, x.a), "MPI buffer must be contiguous"
+            if not np.shares_memory(f_, x.a):
+                # a non-contiguous section, e.g. var(:, :, 1) of fxa(1:nx, 1:ny, lbz:nz): the compiler passes a
+                # contiguous temporary (copy-in / copy-out); the whole section is the message
+                assert count == x.a.size, "a non-contiguous MPI buffer must be sent or received whole"
+                return None
             return f_[:count]
 
         def box(src, dst, tag):
@@ -135,11 +139,17 @@ class Reference:
 
         def send_to(buf, count, dest, tag):
             if valid(dest):
-                box(me, dest, tag).put(np.array(flat(buf, count), copy=True))
+                v = flat(buf, count)
+                box(me, dest, tag).put(np.array(v, copy=True) if v is not None else buf.a.flatten(order="F"))
 
         def recv_from(buf, count, src, tag):
             if valid(src):
-                flat(buf, count)[...] = box(src, me, tag).get(timeout=600)
+                data = box(src, me, tag).get(timeout=MPI_TIMEOUT)
+                v = flat(buf, count)
+                if v is not None:
+                    v[...] = data
+                else:
+                    buf.a[...] = np.asarray(data).reshape(buf.a.shape, order="F")
 
         def sendrecv(fr, a):
             send_to(a[0][0], int(a[1][0]), int(a[3][0]), int(a[4][0]))
@@ -159,7 +169,7 @@ class Reference:
                 if r != me:
                     box(me, r, ("ar", op)).put(mine)
             for r in range(nproc):                                # rank order: every rank forms the same result
-                x = mine if r == me else box(r, me, ("ar", op)).get(timeout=600)
+                x = mine if r == me else box(r, me, ("ar", op)).get(timeout=MPI_TIMEOUT)
                 acc = x if acc is None else (np.maximum(acc, x) if op == "mpi_max" else
                                              (np.minimum(acc, x) if op == "mpi_min" else acc + x))
             if isinstance(a[1][0], F.FArray):
@@ -286,6 +296,9 @@ class Reference:
         self.I.exec_lines(main, 135, 144, ["types", "param", "sim_param", "cfl_util"], local={"dt_dim": 0.0})
 
 
+MPI_TIMEOUT = float(os.environ.get("REFRUN_MPI_TIMEOUT", "600"))   # seconds a blocking receive waits for its message
+
+
 def run_ranks(kw, nproc, fn, **ref_kw):
     """The reference on `nproc` ranks: one interpreter per rank, each in its own thread, MPI calls carried by in-process
     mailboxes (blocking, tag-matched, like the MPI the reference uses).  fn(ref, coord) runs on every rank; returns the
@@ -304,6 +317,10 @@ def run_ranks(kw, nproc, fn, **ref_kw):
     ts = [threading.Thread(target=work, args=(r,)) for r in range(nproc)]
     [t.start() for t in ts]
     [t.join() for t in ts]
+    import queue
+    real = [e for e in err if e is not None and not isinstance(e, queue.Empty)]
+    if real:
+        raise real[0]              # a rank that failed, not the peers that then waited for it in vain
     for e in err:
         if e is not None:
             raise e

@@ -352,7 +352,8 @@ def farm_for_rank(farm, p):
 
 
 def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_of=None, mode="core", lasd=False,
-                          turbines=False, tavg=False, p2p=False, local=False, ref_global=None, rotation=None, ref_tavg=None):
+                          turbines=False, tavg=False, p2p=False, local=False, ref_global=None, rotation=None, ref_tavg=None,
+                          farm=None, adm_correction=False, fields0=None, ref_disks=None):
     """nproc ranks (threads of this process, one Core each) advance `nsteps` core steps;
     the gathered result must match the SINGLE-slab oracle (which the multi-slab oracle
     equals, tests/test_oracle_kat.py)."""
@@ -360,12 +361,14 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
     pg = O.Params(nproc=1, **kw)
     spg = O.Spectral(pg)
     ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=seed, amp=0.3, L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+    if fields0 is not None:
+        ug, vg, wg = fields0
     sref = O.State(pg)
     sref.u, sref.v, sref.w = (O.scatter_slab(f, pg) for f in (ug, vg, wg))
     Gg = O.test_filter_kernel(spg)
     G2g = O.test_filter_kernel(spg, alpha=4.0)
     names = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz") + (("Cs_opt2", "F_LM", "F_NN") if lasd else ())
-    farm_g = make_farm(pg) if turbines else None
+    farm_g = (farm if farm is not None else make_farm(pg)) if turbines else None
     farm_ref = [__import__("copy").copy(t) for t in farm_g] if turbines else None
     tkw = dict(turbines=True, turbines_eps=0.3) if turbines else {}
     rkw = dict(use_rotation=True, tip_speed_ratio=float(rotation)) if rotation else {}    # turbines.f90:607-615
@@ -376,7 +379,7 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
             ld_ = dict(sp=spg, G_test=Gg, G_test_test=G2g, lagran_dt=sch["lagran_dt"], cs_init=sch["lasd_cs_init"],
                        update=sch["lasd_update"], init_F=sch["lasd_init_F"])
         O.step(sref, spg, O.LocalComm(), mode=mode, first_step=(it == 0), G_test=Gg, lasd=ld_,
-               turbines=dict(farm=farm_ref, eps=0.3, **rkw) if turbines else None)
+               turbines=dict(farm=farm_ref, eps=0.3, adm_correction=adm_correction, **rkw) if turbines else None)
         if tavg:
             if it == 0:
                 tref = O.Tavg(pg)
@@ -400,7 +403,7 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
             for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz") + (("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2") if lasd else ()):
                 c.upload(n, np.zeros(c.dims.shape))
             if turbines:
-                c.turbines_init(farm_for_rank(farm_g, p), **rkw)
+                c.turbines_init(farm_for_rank(farm_g, p), adm_correction=adm_correction, **rkw)
             for it in range(nsteps):
                 c.step(**step_kwargs(p, it, mode), **(lasd_schedule(p, it) if lasd else {}), **tkw)
                 if tavg:
@@ -453,7 +456,9 @@ def check_multirank_steps(lib, kw, nproc, nsteps=2, tol=1e-11, seed=51, device_o
                 out["ref_tavg_" + n] = rel(g[1:nzt], ref_tavg[n][1:nzt])
     if turbines:
         # one more forcing call on both sides: every rank must hold the same (global) disk velocities
-        O.turbines_forcing(sref, pg, O.LocalComm(), farm_ref, 0.3, **rkw)
+        if ref_disks is not None:      # the disks' running averages after nsteps against the reference's own MPI run
+            out["ref_u_d_T"] = rel([t.u_d_T for t in farm_ref], ref_disks)
+        O.turbines_forcing(sref, pg, O.LocalComm(), farm_ref, 0.3, adm_correction=adm_correction, **rkw)
         for r in range(nproc):
             out[f"u_d_T_rank{r}"] = rel(res[r]["u_d_T"], [t.u_d_T for t in farm_ref])
     cfl_ref = O.get_max_cfl(sref, pg, O.LocalComm())

@@ -43,7 +43,8 @@ def test_fixtures_exist():
     assert len(STEP_FIXTURES) >= 5 and os.path.exists(os.path.join(GOLD, "ref_routines_16x16x6.npz"))
     for f in ("ref_full_lasd_16x16x6", "ref_tavg_16x16x6", "ref_turbines_32x32x8", "ref_turbines_rot_32x32x8", "ref_mpi4_full_16x16x8",
               "ref_filter_kernels_16x32", "ref_mpi2_lasd_16x16x8",
-              "ref_mpi2_tavg_16x16x8", "ref_full_lasd_cfl_dt_16x16x6"):
+              "ref_mpi2_tavg_16x16x8", "ref_full_lasd_cfl_dt_16x16x6",
+              "ref_mpi2_turbines_32x32x8"):
         assert os.path.exists(os.path.join(GOLD, f + ".npz")), f
 
 
@@ -663,6 +664,59 @@ def test_kernel_logic_slabs_match_reference_mpi_tavg_run():
 @pytest.mark.gpu
 def test_cuda_slabs_match_reference_mpi_tavg_run():
     print(_slabs_vs_reference_mpi_tavg(lesgo_b200.load_library(), local=True, device_of=lambda coord: 0, p2p=True))
+
+
+def load_mpi_turbines():
+    d = np.load(os.path.join(GOLD, "ref_mpi2_turbines_32x32x8.npz"))
+    return d, ast.literal_eval(str(d["meta"]))
+
+
+def test_oracle_matches_reference_mpi_turbine_run():
+    """turbines_forcing on the reference's two interpreted MPI ranks (per-rank partial sums + MPI_Allreduce of the disk
+    velocities, force-field halos, interp_to_w_grid across the seam) vs the oracle on ONE slab: force fields bit for bit."""
+    d, meta = load_mpi_turbines()
+    pg = O.Params(nproc=1, **meta["kw"])
+    sp = O.Spectral(pg)
+    s = O.State(pg)
+    s.u, s.v, s.w = (O.scatter_slab(d[n], pg) for n in ("ug", "vg", "wg"))
+    farm = farm_from_fixture(d, meta)
+    for it in range(meta["nsteps"]):
+        O.step(s, sp, O.LocalComm(), mode="core", first_step=(it == 0),
+               turbines=dict(farm=farm, eps=meta["eps"], adm_correction=meta["adm_correction"]))
+    nzt = pg.nz_tot
+    for name in ("fxa", "fya", "fza"):
+        ref = d[name][1:nzt, :, :pg.nx]
+        assert np.count_nonzero(ref) > 100
+        # the two ranks add their partial sums in rank order, the single slab adds node by node: not bit-equal
+        assert rel(getattr(s, name)[1:nzt, :, :pg.nx], ref) <= 1e-14, name
+    assert rel([t.u_d_T for t in farm], d["disk_u_d_t"]) <= 1e-14 and rel([t.f_n for t in farm], d["disk_f_n"]) <= 1e-14
+    for name in FIELDS:
+        hi = nzt if name in ("w", "RHSz", "p") else nzt - 1
+        assert rel(getattr(s, name)[1:hi + 1, :, :pg.nx], d[name][1:hi + 1, :, :pg.nx]) <= 1e-13, name
+
+
+def _slabs_vs_reference_mpi_turbines(lib, local, device_of=None, p2p=False):
+    from helpers import check_multirank_steps
+    d, meta = load_mpi_turbines()
+    out = check_multirank_steps(lib, meta["kw"], meta["nproc"], nsteps=meta["nsteps"], tol=1e-11, mode="core", turbines=True,
+                                local=local, device_of=device_of, p2p=p2p, farm=farm_from_fixture(d, meta),
+                                adm_correction=meta["adm_correction"], fields0=(d["ug"], d["vg"], d["wg"]),
+                                ref_global={n: d[n] for n in FIELDS}, ref_disks=d["disk_u_d_t"])
+    assert all(("ref_" + n) in out for n in FIELDS) and "ref_u_d_T" in out
+    return out
+
+
+def test_kernel_logic_slabs_match_reference_mpi_turbine_run():
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    from helpers import emul_library
+    print(_slabs_vs_reference_mpi_turbines(emul_library(), local=False))
+
+
+@pytest.mark.gpu
+def test_cuda_slabs_match_reference_mpi_turbine_run():
+    print(_slabs_vs_reference_mpi_turbines(lesgo_b200.load_library(), local=True, device_of=lambda coord: 0, p2p=True))
 
 
 # ---- the CUDA path against the reference-source fixtures --------------------------------------------------------

@@ -273,6 +273,33 @@ def run_mpi_turbine_case(name="ref_mpi2_turbines_32x32x8", nproc=2, nsteps=2, ep
     print(f"{name}: done, {meta['statements']} reference statements on {nproc} ranks")
 
 
+def run_mpi_rmsdiv_case(name="ref_mpi2_rmsdiv_16x16x8", nproc=2, seed=67):
+    """rmsdiv.f90:21-59 as main.f90:367 calls it at the end of a step, on two reference ranks: the L1 divergence metric of
+    the derivatives the step formed at :161-172 (i.e. of the synthetic, not divergence-free start field), mpi_reduce to
+    rank 0 and the division by nproc."""
+    kw = dict(nx=16, ny=16, Nz=8, L_x=4.0, L_y=3.0, lbc_mom=1, ubc_mom=1)
+    pg = O.Params(nproc=1, **kw)
+    ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=seed, amp=0.3, L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+    main = os.path.join(refrun.REF, "main.f90")
+
+    def fn(ref, r):
+        ref.I.load(os.path.join(refrun.REF, "rmsdiv.f90"))
+        for n, g in (("u", ug), ("v", vg), ("w", wg)):
+            ref.put(n, O.scatter_slab(g, ref.p))
+        ref.step(1, mode="core")
+        # main.f90:367 sits at the end of the step: dudx, dvdy, dwdz are still those of the field the step STARTED from
+        v = ref.I.exec_lines(main, 367, 367, ["types", "param", "sim_param"], local={"rmsdivvel": 0.0})
+        return {"rms": float(v["rmsdivvel"]), "fields": {n: ref.get(n) for n in ("u", "v", "w")}}
+
+    res = refrun.run_ranks(kw, nproc, fn)
+    out = {"ug": ug, "vg": vg, "wg": wg, "rms_rank0": np.array(res[0]["rms"]), "rms_local": np.array([res[r]["rms"] for r in range(nproc)])}
+    meta = dict(kw=kw, nproc=nproc, seed=seed,
+                made_by="oracle/make_reference_fixtures.py: reference sources interpreted by oracle/f90exec.py, 2 ranks")
+    out["meta"] = np.array(repr(meta))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: done, rms on rank 0 = {res[0]['rms']:.6e}")
+
+
 def run_filter_kernels(name="ref_filter_kernels_16x32"):
     """test_filter_init (test_filtermodule.f90:38-123) for the three filter types: the kernels G_test (2 Delta) and,
     with sgs_model 5, G_test_test (4 Delta) as the reference builds them, plus one plane filtered with each."""
@@ -497,3 +524,5 @@ if __name__ == "__main__":
         run_mpi_tavg_case()
     if not only or "mpi_turbines" in only:
         run_mpi_turbine_case()
+    if not only or "mpi_rmsdiv" in only:
+        run_mpi_rmsdiv_case()

@@ -177,13 +177,29 @@ class Reference:
             else:
                 a[1][1](float(acc))
 
+        def reduce_(fr, a):
+            # mpi_reduce(send, recv, count, type, op, root, comm, ierr): sum in rank order on the root only
+            root = int(a[5][0])
+            mine = np.array(a[0][0].a, copy=True) if isinstance(a[0][0], F.FArray) else np.array(a[0][0])
+            if me != root:
+                box(me, root, ("red",)).put(mine)
+                return
+            acc = None
+            for r in range(nproc):
+                x = mine if r == me else box(r, me, ("red",)).get(timeout=MPI_TIMEOUT)
+                acc = x if acc is None else acc + x
+            if isinstance(a[1][0], F.FArray):
+                a[1][0].a[...] = acc
+            else:
+                a[1][1](float(acc))
+
         def error(fr, a):
             raise F.FortranError("reference called error(): " + " ".join(str(x[0]) for x in a))
 
         I.externals.update({
             "dfftw_plan_dft_r2c_2d": plan("r2c"), "dfftw_plan_dft_c2r_2d": plan("c2r"),
             "dfftw_execute_dft_r2c": execute("r2c"), "dfftw_execute_dft_c2r": execute("c2r"),
-            "mpi_sendrecv": sendrecv, "mpi_send": send, "mpi_recv": recv, "mpi_allreduce": allreduce,
+            "mpi_sendrecv": sendrecv, "mpi_send": send, "mpi_recv": recv, "mpi_allreduce": allreduce, "mpi_reduce": reduce_,
             "error": error, "apply_inflow": lambda fr, a: None, "mpi_barrier": lambda fr, a: None,
         })
 

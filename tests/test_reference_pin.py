@@ -44,7 +44,7 @@ def test_fixtures_exist():
     for f in ("ref_full_lasd_16x16x6", "ref_tavg_16x16x6", "ref_turbines_32x32x8", "ref_turbines_rot_32x32x8", "ref_mpi4_full_16x16x8",
               "ref_filter_kernels_16x32", "ref_mpi2_lasd_16x16x8",
               "ref_mpi2_tavg_16x16x8", "ref_full_lasd_cfl_dt_16x16x6",
-              "ref_mpi2_turbines_32x32x8"):
+              "ref_mpi2_turbines_32x32x8", "ref_mpi2_rmsdiv_16x16x8"):
         assert os.path.exists(os.path.join(GOLD, f + ".npz")), f
 
 
@@ -717,6 +717,61 @@ def test_kernel_logic_slabs_match_reference_mpi_turbine_run():
 @pytest.mark.gpu
 def test_cuda_slabs_match_reference_mpi_turbine_run():
     print(_slabs_vs_reference_mpi_turbines(lesgo_b200.load_library(), local=True, device_of=lambda coord: 0, p2p=True))
+
+
+def _rmsdiv_fixture():
+    d = np.load(os.path.join(GOLD, "ref_mpi2_rmsdiv_16x16x8.npz"))
+    return d, ast.literal_eval(str(d["meta"]))
+
+
+def test_oracle_rmsdiv_matches_reference_mpi_run():
+    """rmsdiv.f90 on two interpreted reference ranks (mpi_reduce to rank 0, / nproc) vs the oracle on two slabs and on one:
+    the metric is the plane-count-weighted mean, so the single-slab value is the same number."""
+    d, meta = _rmsdiv_fixture()
+    kw, nproc = meta["kw"], meta["nproc"]
+    ref = float(d["rms_rank0"])
+    assert ref > 0.1
+
+    def run(p, comm):
+        sp = O.Spectral(p)
+        s = O.State(p)
+        s.u, s.v, s.w = (O.scatter_slab(d[n], p) for n in ("ug", "vg", "wg"))
+        O.step(s, sp, comm, mode="core", first_step=True)
+        return O.rmsdiv(s, p, comm)
+
+    ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
+    many = O.run_ranks(nproc, lambda coord, comm: run(ps[coord], comm))
+    assert abs(many[0] - ref) <= 1e-14 * ref, (many, ref)
+    one = run(O.Params(nproc=1, **kw), O.LocalComm())
+    assert abs(one - ref) <= 1e-13 * ref, (one, ref)
+
+
+def run_core_rmsdiv(core, d, p):
+    for n, g in (("u", d["ug"]), ("v", d["vg"]), ("w", d["wg"])):
+        core.upload(n, O.scatter_slab(g, p))
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+        core.upload(n, np.zeros(core.dims.shape))
+    core.step(**step_kwargs_pre_dyn(p, 0, "core"))
+    return core.rmsdiv()
+
+
+@pytest.mark.gpu
+def test_cuda_rmsdiv_matches_reference_mpi_run():
+    d, meta = _rmsdiv_fixture()
+    p = O.Params(nproc=1, **meta["kw"])
+    ref = float(d["rms_rank0"])
+    assert abs(run_core_rmsdiv(lesgo_b200.Core(make_dims(p, device=0)), d, p) - ref) <= 1e-12 * ref
+
+
+def test_kernel_logic_rmsdiv_matches_reference_mpi_run():
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    from helpers import emul_library
+    d, meta = _rmsdiv_fixture()
+    p = O.Params(nproc=1, **meta["kw"])
+    ref = float(d["rms_rank0"])
+    assert abs(run_core_rmsdiv(lesgo_b200.Core(make_dims(p), lib=emul_library()), d, p) - ref) <= 1e-12 * ref
 
 
 # ---- the CUDA path against the reference-source fixtures --------------------------------------------------------

@@ -159,6 +159,21 @@ interface
         real(c_double), intent(inout) :: u(*)
         integer(c_int), value :: n
     end function
+    !> test_filtermodule.f90:126-168: nplanes planes of f filtered in place with the real kernel G(lh, ny)
+    integer(c_int) function lesgo_gpu_test_filter(ctx, f, G, nplanes) bind(c, name='lesgo_gpu_test_filter')
+        import :: c_int, c_ptr, c_double
+        type(c_ptr), value :: ctx
+        real(c_double), intent(inout) :: f(*)
+        real(c_double), intent(in) :: G(*)
+        integer(c_int), value :: nplanes
+    end function
+    !> mpi_defs.f90:167-264 on a (ld, ny, 0:nz) array: isync = MPI_SYNC_DOWN (1), MPI_SYNC_UP (2), MPI_SYNC_DOWNUP (3)
+    integer(c_int) function lesgo_gpu_sync_real_array(ctx, var, isync) bind(c, name='lesgo_gpu_sync_real_array')
+        import :: c_int, c_ptr, c_double
+        type(c_ptr), value :: ctx
+        real(c_double), intent(inout) :: var(*)
+        integer(c_int), value :: isync
+    end function
 end interface
 
 contains
@@ -235,6 +250,25 @@ call gpu_pin(dwdx); call gpu_pin(dwdy); call gpu_pin(dwdz)
 call gpu_pin(RHSx); call gpu_pin(RHSy); call gpu_pin(RHSz)
 call gpu_pin(p); call gpu_pin(dpdx); call gpu_pin(dpdy); call gpu_pin(dpdz); call gpu_pin(divtz)
 end subroutine gpu_pin_sim_param
+
+!> test_filter / test_test_filter of test_filtermodule.f90:126-168 for ONE plane, with the module's own kernel:
+!>     call gpu_test_filter(f, G_test)       replaces the body of test_filter(f)
+!>     call gpu_test_filter(f, G_test_test)  replaces the body of test_test_filter(f)
+subroutine gpu_test_filter(f, G)
+real(c_double), dimension(:,:), intent(inout) :: f       !< (ld, ny)
+real(c_double), dimension(:,:), intent(in) :: G          !< (lh, ny)
+call gpu_require()
+call gpu_check(lesgo_gpu_test_filter(gpu_ctx, f, G, 1_c_int), 'lesgo_gpu_test_filter')
+end subroutine gpu_test_filter
+
+!> mpi_sync_real_array (mpi_defs.f90:167-264) for a field the host holds, over the library's transport (NCCL or the
+!> peer mappings) instead of MPI: same isync values as MPI_SYNC_DOWN / MPI_SYNC_UP / MPI_SYNC_DOWNUP.
+subroutine gpu_sync_real_array(var, isync)
+real(c_double), intent(inout) :: var(*)
+integer, intent(in) :: isync
+call gpu_require()
+call gpu_check(lesgo_gpu_sync_real_array(gpu_ctx, var, int(isync, c_int)), 'lesgo_gpu_sync_real_array')
+end subroutine gpu_sync_real_array
 
 !> Non-zero return code -> the reference's fatal-error path (messages.f90:228-240).
 subroutine gpu_check(rc, where)

@@ -938,6 +938,18 @@ class Interpreter:
                 mod.vars[vname] = self._initial(d, fr, vname)
         return mod
 
+    def _fresh_struct(self, td):
+        """An instance of derived type `td` with its fixed-shape array members allocated (e.g. nhat(3))."""
+        o = FStruct(td)
+        for n, md in td.members.items():
+            if getattr(md, "dims", None) and not md.attrs.get("allocatable") and not md.attrs.get("pointer"):
+                try:
+                    shape, lb = self._dims(md.dims, None)
+                except Exception:
+                    continue
+                setattr(o, n, FArray.alloc(shape, lb, md.kind if md.kind in ("real", "integer", "logical", "complex") else "real", self.alloc_fill))
+        return o
+
     def _initial(self, d, fr, vname):
         if d.dims and not d.attrs.get("allocatable") and not d.attrs.get("pointer"):
             try:
@@ -1311,6 +1323,18 @@ class Frame:
                     return ElemRef(base, idx), None
                 view = base.a[idx]
                 return FArray(view, None, base.kind), None
+        if ast[0] == "call" and ast[1][0] == "comp":
+            # an element or section of an array COMPONENT, e.g. wind_farm%turbine(s)%ind(1)
+            try:
+                base = self.eval_object(ast[1])
+            except FortranError:
+                base = None
+            if isinstance(base, FArray):
+                subs = [self.subscript(a) for a in ast[2]]
+                idx, scalar = base.index(subs)
+                if scalar:
+                    return ElemRef(base, idx), None
+                return FArray(base.a[idx], None, base.kind), None
         return self.eval(ast), None
 
     def subscript(self, a):
@@ -1608,6 +1632,8 @@ class Frame:
             return v.imag
         if name == "conjg":
             return np.conj(ev(0))
+        if name == "transpose":
+            return np.asarray(ev(0)).T
         if name in ("trim", "adjustl"):
             return str(ev(0)).strip()
         if name == "spacing":
@@ -1718,6 +1744,18 @@ class Frame:
                         setattr(obj, tgt[2], FArray.alloc(shape, lb, k if k in ("real", "integer", "logical", "complex") else "real", self.I.alloc_fill))
                         continue
                     k = self.kind_of(name) or "real"
+                    d = self.proc.decls.get(name) if self.proc is not None else None
+                    if k == "derived" and d is not None and d.attrs.get("typename"):
+                        # an array of derived-type objects: one fresh instance per element
+                        td = next((m.types[d.attrs["typename"]] for m in self.I.modules.values() if d.attrs["typename"] in m.types), None)
+                        if td is None:
+                            raise FortranError(f"allocate: unknown derived type {d.attrs['typename']!r}")
+                        arr = FArray.alloc(shape, lb, "object")
+                        flat = arr.a.reshape(-1, order="F")
+                        for i in range(flat.size):
+                            flat[i] = self.I._fresh_struct(td)
+                        self.store(name, arr)
+                        continue
                     self.store(name, FArray.alloc(shape, lb, k if k in ("real", "integer", "logical", "complex") else "real", self.I.alloc_fill))
             elif t == "ptrassign":
                 src = st[3]

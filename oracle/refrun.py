@@ -49,17 +49,24 @@ def available():
 class Reference:
     """One rank of the reference, interpreted.  Fields are the module arrays of sim_param (Fortran bounds kept)."""
 
-    def __init__(self, p: O.Params, files=FILES, alloc_fill=0.0, dyn_init=100, cs_count=5, turbines=False, boxes=None):
-        """boxes: shared mailbox dict of a multi-rank run (run_ranks below); None = one rank."""
+    def __init__(self, p: O.Params, files=FILES, alloc_fill=0.0, dyn_init=100, cs_count=5, turbines=False, boxes=None,
+                 overrides=None, post_load=None):
+        """boxes: shared mailbox dict of a multi-rank run (run_ranks below); None = one rank.
+        overrides: {file name: path} -- sources taken from elsewhere than the reference tree (an absolute path in `files`
+        is loaded as it is); post_load(self): called after the sources are loaded and the externals installed, before
+        any reference code runs.  Both exist for tests/test_shim_dropin.py, which swaps the five replaced sources for
+        the ISO_C_BINDING shims of fortran/."""
         assert p.nproc == 1 or boxes is not None, "several ranks need the shared mailboxes of run_ranks()"
         self.p = p
         self.boxes = boxes
         self.turbines = turbines
         I = self.I = F.Interpreter(defines=("PPMPI", "PPSAFETYMODE") + (("PPTURBINES",) if turbines else ()), alloc_fill=alloc_fill)
         for f in files:
-            I.load(os.path.join(REF, f))
+            I.load((overrides or {}).get(f) or (f if os.path.isabs(f) else os.path.join(REF, f)))
         self.plans = {}
         self._externals()
+        if post_load is not None:
+            post_load(self)
         S = lambda n, v: I.set("param", n, v)
         # input_util.f90:197-235 (derived sizes) and the lesgo.conf blocks this path reads
         S("nproc", p.nproc); S("coord", p.coord); S("rank", p.coord)

@@ -1,0 +1,180 @@
+"""The reference's OWN time loop (main.f90, interpreted by oracle/f90exec.py) driving the ISO_C_BINDING shims of fortran/
+in place of the five sources they replace, with every `bind(C)` call carried through ctypes into a liblesgo_cuda build
+(the kernel-logic emulator on CPU, the sm_100a library on a B200).  No box of this pool has a Fortran compiler, so this is
+how the drop-in boundary gets executed at all: derivatives.f90, convec.f90, press_stag_array.f90, tridag_array.f90 and
+fft.f90 of fortran/ are parsed and run statement by statement, their arguments marshalled exactly as gfortran would pass
+them (base address of a contiguous array, scalars by value where the interface says `value`).
+
+What is NOT exercised: gpu_require (context creation, MPI / NCCL bootstrap) -- the context is made here and handed in --
+and gpu_check's error-string plumbing; both are replaced by Python stand-ins.  Test infrastructure, like oracle/."""
+import ctypes as C
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from oracle import f90exec as F  # noqa: E402
+from oracle import refrun  # noqa: E402
+import lesgo_b200  # noqa: E402
+from lesgo_b200 import lib as L  # noqa: E402
+
+FORTRAN = os.path.join(ROOT, "fortran")
+REPLACED = ("fft.f90", "derivatives.f90", "convec.f90", "tridag_array.f90", "press_stag_array.f90")
+
+ISO_C_BINDING = """module iso_c_binding
+implicit none
+integer, parameter :: c_int = 4, c_double = 8, c_intptr_t = 8, c_char = 1, c_long = 8
+type :: c_ptr
+    integer :: addr
+end type c_ptr
+end module iso_c_binding
+"""
+
+
+class CPtr:
+    """type(c_ptr): an address."""
+
+    def __init__(self, addr=0):
+        self.addr = int(addr)
+
+    def __repr__(self):
+        return f"CPtr({self.addr:#x})"
+
+
+_KEEP = []          # int32 images of the interpreter's integer arrays (it keeps them as int64), alive while C reads them
+
+
+def _c_image(a):
+    """The memory C sees for a Fortran array: real(c_double) arrays as they are, integer(c_int) arrays as an int32 copy."""
+    assert a.flags.f_contiguous, "the shims pass whole contiguous arrays"
+    if a.dtype == np.float64:
+        return a
+    assert a.dtype.kind == "i", a.dtype
+    img = np.asfortranarray(a.astype(np.int32))
+    _KEEP.append(img)
+    return img
+
+
+def _addr_of(x):
+    if isinstance(x, CPtr):
+        return x.addr
+    if isinstance(x, F.FArray):
+        return _c_image(x.a).ctypes.data
+    if isinstance(x, F.ElemRef):
+        img = _c_image(x.base.a)
+        return img.ctypes.data + int(np.ravel_multi_index(x.idx, img.shape, order="F")) * img.itemsize
+    raise TypeError(f"cannot take the address of {type(x).__name__}")
+
+
+def _vals(a):
+    """Arguments as values: `call x(...)` hands externals (value, setter) pairs, a function reference plain values."""
+    return [x[0] if isinstance(x, tuple) else x for x in a]
+
+
+class ShimmedReference(refrun.Reference):
+    """refrun.Reference with the five replaced sources taken from fortran/ and lesgo_gpu_* bound to `core`'s library."""
+
+    def __init__(self, p, core, files=refrun.FILES, resident=False, **kw):
+        """resident: also load fortran/lesgo_gpu_resident_mod.f90 (whole-step entry points, LASD switches)."""
+        self.core = core
+        self.calls = {}
+        if resident:
+            files = list(files) + [os.path.join(FORTRAN, "lesgo_gpu_resident_mod.f90")]
+        tmp = tempfile.NamedTemporaryFile("w", suffix=".f90", delete=False)
+        tmp.write(ISO_C_BINDING)
+        tmp.close()
+        self._iso = tmp.name
+        order = []
+        for f in files:
+            if f == "fft.f90":                    # lesgo_gpu_mod needs param + messages, the shims need lesgo_gpu_mod
+                order += [self._iso, os.path.join(FORTRAN, "lesgo_gpu_mod.f90")]
+            order.append(f)
+        overrides = {f: os.path.join(FORTRAN, f) for f in REPLACED}
+        try:
+            super().__init__(p, files=order, overrides=overrides, post_load=ShimmedReference._bind, **kw)
+        finally:
+            os.unlink(self._iso)
+
+    # ---- the C side of every bind(C) interface ------------------------------------------------------------------
+    def _bind(self):
+        I, core = self.I, self.core
+        mod = I.modules["lesgo_gpu_mod"]
+        for name in ("gpu_require", "gpu_check", "gpu_pin", "gpu_pin_sim_param"):
+            mod.procs.pop(name, None)             # Python stand-ins below (externals are consulted after module procs)
+        I.set("iso_c_binding", "c_null_ptr", CPtr(0))
+        I.set("iso_c_binding", "c_null_char", "\\0")
+        ctx = CPtr(core._ctx.value if hasattr(core._ctx, "value") else int(core._ctx))
+        I.set("lesgo_gpu_mod", "gpu_ctx", ctx)
+        core._ctx_ptr = lambda: ctx
+        ext = I.externals
+
+        def gpu_check(fr, a):
+            rc, where = _vals(a)[:2]
+            if int(rc) != 0:
+                raise lesgo_b200.LibraryError(f"{where}: {core.lib.error(core._ctx)}")
+
+        ext["gpu_require"] = lambda fr, a: None
+        ext["gpu_pin"] = lambda fr, a: None
+        ext["gpu_pin_sim_param"] = lambda fr, a: None
+        ext["gpu_check"] = gpu_check
+        ext["c_associated"] = lambda fr, a: _vals(a)[0].addr != 0
+        ext["c_loc"] = lambda fr, a: CPtr(_addr_of(_vals(a)[0]))
+
+        def transfer(fr, a):
+            src, mold = _vals(a)[:2]
+            if isinstance(mold, CPtr):
+                return CPtr(int(src))
+            return _addr_of(src) if isinstance(src, (CPtr, F.FArray, F.ElemRef)) else src
+        ext["transfer"] = transfer
+
+        def c_function(cname):
+            restype, argtypes = L.SYMBOLS[cname]
+            fn = getattr(core.lib.dll, cname)
+            fn.restype, fn.argtypes = restype, argtypes
+
+            def call(fr, a):
+                vals = _vals(a)
+                assert len(vals) == len(argtypes), (cname, len(vals), len(argtypes))
+                cargs = []
+                for v, t in zip(vals, argtypes):
+                    if isinstance(v, F.FArray) and v.a.dtype == object:      # an array of bind(C) structs or of c_ptr
+                        elems = list(v.a.reshape(-1, order="F"))
+                        if all(isinstance(e, CPtr) for e in elems):
+                            arr = (C.c_void_p * max(len(elems), 1))(*[e.addr for e in elems])
+                        else:
+                            arr = (L.TurbineStruct * max(len(elems), 1))()
+                            for i, e in enumerate(elems):
+                                arr[i].num_nodes = int(e.num_nodes)
+                                arr[i].nodes, arr[i].ind = e.nodes.addr, e.ind.addr
+                                arr[i].nhat = (C.c_double * 3)(*[float(z) for z in np.asarray(getattr(e.nhat, "a", e.nhat)).reshape(-1)])
+                                arr[i].Ct_prime, arr[i].dia, arr[i].M, arr[i].u_d_T = float(e.ct_prime), float(e.dia), float(e.m), float(e.u_d_t)
+                        _KEEP.append(arr)
+                        cargs.append(arr if t is not C.c_void_p else C.cast(arr, C.c_void_p))   # ctypes converts the array
+                        continue
+                    if isinstance(v, F.FStruct):     # a bind(C) derived type, passed by reference: member by member
+                        cls = {"lesgo_gpu_step_params": L.StepParams, "lesgo_gpu_dims": L.DimsStruct}[v._type.name.lower()]
+                        st = cls()
+                        for fname, ftype in cls._fields_:
+                            val = getattr(v, fname.lower())
+                            setattr(st, fname, (float(val) if ftype is C.c_double else int(val)) if val is not None else 0)
+                        cargs.append(C.byref(st))
+                        continue
+                    if t in (C.c_int, C.c_long, C.c_longlong):
+                        cargs.append(int(v))
+                    elif t is C.c_double:
+                        cargs.append(float(v))
+                    else:                           # pointers: the context, or the base address of an array
+                        cargs.append(C.c_void_p(_addr_of(v)))
+                self.calls[cname] = self.calls.get(cname, 0) + 1
+                return int(fn(*cargs))
+            return call
+
+        for cname in L.SYMBOLS:
+            ext[cname] = c_function(cname)
+        ext["press_raw"] = ext["lesgo_gpu_press_stag_array"]      # the local interface name of fortran/press_stag_array.f90

@@ -1,0 +1,216 @@
+"""The drop-in boundary, executed: the reference's own sources (main.f90's time loop, wallstress, sgs_stag, divstress ...,
+interpreted by oracle/f90exec.py where they lie under /root/reference) with the five sources of the hot path replaced by the
+ISO_C_BINDING shims of fortran/ -- derivatives.f90, convec.f90, press_stag_array.f90, tridag_array.f90, fft.f90 -- whose
+bind(C) calls go through ctypes into liblesgo_cuda's kernel-logic build (tests/shim_driver.py).  The results must equal what
+the ALL-reference run produced (tests/golden/ref_*.npz).  Needs the reference tree, so it runs in the build container only
+(no Fortran compiler exists on any box of this pool: this is the only way the shims get executed)."""
+import ast
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from helpers import O, make_dims, rel, emul_library
+import lesgo_b200
+from oracle import refrun
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+pytestmark = pytest.mark.skipif(not refrun.available() or shutil.which("g++") is None,
+                                reason="needs the reference sources under /root/reference and g++ for the emulator")
+FIELDS = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")
+
+
+def shimmed(p, **kw):
+    from shim_driver import ShimmedReference
+    return ShimmedReference(p, lesgo_b200.Core(make_dims(p), lib=emul_library()), **kw)
+
+
+def load(name):
+    d = np.load(os.path.join(GOLD, name + ".npz"))
+    return d, ast.literal_eval(str(d["meta"]))
+
+
+def test_routines_through_the_fortran_shims():
+    """ddx, ddy, ddxy, filt_da, ddz_uv, ddz_w called as main.f90 / divstress call them (module arrays of sim_param as
+    actual arguments, assumed-shape dummies in the shim), convec for four wall-condition combinations and
+    press_stag_array (the shim hands dpdx, dpdy, dpdz over shifted down by one plane): vs the reference's own routines."""
+    from helpers import random_field
+    d, meta = load("ref_routines_16x16x6")
+    kw = dict(nx=16, ny=16, Nz=6, L_x=4.0, L_y=3.0)
+    p = O.Params(**kw)
+    R = shimmed(p)
+    I, D = R.I, "derivatives"
+    S = lambda n: I.get("sim_param", n)
+    R.put("u", d["f"])
+    I.call("ddx", S("u"), S("dudx"), 0, module=D)
+    I.call("ddy", S("u"), S("dudy"), 0, module=D)
+    I.call("ddxy", S("u"), S("dvdx"), S("dvdy"), 0, module=D)
+    I.call("ddz_uv", S("u"), S("dudz"), 0, module=D)
+    I.call("ddz_w", S("u"), S("dwdz"), 0, module=D)
+    got = {"ddx": R.get("dudx"), "ddy": R.get("dudy"), "ddxy_x": R.get("dvdx"), "ddxy_y": R.get("dvdy"),
+           "ddz_uv": R.get("dudz"), "ddz_w": R.get("dwdz")}
+    I.call("filt_da", S("u"), S("dudx"), S("dudy"), 0, module=D)
+    got.update(filt_da_f=R.get("u"), filt_da_x=R.get("dudx"), filt_da_y=R.get("dudy"))
+    nz, nx = p.nz, p.nx
+    for n, g in got.items():
+        lo = 2 if n == "ddz_uv" else 1            # ddz_uv leaves plane 1 of the bottom rank to the wall model
+        hi = nz if n != "ddz_w" else nz - 1
+        assert rel(g[lo:hi, :, :nx], d[n][lo:hi, :, :nx]) <= 1e-14, n
+    for tag, bc in (("11d", (1, 1, False)), ("00d", (0, 0, False)), ("22l", (2, 2, True)), ("10l", (1, 0, True))):
+        pc = O.Params(lbc_mom=bc[0], ubc_mom=bc[1], sgs=bc[2], **kw)
+        Rc = shimmed(pc, files=[x for x in refrun.FILES if x not in ("sgs_stag_util.f90", "wallstress.f90", "divstress_uv.f90", "divstress_w.f90")])
+        for i, n in enumerate(("u", "v", "w", "dudy", "dudz", "dvdx", "dvdz", "dwdx", "dwdy")):
+            Rc.put(n, random_field(pc, 20 + i))
+        Rc.call("convec")
+        assert Rc.calls.get("lesgo_gpu_convec") == 1
+        for n in ("RHSx", "RHSy", "RHSz"):
+            hi = pc.nz + 1 if n == "RHSz" and False else pc.nz
+            assert rel(Rc.get(n)[1:hi, :, :nx], d[f"convec_{tag}_{n}"][1:hi, :, :nx]) <= 1e-13, (tag, n)
+    Rp = shimmed(O.Params(**kw))
+    for n in ("u", "v", "w", "divtz"):
+        Rp.put(n, d["press_" + n])
+    Rp.call("press_stag_array")
+    assert Rp.calls.get("lesgo_gpu_press_stag_array") == 1
+    for n in ("p", "dpdx", "dpdy", "dpdz"):
+        hi = nz + 1 if n == "p" else nz
+        lo = 0 if n == "p" else 1
+        assert rel(Rp.get(n)[lo:hi, :, :nx], d["press_" + n][lo:hi, :, :nx]) <= 1e-12, n
+
+
+@pytest.mark.parametrize("name", ["ref_core_couette_32x32x8", "ref_full_couette_16x16x8", "ref_full_les_channel_16x32x8",
+                                  "ref_core_free_slip_les_16x16x6"])
+def test_reference_time_loop_over_the_fortran_shims(name):
+    """main.f90:155-344 from the reference text -- with wallstress, calc_Sij, sgs_stag, divstress_uv / divstress_w still the
+    reference's Fortran, calling ddx / ddy / ddxy / ddz_* of the shim -- over the shimmed filt_da, convec and
+    press_stag_array: the fields after one step and after the fixture's last step vs the all-reference run."""
+    d, meta = load(name)
+    p = O.Params(**meta["params"])
+    R = shimmed(p)
+    for n in ("u", "v", "w"):
+        R.put(n, d[n + "0"])
+    last = min(max(meta["record"]), 4)            # the interpreter runs ~3 s per step: four steps are enough here
+    for it in range(1, last + 1):
+        R.step(it, mode=meta["mode"])
+        if it == 1:
+            for n in FIELDS:
+                hi = p.nz + 1 if n in ("w", "RHSz", "p") else p.nz
+                assert rel(R.get(n)[1:hi, :, :p.nx], d[f"{n}_1"][1:hi, :, :p.nx]) <= 1e-13, (n, it)
+    assert R.calls["lesgo_gpu_filt_da"] == 3 * last and R.calls["lesgo_gpu_convec"] == last
+    assert R.calls["lesgo_gpu_press_stag_array"] == last
+    if last in meta["record"]:
+        for n in FIELDS:
+            hi = p.nz + 1 if n in ("w", "RHSz", "p") else p.nz
+            assert rel(R.get(n)[1:hi, :, :p.nx], d[f"{n}_{last}"][1:hi, :, :p.nx]) <= 1e-12, (n, last)
+
+
+def test_tridag_array_shim():
+    """The explicit-shape shim of tridag_array (kept for callers other than press_stag_array): a diagonally dominant
+    system per (kx, ky) mode vs numpy."""
+    p = O.Params(nx=16, ny=16, Nz=6)
+    R = shimmed(p)
+    I = R.I
+    rng = np.random.default_rng(5)
+    n = p.nz + 1
+    a = rng.uniform(-1, 1, (n, p.ny, p.lh)); c = rng.uniform(-1, 1, (n, p.ny, p.lh)); b = 4.0 + rng.uniform(0, 1, (n, p.ny, p.lh))
+    r = rng.uniform(-1, 1, (n, p.ny, p.ld))
+    from oracle import f90exec as F
+    fa = lambda x: F.FArray(np.asfortranarray(x.transpose(2, 1, 0).copy()), (1, 1, 1))
+    A, B, Cc, Rr, U = fa(a), fa(b), fa(c), fa(r), fa(np.zeros_like(r))
+    I.call("tridag_array", A, B, Cc, Rr, U)
+    assert R.calls.get("lesgo_gpu_tridag_array") == 1
+    u = U.a.transpose(2, 1, 0)
+    # solve mode (jx, jy) for the real and the imaginary part: rows 1..n of a x(j-1) + b x(j) + c x(j+1) = r(j)
+    for jy in (0, 3, p.ny - 1):
+        for jx in (1, 4, p.lh - 2):
+            M = np.diag(b[:, jy, jx]) + np.diag(a[1:, jy, jx], -1) + np.diag(c[:-1, jy, jx], 1)
+            for part in (0, 1):
+                x = np.linalg.solve(M, r[:, jy, 2 * jx + part])
+                assert np.allclose(u[:, jy, 2 * jx + part], x, rtol=1e-11, atol=1e-13), (jx, jy, part)
+
+
+def _step_params(R, p, dt, t1, t2, first):
+    from oracle import f90exec as F
+    sp = F.FStruct(R.I.modules["lesgo_gpu_resident_mod"].types["lesgo_gpu_step_params"])
+    vals = dict(dt=dt, tadv1=t1, tadv2=t2, mean_p_force_x=p.mean_p_force_x if p.use_mean_p_force else 0.0,
+                mean_p_force_y=p.mean_p_force_y if p.use_mean_p_force else 0.0, ubot=p.ubot, utop=p.utop, nu_molec_nd=p.nu,
+                first_step=int(first), mode=1, sgs_model=p.sgs_model, ifilter=p.ifilter, co=p.Co, wall_damp_exp=p.wall_damp_exp,
+                vonk=p.vonk, zo=p.zo, lasd_cs_init=0, lasd_update=0, lasd_init_f=0, lagran_dt=0.0, turbines=0, turbines_eps=0.0)
+    for k, v in vals.items():
+        setattr(sp, k, v)
+    return sp
+
+
+@pytest.mark.parametrize("use_cfl_dt", [True, False])
+def test_resident_step_with_the_fortran_lasd_switches(use_cfl_dt):
+    """fortran/lesgo_gpu_resident_mod.f90: gpu_lasd_switches -- the Fortran a maintainer calls before lesgo_gpu_step with
+    sgs_model 5 -- interpreted statement by statement with the reference's own counters (jt, jt_total, DYN_init, cs_count,
+    dt, use_cfl_dt of module param), filling the bind(C) lesgo_gpu_step_params the library then steps with: against the
+    reference-source fixtures of the Lagrangian model with a varying (accumulated lagran_dt) and a fixed
+    time step."""
+    from oracle import f90exec as F
+    from helpers import LasdClock
+    name = "ref_full_lasd_cfl_dt_16x16x6" if use_cfl_dt else "ref_full_lasd_16x16x6"
+    d, meta = load(name)
+    p = O.Params(**meta["params"])
+    R = shimmed(p, files=refrun.LASD_FILES, resident=True, dyn_init=meta["dyn_init"], cs_count=meta["cs_count"])
+    I, core = R.I, R.core
+    for n in ("u", "v", "w"):
+        core.upload(n, d[n + "0"])
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz", "F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2"):
+        core.upload(n, np.zeros(core.dims.shape))
+    I.set("param", "use_cfl_dt", bool(use_cfl_dt))
+    flag = F.FArray(np.zeros(1, dtype=bool), (1,), "logical")
+    clock = LasdClock(meta["cs_count"], meta["dyn_init"], use_cfl_dt)
+    last = max(meta["record"])
+    for it in range(1, last + 1):
+        dt, t1, t2 = (float(x) for x in d["dts"][it - 1]) if use_cfl_dt else (p.dt, p.tadv1, p.tadv2)
+        I.set("param", "jt", it); I.set("param", "jt_total", it); I.set("param", "dt", dt)
+        sp = _step_params(R, p, dt, t1, t2, first=(it == 1))
+        I.call("gpu_lasd_switches", sp, F.ElemRef(flag, (0,)), module="lesgo_gpu_resident_mod")
+        want = clock.switches(it, dt)
+        got = dict(lasd_cs_init=bool(sp.lasd_cs_init), lasd_update=bool(sp.lasd_update), lasd_init_F=bool(sp.lasd_init_f),
+                   lagran_dt=float(sp.lagran_dt))
+        assert got == want, (it, got, want)
+        rc = I.externals["lesgo_gpu_step"](None, [core._ctx_ptr(), sp])
+        assert rc == 0, core.lib.error(core._ctx)
+        if it in meta["record"]:
+            for n in FIELDS + ("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2"):
+                top = n in ("w", "RHSz", "p", "F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2")
+                hi = p.nz + 1 if top else p.nz
+                e = rel(core.download(n)[1:hi, :, :p.nx], d[f"{n}_{it}"][1:hi, :, :p.nx])
+                assert e <= (1e-10 if n == "Cs_opt2" else 1e-11), (n, it, e)
+    assert bool(flag.a[0])
+
+
+@pytest.mark.parametrize("fixture", ["ref_turbines_32x32x8", "ref_turbines_rot_32x32x8"])
+def test_fortran_wind_farm_hand_over(fixture):
+    """fortran/lesgo_gpu_resident_mod.f90: gpu_turbines_set, interpreted: it walks the reference's own wind_farm (stat_defs'
+    derived types, as turbines_nodes leaves it), transposes %nodes and %e_theta into C order, takes c_loc of the members and
+    calls lesgo_gpu_turbines_init (+ lesgo_gpu_turbines_rotation with use_rotation).  The library stepped afterwards must
+    reproduce the reference-source actuator-disk fixtures."""
+    from test_reference_pin import farm_from_fixture, rotation_kw
+    from helpers import step_kwargs_pre_dyn
+    d, meta = load(fixture)
+    p = O.Params(**meta["params"])
+    R = shimmed(p, files=refrun.TURBINE_FILES, resident=True, turbines=True)
+    I, core = R.I, R.core
+    farm = farm_from_fixture(d, meta)
+    rk = rotation_kw(meta)
+    R.farm_set(farm, meta["eps"], adm_correction=meta["adm_correction"], **rk)
+    I.call("gpu_turbines_set", I.get("stat_defs", "wind_farm"), len(farm), bool(meta["adm_correction"]), rk["use_rotation"],
+           rk["tip_speed_ratio"], module="lesgo_gpu_resident_mod")
+    assert R.calls.get("lesgo_gpu_turbines_init") == 1
+    assert R.calls.get("lesgo_gpu_turbines_rotation", 0) == (1 if rk["use_rotation"] else 0)
+    for n in ("u", "v", "w"):
+        core.upload(n, d[n + "0"])
+    for n in ("RHSx", "RHSy", "RHSz", "divtx", "divty", "divtz"):
+        core.upload(n, np.zeros(core.dims.shape))
+    n = meta["nsteps"]
+    for it in range(1, n + 1):
+        core.step(**step_kwargs_pre_dyn(p, it - 1, "core"), turbines=True, turbines_eps=meta["eps"])
+    for name in ("fxa", "fya", "fza"):
+        assert rel(core.download(name)[1:p.nz, :, :p.nx], d[f"{name}_{n}"][1:p.nz, :, :p.nx]) <= 1e-12, name
+    for name in FIELDS:
+        hi = p.nz + 1 if name in ("w", "RHSz", "p") else p.nz
+        assert rel(core.download(name)[1:hi, :, :p.nx], d[f"{name}_{n}"][1:hi, :, :p.nx]) <= 1e-12, name

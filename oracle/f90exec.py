@@ -49,7 +49,8 @@ class FArray:
 
     @staticmethod
     def alloc(shape, lb, kind="real", fill=0.0):
-        dt = {"real": np.float64, "integer": np.int64, "logical": np.bool_, "complex": np.complex128, "object": object}[kind]
+        dt = {"real": np.float64, "integer": np.int64, "logical": np.bool_, "complex": np.complex128, "object": object,
+              "character": np.uint8}[kind]          # character(kind=c_char) buffers: one byte per element
         a = np.empty(tuple(shape), dtype=dt, order="F")
         if kind != "object":
             a[...] = fill if kind in ("real", "complex") else 0

@@ -29,11 +29,15 @@ REPLACED = ("fft.f90", "derivatives.f90", "convec.f90", "tridag_array.f90", "pre
 
 ISO_C_BINDING = """module iso_c_binding
 implicit none
-integer, parameter :: c_int = 4, c_double = 8, c_intptr_t = 8, c_char = 1, c_long = 8
+integer, parameter :: c_int = 4, c_double = 8, c_intptr_t = 8, c_char = 1, c_long = 8, c_size_t = 8
 type :: c_ptr
     integer :: addr
 end type c_ptr
 end module iso_c_binding
+module mpi
+implicit none
+integer, parameter :: MPI_COMM_TYPE_SHARED = 1, MPI_INFO_NULL = 0, MPI_CHARACTER = 1, MPI_INTEGER = 2, MPI_MIN = 3
+end module mpi
 """
 
 
@@ -53,7 +57,7 @@ _KEEP = []          # int32 images of the interpreter's integer arrays (it keeps
 def _c_image(a):
     """The memory C sees for a Fortran array: real(c_double) arrays as they are, integer(c_int) arrays as an int32 copy."""
     assert a.flags.f_contiguous, "the shims pass whole contiguous arrays"
-    if a.dtype == np.float64:
+    if a.dtype == np.float64 or a.dtype == np.uint8:
         return a
     assert a.dtype.kind == "i", a.dtype
     img = np.asfortranarray(a.astype(np.int32))
@@ -80,9 +84,13 @@ def _vals(a):
 class ShimmedReference(refrun.Reference):
     """refrun.Reference with the five replaced sources taken from fortran/ and lesgo_gpu_* bound to `core`'s library."""
 
-    def __init__(self, p, core, files=refrun.FILES, resident=False, **kw):
-        """resident: also load fortran/lesgo_gpu_resident_mod.f90 (whole-step entry points, LASD switches)."""
+    def __init__(self, p, core=None, files=refrun.FILES, resident=False, lib=None, **kw):
+        """resident: also load fortran/lesgo_gpu_resident_mod.f90 (whole-step entry points, LASD switches).
+        core = None (with lib = a loaded Library): nothing is pre-made -- the shims' own gpu_require creates the context
+        through lesgo_gpu_create, gpu_pin registers the arrays, gpu_check is the Fortran one."""
         self.core = core
+        self.lib = lib if lib is not None else core.lib
+        self.ctx = None
         self.calls = {}
         if resident:
             files = list(files) + [os.path.join(FORTRAN, "lesgo_gpu_resident_mod.f90")]
@@ -103,26 +111,102 @@ class ShimmedReference(refrun.Reference):
 
     # ---- the C side of every bind(C) interface ------------------------------------------------------------------
     def _bind(self):
-        I, core = self.I, self.core
+        I, core, lib = self.I, self.core, self.lib
         mod = I.modules["lesgo_gpu_mod"]
-        for name in ("gpu_require", "gpu_check", "gpu_pin", "gpu_pin_sim_param"):
-            mod.procs.pop(name, None)             # Python stand-ins below (externals are consulted after module procs)
         I.set("iso_c_binding", "c_null_ptr", CPtr(0))
         I.set("iso_c_binding", "c_null_char", "\\0")
-        ctx = CPtr(core._ctx.value if hasattr(core._ctx, "value") else int(core._ctx))
-        I.set("lesgo_gpu_mod", "gpu_ctx", ctx)
-        core._ctx_ptr = lambda: ctx
         ext = I.externals
+        if core is not None:
+            for name in ("gpu_require", "gpu_check", "gpu_pin", "gpu_pin_sim_param"):
+                mod.procs.pop(name, None)         # Python stand-ins below (externals are consulted after module procs)
+            ctx = CPtr(core._ctx.value if hasattr(core._ctx, "value") else int(core._ctx))
+            I.set("lesgo_gpu_mod", "gpu_ctx", ctx)
+            core._ctx_ptr = lambda: ctx
+            self.ctx = ctx
 
-        def gpu_check(fr, a):
-            rc, where = _vals(a)[:2]
-            if int(rc) != 0:
-                raise lesgo_b200.LibraryError(f"{where}: {core.lib.error(core._ctx)}")
+            def gpu_check(fr, a):
+                rc, where = _vals(a)[:2]
+                if int(rc) != 0:
+                    raise lesgo_b200.LibraryError(f"{where}: {lib.error(C.c_void_p(ctx.addr))}")
 
-        ext["gpu_require"] = lambda fr, a: None
-        ext["gpu_pin"] = lambda fr, a: None
-        ext["gpu_pin_sim_param"] = lambda fr, a: None
-        ext["gpu_check"] = gpu_check
+            ext["gpu_require"] = lambda fr, a: None
+            ext["gpu_pin"] = lambda fr, a: None
+            ext["gpu_pin_sim_param"] = lambda fr, a: None
+            ext["gpu_check"] = gpu_check
+        else:
+            # the shims' own start-up path: gpu_require -> lesgo_gpu_create(lesgo_gpu_dims(...), gpu_ctx)
+            I.set("lesgo_gpu_mod", "gpu_ctx", CPtr(0))
+            td = mod.types["lesgo_gpu_dims"]
+
+            def dims_constructor(fr, a):
+                o = F.FStruct(td)
+                for name, v in zip(td.members, _vals(a)):
+                    setattr(o, name, v)
+                return o
+
+            def create(fr, a):
+                d = _vals(a)[0]
+                st = L.DimsStruct()
+                for fname, ftype in L.DimsStruct._fields_:
+                    setattr(st, fname, float(getattr(d, fname.lower())) if ftype is C.c_double else int(getattr(d, fname.lower())))
+                out = C.c_void_p()
+                rc = int(lib.create(C.byref(st), C.byref(out)))
+                self.ctx = CPtr(out.value or 0)
+                I.set("lesgo_gpu_mod", "gpu_ctx", self.ctx)
+                self.calls["lesgo_gpu_create"] = self.calls.get("lesgo_gpu_create", 0) + 1
+                return rc
+
+            def out_int(value):
+                def f(fr, a):
+                    a[-2][1](value)               # (..., result, ierr): the result is the last argument but one
+                return f
+            ext["lesgo_gpu_dims"] = dims_constructor
+            ext["mpi_comm_split_type"] = out_int(1)
+            ext["mpi_comm_rank"] = out_int(self.p.coord)      # all ranks of a test share one node: local rank = coord
+            ext["mpi_comm_free"] = lambda fr, a: None
+            # collectives gpu_require uses on byte buffers and flags, over the mailboxes of refrun.run_ranks
+            import queue
+            me, nproc, boxes = self.p.coord, self.p.nproc, self.boxes
+
+            def box(src, dst, tag):
+                with boxes["lock"]:
+                    return boxes.setdefault((src, dst, tag), queue.Queue())
+
+            def bcast(fr, a):
+                buf, count, root = a[0][0], int(a[1][0]), int(a[3][0])
+                flat = buf.a.reshape(-1, order="F")
+                if me == root:
+                    for r in range(nproc):
+                        if r != me:
+                            box(me, r, "bcast").put(np.array(flat[:count], copy=True))
+                else:
+                    flat[:count] = box(root, me, "bcast").get(timeout=refrun.MPI_TIMEOUT)
+
+            def allgather(fr, a):
+                send, scount, recv = a[0][0], int(a[1][0]), a[3][0]
+                mine = np.array(send.a.reshape(-1, order="F")[:scount], copy=True)
+                for r in range(nproc):
+                    if r != me:
+                        box(me, r, "allgather").put(mine)
+                out = recv.a.reshape(-1, order="F")
+                for r in range(nproc):
+                    out[r * scount:(r + 1) * scount] = mine if r == me else box(r, me, "allgather").get(timeout=refrun.MPI_TIMEOUT)
+
+            def allreduce_min_int(fr, a):
+                # gpu_require only reduces its 0 / 1 success flags with MPI_MIN
+                mine = int(a[0][0])
+                for r in range(nproc):
+                    if r != me:
+                        box(me, r, "flag").put(mine)
+                acc = mine
+                for r in range(nproc):
+                    if r != me:
+                        acc = min(acc, box(r, me, "flag").get(timeout=refrun.MPI_TIMEOUT))
+                a[1][1](acc)
+            if nproc > 1:
+                ext["mpi_bcast"] = bcast
+                ext["mpi_allgather"] = allgather
+                self._flag_allreduce = allreduce_min_int
         ext["c_associated"] = lambda fr, a: _vals(a)[0].addr != 0
         ext["c_loc"] = lambda fr, a: CPtr(_addr_of(_vals(a)[0]))
 
@@ -135,7 +219,7 @@ class ShimmedReference(refrun.Reference):
 
         def c_function(cname):
             restype, argtypes = L.SYMBOLS[cname]
-            fn = getattr(core.lib.dll, cname)
+            fn = getattr(lib.dll, cname)
             fn.restype, fn.argtypes = restype, argtypes
 
             def call(fr, a):
@@ -165,7 +249,7 @@ class ShimmedReference(refrun.Reference):
                             setattr(st, fname, (float(val) if ftype is C.c_double else int(val)) if val is not None else 0)
                         cargs.append(C.byref(st))
                         continue
-                    if t in (C.c_int, C.c_long, C.c_longlong):
+                    if t in (C.c_int, C.c_long, C.c_longlong, C.c_size_t, C.c_ulong, C.c_ulonglong, C.c_uint):
                         cargs.append(int(v))
                     elif t is C.c_double:
                         cargs.append(float(v))
@@ -177,4 +261,14 @@ class ShimmedReference(refrun.Reference):
 
         for cname in L.SYMBOLS:
             ext[cname] = c_function(cname)
+        if core is None:
+            ext["lesgo_gpu_create"] = create
+            if self.p.nproc > 1:
+                base_allreduce = ext["mpi_allreduce"]
+
+                def allreduce(fr, a):
+                    if not isinstance(a[0][0], F.FArray) and a[4][0] == 3:      # MPI_MIN of module mpi above
+                        return self._flag_allreduce(fr, a)
+                    return base_allreduce(fr, a)
+                ext["mpi_allreduce"] = allreduce
         ext["press_raw"] = ext["lesgo_gpu_press_stag_array"]      # the local interface name of fortran/press_stag_array.f90

@@ -19,6 +19,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 pytestmark = pytest.mark.skipif(not refrun.available() or shutil.which("g++") is None,
                                 reason="needs the reference sources under /root/reference and g++ for the emulator")
 FIELDS = ("u", "v", "w", "p", "RHSx", "RHSy", "RHSz")
+refrun.MPI_TIMEOUT = min(refrun.MPI_TIMEOUT, 120.0)     # a rank that fails must not keep its peers waiting for ten minutes
 
 
 def shimmed(p, **kw):
@@ -214,3 +215,83 @@ def test_fortran_wind_farm_hand_over(fixture):
     for name in FIELDS:
         hi = p.nz + 1 if name in ("w", "RHSz", "p") else p.nz
         assert rel(core.download(name)[1:hi, :, :p.nx], d[f"{name}_{n}"][1:hi, :, :p.nx]) <= 1e-12, name
+
+
+def test_the_shims_own_start_up():
+    """Nothing pre-made: init_fft of fortran/fft.f90 calls gpu_require, which builds lesgo_gpu_dims with a structure
+    constructor from module param and calls lesgo_gpu_create; gpu_pin_sim_param page-locks the twenty sim_param arrays;
+    gpu_check is the Fortran one.  One core step afterwards equals the all-reference run."""
+    import ctypes as C
+    from shim_driver import ShimmedReference
+    d, meta = load("ref_core_couette_32x32x8")
+    p = O.Params(**meta["params"])
+    lib = emul_library()
+    R = ShimmedReference(p, core=None, lib=lib)
+    try:
+        assert R.ctx is not None and R.ctx.addr != 0
+        assert R.calls["lesgo_gpu_create"] == 1 and R.calls["lesgo_gpu_host_register"] == 20, R.calls
+        for n in ("u", "v", "w"):
+            R.put(n, d[n + "0"])
+        R.step(1, mode="core")
+        assert R.calls["lesgo_gpu_create"] == 1          # c_associated(gpu_ctx): created once
+        for n in FIELDS:
+            hi = p.nz + 1 if n in ("w", "RHSz", "p") else p.nz
+            assert rel(R.get(n)[1:hi, :, :p.nx], d[f"{n}_1"][1:hi, :, :p.nx]) <= 1e-13, n
+    finally:
+        if R.ctx is not None and R.ctx.addr:
+            lib.destroy(C.c_void_p(R.ctx.addr))
+
+
+def test_four_mpi_ranks_over_the_shims():
+    """`mpirun -np 4` in miniature: four interpreted ranks of the reference (its own mpi_sync_real_array halos over the
+    interpreter's mailboxes) with the shims' own multi-rank start-up -- gpu_require makes the transport id on coord 0,
+    MPI_Bcasts it, initialises the library's communicator, exports / all-gathers / imports the peer-memory blobs with the
+    all-reduced success flags -- and the library's slab <-> pencil pressure solve in place of the pipelined tridag_array:
+    two full steps, gathered, vs the reference's own four-rank run."""
+    import ctypes as C
+    import threading
+    from shim_driver import ShimmedReference
+    d = np.load(os.path.join(GOLD, "ref_mpi4_full_16x16x8.npz"))
+    meta = ast.literal_eval(str(d["meta"]))
+    kw, nproc, nsteps = meta["kw"], meta["nproc"], meta["nsteps"]
+    pg = O.Params(nproc=1, **kw)
+    ug, vg, wg = O.synthetic_global(pg.nx, pg.ny, pg.Nz, nproc=nproc, seed=meta["seed"], amp=meta["amp"], L_x=pg.L_x, L_y=pg.L_y, L_z=pg.L_z)
+    lib = emul_library()
+    boxes = {"lock": threading.Lock()}
+    res, err, refs = [None] * nproc, [None] * nproc, [None] * nproc
+
+    def work(r):
+        try:
+            p = O.Params(nproc=nproc, coord=r, **kw)
+            R = refs[r] = ShimmedReference(p, core=None, lib=lib, boxes=boxes)
+            for n, g in (("u", ug), ("v", vg), ("w", wg)):
+                R.put(n, O.scatter_slab(g, p))
+            for it in range(1, nsteps + 1):
+                R.step(it, mode=meta["mode"])
+            res[r] = {n: R.get(n) for n in FIELDS}
+        except BaseException as e:  # noqa
+            err[r] = e
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(nproc)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    try:
+        real = [e for e in err if e is not None and type(e).__name__ != "Empty"]
+        if real:
+            raise real[0]
+        assert not any(err), err
+        for r in range(nproc):
+            c = refs[r].calls
+            assert c["lesgo_gpu_comm_init"] == 1 and c["lesgo_gpu_comm_p2p_export"] == 1 and c["lesgo_gpu_comm_p2p_import"] == 1, c
+            assert c.get("lesgo_gpu_comm_unique_id", 0) == (1 if r == 0 else 0), c
+            assert c["lesgo_gpu_press_stag_array"] == nsteps
+        ps = [O.Params(nproc=nproc, coord=r, **kw) for r in range(nproc)]
+        for n in FIELDS:
+            top = n in ("w", "RHSz", "p")
+            g = O.gather_slabs([res[r][n] for r in range(nproc)], ps, top_extra=top)
+            hi = pg.nz_tot if top else pg.nz_tot - 1
+            assert rel(g[1:hi + 1, :, :pg.nx], d[n][1:hi + 1, :, :pg.nx]) <= 1e-12, n
+    finally:
+        for R in refs:
+            if R is not None and R.ctx is not None and R.ctx.addr:
+                lib.destroy(C.c_void_p(R.ctx.addr))

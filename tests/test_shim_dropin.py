@@ -295,3 +295,28 @@ def test_four_mpi_ranks_over_the_shims():
         for R in refs:
             if R is not None and R.ctx is not None and R.ctx.addr:
                 lib.destroy(C.c_void_p(R.ctx.addr))
+
+
+def test_padd_unpadd_shims_against_the_reference_routines():
+    """padd / unpadd of fortran/fft.f90 (one plane, explicit-shape dummies) vs the reference's own fft.f90:43-99, both
+    interpreted in this process on the same random plane."""
+    from oracle import f90exec as F
+    from helpers import random_field
+    p = O.Params(nx=16, ny=16, Nz=4, L_x=4.0, L_y=3.0)
+    ref = refrun.Reference(p)
+    shim = shimmed(p)
+    rng = np.random.default_rng(11)
+    small = rng.standard_normal((p.ny, p.ld))
+    small[:, p.ld - 2:] = 0.0
+    big = rng.standard_normal((p.ny2, p.ld_big))
+    fa = lambda x: F.FArray(np.asfortranarray(x.T.copy()), (1, 1))
+    out = {}
+    for tag, R in (("ref", ref), ("shim", shim)):
+        ub, u = fa(np.zeros((p.ny2, p.ld_big))), fa(small)
+        R.I.call("padd", ub, u, module="fft")
+        cc, cb = fa(np.zeros((p.ny, p.ld))), fa(big)
+        R.I.call("unpadd", cc, cb, module="fft")
+        out[tag] = (ub.a.T.copy(), cc.a.T.copy())
+    assert shim.calls.get("lesgo_gpu_padd") == 1 and shim.calls.get("lesgo_gpu_unpadd") == 1
+    assert np.count_nonzero(out["ref"][0]) > 50 and np.array_equal(out["shim"][0], out["ref"][0])
+    assert np.array_equal(out["shim"][1][:, :p.ld - 2], out["ref"][1][:, :p.ld - 2])

@@ -320,3 +320,73 @@ def test_padd_unpadd_shims_against_the_reference_routines():
     assert shim.calls.get("lesgo_gpu_padd") == 1 and shim.calls.get("lesgo_gpu_unpadd") == 1
     assert np.count_nonzero(out["ref"][0]) > 50 and np.array_equal(out["shim"][0], out["ref"][0])
     assert np.array_equal(out["shim"][1][:, :p.ld - 2], out["ref"][1][:, :p.ld - 2])
+
+
+def test_gpu_test_filter_wrapper_against_the_reference_test_filter():
+    """gpu_test_filter(f, G_test) / (f, G_test_test) of fortran/lesgo_gpu_mod.f90 -- the one-line bodies of test_filter and
+    test_test_filter -- vs the reference's own routines (test_filtermodule.f90:126-168) on the same plane, with the
+    reference's own kernels, for the three filter types."""
+    from oracle import f90exec as F
+    from helpers import random_field
+    for ifilter in (1, 2, 3):
+        p = O.Params(nx=16, ny=32, Nz=4, L_x=4.0, L_y=3.0, sgs=True, sgs_model=5, ifilter=ifilter)
+        R = shimmed(p, files=refrun.LASD_FILES)
+        I = R.I
+        f = random_field(p, 7)[2]
+        for kernel, routine in (("g_test", "test_filter"), ("g_test_test", "test_test_filter")):
+            a = F.FArray(np.asfortranarray(f.T.copy()), (1, 1))
+            I.call(routine, a, module="test_filtermodule")                    # the reference's body (FFTW -> pocketfft)
+            b = F.FArray(np.asfortranarray(f.T.copy()), (1, 1))
+            I.call("gpu_test_filter", b, I.get("test_filtermodule", kernel), module="lesgo_gpu_mod")
+            assert rel(b.a.T[:, :p.nx], a.a.T[:, :p.nx]) <= 1e-14, (ifilter, routine)
+        assert R.calls.get("lesgo_gpu_test_filter") == 2
+
+
+def test_gpu_sync_real_array_wrapper_on_two_ranks():
+    """gpu_sync_real_array(var, isync) of fortran/lesgo_gpu_mod.f90 over the library's transport vs the reference's
+    mpi_sync_real_array (mpi_defs.f90:167-264) over the interpreter's MPI, on two ranks, for DOWN, UP and DOWNUP."""
+    import ctypes as C
+    import threading
+    from oracle import f90exec as F
+    from shim_driver import ShimmedReference
+    kw = dict(nx=16, ny=16, Nz=8, L_x=4.0, L_y=3.0)
+    nproc = 2
+    lib = emul_library()
+    boxes = {"lock": threading.Lock()}
+    err, refs, out = [None] * nproc, [None] * nproc, [None] * nproc
+
+    def work(r):
+        try:
+            p = O.Params(nproc=nproc, coord=r, **kw)
+            R = refs[r] = ShimmedReference(p, core=None, lib=lib, boxes=boxes)
+            I = R.I
+            got = {}
+            for isync in (1, 2, 3):
+                base = np.arange((p.nz + 1) * p.ny * p.ld, dtype=np.float64).reshape(p.nz + 1, p.ny, p.ld) + 1000.0 * r
+                a = F.FArray(np.asfortranarray(base.transpose(2, 1, 0).copy()), (1, 1, 0))
+                I.call("mpi_sync_real_array", a, 0, isync, module="mpi_defs")
+                b = F.FArray(np.asfortranarray(base.transpose(2, 1, 0).copy()), (1, 1, 0))
+                I.call("gpu_sync_real_array", b, isync, module="lesgo_gpu_mod")
+                got[isync] = (a.a.copy(), b.a.copy())
+            out[r] = got
+        except BaseException as e:  # noqa
+            err[r] = e
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(nproc)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    try:
+        real = [e for e in err if e is not None and type(e).__name__ != "Empty"]
+        if real:
+            raise real[0]
+        assert not any(err), err
+        for r in range(nproc):
+            for isync, (a, b) in out[r].items():
+                assert np.array_equal(a, b), (r, isync)
+            assert refs[r].calls.get("lesgo_gpu_sync_real_array") == 3
+        # and the halos really moved: plane nz of rank 0 is plane 1 of rank 1 after SYNC_DOWN
+        assert np.array_equal(out[0][1][1][:, :, -1], out[1][1][1][:, :, 1])
+    finally:
+        for R in refs:
+            if R is not None and R.ctx is not None and R.ctx.addr:
+                lib.destroy(C.c_void_p(R.ctx.addr))

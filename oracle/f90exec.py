@@ -584,6 +584,7 @@ class Interpreter:
         self.alloc_fill = alloc_fill
         self.trace = False
         self.nstmt = 0
+        self.written = []             # the item lists of executed `write` statements (last 200), as text
 
     # ---- loading -----------------------------------------------------------------------------
     def load(self, path):
@@ -913,6 +914,19 @@ class Interpreter:
             return (s.split()[0], loc), i + 1
         if re.match(r"^stop\b", s):
             return ("stop", loc, s), i + 1
+        if re.match(r"^write\s*\(", s):
+            # write (unit, fmt) items: no file I/O is modelled, but what a routine WOULD print is kept (Interpreter.written)
+            try:
+                depth, k = 0, s.index("(")
+                for j in range(k, len(s)):
+                    depth += s[j] == "("
+                    depth -= s[j] == ")"
+                    if depth == 0:
+                        break
+                items = [parse_expr(x.strip()) for x in _split_top(s[j + 1:]) if x.strip()]
+                return ("write", loc, items), i + 1
+            except Exception:
+                return None, i + 1
         if re.match(r"^(write|print|flush|format|\d+\s+format|open|close)\b", s):
             return None, i + 1
         if re.match(r"^(read|rewind|inquire|backspace)\b", s):
@@ -1772,6 +1786,12 @@ class Frame:
                     self.store(st[2][1], val)
                 else:
                     setattr(self.eval_object(st[2][1]), st[2][2], val)
+            elif t == "write":
+                try:
+                    self.I.written.append(" ".join(str(self.eval(x)) for x in st[2]))
+                    del self.I.written[:-200]
+                except Exception:
+                    pass                         # an item this subset cannot evaluate: output is not part of any check
             elif t == "deallocate":
                 for name in st[2]:
                     self.store(name, None)
@@ -1830,6 +1850,15 @@ class Frame:
             return
         if lhs[0] == "call" and lhs[1][0] == "name":
             base = self.lookup(lhs[1][1])
+            if isinstance(base, str) and len(lhs[2]) == 1 and lhs[2][0][0] == "range":
+                # substring assignment to a character variable: text(lo:hi) = value
+                lo, hi, _ = self.subscript(lhs[2][0])
+                lo = 1 if lo is None else lo
+                hi = max(len(base), lo) if hi is None else hi
+                piece = str(val)[:hi - lo + 1].ljust(hi - lo + 1)
+                padded = base.ljust(hi)
+                self.store(lhs[1][1], padded[:lo - 1] + piece + padded[hi:])
+                return
             if not isinstance(base, FArray):
                 raise FortranError(f"{lhs[1][1]} is not an (allocated) array")
             subs = [self.subscript(a) for a in lhs[2]]

@@ -114,7 +114,7 @@ class ShimmedReference(refrun.Reference):
         I, core, lib = self.I, self.core, self.lib
         mod = I.modules["lesgo_gpu_mod"]
         I.set("iso_c_binding", "c_null_ptr", CPtr(0))
-        I.set("iso_c_binding", "c_null_char", "\\0")
+        I.set("iso_c_binding", "c_null_char", "\x00")
         ext = I.externals
         if core is not None:
             for name in ("gpu_require", "gpu_check", "gpu_pin", "gpu_pin_sim_param"):
@@ -210,6 +210,21 @@ class ShimmedReference(refrun.Reference):
         ext["c_associated"] = lambda fr, a: _vals(a)[0].addr != 0
         ext["c_loc"] = lambda fr, a: CPtr(_addr_of(_vals(a)[0]))
 
+        def c_f_pointer(fr, a):
+            # call c_f_pointer(cptr, fptr, shape) for a character(kind=c_char) pointer array: the C string, NUL padded
+            n = int(np.asarray(getattr(a[2][0], "a", a[2][0])).reshape(-1)[0])
+            raw = C.string_at(a[0][0].addr)[:n]
+            chars = np.empty(n, dtype=object)
+            for i in range(n):
+                chars[i] = chr(raw[i]) if i < len(raw) else "\x00"
+            a[1][1](F.FArray(chars, (1,), "object"))
+        ext["c_f_pointer"] = c_f_pointer
+
+        def last_error(fr, a):
+            fn = lib.dll.lesgo_gpu_last_error
+            fn.restype, fn.argtypes = C.c_void_p, [C.c_void_p]
+            return CPtr(fn(C.c_void_p(_vals(a)[0].addr)) or 0)
+
         def transfer(fr, a):
             src, mold = _vals(a)[:2]
             if isinstance(mold, CPtr):
@@ -241,6 +256,11 @@ class ShimmedReference(refrun.Reference):
                         _KEEP.append(arr)
                         cargs.append(arr if t is not C.c_void_p else C.cast(arr, C.c_void_p))   # ctypes converts the array
                         continue
+                    if isinstance(v, str):           # trim(name) // c_null_char: a NUL-terminated C string
+                        buf = C.create_string_buffer(v.split("\x00")[0].encode())
+                        _KEEP.append(buf)
+                        cargs.append(C.cast(buf, C.c_void_p) if t is C.c_void_p else buf.value)
+                        continue
                     if isinstance(v, F.FStruct):     # a bind(C) derived type, passed by reference: member by member
                         cls = {"lesgo_gpu_step_params": L.StepParams, "lesgo_gpu_dims": L.DimsStruct}[v._type.name.lower()]
                         st = cls()
@@ -261,6 +281,7 @@ class ShimmedReference(refrun.Reference):
 
         for cname in L.SYMBOLS:
             ext[cname] = c_function(cname)
+        ext["lesgo_gpu_last_error"] = last_error
         if core is None:
             ext["lesgo_gpu_create"] = create
             if self.p.nproc > 1:

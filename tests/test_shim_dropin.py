@@ -390,3 +390,50 @@ def test_gpu_sync_real_array_wrapper_on_two_ranks():
         for R in refs:
             if R is not None and R.ctx is not None and R.ctx.addr:
                 lib.destroy(C.c_void_p(R.ctx.addr))
+
+
+def test_gpu_checkpoint_wrapper(tmp_path):
+    """gpu_checkpoint(fname, writing) of fortran/lesgo_gpu_resident_mod.f90: the file name goes over as
+    trim(fname) // c_null_char; the restart record it writes is the oracle writer's byte for byte (io.f90:1204-1211), and
+    reading it back through the wrapper restores the resident fields."""
+    from helpers import random_field
+    p = O.Params(nx=16, ny=16, Nz=6)
+    R = shimmed(p, resident=True)
+    core = R.core
+    s = O.State(p)
+    O.lasd_alloc(s)
+    for i, n in enumerate(O.CHECKPOINT_FIELDS):
+        getattr(s, n)[...] = random_field(p, 300 + i)
+        core.upload(n, getattr(s, n))
+    f1, f2 = str(tmp_path / "vel.out.c0"), str(tmp_path / "vel.oracle.c0")
+    R.I.call("gpu_checkpoint", f1 + "   ", True, module="lesgo_gpu_resident_mod")       # trailing blanks as a character(*) has
+    O.checkpoint_write(s, p, f2)
+    assert open(f1, "rb").read() == open(f2, "rb").read()
+    for n in O.CHECKPOINT_FIELDS:
+        core.upload(n, np.zeros(core.dims.shape))
+    R.I.call("gpu_checkpoint", f2, False, module="lesgo_gpu_resident_mod")
+    for n in O.CHECKPOINT_FIELDS:
+        assert np.array_equal(core.download(n)[1:], getattr(s, n)[1:]), n
+    assert R.calls["lesgo_gpu_checkpoint_write"] == 1 and R.calls["lesgo_gpu_checkpoint_read"] == 1
+
+
+def test_gpu_check_carries_the_library_message_into_the_reference_error_routine():
+    """gpu_check of fortran/lesgo_gpu_mod.f90 on a failing call: it fetches lesgo_gpu_last_error, turns the C string into a
+    Fortran one with c_f_pointer and hands it to the reference's own fatal-error routine (messages.f90)."""
+    import ctypes as C
+    from oracle import f90exec as F
+    from shim_driver import ShimmedReference
+    p = O.Params(nx=16, ny=16, Nz=4)
+    lib = emul_library()
+    R = ShimmedReference(p, core=None, lib=lib)
+    try:
+        plane = np.zeros((p.ny, p.ld))
+        rc = lib.test_filter(C.c_void_p(R.ctx.addr), plane.ctypes.data, plane.ctypes.data, 10 ** 6)
+        assert rc != 0
+        with pytest.raises(F.FStop, match="messages.f90"):                    # the reference's error(): writes, then `stop 1`
+            R.I.call("gpu_check", rc, "test_filter", module="lesgo_gpu_mod")
+        printed = "\n".join(R.I.written[-5:])
+        assert "lesgo_gpu.test_filter" in printed and "at most nz" in printed, printed
+        R.I.call("gpu_check", 0, "anything", module="lesgo_gpu_mod")          # rc = 0 returns quietly
+    finally:
+        lib.destroy(C.c_void_p(R.ctx.addr))

@@ -437,3 +437,23 @@ def test_gpu_check_carries_the_library_message_into_the_reference_error_routine(
         R.I.call("gpu_check", 0, "anything", module="lesgo_gpu_mod")          # rc = 0 returns quietly
     finally:
         lib.destroy(C.c_void_p(R.ctx.addr))
+
+
+def test_reference_lagrangian_model_over_the_fortran_shims():
+    """The same with sgs_model 5: lagrange_Sdep, interpolag_Sdep, test_filter ... stay the reference's Fortran (its FFTW
+    calls answered by the interpreter), the derivative, convective and pressure routines are the shims: four steps with
+    two model updates vs the all-reference fixture, model state included."""
+    d, meta = load("ref_full_lasd_16x16x6")
+    p = O.Params(**meta["params"])
+    R = shimmed(p, files=refrun.LASD_FILES, dyn_init=meta["dyn_init"], cs_count=meta["cs_count"])
+    for n in ("u", "v", "w"):
+        R.put(n, d[n + "0"])
+    for it in range(1, max(meta["record"]) + 1):
+        R.step(it, mode="full")
+        if it in meta["record"]:
+            for n in FIELDS:
+                hi = p.nz + 1 if n in ("w", "RHSz", "p") else p.nz
+                assert rel(R.get(n)[1:hi, :, :p.nx], d[f"{n}_{it}"][1:hi, :, :p.nx]) <= 1e-12, (n, it)
+            for n in ("F_LM", "F_MM", "F_QN", "F_NN", "Cs_opt2"):
+                g = R.get(n.lower(), module="sgs_param")
+                assert rel(g[1:p.nz + 1, :, :p.nx], d[f"{n}_{it}"][1:p.nz + 1, :, :p.nx]) <= (1e-10 if n == "Cs_opt2" else 1e-12), (n, it)

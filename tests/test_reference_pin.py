@@ -731,11 +731,12 @@ def test_oracle_rmsdiv_matches_reference_mpi_run():
     kw, nproc = meta["kw"], meta["nproc"]
     ref = float(d["rms_rank0"])
     assert ref > 0.1
+    g0 = [d[n] for n in ("ug", "vg", "wg")]        # read here: an NpzFile must not be read from several threads at once
 
     def run(p, comm):
         sp = O.Spectral(p)
         s = O.State(p)
-        s.u, s.v, s.w = (O.scatter_slab(d[n], p) for n in ("ug", "vg", "wg"))
+        s.u, s.v, s.w = (O.scatter_slab(g, p) for g in g0)
         O.step(s, sp, comm, mode="core", first_step=True)
         return O.rmsdiv(s, p, comm)
 
